@@ -1,0 +1,100 @@
+"""ctypes binding of libfithic_b200.so (include/fithic_b200.h).
+
+The library is the only compute path: if it is missing or fails to load this module raises -- there is no CPU or
+PyTorch fallback.  PyTorch tensors are used purely as device buffers (data_ptr()) and for the CUDA stream handle.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
+
+FHC_OK = 0
+FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
+FHC_ABI_VERSION = 1
+(S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
+ S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
+N_SCALARS = 8
+MODE_INTRA_ONLY, MODE_INTER_ONLY, MODE_ALL = 0, 1, 2
+
+
+class FithicB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libfithic_b200: %s (code %d)" % (message, code))
+        self.code = code
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "fhc_abi_version": (ctypes.c_int, []),
+    "fhc_last_error": (c_char_p, []),
+    "fhc_launch_count": (c_int64, []),
+    "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                          c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_host_make_bins": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "fhc_host_frag_pairs": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
+                                            c_int32, c_void_p, c_void_p, c_void_p]),
+    "fhc_spline_workspace_bytes": (c_size_t, [c_int64]),
+    "fhc_spline_table": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_double, c_double, c_int32,
+                                         c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "fhc_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_void_p]),
+    "fhc_host_log_cr": (c_double, [c_double]),
+    "fhc_host_lbeta": (c_double, [c_double, c_double]),
+    "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                    c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fhc_bdtrc": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),
+    "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
+    "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
+                                           c_void_p]),
+    "fhc_outlier_bin_decrements": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
+                                                   c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libfithic_b200.so, bind every symbol of include/fithic_b200.h, check the ABI version."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "fithic_b200: %s is missing -- build it with `python -m fithic_b200.build` (needs nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fhc_abi_version() != FHC_ABI_VERSION:
+        raise ImportError("fithic_b200: ABI version mismatch (library %d, binding %d)" %
+                          (lib.fhc_abi_version(), FHC_ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Turn a negative status code into an exception carrying fhc_last_error()."""
+    if rc < 0:
+        raise FithicB200Error(rc, load().fhc_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def launch_count():
+    return int(load().fhc_launch_count())
+
+
+def dptr(t):
+    """Device (or host numpy) pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return c_void_p(t.data_ptr())
+    return c_void_p(t.ctypes.data)

@@ -1,0 +1,535 @@
+// K4 -- q-values: compaction, 64-bit LSD radix sort with index payload, forward prefix-MAX scan, scatter.
+//
+// Replaces myStats.benjamini_hochberg_correction (reference fithic/myStats.py:24-48).  The reference walks the p-values
+// in ascending order and keeps a FORWARD running MAX of min(1, p*T/rank) (not the textbook backward-min BH);
+// p == 1.0 short-circuits to 1.0 and NaN sorts last and stays NaN, so only p < 1 needs ranking.
+//
+//   bh_compact_kernel   p -> (order-preserving uint64 key, line index) for p < 1; q = 1 / NaN written directly
+//   radix sort          8 passes of 8 bits: per-tile digit histogram, exclusive scan, stable rank + scatter
+//                       (warp-level match_any ranking, tile reordered in shared memory so global writes are runs)
+//   bh_tilemax/bh_scan  bh_j = min((p_j*T)/rank_j, 1) with IEEE mul/div in the reference's order (bit exact), running
+//                       max as a two-level scan (tile maxima, then warp-shuffle scans inside the tile), q[line] = value
+//
+// Every kernel reads the number of sorted elements from device memory, so the whole K4 is enqueued without a host sync.
+// HBM-bound: 16 algorithmic bytes per contact (read p, write q); the LSD passes move (8+12+12) B per element per pass.
+#include "common.cuh"
+
+namespace fhc {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortIPT = 16;
+constexpr int kSortTile = kSortThreads * kSortIPT;  // 4096 keys per CTA
+constexpr int kRadix = 256;
+constexpr int kScanThreads = 1024;
+constexpr int kScanTile = kScanThreads * 4;
+constexpr size_t kDownsweepSmem = kSortTile * (sizeof(unsigned long long) + sizeof(unsigned int)) +
+                                  (kSortWarps * kRadix + 2 * kRadix + 36) * sizeof(unsigned int);
+
+__device__ __forceinline__ u64 key_of(double p) {  // order preserving for every non-NaN double
+    const u64 b = (u64)__double_as_longlong(p);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double p_of(u64 k) {
+    const u64 b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// compaction
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n, double *__restrict__ q,
+                                                        u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel) {
+    __shared__ u32 warp_cnt[8];
+    __shared__ u64 block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = (long long)blockIdx.x * 256; base < n; base += (long long)gridDim.x * 256) {
+        const long long i = base + threadIdx.x;
+        double v = 0.0;
+        bool sel = false;
+        if (i < n) {
+            v = __ldcs(p + i);
+            if (v == 1.0)
+                q[i] = 1.0;  // fithic/myStats.py:32-33
+            else if (isnan(v))
+                q[i] = v;  // min(nan, 1) -> nan, max(nan, prev) -> nan; NaNs sort last so nothing follows them
+            else
+                sel = true;
+        }
+        const u32 m = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const u32 c = warp_cnt[w];
+                warp_cnt[w] = tot;
+                tot += c;
+            }
+            block_base = tot ? atomicAdd(nsel, (u64)tot) : 0;
+        }
+        __syncthreads();
+        if (sel) {
+            const u64 dst = block_base + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+            keys[dst] = key_of(v);
+            vals[dst] = (u32)i;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// exclusive scan of a uint32 array (three phases)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 block_exclusive_scan_u32(u32 v, u32 *smem_warp /*32*/, u32 &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < nw ? smem_warp[lane] : 0;
+        u32 winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem_warp[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = winc;
+    }
+    __syncthreads();
+    const u32 r = smem_warp[warp] + inc - v;
+    total = smem_warp[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const u32 *__restrict__ data, long long len,
+                                                                  u32 *__restrict__ blocksums) {
+    __shared__ u32 sw[33];
+    const long long i0 = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * 4;
+    u32 s = 0;
+    if (i0 + 3 < len) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(data + i0);
+        s = v.x + v.y + v.z + v.w;
+    } else {
+        for (long long i = i0; i < len; ++i) s += data[i];
+    }
+    u32 total;
+    block_exclusive_scan_u32(s, sw, total);
+    if (threadIdx.x == 0) blocksums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(u32 *blocksums, int nb) {
+    __shared__ u32 sw[33];
+    __shared__ u32 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += kScanThreads) {
+        const int i = base + threadIdx.x;
+        const u32 v = i < nb ? blocksums[i] : 0;
+        u32 total;
+        const u32 ex = block_exclusive_scan_u32(v, sw, total);
+        if (i < nb) blocksums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(u32 *__restrict__ data, long long len,
+                                                                 const u32 *__restrict__ blocksums) {
+    __shared__ u32 sw[33];
+    const long long i0 = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * 4;
+    u32 a = 0, b = 0, c = 0, d = 0;
+    const bool full = i0 + 3 < len;
+    if (full) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(data + i0);
+        a = v.x; b = v.y; c = v.z; d = v.w;
+    } else {
+        if (i0 < len) a = data[i0];
+        if (i0 + 1 < len) b = data[i0 + 1];
+        if (i0 + 2 < len) c = data[i0 + 2];
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan_u32(a + b + c + d, sw, total) + blocksums[blockIdx.x];
+    const uint4 o = make_uint4(ex, ex + a, ex + a + b, ex + a + b + c);
+    if (full) {
+        *reinterpret_cast<uint4 *>(data + i0) = o;
+    } else {
+        if (i0 < len) data[i0] = o.x;
+        if (i0 + 1 < len) data[i0 + 1] = o.y;
+        if (i0 + 2 < len) data[i0 + 2] = o.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// radix sort passes
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const u64 *__restrict__ keys, const u64 *d_n,
+                                                                    int shift, u32 *__restrict__ counts, u32 ntiles) {
+    __shared__ u32 hist[kSortWarps][kRadix];
+    const long long n = (long long)*d_n;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kSortTile;
+    if (base < n) {
+#pragma unroll
+        for (int r = 0; r < kSortIPT; ++r) {
+            const long long i = base + r * kSortThreads + threadIdx.x;
+            if (i < n) atomicAdd(&hist[warp][(u32)(keys[i] >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) s += hist[w][threadIdx.x];
+    counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = s;  // digit-major so one flat scan gives global offsets
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u64 *__restrict__ keys_out,
+                       u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ offsets,
+                       u32 ntiles) {
+    extern __shared__ __align__(16) unsigned char dsmem[];
+    u64 *skeys = reinterpret_cast<u64 *>(dsmem);                                  // [kSortTile]
+    u32 *svals = reinterpret_cast<u32 *>(skeys + kSortTile);                      // [kSortTile]
+    u32(*whist)[kRadix] = reinterpret_cast<u32(*)[kRadix]>(svals + kSortTile);    // [kSortWarps][kRadix]
+    u32 *tile_off = reinterpret_cast<u32 *>(whist + kSortWarps);                  // [kRadix]
+    u32 *gbase = tile_off + kRadix;                                               // [kRadix]
+    u32 *sw = gbase + kRadix;                                                     // [33]
+    const long long n = (long long)*d_n;
+    const long long base = (long long)blockIdx.x * kSortTile;
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_n = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
+    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
+    __syncthreads();
+
+    u64 key[kSortIPT];
+    unsigned short rank[kSortIPT];
+    const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kSortIPT; ++r) {  // warp `warp` owns [warp*512, warp*512+512) of the tile, 32 at a time
+        const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        const bool valid = li < tile_n;
+        key[r] = valid ? keys_in[base + li] : ~0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortIPT; ++r) {
+        const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        const bool valid = li < tile_n;
+        const u32 d = valid ? ((u32)(key[r] >> shift) & 255u) : 256u;
+        const u32 m = __match_any_sync(0xffffffffu, d);
+        u32 pre = 0;
+        if (valid) pre = whist[warp][d];
+        __syncwarp();
+        if (valid && lane == (__ffs(m) - 1)) whist[warp][d] = pre + __popc(m);
+        __syncwarp();
+        rank[r] = (unsigned short)(pre + __popc(m & lt));
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, tile total
+    u32 cnt = 0;
+    {
+        const int d = threadIdx.x;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const u32 c = whist[w][d];
+            whist[w][d] = cnt;
+            cnt += c;
+        }
+    }
+    u32 total;
+    const u32 ex = block_exclusive_scan_u32(cnt, sw, total);
+    tile_off[threadIdx.x] = ex;
+    gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * ntiles + blockIdx.x];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortIPT; ++r) {
+        const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        if (li < tile_n) {
+            const u32 d = (u32)(key[r] >> shift) & 255u;
+            const u32 pos = tile_off[d] + whist[warp][d] + rank[r];
+            skeys[pos] = key[r];
+            svals[pos] = vals_in[base + li];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortIPT; ++r) {
+        const int i = r * kSortThreads + threadIdx.x;
+        if (i < tile_n) {
+            const u64 k = skeys[i];
+            const u32 d = (u32)(k >> shift) & 255u;
+            const u32 dst = gbase[d] + ((u32)i - tile_off[d]);
+            keys_out[dst] = k;
+            vals_out[dst] = svals[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// running max of min((p*T)/rank, 1) over the sorted keys and scatter
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bh_value(u64 key, double T, long long rank) {
+    // bh = pv * T / (i + 1); bh = min(bh, 1)   (fithic/myStats.py:35-37, evaluated left to right)
+    const double v = __ddiv_rn(__dmul_rn(p_of(key), T), (double)rank);
+    return v > 1.0 ? 1.0 : v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) bh_tilemax_kernel(const u64 *__restrict__ keys, const u64 *d_n, double T,
+                                                                 long long rank_offset, double *__restrict__ tilemax) {
+    __shared__ double sm[kSortWarps];
+    const long long n = (long long)*d_n;
+    const long long base = (long long)blockIdx.x * kSortTile;
+    double m = 0.0;
+    if (base < n) {
+#pragma unroll 4
+        for (int r = 0; r < kSortIPT; ++r) {
+            const long long i = base + r * kSortThreads + threadIdx.x;
+            if (i < n) m = fmax(m, bh_value(keys[i], T, rank_offset + i + 1));
+        }
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sm[0];
+#pragma unroll
+        for (int w = 1; w < kSortWarps; ++w) t = fmax(t, sm[w]);
+        tilemax[blockIdx.x] = t;
+    }
+}
+
+// exclusive running max over the tile maxima, seeded with carry_in (single CTA)
+__global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilemax, int ntiles, double carry_in,
+                                                                  double *carry_out, const u64 *d_n, u64 *n_sorted_out) {
+    __shared__ double sw[32];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = carry_in;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < ntiles; base += kScanThreads) {
+        const int i = base + threadIdx.x;
+        const double v = i < ntiles ? tilemax[i] : 0.0;
+        double inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = fmax(inc, t);
+        }
+        double exl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exl = 0.0;
+        if (lane == 31) sw[warp] = inc;
+        __syncthreads();
+        double wpre = 0.0;
+        for (int w = 0; w < warp; ++w) wpre = fmax(wpre, sw[w]);
+        const double c = carry;
+        if (i < ntiles) tilemax[i] = fmax(c, fmax(wpre, exl));
+        __syncthreads();
+        if (threadIdx.x == kScanThreads - 1) carry = fmax(c, fmax(wpre, inc));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (carry_out) *carry_out = carry;
+        if (n_sorted_out) *n_sorted_out = *d_n;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, const u64 *d_n, double T,
+                  long long rank_offset, const double *__restrict__ tilepre, double *__restrict__ q) {
+    __shared__ double sw[kSortWarps];
+    const long long n = (long long)*d_n;
+    const long long base = (long long)blockIdx.x * kSortTile;
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double carry = tilepre[blockIdx.x];
+    for (int r = 0; r < kSortIPT; ++r) {
+        const long long i = base + r * kSortThreads + threadIdx.x;
+        const bool valid = i < n;
+        double inc = valid ? bh_value(keys[i], T, rank_offset + i + 1) : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = fmax(inc, t);
+        }
+        if (lane == 31) sw[warp] = inc;
+        __syncthreads();
+        double wpre = carry;
+        double all = carry;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const double s = sw[w];
+            if (w < warp) wpre = fmax(wpre, s);
+            all = fmax(all, s);
+        }
+        if (valid) q[vals[i]] = fmax(inc, wpre);  // bh = max(bh, prev)   (fithic/myStats.py:43)
+        carry = all;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+struct SortWs {
+    u32 *counts;
+    u32 *blocksums;
+    size_t counts_len;
+    int nb;
+    u32 ntiles;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
+    const u32 ntiles = (u32)((n + kSortTile - 1) / kSortTile);
+    const size_t counts_len = (size_t)kRadix * (ntiles ? ntiles : 1);
+    const int nb = (int)((counts_len + kScanTile - 1) / kScanTile);
+    size_t off = 0;
+    if (ws) ws->counts = reinterpret_cast<u32 *>(base + off);
+    off += align_up(counts_len * sizeof(u32) + 16);
+    if (ws) ws->blocksums = reinterpret_cast<u32 *>(base + off);
+    off += align_up((size_t)nb * sizeof(u32));
+    if (ws) {
+        ws->counts_len = counts_len;
+        ws->nb = nb;
+        ws->ntiles = ntiles ? ntiles : 1;
+    }
+    return off;
+}
+
+// sorts n_max-capacity buffers holding *d_n valid pairs; result ends in (keys_b, vals_b) after 8 passes -> we run an
+// even number of passes so the result is back in (keys_a, vals_a)
+static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_b, int64_t n_max, const u64 *d_n,
+                               const SortWs &ws, cudaStream_t st) {
+    u64 *kin = keys_a, *kout = keys_b;
+    u32 *vin = vals_a, *vout = vals_b;
+    FHC_CUDA(cudaFuncSetAttribute(radix_downsweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kDownsweepSmem));
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        radix_upsweep_kernel<<<ws.ntiles, kSortThreads, 0, st>>>(kin, d_n, shift, ws.counts, ws.ntiles);
+        FHC_LAUNCH_CHECK("radix_upsweep_kernel");
+        scan_reduce_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, (long long)ws.counts_len, ws.blocksums);
+        FHC_LAUNCH_CHECK("scan_reduce_kernel");
+        scan_blocksums_kernel<<<1, kScanThreads, 0, st>>>(ws.blocksums, ws.nb);
+        FHC_LAUNCH_CHECK("scan_blocksums_kernel");
+        scan_apply_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, (long long)ws.counts_len, ws.blocksums);
+        FHC_LAUNCH_CHECK("scan_apply_kernel");
+        radix_downsweep_kernel<<<ws.ntiles, kSortThreads, kDownsweepSmem, st>>>(kin, vin, kout, vout, d_n, shift, ws.counts, ws.ntiles);
+        FHC_LAUNCH_CHECK("radix_downsweep_kernel");
+        u64 *tk = kin; kin = kout; kout = tk;
+        u32 *tv = vin; vin = vout; vout = tv;
+    }
+    (void)n_max;
+    return FHC_OK;
+}
+
+}  // namespace fhc
+
+extern "C" size_t fhc_sort_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return fhc::sort_ws_layout(n, nullptr, nullptr) + 256 /* device copy of n */;
+}
+
+extern "C" int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out, uint32_t *vals_out,
+                                  int64_t n, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32), FHC_E_INVALID, "fhc_sort_pairs_u64: need 0 <= n < 2^32 (got %lld)", (long long)n);
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(keys_in && vals_in && keys_out && vals_out && workspace, FHC_E_INVALID, "fhc_sort_pairs_u64: null pointer");
+    FHC_REQUIRE(workspace_bytes >= fhc_sort_workspace_bytes(n), FHC_E_WORKSPACE,
+                "fhc_sort_pairs_u64: workspace of %zu bytes, need %zu", workspace_bytes, fhc_sort_workspace_bytes(n));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *base = reinterpret_cast<char *>(workspace);
+    u64 *d_n = reinterpret_cast<u64 *>(base);
+    SortWs ws;
+    sort_ws_layout(n, base + 256, &ws);
+    const u64 hn = (u64)n;
+    FHC_CUDA(cudaMemcpyAsync(d_n, &hn, sizeof(u64), cudaMemcpyHostToDevice, st));
+    const int rc = sort_pairs_device_n(reinterpret_cast<u64 *>(keys_in), vals_in, reinterpret_cast<u64 *>(keys_out),
+                                       vals_out, n, d_n, ws, st);
+    if (rc != FHC_OK) return rc;
+    // 8 passes: the result is back in keys_in / vals_in; move it where the caller asked for it
+    FHC_CUDA(cudaMemcpyAsync(keys_out, keys_in, sizeof(u64) * n, cudaMemcpyDeviceToDevice, st));
+    FHC_CUDA(cudaMemcpyAsync(vals_out, vals_in, sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+    return FHC_OK;
+}
+
+namespace fhc {
+struct BhWs {
+    u64 *d_n;
+    u64 *keys_a, *keys_b;
+    u32 *vals_a, *vals_b;
+    double *tilemax;
+    SortWs sort;
+};
+static size_t bh_ws_layout(int64_t n, char *base, BhWs *ws) {
+    size_t off = 0;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    const size_t ntiles = (nn + kSortTile - 1) / kSortTile;
+    if (ws) ws->d_n = reinterpret_cast<u64 *>(base + off);
+    off += 256;
+    if (ws) ws->keys_a = reinterpret_cast<u64 *>(base + off);
+    off += align_up(nn * sizeof(u64));
+    if (ws) ws->keys_b = reinterpret_cast<u64 *>(base + off);
+    off += align_up(nn * sizeof(u64));
+    if (ws) ws->vals_a = reinterpret_cast<u32 *>(base + off);
+    off += align_up(nn * sizeof(u32));
+    if (ws) ws->vals_b = reinterpret_cast<u32 *>(base + off);
+    off += align_up(nn * sizeof(u32));
+    if (ws) ws->tilemax = reinterpret_cast<double *>(base + off);
+    off += align_up(ntiles * sizeof(double));
+    off += sort_ws_layout(n, base + off, ws ? &ws->sort : nullptr);
+    return off;
+}
+}  // namespace fhc
+
+extern "C" size_t fhc_bh_workspace_bytes(int64_t n) { return fhc::bh_ws_layout(n, nullptr, nullptr); }
+
+extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                              double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32), FHC_E_INVALID, "fhc_bh_qvalues: need 0 <= n < 2^32 (got %lld)", (long long)n);
+    FHC_REQUIRE(workspace != nullptr, FHC_E_INVALID, "fhc_bh_qvalues: null workspace");
+    FHC_REQUIRE(workspace_bytes >= fhc_bh_workspace_bytes(n), FHC_E_WORKSPACE,
+                "fhc_bh_qvalues: workspace of %zu bytes, need %zu", workspace_bytes, fhc_bh_workspace_bytes(n));
+    FHC_REQUIRE(n == 0 || (p && q && p != q), FHC_E_INVALID, "fhc_bh_qvalues: p and q must be distinct non-null arrays");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BhWs ws;
+    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
+    FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, sizeof(u64), st));
+    const int ntiles = (int)ws.sort.ntiles;
+    if (n > 0) {
+        long long blocks = (n + 255) / 256;
+        if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
+        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, q, ws.keys_a, ws.vals_a, ws.d_n);
+        FHC_LAUNCH_CHECK("bh_compact_kernel");
+        const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st);
+        if (rc != FHC_OK) return rc;
+        bh_tilemax_kernel<<<ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
+        FHC_LAUNCH_CHECK("bh_tilemax_kernel");
+    }
+    bh_tilescan_kernel<<<1, kScanThreads, 0, st>>>(ws.tilemax, n > 0 ? ntiles : 0, carry_in, carry_out, ws.d_n,
+                                                   reinterpret_cast<u64 *>(n_sorted_out));
+    FHC_LAUNCH_CHECK("bh_tilescan_kernel");
+    if (n > 0) {
+        bh_scatter_kernel<<<ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset, ws.tilemax, q);
+        FHC_LAUNCH_CHECK("bh_scatter_kernel");
+    }
+    return FHC_OK;
+}

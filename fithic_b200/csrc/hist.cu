@@ -1,0 +1,187 @@
+// K1 -- distance histogram + observed totals.
+//
+// Replaces the accumulation loop of read_Interactions (reference fithic/fithic.py:406-441) and the classification of
+// myUtils.Interaction.getType (fithic/myUtils.py:135-148).
+//
+// Design (B200): HBM-bound streaming pass, 16 algorithmic bytes per contact (4 x int32 SoA, 128-bit loads, 4 contacts
+// per thread per tile).  One persistent 1024-thread CTA per SM keeps a private uint32 histogram of the whole distance
+// axis in shared memory (D <= 53,248 slots = 208 KB covers 5 kb whole-genome: chr1 = 49,792 slots), so the hot
+// short-distance slots never leave the SM; the CTA flushes to the global uint64 histogram every 2^20 contacts (bounds
+// every 32-bit partial sum below 2^32 because only counts < 4096 take the shared path) and at the end.  Totals are kept
+// in registers and reduced warp -> CTA -> one global atomic per CTA.
+#include "common.cuh"
+
+namespace fhc {
+
+constexpr int kHistThreads = 1024;
+constexpr int kHistPairsPerTile = kHistThreads * 4;
+constexpr int kHistSmemSlotsMax = 53248;    // 208 KB of uint32 slots (227 KB usable per CTA)
+constexpr int kHistSmallCount = 4096;       // counts below this go through shared memory
+constexpr int kHistFlushTiles = 256;        // 256 tiles x 4096 contacts x 4095 < 2^32
+
+struct HistAcc {
+    unsigned long long inrange_sum = 0, intra_sum = 0, inter_sum = 0;
+    unsigned int inter_n = 0, inrange_n = 0, intra_n = 0, offgrid = 0;
+    int maxc = 0;
+};
+
+__device__ __forceinline__ void hist_one(int m1, int m2, int c, unsigned int ch, bool skipped, long long Llo,
+                                         long long Uhi, unsigned int res, long long D, int S, unsigned int *sh,
+                                         unsigned long long *hist, unsigned int *present, HistAcc &a) {
+    a.maxc = max(a.maxc, c);
+    if (skipped) return;
+    const long long cs = c;
+    if ((ch & 0xffffu) != (ch >> 16)) {  // inter (fithic/fithic.py:420-422)
+        a.inter_sum += (unsigned long long)cs;
+        a.inter_n += 1;
+        return;
+    }
+    a.intra_sum += (unsigned long long)cs;  // any type of intra (:423-425)
+    a.intra_n += 1;
+    long long d = (long long)m1 - (long long)m2;
+    d = d < 0 ? -d : d;
+    if (d < Llo || d > Uhi) return;  // intraShort / intraLong
+    a.inrange_sum += (unsigned long long)cs;  // :439
+    a.inrange_n += 1;
+    const unsigned int du = (unsigned int)d;  // d < 2^32 always (int32 mids)
+    const unsigned int slot = du / res;
+    if (slot * res != du || (long long)slot >= D) {
+        a.offgrid += 1;
+        return;
+    }
+    if (c > 0 && c < kHistSmallCount && slot < (unsigned int)S) {
+        atomicAdd(&sh[slot], (unsigned int)c);
+    } else {
+        if (c != 0) atomicAdd(&hist[slot], (unsigned long long)cs);
+        if (c <= 0) atomicOr(&present[slot >> 5], 1u << (slot & 31));
+    }
+}
+
+__device__ __forceinline__ void hist_flush(unsigned int *sh, int S, unsigned long long *hist) {
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += kHistThreads) {
+        const unsigned int v = sh[s];
+        if (v) {
+            atomicAdd(&hist[s], (unsigned long long)v);
+            sh[s] = 0;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid2, const int4 *__restrict__ cnt,
+                     const int4 *__restrict__ chrs, const unsigned int *__restrict__ skip, long long skip_limit,
+                     long long n, long long Llo, long long Uhi, unsigned int res, unsigned long long *hist,
+                     unsigned int *present, long long D, int S, unsigned long long *scalars) {
+    extern __shared__ unsigned int sh[];
+    __shared__ unsigned long long red[FHC_N_SCALARS];
+    for (int s = threadIdx.x; s < S; s += kHistThreads) sh[s] = 0;
+    if (threadIdx.x < FHC_N_SCALARS) red[threadIdx.x] = 0;
+    __syncthreads();
+
+    HistAcc a;
+    const long long ntiles = n / kHistPairsPerTile;  // full tiles; the tail is handled below
+    int since_flush = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long g = t * kHistThreads + threadIdx.x;  // index of this thread's group of 4 contacts
+        const int4 a1 = ldg_stream(mid1 + g), a2 = ldg_stream(mid2 + g), ac = ldg_stream(cnt + g);
+        const int4 ah = ldg_stream(chrs + g);
+        unsigned int sk = 0;
+        const long long i0 = g * 4;
+        if (skip != nullptr) {
+            sk = __ldg(skip + g);
+            // a line is dropped when flagged and not past the reference's stalled pointer (:408-412)
+            if (i0 + 0 > skip_limit) sk &= ~0x000000ffu;
+            if (i0 + 1 > skip_limit) sk &= ~0x0000ff00u;
+            if (i0 + 2 > skip_limit) sk &= ~0x00ff0000u;
+            if (i0 + 3 > skip_limit) sk &= ~0xff000000u;
+        }
+        hist_one(a1.x, a2.x, ac.x, (unsigned int)ah.x, (sk & 0x000000ffu) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
+        hist_one(a1.y, a2.y, ac.y, (unsigned int)ah.y, (sk & 0x0000ff00u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
+        hist_one(a1.z, a2.z, ac.z, (unsigned int)ah.z, (sk & 0x00ff0000u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
+        hist_one(a1.w, a2.w, ac.w, (unsigned int)ah.w, (sk & 0xff000000u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
+        if (++since_flush == kHistFlushTiles) {
+            hist_flush(sh, S, hist);
+            since_flush = 0;
+        }
+    }
+    // tail: fewer than one tile of contacts, scalar loads, spread over the first CTA
+    if (blockIdx.x == 0) {
+        const int *m1 = reinterpret_cast<const int *>(mid1), *m2 = reinterpret_cast<const int *>(mid2);
+        const int *cc = reinterpret_cast<const int *>(cnt);
+        const unsigned int *hh = reinterpret_cast<const unsigned int *>(chrs);
+        const unsigned char *sb = reinterpret_cast<const unsigned char *>(skip);
+        for (long long i = ntiles * kHistPairsPerTile + threadIdx.x; i < n; i += kHistThreads) {
+            const bool skipped = sb != nullptr && sb[i] != 0 && i <= skip_limit;
+            hist_one(m1[i], m2[i], cc[i], hh[i], skipped, Llo, Uhi, res, D, S, sh, hist, present, a);
+        }
+    }
+    hist_flush(sh, S, hist);
+
+    // totals: warp shuffle -> shared atomics -> one global atomic per CTA and scalar
+    unsigned long long v[FHC_N_SCALARS];
+    v[FHC_S_INTRA_INRANGE_SUM] = warp_sum(a.inrange_sum);
+    v[FHC_S_INTRA_ALL_SUM] = warp_sum(a.intra_sum);
+    v[FHC_S_INTER_ALL_SUM] = warp_sum(a.inter_sum);
+    v[FHC_S_INTER_ALL_COUNT] = warp_sum((unsigned long long)a.inter_n);
+    v[FHC_S_OFFGRID] = warp_sum((unsigned long long)a.offgrid);
+    v[FHC_S_INTRA_INRANGE_LINES] = warp_sum((unsigned long long)a.inrange_n);
+    v[FHC_S_INTRA_ALL_LINES] = warp_sum((unsigned long long)a.intra_n);
+    int mc = a.maxc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < FHC_N_SCALARS; ++k)
+            if (k != FHC_S_MAX_COUNT && v[k]) atomicAdd(&red[k], v[k]);
+        atomicMax(&red[FHC_S_MAX_COUNT], (unsigned long long)mc);
+    }
+    __syncthreads();
+    if (threadIdx.x < FHC_N_SCALARS) {
+        const unsigned long long r = red[threadIdx.x];
+        if (threadIdx.x == FHC_S_MAX_COUNT)
+            atomicMax(&scalars[threadIdx.x], r);
+        else if (r)
+            atomicAdd(&scalars[threadIdx.x], r);
+    }
+}
+
+}  // namespace fhc
+
+extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
+                                 const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
+                                 uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && D > 0 && res > 0, FHC_E_INVALID, "fhc_hist_distance: need n >= 0, D > 0, res > 0 (got %lld, %lld, %d)",
+                (long long)n, (long long)D, res);
+    FHC_REQUIRE(hist && present && scalars, FHC_E_INVALID, "fhc_hist_distance: null output pointer");
+    FHC_REQUIRE(n == 0 || (mid1 && mid2 && cnt && chrs), FHC_E_INVALID, "fhc_hist_distance: null input pointer");
+    FHC_REQUIRE(aligned16(mid1) && aligned16(mid2) && aligned16(cnt) && aligned16(chrs) && aligned16(skip), FHC_E_INVALID,
+                "fhc_hist_distance: input arrays must be 16-byte aligned");
+    FHC_REQUIRE(L >= -1 && U >= -1, FHC_E_INVALID, "fhc_hist_distance: L and U must be >= -1");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * D, st));
+    FHC_CUDA(cudaMemsetAsync(present, 0, sizeof(uint32_t) * ((D + 31) / 32), st));
+    FHC_CUDA(cudaMemsetAsync(scalars, 0, sizeof(uint64_t) * FHC_N_SCALARS, st));
+    if (n == 0) return FHC_OK;
+    const int S = (int)(D < kHistSmemSlotsMax ? D : kHistSmemSlotsMax);
+    const size_t smem = sizeof(unsigned int) * (size_t)S;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHC_CUDA(cudaFuncSetAttribute(hist_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned int) * kHistSmemSlotsMax)));
+        attr_set = true;
+    }
+    const long long ntiles = n / kHistPairsPerTile;
+    int grid = (int)(ntiles < kNumSMs ? (ntiles > 0 ? ntiles : 1) : kNumSMs);
+    const long long Llo = L < 0 ? 0 : L;
+    const long long Uhi = U < 0 ? INT64_MAX : U;
+    hist_distance_kernel<<<grid, kHistThreads, smem, st>>>(
+        reinterpret_cast<const int4 *>(mid1), reinterpret_cast<const int4 *>(mid2), reinterpret_cast<const int4 *>(cnt),
+        reinterpret_cast<const int4 *>(chrs), reinterpret_cast<const unsigned int *>(skip), skip_limit, n, Llo, Uhi,
+        (unsigned int)res, reinterpret_cast<unsigned long long *>(hist), present, D, S,
+        reinterpret_cast<unsigned long long *>(scalars));
+    FHC_LAUNCH_CHECK("hist_distance_kernel");
+    return FHC_OK;
+}

@@ -1,0 +1,107 @@
+// Host-side O(D) bookkeeping between K1 and K2: equal-occupancy binning and possible-pair counts.
+//
+// These two stages are sequential scans over at most D (~5e4) distances / sum(chromosome bins) (~6e5) slots with
+// order-dependent integer and double accumulations; they run on the host between two kernels and must be bit exact,
+// so they are plain C++ mirroring the reference's evaluation order:
+//   fhc_host_make_bins   <- makeBinsFromInteractions   (reference fithic/fithic.py:463-553)
+//   fhc_host_frag_pairs  <- generate_FragPairs, fixed-size branch (fithic/fithic.py:596-689)
+#include <vector>
+
+#include "common.cuh"
+
+extern "C" int fhc_host_make_bins(const int64_t *dists, const int64_t *sums, int64_t m, int32_t noOfBins, int64_t N,
+                                  int64_t *bin_lb, int64_t *bin_ub, int64_t *bin_sumcc) {
+    FHC_REQUIRE(m >= 0 && noOfBins > 0, FHC_E_INVALID, "fhc_host_make_bins: need m >= 0 and noOfBins > 0");
+    FHC_REQUIRE(m == 0 || (dists && sums), FHC_E_INVALID, "fhc_host_make_bins: null input");
+    FHC_REQUIRE(bin_lb && bin_ub && bin_sumcc, FHC_E_INVALID, "fhc_host_make_bins: null output");
+    // desiredPerBin = observedIntraInRangeSum / noOfBins  (true division, :476)
+    double desired = (double)N / (double)noOfBins;
+    int64_t total = 0;     // interactionTotalForBinTermination (:479)
+    int64_t acc = 0;       // currentBinContactCount
+    int64_t binsum = 0;    // sum of counts of the distances gathered in the open bin
+    int64_t prev_ub = -1;  // last distance of the previous closed bin
+    int nb = 0;            // closed bins
+
+    for (int64_t i = 0; i < m; ++i) {
+        const int64_t cc = sums[i];
+        total += cc;
+        bool full;
+        // Python compares int with float exactly; both sides are < 2^53 here so the double compare is exact too
+        if ((double)cc >= desired) {
+            full = true;  // :481
+        } else if ((double)(acc + cc) >= desired) {
+            full = true;  // :486
+        } else {
+            full = false;
+            acc += cc;  // :493
+        }
+        binsum += cc;
+
+        if (full) {
+            if (nb >= noOfBins) {
+                // cannot happen for consistent input (sum of sums == N); refuse rather than write out of bounds
+                fhc::set_error("fhc_host_make_bins: more than noOfBins=%d bins closed", noOfBins);
+                return FHC_E_RANGE;
+            }
+            bin_lb[nb] = nb == 0 ? 0 : prev_ub + 1;  // :518-521
+            bin_ub[nb] = dists[i];
+            bin_sumcc[nb] = binsum;
+            prev_ub = dists[i];
+            nb += 1;
+            if (nb < noOfBins) desired = 1.0 * (double)(N - total) / (double)(noOfBins - nb);  // :500-502
+            acc = 0;
+            binsum = 0;
+
+        }
+    }
+    // distances after the last closed bin are dropped, as in the reference
+    return nb;
+}
+
+extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxmid, int32_t nchr, int32_t res, int64_t L,
+                                   int64_t U, const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins,
+                                   int64_t *bin_pairs, double *bin_sumdist, int64_t *totals) {
+    FHC_REQUIRE(nchr >= 0 && res > 0 && nbins >= 0, FHC_E_INVALID, "fhc_host_frag_pairs: bad nchr / res / nbins");
+    FHC_REQUIRE(totals != nullptr, FHC_E_INVALID, "fhc_host_frag_pairs: null totals");
+    FHC_REQUIRE(nbins == 0 || (bin_lb && bin_ub && bin_pairs && bin_sumdist), FHC_E_INVALID,
+                "fhc_host_frag_pairs: null bin arrays");
+    int64_t noOfFrags = 0;
+    for (int c = 0; c < nchr; ++c) noOfFrags += chr_n[c];  // first loop of the reference (:596-604)
+    int64_t inrange = 0, interpairs2 = 0, intraall2 = 0;
+    for (int c = 0; c < nchr; ++c) {  // caller passes chromosomes in sorted-name order (:606)
+        const int64_t n = chr_n[c];
+        if (n <= 0) continue;
+        const double maxFrag = (double)chr_maxmid[c] - (double)res / 2.0;  // :602
+        const int64_t stop = (int64_t)(maxFrag + 1.0);                     // int(maxFrags[ch]+1), truncation
+        int64_t d = 0, perchr = 0;
+        int tr = 0;
+        for (int64_t dist = 0; dist < stop; dist += res) {  // range(0, stop, res) (:613)
+            const int64_t npairs = n - d;                   // may go negative when loci are unmappable
+            d += 1;
+            const bool lo_ok = (L == -1) || (L > -1 && dist >= L);  // myUtils.in_range_check
+            const bool hi_ok = (U == -1) || (U > -1 && dist <= U);
+            if (!(lo_ok && hi_ok)) continue;
+            perchr += npairs;  // :618
+            if (nbins > 0) {
+                while (!(bin_lb[tr] <= dist && dist <= bin_ub[tr])) {  // forward tracker, clamp to the last bin (:627-638)
+                    tr += 1;
+                    if (tr >= nbins) {
+                        tr -= 1;
+                        break;
+                    }
+                }
+                bin_pairs[tr] += npairs;                                             // [7] and [1] (:639-640)
+                bin_sumdist[tr] += ((double)dist / 1000000.0) * (double)npairs;      // :641
+                perchr += npairs;                                                    // :642 (the x2 of SURVEY F4)
+            }
+        }
+        interpairs2 += n * (noOfFrags - n);  // :645
+        intraall2 += n * (n + 1);            // :647 (x2)
+        inrange += perchr;
+    }
+    totals[0] = inrange;
+    totals[1] = intraall2;
+    totals[2] = interpairs2;
+    totals[3] = noOfFrags;
+    return FHC_OK;
+}

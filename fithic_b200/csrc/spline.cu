@@ -1,0 +1,213 @@
+// K2 -- spline table: FITPACK splev (de Boor) at the observed distances, antitonic regression (PAVA), dense lookup table.
+//
+// Replaces `splineY = ius(splineX)` and `IsotonicRegression(increasing=False).fit_transform(splineX, splineY)` of
+// fit_Spline (reference fithic/fithic.py:952-966; scipy FITPACK splev/fpbspl and scipy.optimize.isotonic_regression are
+// third party) and bakes the clamp + bisect of the per-contact lookup (:1066-1068) into a table indexed by distance slot.
+//
+// Latency-bound (m <= D <= ~50k points), one CTA:
+//   1. splev: one thread per point, same operation order as fpbspl/splev, round-to-nearest without contraction -> bit
+//      exact against FITPACK.
+//   2. PAVA as a merge tree: 1024 threads pool adjacent violators inside their own contiguous chunk, then log2(1024)
+//      rounds merge neighbouring chunks by cascading only across the shared boundary.  Blocks live in three arrays
+//      (sum at block start, end-of-block at block start, start-of-block at block end), so a pool is O(1) and nothing
+//      is compacted.  Pooling adjacent violators in any order gives the unique antitonic least-squares fit.
+//   3. a second kernel fills lut[k] for every distance slot.
+#include "common.cuh"
+
+namespace fhc {
+
+constexpr int kPavaThreads = 1024;
+
+// FITPACK splev for k = 3 at one abscissa.  t[0..nt), c[0..nt) (zero padded), x inside [t[3], t[nt-4]].
+__device__ double splev3(const double *__restrict__ t, const double *__restrict__ c, int nt, double x) {
+    // interval: largest l in [3, nt-5] with t[l] <= x  (splev.f: "search for knot interval t(l) <= arg < t(l+1)")
+    int lo = 3, hi = nt - 5;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t[mid] <= x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const int l = lo;
+    double h[4] = {1.0, 0.0, 0.0, 0.0}, hh[3];
+    for (int j = 1; j <= 3; ++j) {  // fpbspl.f
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+        for (int i = 0; i < j; ++i) {
+            const int li = l + 1 + i, lj = li - j;
+            if (t[li] == t[lj]) {
+                h[i + 1] = 0.0;
+            } else {
+                const double f = __ddiv_rn(hh[i], __dsub_rn(t[li], t[lj]));
+                h[i] = __dadd_rn(h[i], __dmul_rn(f, __dsub_rn(t[li], x)));
+                h[i + 1] = __dmul_rn(f, __dsub_rn(x, t[lj]));
+            }
+        }
+    }
+    double sp = 0.0;
+    for (int j = 0; j < 4; ++j) sp = __dadd_rn(sp, __dmul_rn(c[l - 3 + j], h[j]));
+    return sp;
+}
+
+// true when block A (sum sa over na points) followed by block B violates "non-increasing": mean(A) < mean(B)
+__device__ __forceinline__ bool violates(double sa, long long na, double sb, long long nb) {
+    return sa * (double)nb < sb * (double)na;
+}
+
+__global__ void __launch_bounds__(kPavaThreads, 1)
+spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, int nt,
+                   const long long *__restrict__ splineX, long long m, double *__restrict__ table, double *sum,
+                   int *endOf, int *startOf) {
+    // ---- 1. splev ----
+    for (long long i = threadIdx.x; i < m; i += kPavaThreads) {
+        sum[i] = splev3(t, c, nt, (double)splineX[i]);
+    }
+    __syncthreads();
+    // ---- 2a. PAVA inside each chunk ----
+    const long long chunk = (m + kPavaThreads - 1) / kPavaThreads;
+    {
+        const long long lo = (long long)threadIdx.x * chunk;
+        const long long hi = lo + chunk < m ? lo + chunk : m;
+        if (lo < hi) {
+            endOf[lo] = (int)lo;
+            startOf[lo] = (int)lo;
+            for (long long i = lo + 1; i < hi; ++i) {
+                long long s = i;
+                double sm = sum[i];
+                while (s > lo) {
+                    const long long ps = startOf[s - 1];
+                    const double psum = sum[ps];
+                    if (!violates(psum, s - ps, sm, i - s + 1)) break;
+                    endOf[s] = -1;  // s stops being a block start
+                    sm += psum;
+                    s = ps;
+                }
+                sum[s] = sm;
+                endOf[s] = (int)i;
+                startOf[i] = (int)s;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 2b. merge tree across chunk boundaries ----
+    for (long long seg = chunk; seg < m; seg <<= 1) {
+        const long long b = (2ll * threadIdx.x + 1) * seg;  // first index of the right segment
+        if (b < m) {
+            const long long lo = b - seg;
+            const long long hi = b + seg < m ? b + seg : m;
+            long long cs = startOf[b - 1], ce = endOf[b];
+            double s_left = sum[cs], s_right = sum[b];
+            if (violates(s_left, b - cs, s_right, ce - b + 1)) {
+                double sm = s_left + s_right;
+                endOf[b] = -1;
+                bool changed = true;
+                while (changed) {
+                    changed = false;
+                    if (cs > lo) {
+                        const long long ps = startOf[cs - 1];
+                        const double psum = sum[ps];
+                        if (violates(psum, cs - ps, sm, ce - cs + 1)) {
+                            endOf[cs] = -1;
+                            sm += psum;
+                            cs = ps;
+                            changed = true;
+                        }
+                    }
+                    if (ce + 1 < hi) {
+                        const long long ns = ce + 1, ne = endOf[ns];
+                        const double nsum = sum[ns];
+                        if (violates(sm, ce - cs + 1, nsum, ne - ns + 1)) {
+                            endOf[ns] = -1;
+                            sm += nsum;
+                            ce = ne;
+                            changed = true;
+                        }
+                    }
+                }
+                sum[cs] = sm;
+                endOf[cs] = (int)ce;
+                startOf[ce] = (int)cs;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 2c. block means: propagate the last block start (max-scan over chunks), then fill ----
+    __shared__ long long last_start[kPavaThreads];
+    const long long lo = (long long)threadIdx.x * chunk;
+    const long long hi = lo + chunk < m ? lo + chunk : m;
+    long long mine = -1;
+    for (long long i = lo; i < hi; ++i)
+        if (endOf[i] >= 0) mine = i;
+    last_start[threadIdx.x] = mine;
+    __syncthreads();
+    for (int off = 1; off < kPavaThreads; off <<= 1) {  // inclusive max-scan (Hillis-Steele)
+        long long v = last_start[threadIdx.x];
+        if (threadIdx.x >= off) v = max(v, last_start[threadIdx.x - off]);
+        __syncthreads();
+        last_start[threadIdx.x] = v;
+        __syncthreads();
+    }
+    long long cur = threadIdx.x > 0 ? last_start[threadIdx.x - 1] : -1;
+    double mean = 0.0;
+    if (cur >= 0) mean = __ddiv_rn(sum[cur], (double)(endOf[cur] - cur + 1));
+    for (long long i = lo; i < hi; ++i) {
+        if (endOf[i] >= 0) {
+            cur = i;
+            mean = __ddiv_rn(sum[cur], (double)(endOf[cur] - cur + 1));
+        }
+        table[i] = mean;
+    }
+}
+
+__global__ void spline_lut_kernel(const long long *__restrict__ splineX, const double *__restrict__ table, long long m,
+                                  double xmin, double xmax, unsigned int res, double *__restrict__ lut, long long D) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= D) return;
+    double dl = (double)(k * (long long)res);
+    dl = fmax(dl, xmin);  // distToLookUp = max(d, min(x)); min(., max(x))   (fithic/fithic.py:1066-1067)
+    dl = fmin(dl, xmax);
+    long long lo = 0, hi = m;  // bisect_left: first j with splineX[j] >= dl
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if ((double)splineX[mid] < dl)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo > m - 1) lo = m - 1;
+    lut[k] = table[lo];
+}
+
+}  // namespace fhc
+
+extern "C" size_t fhc_spline_workspace_bytes(int64_t m) {
+    if (m < 0) m = 0;
+    return (size_t)m * (sizeof(double) + 2 * sizeof(int)) + 64;
+}
+
+extern "C" int fhc_spline_table(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m,
+                                double xmin, double xmax, int32_t res, double *table, double *lut, int64_t D,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(t && c && splineX && table && workspace, FHC_E_INVALID, "fhc_spline_table: null pointer");
+    FHC_REQUIRE(nt >= 8, FHC_E_INVALID, "fhc_spline_table: a cubic spline has at least 8 knots (got %d)", nt);
+    FHC_REQUIRE(m > 0 && m < (1ll << 31), FHC_E_INVALID, "fhc_spline_table: need 0 < m < 2^31 (got %lld)", (long long)m);
+    FHC_REQUIRE(res > 0 && D >= 0 && (D == 0 || lut != nullptr), FHC_E_INVALID, "fhc_spline_table: bad res / D / lut");
+    FHC_REQUIRE(workspace_bytes >= fhc_spline_workspace_bytes(m), FHC_E_WORKSPACE,
+                "fhc_spline_table: workspace of %zu bytes, need %zu", workspace_bytes, fhc_spline_workspace_bytes(m));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *sum = reinterpret_cast<double *>(workspace);
+    int *endOf = reinterpret_cast<int *>(sum + m);
+    int *startOf = endOf + m;
+    spline_pava_kernel<<<1, kPavaThreads, 0, st>>>(t, c, nt, reinterpret_cast<const long long *>(splineX), m, table, sum,
+                                                  endOf, startOf);
+    FHC_LAUNCH_CHECK("spline_pava_kernel");
+    if (D > 0) {
+        const int threads = 256;
+        spline_lut_kernel<<<(unsigned int)((D + threads - 1) / threads), threads, 0, st>>>(
+            reinterpret_cast<const long long *>(splineX), table, m, xmin, xmax, (unsigned int)res, lut, D);
+        FHC_LAUNCH_CHECK("spline_lut_kernel");
+    }
+    return FHC_OK;
+}

@@ -1,0 +1,235 @@
+"""`fithic` command line on the B200 path -- same flags, file names and output format as the reference CLI
+(fithic/fithic.py:43-124 parse_args, :129-379 main).
+
+    fithic -i CONTACTS.gz -f FRAGS.gz -o OUTDIR -r RES [-t BIAS.gz] [-p N] [-b N] [-m N] [-l LIB] [-U bp] [-L bp]
+           [-x intraOnly|interOnly|All] [-tL f] [-tU f] [-V]
+
+Differences that are deliberate: `-r 0` (restriction-fragment mode) and `-v` (plots) are outside the accelerated path
+and are refused / ignored with a message; everything numeric is computed on the GPU (no CPU fallback).
+"""
+import argparse
+import gzip
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import __version__
+from . import io as fio
+from .engine import Engine, Settings
+
+
+def parse_args(args):
+    parser = argparse.ArgumentParser(description="Check the help flag")
+    parser.add_argument("-i", "--interactions", dest="intersfile", required=True,
+                        help="REQUIRED: interactions between fragment pairs are read from INTERSFILE")
+    parser.add_argument("-f", "--fragments", dest="fragsfile", required=True,
+                        help="REQUIRED: midpoints (or start indices) of the fragments are read from FRAGSFILE")
+    parser.add_argument("-o", "--outdir", dest="outdir", required=True,
+                        help="REQUIRED: where the output files will be written")
+    parser.add_argument("-r", "--resolution", dest="resolution", type=int, required=True,
+                        help="REQUIRED: resolution of the fixed-size dataset (0 = non fixed size: not supported here)")
+    parser.add_argument("-t", "--biases", dest="biasfile", required=False,
+                        help="RECOMMENDED: biases calculated by ICE or KR norm for each locus are read from BIASFILE")
+    parser.add_argument("-p", "--passes", dest="noOfPasses", type=int, required=False,
+                        help="OPTIONAL: number of spline passes to run. Default is 1")
+    parser.add_argument("-b", "--noOfBins", dest="noOfBins", type=int, required=False,
+                        help="OPTIONAL: number of equal-occupancy (count) bins. Default is 100")
+    parser.add_argument("-m", "--mappabilityThres", dest="mappabilityThreshold", type=int, required=False,
+                        help="OPTIONAL: minimum number of hits per locus that has to exist to call it mappable. "
+                             "DEFAULT is 1.")
+    parser.add_argument("-l", "--lib", dest="libname", required=False,
+                        help="OPTIONAL: Name of the library that is analyzed to be used for name of file prefixes. "
+                             "DEFAULT is FitHiC")
+    parser.add_argument("-U", "--upperbound", dest="distUpThres", type=int, required=False,
+                        help="OPTIONAL: upper bound on the intra-chromosomal distance range (unit: base pairs). "
+                             "DEFAULT no limit.")
+    parser.add_argument("-L", "--lowerbound", dest="distLowThres", type=int, required=False,
+                        help="OPTIONAL: lower bound on the intra-chromosomal distance range (unit: base pairs). "
+                             "DEFAULT no limit.")
+    parser.add_argument("-v", "--visual", action="store_true", dest="visual", required=False,
+                        help="OPTIONAL: plots (not produced by this implementation)")
+    parser.add_argument("-x", "--contactType", dest="contactType", required=False,
+                        help="OPTIONAL: which chromosomal regions to study (intraOnly, interOnly, All). "
+                             "DEFAULT is intraOnly")
+    parser.add_argument("-tL", "--biasLowerBound", dest="biasLowerBound", type=float, required=False,
+                        help="OPTIONAL: lower bound of bias values to discard. DEFAULT is 0.5")
+    parser.add_argument("-tU", "--biasUpperBound", dest="biasUpperBound", type=float, required=False,
+                        help="OPTIONAL: upper bound of bias values to discard. DEFAULT is 2")
+    parser.add_argument("-V", "--version", action="version", version="Fit-Hi-C (fithic_b200) {}".format(__version__),
+                        help="Print version and exit")
+    return parser.parse_args(args)
+
+
+def _is_gz(path):
+    return path.endswith(".gz")
+
+
+def settings_from_args(args):
+    """Validation and defaults of main() (fithic/fithic.py:136-263); exits with status 2 like the reference."""
+    print("\n")
+    print("GIVEN FIT-HI-C ARGUMENTS")
+    print("=========================")
+    for label, path in (("interactions", args.intersfile), ("fragments", args.fragsfile)):
+        if not os.path.exists(path):
+            print("%s file not found" % label.capitalize())
+            sys.exit(2)
+        if not _is_gz(path):
+            print("%s file must be gzipped (.gz)" % label.capitalize())
+            sys.exit(2)
+        print("Reading %s file from: %s" % (label, path))
+    if not os.path.isdir(args.outdir):
+        os.makedirs(args.outdir)
+    print("Output path being used from %s" % args.outdir)
+    if args.resolution == 0:
+        print("Fixed size option: the B200 path only supports fixed-size data (-r > 0); "
+              "restriction-fragment mode (-r 0) is not accelerated")
+        sys.exit(2)
+    if args.resolution < 0:
+        print("Resolution must be a positive integer")
+        sys.exit(2)
+    print("Fixed size data being used with resolution: %s" % args.resolution)
+    if args.biasfile:
+        if not os.path.exists(args.biasfile):
+            print("Bias file not found")
+            sys.exit(2)
+        if not _is_gz(args.biasfile):
+            print("Bias file must be gzipped (.gz)")
+            sys.exit(2)
+        print("Reading bias file from: %s" % args.biasfile)
+    else:
+        print("No bias file")
+    st = Settings(resolution=args.resolution)
+    # the reference's falsy-zero idiom: 0 means "use the default" (fithic/fithic.py:194-220)
+    if args.noOfPasses:
+        st.noOfPasses = args.noOfPasses
+    print("The number of spline passes is %s" % st.noOfPasses)
+    if args.noOfBins:
+        st.noOfBins = args.noOfBins
+    print("The number of bins is %s" % st.noOfBins)
+    if args.mappabilityThreshold:
+        st.mappThres = args.mappabilityThreshold
+    print("The number of reads required to consider an interaction is %s" % st.mappThres)
+    libName = args.libname if args.libname else "FitHiC"
+    print("The name of the library for outputted files will be %s" % libName)
+    if args.distUpThres:
+        st.distUpThres = args.distUpThres
+    if args.distLowThres:
+        st.distLowThres = args.distLowThres
+    print("Upper Distance threshold is %s" % st.distUpThres)
+    print("Lower Distance threshold is %s" % st.distLowThres)
+    if args.visual:
+        print("Graphs are not produced by the B200 path (-v ignored)")
+    region = args.contactType if args.contactType is not None else "intraOnly"
+    if region == "All":
+        print("All genomic regions will be analyzed")
+        st.allReg = True
+    elif region == "interOnly":
+        print("Only inter-chromosomal regions will be analyzed")
+        st.interOnly = True
+    elif region == "intraOnly":
+        print("Only intra-chromosomal regions will be analyzed")
+    else:
+        print("Invalid Option. Only options are 'All', 'interOnly', or 'intraOnly'")
+        sys.exit(2)
+    if args.biasLowerBound:
+        st.biasLowerBound = args.biasLowerBound
+    if args.biasUpperBound:
+        st.biasUpperBound = args.biasUpperBound
+    if st.biasLowerBound > st.biasUpperBound:
+        print("Invalid Option. Bias lower bound is greater than bias upper bound. Please fix.")
+        sys.exit(2)
+    print("Lower bound of bias values is %s" % st.biasLowerBound)
+    print("Upper bound of bias values is %s" % st.biasUpperBound)
+    print("All arguments processed. Running FitHiC now...")
+    print("=========================")
+    print("\n")
+    return st, libName
+
+
+def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=False):
+    """Everything main() does after argument parsing.  Returns the per-pass result dicts (host numpy p/q/expcc)."""
+    import torch
+    say = (lambda *a: None) if quiet else print
+    t0 = time.time()
+    say("Reading the contact counts file to generate bins...")
+    contacts = fio.read_contacts(contacts_path)
+    chroms = list(contacts.chroms)
+    say("Interactions file read. Time took %s" % (time.time() - t0))
+    t1 = time.time()
+    frags = fio.read_fragments(frags_path, chroms, st.mappThres)
+    say("Fragments file read. Time took %s" % (time.time() - t1))
+    biases, bias_log = None, []
+    if bias_path:
+        t1 = time.time()
+        biases, bias_log = fio.read_biases(bias_path, chroms, st.resolution, st.biasLowerBound, st.biasUpperBound)
+        say("Bias file read. Time took %s" % (time.time() - t1))
+    contacts.chroms = chroms
+    logfile = os.path.join(outdir, libName + ".fithic.log")
+
+    eng = Engine(st, frags, biases)
+    eng.upload_contacts(contacts)
+    outl, stats = eng.new_outlier_state()
+    c1 = (contacts.chrs & 0xffff)
+    c2 = (contacts.chrs >> 16)
+    bias1 = fio.lookup_biases(biases, c1, contacts.mid1, st.resolution)
+    bias2 = fio.lookup_biases(biases, c2, contacts.mid2, st.resolution)
+    results = []
+    for passNo in range(1, st.noOfPasses + 1):
+        if passNo > 1 and st.interOnly:
+            say("Extra spline fits will not help with interOnly spline fit... Bypassing option")
+            break
+        ts = time.time()
+        say("Spline fit Pass %s starting..." % passNo)
+        r = eng.run_pass(passNo, outl, stats)
+        torch.cuda.synchronize()
+        p = r["p"].cpu().numpy()
+        q = r["q"].cpu().numpy()
+        e = r["expcc"].cpu().numpy()
+        r.update(p=p, q=q, expcc=e, n_outliers_total=int(stats[0].item()))
+        say("Outlier threshold is... %s" % r["outlierThres"])
+        suffix = ".res" + str(st.resolution)
+        # log (re-opened 'w' in every pass like the reference, fithic/fithic.py:444)
+        with open(logfile, "w") as log:
+            log.write("\n\nInteractions file read successfully\n")
+            log.write("------------------------------------------------------------------------------------\n")
+            log.write("Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" %
+                      (r["observedIntraInRangeLines"], r["N"]))
+            log.write("Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" %
+                      (r["observedIntraAllLines"], r["observedIntraAllSum"]))
+            log.write("Observed, Inter-chr all: pairs= %d\t totalCount= %d\n" %
+                      (r["observedInterAllCount"], r["observedInterAllSum"]))
+            log.write("\nPossible, Intra-chr in range: pairs= %d\n" % r["possibleIntraInRangeCount"])
+            log.write("Possible, Inter-chr all: pairs= %s\n" % r["possibleInterAllCount"])
+            for line in bias_log:
+                log.write(line + "\n")
+            log.write("Spline successfully fit\n\n\n")
+        # bin table
+        tab = os.path.join(outdir, libName + ".fithic_pass" + str(passNo) + suffix + ".txt")
+        say("Writing %s" % tab)
+        with open(tab, "w") as out:
+            out.write("avgGenomicDist\tcontactProbability\tstandardError\tnoOfLocusPairs\ttotalOfContactCounts\n")
+            b = r["bins"]
+            for i in range(b["n"]):
+                out.write("%d\t%.2e\t%.2e\t%d\t%d\n" % (r["x_bins"][i], r["y_bins"][i], 0, b["pairs"][i], b["sumcc"][i]))
+        sig = os.path.join(outdir, libName + ".spline_pass" + str(passNo) + suffix + ".significances.txt.gz")
+        say("Writing p-values and q-values to file %s" % sig[:-3])
+        fio.write_significances(sig, contacts, p, q, e, bias1, bias2, st)
+        say("Number of outliers is... %s" % r["n_outliers_total"])
+        say("Spline fit Pass %s completed. Time took %s" % (passNo, time.time() - ts))
+        results.append(r)
+    say("=========================")
+    say("Fit-Hi-C completed successfully")
+    say("\n")
+    return results
+
+
+def main(argv=None):
+    args = parse_args(sys.argv[1:] if argv is None else argv)
+    st, libName = settings_from_args(args)
+    run(args.intersfile, args.fragsfile, args.outdir, st, libName, args.biasfile)
+
+
+if __name__ == "__main__":
+    main()

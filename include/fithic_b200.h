@@ -1,0 +1,163 @@
+/*
+ * fithic_b200 -- C ABI of the B200-native Fit-Hi-C significance path.
+ *
+ * The reference (ay-lab/fithic) is pure Python and has no FFI seam of its own; the seams it does have are the Python
+ * functions of fithic/fithic.py and fithic/myStats.py.  Each entry point below replaces the per-contact (or per-bin)
+ * loop inside one of those functions, cited as <file>:<lines> relative to the reference root.  The Python host
+ * (fithic_b200/fithic.py) keeps the reference's function names and argument meaning and binds these symbols through
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - every pointer marked [dev] is device memory owned by the caller (16-byte aligned), [host] is host memory.
+ *   - every call returns 0 on success or a negative FHC_E_* code; fhc_last_error() gives the message (thread local).
+ *   - device entry points are asynchronous on `stream`; they allocate nothing except where a *_workspace_bytes
+ *     companion exists, in which case the caller passes the workspace.
+ *   - contacts ("pairs") are a structure of arrays, one element per line of the contact-counts file, in file order:
+ *        mid1[i], mid2[i]  fragment mid points (int32)
+ *        cnt[i]            contact count, already truncated toward zero (fithic/fithic.py:415, myUtils.py:123-124)
+ *        chrs[i]           chromosome ids, chr1 | chr2 << 16 (uint32); intra <=> both halves equal
+ */
+#ifndef FITHIC_B200_H
+#define FITHIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHC_OK 0
+#define FHC_E_INVALID (-1)   /* bad argument (null pointer, misaligned pointer, negative size ...) */
+#define FHC_E_CUDA (-2)      /* a CUDA runtime call or kernel launch failed */
+#define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
+#define FHC_E_WORKSPACE (-4) /* workspace too small */
+
+#define FHC_ABI_VERSION 1
+
+/* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
+#define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
+#define FHC_S_INTRA_ALL_SUM 1     /* observedIntraAllSum      fithic/fithic.py:424 */
+#define FHC_S_INTER_ALL_SUM 2     /* observedInterAllSum      fithic/fithic.py:421 */
+#define FHC_S_INTER_ALL_COUNT 3   /* observedInterAllCount    fithic/fithic.py:422 */
+#define FHC_S_MAX_COUNT 4         /* largest cnt[i] over kept lines (sizes the lbeta table) */
+#define FHC_S_OFFGRID 5           /* in-range intra lines whose distance is not k*res with k < D (must be 0) */
+#define FHC_S_INTRA_INRANGE_LINES 6 /* observedIntraInRangeCount fithic/fithic.py:440 */
+#define FHC_S_INTRA_ALL_LINES 7   /* observedIntraAllCount    fithic/fithic.py:425 */
+#define FHC_N_SCALARS 8
+
+/* fhc_pvalues mode bits (fithic/fithic.py:232-248) */
+#define FHC_MODE_INTRA_ONLY 0
+#define FHC_MODE_INTER_ONLY 1
+#define FHC_MODE_ALL 2
+
+int fhc_abi_version(void);
+const char *fhc_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t fhc_launch_count(void);
+
+/* ---- K1: distance histogram + totals ------------------------------------------------------------------------
+ * Replaces the accumulation loop of read_Interactions (fithic/fithic.py:406-441) with the classification of
+ * myUtils.Interaction.getType (fithic/myUtils.py:135-148).
+ *   hist[k]    += cnt[i] for every kept intra line with L <= d <= U, d = |mid1-mid2| = k*res  (mainDic[d][1])
+ *   present bit k is set when such a line has cnt <= 0 (so "distance seen" survives a zero sum, :434-436)
+ *   skip       nullable per-line outlier multiplicity (pass >= 2, :408-412); line i is dropped when
+ *              skip[i] != 0 and i <= skip_limit (the reference's pointer walk stalls at the first duplicate)
+ *   L, U       distLowThres / distUpThres; -1 = unbounded
+ * hist, present and scalars are zeroed by the callee.  present has (D+31)/32 words. */
+int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
+                      const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
+                      uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, void *stream);
+
+/* ---- host helpers for the O(D) sequential stages (bit-exact integer/float bookkeeping) ------------------------
+ * makeBinsFromInteractions, fithic/fithic.py:463-553.  dists/sums [host]: the m distinct in-range distances
+ * ascending with their count sums.  outl_dec [host, nullable]: not used here (see fhc_host_frag_pairs).
+ * Writes bin_lb/bin_ub/bin_sumcc [host, capacity noOfBins]; returns the number of bins (>= 0) or an error. */
+int fhc_host_make_bins(const int64_t *dists, const int64_t *sums, int64_t m, int32_t noOfBins, int64_t N,
+                       int64_t *bin_lb, int64_t *bin_ub, int64_t *bin_sumcc);
+
+/* generate_FragPairs, fixed-size branch, fithic/fithic.py:596-689.  Per chromosome (ALREADY in the reference's
+ * sorted-name order): chr_n[c] mappable loci and chr_maxmid[c] = max(mid) over them (maxFrag = max(mid) - res/2,
+ * :602).  bin_pairs (in/out, int64) carries the pass>=2 outlier decrements on entry ([1] and [7] move together).
+ * Outputs: bin_pairs, bin_sumdist, totals[0]=possibleIntraInRangeCount (x2 quirk kept, :618+:642),
+ * totals[1]=possibleIntraAllCount*2, totals[2]=sum n*(noOfFrags-n) (=2*possibleInterAllCount), totals[3]=noOfFrags */
+int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxmid, int32_t nchr, int32_t res, int64_t L,
+                        int64_t U, const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs,
+                        double *bin_sumdist, int64_t *totals);
+
+/* ---- K2: spline table ------------------------------------------------------------------------------------------
+ * Replaces ius(splineX) + IsotonicRegression(increasing=False) of fit_Spline (fithic/fithic.py:952-966) and bakes
+ * the clamp + bisect lookup of :1066-1068 into a dense table:
+ *   table[j] = antitonic(splev(t, c, 3, splineX[j]))                      j < m
+ *   lut[k]   = table[min(bisect_left(splineX, clamp(k*res, xmin, xmax)), m-1)]   k < D
+ * t, c: FITPACK knots/coefficients (nt each, c zero padded) [dev]; splineX [dev] int64 ascending.
+ * workspace: fhc_spline_workspace_bytes(m) bytes [dev]. */
+size_t fhc_spline_workspace_bytes(int64_t m);
+int fhc_spline_table(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m, double xmin,
+                     double xmax, int32_t res, double *table, double *lut, int64_t D, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ---- lbeta table -----------------------------------------------------------------------------------------------
+ * tab[c] = cephes lbeta(c, N - c + 1) for 1 <= c < ntab, the only third-party quantity whose ROUNDING matters at
+ * 1e-6: scipy.special.bdtrc -> xsf::cephes::incbet -> lbeta, reached from fithic/fithic.py:1070,:1101. */
+int fhc_lbeta_table(int64_t N, double *tab, int64_t ntab, void *stream);
+
+/* Host builds of the same source the device table kernel runs (log evaluated in double-double and rounded once, cephes
+ * lgam/lbeta with explicit round-to-nearest steps): lets CPU-only tests pin the table arithmetic.  Not a product path. */
+double fhc_host_log_cr(double x);
+double fhc_host_lbeta(double a, double b);
+
+/* ---- K3: per-contact p-value ---------------------------------------------------------------------------------
+ * Replaces the per-line loop of fit_Spline (fithic/fithic.py:1017-1123) including scipy.special.bdtrc (:1070,:1101).
+ *   bias       nullable dense per-locus bias (-1 = discarded by read_biases, :818-832) with bias_mid the mid point
+ *              each slot was read for and chr_off[nchr+1] the first slot of each chromosome id; the slot of
+ *              (chr, mid) is chr_off[chr] + mid / res; a slot outside the chromosome or with another mid is "missing"
+ *              (-1, :1026-1054)
+ *   lut        K2's table (intra in-range prior by distance slot), D entries; may be NULL in inter-only mode
+ *   N_intra    observedIntraInRangeSum, N_inter observedInterAllSum (both < 2^31, else FHC_E_RANGE: SURVEY F5)
+ *   lbeta_*    fhc_lbeta_table outputs for N_intra / N_inter (nullable => computed per contact)
+ *   outl       nullable per-line outlier multiplicity, incremented where p < outl_thres (:1215-1217);
+ *              outl_stats[0] += lines flagged now, outl_stats[1] = min(itself, line index whose multiplicity reached
+ *              >= 2) -- the caller initialises outl_stats to {0, UINT64_MAX} before the first pass
+ *   p, expcc   outputs, one double per line (:1119-1122) */
+int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
+                int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
+                int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
+                double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
+                const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, double outl_thres,
+                uint64_t *outl_stats, double *p, double *expcc, void *stream);
+
+/* scipy.special.bdtrc(k, n, prior) element-wise on device arrays (the arithmetic core of K3, exposed for parity
+ * tests against the oracle; call sites fithic/fithic.py:1070,:1101).  lbeta nullable. */
+int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *prior, int64_t n, const double *lbeta,
+              int64_t ntab, double *out, void *stream);
+
+/* ---- K4: q-values -----------------------------------------------------------------------------------------------
+ * Replaces myStats.benjamini_hochberg_correction (fithic/myStats.py:24-48): ascending order, bh = p*T/rank capped
+ * at 1, FORWARD running max, p == 1.0 -> 1.0, NaN -> NaN (sorted last).  rank_offset / carry_in allow a caller that
+ * range-partitions p-values over several GPUs to chain the scan (single GPU: 0 and 0.0); carry_out [dev, nullable]
+ * receives {running max after the last sorted element} and n_sorted_out [dev, nullable] the number of p < 1.
+ *   p [dev] n doubles, q [dev] n doubles (may not alias p). */
+size_t fhc_bh_workspace_bytes(int64_t n);
+int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                   double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Device radix sort of 64-bit keys with 32-bit payloads (ascending, stable), the sort inside K4, exposed for tests
+ * and for the multi-GPU range-partitioned BH.  Sorted data ends in keys_out/vals_out; *_in are clobbered.
+ * workspace: fhc_sort_workspace_bytes(n). */
+size_t fhc_sort_workspace_bytes(int64_t n);
+int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out, uint32_t *vals_out, int64_t n,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K5: outlier bookkeeping for pass >= 2 ---------------------------------------------------------------------
+ * Per-bin decrements of makeBinsFromInteractions (fithic/fithic.py:528-548): for every line, dec[b] += outl[i] where
+ * b is the bin whose [lb,ub] holds |mid1-mid2| (clamped to the last bin), exactly the forward scan of the reference
+ * over its sorted outlier distances (taken for inter lines too, :1217). */
+int fhc_outlier_bin_decrements(const int32_t *mid1, const int32_t *mid2, const uint8_t *outl, int64_t n,
+                               const int64_t *bin_ub, int32_t nbins, uint64_t *dec, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FITHIC_B200_H */

@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The built C-ABI library; built on demand where nvcc exists (the GPU box receives the prebuilt .so)."""
+    from fithic_b200 import _capi, build
+    if not os.path.exists(_capi.LIB_PATH):
+        build.build()
+    return _capi.load()

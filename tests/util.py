@@ -1,0 +1,83 @@
+"""Helpers shared by the parity tests: engine-format inputs -> oracle-format inputs, comparisons."""
+import numpy as np
+
+from oracle import fithic_oracle as O
+
+
+def oracle_inputs(contacts, frags, st, biases=None):
+    """fithic_b200 Contacts/Fragments/Biases/Settings -> arguments of oracle.run_pipeline."""
+    c1 = (contacts.chrs & 0xffff).astype(np.int32)
+    c2 = (contacts.chrs >> 16).astype(np.int32)
+    oc = O.Contacts(c1, contacts.mid1.astype(np.int64), c2, contacts.mid2.astype(np.int64),
+                    contacts.cnt.astype(np.int64), list(frags.chroms))
+    res = st.resolution
+    fchr, fmid = [], []
+    for ci in range(len(frags.chroms)):
+        n = int(frags.n_mappable[ci])
+        if n == 0:
+            continue
+        # synthetic fragments: n loci, the last one at max_mid, spaced by res
+        mids = frags.max_mid[ci] - (n - 1 - np.arange(n, dtype=np.int64)) * res
+        fchr.append(np.full(n, ci, dtype=np.int32))
+        fmid.append(mids)
+    fchr = np.concatenate(fchr) if fchr else np.zeros(0, np.int32)
+    fmid = np.concatenate(fmid) if fmid else np.zeros(0, np.int64)
+    fh = np.ones(len(fmid), dtype=np.int64)
+    ost = O.Settings(resolution=res, noOfBins=st.noOfBins, mappThres=st.mappThres, distLowThres=st.distLowThres,
+                     distUpThres=st.distUpThres, interOnly=st.interOnly, allReg=st.allReg,
+                     biasLowerBound=st.biasLowerBound, biasUpperBound=st.biasUpperBound, noOfPasses=st.noOfPasses)
+    ob = None
+    if biases is not None:
+        ob = {}
+        for ci in range(len(biases.chr_off) - 1):
+            lo, hi = int(biases.chr_off[ci]), int(biases.chr_off[ci + 1])
+            m = biases.mids[lo:hi]
+            ok = m >= 0
+            if ok.any():
+                ob[ci] = dict(zip(m[ok].astype(np.int64).tolist(), biases.values[lo:hi][ok].tolist()))
+    return oc, fchr, fmid, fh, ost, ob
+
+
+def rel_err(a, b):
+    """max |a-b|/|b| over entries where b is finite and non-zero; classes {0, NaN} must agree exactly."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    assert np.array_equal(a == 0, b == 0), "zero pattern differs"
+    m = ~np.isnan(b) & (b != 0)
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m])))
+
+
+def compare_pass(r, o, tol=1e-6, check_ones=True):
+    """r: engine result dict (host numpy p/q/expcc), o: oracle pass dict.  Returns dict of max relative errors."""
+    assert r["N"] == o["N"], (r["N"], o["N"])
+    assert r["T"] == o["T"], (r["T"], o["T"])
+    assert r["observedInterAllCount"] == o["observedInterAllCount"]
+    assert r["observedInterAllSum"] == o["observedInterAllSum"]
+    assert r["observedIntraAllSum"] == o["observedIntraAllSum"]
+    assert np.array_equal(r["dists"], o["dists"])
+    assert np.array_equal(r["sums"], o["sums"])
+    ob = o["bins"]
+    rb = r["bins"]
+    assert rb["n"] == len(ob)
+    for i, b in enumerate(ob):
+        assert (int(rb["lb"][i]), int(rb["ub"][i]), int(rb["sumcc"][i]), int(rb["pairs"][i])) == \
+            (b["lb"], b["ub"], b["sumcc"], b["pairs"]), (i, b)
+        assert float(rb["sumdist"][i]) == b["sumdist"], (i, rb["sumdist"][i], b["sumdist"])
+    out = {}
+    if o["splineX"] is not None:
+        assert list(r["x"]) == list(o["x"]) and list(r["y"]) == list(o["y"])
+        assert np.array_equal(np.asarray(r["splineX"]), np.asarray(o["splineX"]))
+        out["table"] = rel_err(r["table"], o["newSplineY"])
+        assert out["table"] <= 1e-12, out
+    p, q, e = r["p"], r["q"], r["expcc"]
+    if check_ones:
+        assert np.array_equal(p == 1.0, o["p"] == 1.0), "p == 1.0 class differs"
+    out["p"] = rel_err(p, o["p"])
+    out["q"] = rel_err(q, o["q"])
+    out["expcc"] = rel_err(e, o["expcc"])
+    assert out["p"] <= tol and out["q"] <= tol and out["expcc"] <= 1e-12, out
+    return out
