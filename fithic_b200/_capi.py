@@ -30,6 +30,8 @@ _SIGNATURES = {
     "fhc_abi_version": (ctypes.c_int, []),
     "fhc_last_error": (c_char_p, []),
     "fhc_launch_count": (c_int64, []),
+    "fhc_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "fhc_profile_collect": (ctypes.c_int, [c_char_p, c_size_t]),
     "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                           c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_host_make_bins": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -98,3 +100,15 @@ def dptr(t):
     if hasattr(t, "data_ptr"):
         return c_void_p(t.data_ptr())
     return c_void_p(t.ctypes.data)
+
+
+def profile_enable(on=True):
+    check(load().fhc_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """{kernel name: {"ms": total device ms, "launches": n}} since the last collect (synchronises the device)."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().fhc_profile_collect(buf, len(buf)))
+    return json.loads(buf.value.decode())

@@ -1,0 +1,52 @@
+"""Public array-level API: host contact arrays in, host p / q / ExpCC out.
+
+    from fithic_b200 import api
+    passes = api.significance(contacts, fragments, settings, biases=None)
+
+This is the call a user (or the `fithic` CLI) makes; bench.py times it end to end ("e2e"): every call copies the
+contact arrays host -> device and the three result arrays device -> host.
+"""
+import numpy as np
+import torch
+
+from .engine import Biases, Contacts, Engine, Fragments, Settings  # noqa: F401  (re-exported)
+
+
+class HostBuffers:
+    """Reusable pinned host buffers for the results of one run (3 x 8 B per contact)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.p = torch.empty(n, dtype=torch.float64).pin_memory()
+        self.q = torch.empty(n, dtype=torch.float64).pin_memory()
+        self.expcc = torch.empty(n, dtype=torch.float64).pin_memory()
+
+
+def significance(contacts, fragments, settings, biases=None, engine=None, out=None):
+    """Run every spline pass on the current CUDA device.
+
+    contacts: engine.Contacts (numpy int32/uint32 arrays, ideally views of pinned memory).
+    Returns a list with one dict per pass: p, q, expcc (numpy float64, file order) plus the per-pass tables
+    (bins, x, y, spline knots, N, T, outlier threshold).  `out` (HostBuffers) is reused for the last pass's arrays.
+    """
+    eng = engine if engine is not None else Engine(settings, fragments, biases)
+    eng.upload_contacts(contacts, non_blocking=True)
+    n = len(contacts)
+    if out is None or out.n != n:
+        out = HostBuffers(n)
+    outl, stats = eng.new_outlier_state()
+    results = []
+    for passNo in range(1, settings.noOfPasses + 1):
+        if passNo > 1 and settings.interOnly:
+            break
+        r = eng.run_pass(passNo, outl, stats)
+        out.p.copy_(r["p"], non_blocking=True)
+        out.q.copy_(r["q"], non_blocking=True)
+        out.expcc.copy_(r["expcc"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        last = passNo == settings.noOfPasses or settings.interOnly
+        r["p"] = out.p.numpy() if last else out.p.numpy().copy()
+        r["q"] = out.q.numpy() if last else out.q.numpy().copy()
+        r["expcc"] = out.expcc.numpy() if last else out.expcc.numpy().copy()
+        results.append(r)
+    return results

@@ -2,6 +2,11 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,8 +24,75 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- per-kernel timing -------------------------------------------------------------------------------------------
+// When enabled, every launch is followed by a cudaEventRecord on its stream; an entry point records one more event
+// when it is entered (name == nullptr).  All launches of a run share one stream, so the time between two consecutive
+// events is the device time of the kernel recorded by the second one (plus any idle gap in front of it, which is zero
+// while the host runs ahead of the GPU).
+bool g_profile_on = false;
+struct Mark {
+    cudaEvent_t ev;
+    const char *name;
+};
+static std::vector<Mark> g_marks;
+static std::vector<cudaEvent_t> g_pool;
+static std::mutex g_prof_mu;
+
+void profile_mark(const char *name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t ev;
+    if (!g_pool.empty()) {
+        ev = g_pool.back();
+        g_pool.pop_back();
+    } else if (cudaEventCreate(&ev) != cudaSuccess) {
+        return;
+    }
+    cudaEventRecord(ev, st);
+    g_marks.push_back({ev, name});
+}
+
 }  // namespace fhc
 
 extern "C" int fhc_abi_version(void) { return FHC_ABI_VERSION; }
 extern "C" const char *fhc_last_error(void) { return fhc::g_err; }
 extern "C" int64_t fhc_launch_count(void) { return fhc::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int fhc_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(fhc::g_prof_mu);
+    fhc::g_profile_on = on != 0;
+    return FHC_OK;
+}
+
+// Synchronises the device, folds the recorded events into per-kernel totals and writes them as JSON
+// ({"kernel": {"ms": total, "launches": n}, ...}) into buf; clears the log.  Returns the JSON length or an error.
+extern "C" int fhc_profile_collect(char *buf, size_t buf_bytes) {
+    using namespace fhc;
+    FHC_REQUIRE(buf != nullptr && buf_bytes > 2, FHC_E_INVALID, "fhc_profile_collect: no buffer");
+    FHC_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, long long>> acc;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        if (g_marks[i].name == nullptr) continue;  // entry marker: starts a new interval
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) continue;
+        auto &a = acc[g_marks[i].name];
+        a.first += ms;
+        a.second += 1;
+    }
+    for (auto &m : g_marks) g_pool.push_back(m.ev);
+    g_marks.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto &kv : acc) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", kv.first.c_str(),
+                 kv.second.first, kv.second.second);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    FHC_REQUIRE(out.size() + 1 <= buf_bytes, FHC_E_WORKSPACE, "fhc_profile_collect: buffer of %zu bytes, need %zu",
+                buf_bytes, out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}

@@ -12,6 +12,7 @@
 //
 // Every kernel reads the number of sorted elements from device memory, so the whole K4 is enqueued without a host sync.
 // HBM-bound: 16 algorithmic bytes per contact (read p, write q); the LSD passes move (8+12+12) B per element per pass.
+#define FHC_PROFILE_STREAM st
 #include "common.cuh"
 
 namespace fhc {
@@ -454,6 +455,7 @@ extern "C" int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t
     FHC_REQUIRE(workspace_bytes >= fhc_sort_workspace_bytes(n), FHC_E_WORKSPACE,
                 "fhc_sort_pairs_u64: workspace of %zu bytes, need %zu", workspace_bytes, fhc_sort_workspace_bytes(n));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
     char *base = reinterpret_cast<char *>(workspace);
     u64 *d_n = reinterpret_cast<u64 *>(base);
     SortWs ws;
@@ -510,6 +512,7 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
                 "fhc_bh_qvalues: workspace of %zu bytes, need %zu", workspace_bytes, fhc_bh_workspace_bytes(n));
     FHC_REQUIRE(n == 0 || (p && q && p != q), FHC_E_INVALID, "fhc_bh_qvalues: p and q must be distinct non-null arrays");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
     BhWs ws;
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
     FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, sizeof(u64), st));

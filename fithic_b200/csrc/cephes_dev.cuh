@@ -235,83 +235,174 @@ double lbeta_cephes(double a, double b) {
 // cephes incbcf (use_d = false, z = x) and incbd (use_d = true, z = x / (1 - x)):
 //   p_j = p_{j-1} + (n_j / d_j) p_{j-2}  is carried as  P_j = d_j P_{j-1} + d_{j-1} n_j P_{j-2}  (same for Q), so
 // P_j / Q_j is unchanged and no division is needed until the end; convergence is tested by cross multiplication.
-__device__ __forceinline__ double incbeta_cf(double a, double b, double x, bool use_d) {
-    double k1 = a, k3 = a, k4 = a + 1.0, k5 = 1.0, k7 = a + 1.0, k8 = a + 2.0;
-    double k2, k6, z, s2, s6;
-    if (use_d) {
-        k2 = b - 1.0; s2 = -1.0; k6 = a + b; s6 = 1.0; z = x / (1.0 - x);
-    } else {
-        k2 = a + b; s2 = 1.0; k6 = b - 1.0; s6 = -1.0; z = x;
-    }
-    double pkm2 = 0.0, qkm2 = 1.0, pkm1 = 1.0, qkm1 = 1.0, dprev = 1.0;
-    double pa = 1.0, qa = 1.0;  // previous convergent (ans = pa / qa)
-    for (int it = 0; it < kCfMaxIter; ++it) {
-        const double d1 = k3 * k4;
-        const double a1 = -(z * k1 * k2) * dprev;
-        double pk = d1 * pkm1 + a1 * pkm2;
-        double qk = d1 * qkm1 + a1 * qkm2;
-        pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
-        const double d2 = k7 * k8;
-        const double a2 = (z * k5 * k6) * d1;
-        pk = d2 * pkm1 + a2 * pkm2;
-        qk = d2 * qkm1 + a2 * qkm2;
-        pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
-        dprev = d2;
-        // |pa/qa - pk/qk| < tol |pk/qk|
-        const double lhs = fabs(pa * qk - pk * qa), rhs = kCfTol * fabs(qa * pk);
-        pa = pk; qa = qk;
-        if (lhs < rhs) break;
-        k1 += 1.0; k2 += s2; k3 += 2.0; k4 += 2.0; k5 += 1.0; k6 += s6; k7 += 2.0; k8 += 2.0;
-        const double mag = fabs(qk) + fabs(pk);
-        if (mag > 1.2676506002282294e30 || mag < 7.8886090522101181e-31) {  // 2^100, 2^-100: renormalise exactly
-            const int ex = ((__double2hiint(mag) >> 20) & 0x7ff);
-            if (ex != 0 && ex != 0x7ff) {
-                const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^-(ex-1023)
-                pkm2 *= sc; pkm1 *= sc; qkm2 *= sc; qkm1 *= sc; pa *= sc; qa *= sc;
-            }
-        }
-    }
-    return pa / qa;
+// The state is explicit so that a warp can keep all 32 lanes busy: a lane whose fraction has converged picks up the
+// next contact from a shared work list while its neighbours keep iterating (pvalue.cu).
+struct CfState {
+    double a, apb, bm1, z;  // parameters: a, a + b, b - 1, x or x / (1 - x)
+    double fi;              // iteration counter as a double
+    double pkm2, qkm2, pkm1, qkm1, dprev, pa, qa;
+    bool use_d;
+};
+
+__device__ __forceinline__ void cf_init(CfState &s, double a, double b, double x, bool use_d) {
+    s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
+    s.z = use_d ? x / (1.0 - x) : x;
+    s.fi = 0.0;
+    s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0; s.pa = 1.0; s.qa = 1.0;
 }
 
-// regularized incomplete beta I_x(a, b) for the bdtrc regime (a = count >= 2, b = N - count + 1); lbeta_ab is
-// cephes' lbeta(a, b) (tabulated).  Mirrors the branch structure of cephes incbet (swap about the mean, complement).
-__device__ __forceinline__ double incbet_dev(double aa, double bb, double xx, double lbeta_ab) {
-    if (xx <= 0.0) return xx == 0.0 ? 0.0 : NAN;
-    if (xx >= 1.0) return xx == 1.0 ? 1.0 : NAN;
-    double a, b, x, xc;
-    const double w1 = __dsub_rn(1.0, xx);  // cephes rounds 1 - x before taking its log
-    const bool flag = xx > aa / (aa + bb);
-    if (flag) {
-        a = bb; b = aa; xc = xx; x = w1;
-    } else {
-        a = aa; b = bb; xc = w1; x = xx;
+// one iteration (two recurrence steps); returns true when the fraction has converged (or hit the iteration cap):
+// the value is then s.pa / s.qa
+__device__ __forceinline__ bool cf_step(CfState &s) {
+    const double k1 = s.a + s.fi, k3 = k1 + s.fi, k4 = k3 + 1.0, k5 = 1.0 + s.fi, k8 = k3 + 2.0;
+    const double up = s.apb + s.fi, dn = s.bm1 - s.fi;
+    const double k2 = s.use_d ? dn : up, k6 = s.use_d ? up : dn;
+    const double d1 = k3 * k4;
+    const double a1 = -(s.z * k1 * k2) * s.dprev;
+    double pk = d1 * s.pkm1 + a1 * s.pkm2;
+    double qk = d1 * s.qkm1 + a1 * s.qkm2;
+    s.pkm2 = s.pkm1; s.pkm1 = pk; s.qkm2 = s.qkm1; s.qkm1 = qk;
+    const double d2 = k4 * k8;
+    const double a2 = (s.z * k5 * k6) * d1;
+    pk = d2 * s.pkm1 + a2 * s.pkm2;
+    qk = d2 * s.qkm1 + a2 * s.qkm2;
+    s.pkm2 = s.pkm1; s.pkm1 = pk; s.qkm2 = s.qkm1; s.qkm1 = qk;
+    s.dprev = d2;
+    // |pa/qa - pk/qk| < tol |pk/qk|
+    const double lhs = fabs(s.pa * qk - pk * s.qa), rhs = kCfTol * fabs(s.qa * pk);
+    s.pa = pk; s.qa = qk;
+    s.fi += 1.0;
+    if (lhs < rhs || s.fi >= (double)kCfMaxIter) return true;
+    const double mag = fabs(qk) + fabs(pk);
+    if (mag > 1.2676506002282294e30 || mag < 7.8886090522101181e-31) {  // 2^100, 2^-100: renormalise exactly
+        const int ex = ((__double2hiint(mag) >> 20) & 0x7ff);
+        if (ex != 0 && ex != 0x7ff) {
+            const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^-(ex-1023)
+            s.pkm2 *= sc; s.pkm1 *= sc; s.qkm2 *= sc; s.qkm1 *= sc; s.pa *= sc; s.qa *= sc;
+        }
     }
-    const double y = x * (a + b - 2.0) - (a - 1.0);
-    double w = incbeta_cf(a, b, x, !(y < 0.0));
-    if (!(y < 0.0)) w = w / xc;
-    double t = a * log(x) + b * log(xc) - lbeta_ab + log(w / a);
+    return false;
+}
+
+// Lower binomial tail relative to its last term, for the swapped branch of incbet (x > a/(a+b): the observed count is
+// below its expectation).  cephes evaluates I_{1-x}(b, a) there with the same continued fraction, but with a ~ N ~ 1e9
+// that fraction no longer reaches 3 ulp: 94-100 % of such inputs run into the 300-iteration cap and land within ~1e-7
+// of the true value (measured against Boost).  The tail is a short, all-positive finite sum instead:
+//   P(X <= k) = pmf(k) (1 + s_k (1 + s_{k-1} (1 + ...))),   s_j = pmf(j-1)/pmf(j) = j (1-x) / ((N-j+1) x),  k = count-1
+// evaluated inside-out as a ratio P/Q (no division in the loop).  Terms below 1e-17 of the sum are skipped: the term i
+// steps below k is <= r^i exp(-i(i-1)/2k) with r = k/(N x) <= 1, which bounds the number of terms M.
+// The sum S = P/Q gives  I_{1-x}(b, a) = (1-x)^b x^a / (b B(a, b)) * (S / x),  S / x being what cephes' fraction stands for.
+struct TailState {
+    double P, Q, j, d, cN, invN;
+    int m;  // terms left
+};
+
+__device__ __forceinline__ void tail_init(TailState &s, double count, double N, double x, double one_minus_x) {
+    const double k = count - 1.0;
+    s.invN = 1.0 / N;
+    s.cN = (one_minus_x / x) * s.invN;
+    const double r = k / (N * x);
+    double M = k;
+    if (r > 0.0 && r < 1.0) M = fmin(M, ceil(-39.2 / log(r)) + 1.0);
+    M = fmin(M, ceil(sqrt(78.4 * k)) + 1.0);
+    s.P = 1.0; s.Q = 1.0;
+    s.j = k - M + 1.0;
+    s.d = (N - s.j + 1.0) * s.invN;
+    s.m = (int)M;
+}
+
+// one term; returns true when the sum is complete (value s.P / s.Q)
+__device__ __forceinline__ bool tail_step(TailState &s) {
+    if (s.m <= 0) return true;
+    const double n = s.j * s.cN;
+    const double dq = s.d * s.Q;
+    s.P = fma(n, s.P, dq);
+    s.Q = dq;
+    s.j += 1.0;
+    s.d -= s.invN;
+    if (s.Q < 7.8886090522101181e-31) {  // 2^-100: only reachable when count is a sizeable fraction of N
+        s.P *= 1.2676506002282294e30;
+        s.Q *= 1.2676506002282294e30;
+    }
+    return --s.m <= 0;
+}
+
+// which evaluation a contact needs once the cheap exits of bdtrc / incbet are taken
+enum PvalClass : int { kClsDone = 0, kClsK0 = 1, kClsTail = 2, kClsCf = 3 };
+
+// The branch structure of scipy.special.bdtrc(k = count - 1, n = N, p = prior) and of cephes incbet up to the point
+// where real work starts.  Returns the class; for kClsDone `value` is the result.
+__device__ __forceinline__ PvalClass bdtrc_classify(int count, int N, double prior, double &value) {
+    value = NAN;
+    if (isnan(prior)) return kClsDone;
+    if (prior < 0.0 || prior > 1.0) return kClsDone;
+    const long long k = (long long)count - 1;
+    if (k < 0) { value = 1.0; return kClsDone; }
+    if ((long long)N < k) return kClsDone;
+    if (k == (long long)N) { value = 0.0; return kClsDone; }
+    if (k == 0) return kClsK0;
+    if (prior <= 0.0) { value = 0.0; return kClsDone; }  // incbet: xx == 0
+    if (prior >= 1.0) { value = 1.0; return kClsDone; }  // incbet: xx == 1
+    const double aa = (double)count, bb = (double)((long long)N - k);
+    return prior > aa / (aa + bb) ? kClsTail : kClsCf;
+}
+
+// k == 0: 1 - (1 - p)^n in cephes' two forms
+__device__ __forceinline__ double bdtrc_k0(int N, double prior) {
+    const double dn = (double)N;
+    if (prior < 0.01) {
+        // -expm1(y): for y <= -1 there is no cancellation in 1 - exp(y), and that form rounds like libm's expm1 where
+        // CUDA's expm1 saturates to -1 one ulp early (y in (-37.4, -36.7) decides p == 1.0 versus 1 - 2^-53)
+        const double y = dn * log1p(-prior);
+        return y <= -1.0 ? 1.0 - exp(y) : -expm1(y);
+    }
+    return 1.0 - pow(1.0 - prior, dn);
+}
+
+__device__ __forceinline__ bool cf_uses_d(double aa, double bb, double xx) {
+    return !(xx * (aa + bb - 2.0) - (aa - 1.0) < 0.0);  // cephes: y < 0 -> incbcf, else incbd
+}
+
+// last step of incbet: prefactor in log space times the fraction / tail value w = wp / wq
+__device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb, double xx, double lbeta_ab, double wp,
+                                                double wq) {
+    const double w1 = __dsub_rn(1.0, xx);  // cephes rounds 1 - x before taking its log
+    double w = wp / wq;
+    double div;
+    if (tail) {
+        w = w / xx;
+        div = bb;
+    } else {
+        if (cf_uses_d(aa, bb, xx)) w = w / w1;
+        div = aa;
+    }
+    double t = aa * log(xx) + bb * log(w1) - lbeta_ab + log(w / div);
     t = t < kMINLOG ? 0.0 : exp(t);
-    if (flag) t = (t <= kMACHEP) ? 1.0 - kMACHEP : 1.0 - t;
+    if (tail) t = (t <= kMACHEP) ? 1.0 - kMACHEP : 1.0 - t;
     return t;
 }
 
-// scipy.special.bdtrc(k = count - 1, n = N, p = prior) with n already known to fit an int32.
+// scalar evaluation (one contact start to finish): used by the element-wise test entry point
 __device__ __forceinline__ double bdtrc_dev(int count, int N, double prior, const double *__restrict__ lbeta_tab,
                                             long long ntab) {
-    if (isnan(prior)) return NAN;
-    if (prior < 0.0 || prior > 1.0) return NAN;
-    const long long k = (long long)count - 1;
-    if (k < 0) return 1.0;
-    if ((long long)N < k) return NAN;
-    if (k == (long long)N) return 0.0;
-    const double dn = (double)((long long)N - k);
-    if (k == 0) {
-        if (prior < 0.01) return -expm1(dn * log1p(-prior));
-        return 1.0 - pow(1.0 - prior, dn);
+    double v;
+    const PvalClass cls = bdtrc_classify(count, N, prior, v);
+    if (cls == kClsDone) return v;
+    if (cls == kClsK0) return bdtrc_k0(N, prior);
+    const double aa = (double)count, bb = (double)((long long)N - count + 1);
+    const double lb = (count < ntab) ? __ldg(lbeta_tab + count) : lbeta_cephes(aa, bb);
+    if (cls == kClsTail) {
+        TailState s;
+        tail_init(s, aa, (double)N, prior, __dsub_rn(1.0, prior));
+        while (!tail_step(s)) {
+        }
+        return incbet_finish(true, aa, bb, prior, lb, s.P, s.Q);
     }
-    const double lb = (count < ntab) ? __ldg(lbeta_tab + count) : lbeta_cephes((double)count, dn);
-    return incbet_dev((double)count, dn, prior, lb);
+    CfState s;
+    cf_init(s, aa, bb, prior, cf_uses_d(aa, bb, prior));
+    while (!cf_step(s)) {
+    }
+    return incbet_finish(false, aa, bb, prior, lb, s.pa, s.qa);
 }
 #endif  // __CUDACC__
 

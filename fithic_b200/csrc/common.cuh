@@ -12,6 +12,9 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// optional per-kernel timing (fhc_profile_*): one CUDA event after every launch on the launching stream
+void profile_mark(const char *name, cudaStream_t st);
+extern bool g_profile_on;
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -40,6 +43,13 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
             return FHC_E_CUDA;                                                                \
         }                                                                                     \
         fhc::count_launch();                                                                  \
+        if (fhc::g_profile_on) fhc::profile_mark(name, FHC_PROFILE_STREAM);                   \
+    } while (0)
+
+// entry points define this to the stream they launch on before using FHC_LAUNCH_CHECK
+#define FHC_PROFILE_ENTRY(st) \
+    do {                      \
+        if (fhc::g_profile_on) fhc::profile_mark(nullptr, st); \
     } while (0)
 
 __device__ __forceinline__ double warp_max(double v) {

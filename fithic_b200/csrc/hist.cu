@@ -9,6 +9,7 @@
 // short-distance slots never leave the SM; the CTA flushes to the global uint64 histogram every 2^20 contacts (bounds
 // every 32-bit partial sum below 2^32 because only counts < 4096 take the shared path) and at the end.  Totals are kept
 // in registers and reduced warp -> CTA -> one global atomic per CTA.
+#define FHC_PROFILE_STREAM st
 #include "common.cuh"
 
 namespace fhc {
@@ -161,18 +162,15 @@ extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const
                 "fhc_hist_distance: input arrays must be 16-byte aligned");
     FHC_REQUIRE(L >= -1 && U >= -1, FHC_E_INVALID, "fhc_hist_distance: L and U must be >= -1");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
     FHC_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * D, st));
     FHC_CUDA(cudaMemsetAsync(present, 0, sizeof(uint32_t) * ((D + 31) / 32), st));
     FHC_CUDA(cudaMemsetAsync(scalars, 0, sizeof(uint64_t) * FHC_N_SCALARS, st));
     if (n == 0) return FHC_OK;
     const int S = (int)(D < kHistSmemSlotsMax ? D : kHistSmemSlotsMax);
     const size_t smem = sizeof(unsigned int) * (size_t)S;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FHC_CUDA(cudaFuncSetAttribute(hist_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(unsigned int) * kHistSmemSlotsMax)));
-        attr_set = true;
-    }
+    FHC_CUDA(cudaFuncSetAttribute(hist_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(unsigned int) * kHistSmemSlotsMax)));
     const long long ntiles = n / kHistPairsPerTile;
     int grid = (int)(ntiles < kNumSMs ? (ntiles > 0 ? ntiles : 1) : kNumSMs);
     const long long Llo = L < 0 ? 0 : L;

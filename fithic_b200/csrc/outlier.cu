@@ -5,6 +5,7 @@
 // possible-pair count of the bin that holds each one, clamping past the last bin (:528-548).  Bins are contiguous from
 // 0, so "the bin that holds d" is the first bin with ub >= d, or the last bin.  The flagging itself is fused into K3
 // (pvalue.cu: outlier_mark); this kernel turns the per-line multiplicities into per-bin decrements.  HBM-bound: 9 B/line.
+#define FHC_PROFILE_STREAM st
 #include "common.cuh"
 
 namespace fhc {
@@ -65,6 +66,7 @@ extern "C" int fhc_outlier_bin_decrements(const int32_t *mid1, const int32_t *mi
                 "fhc_outlier_bin_decrements: need n >= 0 and 0 < nbins <= %d (got %d)", kOutlMaxBins, nbins);
     FHC_REQUIRE(dec && bin_ub, FHC_E_INVALID, "fhc_outlier_bin_decrements: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
     FHC_CUDA(cudaMemsetAsync(dec, 0, sizeof(uint64_t) * nbins, st));
     if (n == 0) return FHC_OK;
     FHC_REQUIRE(mid1 && mid2 && outl, FHC_E_INVALID, "fhc_outlier_bin_decrements: null pointer");

@@ -1,15 +1,28 @@
 // K3 -- fused per-contact significance: classify, bias gather, spline-table lookup, binomial survival, ExpCC.
 //
 // Replaces the per-line loop of fit_Spline (reference fithic/fithic.py:1017-1123) and scipy.special.bdtrc
-// (:1070, :1101).  One thread handles 4 consecutive contacts: four 128-bit streaming loads in (16 B/contact), two
-// 128-bit stores out for p and two for ExpCC (16 B/contact).  The bias vector, the distance table and the lbeta table
-// are small (<= 5 MB) and stay in L1/L2.  The kernel is FP64-ALU bound (continued fraction + 4 transcendentals per
-// contact), not HBM bound.
+// (:1070, :1101).  16 B/contact in (four 128-bit streaming loads per 4 contacts), 16 B/contact out (p and ExpCC as
+// 128-bit stores).  The bias vector, the distance table and the lbeta table are small (<= 5 MB) and stay in L1/L2.
+// The kernel is FP64-ALU bound (a continued fraction or a tail sum plus 4 transcendentals per contact), so what matters
+// is keeping all 32 lanes of a warp on the same instruction.  A contact needs one of three very different evaluations
+// (count == 1 closed form; tail sum when the count is below its expectation; continued fraction above it), each with a
+// data-dependent trip count, which in a thread-per-contact kernel leaves ~8 of 32 lanes active (measured).  Instead a
+// CTA works on a tile of 2048 contacts in phases:
+//   1. load + classify + prior + ExpCC; cheap results go straight to shared memory, the rest is appended to one work
+//      list per evaluation kind (warp-aggregated shared-memory appends);
+//   2. continued fractions: each lane steps its own fraction; a lane that converges stores numerator/denominator and
+//      takes the next contact from the list while its neighbours keep iterating (no lane waits for the slowest);
+//   3. tail sums, same scheme;
+//   4. one uniform pass turns every numerator/denominator into a p-value (3 logs + 1 exp, same code for both kinds),
+//      another handles the closed forms;
+//   5. p leaves through coalesced 128-bit stores; outliers are flagged.
+#define FHC_PROFILE_STREAM st
 #include "cephes_dev.cuh"
 
 namespace fhc {
 
 constexpr int kPvalThreads = 256;
+constexpr int kPvalTile = 2048;  // contacts per CTA tile (8 per thread)
 
 struct PvalParams {
     int mode;  // FHC_MODE_*
@@ -33,6 +46,17 @@ struct PvalParams {
     double *p, *expcc;
 };
 
+struct PvalSmem {
+    double x[kPvalTile];   // prior of the contacts that need real work
+    double wp[kPvalTile];  // trivial p / numerator of the fraction or tail / finally p
+    double wq[kPvalTile];  // denominator
+    int cnt[kPvalTile];
+    unsigned short list[3][kPvalTile];  // work lists: [0] closed form, [1] tail sum, [2] continued fraction
+    unsigned char inter[kPvalTile];     // 1: the contact is scored against N_inter
+    unsigned int n[3];
+    unsigned int cursor[2];  // next unclaimed entry of list[1] / list[2]
+};
+
 // bias dictionary lookup of fithic/fithic.py:1026-1054: missing chromosome or mid point -> -1
 __device__ __forceinline__ double bias_lookup(const PvalParams &P, unsigned int chr, int mid) {
     if ((int)chr >= P.nchr || mid < 0) return -1.0;
@@ -43,9 +67,11 @@ __device__ __forceinline__ double bias_lookup(const PvalParams &P, unsigned int 
     return __ldg(P.bias + s);
 }
 
+// The branch order of the reference's per-line loop (fithic/fithic.py:1057-1115) up to the bdtrc call.
+// Returns the evaluation class; `p` holds the result when the class is kClsDone.
 template <bool HAS_BIAS>
-__device__ __forceinline__ void pval_one(const PvalParams &P, int m1, int m2, int c, unsigned int ch, double &p_out,
-                                         double &e_out) {
+__device__ __forceinline__ PvalClass pval_prepare(const PvalParams &P, int m1, int m2, int c, unsigned int ch, double &p,
+                                                  double &e, double &prior, bool &use_inter) {
     const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
     const bool inter = c1 != c2;
     long long d = (long long)m1 - (long long)m2;
@@ -56,27 +82,28 @@ __device__ __forceinline__ void pval_one(const PvalParams &P, int m1, int m2, in
         b2 = bias_lookup(P, c2, m2);
     }
     const bool interOnly = P.mode == FHC_MODE_INTER_ONLY;
-    double p = 1.0, e = 0.0;
-    if ((b1 < 0.0 || b2 < 0.0) && !inter) {
-        // discarded locus (:1057-1063)
-    } else if (!inter && !interOnly) {
-        if (d >= P.Llo && d <= P.Uhi) {  // intraInRange (:1065-1079)
-            const unsigned int du = (unsigned int)d;
-            const unsigned int slot = du / P.res;
-            const double prior0 = ((long long)slot < P.D) ? __ldg(P.lut + slot) : NAN;
-            const double prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
-            p = bdtrc_dev(c, P.N_intra, prior, P.lbeta_intra, P.ntab_intra);
-            if (b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU) e = __dmul_rn((double)P.N_intra, prior);
-        }
-        // intraShort / intraLong: p = 1, ExpCC = 0 (:1081-1096)
+    p = 1.0;
+    e = 0.0;
+    prior = 0.0;
+    use_inter = false;
+    if ((b1 < 0.0 || b2 < 0.0) && !inter) return kClsDone;  // discarded locus (:1057-1063)
+    int N;
+    if (!inter && !interOnly) {
+        if (!(d >= P.Llo && d <= P.Uhi)) return kClsDone;  // intraShort / intraLong: p = 1, ExpCC = 0 (:1081-1096)
+        const unsigned int slot = (unsigned int)d / P.res;  // intraInRange (:1065-1079)
+        const double prior0 = ((long long)slot < P.D) ? __ldg(P.lut + slot) : NAN;
+        prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
+        N = P.N_intra;
     } else if (P.mode != FHC_MODE_INTRA_ONLY) {
         // inter lines, and under interOnly every line that was not discarded (:1098-1108)
-        const double prior = __dmul_rn(P.interChrProb, __dmul_rn(b1, b2));
-        p = bdtrc_dev(c, P.N_inter, prior, P.lbeta_inter, P.ntab_inter);
-        if (b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU) e = __dmul_rn((double)P.N_inter, prior);
+        prior = __dmul_rn(P.interChrProb, __dmul_rn(b1, b2));
+        N = P.N_inter;
+        use_inter = true;
+    } else {
+        return kClsDone;  // inter line in an intraOnly run (:1110-1115)
     }
-    p_out = p;
-    e_out = e;
+    if (b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU) e = __dmul_rn((double)N, prior);
+    return bdtrc_classify(c, N, prior, p);
 }
 
 __device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, double p, unsigned int &flagged) {
@@ -89,46 +116,208 @@ __device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, d
     }
 }
 
+// all 32 lanes call this; lanes with pred append li to the list
+__device__ __forceinline__ void list_append(bool pred, unsigned short *list, unsigned int *counter, int li, int lane) {
+    const unsigned int m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)li;
+}
+
+// claim the next entries of a work list for the lanes that need one; returns the local contact index or -1
+__device__ __forceinline__ int list_claim(bool need, const unsigned short *list, unsigned int total, unsigned int *cursor,
+                                          int lane) {
+    const unsigned int m = __ballot_sync(0xffffffffu, need);
+    if (m == 0) return -1;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!need) return -1;
+    const unsigned int k = base + __popc(m & ((1u << lane) - 1u));
+    return k < total ? (int)list[k] : -1;
+}
+
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(kPvalThreads) pvalues_kernel(const PvalParams P) {
-    const long long ngroups = P.n >> 2;
+__global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalParams P) {
+    extern __shared__ __align__(16) unsigned char pval_smem_raw[];
+    PvalSmem &S = *reinterpret_cast<PvalSmem *>(pval_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long ntiles = (P.n + kPvalTile - 1) / kPvalTile;
     unsigned int flagged = 0;
-    for (long long g = (long long)blockIdx.x * kPvalThreads + threadIdx.x; g < ngroups;
-         g += (long long)gridDim.x * kPvalThreads) {
-        const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
-        const int4 ah = ldg_stream(P.chrs + g);
-        double p0, p1, p2, p3, e0, e1, e2, e3;
-        pval_one<HAS_BIAS>(P, a1.x, a2.x, ac.x, (unsigned int)ah.x, p0, e0);
-        pval_one<HAS_BIAS>(P, a1.y, a2.y, ac.y, (unsigned int)ah.y, p1, e1);
-        pval_one<HAS_BIAS>(P, a1.z, a2.z, ac.z, (unsigned int)ah.z, p2, e2);
-        pval_one<HAS_BIAS>(P, a1.w, a2.w, ac.w, (unsigned int)ah.w, p3, e3);
-        double2 *pp = reinterpret_cast<double2 *>(P.p) + 2 * g;
-        double2 *ee = reinterpret_cast<double2 *>(P.expcc) + 2 * g;
-        __stcs(pp, make_double2(p0, p1));
-        __stcs(pp + 1, make_double2(p2, p3));
-        __stcs(ee, make_double2(e0, e1));
-        __stcs(ee + 1, make_double2(e2, e3));
-        if (P.outl != nullptr) {
-            outlier_mark(P, 4 * g + 0, p0, flagged);
-            outlier_mark(P, 4 * g + 1, p1, flagged);
-            outlier_mark(P, 4 * g + 2, p2, flagged);
-            outlier_mark(P, 4 * g + 3, p3, flagged);
+    const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
+    const int *cs = reinterpret_cast<const int *>(P.cnt);
+    const unsigned int *hs = reinterpret_cast<const unsigned int *>(P.chrs);
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kPvalTile;
+        const bool full = base + kPvalTile <= P.n;
+        if (tid < 3) S.n[tid] = 0;
+        if (tid < 2) S.cursor[tid] = 0;
+        __syncthreads();
+        // ---- phase 1: load, classify, prior, ExpCC ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l0 = (h * kPvalThreads + tid) * 4;  // local index of this thread's 4 contacts
+            int m1[4], m2[4], cc[4];
+            unsigned int ch[4];
+            if (full) {
+                const long long g = (base + l0) >> 2;
+                const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
+                const int4 ah = ldg_stream(P.chrs + g);
+                m1[0] = a1.x; m1[1] = a1.y; m1[2] = a1.z; m1[3] = a1.w;
+                m2[0] = a2.x; m2[1] = a2.y; m2[2] = a2.z; m2[3] = a2.w;
+                cc[0] = ac.x; cc[1] = ac.y; cc[2] = ac.z; cc[3] = ac.w;
+                ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y; ch[2] = (unsigned int)ah.z; ch[3] = (unsigned int)ah.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long i = base + l0 + k;
+                    const bool ok = i < P.n;
+                    m1[k] = ok ? m1s[i] : 0;
+                    m2[k] = ok ? m2s[i] : 0;
+                    cc[k] = ok ? cs[i] : 0;
+                    ch[k] = ok ? hs[i] : 0x00010000u;  // padding: an inter line
+                }
+            }
+            double e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int li = l0 + k;
+                double p, prior;
+                bool use_inter;
+                PvalClass cls = pval_prepare<HAS_BIAS>(P, m1[k], m2[k], cc[k], ch[k], p, e[k], prior, use_inter);
+                if (!full && base + li >= P.n) cls = kClsDone;
+                if (cls == kClsDone) {
+                    S.wp[li] = p;
+                } else {
+                    S.x[li] = prior;
+                    S.cnt[li] = cc[k];
+                    S.inter[li] = use_inter ? 1 : 0;
+                }
+                list_append(cls == kClsK0, S.list[0], &S.n[0], li, lane);
+                list_append(cls == kClsTail, S.list[1], &S.n[1], li, lane);
+                list_append(cls == kClsCf, S.list[2], &S.n[2], li, lane);
+            }
+            if (full) {
+                double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
+                __stcs(ee, make_double2(e[0], e[1]));
+                __stcs(ee + 1, make_double2(e[2], e[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (base + l0 + k < P.n) P.expcc[base + l0 + k] = e[k];
+            }
         }
-    }
-    // tail (n % 4 contacts)
-    if (blockIdx.x == 0 && threadIdx.x < (P.n & 3)) {
-        const long long i = (ngroups << 2) + threadIdx.x;
-        double p, e;
-        pval_one<HAS_BIAS>(P, reinterpret_cast<const int *>(P.mid1)[i], reinterpret_cast<const int *>(P.mid2)[i],
-                           reinterpret_cast<const int *>(P.cnt)[i], reinterpret_cast<const unsigned int *>(P.chrs)[i], p,
-                           e);
-        P.p[i] = p;
-        P.expcc[i] = e;
-        if (P.outl != nullptr) outlier_mark(P, i, p, flagged);
+        __syncthreads();
+        const unsigned int nK0 = S.n[0], nTail = S.n[1], nCf = S.n[2];
+        // ---- phase 2: continued fractions, lanes refill from the list as they converge ----
+        {
+            CfState st;
+            int item = -1;
+            bool exhausted = false;
+            while (true) {
+                const bool need = item < 0 && !exhausted;
+                const int got = list_claim(need, S.list[2], nCf, &S.cursor[1], lane);  // every lane takes part
+                if (need) {
+                    if (got < 0) {
+                        exhausted = true;
+                    } else {
+                        item = got;
+                        const int N = S.inter[item] ? P.N_inter : P.N_intra;
+                        const double aa = (double)S.cnt[item], bb = (double)((long long)N - S.cnt[item] + 1);
+                        const double xx = S.x[item];
+                        cf_init(st, aa, bb, xx, cf_uses_d(aa, bb, xx));
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, item >= 0) == 0) break;
+                if (item >= 0 && cf_step(st)) {
+                    S.wp[item] = st.pa;
+                    S.wq[item] = st.qa;
+                    item = -1;
+                }
+            }
+        }
+        // ---- phase 3: tail sums, same scheme ----
+        {
+            TailState st;
+            int item = -1;
+            bool exhausted = false;
+            while (true) {
+                const bool need = item < 0 && !exhausted;
+                const int got = list_claim(need, S.list[1], nTail, &S.cursor[0], lane);  // every lane takes part
+                if (need) {
+                    if (got < 0) {
+                        exhausted = true;
+                    } else {
+                        item = got;
+                        const int N = S.inter[item] ? P.N_inter : P.N_intra;
+                        const double xx = S.x[item];
+                        tail_init(st, (double)S.cnt[item], (double)N, xx, __dsub_rn(1.0, xx));
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, item >= 0) == 0) break;
+                if (item >= 0 && tail_step(st)) {
+                    S.wp[item] = st.P;
+                    S.wq[item] = st.Q;
+                    item = -1;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: p-values ----
+        for (unsigned int i = tid; i < nTail + nCf; i += kPvalThreads) {
+            const bool tail = i < nTail;
+            const int item = tail ? S.list[1][i] : S.list[2][i - nTail];
+            const bool ui = S.inter[item] != 0;
+            const int N = ui ? P.N_inter : P.N_intra;
+            const int c = S.cnt[item];
+            const double aa = (double)c, bb = (double)((long long)N - c + 1);
+            const double *tab = ui ? P.lbeta_inter : P.lbeta_intra;
+            const long long ntab = ui ? P.ntab_inter : P.ntab_intra;
+            const double lb = (c < ntab) ? __ldg(tab + c) : lbeta_cephes(aa, bb);
+            S.wp[item] = incbet_finish(tail, aa, bb, S.x[item], lb, S.wp[item], S.wq[item]);
+        }
+        for (unsigned int i = tid; i < nK0; i += kPvalThreads) {
+            const int item = S.list[0][i];
+            S.wp[item] = bdtrc_k0(S.inter[item] ? P.N_inter : P.N_intra, S.x[item]);
+        }
+        __syncthreads();
+        // ---- phase 5: coalesced stores of p, outlier flags ----
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l0 = (h * kPvalThreads + tid) * 4;
+            const double p0 = S.wp[l0], p1 = S.wp[l0 + 1], p2 = S.wp[l0 + 2], p3 = S.wp[l0 + 3];
+            if (full) {
+                double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
+                __stcs(pp, make_double2(p0, p1));
+                __stcs(pp + 1, make_double2(p2, p3));
+                if (P.outl != nullptr) {
+                    outlier_mark(P, base + l0 + 0, p0, flagged);
+                    outlier_mark(P, base + l0 + 1, p1, flagged);
+                    outlier_mark(P, base + l0 + 2, p2, flagged);
+                    outlier_mark(P, base + l0 + 3, p3, flagged);
+                }
+            } else {
+                const double pv[4] = {p0, p1, p2, p3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long i = base + l0 + k;
+                    if (i < P.n) {
+                        P.p[i] = pv[k];
+                        if (P.outl != nullptr) outlier_mark(P, i, pv[k], flagged);
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
     if (P.outl != nullptr) {
         const unsigned long long f = warp_sum((unsigned long long)flagged);
-        if ((threadIdx.x & 31) == 0 && f) atomicAdd(P.outl_stats, f);
+        if (lane == 0 && f) atomicAdd(P.outl_stats, f);
     }
 }
 
@@ -156,7 +345,9 @@ extern "C" int fhc_lbeta_table(int64_t N, double *tab, int64_t ntab, void *strea
                 "fhc_lbeta_table: N = %lld does not fit the int32 that scipy.special.bdtrc truncates n to", (long long)N);
     const int threads = 128;
     const long long blocks = (ntab + threads - 1) / threads;
-    lbeta_table_kernel<<<(unsigned int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>((int)N, tab, ntab);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    lbeta_table_kernel<<<(unsigned int)blocks, threads, 0, st>>>((int)N, tab, ntab);
     FHC_LAUNCH_CHECK("lbeta_table_kernel");
     return FHC_OK;
 }
@@ -170,7 +361,9 @@ extern "C" int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *pr
     FHC_REQUIRE(cnt_minus_1 && prior && out, FHC_E_INVALID, "fhc_bdtrc: null pointer");
     const int threads = 256;
     const long long blocks = (n + threads - 1) / threads;
-    bdtrc_kernel<<<(unsigned int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    bdtrc_kernel<<<(unsigned int)blocks, threads, 0, st>>>(
         cnt_minus_1, (int)N, prior, n, lbeta, lbeta ? ntab : 0, out);
     FHC_LAUNCH_CHECK("bdtrc_kernel");
     return FHC_OK;
@@ -231,16 +424,19 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;
     P.expcc = expcc;
-    const long long ngroups = n >> 2;
-    long long blocks = (ngroups + kPvalThreads - 1) / kPvalThreads;
-    const long long cap = (long long)kNumSMs * 64;  // grid-stride beyond 64 CTAs per SM
+    long long blocks = (n + kPvalTile - 1) / kPvalTile;
+    const long long cap = (long long)kNumSMs * 2;  // persistent: 2 resident CTAs per SM, grid-stride over tiles
     if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (bias)
-        pvalues_kernel<true><<<(unsigned int)blocks, kPvalThreads, 0, st>>>(P);
-    else
-        pvalues_kernel<false><<<(unsigned int)blocks, kPvalThreads, 0, st>>>(P);
+    FHC_PROFILE_ENTRY(st);
+    const size_t smem = sizeof(PvalSmem);
+    if (bias) {
+        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pvalues_kernel<true><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);
+    } else {
+        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pvalues_kernel<false><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);
+    }
     FHC_LAUNCH_CHECK("pvalues_kernel");
     return FHC_OK;
 }

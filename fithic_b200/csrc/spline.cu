@@ -12,6 +12,7 @@
 //      (sum at block start, end-of-block at block start, start-of-block at block end), so a pool is O(1) and nothing
 //      is compacted.  Pooling adjacent violators in any order gives the unique antitonic least-squares fit.
 //   3. a second kernel fills lut[k] for every distance slot.
+#define FHC_PROFILE_STREAM st
 #include "common.cuh"
 
 namespace fhc {
@@ -197,6 +198,7 @@ extern "C" int fhc_spline_table(const double *t, const double *c, int32_t nt, co
     FHC_REQUIRE(workspace_bytes >= fhc_spline_workspace_bytes(m), FHC_E_WORKSPACE,
                 "fhc_spline_table: workspace of %zu bytes, need %zu", workspace_bytes, fhc_spline_workspace_bytes(m));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
     double *sum = reinterpret_cast<double *>(workspace);
     int *endOf = reinterpret_cast<int *>(sum + m);
     int *startOf = endOf + m;

@@ -106,9 +106,23 @@ def make_intra(n_pairs, res, seed, chroms=None, mean_count=3.0, with_bias=False,
     return contacts, frags, biases, raw
 
 
-def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, chunk=1 << 26):
-    """torch generator on the GPU for bench-sized inputs (300 M pairs in seconds).  Same law as make_intra.
-    Returns (mid1, mid2, cnt, chrs) int32 device tensors, Fragments, Biases, per-chromosome pair counts."""
+def lpt_shards(weights, nshards):
+    """Largest-processing-time-first assignment of chromosomes to GPUs.  Returns list of index lists."""
+    order = sorted(range(len(weights)), key=lambda i: -weights[i])
+    loads = [0] * nshards
+    out = [[] for _ in range(nshards)]
+    for i in order:
+        r = min(range(nshards), key=lambda k: loads[k])
+        out[r].append(i)
+        loads[r] += weights[i]
+    return [sorted(o) for o in out]
+
+
+def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, only=None, chunk=1 << 26):
+    """torch generator on the GPU for bench-sized inputs (300 M pairs in seconds).  Same law as make_intra; every
+    chromosome has its own seeded stream, so a rank that generates only the chromosomes in `only` (indices) gets exactly
+    the lines the single-GPU run has for them.  Returns ((mid1, mid2, cnt, chrs) int32 device tensors, Fragments,
+    Biases, per-chromosome pair counts of the WHOLE data set)."""
     import torch
     names, sizes = genome(None)
     nb = n_bins(sizes, res)
@@ -123,16 +137,19 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
     pk = 1.0 / (ks + 1.0)
     pk /= pk.sum()
     lam0 = (mean_count - 1.0) / float((pk * (ks + 1.0) ** -1.08).sum())
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    mid1 = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    mid2 = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    cnt = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    chrs = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    which = list(range(len(names))) if only is None else list(only)
+    n_local = int(per[which].sum()) if len(which) else 0
+    mid1 = torch.empty(n_local, dtype=torch.int32, device=device)
+    mid2 = torch.empty(n_local, dtype=torch.int32, device=device)
+    cnt = torch.empty(n_local, dtype=torch.int32, device=device)
+    chrs = torch.empty(n_local, dtype=torch.int32, device=device)
     bvals = torch.from_numpy(biases.values).to(device) if biases is not None else None
     pos = 0
-    for ci, n in enumerate(per.tolist()):
+    for ci in which:
+        n = int(per[ci])
         nbc = int(nb[ci])
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000 + ci)
         done = 0
         while done < n:
             m = min(chunk, n - done)

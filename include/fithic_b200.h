@@ -57,6 +57,12 @@ const char *fhc_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t fhc_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled every kernel launch of this library is followed by a
+ * cudaEventRecord on its stream.  fhc_profile_collect synchronises the device, writes
+ * {"<kernel>": {"ms": total, "launches": n}, ...} into buf and clears the log; returns the string length. */
+int fhc_profile_enable(int on);
+int fhc_profile_collect(char *buf, size_t buf_bytes);
+
 /* ---- K1: distance histogram + totals ------------------------------------------------------------------------
  * Replaces the accumulation loop of read_Interactions (fithic/fithic.py:406-441) with the classification of
  * myUtils.Interaction.getType (fithic/myUtils.py:135-148).

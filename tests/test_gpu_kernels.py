@@ -1,0 +1,314 @@
+"""GPU parity of each C-ABI entry point against the oracle / numpy on seeded inputs, plus the reference KATs
+(generated from the unmodified reference)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from fithic_b200 import _capi
+from fithic_b200._capi import check, dptr
+from oracle import fithic_oracle as O
+from tests.util import rel_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3 arithmetic: scipy.special.bdtrc
+# ---------------------------------------------------------------------------------------------------------------------
+def gpu_bdtrc(lib, km1, N, prior, with_table=True):
+    km1 = np.ascontiguousarray(km1, dtype=np.int32)
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    n = len(km1)
+    out = torch.empty(n, dtype=torch.float64, device=DEV)
+    tab, ntab = None, 0
+    if with_table:
+        ntab = int(min(max(int(km1.max()) + 2, 2), N + 1, 1 << 20))
+        tab = torch.empty(ntab, dtype=torch.float64, device=DEV)
+        check(lib.fhc_lbeta_table(int(N), dptr(tab), ntab, stream()))
+    dk, dp = dev(km1), dev(prior)  # keep the device buffers alive across the asynchronous call
+    check(lib.fhc_bdtrc(dptr(dk), int(N), dptr(dp), n, dptr(tab), ntab, dptr(out), stream()))
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("N", [100, 171, 5000, 4219169, 300_000_000, 900_000_000, (1 << 31) - 1])
+def test_bdtrc_matches_oracle(lib, N):
+    rng = np.random.default_rng(N % 9973)
+    n = 200_000
+    cmax = min(N, 4000)
+    cnt = np.minimum(np.floor(np.exp(rng.uniform(0, np.log(cmax + 1), n))).astype(np.int64), cmax)
+    ratio = np.exp(rng.uniform(np.log(0.01), np.log(100), n))  # expected / observed
+    prior = np.minimum(cnt * ratio / N, 1.0)
+    prior[::97] = np.exp(rng.uniform(np.log(1e-14), 0, len(prior[::97])))
+    want = O.bdtrc(cnt - 1.0, N, prior)
+    got = gpu_bdtrc(lib, cnt - 1, N, prior)
+    assert np.array_equal(got == 1.0, want == 1.0)
+    e = rel_err(got, want)
+    print("N=%d max rel err %.3e" % (N, e))
+    assert e <= 1e-6  # the contract; typical 1e-10 .. 1e-7 (cephes' own error vs Boost is 1e-8 .. 1e-7)
+    # the per-contact fallback (no table) must agree with the table path bit for bit
+    sub = slice(0, 5000)
+    assert np.array_equal(gpu_bdtrc(lib, cnt[sub] - 1, N, prior[sub], with_table=False), got[sub], equal_nan=True)
+
+
+def test_bdtrc_known_answers(lib):
+    """values of scipy.special.bdtrc as the reference calls it."""
+    kat = [(0, 1000, 1e-3, 0.6323045752290359), (0, 1000, 0.5, 1.0), (-1, 10, 0.3, 1.0), (10, 10, 0.5, 0.0),
+           (4, 4219169, 2.4e-06, 0.973042930439372), (49, 4219169, 7.4e-06, 0.0011871506001787358),
+           (399, 4219169, 7.4e-05, 1.0582078639719162e-06), (2, 10 ** 9, 1e-09, 0.08030139697942389),
+           (1999, 10 ** 9, 1.5e-06, 6.60069186605028e-35), (5, 100, 0.0, 0.0), (5, 100, 1.0, 1.0)]
+    for k, N, p, want in kat:
+        got = gpu_bdtrc(lib, [k], N, [p])[0]
+        assert got == want or abs(got - want) <= 1e-6 * abs(want), (k, N, p, got, want)
+    assert np.isnan(gpu_bdtrc(lib, [5], 100, [-0.1])[0])
+    assert np.isnan(gpu_bdtrc(lib, [5], 100, [1.5])[0])
+    assert np.isnan(gpu_bdtrc(lib, [5], 100, [np.nan])[0])
+    assert np.isnan(gpu_bdtrc(lib, [11], 10, [0.5])[0])  # n < k
+    # n >= 2^31 is where the reference itself breaks (int32 wrap): refused loudly
+    with pytest.raises(_capi.FithicB200Error):
+        gpu_bdtrc(lib, [2], 1 << 31, [1e-9])
+
+
+def test_lbeta_table_bit_exact(lib):
+    """Device table == host build of the same source == oracle's cephes lbeta (for N + 1 > MAXGAM)."""
+    ol = O._lib()
+    ol.oracle_lbeta.restype = ctypes.c_double
+    ol.oracle_lbeta.argtypes = [ctypes.c_double, ctypes.c_double]
+    for N in (172, 4219169, 900_000_000, (1 << 31) - 1):
+        ntab = min(N, 3000) + 1
+        tab = torch.empty(ntab, dtype=torch.float64, device=DEV)
+        check(lib.fhc_lbeta_table(N, dptr(tab), ntab, stream()))
+        torch.cuda.synchronize()
+        t = tab.cpu().numpy()
+        want = np.array([ol.oracle_lbeta(float(c), float(N - c + 1)) for c in range(1, ntab)])
+        host = np.array([lib.fhc_host_lbeta(float(c), float(N - c + 1)) for c in range(1, ntab)])
+        assert np.array_equal(t[1:], host)
+        assert np.array_equal(t[1:], want), N
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 3, 4097, 1_000_003])
+@pytest.mark.parametrize("LU", [(0, -1), (20000, 2_000_000), (-1, 50000)])
+def test_hist_distance(lib, n, LU):
+    rng = np.random.default_rng(n + 17)
+    res = 10000
+    nb = 5000
+    i = rng.integers(0, nb, n)
+    k = np.minimum((rng.pareto(0.7, n) * 3).astype(np.int64), nb - 1 - i)
+    m1 = (i * res + res // 2).astype(np.int32)
+    m2 = ((i + k) * res + res // 2).astype(np.int32)
+    swap = rng.random(n) < 0.5
+    m1, m2 = np.where(swap, m2, m1), np.where(swap, m1, m2)
+    cnt = (1 + rng.poisson(3, n)).astype(np.int32)
+    if n > 10:
+        cnt[rng.integers(0, n, 5)] = 0           # zero counts keep the distance "seen"
+        cnt[rng.integers(0, n, 5)] = 100_000     # large counts take the global-atomic path
+    c1 = rng.integers(0, 3, n).astype(np.uint32)
+    c2 = np.where(rng.random(n) < 0.8, c1, rng.integers(0, 3, n)).astype(np.uint32)
+    chrs = (c1 | (c2 << 16)).astype(np.uint32)
+    skip = (rng.random(n) < 0.1).astype(np.uint8) * rng.integers(1, 3, n).astype(np.uint8)
+    skip_limit = n // 2
+    L, U = LU
+    D = nb + 1
+    hist = torch.empty(D, dtype=torch.int64, device=DEV)
+    present = torch.empty((D + 31) // 32, dtype=torch.int32, device=DEV)
+    scal = torch.empty(8, dtype=torch.int64, device=DEV)
+    pad = lambda a: dev(a) if n else torch.empty(4, dtype=torch.from_numpy(a).dtype, device=DEV)
+    bufs = [pad(m1), pad(m2), pad(cnt), pad(chrs.view(np.int32)), pad(skip)]
+    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), dptr(bufs[4]), skip_limit,
+                                n, L, U, res, dptr(hist), dptr(present), D, dptr(scal), stream()))
+    torch.cuda.synchronize()
+    h, pr, s = hist.cpu().numpy(), present.cpu().numpy().view(np.uint32), scal.cpu().numpy()
+    kept = ~((skip != 0) & (np.arange(n) <= skip_limit))
+    intra = (c1 == c2) & kept
+    d = np.abs(m1.astype(np.int64) - m2.astype(np.int64))
+    inr = intra & (d >= max(L, 0)) & ((U == -1) | (d <= U))
+    want = np.zeros(D, dtype=np.int64)
+    np.add.at(want, d[inr] // res, cnt[inr].astype(np.int64))
+    assert np.array_equal(h, want)
+    bits = np.unpackbits(pr.view(np.uint8), bitorder="little")[:D].astype(bool)
+    wbits = np.zeros(D, dtype=bool)
+    wbits[d[inr & (cnt <= 0)] // res] = True
+    assert np.array_equal(bits, wbits)
+    inter = (c1 != c2) & kept
+    assert s[_capi.S_INTRA_INRANGE_SUM] == cnt[inr].astype(np.int64).sum()
+    assert s[_capi.S_INTRA_ALL_SUM] == cnt[intra].astype(np.int64).sum()
+    assert s[_capi.S_INTER_ALL_SUM] == cnt[inter].astype(np.int64).sum()
+    assert s[_capi.S_INTER_ALL_COUNT] == inter.sum()
+    assert s[_capi.S_INTRA_INRANGE_LINES] == inr.sum()
+    assert s[_capi.S_INTRA_ALL_LINES] == intra.sum()
+    assert s[_capi.S_MAX_COUNT] == (cnt.max() if n else 0)
+    assert s[_capi.S_OFFGRID] == 0
+
+
+def test_hist_offgrid_is_reported(lib):
+    m1 = np.array([5000, 5000, 5000, 5000], dtype=np.int32)
+    m2 = np.array([15000, 15001, 25000, 5000], dtype=np.int32)
+    cnt = np.ones(4, dtype=np.int32)
+    chrs = np.zeros(4, dtype=np.int32)
+    hist = torch.empty(8, dtype=torch.int64, device=DEV)
+    present = torch.empty(1, dtype=torch.int32, device=DEV)
+    scal = torch.empty(8, dtype=torch.int64, device=DEV)
+    bufs = [dev(m1), dev(m2), dev(cnt), dev(chrs)]
+    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), None, -1, 4, 0, -1, 10000,
+                                dptr(hist), dptr(present), 8, dptr(scal), stream()))
+    torch.cuda.synchronize()
+    assert scal.cpu().numpy()[_capi.S_OFFGRID] == 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K4: sort and q-values
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 31, 4096, 4097, 250_001, 3_000_000])
+def test_sort_pairs(lib, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 63, n, dtype=np.uint64) * 2 + rng.integers(0, 2, n).astype(np.uint64)
+    if n > 100:
+        keys[rng.integers(0, n, n // 3)] = keys[rng.integers(0, n, n // 3)]  # duplicates: stability matters
+        keys[:50] &= np.uint64(0xff)                                          # shared high digits
+    vals = np.arange(n, dtype=np.uint32)
+    ki, vi = dev(keys.view(np.int64)), dev(vals.view(np.int32))
+    ko, vo = torch.empty_like(ki), torch.empty_like(vi)
+    wsb = int(lib.fhc_sort_workspace_bytes(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    check(lib.fhc_sort_pairs_u64(dptr(ki), dptr(vi), dptr(ko), dptr(vo), n, dptr(ws), wsb, stream()))
+    torch.cuda.synchronize()
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko.cpu().numpy().view(np.uint64), keys[order])
+    assert np.array_equal(vo.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+
+
+def gpu_bh(lib, p, T, rank_offset=0, carry_in=0.0):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    n = len(p)
+    pd_ = dev(p) if n else torch.empty(1, dtype=torch.float64, device=DEV)
+    q = torch.full((max(n, 1),), -7.0, dtype=torch.float64, device=DEV)
+    carry = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ns = torch.zeros(1, dtype=torch.int64, device=DEV)
+    wsb = int(lib.fhc_bh_workspace_bytes(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    check(lib.fhc_bh_qvalues(dptr(pd_), n, float(T), rank_offset, carry_in, dptr(q), dptr(carry), dptr(ns), dptr(ws), wsb,
+                             stream()))
+    torch.cuda.synchronize()
+    return q.cpu().numpy()[:n], float(carry.item()), int(ns.item())
+
+
+def test_bh_known_answers(lib):
+    """SURVEY.md Appendix B (outputs of the unmodified myStats.benjamini_hochberg_correction)."""
+    nan = float("nan")
+    kat = [([0.03, 0.4, 0.7, 0.01], 10, [0.15, 1, 1, 0.1]),
+           ([0.03, 0.4, 0.7, 0.01], 4, [0.06, 0.5333333333333333, 0.7, 0.04]),
+           ([0.02, 0.02, 1.0, 0.5, 0.02, 1.0, 0.0], 7, [0.07, 0.07, 1.0, 0.7, 0.07, 1.0, 0.0]),
+           ([0.2, nan, 0.01, 1.0, nan, 0.9], 6, [0.6000000000000001, nan, 0.06, 1.0, nan, 1]),
+           ([0.01, 0.011, 0.012, 0.5], 4, [0.04, 0.04, 0.04, 0.5]),   # forward running MAX, not textbook BH
+           ([1e-9, 1e-3, 0.5], 1000, [1.0000000000000002e-06, 0.5, 1])]
+    for p, T, want in kat:
+        got, _, _ = gpu_bh(lib, p, T)
+        assert np.array_equal(got, np.array(want, dtype=np.float64), equal_nan=True), (p, T, got, want)
+        assert np.array_equal(got, np.array(O.benjamini_hochberg_loop(p, T), dtype=np.float64), equal_nan=True)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 100_003, 2_000_000])
+def test_bh_matches_oracle_bit_exact(lib, n):
+    rng = np.random.default_rng(n + 5)
+    p = rng.random(n) ** 3
+    if n > 4:
+        p[rng.integers(0, n, n // 4)] = 1.0
+        p[rng.integers(0, n, n // 50 + 1)] = np.nan
+        p[rng.integers(0, n, n // 10)] = p[rng.integers(0, n, n // 10)]  # ties
+        p[rng.integers(0, n, 2)] = 0.0
+    for T in (max(n // 3, 1), 10 * n + 7):
+        got, carry, ns = gpu_bh(lib, p, T)
+        want = O.benjamini_hochberg(p, T)
+        assert np.array_equal(got, want, equal_nan=True)
+        assert ns == int(np.sum(p < 1.0))
+        if ns:
+            assert carry == np.nanmax(want[p < 1.0])
+
+
+def test_bh_chained_partitions(lib):
+    """rank_offset / carry_in: q of a key range computed separately equals the global result (multi-GPU contract)."""
+    rng = np.random.default_rng(99)
+    p = rng.random(300_000) ** 2
+    T = 1_000_000
+    want = O.benjamini_hochberg(p, T)
+    cut = np.quantile(p, 0.37)
+    lo, hi = p < cut, p >= cut
+    q_lo, carry, ns = gpu_bh(lib, p[lo], T)
+    q_hi, _, _ = gpu_bh(lib, p[hi], T, rank_offset=ns, carry_in=carry)
+    assert np.array_equal(q_lo, want[lo]) and np.array_equal(q_hi, want[hi])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,noise", [(5, 0.0), (300, 0.0), (300, 0.3), (1024, 1.0), (5000, 0.05), (50_000, 0.2)])
+def test_spline_table(lib, m, noise):
+    from scipy.interpolate import UnivariateSpline
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(m)
+    res = 10000
+    xk = np.sort(rng.uniform(2e4, 2e8, 60))
+    yk = 1e-3 * (xk / 1e4) ** -1.1 * np.exp(noise * rng.normal(size=60))   # noisy decay -> PAVA has work to do
+    ius = UnivariateSpline(xk, yk, s=min(yk) ** 2)
+    t, c, k = ius._eval_args
+    D = 21000
+    slots = np.sort(rng.choice(np.arange(D), size=min(m, D), replace=False))
+    sx = slots * res
+    sx = sx[(sx >= xk.min()) & (sx <= xk.max())].astype(np.int64)
+    mm = len(sx)
+    splineY = ius(sx)
+    want = IsotonicRegression(increasing=False).fit_transform(sx, splineY)
+    tc = dev(np.concatenate([t, c]))
+    table = torch.empty(mm, dtype=torch.float64, device=DEV)
+    lut = torch.empty(D, dtype=torch.float64, device=DEV)
+    wsb = int(lib.fhc_spline_workspace_bytes(mm))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    nt = len(t)
+    dsx = dev(sx)
+    check(lib.fhc_spline_table(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(dsx), mm, float(xk.min()), float(xk.max()),
+                               res, dptr(table), dptr(lut), D, dptr(ws), wsb, stream()))
+    torch.cuda.synchronize()
+    got = table.cpu().numpy()
+    assert np.all(np.diff(got) <= 0)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-25), np.max(np.abs(got - want) / np.abs(want))
+    # lookup semantics of fithic/fithic.py:1066-1068
+    dl = np.clip(np.arange(D, dtype=np.float64) * res, xk.min(), xk.max())
+    idx = np.minimum(np.searchsorted(sx.astype(np.float64), dl, side="left"), mm - 1)
+    assert np.array_equal(lut.cpu().numpy(), got[idx])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K5
+# ---------------------------------------------------------------------------------------------------------------------
+def test_outlier_bin_decrements(lib):
+    rng = np.random.default_rng(8)
+    n = 500_003
+    m1 = rng.integers(0, 10_000_000, n).astype(np.int32)
+    m2 = rng.integers(0, 10_000_000, n).astype(np.int32)
+    outl = ((rng.random(n) < 0.02) * rng.integers(1, 4, n)).astype(np.uint8)
+    ub = np.sort(rng.choice(np.arange(1, 6_000_000), 99, replace=False)).astype(np.int64)  # last bin clamps
+    dec = torch.empty(len(ub), dtype=torch.int64, device=DEV)
+    bufs = [dev(m1), dev(m2), dev(outl), dev(ub)]
+    check(lib.fhc_outlier_bin_decrements(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), n, dptr(bufs[3]), len(ub),
+                                         dptr(dec), stream()))
+    torch.cuda.synchronize()
+    d = np.abs(m1.astype(np.int64) - m2.astype(np.int64))
+    b = np.minimum(np.searchsorted(ub, d, side="left"), len(ub) - 1)
+    want = np.zeros(len(ub), dtype=np.int64)
+    np.add.at(want, b, outl.astype(np.int64))
+    assert np.array_equal(dec.cpu().numpy(), want)
