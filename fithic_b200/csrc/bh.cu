@@ -13,6 +13,8 @@
 // Every kernel reads the number of sorted elements from device memory, so the whole K4 is enqueued without a host sync.
 // HBM-bound: 16 algorithmic bytes per contact (read p, write q); the LSD passes move (8+12+12) B per element per pass.
 #define FHC_PROFILE_STREAM st
+#include <string.h>
+
 #include "common.cuh"
 
 namespace fhc {
@@ -350,13 +352,13 @@ __global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilem
 
 __global__ void __launch_bounds__(kSortThreads)
 bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, const u64 *d_n, double T,
-                  long long rank_offset, const double *__restrict__ tilepre, double *__restrict__ q) {
+                  long long rank_offset, const double *__restrict__ tilepre, double floor_in, double *__restrict__ q) {
     __shared__ double sw[kSortWarps];
     const long long n = (long long)*d_n;
     const long long base = (long long)blockIdx.x * kSortTile;
     if (base >= n) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double carry = tilepre[blockIdx.x];
+    double carry = fmax(tilepre[blockIdx.x], floor_in);
     for (int r = 0; r < kSortIPT; ++r) {
         const long long i = base + r * kSortThreads + threadIdx.x;
         const bool valid = i < n;
@@ -502,19 +504,11 @@ static size_t bh_ws_layout(int64_t n, char *base, BhWs *ws) {
 
 extern "C" size_t fhc_bh_workspace_bytes(int64_t n) { return fhc::bh_ws_layout(n, nullptr, nullptr); }
 
-extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
-                              double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes,
-                              void *stream) {
+// compaction + sort + tile maxima + tile scan: everything of K4 that does not need the running max of smaller keys held
+// by other GPUs.  carry_out receives max(carry_in, every bh value of this call).
+static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                      double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st) {
     using namespace fhc;
-    FHC_REQUIRE(n >= 0 && n < (1ll << 32), FHC_E_INVALID, "fhc_bh_qvalues: need 0 <= n < 2^32 (got %lld)", (long long)n);
-    FHC_REQUIRE(workspace != nullptr, FHC_E_INVALID, "fhc_bh_qvalues: null workspace");
-    FHC_REQUIRE(workspace_bytes >= fhc_bh_workspace_bytes(n), FHC_E_WORKSPACE,
-                "fhc_bh_qvalues: workspace of %zu bytes, need %zu", workspace_bytes, fhc_bh_workspace_bytes(n));
-    FHC_REQUIRE(n == 0 || (p && q && p != q), FHC_E_INVALID, "fhc_bh_qvalues: p and q must be distinct non-null arrays");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    FHC_PROFILE_ENTRY(st);
-    BhWs ws;
-    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
     FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, sizeof(u64), st));
     const int ntiles = (int)ws.sort.ntiles;
     if (n > 0) {
@@ -530,9 +524,232 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
     bh_tilescan_kernel<<<1, kScanThreads, 0, st>>>(ws.tilemax, n > 0 ? ntiles : 0, carry_in, carry_out, ws.d_n,
                                                    reinterpret_cast<u64 *>(n_sorted_out));
     FHC_LAUNCH_CHECK("bh_tilescan_kernel");
+    return FHC_OK;
+}
+
+static int bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, const fhc::BhWs &ws,
+                     cudaStream_t st) {
+    using namespace fhc;
     if (n > 0) {
-        bh_scatter_kernel<<<ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset, ws.tilemax, q);
+        bh_scatter_kernel<<<(int)ws.sort.ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
+                                                                        ws.tilemax, floor_in, q);
         FHC_LAUNCH_CHECK("bh_scatter_kernel");
     }
+    return FHC_OK;
+}
+
+static int bh_check_args(const char *who, const double *p, int64_t n, double *q, void *workspace, size_t workspace_bytes) {
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32), FHC_E_INVALID, "%s: need 0 <= n < 2^32 (got %lld)", who, (long long)n);
+    FHC_REQUIRE(workspace != nullptr, FHC_E_INVALID, "%s: null workspace", who);
+    FHC_REQUIRE(workspace_bytes >= fhc_bh_workspace_bytes(n), FHC_E_WORKSPACE, "%s: workspace of %zu bytes, need %zu", who,
+                workspace_bytes, fhc_bh_workspace_bytes(n));
+    FHC_REQUIRE(n == 0 || (p && q && p != q), FHC_E_INVALID, "%s: p and q must be distinct non-null arrays", who);
+    return FHC_OK;
+}
+
+extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                              double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    using namespace fhc;
+    int rc = bh_check_args("fhc_bh_qvalues", p, n, q, workspace, workspace_bytes);
+    if (rc != FHC_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    BhWs ws;
+    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
+    rc = bh_prepare(p, n, T, rank_offset, carry_in, q, carry_out, n_sorted_out, ws, st);
+    if (rc != FHC_OK) return rc;
+    return bh_finish(n, T, rank_offset, 0.0, q, ws, st);  // carry_in is already folded into the tile prefixes
+}
+
+extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double *q, double *local_max_out,
+                              int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    int rc = bh_check_args("fhc_bh_prepare", p, n, q, workspace, workspace_bytes);
+    if (rc != FHC_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    BhWs ws;
+    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
+    return bh_prepare(p, n, T, rank_offset, 0.0, q, local_max_out, n_sorted_out, ws, st);
+}
+
+extern "C" int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32) && workspace != nullptr && workspace_bytes >= fhc_bh_workspace_bytes(n),
+                FHC_E_INVALID, "fhc_bh_finish: bad n / workspace");
+    FHC_REQUIRE(n == 0 || q != nullptr, FHC_E_INVALID, "fhc_bh_finish: null q");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    BhWs ws;
+    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
+    return bh_finish(n, T, rank_offset, floor_in, q, ws, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// range partitioning of p-values over GPUs (multi-GPU BH): sample, count, scatter, gather back
+// ---------------------------------------------------------------------------------------------------------------------
+namespace fhc {
+
+constexpr int kMaxParts = 64;
+
+struct Splitters {
+    u64 key[kMaxParts];  // part r holds keys in [key[r-1], key[r]); key[nparts-1] unused
+    int nparts;
+};
+
+__device__ __forceinline__ int part_of(u64 k, const Splitters &sp) {
+    int r = 0;
+    for (int i = 0; i < sp.nparts - 1; ++i) r += (k >= sp.key[i]) ? 1 : 0;
+    return r;
+}
+
+__global__ void bh_sample_kernel(const double *__restrict__ p, long long n, long long stride, long long nsamples,
+                                 u64 *__restrict__ keys) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsamples) return;
+    const long long i = s * stride;
+    u64 k = ~0ull;  // "no sample": sorts last
+    if (i < n) {
+        const double v = p[i];
+        if (!(v == 1.0) && !isnan(v)) k = key_of(v);
+    }
+    keys[s] = k;
+}
+
+__global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__restrict__ p, long long n, const Splitters sp,
+                                                           u64 *__restrict__ counts) {
+    __shared__ u32 local[kMaxParts];
+    if (threadIdx.x < kMaxParts) local[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double v = __ldcs(p + i);
+        if (!(v == 1.0) && !isnan(v)) atomicAdd(&local[part_of(key_of(v), sp)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < sp.nparts && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)local[threadIdx.x]);
+}
+
+// p -> send buffer grouped by destination part (order inside a part is arbitrary: the receiver sorts); idx[j] = source line
+// of send[j]; q gets 1.0 / NaN for the p-values that are not ranked.  cursors[r] must start at the first slot of part r.
+__global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__restrict__ p, long long n, const Splitters sp,
+                                                             u64 *cursors, double *__restrict__ send,
+                                                             u32 *__restrict__ idx, double *__restrict__ q) {
+    __shared__ u32 cnt[kMaxParts];
+    __shared__ u64 base[kMaxParts];
+    for (long long b0 = (long long)blockIdx.x * 256; b0 < n; b0 += (long long)gridDim.x * 256) {
+        if (threadIdx.x < kMaxParts) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const long long i = b0 + threadIdx.x;
+        int part = -1;
+        u32 slot = 0;
+        double v = 0.0;
+        if (i < n) {
+            v = __ldcs(p + i);
+            if (v == 1.0)
+                q[i] = 1.0;
+            else if (isnan(v))
+                q[i] = v;
+            else {
+                part = part_of(key_of(v), sp);
+                slot = atomicAdd(&cnt[part], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < sp.nparts) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (u64)cnt[threadIdx.x]) : 0;
+        __syncthreads();
+        if (part >= 0) {
+            const u64 dst = base[part] + slot;
+            send[dst] = v;
+            idx[dst] = (u32)i;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void scatter_f64_kernel(const double *__restrict__ src, const u32 *__restrict__ idx, long long n,
+                                   double *__restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = src[i];
+}
+
+static int make_splitters(const uint64_t *splitter_keys, int nparts, Splitters *sp) {
+    FHC_REQUIRE(nparts >= 1 && nparts <= kMaxParts, FHC_E_INVALID, "need 1 <= nparts <= %d (got %d)", kMaxParts, nparts);
+    FHC_REQUIRE(nparts == 1 || splitter_keys != nullptr, FHC_E_INVALID, "null splitters");
+    sp->nparts = nparts;
+    for (int i = 0; i < nparts - 1; ++i) {
+        sp->key[i] = splitter_keys[i];
+        FHC_REQUIRE(i == 0 || sp->key[i] >= sp->key[i - 1], FHC_E_INVALID, "splitters must be ascending");
+    }
+    return FHC_OK;
+}
+
+}  // namespace fhc
+
+extern "C" int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, uint64_t *keys_out, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && nsamples > 0 && keys_out != nullptr, FHC_E_INVALID, "fhc_bh_sample_keys: bad arguments");
+    FHC_REQUIRE(n == 0 || p != nullptr, FHC_E_INVALID, "fhc_bh_sample_keys: null p");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    const long long stride = n > nsamples ? n / nsamples : 1;
+    bh_sample_kernel<<<(unsigned int)((nsamples + 255) / 256), 256, 0, st>>>(p, n, stride, nsamples,
+                                                                            reinterpret_cast<u64 *>(keys_out));
+    FHC_LAUNCH_CHECK("bh_sample_kernel");
+    return FHC_OK;
+}
+
+extern "C" uint64_t fhc_bh_key_of(double p) {  // host copy of the order-preserving key (for choosing splitters)
+    uint64_t b;
+    memcpy(&b, &p, sizeof(b));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+extern "C" int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
+                                      uint64_t *counts, void *stream) {
+    using namespace fhc;
+    Splitters sp;
+    const int rc = make_splitters(splitter_keys, nparts, &sp);
+    if (rc != FHC_OK) return rc;
+    FHC_REQUIRE(n >= 0 && counts != nullptr && (n == 0 || p != nullptr), FHC_E_INVALID, "fhc_bh_partition_count: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    FHC_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * nparts, st));
+    if (n == 0) return FHC_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    bh_part_count_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, reinterpret_cast<u64 *>(counts));
+    FHC_LAUNCH_CHECK("bh_part_count_kernel");
+    return FHC_OK;
+}
+
+extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
+                                        uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream) {
+    using namespace fhc;
+    Splitters sp;
+    const int rc = make_splitters(splitter_keys, nparts, &sp);
+    if (rc != FHC_OK) return rc;
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32) && cursors != nullptr, FHC_E_INVALID, "fhc_bh_partition_scatter: bad arguments");
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(p && send && idx && q, FHC_E_INVALID, "fhc_bh_partition_scatter: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, reinterpret_cast<u64 *>(cursors), send, idx, q);
+    FHC_LAUNCH_CHECK("bh_part_scatter_kernel");
+    return FHC_OK;
+}
+
+extern "C" int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n, double *dst, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0, FHC_E_INVALID, "fhc_scatter_f64: n < 0");
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(src && idx && dst, FHC_E_INVALID, "fhc_scatter_f64: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    scatter_f64_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(src, idx, n, dst);
+    FHC_LAUNCH_CHECK("scatter_f64_kernel");
     return FHC_OK;
 }

@@ -155,6 +155,8 @@ class Engine:
             if len(self.frags.max_mid):
                 mx = max(mx, int(self.frags.max_mid.max()))
             self.D = mx // self.st.resolution + 2
+            if self.dist is not None:
+                self.D = self.dist.max_int(self.D)  # the histogram is all-reduced: every rank needs the same length
         return self.D
 
     # ------------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ def read_contacts(path):
     """contactCounts file: chr1 mid1 chr2 mid2 count, whitespace separated (fithic/fithic.py:413-417)."""
     df = pd.read_csv(path, sep=r"\s+", header=None, names=["c1", "m1", "c2", "m2", "n"], engine="c",
                      dtype={"c1": str, "c2": str, "m1": np.int64, "m2": np.int64, "n": np.float64},
-                     compression="gzip")
+                     compression="gzip", float_precision="round_trip")
     chroms = list(pd.unique(pd.concat([df.c1, df.c2], ignore_index=True)))
     if len(chroms) >= (1 << 16):
         raise ValueError("more than 65535 chromosome names")
@@ -61,7 +61,8 @@ def read_biases(path, chroms, resolution, biasLowerBound, biasUpperBound):
     """bias file: chr mid bias (fithic/fithic.py:798-837).  bias < tL, NaN or > tU -> -1; FIRST occurrence of a
     (chr, mid) wins.  Returns (Biases, log lines); `chroms` is extended in place."""
     df = pd.read_csv(path, sep=r"\s+", header=None, engine="c", names=["c", "m", "b"],
-                     dtype={"c": str, "m": np.int64, "b": np.float64}, compression="gzip")
+                     dtype={"c": str, "m": np.int64, "b": np.float64}, compression="gzip",
+                     float_precision="round_trip")  # Python float() semantics, like the reference
     cid = {c: i for i, c in enumerate(chroms)}
     for c in pd.unique(df.c):
         if c not in cid:

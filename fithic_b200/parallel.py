@@ -1,0 +1,204 @@
+"""Multi-GPU execution: one process per GPU, contacts sharded by chromosome, torch.distributed (NCCL over NVLink /
+NVSwitch) for the two exchange steps of a spline pass.
+
+  exchange 1  all-reduce (sum) of the distance histogram + observed totals (<= 400 kB, latency bound).  Every rank then
+              runs the identical host binning / spline fit on identical inputs, so tables are bit-identical everywhere.
+  exchange 2  global BH: p-values are range-partitioned by value so that rank r ranks one contiguous key range:
+              sample keys -> all-gather -> splitters; count per part -> all-gather -> offsets; scatter into send
+              buffers (kernel) -> all-to-all(v) of p -> local compaction/sort/tile maxima (kernels) -> all-gather of the
+              per-range maxima (carry) -> scan + scatter (kernels) -> all-to-all(v) of q back -> scatter to line order.
+
+The collective choreography only needs a small "ops" interface (sample / count / scatter / prepare / finish / ...),
+implemented by the CUDA library in production (CudaOps) -- world_size-2 gloo tests drive the same choreography with a
+numpy stand-in to check the bookkeeping (offsets, splits, carries) without a GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import check, dptr
+
+_U64_NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def choose_splitters(sorted_sample_keys, nparts):
+    """Splitter keys at the k/nparts quantiles of the valid (non-UINT64_MAX) sample keys; ascending, length nparts-1."""
+    s = np.asarray(sorted_sample_keys, dtype=np.uint64)
+    s = s[s != _U64_NONE]
+    if len(s) == 0:
+        return np.zeros(max(nparts - 1, 0), dtype=np.uint64)
+    pos = (np.arange(1, nparts) * len(s)) // nparts
+    return s[np.minimum(pos, len(s) - 1)].astype(np.uint64)
+
+
+def exchange_plan(count_matrix, rank):
+    """count_matrix[src, part] = rankable p-values src sends to part.  Returns (send_splits, recv_splits, rank_offset,
+    send_offsets) for `rank`: rank_offset = number of keys in all lower parts (global rank of this part's first key)."""
+    cm = np.asarray(count_matrix, dtype=np.int64)
+    send = cm[rank].tolist()
+    recv = cm[:, rank].tolist()
+    rank_offset = int(cm[:, :rank].sum())
+    send_off = np.concatenate([[0], np.cumsum(cm[rank])[:-1]]).astype(np.int64)
+    return send, recv, rank_offset, send_off
+
+
+def carry_floor(local_maxima, rank):
+    """Running max handed to `rank`: the largest bh value of every lower key range (0 for the first, myStats.py:30)."""
+    m = 0.0
+    for v in list(local_maxima)[:rank]:
+        m = max(m, float(v))
+    return m
+
+
+class CudaOps:
+    """The kernels of libfithic_b200.so behind the ops interface (device tensors in, device tensors out)."""
+
+    def __init__(self, device):
+        self.lib = _capi.load()
+        self.device = device
+        self._ws = None
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, n, dtype):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
+
+    def sample_keys(self, p, nsamples):
+        keys = self.empty(nsamples, torch.int64)
+        check(self.lib.fhc_bh_sample_keys(dptr(p), p.numel(), nsamples, dptr(keys), self._stream()))
+        return keys
+
+    def sort_keys(self, keys):
+        n = keys.numel()
+        vals = self.empty(n, torch.int32)
+        ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+        wsb = int(self.lib.fhc_sort_workspace_bytes(n))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        check(self.lib.fhc_sort_pairs_u64(dptr(keys), dptr(vals), dptr(ko), dptr(vo), n, dptr(ws), wsb, self._stream()))
+        return ko
+
+    def partition_count(self, p, splitters):
+        nparts = len(splitters) + 1
+        counts = self.empty(nparts, torch.int64)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        check(self.lib.fhc_bh_partition_count(dptr(p), p.numel(), dptr(sp), nparts, dptr(counts), self._stream()))
+        return counts
+
+    def partition_scatter(self, p, splitters, send_offsets, q):
+        nparts = len(splitters) + 1
+        n = p.numel()
+        cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
+        send = self.empty(n, torch.float64)
+        idx = self.empty(n, torch.int32)
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, dptr(cursors), dptr(send), dptr(idx),
+                                                dptr(q), self._stream()))
+        return send, idx
+
+    def _bh_ws(self, n):
+        wsb = int(self.lib.fhc_bh_workspace_bytes(n))
+        if self._ws is None or self._ws.numel() < wsb:
+            self._ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        return self._ws, wsb
+
+    def bh_prepare(self, p, T, rank_offset, q):
+        n = p.numel()
+        ws, wsb = self._bh_ws(n)
+        local_max = self.empty(1, torch.float64)
+        check(self.lib.fhc_bh_prepare(dptr(p), n, float(T), int(rank_offset), dptr(q), dptr(local_max), None, dptr(ws),
+                                      wsb, self._stream()))
+        return local_max
+
+    def bh_finish(self, n, T, rank_offset, floor, q):
+        ws, wsb = self._bh_ws(n)
+        check(self.lib.fhc_bh_finish(n, float(T), int(rank_offset), float(floor), dptr(q), dptr(ws), wsb, self._stream()))
+
+    def scatter(self, src, idx, dst):
+        check(self.lib.fhc_scatter_f64(dptr(src), dptr(idx), src.numel(), dptr(dst), self._stream()))
+
+
+class DistCtx:
+    """Collective choreography of one rank.  `ops` defaults to the CUDA library."""
+
+    def __init__(self, device=None, ops=None, group=None, samples_per_rank=1 << 16):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device
+        self.ops = ops if ops is not None else CudaOps(device)
+        self.samples_per_rank = samples_per_rank
+
+    # ---- exchange 1 -------------------------------------------------------------------------------------------------
+    def allreduce_hist(self, hist, present, scal):
+        """Sum the per-distance histogram, the 'distance seen' bits and the totals over ranks (in place).
+        One all-reduce(sum) of [hist | totals | seen flags] and one all-reduce(max) for the largest count."""
+        D = hist.numel()
+        slots = torch.arange(D, device=hist.device)
+        flags = (present.to(torch.int64)[slots >> 5] >> (slots & 31)) & 1
+        mx = scal[_capi.S_MAX_COUNT:_capi.S_MAX_COUNT + 1].clone()
+        buf = torch.cat([hist, scal, flags])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        hist.copy_(buf[:D])
+        scal.copy_(buf[D:D + scal.numel()])
+        scal[_capi.S_MAX_COUNT] = mx[0]
+        seen = buf[D + scal.numel():] > 0
+        # re-pack the seen flags into the uint32 bitmap layout of fhc_hist_distance
+        pad = (-D) % 32
+        bits = torch.cat([seen, torch.zeros(pad, dtype=torch.bool, device=seen.device)]).view(-1, 32).to(torch.int64)
+        weights = (1 << torch.arange(32, device=seen.device, dtype=torch.int64))
+        words = (bits * weights).sum(dim=1)
+        words = torch.where(words >= (1 << 31), words - (1 << 32), words).to(torch.int32)
+        present.copy_(words)
+
+    def max_int(self, v):
+        t = torch.tensor([int(v)], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def allreduce_small(self, arr):
+        """Sum a small host int64 array over ranks (per-bin outlier decrements)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device if self.device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    # ---- exchange 2 -------------------------------------------------------------------------------------------------
+    def _all_gather(self, t):
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def global_bh(self, engine, p, T, q=None):
+        """q-values of the union of every rank's p-values (myStats.benjamini_hochberg_correction over the whole file)."""
+        ops, G, r = self.ops, self.world, self.rank
+        n = p.numel()
+        if q is None:
+            q = engine._tensor("q", n, torch.float64) if engine is not None else ops.empty(n, torch.float64)
+        # 1. splitters from a sorted sample of everybody's keys
+        sample = ops.sample_keys(p, self.samples_per_rank)
+        allsamp = ops.sort_keys(self._all_gather(sample))
+        splitters = choose_splitters(allsamp.cpu().numpy().view(np.uint64), G)
+        # 2. how many keys go where
+        counts = ops.partition_count(p, splitters)
+        cm = self._all_gather(counts).cpu().numpy().reshape(G, G)
+        send_splits, recv_splits, rank_offset, send_off = exchange_plan(cm, r)
+        # 3. group by destination, exchange
+        send, idx = ops.partition_scatter(p, splitters, send_off, q)
+        n_send, n_recv = int(sum(send_splits)), int(sum(recv_splits))
+        recv = ops.empty(n_recv, torch.float64)
+        dist.all_to_all_single(recv, send[:n_send], recv_splits, send_splits, group=self.group)
+        # 4. rank my key range; the carry from lower ranges arrives between the two halves
+        q_recv = ops.empty(n_recv, torch.float64)
+        local_max = ops.bh_prepare(recv, T, rank_offset, q_recv)
+        floor = carry_floor(self._all_gather(local_max).cpu().numpy(), r)
+        ops.bh_finish(n_recv, T, rank_offset, floor, q_recv)
+        # 5. send the q-values home and put them back in line order
+        q_back = ops.empty(n_send, torch.float64)
+        dist.all_to_all_single(q_back, q_recv, send_splits, recv_splits, group=self.group)
+        ops.scatter(q_back, idx[:n_send], q)
+        self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor)
+        return q

@@ -149,6 +149,30 @@ size_t fhc_bh_workspace_bytes(int64_t n);
 int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
                    double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same in two halves, for a caller that has to fetch the running max of smaller keys from other GPUs in between:
+ * prepare = compaction + sort + per-tile maxima (local_max_out [dev] = max bh value of this call, 0 if none);
+ * finish  = scan + scatter with floor_in = max over the key ranges below this one.  Same workspace for both calls. */
+int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double *q, double *local_max_out,
+                   int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
+int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* Range partitioning of p-values over `nparts` GPUs for the global correction: part r receives the
+ * rankable p-values (p != 1, not NaN) whose order-preserving key lies in [splitter[r-1], splitter[r]).
+ *   fhc_bh_sample_keys      keys of nsamples evenly strided p-values (UINT64_MAX where the sample is not rankable)
+ *   fhc_bh_key_of           the key of one p-value (host)
+ *   fhc_bh_partition_count  counts[r] = rankable p-values of part r
+ *   fhc_bh_partition_scatter send[] = p-values grouped by part (cursors[r] [dev] = first slot of part r on entry),
+ *                           idx[j] = line of send[j]; q[i] = 1.0 / NaN is written for the p-values that are not ranked
+ *   fhc_scatter_f64         dst[idx[j]] = src[j]  (q-values coming back from the owning GPU) */
+int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, uint64_t *keys_out, void *stream);
+uint64_t fhc_bh_key_of(double p);
+int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, uint64_t *counts,
+                           void *stream);
+int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
+                             uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream);
+int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n, double *dst, void *stream);
+
 /* Device radix sort of 64-bit keys with 32-bit payloads (ascending, stable), the sort inside K4, exposed for tests
  * and for the multi-GPU range-partitioned BH.  Sorted data ends in keys_out/vals_out; *_in are clobbered.
  * workspace: fhc_sort_workspace_bytes(n). */

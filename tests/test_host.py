@@ -1,0 +1,201 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/fithic_b200.h declares, the host-side stages are bit
+exact against the oracle, the table arithmetic (host build of the device source) matches libm / cephes, text I/O."""
+import ctypes
+import gzip
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fithic_b200 import _capi, synth
+from fithic_b200 import io as fio
+from fithic_b200.engine import Settings, calculate_probabilities, fit_spline, frag_pairs, make_bins
+from oracle import fithic_oracle as O
+from tests.util import GOLDEN_CASES, load_golden, oracle_inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "fithic_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fhc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    raw = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "library does not export %s" % name
+    assert declared == set(_capi._SIGNATURES), declared ^ set(_capi._SIGNATURES)
+    assert lib.fhc_abi_version() == _capi.FHC_ABI_VERSION
+
+
+def test_errors_are_reported_not_swallowed(lib):
+    rc = lib.fhc_host_make_bins(None, None, 5, 10, 100, None, None, None)
+    assert rc == _capi.FHC_E_INVALID
+    assert b"fhc_host_make_bins" in lib.fhc_last_error()
+    with pytest.raises(_capi.FithicB200Error):
+        _capi.check(rc)
+    # device entry points validate their arguments before touching the GPU
+    assert lib.fhc_pvalues(7, None, None, None, None, 1, None, None, None, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
+                           None, 0, None, 0, None, 0.0, None, None, None, None) == _capi.FHC_E_INVALID
+    assert lib.fhc_lbeta_table(1 << 31, ctypes.c_void_p(16), 4, None) == _capi.FHC_E_RANGE
+
+
+def test_no_cpu_fallback_without_cuda():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from fithic_b200.engine import Engine, Fragments
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(Settings(resolution=10000), Fragments([], np.zeros(0, np.int64), np.zeros(0, np.int64)))
+
+
+def test_log_cr_is_libm_log(lib):
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.integers(1, 1 << 31, 20000).astype(np.float64), np.arange(1, 3000, dtype=np.float64),
+                         (1 << 31) - np.arange(1, 2000, dtype=np.float64)])
+    bad = [x for x in xs if lib.fhc_host_log_cr(float(x)) != math.log(x)]
+    assert not bad, bad[:5]
+
+
+def test_lbeta_is_cephes_lbeta(lib):
+    ol = O._lib()
+    ol.oracle_lbeta.restype = ctypes.c_double
+    ol.oracle_lbeta.argtypes = [ctypes.c_double, ctypes.c_double]
+    rng = np.random.default_rng(4)
+    for N in (172, 1000, 4219169, 10 ** 8, 9 * 10 ** 8, (1 << 31) - 1):
+        cs = list(range(1, 200)) + [int(c) for c in rng.integers(1, min(N, 3 * 10 ** 6), 1500)]
+        for c in cs:
+            if c > N:
+                continue
+            assert lib.fhc_host_lbeta(float(c), float(N - c + 1)) == ol.oracle_lbeta(float(c), float(N - c + 1)), (N, c)
+    # N + 1 <= MAXGAM: cephes divides Gamma values; the lgam form used here agrees to ~1e-14
+    for c in range(1, 100):
+        a, b = lib.fhc_host_lbeta(float(c), float(100 - c + 1)), ol.oracle_lbeta(float(c), float(100 - c + 1))
+        assert abs(a - b) <= 1e-13 * abs(b)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_host_stages_bit_exact_against_reference_fixture(lib, name):
+    """make_bins / frag_pairs / calculate_probabilities / fit_spline on the reference's own histogram."""
+    contacts, frags, biases, st, ref, _ = load_golden(name)
+    r = ref[0]
+    bins = make_bins(lib, r["dists"], r["sums"], st.noOfBins, r["N"])
+    fp = frag_pairs(lib, frags, st, bins)
+    assert bins["n"] == len(r["bins"])
+    for i, b in enumerate(r["bins"]):
+        assert (int(bins["lb"][i]), int(bins["ub"][i]), int(bins["sumcc"][i]), int(bins["pairs"][i])) == \
+            (b["lb"], b["ub"], b["sumcc"], b["pairs"])
+        assert float(bins["sumdist"][i]) == b["sumdist"]
+    assert fp["possibleIntraInRangeCount"] == r["possibleIntraInRangeCount"]
+    x, y = calculate_probabilities(bins, r["N"])
+    if r["splineX"] is not None:
+        xs, ys, tck = fit_spline(x, y)
+        assert xs == list(r["x"]) and ys == list(r["y"])
+
+
+def test_make_bins_known_answers(lib):
+    """SURVEY.md Appendix B (outputs of the unmodified makeBinsFromInteractions)."""
+    def run(d, nb, N):
+        dists = np.array(sorted(d), dtype=np.int64)
+        sums = np.array([d[k] for k in sorted(d)], dtype=np.int64)
+        b = make_bins(lib, dists, sums, nb, N)
+        return [((int(b["lb"][i]), int(b["ub"][i])), int(b["sumcc"][i])) for i in range(b["n"])]
+    assert run({0: 50, 10: 30, 20: 5, 30: 5, 40: 5, 50: 3, 60: 1, 70: 1}, 4, 100) == \
+        [((0, 0), 50), ((1, 10), 30), ((11, 30), 10), ((31, 70), 10)]
+    assert run({10 * k: 10 for k in range(10)}, 3, 100) == [((0, 30), 40), ((31, 60), 30), ((61, 90), 30)]
+    assert run({0: 1, 10: 1, 20: 1}, 5, 3) == [((0, 0), 1), ((1, 10), 1), ((11, 20), 1)]
+    assert run({0: 7, 10: 0, 20: 3, 30: 0}, 2, 10) == [((0, 0), 7), ((1, 20), 3)]  # distance 30 is dropped
+    assert run({}, 5, 0) == []
+
+
+def test_frag_pairs_quirks(lib):
+    """x2 in-range count, negative npairs with unmappable loci, L/U window."""
+    from fithic_b200.engine import Fragments
+    st = Settings(resolution=10)
+    frags = Fragments(["b", "a"], np.array([3, 5], dtype=np.int64), np.array([45, 65], dtype=np.int64))
+    bins = dict(n=2, lb=np.array([0, 11], np.int64), ub=np.array([10, 40], np.int64), sumcc=np.array([1, 1], np.int64))
+    fp = frag_pairs(lib, frags, st, bins)
+    # chr a: n=5, max mid 65 -> dists 0..60: npairs 5,4,3,2,1,0,-1 ; chr b: n=3, max mid 45 -> dists 0..40: 3,2,1,0,-1
+    # bin 0 = [0, 10], bin 1 = [11, 40] and everything beyond (clamped to the last bin)
+    assert list(bins["pairs"]) == [(5 + 4) + (3 + 2), (3 + 2 + 1 + 0 - 1) + (1 + 0 - 1)]
+    assert fp["possibleIntraInRangeCount"] == 2 * ((5 + 4 + 3 + 2 + 1 + 0 - 1) + (3 + 2 + 1 + 0 - 1))
+    # the same through the oracle's sequential restatement
+    obins = [dict(lb=0, ub=10, pairs=0, sumcc=1, sumdist=0.0, pairs7=0), dict(lb=11, ub=40, pairs=0, sumcc=1, sumdist=0.0,
+                                                                              pairs7=0)]
+    fchr = np.array([0] * 3 + [1] * 5)
+    fmid = np.array([25, 35, 45, 25, 35, 45, 55, 65])
+    out = O.generate_frag_pairs(fchr, fmid, np.ones(8, dtype=np.int64), ["b", "a"], O.Settings(resolution=10), obins, 0)
+    assert [b["pairs"] for b in obins] == list(bins["pairs"])
+    assert [b["sumdist"] for b in obins] == list(bins["sumdist"])
+    assert out[3] == fp["possibleIntraInRangeCount"]
+    assert fp["noOfFrags"] == 8 and fp["possibleInterAllCount"] == 15.0
+
+
+def test_io_round_trip_and_bias_semantics(tmp_path):
+    contacts, frags, biases, raw = synth.make_intra(5000, 100000, 5, chroms=["chr21", "chr22"], with_bias=True,
+                                                    inter_fraction=0.2)
+    cpath, fpath, bpath = synth.write_inputs(str(tmp_path), contacts, frags, 100000, raw, biases)
+    c2 = fio.read_contacts(cpath)
+    names = c2.chroms
+    m = {n: contacts.chroms.index(n) for n in names}
+    remap = np.array([m[n] for n in names])
+    assert np.array_equal(c2.mid1, contacts.mid1) and np.array_equal(c2.cnt, contacts.cnt)
+    assert np.array_equal(remap[c2.chrs & 0xffff], contacts.chrs & 0xffff)
+    chroms = list(c2.chroms)
+    f2 = fio.read_fragments(fpath, chroms, 1)
+    for i, n in enumerate(f2.chroms):
+        j = frags.chroms.index(n)
+        assert f2.n_mappable[i] == frags.n_mappable[j] and f2.max_mid[i] == frags.max_mid[j]
+    b2, log = fio.read_biases(bpath, chroms, 100000, 0.5, 2.0)
+    for ci, n in enumerate(chroms):
+        j = contacts.chroms.index(n)
+        lo, hi = int(biases.chr_off[j]), int(biases.chr_off[j + 1])
+        a = b2.values[int(b2.chr_off[ci]):int(b2.chr_off[ci + 1])]
+        assert np.array_equal(a, biases.values[lo:hi])
+    assert any("discarded" in line for line in log)
+    # count truncation toward zero and first-occurrence-wins for biases (fithic/fithic.py:415, :831-832)
+    p = tmp_path / "t.gz"
+    with gzip.open(p, "wt") as f:
+        f.write("c1\t5\tc1\t15\t2.9\nc1\t5\tc2\t25\t-1.5\n")
+    c = fio.read_contacts(str(p))
+    assert list(c.cnt) == [2, -1]
+    bp = tmp_path / "b.gz"
+    with gzip.open(bp, "wt") as f:
+        f.write("c1\t5\t0.9\nc1\t5\t1.7\nc1\t15\tnan\nc1\t25\t2.5\nc1\t35\t0.4\n")
+    b, _ = fio.read_biases(str(bp), ["c1"], 10, 0.5, 2.0)
+    assert list(b.values) == [0.9, -1.0, -1.0, -1.0]
+    assert list(fio.lookup_biases(b, np.array([0, 0, 1]), np.array([5, 45, 5]), 10)) == [0.9, -1.0, -1.0]
+
+
+def test_cli_argument_handling(tmp_path, capsys):
+    from fithic_b200 import fithic as cli
+    a = cli.parse_args(["-i", "x.gz", "-f", "y.gz", "-o", str(tmp_path), "-r", "5000", "-p", "0", "-b", "0", "-L", "0",
+                        "-x", "All", "-tL", "0.4"])
+    open(tmp_path / "x.gz", "w").close()
+    open(tmp_path / "y.gz", "w").close()
+    a.intersfile, a.fragsfile = str(tmp_path / "x.gz"), str(tmp_path / "y.gz")
+    st, lib_name = cli.settings_from_args(a)
+    # the reference's falsy-zero idiom: 0 means default (fithic/fithic.py:194-220)
+    assert (st.noOfPasses, st.noOfBins, st.distLowThres, st.allReg, st.biasLowerBound, lib_name) == \
+        (1, 100, 0, True, 0.4, "FitHiC")
+    a.contactType = "bogus"
+    with pytest.raises(SystemExit) as e:
+        cli.settings_from_args(a)
+    assert e.value.code == 2
+    a.contactType = None
+    a.resolution = 0
+    with pytest.raises(SystemExit) as e:
+        cli.settings_from_args(a)
+    assert e.value.code == 2
+
+
+def test_synthetic_generator_is_deterministic():
+    a = synth.make_intra(2000, 100000, 9, chroms=["chr22"], with_bias=True)[0]
+    b = synth.make_intra(2000, 100000, 9, chroms=["chr22"], with_bias=True)[0]
+    assert np.array_equal(a.mid1, b.mid1) and np.array_equal(a.cnt, b.cnt)
+    shards = synth.lpt_shards([int(s) for s in synth.genome(None)[1]], 8)
+    loads = [sum(int(synth.genome(None)[1][i]) for i in s) for s in shards]
+    assert sorted(i for s in shards for i in s) == list(range(24))
+    assert max(loads) / (sum(loads) / 8) < 1.05

@@ -1,0 +1,153 @@
+"""CPU, world_size 2 over gloo: the multi-GPU choreography of fithic_b200/parallel.py (splitters, exchange plan,
+all-to-all sizes, carry between key ranges, histogram all-reduce packing) with a numpy stand-in for the CUDA ops.
+The stand-in exists only in this test; the product's ops are the kernels of libfithic_b200.so (CudaOps)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fithic_b200 import _capi, parallel
+from oracle import fithic_oracle as O
+
+U64_NONE = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def key_of(p):
+    b = np.asarray(p, dtype=np.float64).view(np.uint64)
+    return np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+
+
+class NumpyOps:
+    """Same interface as parallel.CudaOps, numpy on CPU tensors (test double)."""
+
+    def empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype)
+
+    def sample_keys(self, p, nsamples):
+        p = p.numpy()
+        n = len(p)
+        stride = n // nsamples if n > nsamples else 1
+        keys = np.full(nsamples, U64_NONE, dtype=np.uint64)
+        idx = np.arange(nsamples) * stride
+        ok = idx < n
+        v = p[idx[ok]]
+        k = key_of(v)
+        k[(v == 1.0) | np.isnan(v)] = U64_NONE
+        keys[ok] = k
+        return torch.from_numpy(keys.view(np.int64))
+
+    def sort_keys(self, keys):
+        return torch.from_numpy(np.sort(keys.numpy().view(np.uint64)).view(np.int64))
+
+    def _part(self, p, splitters):
+        k = key_of(p)
+        return np.searchsorted(np.asarray(splitters, dtype=np.uint64), k, side="right")
+
+    def partition_count(self, p, splitters):
+        p = p.numpy()
+        ok = ~((p == 1.0) | np.isnan(p))
+        return torch.from_numpy(np.bincount(self._part(p[ok], splitters), minlength=len(splitters) + 1).astype(np.int64))
+
+    def partition_scatter(self, p, splitters, send_offsets, q):
+        p = p.numpy()
+        qn = q.numpy()
+        qn[p == 1.0] = 1.0
+        qn[np.isnan(p)] = np.nan
+        ok = np.nonzero(~((p == 1.0) | np.isnan(p)))[0]
+        part = self._part(p[ok], splitters)
+        order = np.argsort(part, kind="stable")
+        send = np.zeros(len(p))
+        idx = np.zeros(len(p), dtype=np.int32)
+        send[:len(ok)] = p[ok][order]
+        idx[:len(ok)] = ok[order]
+        return torch.from_numpy(send), torch.from_numpy(idx)
+
+    def bh_prepare(self, p, T, rank_offset, q):
+        self._p, self._T = p.numpy().copy(), T
+        order = np.argsort(self._p, kind="stable")
+        bh = np.minimum(self._p[order] * T / (rank_offset + np.arange(1, len(order) + 1)), 1.0)
+        self._order, self._bh = order, bh
+        return torch.tensor([bh.max() if len(bh) else 0.0], dtype=torch.float64)
+
+    def bh_finish(self, n, T, rank_offset, floor, q):
+        run = np.maximum.accumulate(np.concatenate(([floor], self._bh)))[1:]
+        q.numpy()[self._order] = run
+
+    def scatter(self, src, idx, dst):
+        dst.numpy()[idx.numpy()] = src.numpy()
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = parallel.DistCtx(device=None, ops=NumpyOps(), samples_per_rank=2048)
+        rng = np.random.default_rng(123)
+        p_all = rng.random(60_001) ** 3
+        p_all[rng.integers(0, len(p_all), 5000)] = 1.0
+        p_all[rng.integers(0, len(p_all), 300)] = np.nan
+        p_all[rng.integers(0, len(p_all), 4000)] = p_all[rng.integers(0, len(p_all), 4000)]  # ties across ranks
+        T = 250_000
+        cut = 41_000  # uneven shards
+        mine = p_all[:cut] if rank == 0 else p_all[cut:]
+        q = torch.full((len(mine),), -1.0, dtype=torch.float64)
+        ctx.global_bh(None, torch.from_numpy(mine.copy()), float(T), q=q)
+        want = O.benjamini_hochberg(p_all, T)
+        want = want[:cut] if rank == 0 else want[cut:]
+        assert np.array_equal(q.numpy(), want, equal_nan=True), "global BH differs on rank %d" % rank
+        cm = ctx.last_plan["count_matrix"]
+        assert cm.sum() == np.sum(~((p_all == 1.0) | np.isnan(p_all)))
+        assert abs(cm[:, 0].sum() - cm[:, 1].sum()) < 0.1 * cm.sum()  # the sample balances the two key ranges
+
+        # exchange 1: histogram + seen bits + totals
+        D = 70
+        hist = torch.zeros(D, dtype=torch.int64)
+        present = torch.zeros((D + 31) // 32, dtype=torch.int32)
+        scal = torch.zeros(_capi.N_SCALARS, dtype=torch.int64)
+        hist[rank::2] = rank + 1
+        seen = [3, 40] if rank == 0 else [40, 63, 69]
+        words = np.zeros((D + 31) // 32, dtype=np.uint32)
+        for b in seen:
+            words[b >> 5] |= np.uint32(1 << (b & 31))
+        present.copy_(torch.from_numpy(words.view(np.int32)))
+        scal[_capi.S_INTRA_INRANGE_SUM] = 100 + rank
+        scal[_capi.S_MAX_COUNT] = 7 if rank == 0 else 19
+        ctx.allreduce_hist(hist, present, scal)
+        exp = np.zeros(D, dtype=np.int64)
+        exp[0::2] = 1
+        exp[1::2] = 2
+        assert np.array_equal(hist.numpy(), exp)
+        got_bits = np.unpackbits(present.numpy().view(np.uint8), bitorder="little")[:D]
+        assert sorted(np.nonzero(got_bits)[0].tolist()) == [3, 40, 63, 69]
+        assert int(scal[_capi.S_INTRA_INRANGE_SUM]) == 201 and int(scal[_capi.S_MAX_COUNT]) == 19
+        assert ctx.max_int(5 + rank) == 6
+        assert ctx.allreduce_small(np.array([1, 2 + rank])).tolist() == [2, 5]
+        open(os.path.join(tmp, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_choreography(tmp_path):
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_plan_helpers():
+    keys = np.sort(np.concatenate([np.arange(1000, dtype=np.uint64), np.full(24, U64_NONE)]))
+    sp = parallel.choose_splitters(keys, 4)
+    assert sp.tolist() == [250, 500, 750]
+    assert parallel.choose_splitters(np.full(8, U64_NONE), 4).tolist() == [0, 0, 0]
+    cm = np.array([[5, 1, 0], [2, 2, 2], [0, 7, 1]])
+    send, recv, off, soff = parallel.exchange_plan(cm, 1)
+    assert (send, recv, off, soff.tolist()) == ([2, 2, 2], [1, 2, 7], 7, [0, 2, 4])
+    assert parallel.exchange_plan(cm, 0)[2] == 0 and parallel.exchange_plan(cm, 2)[2] == 17
+    assert parallel.carry_floor([0.3, 0.9, 0.5], 0) == 0.0
+    assert parallel.carry_floor([0.3, 0.9, 0.5], 2) == 0.9
+    lib = _capi.load()
+    for v in (0.0, 1e-300, 0.25, 0.5, 0.999999, 1.0, 2.5):
+        assert lib.fhc_bh_key_of(v) == int(key_of([v])[0])

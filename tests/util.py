@@ -88,3 +88,68 @@ def compare_pass(r, o, tol=1e-6, check_ones=True):
     out["expcc"] = rel_err(e, o["expcc"])
     assert out["p"] <= tol and out["q"] <= tol and out["expcc"] <= 1e-12, out
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# golden fixtures (tests/golden/*.npz, generated from the unmodified reference by tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+import json  # noqa: E402
+import os  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["intra_40kb", "intra_bias_LU_p2", "all_bias", "inter_only_bias", "intra_p3"]
+
+
+def load_kat():
+    with open(os.path.join(GOLDEN_DIR, "kat.json")) as f:
+        return json.load(f)
+
+
+def load_golden(name):
+    """-> (Contacts, Fragments, Biases or None, Settings, list of per-pass reference dicts)."""
+    from fithic_b200.engine import Biases, Contacts, Fragments, Settings
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    chroms = [str(c) for c in z["chroms"]]
+    contacts = Contacts(z["mid1"], z["mid2"], z["cnt"], z["chrs"], chroms)
+    frags = Fragments(chroms, z["frag_n"], z["frag_maxmid"])
+    biases = None
+    if "bias_values" in z:
+        biases = Biases(z["bias_values"], z["bias_mids"], z["bias_chr_off"])
+    st = Settings(resolution=int(z["res"]))
+    flags = [str(f) for f in z["flags"]]
+    i = 0
+    while i < len(flags):
+        f, v = flags[i], flags[i + 1]
+        if f == "-b":
+            st.noOfBins = int(v)
+        elif f == "-p":
+            st.noOfPasses = int(v)
+        elif f == "-L":
+            st.distLowThres = int(v)
+        elif f == "-U":
+            st.distUpThres = int(v)
+        elif f == "-x":
+            st.interOnly = v == "interOnly"
+            st.allReg = v == "All"
+        i += 2
+    passes = []
+    for k in range(1, int(z["npasses"]) + 1):
+        pre = "p%d_" % k
+        sc = z[pre + "scalars"]
+        nb = len(z[pre + "bin_lb"])
+        bins = [dict(lb=int(z[pre + "bin_lb"][i]), ub=int(z[pre + "bin_ub"][i]), pairs=int(z[pre + "bin_pairs"][i]),
+                     sumcc=int(z[pre + "bin_sumcc"][i]), sumdist=float(z[pre + "bin_sumdist"][i])) for i in range(nb)]
+        has_spline = (pre + "splineX") in z
+        passes.append(dict(N=int(z[pre + "N"]), T=int(z[pre + "T"]), observedInterAllCount=int(sc[0]),
+                           observedInterAllSum=int(sc[1]), observedIntraAllSum=int(sc[2]),
+                           possibleIntraInRangeCount=int(sc[3]), dists=z[pre + "dists"], sums=z[pre + "sums"], bins=bins,
+                           x=sorted(z[pre + "x"].tolist()) if has_spline else z[pre + "x"].tolist(),
+                           y=[v for _, v in sorted(zip(z[pre + "x"].tolist(), z[pre + "y"].tolist()))]
+                           if has_spline else z[pre + "y"].tolist(),
+                           splineX=z[pre + "splineX"] if has_spline else None,
+                           newSplineY=z[pre + "newSplineY"] if has_spline else None, p=z[pre + "p"], q=z[pre + "q"],
+                           outliersline=z[pre + "outliersline"], outliersdist=z[pre + "outliersdist"],
+                           interChrProb=float(z[pre + "interChrProb"])))
+    extra = dict(sig_head=[str(s) for s in z["sig_head"]], sig_nrows=int(z["sig_nrows"]),
+                 bias_raw=z["bias_raw"] if "bias_raw" in z else None)
+    return contacts, frags, biases, st, passes, extra
