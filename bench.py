@@ -23,14 +23,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES = {  # algorithmic HBM bytes per unit per launch
-    "hist_distance_kernel": ("pairs", 16),      # 4 x int32 read
-    "pvalues_kernel": ("pairs", 32),            # 16 read + p, ExpCC written
-    "bh_compact_kernel": ("pairs", 20),         # p read, (key, index) written
-    "radix_upsweep_kernel": ("sorted", 8),      # key read
-    "radix_downsweep_kernel": ("sorted", 24),   # (key, index) read and written
-    "bh_tilemax_kernel": ("sorted", 8),
-    "bh_scatter_kernel": ("sorted", 20),        # (key, index) read, q written
+ALGO_BYTES = {  # kernel: (unit, algorithmic HBM bytes per unit per launch, full-size launches per pass); DESIGN.md 4
+    "hist_distance_kernel": ("pairs", 16, 1),      # 4 x int32 read
+    "pvalues_kernel": ("pairs", 32, 1),            # 16 read + p, ExpCC written
+    "bh_compact_kernel": ("pairs", 20, 1),         # p read, (key, index) written
+    "radix_upsweep_kernel": ("sorted", 8, 8),      # key read, one launch per 8-bit digit
+    "radix_downsweep_kernel": ("sorted", 24, 8),   # (key, index) read and written, one launch per digit
+    "bh_tilemax_kernel": ("sorted", 8, 1),
+    "bh_scatter_kernel": ("sorted", 20, 1),        # (key, index) read, q written
 }
 PASS_BYTES_PER_PAIR = 64  # K1 16 + K3 32 + K4 16 (read p, write q)
 
@@ -182,7 +182,18 @@ def main():
     dctx = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL may print its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         from fithic_b200.parallel import DistCtx
         dctx = DistCtx(device)
     _capi.load()
@@ -275,8 +286,11 @@ def main():
     breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
                  for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
     if top is not None:
-        unit, bpu = ALGO_BYTES.get(top, ("pairs", 0))
-        avg_ms = kern[top]["ms"] / kern[top]["launches"]
+        # per full-size launch: the multi-GPU path also runs the sort on a 64k-key sample (negligible bytes and time),
+        # so bytes and time are both taken per step and divided by the number of full-size launches
+        unit, bpu, mult = ALGO_BYTES.get(top, ("pairs", 0, 1))
+        mult *= args.passes
+        avg_ms = kern[top]["ms"] / args.steps / mult
         achieved = bpu * units[unit] / (avg_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -288,6 +302,7 @@ def main():
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bpu * units[unit], "avg_launch_ms": avg_ms,
+                    "launches_per_step": mult,
                     "note": "pvalues_kernel is FP64-ALU bound by construction (SURVEY F9); its HBM fraction is low by "
                             "design" if top == "pvalues_kernel" else None,
                     "whole_step": {"algorithmic_bytes_per_pair": PASS_BYTES_PER_PAIR,
@@ -305,6 +320,7 @@ def main():
                     "d2h_bytes_per_step": 24 * args.pairs * args.passes, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb, "kernels": breakdown,
+            "host_ms_per_pass": {k: v * 1e3 for k, v in eng.timings.get(1, {}).items()},
             "sorted_pairs": n_sorted, "checksum_q": checksum}
     print(json.dumps(line))
     if world > 1:

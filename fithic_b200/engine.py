@@ -249,8 +249,8 @@ class Engine:
         else:
             q = self.bh_qvalues(p, float(T))
         out.update(p=p, q=q, expcc=e)
-        ev["k1_and_d2h"] = t1 - t0
-        ev["host_fit"] = t2 - t1
+        ev["k1_and_d2h"] = t1 - t0     # K1 launch + wait + histogram D2H (includes the device time of K1)
+        ev["host_bins_fit"] = t2 - t1  # make_bins + frag_pairs + probabilities + scipy spline fit
         self.timings[passNo] = ev
         return out
 
