@@ -51,14 +51,15 @@ _SIGNATURES = {
     "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
-    "fhc_bh_prepare": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_size_t, c_void_p]),
+    "fhc_bh_prepare": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "fhc_bh_p_cut": (c_double, [c_double, c_double]),
     "fhc_bh_finish": (ctypes.c_int, [c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "fhc_bh_sample_keys": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fhc_bh_sample_keys": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
     "fhc_bh_key_of": (ctypes.c_uint64, [c_double]),
-    "fhc_bh_partition_count": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
-    "fhc_bh_partition_scatter": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
-                                                 c_void_p, c_void_p]),
+    "fhc_bh_partition_count": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p]),
+    "fhc_bh_partition_scatter": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p]),
     "fhc_scatter_f64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,

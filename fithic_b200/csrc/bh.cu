@@ -44,45 +44,88 @@ __device__ __forceinline__ double p_of(u64 k) {
 // ---------------------------------------------------------------------------------------------------------------------
 // compaction
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n, double *__restrict__ q,
-                                                        u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel) {
-    __shared__ u32 warp_cnt[8];
+// p_cut: every p >= p_cut is known to end with q = 1.0 exactly, so it is not ranked (see bh_p_cut below).
+// One CTA iteration handles 2048 p-values (8 per thread as two 4-value groups); the (key, line) pairs of the ranked ones
+// are appended with ONE global atomic per CTA iteration (same-address atomics serialise in L2: a per-warp atomic costs
+// 5 ms at 300 M lines).  The order of the appended pairs is irrelevant, the sort follows.
+constexpr int kCompactPerThread = 8;
+__global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n, double p_cut,
+                                                        double *__restrict__ q, u64 *__restrict__ keys,
+                                                        u32 *__restrict__ vals, u64 *nsel) {
+    __shared__ u32 warp_tot[8];
     __shared__ u64 block_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = (long long)blockIdx.x * 256; base < n; base += (long long)gridDim.x * 256) {
-        const long long i = base + threadIdx.x;
-        double v = 0.0;
-        bool sel = false;
-        if (i < n) {
-            v = __ldcs(p + i);
-            if (v == 1.0)
-                q[i] = 1.0;  // fithic/myStats.py:32-33
-            else if (isnan(v))
-                q[i] = v;  // min(nan, 1) -> nan, max(nan, prev) -> nan; NaNs sort last so nothing follows them
-            else
-                sel = true;
+    const long long per_iter = 256ll * kCompactPerThread;
+    u32 cut_total = 0;
+    for (long long b0 = (long long)blockIdx.x * per_iter; b0 < n; b0 += (long long)gridDim.x * per_iter) {
+        double v[kCompactPerThread];
+        u32 selmask = 0;
+        int mine = 0;
+#pragma unroll
+        for (int h = 0; h < kCompactPerThread / 4; ++h) {
+            const long long i0 = b0 + (long long)(h * 256 + threadIdx.x) * 4;
+            double qv[4];
+            if (i0 + 3 < n) {
+                const double2 a = __ldcs(reinterpret_cast<const double2 *>(p + i0));
+                const double2 b = __ldcs(reinterpret_cast<const double2 *>(p + i0 + 2));
+                v[h * 4 + 0] = a.x; v[h * 4 + 1] = a.y; v[h * 4 + 2] = b.x; v[h * 4 + 3] = b.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[h * 4 + k] = (i0 + k < n) ? p[i0 + k] : 1.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double x = v[h * 4 + k];
+                // p == 1.0 -> 1.0 (fithic/myStats.py:32-33); NaN -> NaN (min(nan, 1) -> nan, NaNs sort last)
+                const bool rankable = !(x == 1.0) && !isnan(x) && (i0 + k < n);
+                const bool sel = rankable && !(x >= p_cut);
+                qv[k] = isnan(x) ? x : 1.0;
+                selmask |= sel ? (1u << (h * 4 + k)) : 0u;
+                mine += sel ? 1 : 0;
+                cut_total += (rankable && !sel) ? 1u : 0u;
+            }
+            if (i0 + 3 < n) {
+                // ranked lines get their q from bh_scatter_kernel later; writing 1.0 first is harmless
+                __stcs(reinterpret_cast<double2 *>(q + i0), make_double2(qv[0], qv[1]));
+                __stcs(reinterpret_cast<double2 *>(q + i0 + 2), make_double2(qv[2], qv[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (i0 + k < n) q[i0 + k] = qv[k];
+            }
         }
-        const u32 m = __ballot_sync(0xffffffffu, sel);
-        if (lane == 0) warp_cnt[warp] = __popc(m);
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = (u32)inc;
         __syncthreads();
         if (threadIdx.x == 0) {
             u32 tot = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                const u32 c = warp_cnt[w];
-                warp_cnt[w] = tot;
+                const u32 c = warp_tot[w];
+                warp_tot[w] = tot;
                 tot += c;
             }
             block_base = tot ? atomicAdd(nsel, (u64)tot) : 0;
         }
         __syncthreads();
-        if (sel) {
-            const u64 dst = block_base + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u));
-            keys[dst] = key_of(v);
-            vals[dst] = (u32)i;
+        u64 dst = block_base + warp_tot[warp] + (u64)(inc - mine);
+#pragma unroll
+        for (int j = 0; j < kCompactPerThread; ++j) {
+            if (selmask & (1u << j)) {
+                keys[dst] = key_of(v[j]);
+                vals[dst] = (u32)(b0 + (long long)((j >> 2) * 256 + threadIdx.x) * 4 + (j & 3));
+                ++dst;
+            }
         }
         __syncthreads();
     }
+    const u32 cut = (u32)warp_sum((unsigned long long)cut_total);
+    if (lane == 0 && cut) atomicAdd(nsel + 1, (u64)cut);  // rankable but known to end at q = 1.0
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -345,8 +388,10 @@ __global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilem
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        if (carry_out) *carry_out = carry;
-        if (n_sorted_out) *n_sorted_out = *d_n;
+        // d_n[1] = p-values that were not ranked because they end at exactly 1.0: they follow every ranked one
+        const u64 ncut = d_n[1];
+        if (carry_out) *carry_out = ncut ? fmax(carry, 1.0) : carry;
+        if (n_sorted_out) *n_sorted_out = *d_n + ncut;
     }
 }
 
@@ -506,15 +551,24 @@ extern "C" size_t fhc_bh_workspace_bytes(int64_t n) { return fhc::bh_ws_layout(n
 
 // compaction + sort + tile maxima + tile scan: everything of K4 that does not need the running max of smaller keys held
 // by other GPUs.  carry_out receives max(carry_in, every bh value of this call).
-static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+// Every p-value of this call has rank <= rank_bound, so p >= rank_bound / T gives (p*T)/rank >= 1: bh is capped at 1
+// and the running max is exactly 1.0 from the first such p on (they all sort after the smaller ones, whose ranks they do
+// not influence).  Those lines get q = 1.0 without being ranked.  With T (possible pairs) >> lines, as in every
+// sparse high-resolution map, this removes ~98 % of the sort.  The 1e-9 margin keeps the claim safe under rounding.
+static double bh_p_cut(double T, double rank_bound) {
+    if (!(T > 0.0) || !(rank_bound >= 0.0)) return INFINITY;
+    return (rank_bound / T) * (1.0 + 1e-9);
+}
+
+static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double p_cut, double *q,
                       double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st) {
     using namespace fhc;
-    FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, sizeof(u64), st));
+    FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 2 * sizeof(u64), st));
     const int ntiles = (int)ws.sort.ntiles;
     if (n > 0) {
-        long long blocks = (n + 255) / 256;
-        if (blocks > (long long)kNumSMs * 32) blocks = (long long)kNumSMs * 32;
-        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, q, ws.keys_a, ws.vals_a, ws.d_n);
+        long long blocks = (n + 256 * kCompactPerThread - 1) / (256 * kCompactPerThread);
+        if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, p_cut, q, ws.keys_a, ws.vals_a, ws.d_n);
         FHC_LAUNCH_CHECK("bh_compact_kernel");
         const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st);
         if (rc != FHC_OK) return rc;
@@ -557,13 +611,15 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
     FHC_PROFILE_ENTRY(st);
     BhWs ws;
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
-    rc = bh_prepare(p, n, T, rank_offset, carry_in, q, carry_out, n_sorted_out, ws, st);
+    rc = bh_prepare(p, n, T, rank_offset, carry_in, bh_p_cut(T, (double)rank_offset + (double)n), q, carry_out,
+                    n_sorted_out, ws, st);
     if (rc != FHC_OK) return rc;
     return bh_finish(n, T, rank_offset, 0.0, q, ws, st);  // carry_in is already folded into the tile prefixes
 }
 
-extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double *q, double *local_max_out,
-                              int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double p_cut, double *q,
+                              double *local_max_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes,
+                              void *stream) {
     using namespace fhc;
     int rc = bh_check_args("fhc_bh_prepare", p, n, q, workspace, workspace_bytes);
     if (rc != FHC_OK) return rc;
@@ -571,7 +627,7 @@ extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank
     FHC_PROFILE_ENTRY(st);
     BhWs ws;
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
-    return bh_prepare(p, n, T, rank_offset, 0.0, q, local_max_out, n_sorted_out, ws, st);
+    return bh_prepare(p, n, T, rank_offset, 0.0, p_cut, q, local_max_out, n_sorted_out, ws, st);
 }
 
 extern "C" int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, void *workspace,
@@ -606,26 +662,26 @@ __device__ __forceinline__ int part_of(u64 k, const Splitters &sp) {
 }
 
 __global__ void bh_sample_kernel(const double *__restrict__ p, long long n, long long stride, long long nsamples,
-                                 u64 *__restrict__ keys) {
+                                 double p_cut, u64 *__restrict__ keys) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsamples) return;
     const long long i = s * stride;
     u64 k = ~0ull;  // "no sample": sorts last
     if (i < n) {
         const double v = p[i];
-        if (!(v == 1.0) && !isnan(v)) k = key_of(v);
+        if (!(v >= p_cut) && !(v == 1.0) && !isnan(v)) k = key_of(v);
     }
     keys[s] = k;
 }
 
 __global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__restrict__ p, long long n, const Splitters sp,
-                                                           u64 *__restrict__ counts) {
+                                                           double p_cut, u64 *__restrict__ counts) {
     __shared__ u32 local[kMaxParts];
     if (threadIdx.x < kMaxParts) local[threadIdx.x] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const double v = __ldcs(p + i);
-        if (!(v == 1.0) && !isnan(v)) atomicAdd(&local[part_of(key_of(v), sp)], 1u);
+        if (!(v >= p_cut) && !(v == 1.0) && !isnan(v)) atomicAdd(&local[part_of(key_of(v), sp)], 1u);
     }
     __syncthreads();
     if (threadIdx.x < sp.nparts && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)local[threadIdx.x]);
@@ -634,7 +690,7 @@ __global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__rest
 // p -> send buffer grouped by destination part (order inside a part is arbitrary: the receiver sorts); idx[j] = source line
 // of send[j]; q gets 1.0 / NaN for the p-values that are not ranked.  cursors[r] must start at the first slot of part r.
 __global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__restrict__ p, long long n, const Splitters sp,
-                                                             u64 *cursors, double *__restrict__ send,
+                                                             double p_cut, u64 *cursors, double *__restrict__ send,
                                                              u32 *__restrict__ idx, double *__restrict__ q) {
     __shared__ u32 cnt[kMaxParts];
     __shared__ u64 base[kMaxParts];
@@ -647,10 +703,10 @@ __global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__re
         double v = 0.0;
         if (i < n) {
             v = __ldcs(p + i);
-            if (v == 1.0)
-                q[i] = 1.0;
-            else if (isnan(v))
+            if (isnan(v))
                 q[i] = v;
+            else if (v >= p_cut || v == 1.0)
+                q[i] = 1.0;
             else {
                 part = part_of(key_of(v), sp);
                 slot = atomicAdd(&cnt[part], 1u);
@@ -687,18 +743,22 @@ static int make_splitters(const uint64_t *splitter_keys, int nparts, Splitters *
 
 }  // namespace fhc
 
-extern "C" int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, uint64_t *keys_out, void *stream) {
+extern "C" int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out,
+                                  void *stream) {
     using namespace fhc;
     FHC_REQUIRE(n >= 0 && nsamples > 0 && keys_out != nullptr, FHC_E_INVALID, "fhc_bh_sample_keys: bad arguments");
     FHC_REQUIRE(n == 0 || p != nullptr, FHC_E_INVALID, "fhc_bh_sample_keys: null p");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     const long long stride = n > nsamples ? n / nsamples : 1;
-    bh_sample_kernel<<<(unsigned int)((nsamples + 255) / 256), 256, 0, st>>>(p, n, stride, nsamples,
+    bh_sample_kernel<<<(unsigned int)((nsamples + 255) / 256), 256, 0, st>>>(p, n, stride, nsamples, p_cut,
                                                                             reinterpret_cast<u64 *>(keys_out));
     FHC_LAUNCH_CHECK("bh_sample_kernel");
     return FHC_OK;
 }
+
+// smallest p that is certain to end with q = 1.0 when no p-value has a rank above rank_bound (host helper)
+extern "C" double fhc_bh_p_cut(double T, double rank_bound) { return bh_p_cut(T, rank_bound); }
 
 extern "C" uint64_t fhc_bh_key_of(double p) {  // host copy of the order-preserving key (for choosing splitters)
     uint64_t b;
@@ -707,7 +767,7 @@ extern "C" uint64_t fhc_bh_key_of(double p) {  // host copy of the order-preserv
 }
 
 extern "C" int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
-                                      uint64_t *counts, void *stream) {
+                                      double p_cut, uint64_t *counts, void *stream) {
     using namespace fhc;
     Splitters sp;
     const int rc = make_splitters(splitter_keys, nparts, &sp);
@@ -719,13 +779,14 @@ extern "C" int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t
     if (n == 0) return FHC_OK;
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    bh_part_count_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, reinterpret_cast<u64 *>(counts));
+    bh_part_count_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(counts));
     FHC_LAUNCH_CHECK("bh_part_count_kernel");
     return FHC_OK;
 }
 
 extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
-                                        uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream) {
+                                        double p_cut, uint64_t *cursors, double *send, uint32_t *idx, double *q,
+                                        void *stream) {
     using namespace fhc;
     Splitters sp;
     const int rc = make_splitters(splitter_keys, nparts, &sp);
@@ -737,7 +798,8 @@ extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64
     FHC_PROFILE_ENTRY(st);
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-    bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, reinterpret_cast<u64 *>(cursors), send, idx, q);
+    bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(cursors), send,
+                                                                 idx, q);
     FHC_LAUNCH_CHECK("bh_part_scatter_kernel");
     return FHC_OK;
 }

@@ -240,7 +240,7 @@ double lbeta_cephes(double a, double b) {
 struct CfState {
     double a, apb, bm1, z;  // parameters: a, a + b, b - 1, x or x / (1 - x)
     double fi;              // iteration counter as a double
-    double pkm2, qkm2, pkm1, qkm1, dprev, pa, qa;
+    double pkm2, qkm2, pkm1, qkm1, dprev;  // value = pkm1 / qkm1
     bool use_d;
 };
 
@@ -248,37 +248,35 @@ __device__ __forceinline__ void cf_init(CfState &s, double a, double b, double x
     s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
     s.z = use_d ? x / (1.0 - x) : x;
     s.fi = 0.0;
-    s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0; s.pa = 1.0; s.qa = 1.0;
+    s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0;
 }
 
-// one iteration (two recurrence steps); returns true when the fraction has converged (or hit the iteration cap):
-// the value is then s.pa / s.qa
+// one iteration (two recurrence steps, updated in place: after step 1 the slot "km2" holds the newest convergent, after
+// step 2 "km1" does again); returns true when the fraction has converged (or hit the iteration cap)
 __device__ __forceinline__ bool cf_step(CfState &s) {
     const double k1 = s.a + s.fi, k3 = k1 + s.fi, k4 = k3 + 1.0, k5 = 1.0 + s.fi, k8 = k3 + 2.0;
     const double up = s.apb + s.fi, dn = s.bm1 - s.fi;
     const double k2 = s.use_d ? dn : up, k6 = s.use_d ? up : dn;
+    const double pprev = s.pkm1, qprev = s.qkm1;  // previous convergent (cephes' `ans`)
     const double d1 = k3 * k4;
     const double a1 = -(s.z * k1 * k2) * s.dprev;
-    double pk = d1 * s.pkm1 + a1 * s.pkm2;
-    double qk = d1 * s.qkm1 + a1 * s.qkm2;
-    s.pkm2 = s.pkm1; s.pkm1 = pk; s.qkm2 = s.qkm1; s.qkm1 = qk;
+    s.pkm2 = d1 * s.pkm1 + a1 * s.pkm2;
+    s.qkm2 = d1 * s.qkm1 + a1 * s.qkm2;
     const double d2 = k4 * k8;
     const double a2 = (s.z * k5 * k6) * d1;
-    pk = d2 * s.pkm1 + a2 * s.pkm2;
-    qk = d2 * s.qkm1 + a2 * s.qkm2;
-    s.pkm2 = s.pkm1; s.pkm1 = pk; s.qkm2 = s.qkm1; s.qkm1 = qk;
+    s.pkm1 = d2 * s.pkm2 + a2 * s.pkm1;
+    s.qkm1 = d2 * s.qkm2 + a2 * s.qkm1;
     s.dprev = d2;
-    // |pa/qa - pk/qk| < tol |pk/qk|
-    const double lhs = fabs(s.pa * qk - pk * s.qa), rhs = kCfTol * fabs(s.qa * pk);
-    s.pa = pk; s.qa = qk;
     s.fi += 1.0;
+    // |pprev/qprev - pk/qk| < tol |pk/qk|, by cross multiplication
+    const double lhs = fabs(pprev * s.qkm1 - s.pkm1 * qprev), rhs = kCfTol * fabs(qprev * s.pkm1);
     if (lhs < rhs || s.fi >= (double)kCfMaxIter) return true;
-    const double mag = fabs(qk) + fabs(pk);
+    const double mag = fabs(s.qkm1) + fabs(s.pkm1);
     if (mag > 1.2676506002282294e30 || mag < 7.8886090522101181e-31) {  // 2^100, 2^-100: renormalise exactly
         const int ex = ((__double2hiint(mag) >> 20) & 0x7ff);
         if (ex != 0 && ex != 0x7ff) {
             const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^-(ex-1023)
-            s.pkm2 *= sc; s.pkm1 *= sc; s.qkm2 *= sc; s.qkm1 *= sc; s.pa *= sc; s.qa *= sc;
+            s.pkm2 *= sc; s.pkm1 *= sc; s.qkm2 *= sc; s.qkm1 *= sc;
         }
     }
     return false;
@@ -292,39 +290,37 @@ __device__ __forceinline__ bool cf_step(CfState &s) {
 // evaluated inside-out as a ratio P/Q (no division in the loop).  Terms below 1e-17 of the sum are skipped: the term i
 // steps below k is <= r^i exp(-i(i-1)/2k) with r = k/(N x) <= 1, which bounds the number of terms M.
 // The sum S = P/Q gives  I_{1-x}(b, a) = (1-x)^b x^a / (b B(a, b)) * (S / x),  S / x being what cephes' fraction stands for.
-struct TailState {
-    double P, Q, j, d, cN, invN;
-    int m;  // terms left
-};
-
-__device__ __forceinline__ void tail_init(TailState &s, double count, double N, double x, double one_minus_x) {
+// The state lives in the fields of a CfState (a lane works on one kind at a time, pvalue.cu):
+//   P = pkm1, Q = qkm1 (so the value is pkm1 / qkm1 for both kinds), j = fi, d = dprev, cN = z, invN = a, terms left = bm1
+__device__ __forceinline__ void tail_init(CfState &s, double count, double N, double x, double one_minus_x) {
     const double k = count - 1.0;
-    s.invN = 1.0 / N;
-    s.cN = (one_minus_x / x) * s.invN;
+    s.a = 1.0 / N;
+    s.z = (one_minus_x / x) * s.a;
     const double r = k / (N * x);
     double M = k;
     if (r > 0.0 && r < 1.0) M = fmin(M, ceil(-39.2 / log(r)) + 1.0);
     M = fmin(M, ceil(sqrt(78.4 * k)) + 1.0);
-    s.P = 1.0; s.Q = 1.0;
-    s.j = k - M + 1.0;
-    s.d = (N - s.j + 1.0) * s.invN;
-    s.m = (int)M;
+    s.pkm1 = 1.0; s.qkm1 = 1.0;
+    s.fi = k - M + 1.0;
+    s.dprev = (N - s.fi + 1.0) * s.a;
+    s.bm1 = M;
 }
 
-// one term; returns true when the sum is complete (value s.P / s.Q)
-__device__ __forceinline__ bool tail_step(TailState &s) {
-    if (s.m <= 0) return true;
-    const double n = s.j * s.cN;
-    const double dq = s.d * s.Q;
-    s.P = fma(n, s.P, dq);
-    s.Q = dq;
-    s.j += 1.0;
-    s.d -= s.invN;
-    if (s.Q < 7.8886090522101181e-31) {  // 2^-100: only reachable when count is a sizeable fraction of N
-        s.P *= 1.2676506002282294e30;
-        s.Q *= 1.2676506002282294e30;
+// one term; returns true when the sum is complete
+__device__ __forceinline__ bool tail_step(CfState &s) {
+    if (s.bm1 <= 0.0) return true;
+    const double n = s.fi * s.z;
+    const double dq = s.dprev * s.qkm1;
+    s.pkm1 = fma(n, s.pkm1, dq);
+    s.qkm1 = dq;
+    s.fi += 1.0;
+    s.dprev -= s.a;
+    s.bm1 -= 1.0;
+    if (s.qkm1 < 7.8886090522101181e-31) {  // 2^-100: only reachable when count is a sizeable fraction of N
+        s.pkm1 *= 1.2676506002282294e30;
+        s.qkm1 *= 1.2676506002282294e30;
     }
-    return --s.m <= 0;
+    return s.bm1 <= 0.0;
 }
 
 // which evaluation a contact needs once the cheap exits of bdtrc / incbet are taken
@@ -363,11 +359,9 @@ __device__ __forceinline__ bool cf_uses_d(double aa, double bb, double xx) {
     return !(xx * (aa + bb - 2.0) - (aa - 1.0) < 0.0);  // cephes: y < 0 -> incbcf, else incbd
 }
 
-// last step of incbet: prefactor in log space times the fraction / tail value w = wp / wq
-__device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb, double xx, double lbeta_ab, double wp,
-                                                double wq) {
+// last step of incbet: prefactor in log space times the fraction / tail value w
+__device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb, double xx, double lbeta_ab, double w) {
     const double w1 = __dsub_rn(1.0, xx);  // cephes rounds 1 - x before taking its log
-    double w = wp / wq;
     double div;
     if (tail) {
         w = w / xx;
@@ -391,18 +385,17 @@ __device__ __forceinline__ double bdtrc_dev(int count, int N, double prior, cons
     if (cls == kClsK0) return bdtrc_k0(N, prior);
     const double aa = (double)count, bb = (double)((long long)N - count + 1);
     const double lb = (count < ntab) ? __ldg(lbeta_tab + count) : lbeta_cephes(aa, bb);
+    CfState s;
     if (cls == kClsTail) {
-        TailState s;
         tail_init(s, aa, (double)N, prior, __dsub_rn(1.0, prior));
         while (!tail_step(s)) {
         }
-        return incbet_finish(true, aa, bb, prior, lb, s.P, s.Q);
+        return incbet_finish(true, aa, bb, prior, lb, s.pkm1 / s.qkm1);
     }
-    CfState s;
     cf_init(s, aa, bb, prior, cf_uses_d(aa, bb, prior));
     while (!cf_step(s)) {
     }
-    return incbet_finish(false, aa, bb, prior, lb, s.pa, s.qa);
+    return incbet_finish(false, aa, bb, prior, lb, s.pkm1 / s.qkm1);
 }
 #endif  // __CUDACC__
 

@@ -67,39 +67,63 @@ extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxm
                 "fhc_host_frag_pairs: null bin arrays");
     int64_t noOfFrags = 0;
     for (int c = 0; c < nchr; ++c) noOfFrags += chr_n[c];  // first loop of the reference (:596-604)
-    int64_t inrange = 0, interpairs2 = 0, intraall2 = 0;
-    for (int c = 0; c < nchr; ++c) {  // caller passes chromosomes in sorted-name order (:606)
+    // number of distance steps per chromosome: range(0, int(maxFrag + 1), res) with maxFrag = max(mid) - res/2 (:602,:613)
+    std::vector<int64_t> nsteps(nchr, 0);
+    for (int c = 0; c < nchr; ++c) {
+        if (chr_n[c] <= 0) continue;
+        const double maxFrag = (double)chr_maxmid[c] - (double)res / 2.0;
+        const int64_t stop = (int64_t)(maxFrag + 1.0);  // int(): truncation
+        nsteps[c] = stop > 0 ? (stop + res - 1) / res : 0;
+    }
+    // the in-range window in steps: dist = k * res with L <= dist <= U (myUtils.in_range_check; -1 = unbounded)
+    const int64_t kLo = L <= 0 ? 0 : (L + res - 1) / res;
+    const int64_t kHi = U < 0 ? INT64_MAX : U / res;
+    // The reference walks chromosome by chromosome (sorted names) and distance by distance, adding into the bin that
+    // holds the distance (forward tracker, clamped to the last bin).  Every bin therefore receives its terms in the
+    // order (chromosome, distance); bins are independent of each other, so each bin is filled on its own
+    // in exactly that order -- the double sum is bit-identical to the sequential walk (and bins could run concurrently).
+    int64_t inrange_once = 0;
+    for (int c = 0; c < nchr; ++c) {
         const int64_t n = chr_n[c];
         if (n <= 0) continue;
-        const double maxFrag = (double)chr_maxmid[c] - (double)res / 2.0;  // :602
-        const int64_t stop = (int64_t)(maxFrag + 1.0);                     // int(maxFrags[ch]+1), truncation
-        int64_t d = 0, perchr = 0;
-        int tr = 0;
-        for (int64_t dist = 0; dist < stop; dist += res) {  // range(0, stop, res) (:613)
-            const int64_t npairs = n - d;                   // may go negative when loci are unmappable
-            d += 1;
-            const bool lo_ok = (L == -1) || (L > -1 && dist >= L);  // myUtils.in_range_check
-            const bool hi_ok = (U == -1) || (U > -1 && dist <= U);
-            if (!(lo_ok && hi_ok)) continue;
-            perchr += npairs;  // :618
-            if (nbins > 0) {
-                while (!(bin_lb[tr] <= dist && dist <= bin_ub[tr])) {  // forward tracker, clamp to the last bin (:627-638)
-                    tr += 1;
-                    if (tr >= nbins) {
-                        tr -= 1;
-                        break;
-                    }
-                }
-                bin_pairs[tr] += npairs;                                             // [7] and [1] (:639-640)
-                bin_sumdist[tr] += ((double)dist / 1000000.0) * (double)npairs;      // :641
-                perchr += npairs;                                                    // :642 (the x2 of SURVEY F4)
+        const int64_t k1 = nsteps[c] - 1 < kHi ? nsteps[c] - 1 : kHi;
+        if (k1 >= kLo) {
+            const int64_t cntk = k1 - kLo + 1;  // sum over k in [kLo, k1] of (n - k)
+            inrange_once += n * cntk - (kLo + k1) * cntk / 2;
+        }
+    }
+    for (int b = 0; b < nbins; ++b) {
+        // distances of bin b: lb <= k*res <= ub; the last bin also takes everything beyond its ub (tracker clamp), and a
+        // distance below bin_lb[0] cannot occur (bin_lb[0] == 0)
+        int64_t kb0 = (bin_lb[b] + res - 1) / res;
+        int64_t kb1 = (b == nbins - 1) ? INT64_MAX : bin_ub[b] / res;
+        if (kb0 < kLo) kb0 = kLo;
+        if (kb1 > kHi) kb1 = kHi;
+        int64_t pairs = bin_pairs[b];
+        double sumdist = bin_sumdist[b];
+        for (int c = 0; c < nchr; ++c) {
+            const int64_t n = chr_n[c];
+            if (n <= 0) continue;
+            const int64_t k1 = nsteps[c] - 1 < kb1 ? nsteps[c] - 1 : kb1;
+            for (int64_t k = kb0; k <= k1; ++k) {
+                const int64_t npairs = n - k;  // may go negative when loci are unmappable
+                const int64_t dist = k * res;
+                pairs += npairs;                                               // [7] and [1] (:639-640)
+                sumdist += ((double)dist / 1000000.0) * (double)npairs;        // :641
             }
         }
+        bin_pairs[b] = pairs;
+        bin_sumdist[b] = sumdist;
+    }
+    int64_t interpairs2 = 0, intraall2 = 0;
+    for (int c = 0; c < nchr; ++c) {
+        const int64_t n = chr_n[c];
+        if (n <= 0) continue;
         interpairs2 += n * (noOfFrags - n);  // :645
         intraall2 += n * (n + 1);            // :647 (x2)
-        inrange += perchr;
     }
-    totals[0] = inrange;
+    // :618 adds npairs once per in-range distance, :642 once more when there are bins (the x2 of SURVEY F4)
+    totals[0] = nbins > 0 ? 2 * inrange_once : inrange_once;
     totals[1] = intraall2;
     totals[2] = interpairs2;
     totals[3] = noOfFrags;

@@ -17,12 +17,23 @@
 //      another handles the closed forms;
 //   5. p leaves through coalesced 128-bit stores; outliers are flagged.
 #define FHC_PROFILE_STREAM st
+#include <stdlib.h>
+
 #include "cephes_dev.cuh"
 
 namespace fhc {
 
 constexpr int kPvalThreads = 256;
 constexpr int kPvalTile = 2048;  // contacts per CTA tile (8 per thread)
+
+// n / d for 32-bit n by one 64-bit multiply-high: M = ceil(2^64 / d) is exact for every n < 2^32 (d == 1 is flagged)
+struct FastDiv {
+    unsigned long long M;
+    unsigned int d;
+};
+__device__ __forceinline__ unsigned int fastdiv(unsigned int n, const FastDiv &f) {
+    return f.d == 1 ? n : (unsigned int)__umul64hi((unsigned long long)n, f.M);
+}
 
 struct PvalParams {
     int mode;  // FHC_MODE_*
@@ -32,7 +43,7 @@ struct PvalParams {
     const int *bias_mid;
     const long long *chr_off;
     int nchr;
-    unsigned int res;
+    FastDiv res;
     long long Llo, Uhi;  // effective in-range window (L == -1 -> 0, U == -1 -> max)
     const double *lut;
     long long D;
@@ -48,20 +59,20 @@ struct PvalParams {
 
 struct PvalSmem {
     double x[kPvalTile];   // prior of the contacts that need real work
-    double wp[kPvalTile];  // trivial p / numerator of the fraction or tail / finally p
-    double wq[kPvalTile];  // denominator
+    double wp[kPvalTile];  // trivial p / value of the fraction or tail sum / finally p
     int cnt[kPvalTile];
-    unsigned short list[3][kPvalTile];  // work lists: [0] closed form, [1] tail sum, [2] continued fraction
-    unsigned char inter[kPvalTile];     // 1: the contact is scored against N_inter
-    unsigned int n[3];
-    unsigned int cursor[2];  // next unclaimed entry of list[1] / list[2]
+    unsigned short work[kPvalTile];  // [0, nCf) continued fractions, [nCf, nCf + nTail) tail sums (local contact indices)
+    unsigned short k0[kPvalTile];    // closed forms
+    unsigned char inter[kPvalTile];  // 1: the contact is scored against N_inter
+    unsigned long long warp_tot[kPvalThreads / 32 + 1];
+    unsigned int cursor;             // next unclaimed entry of work[]
 };
 
 // bias dictionary lookup of fithic/fithic.py:1026-1054: missing chromosome or mid point -> -1
 __device__ __forceinline__ double bias_lookup(const PvalParams &P, unsigned int chr, int mid) {
     if ((int)chr >= P.nchr || mid < 0) return -1.0;
     const long long lo = __ldg(P.chr_off + chr), hi = __ldg(P.chr_off + chr + 1);
-    const long long s = lo + (long long)((unsigned int)mid / P.res);
+    const long long s = lo + (long long)fastdiv((unsigned int)mid, P.res);
     if (s >= hi) return -1.0;
     if (__ldg(P.bias_mid + s) != mid) return -1.0;
     return __ldg(P.bias + s);
@@ -90,7 +101,7 @@ __device__ __forceinline__ PvalClass pval_prepare(const PvalParams &P, int m1, i
     int N;
     if (!inter && !interOnly) {
         if (!(d >= P.Llo && d <= P.Uhi)) return kClsDone;  // intraShort / intraLong: p = 1, ExpCC = 0 (:1081-1096)
-        const unsigned int slot = (unsigned int)d / P.res;  // intraInRange (:1065-1079)
+        const unsigned int slot = fastdiv((unsigned int)d, P.res);  // intraInRange (:1065-1079)
         const double prior0 = ((long long)slot < P.D) ? __ldg(P.lut + slot) : NAN;
         prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
         N = P.N_intra;
@@ -116,20 +127,9 @@ __device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, d
     }
 }
 
-// all 32 lanes call this; lanes with pred append li to the list
-__device__ __forceinline__ void list_append(bool pred, unsigned short *list, unsigned int *counter, int li, int lane) {
-    const unsigned int m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return;
-    const int leader = __ffs(m) - 1;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)li;
-}
-
-// claim the next entries of a work list for the lanes that need one; returns the local contact index or -1
-__device__ __forceinline__ int list_claim(bool need, const unsigned short *list, unsigned int total, unsigned int *cursor,
-                                          int lane) {
+// claim the next entries of the work list for the lanes that need one (every lane of the warp must call);
+// returns the position in the list or -1
+__device__ __forceinline__ int work_claim(bool need, unsigned int total, unsigned int *cursor, int lane) {
     const unsigned int m = __ballot_sync(0xffffffffu, need);
     if (m == 0) return -1;
     const int leader = __ffs(m) - 1;
@@ -138,14 +138,16 @@ __device__ __forceinline__ int list_claim(bool need, const unsigned short *list,
     base = __shfl_sync(0xffffffffu, base, leader);
     if (!need) return -1;
     const unsigned int k = base + __popc(m & ((1u << lane) - 1u));
-    return k < total ? (int)list[k] : -1;
+    return k < total ? (int)k : -1;
 }
 
-template <bool HAS_BIAS>
-__global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalParams P) {
+constexpr unsigned long long kPack = 1ull << 21;  // three 21-bit counters in one 64-bit word
+
+template <bool HAS_BIAS, int kMinCtas>
+__global__ void __launch_bounds__(kPvalThreads, kMinCtas) pvalues_kernel(const PvalParams P) {
     extern __shared__ __align__(16) unsigned char pval_smem_raw[];
     PvalSmem &S = *reinterpret_cast<PvalSmem *>(pval_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long ntiles = (P.n + kPvalTile - 1) / kPvalTile;
     unsigned int flagged = 0;
     const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
@@ -155,10 +157,9 @@ __global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalPara
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * kPvalTile;
         const bool full = base + kPvalTile <= P.n;
-        if (tid < 3) S.n[tid] = 0;
-        if (tid < 2) S.cursor[tid] = 0;
-        __syncthreads();
+        if (tid == 0) S.cursor = 0;
         // ---- phase 1: load, classify, prior, ExpCC ----
+        unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int l0 = (h * kPvalThreads + tid) * 4;  // local index of this thread's 4 contacts
@@ -198,9 +199,7 @@ __global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalPara
                     S.cnt[li] = cc[k];
                     S.inter[li] = use_inter ? 1 : 0;
                 }
-                list_append(cls == kClsK0, S.list[0], &S.n[0], li, lane);
-                list_append(cls == kClsTail, S.list[1], &S.n[1], li, lane);
-                list_append(cls == kClsCf, S.list[2], &S.n[2], li, lane);
+                codes |= (unsigned int)cls << (2 * (h * 4 + k));
             }
             if (full) {
                 double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
@@ -212,66 +211,92 @@ __global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalPara
                     if (base + l0 + k < P.n) P.expcc[base + l0 + k] = e[k];
             }
         }
+        // work lists by a CTA-wide exclusive scan of (cf, tail, k0) counts packed in one word: no atomics, and the
+        // lists come out in contact order
+        unsigned long long mine = 0;
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+            const unsigned int c = (codes >> (2 * s8)) & 3u;
+            mine += (c == kClsCf ? 1ull : 0ull) + (c == kClsTail ? kPack : 0ull) + (c == kClsK0 ? kPack * kPack : 0ull);
+        }
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) S.warp_tot[warp] = inc;
         __syncthreads();
-        const unsigned int nK0 = S.n[0], nTail = S.n[1], nCf = S.n[2];
-        // ---- phase 2: continued fractions, lanes refill from the list as they converge ----
+        unsigned long long pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kPvalThreads / 32; ++w) {
+            const unsigned long long t = S.warp_tot[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        const unsigned int nCf = (unsigned int)(tot & (kPack - 1)), nTail = (unsigned int)((tot >> 21) & (kPack - 1));
+        const unsigned int nK0 = (unsigned int)(tot >> 42);
+        {
+            const unsigned long long ex = pre + inc - mine;
+            unsigned int oCf = (unsigned int)(ex & (kPack - 1));
+            unsigned int oTail = nCf + (unsigned int)((ex >> 21) & (kPack - 1));
+            unsigned int oK0 = (unsigned int)(ex >> 42);
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const unsigned int c = (codes >> (2 * s8)) & 3u;
+                const unsigned short li = (unsigned short)(((s8 >> 2) * kPvalThreads + tid) * 4 + (s8 & 3));
+                if (c == kClsCf) S.work[oCf++] = li;
+                if (c == kClsTail) S.work[oTail++] = li;
+                if (c == kClsK0) S.k0[oK0++] = li;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: continued fractions and tail sums from one work list; a lane that finishes its contact takes the
+        // next one while its neighbours keep iterating.  Only the warps that straddle nCf run both bodies. ----
         {
             CfState st;
-            int item = -1;
+            int pos = -1;  // position in S.work
+            int item = 0;
             bool exhausted = false;
+            const unsigned int nWork = nCf + nTail;
             while (true) {
-                const bool need = item < 0 && !exhausted;
-                const int got = list_claim(need, S.list[2], nCf, &S.cursor[1], lane);  // every lane takes part
+                const bool need = pos < 0 && !exhausted;
+                const int got = work_claim(need, nWork, &S.cursor, lane);
                 if (need) {
                     if (got < 0) {
                         exhausted = true;
                     } else {
-                        item = got;
+                        pos = got;
+                        item = S.work[pos];
                         const int N = S.inter[item] ? P.N_inter : P.N_intra;
-                        const double aa = (double)S.cnt[item], bb = (double)((long long)N - S.cnt[item] + 1);
-                        const double xx = S.x[item];
-                        cf_init(st, aa, bb, xx, cf_uses_d(aa, bb, xx));
+                        const double aa = (double)S.cnt[item], xx = S.x[item];
+                        if ((unsigned int)pos < nCf) {
+                            const double bb = (double)((long long)N - S.cnt[item] + 1);
+                            cf_init(st, aa, bb, xx, cf_uses_d(aa, bb, xx));
+                        } else {
+                            tail_init(st, aa, (double)N, xx, __dsub_rn(1.0, xx));
+                        }
                     }
                 }
-                if (__ballot_sync(0xffffffffu, item >= 0) == 0) break;
-                if (item >= 0 && cf_step(st)) {
-                    S.wp[item] = st.pa;
-                    S.wq[item] = st.qa;
-                    item = -1;
+                if (__ballot_sync(0xffffffffu, pos >= 0) == 0) break;
+                bool done = false;
+                if (pos >= 0) {
+                    if ((unsigned int)pos < nCf)
+                        done = cf_step(st);
+                    else
+                        done = tail_step(st);
                 }
-            }
-        }
-        // ---- phase 3: tail sums, same scheme ----
-        {
-            TailState st;
-            int item = -1;
-            bool exhausted = false;
-            while (true) {
-                const bool need = item < 0 && !exhausted;
-                const int got = list_claim(need, S.list[1], nTail, &S.cursor[0], lane);  // every lane takes part
-                if (need) {
-                    if (got < 0) {
-                        exhausted = true;
-                    } else {
-                        item = got;
-                        const int N = S.inter[item] ? P.N_inter : P.N_intra;
-                        const double xx = S.x[item];
-                        tail_init(st, (double)S.cnt[item], (double)N, xx, __dsub_rn(1.0, xx));
-                    }
-                }
-                if (__ballot_sync(0xffffffffu, item >= 0) == 0) break;
-                if (item >= 0 && tail_step(st)) {
-                    S.wp[item] = st.P;
-                    S.wq[item] = st.Q;
-                    item = -1;
+                if (done) {
+                    S.wp[item] = st.pkm1 / st.qkm1;
+                    pos = -1;
                 }
             }
         }
         __syncthreads();
-        // ---- phase 4: p-values ----
-        for (unsigned int i = tid; i < nTail + nCf; i += kPvalThreads) {
-            const bool tail = i < nTail;
-            const int item = tail ? S.list[1][i] : S.list[2][i - nTail];
+        // ---- phase 3: p-values (same code for both kinds: 3 log + 1 exp), closed forms ----
+        for (unsigned int i = tid; i < nCf + nTail; i += kPvalThreads) {
+            const bool tail = i >= nCf;
+            const int item = S.work[i];
             const bool ui = S.inter[item] != 0;
             const int N = ui ? P.N_inter : P.N_intra;
             const int c = S.cnt[item];
@@ -279,14 +304,14 @@ __global__ void __launch_bounds__(kPvalThreads, 2) pvalues_kernel(const PvalPara
             const double *tab = ui ? P.lbeta_inter : P.lbeta_intra;
             const long long ntab = ui ? P.ntab_inter : P.ntab_intra;
             const double lb = (c < ntab) ? __ldg(tab + c) : lbeta_cephes(aa, bb);
-            S.wp[item] = incbet_finish(tail, aa, bb, S.x[item], lb, S.wp[item], S.wq[item]);
+            S.wp[item] = incbet_finish(tail, aa, bb, S.x[item], lb, S.wp[item]);
         }
         for (unsigned int i = tid; i < nK0; i += kPvalThreads) {
-            const int item = S.list[0][i];
+            const int item = S.k0[i];
             S.wp[item] = bdtrc_k0(S.inter[item] ? P.N_inter : P.N_intra, S.x[item]);
         }
         __syncthreads();
-        // ---- phase 5: coalesced stores of p, outlier flags ----
+        // ---- phase 4: coalesced stores of p, outlier flags ----
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int l0 = (h * kPvalThreads + tid) * 4;
@@ -405,7 +430,8 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.bias_mid = bias_mid;
     P.chr_off = reinterpret_cast<const long long *>(chr_off);
     P.nchr = nchr;
-    P.res = (unsigned int)res;
+    P.res.d = (unsigned int)res;
+    P.res.M = res == 1 ? 0ull : (~0ull) / (unsigned long long)res + 1ull;  // ceil(2^64 / res)
     P.Llo = L < 0 ? 0 : L;
     P.Uhi = U < 0 ? INT64_MAX : U;
     P.lut = lut;
@@ -424,19 +450,28 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;
     P.expcc = expcc;
+    static int occ = -1;  // resident CTAs per SM: 2 (no spills, 116 registers) or 3 (80 registers); FHC_PVAL_OCC overrides
+    if (occ < 0) {
+        const char *e = getenv("FHC_PVAL_OCC");
+        occ = (e && atoi(e) == 3) ? 3 : 2;
+    }
     long long blocks = (n + kPvalTile - 1) / kPvalTile;
-    const long long cap = (long long)kNumSMs * 2;  // persistent: 2 resident CTAs per SM, grid-stride over tiles
+    const long long cap = (long long)kNumSMs * occ;  // persistent CTAs, grid-stride over tiles
     if (blocks > cap) blocks = cap;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     const size_t smem = sizeof(PvalSmem);
+#define FHC_LAUNCH_PVAL(B, O)                                                                                           \
+    do {                                                                                                                \
+        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        pvalues_kernel<B, O><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);                                     \
+    } while (0)
     if (bias) {
-        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pvalues_kernel<true><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);
+        if (occ == 3) FHC_LAUNCH_PVAL(true, 3); else FHC_LAUNCH_PVAL(true, 2);
     } else {
-        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pvalues_kernel<false><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);
+        if (occ == 3) FHC_LAUNCH_PVAL(false, 3); else FHC_LAUNCH_PVAL(false, 2);
     }
+#undef FHC_LAUNCH_PVAL
     FHC_LAUNCH_CHECK("pvalues_kernel");
     return FHC_OK;
 }

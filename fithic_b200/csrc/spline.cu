@@ -56,38 +56,51 @@ __device__ __forceinline__ bool violates(double sa, long long na, double sb, lon
     return sa * (double)nb < sb * (double)na;
 }
 
+// A block [s, e] of pooled points is described twice, at its first and at its last index, so that a neighbour reaches
+// everything it needs (sum and extent) with ONE 16-byte load: the merge cascade is a chain of dependent loads and its
+// length is data dependent (a rising tail of the spline pools back over thousands of blocks), so latency per step is
+// what matters.
+struct __align__(16) BlockRec {
+    double sum;
+    int other;  // at the first index: last index of the block (-1: not a block start any more); at the last index: first
+    int pad;
+};
+
+__device__ __forceinline__ BlockRec ld_rec(const BlockRec *p) {
+    const int4 v = *reinterpret_cast<const int4 *>(p);
+    BlockRec r;
+    r.sum = __hiloint2double(v.y, v.x);
+    r.other = v.z;
+    r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ void st_rec(BlockRec *p, double sum, int other) {
+    *reinterpret_cast<int4 *>(p) = make_int4(__double2loint(sum), __double2hiint(sum), other, 0);
+}
+
 __global__ void __launch_bounds__(kPavaThreads, 1)
 spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, int nt,
-                   const long long *__restrict__ splineX, long long m, double *__restrict__ table, double *sum,
-                   int *endOf, int *startOf) {
-    // ---- 1. splev ----
-    for (long long i = threadIdx.x; i < m; i += kPavaThreads) {
-        sum[i] = splev3(t, c, nt, (double)splineX[i]);
-    }
-    __syncthreads();
-    // ---- 2a. PAVA inside each chunk ----
+                   const long long *__restrict__ splineX, long long m, double *__restrict__ table, BlockRec *atStart,
+                   BlockRec *atEnd) {
+    // ---- 1 + 2a. splev, then PAVA inside each thread's chunk ----
     const long long chunk = (m + kPavaThreads - 1) / kPavaThreads;
     {
         const long long lo = (long long)threadIdx.x * chunk;
         const long long hi = lo + chunk < m ? lo + chunk : m;
-        if (lo < hi) {
-            endOf[lo] = (int)lo;
-            startOf[lo] = (int)lo;
-            for (long long i = lo + 1; i < hi; ++i) {
-                long long s = i;
-                double sm = sum[i];
-                while (s > lo) {
-                    const long long ps = startOf[s - 1];
-                    const double psum = sum[ps];
-                    if (!violates(psum, s - ps, sm, i - s + 1)) break;
-                    endOf[s] = -1;  // s stops being a block start
-                    sm += psum;
-                    s = ps;
-                }
-                sum[s] = sm;
-                endOf[s] = (int)i;
-                startOf[i] = (int)s;
+        for (long long i = lo; i < hi; ++i) {
+            const double y = splev3(t, c, nt, (double)splineX[i]);
+            long long s = i;
+            double sm = y;
+            while (s > lo) {
+                const BlockRec prev = ld_rec(atEnd + (s - 1));  // the block that ends just before s
+                const long long ps = prev.other;
+                if (!violates(prev.sum, s - ps, sm, i - s + 1)) break;
+                atStart[s].other = -1;  // s stops being a block start
+                sm += prev.sum;
+                s = ps;
             }
+            st_rec(atStart + s, sm, (int)i);
+            st_rec(atEnd + i, sm, (int)s);
         }
     }
     __syncthreads();
@@ -97,38 +110,34 @@ spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, i
         if (b < m) {
             const long long lo = b - seg;
             const long long hi = b + seg < m ? b + seg : m;
-            long long cs = startOf[b - 1], ce = endOf[b];
-            double s_left = sum[cs], s_right = sum[b];
-            if (violates(s_left, b - cs, s_right, ce - b + 1)) {
-                double sm = s_left + s_right;
-                endOf[b] = -1;
+            const BlockRec L = ld_rec(atEnd + (b - 1)), R = ld_rec(atStart + b);
+            long long cs = L.other, ce = R.other;
+            if (violates(L.sum, b - cs, R.sum, ce - b + 1)) {
+                double sm = L.sum + R.sum;
+                atStart[b].other = -1;
                 bool changed = true;
                 while (changed) {
                     changed = false;
-                    if (cs > lo) {
-                        const long long ps = startOf[cs - 1];
-                        const double psum = sum[ps];
-                        if (violates(psum, cs - ps, sm, ce - cs + 1)) {
-                            endOf[cs] = -1;
-                            sm += psum;
-                            cs = ps;
-                            changed = true;
-                        }
+                    // both neighbours are fetched before either is tested: two independent loads per round
+                    BlockRec pl, nr;
+                    const bool hasl = cs > lo, hasr = ce + 1 < hi;
+                    if (hasl) pl = ld_rec(atEnd + (cs - 1));
+                    if (hasr) nr = ld_rec(atStart + (ce + 1));
+                    if (hasl && violates(pl.sum, cs - pl.other, sm, ce - cs + 1)) {
+                        atStart[cs].other = -1;
+                        sm += pl.sum;
+                        cs = pl.other;
+                        changed = true;
                     }
-                    if (ce + 1 < hi) {
-                        const long long ns = ce + 1, ne = endOf[ns];
-                        const double nsum = sum[ns];
-                        if (violates(sm, ce - cs + 1, nsum, ne - ns + 1)) {
-                            endOf[ns] = -1;
-                            sm += nsum;
-                            ce = ne;
-                            changed = true;
-                        }
+                    if (hasr && violates(sm, ce - cs + 1, nr.sum, nr.other - ce)) {
+                        atStart[ce + 1].other = -1;
+                        sm += nr.sum;
+                        ce = nr.other;
+                        changed = true;
                     }
                 }
-                sum[cs] = sm;
-                endOf[cs] = (int)ce;
-                startOf[ce] = (int)cs;
+                st_rec(atStart + cs, sm, (int)ce);
+                st_rec(atEnd + ce, sm, (int)cs);
             }
         }
         __syncthreads();
@@ -139,7 +148,7 @@ spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, i
     const long long hi = lo + chunk < m ? lo + chunk : m;
     long long mine = -1;
     for (long long i = lo; i < hi; ++i)
-        if (endOf[i] >= 0) mine = i;
+        if (atStart[i].other >= 0) mine = i;
     last_start[threadIdx.x] = mine;
     __syncthreads();
     for (int off = 1; off < kPavaThreads; off <<= 1) {  // inclusive max-scan (Hillis-Steele)
@@ -151,12 +160,13 @@ spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, i
     }
     long long cur = threadIdx.x > 0 ? last_start[threadIdx.x - 1] : -1;
     double mean = 0.0;
-    if (cur >= 0) mean = __ddiv_rn(sum[cur], (double)(endOf[cur] - cur + 1));
+    if (cur >= 0) {
+        const BlockRec r = ld_rec(atStart + cur);
+        mean = __ddiv_rn(r.sum, (double)(r.other - cur + 1));
+    }
     for (long long i = lo; i < hi; ++i) {
-        if (endOf[i] >= 0) {
-            cur = i;
-            mean = __ddiv_rn(sum[cur], (double)(endOf[cur] - cur + 1));
-        }
+        const BlockRec r = ld_rec(atStart + i);
+        if (r.other >= 0) mean = __ddiv_rn(r.sum, (double)(r.other - i + 1));
         table[i] = mean;
     }
 }
@@ -184,7 +194,7 @@ __global__ void spline_lut_kernel(const long long *__restrict__ splineX, const d
 
 extern "C" size_t fhc_spline_workspace_bytes(int64_t m) {
     if (m < 0) m = 0;
-    return (size_t)m * (sizeof(double) + 2 * sizeof(int)) + 64;
+    return (size_t)m * 32 + 64;  // two 16-byte block records per point
 }
 
 extern "C" int fhc_spline_table(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m,
@@ -199,11 +209,11 @@ extern "C" int fhc_spline_table(const double *t, const double *c, int32_t nt, co
                 "fhc_spline_table: workspace of %zu bytes, need %zu", workspace_bytes, fhc_spline_workspace_bytes(m));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
-    double *sum = reinterpret_cast<double *>(workspace);
-    int *endOf = reinterpret_cast<int *>(sum + m);
-    int *startOf = endOf + m;
-    spline_pava_kernel<<<1, kPavaThreads, 0, st>>>(t, c, nt, reinterpret_cast<const long long *>(splineX), m, table, sum,
-                                                  endOf, startOf);
+    FHC_REQUIRE(aligned16(workspace), FHC_E_INVALID, "fhc_spline_table: workspace must be 16-byte aligned");
+    BlockRec *atStart = reinterpret_cast<BlockRec *>(workspace);
+    BlockRec *atEnd = atStart + m;
+    spline_pava_kernel<<<1, kPavaThreads, 0, st>>>(t, c, nt, reinterpret_cast<const long long *>(splineX), m, table,
+                                                  atStart, atEnd);
     FHC_LAUNCH_CHECK("spline_pava_kernel");
     if (D > 0) {
         const int threads = 256;

@@ -67,9 +67,12 @@ class CudaOps:
     def empty(self, n, dtype):
         return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
 
-    def sample_keys(self, p, nsamples):
+    def p_cut(self, T, rank_bound):
+        return float(self.lib.fhc_bh_p_cut(float(T), float(rank_bound)))
+
+    def sample_keys(self, p, nsamples, p_cut):
         keys = self.empty(nsamples, torch.int64)
-        check(self.lib.fhc_bh_sample_keys(dptr(p), p.numel(), nsamples, dptr(keys), self._stream()))
+        check(self.lib.fhc_bh_sample_keys(dptr(p), p.numel(), nsamples, float(p_cut), dptr(keys), self._stream()))
         return keys
 
     def sort_keys(self, keys):
@@ -81,22 +84,23 @@ class CudaOps:
         check(self.lib.fhc_sort_pairs_u64(dptr(keys), dptr(vals), dptr(ko), dptr(vo), n, dptr(ws), wsb, self._stream()))
         return ko
 
-    def partition_count(self, p, splitters):
+    def partition_count(self, p, splitters, p_cut):
         nparts = len(splitters) + 1
         counts = self.empty(nparts, torch.int64)
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
-        check(self.lib.fhc_bh_partition_count(dptr(p), p.numel(), dptr(sp), nparts, dptr(counts), self._stream()))
+        check(self.lib.fhc_bh_partition_count(dptr(p), p.numel(), dptr(sp), nparts, float(p_cut), dptr(counts),
+                                              self._stream()))
         return counts
 
-    def partition_scatter(self, p, splitters, send_offsets, q):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut):
         nparts = len(splitters) + 1
         n = p.numel()
         cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
         send = self.empty(n, torch.float64)
         idx = self.empty(n, torch.int32)
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
-        check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, dptr(cursors), dptr(send), dptr(idx),
-                                                dptr(q), self._stream()))
+        check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, float(p_cut), dptr(cursors), dptr(send),
+                                                dptr(idx), dptr(q), self._stream()))
         return send, idx
 
     def _bh_ws(self, n):
@@ -109,8 +113,9 @@ class CudaOps:
         n = p.numel()
         ws, wsb = self._bh_ws(n)
         local_max = self.empty(1, torch.float64)
-        check(self.lib.fhc_bh_prepare(dptr(p), n, float(T), int(rank_offset), dptr(q), dptr(local_max), None, dptr(ws),
-                                      wsb, self._stream()))
+        # the received p-values are already below the global p_cut: rank all of them
+        check(self.lib.fhc_bh_prepare(dptr(p), n, float(T), int(rank_offset), float("inf"), dptr(q), dptr(local_max), None,
+                                      dptr(ws), wsb, self._stream()))
         return local_max
 
     def bh_finish(self, n, T, rank_offset, floor, q):
@@ -178,16 +183,19 @@ class DistCtx:
         n = p.numel()
         if q is None:
             q = engine._tensor("q", n, torch.float64) if engine is not None else ops.empty(n, torch.float64)
+        # 0. p-values that are certain to end with q = 1.0 are neither exchanged nor ranked (bh.cu: bh_p_cut)
+        n_global = int(self._all_gather(torch.tensor([n], dtype=torch.int64, device=p.device)).sum().item())
+        p_cut = ops.p_cut(T, n_global)
         # 1. splitters from a sorted sample of everybody's keys
-        sample = ops.sample_keys(p, self.samples_per_rank)
+        sample = ops.sample_keys(p, self.samples_per_rank, p_cut)
         allsamp = ops.sort_keys(self._all_gather(sample))
         splitters = choose_splitters(allsamp.cpu().numpy().view(np.uint64), G)
         # 2. how many keys go where
-        counts = ops.partition_count(p, splitters)
+        counts = ops.partition_count(p, splitters, p_cut)
         cm = self._all_gather(counts).cpu().numpy().reshape(G, G)
         send_splits, recv_splits, rank_offset, send_off = exchange_plan(cm, r)
         # 3. group by destination, exchange
-        send, idx = ops.partition_scatter(p, splitters, send_off, q)
+        send, idx = ops.partition_scatter(p, splitters, send_off, q, p_cut)
         n_send, n_recv = int(sum(send_splits)), int(sum(recv_splits))
         recv = ops.empty(n_recv, torch.float64)
         dist.all_to_all_single(recv, send[:n_send], recv_splits, send_splits, group=self.group)
@@ -200,5 +208,5 @@ class DistCtx:
         q_back = ops.empty(n_send, torch.float64)
         dist.all_to_all_single(q_back, q_recv, send_splits, recv_splits, group=self.group)
         ops.scatter(q_back, idx[:n_send], q)
-        self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor)
+        self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor, p_cut=p_cut)
         return q

@@ -143,7 +143,8 @@ int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *prior, int64_
  * Replaces myStats.benjamini_hochberg_correction (fithic/myStats.py:24-48): ascending order, bh = p*T/rank capped
  * at 1, FORWARD running max, p == 1.0 -> 1.0, NaN -> NaN (sorted last).  rank_offset / carry_in allow a caller that
  * range-partitions p-values over several GPUs to chain the scan (single GPU: 0 and 0.0); carry_out [dev, nullable]
- * receives {running max after the last sorted element} and n_sorted_out [dev, nullable] the number of p < 1.
+ * receives {running max after the last rankable element} and n_sorted_out [dev, nullable] the number of rankable
+ * p-values (p != 1, not NaN).  p-values that are certain to end at q = 1.0 are not sorted at all (see fhc_bh_p_cut).
  *   p [dev] n doubles, q [dev] n doubles (may not alias p). */
 size_t fhc_bh_workspace_bytes(int64_t n);
 int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
@@ -152,24 +153,29 @@ int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, do
 /* The same in two halves, for a caller that has to fetch the running max of smaller keys from other GPUs in between:
  * prepare = compaction + sort + per-tile maxima (local_max_out [dev] = max bh value of this call, 0 if none);
  * finish  = scan + scatter with floor_in = max over the key ranges below this one.  Same workspace for both calls. */
-int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double *q, double *local_max_out,
-                   int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
+int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double p_cut, double *q,
+                   double *local_max_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
 int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, void *workspace,
                   size_t workspace_bytes, void *stream);
 
 /* Range partitioning of p-values over `nparts` GPUs for the global correction: part r receives the
  * rankable p-values (p != 1, not NaN) whose order-preserving key lies in [splitter[r-1], splitter[r]).
+ * p_cut (every entry point below and fhc_bh_prepare): p-values >= p_cut are not ranked and get q = 1.0 directly.
+ * fhc_bh_p_cut(T, rank_bound) returns the smallest safe value when no rank exceeds rank_bound (the total number of lines):
+ * (p*T)/rank >= 1 there, which the reference caps at 1 and the forward running max then keeps at exactly 1.0
+ * (fithic/myStats.py:36-43).  Pass INFINITY to rank everything.  fhc_bh_qvalues applies the bound internally.
  *   fhc_bh_sample_keys      keys of nsamples evenly strided p-values (UINT64_MAX where the sample is not rankable)
  *   fhc_bh_key_of           the key of one p-value (host)
  *   fhc_bh_partition_count  counts[r] = rankable p-values of part r
  *   fhc_bh_partition_scatter send[] = p-values grouped by part (cursors[r] [dev] = first slot of part r on entry),
  *                           idx[j] = line of send[j]; q[i] = 1.0 / NaN is written for the p-values that are not ranked
  *   fhc_scatter_f64         dst[idx[j]] = src[j]  (q-values coming back from the owning GPU) */
-int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, uint64_t *keys_out, void *stream);
+double fhc_bh_p_cut(double T, double rank_bound);
+int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out, void *stream);
 uint64_t fhc_bh_key_of(double p);
-int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, uint64_t *counts,
-                           void *stream);
-int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
+int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
+                           uint64_t *counts, void *stream);
+int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
                              uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream);
 int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n, double *dst, void *stream);
 

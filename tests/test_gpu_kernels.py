@@ -238,6 +238,10 @@ def test_bh_matches_oracle_bit_exact(lib, n):
         assert ns == int(np.sum(p < 1.0))
         if ns:
             assert carry == np.nanmax(want[p < 1.0])
+    # T far above the number of lines (the usual case: possible pairs >> observed lines): almost nothing is ranked
+    if n:
+        got, carry, ns = gpu_bh(lib, p, 1000 * n)
+        assert np.array_equal(got, O.benjamini_hochberg(p, 1000 * n), equal_nan=True)
 
 
 def test_bh_chained_partitions(lib):

@@ -26,7 +26,10 @@ class NumpyOps:
     def empty(self, n, dtype):
         return torch.empty(int(n), dtype=dtype)
 
-    def sample_keys(self, p, nsamples):
+    def p_cut(self, T, rank_bound):
+        return float(_capi.load().fhc_bh_p_cut(float(T), float(rank_bound)))
+
+    def sample_keys(self, p, nsamples, p_cut):
         p = p.numpy()
         n = len(p)
         stride = n // nsamples if n > nsamples else 1
@@ -35,7 +38,7 @@ class NumpyOps:
         ok = idx < n
         v = p[idx[ok]]
         k = key_of(v)
-        k[(v == 1.0) | np.isnan(v)] = U64_NONE
+        k[(v == 1.0) | np.isnan(v) | (v >= p_cut)] = U64_NONE
         keys[ok] = k
         return torch.from_numpy(keys.view(np.int64))
 
@@ -46,17 +49,20 @@ class NumpyOps:
         k = key_of(p)
         return np.searchsorted(np.asarray(splitters, dtype=np.uint64), k, side="right")
 
-    def partition_count(self, p, splitters):
+    def partition_count(self, p, splitters, p_cut):
         p = p.numpy()
-        ok = ~((p == 1.0) | np.isnan(p))
+        with np.errstate(invalid="ignore"):
+            ok = ~((p == 1.0) | np.isnan(p) | (p >= p_cut))
         return torch.from_numpy(np.bincount(self._part(p[ok], splitters), minlength=len(splitters) + 1).astype(np.int64))
 
-    def partition_scatter(self, p, splitters, send_offsets, q):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut):
         p = p.numpy()
         qn = q.numpy()
-        qn[p == 1.0] = 1.0
+        with np.errstate(invalid="ignore"):
+            one = (p == 1.0) | (p >= p_cut)
+        qn[one] = 1.0
         qn[np.isnan(p)] = np.nan
-        ok = np.nonzero(~((p == 1.0) | np.isnan(p)))[0]
+        ok = np.nonzero(~(one | np.isnan(p)))[0]
         part = self._part(p[ok], splitters)
         order = np.argsort(part, kind="stable")
         send = np.zeros(len(p))
@@ -100,7 +106,9 @@ def _worker(rank, world, port, tmp):
         want = want[:cut] if rank == 0 else want[cut:]
         assert np.array_equal(q.numpy(), want, equal_nan=True), "global BH differs on rank %d" % rank
         cm = ctx.last_plan["count_matrix"]
-        assert cm.sum() == np.sum(~((p_all == 1.0) | np.isnan(p_all)))
+        with np.errstate(invalid="ignore"):
+            assert cm.sum() == np.sum(~((p_all == 1.0) | np.isnan(p_all) | (p_all >= ctx.last_plan["p_cut"])))
+        assert 0.2 < ctx.last_plan["p_cut"] < 0.3  # 60,001 lines / T = 250,000: three quarters of the lines are not ranked
         assert abs(cm[:, 0].sum() - cm[:, 1].sum()) < 0.1 * cm.sum()  # the sample balances the two key ranges
 
         # exchange 1: histogram + seen bits + totals

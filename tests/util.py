@@ -85,8 +85,10 @@ def compare_pass(r, o, tol=1e-6, check_ones=True):
         assert np.array_equal(p == 1.0, o["p"] == 1.0), "p == 1.0 class differs"
     out["p"] = rel_err(p, o["p"])
     out["q"] = rel_err(q, o["q"])
-    out["expcc"] = rel_err(e, o["expcc"])
-    assert out["p"] <= tol and out["q"] <= tol and out["expcc"] <= 1e-12, out
+    if "expcc" in o:  # the reference fixtures carry p and q only (ExpCC is printed with %f)
+        out["expcc"] = rel_err(e, o["expcc"])
+        assert out["expcc"] <= 1e-12, out
+    assert out["p"] <= tol and out["q"] <= tol, out
     return out
 
 
