@@ -450,10 +450,12 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;
     P.expcc = expcc;
-    static int occ = -1;  // resident CTAs per SM: 2 (no spills, 116 registers) or 3 (80 registers); FHC_PVAL_OCC overrides
+    // resident CTAs per SM: 3 (80 registers, ~130 B of spills outside the loops; measured 15.6 ms at 300 M contacts) or
+    // 2 (116 registers, no spills; 18.5 ms).  FHC_PVAL_OCC=2 selects the latter for experiments.
+    static int occ = -1;
     if (occ < 0) {
         const char *e = getenv("FHC_PVAL_OCC");
-        occ = (e && atoi(e) == 3) ? 3 : 2;
+        occ = (e && atoi(e) == 2) ? 2 : 3;
     }
     long long blocks = (n + kPvalTile - 1) / kPvalTile;
     const long long cap = (long long)kNumSMs * occ;  // persistent CTAs, grid-stride over tiles
