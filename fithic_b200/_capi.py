@@ -40,6 +40,10 @@ _SIGNATURES = {
     "fhc_spline_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_spline_table": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_double, c_double, c_int32,
                                          c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "fhc_spline_eval": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_host_antitonic": (ctypes.c_int, [c_void_p, c_int64]),
+    "fhc_spline_lut": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p, c_int64,
+                                       c_void_p]),
     "fhc_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_void_p]),
     "fhc_host_log_cr": (c_double, [c_double]),
     "fhc_host_lbeta": (c_double, [c_double, c_double]),

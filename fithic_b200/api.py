@@ -35,15 +35,28 @@ def significance(contacts, fragments, settings, biases=None, engine=None, out=No
     if out is None or out.n != n:
         out = HostBuffers(n)
     outl, stats = eng.new_outlier_state()
+    main = torch.cuda.current_stream(eng.device)
+    copy = getattr(eng, "_copy_stream", None)
+    if copy is None:
+        copy = eng._copy_stream = torch.cuda.Stream(device=eng.device)
     results = []
     for passNo in range(1, settings.noOfPasses + 1):
         if passNo > 1 and settings.interOnly:
             break
-        r = eng.run_pass(passNo, outl, stats)
-        out.p.copy_(r["p"], non_blocking=True)
+
+        def start_copies(p, e):
+            # p and ExpCC leave for the host on a second stream while K4 (sort + scan) runs on the first
+            ev = torch.cuda.Event()
+            ev.record(main)
+            copy.wait_stream(main)
+            with torch.cuda.stream(copy):
+                out.p.copy_(p, non_blocking=True)
+                out.expcc.copy_(e, non_blocking=True)
+
+        r = eng.run_pass(passNo, outl, stats, after_pvalues=start_copies)
         out.q.copy_(r["q"], non_blocking=True)
-        out.expcc.copy_(r["expcc"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        copy.synchronize()
         last = passNo == settings.noOfPasses or settings.interOnly
         r["p"] = out.p.numpy() if last else out.p.numpy().copy()
         r["q"] = out.q.numpy() if last else out.q.numpy().copy()

@@ -13,6 +13,8 @@
 //      is compacted.  Pooling adjacent violators in any order gives the unique antitonic least-squares fit.
 //   3. a second kernel fills lut[k] for every distance slot.
 #define FHC_PROFILE_STREAM st
+#include <vector>
+
 #include "common.cuh"
 
 namespace fhc {
@@ -171,6 +173,12 @@ spline_pava_kernel(const double *__restrict__ t, const double *__restrict__ c, i
     }
 }
 
+__global__ void spline_eval_kernel(const double *__restrict__ t, const double *__restrict__ c, int nt,
+                                   const long long *__restrict__ splineX, long long m, double *__restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) y[i] = splev3(t, c, nt, (double)splineX[i]);
+}
+
 __global__ void spline_lut_kernel(const long long *__restrict__ splineX, const double *__restrict__ table, long long m,
                                   double xmin, double xmax, unsigned int res, double *__restrict__ lut, long long D) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,5 +229,67 @@ extern "C" int fhc_spline_table(const double *t, const double *c, int32_t nt, co
             reinterpret_cast<const long long *>(splineX), table, m, xmin, xmax, (unsigned int)res, lut, D);
         FHC_LAUNCH_CHECK("spline_lut_kernel");
     }
+    return FHC_OK;
+}
+
+// ---- the same stages one by one ------------------------------------------------------------------------------------
+// PAVA is a sequential scan whose merge cascade can run over thousands of blocks (a rising tail of the spline pools
+// back over most of the curve: 5,931 dependent steps at the top of the merge tree on the 5 kb whole-genome bench
+// input, 1.6 ms in spline_pava_kernel).  A CPU core does the whole scan from L1 in ~0.1 ms, so for large tables the
+// engine evaluates the spline on the device (bit exact, parallel), pools on the host and builds the lookup table on
+// the device again.
+extern "C" int fhc_spline_eval(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m, double *y,
+                               void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(t && c && splineX && y, FHC_E_INVALID, "fhc_spline_eval: null pointer");
+    FHC_REQUIRE(nt >= 8 && m > 0, FHC_E_INVALID, "fhc_spline_eval: need nt >= 8 and m > 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    spline_eval_kernel<<<(unsigned int)((m + 127) / 128), 128, 0, st>>>(t, c, nt, reinterpret_cast<const long long *>(splineX),
+                                                                       m, y);
+    FHC_LAUNCH_CHECK("spline_eval_kernel");
+    return FHC_OK;
+}
+
+// IsotonicRegression(increasing=False).fit_transform with unit weights (fithic/fithic.py:965-966): pool adjacent
+// violators, every point takes the mean of its block.  In place on a host array.
+extern "C" int fhc_host_antitonic(double *y, int64_t m) {
+    FHC_REQUIRE(m >= 0 && (m == 0 || y != nullptr), FHC_E_INVALID, "fhc_host_antitonic: bad arguments");
+    if (m == 0) return FHC_OK;
+    std::vector<double> sum;
+    std::vector<int64_t> cnt;
+    sum.reserve((size_t)m);
+    cnt.reserve((size_t)m);
+    for (int64_t i = 0; i < m; ++i) {
+        double s = y[i];
+        int64_t c = 1;
+        // non-increasing: the previous block violates when its mean is below the new block's mean
+        while (!sum.empty() && sum.back() * (double)c < s * (double)cnt.back()) {
+            s += sum.back();
+            c += cnt.back();
+            sum.pop_back();
+            cnt.pop_back();
+        }
+        sum.push_back(s);
+        cnt.push_back(c);
+    }
+    int64_t i = 0;
+    for (size_t b = 0; b < sum.size(); ++b) {
+        const double mean = sum[b] / (double)cnt[b];
+        for (int64_t k = 0; k < cnt[b]; ++k) y[i++] = mean;
+    }
+    return FHC_OK;
+}
+
+extern "C" int fhc_spline_lut(const int64_t *splineX, const double *table, int64_t m, double xmin, double xmax,
+                              int32_t res, double *lut, int64_t D, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(splineX && table && lut && m > 0 && D > 0 && res > 0, FHC_E_INVALID, "fhc_spline_lut: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    const int threads = 256;
+    spline_lut_kernel<<<(unsigned int)((D + threads - 1) / threads), threads, 0, st>>>(
+        reinterpret_cast<const long long *>(splineX), table, m, xmin, xmax, (unsigned int)res, lut, D);
+    FHC_LAUNCH_CHECK("spline_lut_kernel");
     return FHC_OK;
 }

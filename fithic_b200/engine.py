@@ -164,16 +164,19 @@ class Engine:
     def hist_distance(self, skip=None, skip_limit=-1):
         D = self.distance_slots()
         mid1, mid2, cnt, chrs = self.contacts
-        hist = self._tensor("hist", D, torch.int64)
-        present = self._tensor("present", (D + 31) // 32, torch.int32)
-        scal = self._tensor("scalars", _capi.N_SCALARS, torch.int64)
+        # one buffer [hist | totals | seen bitmap] so that the host needs a single device->host copy per pass
+        nwords = (D + 31) // 32
+        buf = self._tensor("k1buf", D + _capi.N_SCALARS + (nwords + 1) // 2, torch.int64)
+        hist = buf[:D]
+        scal = buf[D:D + _capi.N_SCALARS]
+        present = buf[D + _capi.N_SCALARS:].view(torch.int32)[:nwords]
         check(self.lib.fhc_hist_distance(dptr(mid1), dptr(mid2), dptr(cnt), dptr(chrs), dptr(skip), int(skip_limit),
                                          self.n, self.st.L, self.st.U, self.st.resolution, dptr(hist), dptr(present), D,
                                          dptr(scal), self._stream()))
         return hist, present, scal
 
     # ------------------------------------------------------------------------------------------------------------
-    def run_pass(self, passNo, outl=None, outl_stats=None, keep_q_on_device=True):
+    def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
         st, lib = self.st, self.lib
         res = st.resolution
@@ -189,9 +192,10 @@ class Engine:
         if self.dist is not None:
             self.dist.allreduce_hist(hist_d, present_d, scal_d)
         D = self.D
-        hist = hist_d.cpu().numpy()
-        present = present_d.cpu().numpy().view(np.uint32)
-        scal = scal_d.cpu().numpy()
+        hbuf = self._ws["k1buf"][:D + _capi.N_SCALARS + ((D + 31) // 32 + 1) // 2].cpu().numpy()
+        hist = hbuf[:D]
+        scal = hbuf[D:D + _capi.N_SCALARS]
+        present = hbuf[D + _capi.N_SCALARS:].view(np.uint32)[:(D + 31) // 32]
         if int(scal[_capi.S_OFFGRID]) != 0:
             raise ValueError("%d in-range intra contacts have a distance that is not a multiple of the resolution %d "
                              "(or beyond the fragment list); only fixed-size bins on a common grid are supported"
@@ -243,6 +247,8 @@ class Engine:
         thres = (1.0 / T) if T != 0 else float("inf")
         out["outlierThres"] = thres
         p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, max_count, outl, thres, outl_stats)
+        if after_pvalues is not None:
+            after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
         # ---- K4 ----
         if self.dist is not None:
             q = self.dist.global_bh(self, p, float(T))
@@ -256,6 +262,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     # K2
+    HOST_PAVA_MIN_POINTS = 4096  # above this the pooling runs on the host (see csrc/spline.cu)
+
     def spline_table(self, tck, splineX, xmin, xmax):
         t, c, k = tck
         assert k == 3
@@ -269,10 +277,19 @@ class Engine:
         nt = len(t)
         table = self._tensor("table", m, torch.float64)
         lut = self._tensor("lut", D, torch.float64)
-        wsb = int(self.lib.fhc_spline_workspace_bytes(m))
-        ws = self._buf("spline_ws", wsb)
-        check(self.lib.fhc_spline_table(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(sx), m, float(xmin), float(xmax),
-                                        self.st.resolution, dptr(table), dptr(lut), D, dptr(ws), wsb, self._stream()))
+        res = self.st.resolution
+        if m < self.HOST_PAVA_MIN_POINTS:
+            wsb = int(self.lib.fhc_spline_workspace_bytes(m))
+            ws = self._buf("spline_ws", wsb)
+            check(self.lib.fhc_spline_table(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(sx), m, float(xmin), float(xmax), res,
+                                            dptr(table), dptr(lut), D, dptr(ws), wsb, self._stream()))
+        else:
+            check(self.lib.fhc_spline_eval(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(sx), m, dptr(table), self._stream()))
+            y = table.cpu().numpy()
+            check(self.lib.fhc_host_antitonic(dptr(y), m))
+            table.copy_(torch.from_numpy(y))
+            check(self.lib.fhc_spline_lut(dptr(sx), dptr(table), m, float(xmin), float(xmax), res, dptr(lut), D,
+                                          self._stream()))
         self._keep = (tc, sx)  # keep the small inputs alive until the stream has consumed them
         return table, lut
 

@@ -104,6 +104,17 @@ int fhc_spline_table(const double *t, const double *c, int32_t nt, const int64_t
                      double xmax, int32_t res, double *table, double *lut, int64_t D, void *workspace,
                      size_t workspace_bytes, void *stream);
 
+/* The three stages of fhc_spline_table one by one, for callers that pool on the host (the PAVA cascade is a chain of
+ * dependent steps; a CPU core runs it from L1 faster than one GPU thread from L2 when the table is large):
+ *   fhc_spline_eval      y[j] = splev(t, c, 3, splineX[j])                      [dev]
+ *   fhc_host_antitonic   y <- IsotonicRegression(increasing=False)(y), in place [host]
+ *   fhc_spline_lut       lut[k] = table[min(bisect_left(splineX, clamp(k*res, xmin, xmax)), m-1)]   [dev] */
+int fhc_spline_eval(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m, double *y,
+                    void *stream);
+int fhc_host_antitonic(double *y, int64_t m);
+int fhc_spline_lut(const int64_t *splineX, const double *table, int64_t m, double xmin, double xmax, int32_t res,
+                   double *lut, int64_t D, void *stream);
+
 /* ---- lbeta table -----------------------------------------------------------------------------------------------
  * tab[c] = cephes lbeta(c, N - c + 1) for 1 <= c < ntab, the only third-party quantity whose ROUNDING matters at
  * 1e-6: scipy.special.bdtrc -> xsf::cephes::incbet -> lbeta, reached from fithic/fithic.py:1070,:1101. */

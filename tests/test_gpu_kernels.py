@@ -290,6 +290,18 @@ def test_spline_table(lib, m, noise):
     got = table.cpu().numpy()
     assert np.all(np.diff(got) <= 0)
     assert np.allclose(got, want, rtol=1e-12, atol=1e-25), np.max(np.abs(got - want) / np.abs(want))
+    # the staged variant (device splev, host pooling, device lookup table) gives the same table
+    y = torch.empty(mm, dtype=torch.float64, device=DEV)
+    check(lib.fhc_spline_eval(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(dsx), mm, dptr(y), stream()))
+    torch.cuda.synchronize()
+    yh = y.cpu().numpy()
+    assert np.array_equal(yh, splineY)  # FITPACK splev, bit for bit
+    check(lib.fhc_host_antitonic(dptr(yh), mm))
+    assert np.allclose(yh, got, rtol=1e-13, atol=1e-25)
+    lut2 = torch.empty(D, dtype=torch.float64, device=DEV)
+    check(lib.fhc_spline_lut(dptr(dsx), dptr(table), mm, float(xk.min()), float(xk.max()), res, dptr(lut2), D, stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(lut2.cpu().numpy(), lut.cpu().numpy())
     # lookup semantics of fithic/fithic.py:1066-1068
     dl = np.clip(np.arange(D, dtype=np.float64) * res, xk.min(), xk.max())
     idx = np.minimum(np.searchsorted(sx.astype(np.float64), dl, side="left"), mm - 1)

@@ -199,3 +199,17 @@ def test_synthetic_generator_is_deterministic():
     loads = [sum(int(synth.genome(None)[1][i]) for i in s) for s in shards]
     assert sorted(i for s in shards for i in s) == list(range(24))
     assert max(loads) / (sum(loads) / 8) < 1.05
+
+
+def test_host_antitonic_matches_sklearn(lib):
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(12)
+    for m, noise in ((1, 0.0), (7, 1.0), (500, 0.3), (20000, 0.05)):
+        y = 1e-3 * (np.arange(m) + 1.0) ** -1.1 * np.exp(noise * rng.normal(size=m))
+        if m > 100:
+            y[-m // 3:] = y[-m // 3:][::-1]  # a rising tail: one long cascade
+        want = IsotonicRegression(increasing=False).fit_transform(np.arange(m), y)
+        got = y.copy()
+        _capi.check(lib.fhc_host_antitonic(_capi.dptr(got), m))
+        assert np.all(np.diff(got) <= 0)
+        assert np.allclose(got, want, rtol=1e-12, atol=0)
