@@ -250,6 +250,13 @@ __device__ __forceinline__ void cf_init(CfState &s, double a, double b, double x
     s.fi = 0.0;
     s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0;
 }
+// the same from a precomputed z (pvalue.cu prepares z for a whole work list in one uniform pass)
+__device__ __forceinline__ void cf_load(CfState &s, double a, double b, double z, bool use_d) {
+    s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
+    s.z = z;
+    s.fi = 0.0;
+    s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0;
+}
 
 // one iteration (two recurrence steps, updated in place: after step 1 the slot "km2" holds the newest convergent, after
 // step 2 "km1" does again); returns true when the fraction has converged (or hit the iteration cap)
@@ -292,18 +299,33 @@ __device__ __forceinline__ bool cf_step(CfState &s) {
 // The sum S = P/Q gives  I_{1-x}(b, a) = (1-x)^b x^a / (b B(a, b)) * (S / x),  S / x being what cephes' fraction stands for.
 // The state lives in the fields of a CfState (a lane works on one kind at a time, pvalue.cu):
 //   P = pkm1, Q = qkm1 (so the value is pkm1 / qkm1 for both kinds), j = fi, d = dprev, cN = z, invN = a, terms left = bm1
-__device__ __forceinline__ void tail_init(CfState &s, double count, double N, double x, double one_minus_x) {
+// number of terms and the per-term factor (1-x)/(x N): the expensive part of the set-up
+__device__ __forceinline__ void tail_prepare(double count, double N, double invN, double x, double one_minus_x, double &cN,
+                                             int &M) {
     const double k = count - 1.0;
-    s.a = 1.0 / N;
-    s.z = (one_minus_x / x) * s.a;
-    const double r = k / (N * x);
-    double M = k;
-    if (r > 0.0 && r < 1.0) M = fmin(M, ceil(-39.2 / log(r)) + 1.0);
-    M = fmin(M, ceil(sqrt(78.4 * k)) + 1.0);
+    cN = (one_minus_x / x) * invN;
+    double Md = k;
+    if (k > 24.0) {  // for short sums the bound cannot beat k by much: skip the log and the square root
+        const double r = k / (N * x);
+        if (r > 0.0 && r < 1.0) Md = fmin(Md, ceil(-39.2 / log(r)) + 1.0);
+        Md = fmin(Md, ceil(sqrt(78.4 * k)) + 1.0);
+    }
+    M = (int)Md;
+}
+__device__ __forceinline__ void tail_load(CfState &s, double count, double N, double invN, double cN, int M) {
+    s.a = invN;
+    s.z = cN;
     s.pkm1 = 1.0; s.qkm1 = 1.0;
-    s.fi = k - M + 1.0;
-    s.dprev = (N - s.fi + 1.0) * s.a;
-    s.bm1 = M;
+    s.fi = count - (double)M;  // k - M + 1
+    s.dprev = (N - s.fi + 1.0) * invN;
+    s.bm1 = (double)M;
+}
+__device__ __forceinline__ void tail_init(CfState &s, double count, double N, double x, double one_minus_x) {
+    double cN;
+    int M;
+    const double invN = 1.0 / N;
+    tail_prepare(count, N, invN, x, one_minus_x, cN, M);
+    tail_load(s, count, N, invN, cN, M);
 }
 
 // one term; returns true when the sum is complete
@@ -370,7 +392,12 @@ __device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb,
         if (cf_uses_d(aa, bb, xx)) w = w / w1;
         div = aa;
     }
-    double t = aa * log(xx) + bb * log(w1) - lbeta_ab + log(w / div);
+    // log(w1): w1 - 1 is exact, and for the tiny priors of sparse maps a four-term series of log1p is exact to 1e-21
+    const double y1 = w1 - 1.0;
+    const double logw1 = (y1 > -7.62939453125e-06)
+                             ? y1 * (1.0 + y1 * (-0.5 + y1 * (0.33333333333333331 + y1 * -0.25)))
+                             : log(w1);
+    double t = aa * log(xx) + bb * logw1 - lbeta_ab + log(w / div);
     t = t < kMINLOG ? 0.0 : exp(t);
     if (tail) t = (t <= kMACHEP) ? 1.0 - kMACHEP : 1.0 - t;
     return t;
