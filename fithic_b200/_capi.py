@@ -50,7 +50,7 @@ _SIGNATURES = {
     "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_bdtrc": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,

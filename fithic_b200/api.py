@@ -44,16 +44,15 @@ def significance(contacts, fragments, settings, biases=None, engine=None, out=No
         if passNo > 1 and settings.interOnly:
             break
 
-        def start_copies(p, e):
-            # p and ExpCC leave for the host on a second stream while K4 (sort + scan) runs on the first
-            ev = torch.cuda.Event()
-            ev.record(main)
+        def copy_slice(lo, hi, p, e):
+            # finished slices of p and ExpCC leave for the host on a second stream while K3 works on the next slice and
+            # K4 (sort + scan) runs afterwards: the PCIe link is the bottleneck of the end-to-end call
             copy.wait_stream(main)
             with torch.cuda.stream(copy):
-                out.p.copy_(p, non_blocking=True)
-                out.expcc.copy_(e, non_blocking=True)
+                out.p[lo:hi].copy_(p[lo:hi], non_blocking=True)
+                out.expcc[lo:hi].copy_(e[lo:hi], non_blocking=True)
 
-        r = eng.run_pass(passNo, outl, stats, after_pvalues=start_copies)
+        r = eng.run_pass(passNo, outl, stats, pvalue_chunks=8 if n >= (1 << 22) else 1, after_chunk=copy_slice)
         out.q.copy_(r["q"], non_blocking=True)
         main.synchronize()
         copy.synchronize()

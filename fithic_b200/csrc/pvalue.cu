@@ -53,6 +53,7 @@ struct PvalParams {
     const double *lbeta_intra, *lbeta_inter;
     long long ntab_intra, ntab_inter;
     unsigned char *outl;
+    long long line_base;  // index of the first contact of this call in the whole file (for the outlier statistics)
     double outl_thres;
     unsigned long long *outl_stats;
     double *p, *expcc;
@@ -124,7 +125,7 @@ __device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, d
         const unsigned char m2 = m == 255 ? 255 : m + 1;
         P.outl[i] = m2;
         flagged += 1;
-        if (m2 >= 2) atomicMin(P.outl_stats + 1, (unsigned long long)i);
+        if (m2 >= 2) atomicMin(P.outl_stats + 1, (unsigned long long)(P.line_base + i));
     }
 }
 
@@ -408,8 +409,8 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
                            const int64_t *chr_off, int32_t nchr, int32_t res, int64_t L, int64_t U, const double *lut,
                            int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
                            const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
-                           uint8_t *outl, double outl_thres, uint64_t *outl_stats, double *p, double *expcc,
-                           void *stream) {
+                           uint8_t *outl, int64_t line_base, double outl_thres, uint64_t *outl_stats, double *p,
+                           double *expcc, void *stream) {
     using namespace fhc;
     FHC_REQUIRE(mode == FHC_MODE_INTRA_ONLY || mode == FHC_MODE_INTER_ONLY || mode == FHC_MODE_ALL, FHC_E_INVALID,
                 "fhc_pvalues: unknown mode %d", mode);
@@ -457,6 +458,7 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.lbeta_inter = lbeta_inter;
     P.ntab_inter = lbeta_inter ? ntab_inter : 0;
     P.outl = outl;
+    P.line_base = line_base;
     P.outl_thres = outl_thres;
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;

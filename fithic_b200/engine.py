@@ -176,7 +176,7 @@ class Engine:
         return hist, present, scal
 
     # ------------------------------------------------------------------------------------------------------------
-    def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None):
+    def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
         st, lib = self.st, self.lib
         res = st.resolution
@@ -246,7 +246,8 @@ class Engine:
         # ---- K3 ----
         thres = (1.0 / T) if T != 0 else float("inf")
         out["outlierThres"] = thres
-        p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, max_count, outl, thres, outl_stats)
+        p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, max_count, outl, thres, outl_stats, pvalue_chunks,
+                            after_chunk)
         if after_pvalues is not None:
             after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
         # ---- K4 ----
@@ -301,7 +302,10 @@ class Engine:
         return tab, ntab
 
     # K3  (fit_Spline per-line loop, fithic/fithic.py:1017-1123)
-    def pvalues(self, lut, N_intra, N_inter, interChrProb, max_count, outl=None, outl_thres=0.0, outl_stats=None):
+    def pvalues(self, lut, N_intra, N_inter, interChrProb, max_count, outl=None, outl_thres=0.0, outl_stats=None,
+                nchunks=1, after_chunk=None):
+        """nchunks > 1 launches K3 once per contiguous slice of the contacts and calls after_chunk(lo, hi, p, e) after
+        each launch, so that a caller can start moving finished slices to the host while the next one is computed."""
         st = self.st
         mid1, mid2, cnt, chrs = self.contacts
         n = self.n
@@ -318,11 +322,22 @@ class Engine:
         if self._bias_dev is not None:
             bias, bmid, boff = self._bias_dev
             nchr = boff.numel() - 1
-        check(self.lib.fhc_pvalues(st.mode, dptr(mid1), dptr(mid2), dptr(cnt), dptr(chrs), n, dptr(bias), dptr(bmid),
-                                   dptr(boff), nchr, st.resolution, st.L, st.U, dptr(lut), self.D if lut is not None else 0,
-                                   int(N_intra), int(N_inter), float(interChrProb), float(st.biasLowerBound),
-                                   float(st.biasUpperBound), dptr(tab_a), nta, dptr(tab_b), ntb, dptr(outl),
-                                   float(outl_thres), dptr(outl_stats), dptr(p), dptr(e), self._stream()))
+        step = n if nchunks <= 1 else max(((n + nchunks - 1) // nchunks + 4095) // 4096 * 4096, 4096)
+        lo = 0
+        while True:
+            hi = min(lo + step, n)
+            o = None if outl is None else outl[lo:hi]
+            check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]), dptr(chrs[lo:hi]),
+                                       hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr, st.resolution, st.L, st.U,
+                                       dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
+                                       float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
+                                       nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),
+                                       dptr(e[lo:hi]), self._stream()))
+            if after_chunk is not None:
+                after_chunk(lo, hi, p, e)
+            lo = hi
+            if lo >= n:
+                break
         return p, e
 
     # K4  (myStats.benjamini_hochberg_correction, fithic/myStats.py:24-48)

@@ -137,12 +137,14 @@ double fhc_host_lbeta(double a, double b);
  *   outl       nullable per-line outlier multiplicity, incremented where p < outl_thres (:1215-1217);
  *              outl_stats[0] += lines flagged now, outl_stats[1] = min(itself, line index whose multiplicity reached
  *              >= 2) -- the caller initialises outl_stats to {0, UINT64_MAX} before the first pass
+ *   line_base  index in the whole file of the first contact passed (a caller may score the file slice by slice; the
+ *              index is only used for outl_stats[1])
  *   p, expcc   outputs, one double per line (:1119-1122) */
 int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
                 int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
                 int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
                 double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
-                const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, double outl_thres,
+                const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, int64_t line_base, double outl_thres,
                 uint64_t *outl_stats, double *p, double *expcc, void *stream);
 
 /* scipy.special.bdtrc(k, n, prior) element-wise on device arrays (the arithmetic core of K3, exposed for parity

@@ -58,3 +58,31 @@ def test_pipeline_matches_oracle(lib, case):
         lines = np.repeat(np.arange(len(contacts)), r["outl"])
         assert np.array_equal(lines, np.asarray(o["outliersline"], dtype=np.int64)), name
         print(name, "pass", r["passNo"], errs, "outliers", len(lines))
+
+
+def test_api_sliced_pvalues_match_single_launch(lib):
+    """api.significance scores large inputs slice by slice (device->host copies overlap the next slice); results,
+    outlier multiplicities and the first-duplicate statistic must not depend on the slicing."""
+    from fithic_b200 import api
+    from fithic_b200.engine import Contacts
+    dev = torch.device("cuda", 0)
+    n = (1 << 22) + 12345
+    (mid1, mid2, cnt, chrs), frags, biases, _ = synth.make_intra_device(n, 10000, 77, dev, mean_count=3.0, with_bias=True)
+    st = Settings(resolution=10000, noOfBins=100, noOfPasses=2)
+    eng = Engine(st, frags, biases, device=dev)
+    eng.set_contacts_device(mid1, mid2, cnt, chrs)
+    outl, stats = eng.new_outlier_state()
+    ref = None
+    for passNo in (1, 2):
+        ref = eng.run_pass(passNo, outl, stats)
+    torch.cuda.synchronize()
+    want = {k: ref[k].cpu().numpy().copy() for k in ("p", "q", "expcc")}
+    want_outl, want_stats = outl.cpu().numpy().copy(), stats.cpu().numpy().copy()
+    host = Contacts(mid1.cpu().numpy(), mid2.cpu().numpy(), cnt.cpu().numpy(), chrs.cpu().numpy().view(np.uint32),
+                    list(frags.chroms))
+    eng2 = Engine(st, frags, biases, device=dev)
+    got = api.significance(host, frags, st, biases, engine=eng2)
+    assert len(got) == 2
+    for k in ("p", "q", "expcc"):
+        assert np.array_equal(got[-1][k], want[k], equal_nan=True), k
+    assert got[-1]["N"] == ref["N"] and got[-1]["T"] == ref["T"]
