@@ -68,6 +68,16 @@ _SIGNATURES = {
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                            c_void_p]),
+    "fhc_io_format_double": (ctypes.c_int, [c_double, ctypes.c_int, c_char_p]),
+    "fhc_io_read_contacts": (c_void_p, [c_char_p]),
+    "fhc_io_contacts_n": (c_int64, [c_void_p]),
+    "fhc_io_contacts_nchrom": (c_int32, [c_void_p]),
+    "fhc_io_contacts_chrom": (c_char_p, [c_void_p, c_int32]),
+    "fhc_io_contacts_copy": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fhc_io_free": (None, [c_void_p]),
+    "fhc_io_write_significances": (c_int64, [c_char_p, ctypes.POINTER(c_char_p), c_int32, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
+                                             c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "fhc_outlier_bin_decrements": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                                    c_void_p]),
 }

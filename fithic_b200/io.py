@@ -6,6 +6,7 @@ work (the reference spends most of its wall time here); the arrays they produce 
 import gzip
 import io as _io
 import math
+import os
 
 import numpy as np
 import pandas as pd
@@ -20,7 +21,28 @@ def _open_text(path):
 
 
 def read_contacts(path):
-    """contactCounts file: chr1 mid1 chr2 mid2 count, whitespace separated (fithic/fithic.py:413-417)."""
+    """contactCounts file: chr1 mid1 chr2 mid2 count, whitespace separated (fithic/fithic.py:413-417).
+    Native reader (csrc/textio.cu): one thread inflates, one parses straight into the int32 arrays."""
+    from . import _capi
+    lib = _capi.load()
+    h = lib.fhc_io_read_contacts(os.fsencode(path))
+    if not h:
+        raise ValueError(lib.fhc_last_error().decode("utf-8", "replace"))
+    try:
+        n = int(lib.fhc_io_contacts_n(h))
+        chroms = [lib.fhc_io_contacts_chrom(h, i).decode() for i in range(int(lib.fhc_io_contacts_nchrom(h)))]
+        m1 = np.empty(n, dtype=np.int32)
+        m2 = np.empty(n, dtype=np.int32)
+        cnt = np.empty(n, dtype=np.int32)
+        chrs = np.empty(n, dtype=np.uint32)
+        _capi.check(lib.fhc_io_contacts_copy(h, _capi.dptr(m1), _capi.dptr(m2), _capi.dptr(cnt), _capi.dptr(chrs)))
+    finally:
+        lib.fhc_io_free(h)
+    return Contacts(m1, m2, cnt, chrs, chroms)
+
+
+def read_contacts_pandas(path):
+    """The same through pandas (kept to cross-check the native reader in tests)."""
     df = pd.read_csv(path, sep=r"\s+", header=None, names=["c1", "m1", "c2", "m2", "n"], engine="c",
                      dtype={"c1": str, "c2": str, "m1": np.int64, "m2": np.int64, "n": np.float64},
                      compression="gzip", float_precision="round_trip")
@@ -120,8 +142,37 @@ def lookup_biases(biases, chr_ids, mids, resolution):
     return np.full(len(mids), -1.0)
 
 
+def write_significances_native(path, contacts, p, q, expcc, biases, settings, nthreads=None, level=6):
+    """`.significances.txt.gz` (fithic/fithic.py:1166-1212) through the native multi-threaded formatter + gzip
+    (csrc/textio.cu).  Returns the number of rows written."""
+    import ctypes
+    from . import _capi
+    lib = _capi.load()
+    st = settings
+    n = len(contacts)
+    names = (ctypes.c_char_p * len(contacts.chroms))(*[c.encode() for c in contacts.chroms])
+    arr = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    m1, m2, cnt, chrs = arr(contacts.mid1, np.int32), arr(contacts.mid2, np.int32), arr(contacts.cnt, np.int32), \
+        arr(contacts.chrs, np.uint32)
+    p, q, e = arr(p, np.float64), arr(q, np.float64), arr(expcc, np.float64)
+    mode = _capi.MODE_ALL if st.allReg else (_capi.MODE_INTER_ONLY if st.interOnly else _capi.MODE_INTRA_ONLY)
+    U = -1 if math.isinf(st.distUpThres) else int(st.distUpThres)
+    bv = bm = bo = None
+    nb = 0
+    if biases is not None:
+        bv, bm, bo = arr(biases.values, np.float64), arr(biases.mids, np.int32), arr(biases.chr_off, np.int64)
+        nb = len(bo) - 1
+    if nthreads is None:
+        nthreads = min(os.cpu_count() or 1, 32)
+    rows = lib.fhc_io_write_significances(os.fsencode(path), names, len(contacts.chroms), _capi.dptr(m1), _capi.dptr(m2),
+                                          _capi.dptr(cnt), _capi.dptr(chrs), _capi.dptr(p), _capi.dptr(q), _capi.dptr(e),
+                                          n, mode, int(st.distLowThres), U, _capi.dptr(bv), _capi.dptr(bm), _capi.dptr(bo),
+                                          nb, int(st.resolution), int(nthreads), int(level))
+    return _capi.check(rows)
+
+
 def write_significances(path, contacts, p, q, expcc, bias1, bias2, settings, chunk=1 << 18):
-    """`.significances.txt.gz` (fithic/fithic.py:1166-1212): header + one row per reported line."""
+    """The same in pure Python (the reference's own formatting expression; used to cross-check the native writer)."""
     st = settings
     c1 = (contacts.chrs & 0xffff).astype(np.int64)
     c2 = (contacts.chrs >> 16).astype(np.int64)

@@ -206,6 +206,28 @@ int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out,
 int fhc_outlier_bin_decrements(const int32_t *mid1, const int32_t *mid2, const uint8_t *outl, int64_t n,
                                const int64_t *bin_ub, int32_t nbins, uint64_t *dec, void *stream);
 
+/* ---- text boundary (host) ---------------------------------------------------------------------------------------------
+ * Native replacements of the two text loops that dominate the reference's wall time once the kernels are fast:
+ * `for lines in gzip.open(contactCountsFile)` + split/int/float (fithic/fithic.py:406-417, :1017-1023) and the
+ * `.significances.txt.gz` writer (:1166-1212; header :1178, row format :1202/:1212).
+ *   fhc_io_read_contacts   parses `chr1 mid1 chr2 mid2 count` lines (whitespace separated, count = int(float(text)));
+ *                          returns a handle (NULL on error); chromosome ids are assigned in order of first appearance
+ *   fhc_io_contacts_*      size / chromosome names / copy into caller arrays; fhc_io_free releases the handle
+ *   fhc_io_write_significances  formats and gzips the reported rows with `nthreads` threads (multi-member gzip, `level`
+ *                          0-9); returns the number of rows written or a negative error code */
+int fhc_io_format_double(double v, int kind /* 'e' or 'f' */, char *out /* >= 400 bytes */); /* the writer's "%e" / "%f" */
+void *fhc_io_read_contacts(const char *path);
+int64_t fhc_io_contacts_n(void *handle);
+int32_t fhc_io_contacts_nchrom(void *handle);
+const char *fhc_io_contacts_chrom(void *handle, int32_t i);
+int fhc_io_contacts_copy(void *handle, int32_t *mid1, int32_t *mid2, int32_t *cnt, uint32_t *chrs);
+void fhc_io_free(void *handle);
+int64_t fhc_io_write_significances(const char *path, const char *const *chrom_names, int32_t nchrom, const int32_t *mid1,
+                                   const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs, const double *p,
+                                   const double *q, const double *expcc, int64_t n, int32_t mode, int64_t L, int64_t U,
+                                   const double *bias, const int32_t *bias_mid, const int64_t *chr_off,
+                                   int32_t nbias_chr, int32_t res, int32_t nthreads, int32_t level);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,10 @@ def test_io_round_trip_and_bias_semantics(tmp_path):
                                                     inter_fraction=0.2)
     cpath, fpath, bpath = synth.write_inputs(str(tmp_path), contacts, frags, 100000, raw, biases)
     c2 = fio.read_contacts(cpath)
+    cp = fio.read_contacts_pandas(cpath)  # the native reader against pandas
+    assert c2.chroms == cp.chroms
+    for k in ("mid1", "mid2", "cnt", "chrs"):
+        assert np.array_equal(getattr(c2, k), getattr(cp, k)), k
     names = c2.chroms
     m = {n: contacts.chroms.index(n) for n in names}
     remap = np.array([m[n] for n in names])
@@ -161,6 +165,17 @@ def test_io_round_trip_and_bias_semantics(tmp_path):
         f.write("c1\t5\tc1\t15\t2.9\nc1\t5\tc2\t25\t-1.5\n")
     c = fio.read_contacts(str(p))
     assert list(c.cnt) == [2, -1]
+    with gzip.open(p, "wt") as f:
+        f.write("c1  5 \t c1 15   7e2\n\nc1\t5\tc2\t25\t+3\n")  # mixed whitespace, blank line, exponent, sign
+    c = fio.read_contacts(str(p))
+    assert list(c.cnt) == [700, 3] and c.chroms == ["c1", "c2"] and list(c.mid2) == [15, 25]
+    for bad in ("c1\t5\tc1\t15\n", "c1\tx\tc1\t15\t2\n", "c1\t5\tc1\t15\tabc\n", "c1\t5\tc1\t15\t2\t9\n"):
+        with gzip.open(p, "wt") as f:
+            f.write(bad)
+        with pytest.raises(ValueError):
+            fio.read_contacts(str(p))
+    with pytest.raises(ValueError):
+        fio.read_contacts(str(tmp_path / "missing.gz"))
     bp = tmp_path / "b.gz"
     with gzip.open(bp, "wt") as f:
         f.write("c1\t5\t0.9\nc1\t5\t1.7\nc1\t15\tnan\nc1\t25\t2.5\nc1\t35\t0.4\n")
@@ -213,3 +228,58 @@ def test_host_antitonic_matches_sklearn(lib):
         _capi.check(lib.fhc_host_antitonic(_capi.dptr(got), m))
         assert np.all(np.diff(got) <= 0)
         assert np.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_native_writer_matches_python_formatting(tmp_path):
+    """fhc_io_write_significances against the reference's own formatting expression, row filters included."""
+    contacts, frags, biases, raw = synth.make_intra(70_000, 100000, 8, chroms=["chr20", "chr21", "chr22"], with_bias=True,
+                                                    inter_fraction=0.3)
+    n = len(contacts)
+    rng = np.random.default_rng(1)
+    p = rng.random(n) ** 8
+    p[rng.integers(0, n, 50)] = np.nan
+    p[rng.integers(0, n, 50)] = 1.0
+    p[rng.integers(0, n, 50)] = 1e-300
+    p[rng.integers(0, n, 50)] = 0.0
+    q = np.minimum(p * 3.7, 1.0)
+    e = rng.random(n) * 1e4
+    e[rng.integers(0, n, 100)] = 0.0
+    c1, c2 = contacts.chrs & 0xffff, contacts.chrs >> 16
+    b1 = fio.lookup_biases(biases, c1, contacts.mid1, 100000)
+    b2 = fio.lookup_biases(biases, c2, contacts.mid2, 100000)
+    for kw in (dict(), dict(allReg=True), dict(interOnly=True), dict(distLowThres=200000, distUpThres=5000000)):
+        st = Settings(resolution=100000, **kw)
+        a, b = str(tmp_path / "py.gz"), str(tmp_path / "native.gz")
+        rows_py = fio.write_significances(a, contacts, p, q, e, b1, b2, st)
+        rows_nat = fio.write_significances_native(b, contacts, p, q, e, biases, st, nthreads=3)
+        assert rows_py == rows_nat
+        with gzip.open(a, "rb") as fa, gzip.open(b, "rb") as fb:
+            assert fa.read() == fb.read()
+    # no bias table: both bias columns are 1
+    st = Settings(resolution=100000)
+    a, b = str(tmp_path / "py2.gz"), str(tmp_path / "native2.gz")
+    ones = np.ones(n)
+    fio.write_significances(a, contacts, p, q, e, ones, ones, st)
+    fio.write_significances_native(b, contacts, p, q, e, None, st, nthreads=1)
+    with gzip.open(a, "rb") as fa, gzip.open(b, "rb") as fb:
+        assert fa.read() == fb.read()
+
+
+def test_fast_double_formatting_is_printf(lib):
+    """The writer's own "%e" / "%f" (one extended-precision multiply, printf only near ties) against Python's."""
+    import ctypes
+    import struct
+    buf = ctypes.create_string_buffer(512)
+    rng = np.random.default_rng(2)
+    vals = [0.0, -0.0, 1.0, -1.0, 0.5, 2.0 ** -11, 2.0 ** -20, 9.9999995, 9.99999949999, 9.9999995000001, 1e-7, 123456.5,
+            0.1, 1e-300, 5e-324, 1e300, 1.7976931348623157e308, 999999.95, 0.0000005, 0.0000015, 1e15, 1e11 + 0.5, -3.25,
+            float("nan"), float("inf"), -float("inf"), 312.808149, 4.8828125e-04, 1.2345675, 7.4e-06, 2.15549759662018e-06]
+    vals += list(rng.random(20000) ** 12) + list(rng.random(5000) * 1e5) + list(10.0 ** rng.uniform(-280, 280, 20000))
+    vals += [struct.unpack("<d", struct.pack("<Q", int(b)))[0] for b in rng.integers(1, 0x7fefffffffffffff, 20000)]
+    vals += [k / 2.0 ** j for k in range(1, 400, 7) for j in range(0, 30, 3)]  # short dyadic values: exact ties
+    for v in vals:
+        v = float(v)
+        n = lib.fhc_io_format_double(v, ord("e"), buf)
+        assert buf.value[:n].decode() == "%e" % v, (v, buf.value, "%e" % v)
+        n = lib.fhc_io_format_double(v, ord("f"), buf)
+        assert buf.value[:n].decode() == "%f" % v, (v, buf.value, "%f" % v)
