@@ -303,8 +303,9 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bpu * units[unit], "avg_launch_ms": avg_ms,
                     "launches_per_step": mult,
-                    "note": "pvalues_kernel is FP64-ALU bound by construction (SURVEY F9); its HBM fraction is low by "
-                            "design" if top == "pvalues_kernel" else None,
+                    "note": "pvalues_kernel is bound by instruction issue and FP64 latency, not HBM (ncu: issue slots 53 %, FP64 "
+                            "pipe 20 %, DRAM 8 %; traffic = algorithmic bytes); see DESIGN.md section 4"
+                    if top == "pvalues_kernel" else None,
                     "whole_step": {"algorithmic_bytes_per_pair": PASS_BYTES_PER_PAIR,
                                    "achieved_gbs": PASS_BYTES_PER_PAIR * n_local * args.passes / (ms_per_step * 1e-3) / 1e9,
                                    "frac": PASS_BYTES_PER_PAIR * n_local * args.passes / (ms_per_step * 1e-3) / 1e9 / peak}}
