@@ -674,14 +674,39 @@ __global__ void bh_sample_kernel(const double *__restrict__ p, long long n, long
     keys[s] = k;
 }
 
+// part of a value for the two kernels below: -1 when the value is not ranked
+__device__ __forceinline__ int part_or_none(double v, double p_cut, const Splitters &sp) {
+    if (v >= p_cut || v == 1.0 || isnan(v)) return -1;
+    return part_of(key_of(v), sp);
+}
+
+// Both kernels read 8 values per thread (two 4-value groups, 128-bit loads) and aggregate per warp before touching a
+// shared counter: lanes with the same destination are found with match_any, one of them adds the group's size.
 __global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__restrict__ p, long long n, const Splitters sp,
                                                            double p_cut, u64 *__restrict__ counts) {
     __shared__ u32 local[kMaxParts];
     if (threadIdx.x < kMaxParts) local[threadIdx.x] = 0;
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const double v = __ldcs(p + i);
-        if (!(v >= p_cut) && !(v == 1.0) && !isnan(v)) atomicAdd(&local[part_of(key_of(v), sp)], 1u);
+    const int lane = threadIdx.x & 31;
+    const long long ngroups = (n + 3) >> 2;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ((ngroups + 31) & ~31ll);
+         g += (long long)gridDim.x * 256) {
+        const long long i0 = g << 2;
+        double v[4];
+        if (i0 + 3 < n) {
+            const double2 a = __ldcs(reinterpret_cast<const double2 *>(p + i0));
+            const double2 b = __ldcs(reinterpret_cast<const double2 *>(p + i0 + 2));
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? p[i0 + k] : 1.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int part = part_or_none(v[k], p_cut, sp);
+            const u32 m = __match_any_sync(0xffffffffu, part);
+            if (part >= 0 && lane == __ffs(m) - 1) atomicAdd(&local[part], (u32)__popc(m));
+        }
     }
     __syncthreads();
     if (threadIdx.x < sp.nparts && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)local[threadIdx.x]);
@@ -689,36 +714,61 @@ __global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__rest
 
 // p -> send buffer grouped by destination part (order inside a part is arbitrary: the receiver sorts); idx[j] = source line
 // of send[j]; q gets 1.0 / NaN for the p-values that are not ranked.  cursors[r] must start at the first slot of part r.
+// Per CTA iteration (1024 values): count per part in shared memory, reserve the ranges with one global atomic per part,
+// then write.
 __global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__restrict__ p, long long n, const Splitters sp,
                                                              double p_cut, u64 *cursors, double *__restrict__ send,
                                                              u32 *__restrict__ idx, double *__restrict__ q) {
     __shared__ u32 cnt[kMaxParts];
     __shared__ u64 base[kMaxParts];
-    for (long long b0 = (long long)blockIdx.x * 256; b0 < n; b0 += (long long)gridDim.x * 256) {
+    const int lane = threadIdx.x & 31;
+    for (long long b0 = (long long)blockIdx.x * 1024; b0 < n; b0 += (long long)gridDim.x * 1024) {
         if (threadIdx.x < kMaxParts) cnt[threadIdx.x] = 0;
         __syncthreads();
-        const long long i = b0 + threadIdx.x;
-        int part = -1;
-        u32 slot = 0;
-        double v = 0.0;
-        if (i < n) {
-            v = __ldcs(p + i);
-            if (isnan(v))
-                q[i] = v;
-            else if (v >= p_cut || v == 1.0)
-                q[i] = 1.0;
-            else {
-                part = part_of(key_of(v), sp);
-                slot = atomicAdd(&cnt[part], 1u);
-            }
+        const long long i0 = b0 + (long long)threadIdx.x * 4;
+        double v[4];
+        if (i0 + 3 < n) {
+            const double2 a = __ldcs(reinterpret_cast<const double2 *>(p + i0));
+            const double2 b = __ldcs(reinterpret_cast<const double2 *>(p + i0 + 2));
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? p[i0 + k] : 1.0;
+        }
+        int part[4];
+        u32 slot[4];
+        double qv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            part[k] = (i0 + k < n) ? part_or_none(v[k], p_cut, sp) : -1;
+            qv[k] = isnan(v[k]) ? v[k] : 1.0;
+            const u32 m = __match_any_sync(0xffffffffu, part[k]);
+            const int leader = __ffs(m) - 1;
+            u32 first = 0;
+            if (part[k] >= 0 && lane == leader) first = atomicAdd(&cnt[part[k]], (u32)__popc(m));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            slot[k] = first + __popc(m & ((1u << lane) - 1u));
+        }
+        if (i0 + 3 < n) {
+            // ranked lines get their q back from the owning GPU later; writing 1.0 first is harmless
+            __stcs(reinterpret_cast<double2 *>(q + i0), make_double2(qv[0], qv[1]));
+            __stcs(reinterpret_cast<double2 *>(q + i0 + 2), make_double2(qv[2], qv[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < n) q[i0 + k] = qv[k];
         }
         __syncthreads();
-        if (threadIdx.x < sp.nparts) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (u64)cnt[threadIdx.x]) : 0;
+        if (threadIdx.x < sp.nparts)
+            base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], (u64)cnt[threadIdx.x]) : 0;
         __syncthreads();
-        if (part >= 0) {
-            const u64 dst = base[part] + slot;
-            send[dst] = v;
-            idx[dst] = (u32)i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (part[k] >= 0) {
+                const u64 dst = base[part[k]] + slot[k];
+                send[dst] = v[k];
+                idx[dst] = (u32)(i0 + k);
+            }
         }
         __syncthreads();
     }
@@ -777,8 +827,8 @@ extern "C" int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t
     FHC_PROFILE_ENTRY(st);
     FHC_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * nparts, st));
     if (n == 0) return FHC_OK;
-    long long blocks = (n + 255) / 256;
-    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    long long blocks = (((n + 3) >> 2) + 255) / 256;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
     bh_part_count_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(counts));
     FHC_LAUNCH_CHECK("bh_part_count_kernel");
     return FHC_OK;
@@ -796,8 +846,8 @@ extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64
     FHC_REQUIRE(p && send && idx && q, FHC_E_INVALID, "fhc_bh_partition_scatter: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
-    long long blocks = (n + 255) / 256;
-    if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
     bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(cursors), send,
                                                                  idx, q);
     FHC_LAUNCH_CHECK("bh_part_scatter_kernel");

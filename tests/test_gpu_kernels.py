@@ -328,3 +328,51 @@ def test_outlier_bin_decrements(lib):
     want = np.zeros(len(ub), dtype=np.int64)
     np.add.at(want, b, outl.astype(np.int64))
     assert np.array_equal(dec.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# range partitioning for the multi-GPU correction
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nparts", [(0, 3), (5, 2), (100_003, 5), (1_000_000, 8), (4096, 1)])
+def test_partition_kernels(lib, n, nparts):
+    rng = np.random.default_rng(n + nparts)
+    p = rng.random(n) ** 2
+    if n > 10:
+        p[rng.integers(0, n, n // 10)] = 1.0
+        p[rng.integers(0, n, n // 50 + 1)] = np.nan
+        p[rng.integers(0, n, n // 20)] = p[rng.integers(0, n, n // 20)]
+    p_cut = 0.6
+    with np.errstate(invalid="ignore"):
+        ranked = ~((p == 1.0) | np.isnan(p) | (p >= p_cut))
+    keys = np.array([lib.fhc_bh_key_of(float(v)) for v in np.quantile(p[ranked], np.arange(1, nparts) / nparts)]
+                    if ranked.any() and nparts > 1 else [0] * (nparts - 1), dtype=np.uint64)
+    pd_ = dev(p) if n else torch.empty(1, dtype=torch.float64, device=DEV)
+    counts = torch.zeros(nparts, dtype=torch.int64, device=DEV)
+    check(lib.fhc_bh_partition_count(dptr(pd_), n, dptr(keys), nparts, p_cut, dptr(counts), stream()))
+    torch.cuda.synchronize()
+    kp = np.array([lib.fhc_bh_key_of(float(v)) for v in p[ranked]], dtype=np.uint64)
+    part = np.searchsorted(keys, kp, side="right")
+    want = np.bincount(part, minlength=nparts)
+    assert np.array_equal(counts.cpu().numpy(), want)
+    off = np.concatenate([[0], np.cumsum(want)[:-1]]).astype(np.int64)
+    cursors = dev(off)
+    send = torch.full((max(n, 1),), -5.0, dtype=torch.float64, device=DEV)
+    idx = torch.zeros(max(n, 1), dtype=torch.int32, device=DEV)
+    q = torch.full((max(n, 1),), -7.0, dtype=torch.float64, device=DEV)
+    check(lib.fhc_bh_partition_scatter(dptr(pd_), n, dptr(keys), nparts, p_cut, dptr(cursors), dptr(send), dptr(idx),
+                                       dptr(q), stream()))
+    torch.cuda.synchronize()
+    sh, ih, qh = send.cpu().numpy(), idx.cpu().numpy().view(np.uint32), q.cpu().numpy()[:n]
+    tot = int(want.sum())
+    assert np.array_equal(sh[:tot], p[ih[:tot]])                      # every sent value comes from the line it names
+    assert np.array_equal(np.sort(ih[:tot]), np.nonzero(ranked)[0])   # each ranked line exactly once
+    for r in range(nparts):
+        seg = ih[off[r]:off[r] + want[r]]
+        assert np.all(part[np.searchsorted(np.nonzero(ranked)[0], seg)] == r)
+    assert np.all(qh[~ranked & ~np.isnan(p)] == 1.0) and np.all(np.isnan(qh[np.isnan(p)]))
+    assert np.array_equal(cursors.cpu().numpy(), off + want)
+    # q back: dst[idx[j]] = src[j]
+    src = dev(np.arange(tot, dtype=np.float64))
+    check(lib.fhc_scatter_f64(dptr(src), dptr(idx), tot, dptr(q), stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(q.cpu().numpy()[ih[:tot]], np.arange(tot, dtype=np.float64))
