@@ -79,14 +79,9 @@ class Biases:
     chr_off: np.ndarray  # int64 [nchr + 1]
 
 
-def _pin(arr):
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    return t.pin_memory() if torch.cuda.is_available() else t
-
-
 class Engine:
-    """Runs spline passes on one GPU.  With `dist_group` set, histograms/totals are all-reduced so that every rank
-    fits the same spline, and q-values come from the range-partitioned global BH (fithic_b200/parallel.py)."""
+    """Runs spline passes on one GPU.  With `dist_ctx` set (parallel.DistCtx), histograms/totals are all-reduced so that
+    every rank fits the same spline, and q-values come from the range-partitioned global BH."""
 
     def __init__(self, settings, fragments, biases=None, device=None, dist_ctx=None):
         self.lib = _capi.load()
@@ -368,17 +363,14 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     def run(self):
-        """All spline passes (fithic/fithic.py:317-376).  Returns the list of per-pass dicts."""
-        outl, stats = (None, None)
-        if self.st.noOfPasses > 1 or True:
-            outl, stats = self.new_outlier_state()
+        """All spline passes (fithic/fithic.py:317-376).  Returns the list of per-pass dicts (device tensors p, q, expcc);
+        the outlier multiplicities of the last pass stay in self.outl / self.outl_stats."""
+        outl, stats = self.new_outlier_state()
         results = []
         for passNo in range(1, self.st.noOfPasses + 1):
             if passNo > 1 and self.st.interOnly:
                 break  # :349-351
-            r = self.run_pass(passNo, outl, stats)
-            r["outliers_flagged_total"] = None
-            results.append(r)
+            results.append(self.run_pass(passNo, outl, stats))
         self.outl, self.outl_stats = outl, stats
         return results
 

@@ -8,13 +8,13 @@ import pytest
 from fithic_b200 import io as fio
 from fithic_b200 import synth
 from tests.test_gpu_pipeline import run_engine
-from tests.util import GOLDEN_CASES, compare_pass, load_golden, load_kat
+from tests.util import GOLDEN_CASES, REAL_CASES, compare_pass, load_golden, load_kat
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + REAL_CASES)
 def test_engine_matches_reference_fixture(lib, name):
     contacts, frags, biases, st, ref, _ = load_golden(name)
     got = run_engine(contacts, frags, biases, st)

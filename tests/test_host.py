@@ -13,7 +13,7 @@ from fithic_b200 import _capi, synth
 from fithic_b200 import io as fio
 from fithic_b200.engine import Settings, calculate_probabilities, fit_spline, frag_pairs, make_bins
 from oracle import fithic_oracle as O
-from tests.util import GOLDEN_CASES, load_golden, oracle_inputs
+from tests.util import GOLDEN_CASES, REAL_CASES, load_golden, oracle_inputs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -76,7 +76,7 @@ def test_lbeta_is_cephes_lbeta(lib):
         assert abs(a - b) <= 1e-13 * abs(b)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + REAL_CASES)
 def test_host_stages_bit_exact_against_reference_fixture(lib, name):
     """make_bins / frag_pairs / calculate_probabilities / fit_spline on the reference's own histogram."""
     contacts, frags, biases, st, ref, _ = load_golden(name)

@@ -100,6 +100,9 @@ import os  # noqa: E402
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["intra_40kb", "intra_bias_LU_p2", "all_bias", "inter_only_bias", "intra_p3"]
+# every k-th line of the reference's own bundled data sets (tests/golden/make_golden_real.py): real count distributions,
+# real ICE biases, real (irregular) fragment lists
+REAL_CASES = ["real_pfal_10kb", "real_hesc_40kb_bias"]
 
 
 def load_kat():
