@@ -17,6 +17,7 @@ FHC_ABI_VERSION = 1
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
 N_SCALARS = 8
 MODE_INTRA_ONLY, MODE_INTER_ONLY, MODE_ALL = 0, 1, 2
+BH_CUT_BUCKETS = 32768
 
 
 class FithicB200Error(RuntimeError):
@@ -58,6 +59,9 @@ _SIGNATURES = {
     "fhc_bh_prepare": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "fhc_bh_p_cut": (c_double, [c_double, c_double]),
+    "fhc_bh_cut_hist": (ctypes.c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "fhc_host_bh_cut_find": (c_double, [c_void_p, c_double, c_double, c_double]),
+    "fhc_host_bh_cut_bucket": (c_int32, [c_double]),
     "fhc_bh_finish": (ctypes.c_int, [c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_bh_sample_keys": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p]),
     "fhc_bh_key_of": (ctypes.c_uint64, [c_double]),

@@ -13,6 +13,7 @@
 // Every kernel reads the number of sorted elements from device memory, so the whole K4 is enqueued without a host sync.
 // HBM-bound: 16 algorithmic bytes per contact (read p, write q); the LSD passes move (8+12+12) B per element per pass.
 #define FHC_PROFILE_STREAM st
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -36,6 +37,15 @@ __device__ __forceinline__ u64 key_of(double p) {  // order preserving for every
     const u64 b = (u64)__double_as_longlong(p);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
+// Number of sort tiles that hold data.  The launch grids are sized for the capacity n_max (known on the host), but how
+// many keys survive the compaction is only known on the device: every sort / scan kernel derives the live tile count from
+// *d_n, and CTAs beyond it leave at once, so the cost of a pass follows the number of RANKED keys, not the lines.
+__device__ __forceinline__ u32 live_tiles(const u64 *d_n) {
+    const u64 n = *d_n;
+    const u64 t = (n + (u64)kSortTile - 1) / (u64)kSortTile;
+    return t ? (u32)t : 1u;
+}
+
 __device__ __forceinline__ double p_of(u64 k) {
     const u64 b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
     return __longlong_as_double((long long)b);
@@ -49,11 +59,12 @@ __device__ __forceinline__ double p_of(u64 k) {
 // are appended with ONE global atomic per CTA iteration (same-address atomics serialise in L2: a per-warp atomic costs
 // 5 ms at 300 M lines).  The order of the appended pairs is irrelevant, the sort follows.
 constexpr int kCompactPerThread = 8;
-__global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n, double p_cut,
-                                                        double *__restrict__ q, u64 *__restrict__ keys,
-                                                        u32 *__restrict__ vals, u64 *nsel) {
+__global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n,
+                                                        const double *__restrict__ d_p_cut, double *__restrict__ q,
+                                                        u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel) {
     __shared__ u32 warp_tot[8];
     __shared__ u64 block_base;
+    const double p_cut = *d_p_cut;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long per_iter = 256ll * kCompactPerThread;
     u32 cut_total = 0;
@@ -129,6 +140,120 @@ __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// tightening the cut: a histogram of the p-values below the rank-bound cut tells where q reaches 1.0 for good
+// ---------------------------------------------------------------------------------------------------------------------
+// bh_p_cut (below) only uses rank <= lines.  The ranks themselves say more: with the p-values below the first cut counted
+// in value buckets (sign/exponent/5 mantissa bits of the double: bucket edges are exact doubles), every p-value of bucket
+// j has rank <= rank_offset + c_j (c_j = p-values in buckets <= j) and p >= edge_j.  If rn(edge_j T) >= rank_offset + c_j
+// for a non-empty bucket j, then rn(rn(p T) / rank) >= 1 for all of bucket j (rounding is monotone), the reference caps
+// those at 1 (fithic/myStats.py:36-37) and its running max (:43) stays 1.0 for every larger p: nothing from edge_j on
+// needs a rank.  The smallest such edge replaces the cut; results are bit-identical, and on sparse maps with few
+// significant contacts almost nothing is left to sort.
+constexpr int kCutBuckets = FHC_BH_CUT_BUCKETS;  // 32768 = top 16 bits of a non-negative double below 1.0
+static_assert(kCutBuckets == 32768, "bucket = high word >> 15");
+constexpr int kCutHistThreads = 1024;
+
+__host__ __device__ inline int cut_bucket(double x) {  // x is not NaN
+    if (!(x > 0.0)) return 0;
+#if defined(__CUDA_ARCH__)
+    const unsigned int hi = (unsigned int)__double2hiint(x);
+#else
+    unsigned long long b;
+    memcpy(&b, &x, sizeof(b));
+    const unsigned int hi = (unsigned int)(b >> 32);
+#endif
+    const unsigned int j = hi >> 15;
+    return j < (unsigned int)kCutBuckets ? (int)j : kCutBuckets - 1;  // x >= 1: last bucket (its edge is below x)
+}
+__host__ __device__ inline double cut_edge(int j) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(j << 15, 0);
+#else
+    const unsigned long long b = (unsigned long long)(unsigned int)(j << 15) << 32;
+    double x;
+    memcpy(&x, &b, sizeof(x));
+    return x;
+#endif
+}
+
+// One CTA per SM with the whole histogram in shared memory (128 KB of uint32); flushed with one global atomic per
+// non-empty bucket.  Only p-values that bh_compact_kernel would rank at the first cut are counted.
+__global__ void __launch_bounds__(kCutHistThreads) bh_cut_hist_kernel(const double *__restrict__ p, long long n, double p_cut0,
+                                                                     u64 *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char cut_smem[];
+    u32 *sh = reinterpret_cast<u32 *>(cut_smem);
+    for (int i = threadIdx.x; i < kCutBuckets; i += kCutHistThreads) sh[i] = 0;
+    __syncthreads();
+    const long long n2 = n >> 1;
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+    for (long long i = (long long)blockIdx.x * kCutHistThreads + threadIdx.x; i < n2;
+         i += (long long)gridDim.x * kCutHistThreads) {
+        const double2 v = p2[i];
+        if (!(v.x == 1.0) && !isnan(v.x) && !(v.x >= p_cut0)) atomicAdd(sh + cut_bucket(v.x), 1u);
+        if (!(v.y == 1.0) && !isnan(v.y) && !(v.y >= p_cut0)) atomicAdd(sh + cut_bucket(v.y), 1u);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double x = p[n - 1];
+        if (!(x == 1.0) && !isnan(x) && !(x >= p_cut0)) atomicAdd(sh + cut_bucket(x), 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCutBuckets; i += kCutHistThreads) {
+        const u32 c = sh[i];
+        if (c) atomicAdd(hist + i, (u64)c);
+    }
+}
+
+// the smallest edge from which on every q is 1.0, or p_cut0 (same code on host and device)
+__host__ __device__ inline bool cut_bucket_closes(int j, u64 c_incl, double T, double rank_offset) {
+#if defined(__CUDA_ARCH__)
+    const double lhs = __dmul_rn(cut_edge(j), T);
+#else
+    const double lhs = cut_edge(j) * T;
+#endif
+    return lhs >= rank_offset + (double)c_incl;  // both sides exact integers below 2^53 or a correctly rounded product
+}
+
+// single CTA: inclusive counts over the buckets, first non-empty bucket that closes; tighten == 0 just forwards p_cut0
+__global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict__ hist, double T, double rank_offset,
+                                                          double p_cut0, int tighten, double *__restrict__ p_cut_out) {
+    __shared__ u64 wsum[32];
+    __shared__ int best;
+    const int per = kCutBuckets / 1024;  // 32 consecutive buckets per thread
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) best = kCutBuckets;
+    if (!tighten || !(T > 0.0)) {
+        if (threadIdx.x == 0) *p_cut_out = p_cut0;
+        return;
+    }
+    u64 mine = 0;
+    for (int k = 0; k < per; ++k) mine += hist[threadIdx.x * per + k];
+    u64 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    u64 pre = inc - mine;
+    for (int w = 0; w < warp; ++w) pre += wsum[w];
+    int found = kCutBuckets;
+    for (int k = 0; k < per; ++k) {
+        const int j = threadIdx.x * per + k;
+        const u64 c = hist[j];
+        pre += c;
+        if (c && found == kCutBuckets && cut_bucket_closes(j, pre, T, rank_offset)) found = j;
+    }
+    if (found < kCutBuckets) atomicMin(&best, found);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cut = p_cut0;
+        if (best < kCutBuckets) cut = fmin(cut, cut_edge(best));
+        *p_cut_out = cut;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // exclusive scan of a uint32 array (three phases)
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 block_exclusive_scan_u32(u32 v, u32 *smem_warp /*32*/, u32 &total) {
@@ -159,9 +284,11 @@ __device__ __forceinline__ u32 block_exclusive_scan_u32(u32 v, u32 *smem_warp /*
     return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const u32 *__restrict__ data, long long len,
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const u32 *__restrict__ data, const u64 *d_n,
                                                                   u32 *__restrict__ blocksums) {
     __shared__ u32 sw[33];
+    const long long len = (long long)kRadix * live_tiles(d_n);
+    if ((long long)blockIdx.x * kScanTile >= len) return;
     const long long i0 = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * 4;
     u32 s = 0;
     if (i0 + 3 < len) {
@@ -175,9 +302,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const u32 *__
     if (threadIdx.x == 0) blocksums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(u32 *blocksums, int nb) {
+__global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(u32 *blocksums, const u64 *d_n) {
     __shared__ u32 sw[33];
     __shared__ u32 carry;
+    const int nb = (int)(((long long)kRadix * live_tiles(d_n) + kScanTile - 1) / kScanTile);
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < nb; base += kScanThreads) {
@@ -192,9 +320,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_blocksums_kernel(u32 *block
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(u32 *__restrict__ data, long long len,
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(u32 *__restrict__ data, const u64 *d_n,
                                                                  const u32 *__restrict__ blocksums) {
     __shared__ u32 sw[33];
+    const long long len = (long long)kRadix * live_tiles(d_n);
+    if ((long long)blockIdx.x * kScanTile >= len) return;
     const long long i0 = ((long long)blockIdx.x * kScanThreads + threadIdx.x) * 4;
     u32 a = 0, b = 0, c = 0, d = 0;
     const bool full = i0 + 3 < len;
@@ -222,8 +352,10 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(u32 *__restric
 // radix sort passes
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const u64 *__restrict__ keys, const u64 *d_n,
-                                                                    int shift, u32 *__restrict__ counts, u32 ntiles) {
+                                                                    int shift, u32 *__restrict__ counts) {
     __shared__ u32 hist[kSortWarps][kRadix];
+    const u32 ntiles = live_tiles(d_n);
+    if (blockIdx.x >= ntiles) return;
     const long long n = (long long)*d_n;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
@@ -245,8 +377,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const u64 *
 
 __global__ void __launch_bounds__(kSortThreads)
 radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u64 *__restrict__ keys_out,
-                       u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ offsets,
-                       u32 ntiles) {
+                       u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ offsets) {
     extern __shared__ __align__(16) unsigned char dsmem[];
     u64 *skeys = reinterpret_cast<u64 *>(dsmem);                                  // [kSortTile]
     u32 *svals = reinterpret_cast<u32 *>(skeys + kSortTile);                      // [kSortTile]
@@ -257,6 +388,7 @@ radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ 
     const long long n = (long long)*d_n;
     const long long base = (long long)blockIdx.x * kSortTile;
     if (base >= n) return;
+    const u32 ntiles = live_tiles(d_n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_n = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
@@ -366,6 +498,7 @@ __global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilem
     if (threadIdx.x == 0) carry = carry_in;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ntiles > 0) ntiles = min(ntiles, (int)live_tiles(d_n));  // tiles beyond hold no keys
     for (int base = 0; base < ntiles; base += kScanThreads) {
         const int i = base + threadIdx.x;
         const double v = i < ntiles ? tilemax[i] : 0.0;
@@ -469,15 +602,15 @@ static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_
                                   (int)kDownsweepSmem));
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
-        radix_upsweep_kernel<<<ws.ntiles, kSortThreads, 0, st>>>(kin, d_n, shift, ws.counts, ws.ntiles);
+        radix_upsweep_kernel<<<ws.ntiles, kSortThreads, 0, st>>>(kin, d_n, shift, ws.counts);
         FHC_LAUNCH_CHECK("radix_upsweep_kernel");
-        scan_reduce_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, (long long)ws.counts_len, ws.blocksums);
+        scan_reduce_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, d_n, ws.blocksums);
         FHC_LAUNCH_CHECK("scan_reduce_kernel");
-        scan_blocksums_kernel<<<1, kScanThreads, 0, st>>>(ws.blocksums, ws.nb);
+        scan_blocksums_kernel<<<1, kScanThreads, 0, st>>>(ws.blocksums, d_n);
         FHC_LAUNCH_CHECK("scan_blocksums_kernel");
-        scan_apply_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, (long long)ws.counts_len, ws.blocksums);
+        scan_apply_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, d_n, ws.blocksums);
         FHC_LAUNCH_CHECK("scan_apply_kernel");
-        radix_downsweep_kernel<<<ws.ntiles, kSortThreads, kDownsweepSmem, st>>>(kin, vin, kout, vout, d_n, shift, ws.counts, ws.ntiles);
+        radix_downsweep_kernel<<<ws.ntiles, kSortThreads, kDownsweepSmem, st>>>(kin, vin, kout, vout, d_n, shift, ws.counts);
         FHC_LAUNCH_CHECK("radix_downsweep_kernel");
         u64 *tk = kin; kin = kout; kout = tk;
         u32 *tv = vin; vin = vout; vout = tv;
@@ -520,7 +653,8 @@ extern "C" int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t
 
 namespace fhc {
 struct BhWs {
-    u64 *d_n;
+    u64 *d_n;        // [0] ranked keys, [1] rankable but cut, then (as double) [2] the cut in force
+    u64 *cut_hist;   // [kCutBuckets]
     u64 *keys_a, *keys_b;
     u32 *vals_a, *vals_b;
     double *tilemax;
@@ -532,6 +666,8 @@ static size_t bh_ws_layout(int64_t n, char *base, BhWs *ws) {
     const size_t ntiles = (nn + kSortTile - 1) / kSortTile;
     if (ws) ws->d_n = reinterpret_cast<u64 *>(base + off);
     off += 256;
+    if (ws) ws->cut_hist = reinterpret_cast<u64 *>(base + off);
+    off += align_up((size_t)kCutBuckets * sizeof(u64));
     if (ws) ws->keys_a = reinterpret_cast<u64 *>(base + off);
     off += align_up(nn * sizeof(u64));
     if (ws) ws->keys_b = reinterpret_cast<u64 *>(base + off);
@@ -560,15 +696,43 @@ static double bh_p_cut(double T, double rank_bound) {
     return (rank_bound / T) * (1.0 + 1e-9);
 }
 
-static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double p_cut, double *q,
-                      double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st) {
+static int cut_hist_launch(const double *p, int64_t n, double p_cut0, fhc::u64 *hist, cudaStream_t st) {
     using namespace fhc;
-    FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 2 * sizeof(u64), st));
+    const size_t smem = (size_t)kCutBuckets * sizeof(u32);
+    FHC_CUDA(cudaFuncSetAttribute(bh_cut_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (n / 2 + kCutHistThreads - 1) / kCutHistThreads;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    if (blocks < 1) blocks = 1;
+    bh_cut_hist_kernel<<<(unsigned int)blocks, kCutHistThreads, smem, st>>>(p, n, p_cut0, hist);
+    FHC_LAUNCH_CHECK("bh_cut_hist_kernel");
+    return FHC_OK;
+}
+
+// tighten: derive the cut from the value histogram (single-GPU path); otherwise p_cut is used as given (the multi-GPU
+// path tightens globally before the exchange, fhc_bh_cut_hist + fhc_host_bh_cut_find)
+static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double p_cut, bool tighten,
+                      double *q, double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st) {
+    using namespace fhc;
+    FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 4 * sizeof(u64), st));
     const int ntiles = (int)ws.sort.ntiles;
     if (n > 0) {
+        static int no_tighten = -1;  // FHC_BH_TIGHTEN=0: rank-bound cut only (experiments, worst-case timing)
+        if (no_tighten < 0) {
+            const char *e = getenv("FHC_BH_TIGHTEN");
+            no_tighten = (e && e[0] == '0') ? 1 : 0;
+        }
+        if (no_tighten) tighten = false;
+        double *d_p_cut = reinterpret_cast<double *>(ws.d_n + 2);
+        if (tighten) {
+            FHC_CUDA(cudaMemsetAsync(ws.cut_hist, 0, (size_t)kCutBuckets * sizeof(u64), st));
+            const int rc = cut_hist_launch(p, n, p_cut, ws.cut_hist, st);
+            if (rc != FHC_OK) return rc;
+        }
+        bh_cut_find_kernel<<<1, 1024, 0, st>>>(ws.cut_hist, T, (double)rank_offset, p_cut, tighten ? 1 : 0, d_p_cut);
+        FHC_LAUNCH_CHECK("bh_cut_find_kernel");
         long long blocks = (n + 256 * kCompactPerThread - 1) / (256 * kCompactPerThread);
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, p_cut, q, ws.keys_a, ws.vals_a, ws.d_n);
+        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, d_p_cut, q, ws.keys_a, ws.vals_a, ws.d_n);
         FHC_LAUNCH_CHECK("bh_compact_kernel");
         const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st);
         if (rc != FHC_OK) return rc;
@@ -611,7 +775,7 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
     FHC_PROFILE_ENTRY(st);
     BhWs ws;
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
-    rc = bh_prepare(p, n, T, rank_offset, carry_in, bh_p_cut(T, (double)rank_offset + (double)n), q, carry_out,
+    rc = bh_prepare(p, n, T, rank_offset, carry_in, bh_p_cut(T, (double)rank_offset + (double)n), true, q, carry_out,
                     n_sorted_out, ws, st);
     if (rc != FHC_OK) return rc;
     return bh_finish(n, T, rank_offset, 0.0, q, ws, st);  // carry_in is already folded into the tile prefixes
@@ -627,7 +791,7 @@ extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank
     FHC_PROFILE_ENTRY(st);
     BhWs ws;
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
-    return bh_prepare(p, n, T, rank_offset, 0.0, p_cut, q, local_max_out, n_sorted_out, ws, st);
+    return bh_prepare(p, n, T, rank_offset, 0.0, p_cut, false, q, local_max_out, n_sorted_out, ws, st);
 }
 
 extern "C" int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, void *workspace,
@@ -809,6 +973,33 @@ extern "C" int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, 
 
 // smallest p that is certain to end with q = 1.0 when no p-value has a rank above rank_bound (host helper)
 extern "C" double fhc_bh_p_cut(double T, double rank_bound) { return bh_p_cut(T, rank_bound); }
+
+extern "C" int fhc_bh_cut_hist(const double *p, int64_t n, double p_cut0, uint64_t *hist, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && hist != nullptr, FHC_E_INVALID, "fhc_bh_cut_hist: n < 0 or null histogram");
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(p != nullptr && aligned16(p), FHC_E_INVALID, "fhc_bh_cut_hist: p must be a 16-byte aligned device array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    return cut_hist_launch(p, n, p_cut0, reinterpret_cast<u64 *>(hist), st);
+}
+
+extern "C" int32_t fhc_host_bh_cut_bucket(double p) { return fhc::cut_bucket(p); }
+
+extern "C" double fhc_host_bh_cut_find(const uint64_t *hist, double T, double rank_offset, double p_cut0) {
+    using namespace fhc;
+    if (hist == nullptr || !(T > 0.0)) return p_cut0;
+    u64 c = 0;
+    for (int j = 0; j < kCutBuckets; ++j) {
+        if (hist[j] == 0) continue;
+        c += hist[j];
+        if (cut_bucket_closes(j, c, T, rank_offset)) {
+            const double e = cut_edge(j);
+            return e < p_cut0 ? e : p_cut0;
+        }
+    }
+    return p_cut0;
+}
 
 extern "C" uint64_t fhc_bh_key_of(double p) {  // host copy of the order-preserving key (for choosing splitters)
     uint64_t b;

@@ -3,7 +3,8 @@ NVSwitch) for the two exchange steps of a spline pass.
 
   exchange 1  all-reduce (sum) of the distance histogram + observed totals (<= 400 kB, latency bound).  Every rank then
               runs the identical host binning / spline fit on identical inputs, so tables are bit-identical everywhere.
-  exchange 2  global BH: p-values are range-partitioned by value so that rank r ranks one contiguous key range:
+  exchange 2  global BH: an all-reduce of a 32768-bucket value histogram fixes the cut above which every q is 1.0;
+              the p-values below it are range-partitioned by value so that rank r ranks one contiguous key range:
               sample keys -> all-gather -> splitters; count per part -> all-gather -> offsets; scatter into send
               buffers (kernel) -> all-to-all(v) of p -> local compaction/sort/tile maxima (kernels) -> all-gather of the
               per-range maxima (carry) -> scan + scatter (kernels) -> all-to-all(v) of q back -> scatter to line order.
@@ -69,6 +70,16 @@ class CudaOps:
 
     def p_cut(self, T, rank_bound):
         return float(self.lib.fhc_bh_p_cut(float(T), float(rank_bound)))
+
+    def cut_hist(self, p, p_cut0):
+        """Value histogram of the rankable p-values below p_cut0 (int64 [BH_CUT_BUCKETS], device)."""
+        hist = torch.zeros(_capi.BH_CUT_BUCKETS, dtype=torch.int64, device=self.device)
+        check(self.lib.fhc_bh_cut_hist(dptr(p), p.numel(), float(p_cut0), dptr(hist), self._stream()))
+        return hist
+
+    def cut_find(self, hist_host, T, p_cut0):
+        h = np.ascontiguousarray(hist_host, dtype=np.uint64)
+        return float(self.lib.fhc_host_bh_cut_find(dptr(h), float(T), 0.0, float(p_cut0)))
 
     def sample_keys(self, p, nsamples, p_cut):
         keys = self.empty(nsamples, torch.int64)
@@ -185,7 +196,12 @@ class DistCtx:
             q = engine._tensor("q", n, torch.float64) if engine is not None else ops.empty(n, torch.float64)
         # 0. p-values that are certain to end with q = 1.0 are neither exchanged nor ranked (bh.cu: bh_p_cut)
         n_global = int(self._all_gather(torch.tensor([n], dtype=torch.int64, device=p.device)).sum().item())
-        p_cut = ops.p_cut(T, n_global)
+        p_cut0 = ops.p_cut(T, n_global)
+        #    ... and the summed value histogram of what is left says where q reaches 1.0 for good (bh.cu: cut_bucket_closes);
+        #    on sparse maps this leaves only the few candidates for significance to exchange and sort
+        hist = ops.cut_hist(p, p_cut0)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+        p_cut = ops.cut_find(hist.cpu().numpy(), T, p_cut0)
         # 1. splitters from a sorted sample of everybody's keys
         sample = ops.sample_keys(p, self.samples_per_rank, p_cut)
         allsamp = ops.sort_keys(self._all_gather(sample))
@@ -208,5 +224,6 @@ class DistCtx:
         q_back = ops.empty(n_send, torch.float64)
         dist.all_to_all_single(q_back, q_recv, send_splits, recv_splits, group=self.group)
         ops.scatter(q_back, idx[:n_send], q)
-        self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor, p_cut=p_cut)
+        self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor, p_cut=p_cut,
+                              p_cut0=p_cut0)
         return q

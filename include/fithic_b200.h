@@ -184,6 +184,20 @@ int fhc_bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, dou
  *                           idx[j] = line of send[j]; q[i] = 1.0 / NaN is written for the p-values that are not ranked
  *   fhc_scatter_f64         dst[idx[j]] = src[j]  (q-values coming back from the owning GPU) */
 double fhc_bh_p_cut(double T, double rank_bound);
+
+/* Tightening the cut with the ranks themselves (exact; fhc_bh_qvalues does this internally on one GPU).  Bucket j of
+ * the value histogram holds the rankable p-values below p_cut0 whose high 16 bits (sign, exponent, 5 mantissa bits) are
+ * j, so every bucket edge is an exact double.  If rn(edge_j * T) >= rank_offset + (p-values in buckets <= j) for a
+ * non-empty bucket j, every p-value from edge_j on has (p*T)/rank >= 1: the reference caps it at 1 and its forward
+ * running max stays 1.0 (fithic/myStats.py:36-43), so the smallest such edge is a valid, usually far smaller, cut.
+ *   fhc_bh_cut_hist        hist[j] += count  (hist [dev] FHC_BH_CUT_BUCKETS uint64, zeroed by the caller; the
+ *                          multi-GPU host sums the histograms of all ranks before looking for the cut)
+ *   fhc_host_bh_cut_find   min(p_cut0, smallest closing edge) from a HOST copy of the (summed) histogram
+ *   fhc_host_bh_cut_bucket the bucket of one p-value (host; for tests) */
+#define FHC_BH_CUT_BUCKETS 32768
+int fhc_bh_cut_hist(const double *p, int64_t n, double p_cut0, uint64_t *hist, void *stream);
+double fhc_host_bh_cut_find(const uint64_t *hist, double T, double rank_offset, double p_cut0);
+int32_t fhc_host_bh_cut_bucket(double p);
 int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out, void *stream);
 uint64_t fhc_bh_key_of(double p);
 int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,

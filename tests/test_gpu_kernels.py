@@ -244,6 +244,30 @@ def test_bh_matches_oracle_bit_exact(lib, n):
         assert np.array_equal(got, O.benjamini_hochberg(p, 1000 * n), equal_nan=True)
 
 
+@pytest.mark.parametrize("n", [1, 7, 100_001, 3_000_000])
+def test_bh_cut_hist_matches_numpy(lib, n):
+    """fhc_bh_cut_hist + fhc_host_bh_cut_find: the value histogram behind the tightened cut (bh.cu)."""
+    from tests.util import cut_hist_numpy
+    rng = np.random.default_rng(n)
+    p = rng.random(n) ** 4
+    p[rng.integers(0, n, n // 5 + 1)] = 1.0
+    p[rng.integers(0, n, n // 40 + 1)] = np.nan
+    p[rng.integers(0, n, 2)] = 0.0
+    p[rng.integers(0, n, 2)] = 1e-310  # subnormal
+    for p_cut0 in (0.3, float("inf")):
+        hist = torch.zeros(_capi.BH_CUT_BUCKETS, dtype=torch.int64, device=DEV)
+        pd_ = dev(p)
+        check(lib.fhc_bh_cut_hist(dptr(pd_), n, p_cut0, dptr(hist), stream()))
+        torch.cuda.synchronize()
+        want = cut_hist_numpy(p, p_cut0)
+        assert np.array_equal(hist.cpu().numpy().view(np.uint64), want)
+        T = 50.0 * n
+        cut = float(lib.fhc_host_bh_cut_find(dptr(want), T, 0.0, p_cut0))
+        q = O.benjamini_hochberg(p, T)
+        with np.errstate(invalid="ignore"):
+            assert np.all(q[(p >= cut) & ~np.isnan(p)] == 1.0)
+
+
 def test_bh_chained_partitions(lib):
     """rank_offset / carry_in: q of a key range computed separately equals the global result (multi-GPU contract)."""
     rng = np.random.default_rng(99)

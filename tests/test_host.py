@@ -13,7 +13,7 @@ from fithic_b200 import _capi, synth
 from fithic_b200 import io as fio
 from fithic_b200.engine import Settings, calculate_probabilities, fit_spline, frag_pairs, make_bins
 from oracle import fithic_oracle as O
-from tests.util import GOLDEN_CASES, REAL_CASES, load_golden, oracle_inputs
+from tests.util import GOLDEN_CASES, REAL_CASES, cut_hist_numpy, load_golden, oracle_inputs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -283,3 +283,49 @@ def test_fast_double_formatting_is_printf(lib):
         assert buf.value[:n].decode() == "%e" % v, (v, buf.value, "%e" % v)
         n = lib.fhc_io_format_double(v, ord("f"), buf)
         assert buf.value[:n].decode() == "%f" % v, (v, buf.value, "%f" % v)
+
+
+@pytest.mark.parametrize("case", ["null", "signal", "T_small", "ties", "offset"])
+def test_bh_cut_from_value_histogram_is_exact(lib, case):
+    """fhc_host_bh_cut_find (the same code the device kernel runs): every p-value at or above the cut has q == 1.0 in
+    the reference's correction (fithic/myStats.py:24-48), so leaving it unranked changes nothing."""
+    rng = np.random.default_rng(7)
+    n = 200_000
+    p = rng.random(n)
+    T, off = 5.0e6, 0.0
+    if case == "signal":
+        p[:20_000] = rng.random(20_000) ** 6 * 1e-4
+    elif case == "T_small":
+        T = 1000.0  # far fewer tests than lines: the rank bound is > 1 and nothing closes early
+    elif case == "ties":
+        p = np.round(p, 2)
+        p[p == 0] = 1e-12
+    elif case == "offset":
+        off = 3.0e6
+    p[rng.integers(0, n, 5000)] = 1.0
+    p[rng.integers(0, n, 100)] = np.nan
+    p_cut0 = float(lib.fhc_bh_p_cut(T, off + n))
+    hist = cut_hist_numpy(p, p_cut0)
+    for v in (0.0, 1e-300, 3e-9, 0.0157, 0.5, 0.99999):
+        assert lib.fhc_host_bh_cut_bucket(v) == (int(np.float64(v).view(np.uint64)) >> 47 if v > 0 else 0)
+    cut = float(lib.fhc_host_bh_cut_find(_capi.dptr(hist), T, off, p_cut0))
+    assert cut <= p_cut0
+    # the reference's correction with ranks shifted by `off` (what a GPU holding a higher key range sees)
+    order = np.argsort(p, kind="stable")
+    ps = p[order]
+    with np.errstate(invalid="ignore"):
+        bh = np.where(ps == 1.0, 1.0, np.minimum(ps * T / (off + np.arange(1, n + 1)), 1.0))
+    q = np.empty(n)
+    run = 0.0
+    for i in range(n):  # max(bh, prev) with Python's NaN semantics (KAT-BH4)
+        run = max(bh[i], run)
+        q[order[i]] = run
+    with np.errstate(invalid="ignore"):
+        above = p >= cut
+    assert np.all(q[above & ~np.isnan(p)] == 1.0)
+    if case == "null":
+        assert np.sum(p < cut) < 0.01 * n  # nearly nothing is left to sort on null data
+    if case == "offset":
+        assert 0.5 < cut < p_cut0  # ranks start at 3e6 of T = 5e6: p T / rank reaches 1 near p = 0.6
+    if case == "T_small":
+        assert cut == p_cut0 or np.all(q[p >= cut] == 1.0)

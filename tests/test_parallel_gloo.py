@@ -29,6 +29,18 @@ class NumpyOps:
     def p_cut(self, T, rank_bound):
         return float(_capi.load().fhc_bh_p_cut(float(T), float(rank_bound)))
 
+    def cut_hist(self, p, p_cut0):
+        p = p.numpy()
+        with np.errstate(invalid="ignore"):
+            ok = ~((p == 1.0) | np.isnan(p) | (p >= p_cut0))
+        v = p[ok]
+        b = np.where(v > 0, np.minimum(v.view(np.uint64) >> np.uint64(47), np.uint64(_capi.BH_CUT_BUCKETS - 1)), 0)
+        return torch.from_numpy(np.bincount(b.astype(np.int64), minlength=_capi.BH_CUT_BUCKETS).astype(np.int64))
+
+    def cut_find(self, hist_host, T, p_cut0):
+        h = np.ascontiguousarray(hist_host, dtype=np.uint64)
+        return float(_capi.load().fhc_host_bh_cut_find(_capi.dptr(h), float(T), 0.0, float(p_cut0)))
+
     def sample_keys(self, p, nsamples, p_cut):
         p = p.numpy()
         n = len(p)
@@ -108,7 +120,8 @@ def _worker(rank, world, port, tmp):
         cm = ctx.last_plan["count_matrix"]
         with np.errstate(invalid="ignore"):
             assert cm.sum() == np.sum(~((p_all == 1.0) | np.isnan(p_all) | (p_all >= ctx.last_plan["p_cut"])))
-        assert 0.2 < ctx.last_plan["p_cut"] < 0.3  # 60,001 lines / T = 250,000: three quarters of the lines are not ranked
+        assert 0.2 < ctx.last_plan["p_cut0"] < 0.3  # 60,001 lines / T = 250,000: the rank bound alone drops three quarters
+        assert ctx.last_plan["p_cut"] <= ctx.last_plan["p_cut0"]
         assert abs(cm[:, 0].sum() - cm[:, 1].sum()) < 0.1 * cm.sum()  # the sample balances the two key ranges
 
         # exchange 1: histogram + seen bits + totals

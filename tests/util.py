@@ -158,3 +158,14 @@ def load_golden(name):
     extra = dict(sig_head=[str(s) for s in z["sig_head"]], sig_nrows=int(z["sig_nrows"]),
                  bias_raw=z["bias_raw"] if "bias_raw" in z else None)
     return contacts, frags, biases, st, passes, extra
+
+
+def cut_hist_numpy(p, p_cut0):
+    """numpy model of fhc_bh_cut_hist: buckets = high 16 bits of the rankable p-values below p_cut0."""
+    from fithic_b200 import _capi
+    p = np.asarray(p, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        ok = ~((p == 1.0) | np.isnan(p) | (p >= p_cut0))
+    v = p[ok]
+    b = np.where(v > 0, np.minimum(v.view(np.uint64) >> np.uint64(47), np.uint64(_capi.BH_CUT_BUCKETS - 1)), 0)
+    return np.bincount(b.astype(np.int64), minlength=_capi.BH_CUT_BUCKETS).astype(np.uint64)
