@@ -11,6 +11,7 @@ HBM; `e2e` = the same through fithic_b200.api.significance with pinned HOST arra
 D2H inside the timed region).  With N GPUs the same 300 M pairs are sharded by chromosome (strong scaling).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -25,7 +26,11 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES = {  # kernel: (unit, algorithmic HBM bytes per unit per launch, full-size launches per pass); DESIGN.md 4
     "hist_distance_kernel": ("pairs", 16, 1),      # 4 x int32 read
-    "pvalues_kernel": ("pairs", 32, 1),            # 16 read + p, ExpCC written
+    "pvalues_kernel": ("pairs", 32, 1),            # tile-phased K3: 16 read + p, ExpCC written
+    "pval_front_kernel": ("pairs", 32, 1),         # work-list K3, front: 16 read + p, ExpCC written (+ 16 per listed item)
+    "pval_iterate_kernel": ("items", 32, 1),       # item read, numerator/denominator written
+    "pval_finish_kernel": ("items", 40, 1),        # item + numerator/denominator read, p written
+    "bh_cut_hist_kernel": ("pairs", 8, 1),         # p read
     "bh_compact_kernel": ("pairs", 20, 1),         # p read, (key, index) written
     "radix_upsweep_kernel": ("sorted", 8, 8),      # key read, one launch per 8-bit digit
     "radix_downsweep_kernel": ("sorted", 24, 8),   # (key, index) read and written, one launch per digit
@@ -44,53 +49,105 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML polled every few ms from a thread (the device-
+    resident leg lasts ~0.1 s, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query per call if NVML is
+    unavailable."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index=0):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index=0, uuid=None, period=0.004):
+        self.index, self.uuid, self.period = index, uuid, period
+        self.samples = []   # (sm_mhz, reasons bitmask, power W)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                try:
+                    u = str(uuid)
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = index
+                if vis:
+                    try:
+                        phys = int(vis.split(",")[index])
+                    except Exception:
+                        phys = index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv, self._h = pynvml, h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _poll(self):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    except Exception:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    try:
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        pw = None
+                    self.samples.append((sm, rs, pw))
+                except Exception:
+                    pass
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+        if self._h is not None and self._thread is None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        self.resume()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def resume(self):
+        self._active.set()
+        if self._h is None:
+            self._smi_sample()
+
+    def pause(self):
+        self._active.clear()
+
+    def _smi_sample(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw,"
+                                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            rs = 0
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    rs |= self.BAD[name]
+            self.samples.append((float(f[0]), rs, float(f[2])))
+            self.sm_max = float(f[1])
+        except Exception:
+            pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._active.clear()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"], "samples": 0}
+        sm = [x[0] for x in self.samples]
+        reasons = sorted(n for n, bit in self.BAD.items() if any(x[1] & bit for x in self.samples))
+        pw = [x[2] for x in self.samples if x[2] is not None]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "source": "nvml" if self._h is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -227,10 +284,11 @@ def main():
     launches0 = _capi.launch_count()
     _capi.profile_enable(True)
     _capi.profile_collect()
-    sampler = ClockSampler(local_rank)
+    uuid = getattr(torch.cuda.get_device_properties(local_rank), "uuid", None)
+    sampler = ClockSampler(local_rank, uuid)
+    barrier()
     if rank == 0:
         sampler.start()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     last = None
@@ -239,11 +297,29 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.pause()
     prof = _capi.profile_collect()
     _capi.profile_enable(False)
     launches = _capi.launch_count() - launches0
-    n_sorted = int((last["p"] < 1).sum().item())
+    # what K4 ranked: the p-values below the cut in force (bh.cu: rank bound tightened by the value histogram)
+    T_last = float(last["T"])
+    if world == 1:
+        lib = _capi.load()
+        p_cut0 = float(lib.fhc_bh_p_cut(T_last, float(n_local)))
+        hist = torch.zeros(_capi.BH_CUT_BUCKETS, dtype=torch.int64, device=device)
+        _capi.check(lib.fhc_bh_cut_hist(_capi.dptr(last["p"]), n_local, p_cut0, _capi.dptr(hist),
+                                        ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        hh = np.ascontiguousarray(hist.cpu().numpy().view(np.uint64))
+        p_cut = float(lib.fhc_host_bh_cut_find(_capi.dptr(hh), T_last, 0.0, p_cut0))
+    else:
+        p_cut0 = p_cut = float(dctx.last_plan["p_cut"])
+        p_cut0 = float(dctx.last_plan["p_cut0"])
+    n_sorted = int((last["p"] < p_cut).sum().item())
+    n_below_rank_bound = int((last["p"] < p_cut0).sum().item())
+    n_items = 0
+    ws = eng._ws.get("pval_ws")
+    if ws is not None and os.environ.get("FHC_PVAL_IMPL", "lists")[0] != "t":
+        n_items = int(ws[:16].view(torch.int64).sum().item())  # continued fractions + tail sums of the last K3 launch
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -258,12 +334,14 @@ def main():
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     api.significance(host, frags, st, biases, engine=eng, out=out)  # warm-up
     barrier()
-    t0 = time.perf_counter()
+    if rank == 0:
+        sampler.resume()
     e0.record()
     for _ in range(e2e_steps):
         res = api.significance(host, frags, st, biases, engine=eng, out=out)
     e1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
@@ -279,7 +357,7 @@ def main():
 
     # ---- roofline of the dominant kernel (device time from CUDA events recorded after every launch) ----
     peak, peak_src = peaks()
-    units = {"pairs": n_local, "sorted": n_sorted}
+    units = {"pairs": n_local, "sorted": n_sorted, "items": n_items}
     kern = {k: v for k, v in prof.items()}
     top = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
     roofline = None
@@ -303,9 +381,8 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bpu * units[unit], "avg_launch_ms": avg_ms,
                     "launches_per_step": mult,
-                    "note": "pvalues_kernel is bound by instruction issue and FP64 latency, not HBM (ncu: issue slots 53 %, FP64 "
-                            "pipe 20 %, DRAM 8 %; traffic = algorithmic bytes); see DESIGN.md section 4"
-                    if top == "pvalues_kernel" else None,
+                    "note": "K3 is bound by instruction issue and FP64 latency, not HBM (see DESIGN.md section 4)"
+                    if top in ("pvalues_kernel", "pval_front_kernel", "pval_iterate_kernel", "pval_finish_kernel") else None,
                     "whole_step": {"algorithmic_bytes_per_pair": PASS_BYTES_PER_PAIR,
                                    "achieved_gbs": PASS_BYTES_PER_PAIR * n_local * args.passes / (ms_per_step * 1e-3) / 1e9,
                                    "frac": PASS_BYTES_PER_PAIR * n_local * args.passes / (ms_per_step * 1e-3) / 1e9 / peak}}
@@ -329,7 +406,8 @@ def main():
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb, "kernels": breakdown,
             "host_ms_per_pass": {k: v * 1e3 for k, v in eng.timings.get(1, {}).items()},
-            "sorted_pairs": n_sorted, "checksum_q": checksum}
+            "sorted_pairs": n_sorted, "pairs_below_rank_bound": n_below_rank_bound, "bh_p_cut": p_cut,
+            "iterated_pairs": n_items, "pval_impl": os.environ.get("FHC_PVAL_IMPL", "lists"), "checksum_q": checksum}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

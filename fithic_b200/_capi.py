@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 1
+FHC_ABI_VERSION = 2
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
 N_SCALARS = 8
@@ -48,10 +48,13 @@ _SIGNATURES = {
     "fhc_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_void_p]),
     "fhc_host_log_cr": (c_double, [c_double]),
     "fhc_host_lbeta": (c_double, [c_double, c_double]),
+    "fhc_host_bdtrc_lists": (c_double, [c_int32, c_int64, c_double]),
+    "fhc_host_one_minus_exp": (c_double, [c_double]),
     "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                    c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fhc_pvalues_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "fhc_bdtrc": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,

@@ -716,12 +716,8 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
     FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 4 * sizeof(u64), st));
     const int ntiles = (int)ws.sort.ntiles;
     if (n > 0) {
-        static int no_tighten = -1;  // FHC_BH_TIGHTEN=0: rank-bound cut only (experiments, worst-case timing)
-        if (no_tighten < 0) {
-            const char *e = getenv("FHC_BH_TIGHTEN");
-            no_tighten = (e && e[0] == '0') ? 1 : 0;
-        }
-        if (no_tighten) tighten = false;
+        const char *tenv = getenv("FHC_BH_TIGHTEN");  // =0: rank-bound cut only (experiments, worst-case timing)
+        if (tenv && tenv[0] == '0') tighten = false;
         double *d_p_cut = reinterpret_cast<double *>(ws.d_n + 2);
         if (tighten) {
             FHC_CUDA(cudaMemsetAsync(ws.cut_hist, 0, (size_t)kCutBuckets * sizeof(u64), st));

@@ -16,6 +16,7 @@
 //     by <= ~1e-10 relative, far inside the 1e-6 contract.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -70,6 +71,36 @@ FHC_HD double rn_fma(double a, double b, double c) {
     return __fma_rn(a, b, c);
 #else
     return fma(a, b, c);
+#endif
+}
+
+// bit access: device intrinsics, memcpy on the host (the host build exists for CPU-only tests of the same source)
+FHC_HD int dbl_hi(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    unsigned long long b;
+    memcpy(&b, &x, sizeof(b));
+    return (int)(b >> 32);
+#endif
+}
+FHC_HD int dbl_lo(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    unsigned long long b;
+    memcpy(&b, &x, sizeof(b));
+    return (int)(b & 0xffffffffull);
+#endif
+}
+FHC_HD double dbl_from_hi(int hi) {  // low word 0
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, 0);
+#else
+    const unsigned long long b = (unsigned long long)(unsigned int)hi << 32;
+    double x;
+    memcpy(&x, &b, sizeof(x));
+    return x;
 #endif
 }
 
@@ -244,14 +275,14 @@ struct CfState {
     bool use_d;
 };
 
-__device__ __forceinline__ void cf_init(CfState &s, double a, double b, double x, bool use_d) {
+FHC_HD void cf_init(CfState &s, double a, double b, double x, bool use_d) {
     s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
     s.z = use_d ? x / (1.0 - x) : x;
     s.fi = 0.0;
     s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0;
 }
 // the same from a precomputed z (pvalue.cu prepares z for a whole work list in one uniform pass)
-__device__ __forceinline__ void cf_load(CfState &s, double a, double b, double z, bool use_d) {
+FHC_HD void cf_load(CfState &s, double a, double b, double z, bool use_d) {
     s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
     s.z = z;
     s.fi = 0.0;
@@ -260,7 +291,7 @@ __device__ __forceinline__ void cf_load(CfState &s, double a, double b, double z
 
 // one iteration (two recurrence steps, updated in place: after step 1 the slot "km2" holds the newest convergent, after
 // step 2 "km1" does again); returns true when the fraction has converged (or hit the iteration cap)
-__device__ __forceinline__ bool cf_step(CfState &s) {
+FHC_HD bool cf_step(CfState &s) {
     const double k1 = s.a + s.fi, k3 = k1 + s.fi, k4 = k3 + 1.0, k5 = 1.0 + s.fi, k8 = k3 + 2.0;
     const double up = s.apb + s.fi, dn = s.bm1 - s.fi;
     const double k2 = s.use_d ? dn : up, k6 = s.use_d ? up : dn;
@@ -280,9 +311,9 @@ __device__ __forceinline__ bool cf_step(CfState &s) {
     if (lhs < rhs || s.fi >= (double)kCfMaxIter) return true;
     const double mag = fabs(s.qkm1) + fabs(s.pkm1);
     if (mag > 1.2676506002282294e30 || mag < 7.8886090522101181e-31) {  // 2^100, 2^-100: renormalise exactly
-        const int ex = ((__double2hiint(mag) >> 20) & 0x7ff);
+        const int ex = ((dbl_hi(mag) >> 20) & 0x7ff);
         if (ex != 0 && ex != 0x7ff) {
-            const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^-(ex-1023)
+            const double sc = dbl_from_hi((2046 - ex) << 20);  // 2^-(ex-1023)
             s.pkm2 *= sc; s.pkm1 *= sc; s.qkm2 *= sc; s.qkm1 *= sc;
         }
     }
@@ -300,7 +331,7 @@ __device__ __forceinline__ bool cf_step(CfState &s) {
 // The state lives in the fields of a CfState (a lane works on one kind at a time, pvalue.cu):
 //   P = pkm1, Q = qkm1 (so the value is pkm1 / qkm1 for both kinds), j = fi, d = dprev, cN = z, invN = a, terms left = bm1
 // number of terms and the per-term factor (1-x)/(x N): the expensive part of the set-up
-__device__ __forceinline__ void tail_prepare(double count, double N, double invN, double x, double one_minus_x, double &cN,
+FHC_HD void tail_prepare(double count, double N, double invN, double x, double one_minus_x, double &cN,
                                              int &M) {
     const double k = count - 1.0;
     cN = (one_minus_x / x) * invN;
@@ -312,7 +343,7 @@ __device__ __forceinline__ void tail_prepare(double count, double N, double invN
     }
     M = (int)Md;
 }
-__device__ __forceinline__ void tail_load(CfState &s, double count, double N, double invN, double cN, int M) {
+FHC_HD void tail_load(CfState &s, double count, double N, double invN, double cN, int M) {
     s.a = invN;
     s.z = cN;
     s.pkm1 = 1.0; s.qkm1 = 1.0;
@@ -320,7 +351,7 @@ __device__ __forceinline__ void tail_load(CfState &s, double count, double N, do
     s.dprev = (N - s.fi + 1.0) * invN;
     s.bm1 = (double)M;
 }
-__device__ __forceinline__ void tail_init(CfState &s, double count, double N, double x, double one_minus_x) {
+FHC_HD void tail_init(CfState &s, double count, double N, double x, double one_minus_x) {
     double cN;
     int M;
     const double invN = 1.0 / N;
@@ -329,7 +360,7 @@ __device__ __forceinline__ void tail_init(CfState &s, double count, double N, do
 }
 
 // one term; returns true when the sum is complete
-__device__ __forceinline__ bool tail_step(CfState &s) {
+FHC_HD bool tail_step(CfState &s) {
     if (s.bm1 <= 0.0) return true;
     const double n = s.fi * s.z;
     const double dq = s.dprev * s.qkm1;
@@ -350,7 +381,7 @@ enum PvalClass : int { kClsDone = 0, kClsK0 = 1, kClsTail = 2, kClsCf = 3 };
 
 // The branch structure of scipy.special.bdtrc(k = count - 1, n = N, p = prior) and of cephes incbet up to the point
 // where real work starts.  Returns the class; for kClsDone `value` is the result.
-__device__ __forceinline__ PvalClass bdtrc_classify(int count, int N, double prior, double &value) {
+FHC_HD PvalClass bdtrc_classify(int count, int N, double prior, double &value) {
     value = NAN;
     if (isnan(prior)) return kClsDone;
     if (prior < 0.0 || prior > 1.0) return kClsDone;
@@ -366,7 +397,7 @@ __device__ __forceinline__ PvalClass bdtrc_classify(int count, int N, double pri
 }
 
 // k == 0: 1 - (1 - p)^n in cephes' two forms
-__device__ __forceinline__ double bdtrc_k0(int N, double prior) {
+FHC_HD double bdtrc_k0(int N, double prior) {
     const double dn = (double)N;
     if (prior < 0.01) {
         // -expm1(y): for y <= -1 there is no cancellation in 1 - exp(y), and that form rounds like libm's expm1 where
@@ -377,13 +408,13 @@ __device__ __forceinline__ double bdtrc_k0(int N, double prior) {
     return 1.0 - pow(1.0 - prior, dn);
 }
 
-__device__ __forceinline__ bool cf_uses_d(double aa, double bb, double xx) {
+FHC_HD bool cf_uses_d(double aa, double bb, double xx) {
     return !(xx * (aa + bb - 2.0) - (aa - 1.0) < 0.0);  // cephes: y < 0 -> incbcf, else incbd
 }
 
 // last step of incbet: prefactor in log space times the fraction / tail value w
-__device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb, double xx, double lbeta_ab, double w) {
-    const double w1 = __dsub_rn(1.0, xx);  // cephes rounds 1 - x before taking its log
+FHC_HD double incbet_finish(bool tail, double aa, double bb, double xx, double lbeta_ab, double w) {
+    const double w1 = rn_sub(1.0, xx);  // cephes rounds 1 - x before taking its log
     double div;
     if (tail) {
         w = w / xx;
@@ -403,6 +434,97 @@ __device__ __forceinline__ double incbet_finish(bool tail, double aa, double bb,
     return t;
 }
 
+// ---- the forms used by the work-list pipeline (pvalue_lists.cu) -------------------------------------------------------
+// Taylor coefficients of (expm1(r) - r) / r^2, highest degree first (1/14! ... 1/2!).  On the device they sit in constant
+// memory so that each DFMA takes its coefficient as an operand instead of two moves of a 64-bit immediate.
+#define FHC_EXPM1_TAYLOR                                                                                        \
+    {1.1470745597729725e-11, 1.6059043836821613e-10, 2.0876756987868100e-09, 2.5052108385441720e-08,            \
+     2.7557319223985893e-07, 2.7557319223985888e-06, 2.4801587301587302e-05, 1.9841269841269841e-04,            \
+     1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5}
+static __constant__ double kExpm1TaylorDev[13] = FHC_EXPM1_TAYLOR;
+static const double kExpm1TaylorHost[13] = FHC_EXPM1_TAYLOR;
+FHC_HD double expm1_taylor(int i) {
+#if defined(__CUDA_ARCH__)
+    return kExpm1TaylorDev[i];
+#else
+    return kExpm1TaylorHost[i];
+#endif
+}
+
+// 1 - exp(y) for y <= 0, one code path for every y: exp(y) = 2^k (1 + P(r)), r = y - k ln2, |r| <= ln2/2, P = expm1(r) by
+// its Taylor polynomial (degree 14: 4e-18 relative).  k == 0 returns -P (full relative accuracy for tiny y); otherwise
+// 1 - 2^k (1 + P) in one fused rounding.  The result is 1.0 from y ~ -37.4 on, like 1 - exp(y) in libm arithmetic.
+FHC_HD double one_minus_exp(double y) {
+    y = fmax(y, -100.0);
+    const double t = fma(y, 1.4426950408889634074, 6755399441055744.0);  // 1.5 * 2^52: round to nearest integer
+    const int k = dbl_lo(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, y);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double q = expm1_taylor(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < 13; ++i) q = fma(q, r, expm1_taylor(i));
+    const double P = fma(q * r, r, r);
+    const double s = dbl_from_hi((1023 + k) << 20);  // 2^k, k in [-145, 0]
+    return k == 0 ? 0.0 - P : fma(-s, 1.0 + P, 1.0);  // 0.0 - P: +0.0 for y == -0.0, like -expm1(-0.0)
+}
+
+// scipy.special.bdtrc(0, N, prior) = 1 - (1 - prior)^N, cephes' form for p < .01 (bdtr.h: -expm1(n log1p(-p))) with
+// log1p by four terms of its series: exact to 7e-22 below 2^-17.  Larger priors take bdtrc_k0.
+FHC_HD bool k0_series_ok(double prior) { return prior < 7.62939453125e-06; }
+FHC_HD double bdtrc_k0_series(double dn, double prior) {
+    const double l = -prior * fma(prior, fma(prior, fma(prior, 0.25, 0.33333333333333331), 0.5), 1.0);
+    return one_minus_exp(dn * l);
+}
+
+// The prefactor of incbet in log space (cephes incbet.h) with the divisions folded into the exponent:
+//   continued fraction  x^a (1-x)^b / (a B(a,b)) * w [/ (1-x) for incbd]   -> sub_cf = lbeta + log a
+//   tail sum            x^a (1-x)^b / (b B(a,b)) * w / x                    -> sub_tail = lbeta + log b
+FHC_HD double incbet_finish_folded(bool tail, double aa, double bb, double xx, double sub_cf, double sub_tail, double w) {
+    const double w1 = rn_sub(1.0, xx);  // cephes rounds 1 - x before taking its log
+    const double y1 = w1 - 1.0;         // exact
+    const double logw1 = (y1 > -7.62939453125e-06)
+                             ? y1 * (1.0 + y1 * (-0.5 + y1 * (0.33333333333333331 + y1 * -0.25)))
+                             : log(w1);
+    double ea = aa, eb = bb, sub = sub_cf;
+    if (tail) {
+        ea = aa - 1.0;
+        sub = sub_tail;
+    } else if (cf_uses_d(aa, bb, xx)) {
+        eb = bb - 1.0;
+    }
+    double t = ea * log(xx) + eb * logw1 - sub + log(w);
+    t = t < kMINLOG ? 0.0 : exp(t);
+    if (tail) t = (t <= kMACHEP) ? 1.0 - kMACHEP : 1.0 - t;
+    return t;
+}
+
+// Host + device scalar evaluation of the work-list pipeline's arithmetic (classification as in front_prepare, iteration,
+// folded finish): what pval_front / pval_iterate / pval_finish compute for one contact.  Used by the CPU tests through
+// fhc_host_bdtrc_lists and by nothing on the product path.
+FHC_HD double bdtrc_lists_scalar(int count, int N, double prior) {
+    double v;
+    const PvalClass cls0 = bdtrc_classify(count, N, prior, v);
+    if (cls0 == kClsDone) return v;
+    if (cls0 == kClsK0) return k0_series_ok(prior) ? bdtrc_k0_series((double)N, prior) : bdtrc_k0(N, prior);
+    const double aa = (double)count, bb = (double)((long long)N - count + 1);
+    const bool tail = rn_mul(prior, (double)N + 1.0) > aa;  // front_prepare's division-free form of x > a / (a + b)
+    const double lb = lbeta_cephes(aa, bb);
+    CfState s;
+    if (tail) {
+        tail_init(s, aa, (double)N, prior, rn_sub(1.0, prior));
+        while (!tail_step(s)) {
+        }
+    } else {
+        cf_init(s, aa, bb, prior, cf_uses_d(aa, bb, prior));
+        while (!cf_step(s)) {
+        }
+    }
+    return incbet_finish_folded(tail, aa, bb, prior, lb + log(aa), lb + log(bb), s.pkm1 / s.qkm1);
+}
+
 // scalar evaluation (one contact start to finish): used by the element-wise test entry point
 __device__ __forceinline__ double bdtrc_dev(int count, int N, double prior, const double *__restrict__ lbeta_tab,
                                             long long ntab) {
@@ -414,7 +536,7 @@ __device__ __forceinline__ double bdtrc_dev(int count, int N, double prior, cons
     const double lb = (count < ntab) ? __ldg(lbeta_tab + count) : lbeta_cephes(aa, bb);
     CfState s;
     if (cls == kClsTail) {
-        tail_init(s, aa, (double)N, prior, __dsub_rn(1.0, prior));
+        tail_init(s, aa, (double)N, prior, rn_sub(1.0, prior));
         while (!tail_step(s)) {
         }
         return incbet_finish(true, aa, bb, prior, lb, s.pkm1 / s.qkm1);

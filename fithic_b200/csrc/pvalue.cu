@@ -19,45 +19,12 @@
 #define FHC_PROFILE_STREAM st
 #include <stdlib.h>
 
-#include "cephes_dev.cuh"
+#include "pvalue_common.cuh"
 
 namespace fhc {
 
 constexpr int kPvalThreads = 256;
 constexpr int kPvalTile = 2048;  // contacts per CTA tile (8 per thread)
-
-// n / d for 32-bit n by one 64-bit multiply-high: M = ceil(2^64 / d) is exact for every n < 2^32 (d == 1 is flagged)
-struct FastDiv {
-    unsigned long long M;
-    unsigned int d;
-};
-__device__ __forceinline__ unsigned int fastdiv(unsigned int n, const FastDiv &f) {
-    return f.d == 1 ? n : (unsigned int)__umul64hi((unsigned long long)n, f.M);
-}
-
-struct PvalParams {
-    int mode;  // FHC_MODE_*
-    const int4 *mid1, *mid2, *cnt, *chrs;
-    long long n;
-    const double *bias;
-    const int *bias_mid;
-    const long long *chr_off;
-    int nchr;
-    FastDiv res;
-    long long Llo, Uhi;  // effective in-range window (L == -1 -> 0, U == -1 -> max)
-    const double *lut;
-    long long D;
-    int N_intra, N_inter;
-    double invN_intra, invN_inter;
-    double interChrProb, tL, tU;
-    const double *lbeta_intra, *lbeta_inter;
-    long long ntab_intra, ntab_inter;
-    unsigned char *outl;
-    long long line_base;  // index of the first contact of this call in the whole file (for the outlier statistics)
-    double outl_thres;
-    unsigned long long *outl_stats;
-    double *p, *expcc;
-};
 
 struct PvalSmem {
     double x[kPvalTile];   // prior of the contacts that need real work
@@ -69,65 +36,6 @@ struct PvalSmem {
     unsigned long long warp_tot[kPvalThreads / 32 + 1];
     unsigned int cursor;             // next unclaimed entry of work[]
 };
-
-// bias dictionary lookup of fithic/fithic.py:1026-1054: missing chromosome or mid point -> -1
-__device__ __forceinline__ double bias_lookup(const PvalParams &P, unsigned int chr, int mid) {
-    if ((int)chr >= P.nchr || mid < 0) return -1.0;
-    const long long lo = __ldg(P.chr_off + chr), hi = __ldg(P.chr_off + chr + 1);
-    const long long s = lo + (long long)fastdiv((unsigned int)mid, P.res);
-    if (s >= hi) return -1.0;
-    if (__ldg(P.bias_mid + s) != mid) return -1.0;
-    return __ldg(P.bias + s);
-}
-
-// The branch order of the reference's per-line loop (fithic/fithic.py:1057-1115) up to the bdtrc call.
-// Returns the evaluation class; `p` holds the result when the class is kClsDone.
-template <bool HAS_BIAS>
-__device__ __forceinline__ PvalClass pval_prepare(const PvalParams &P, int m1, int m2, int c, unsigned int ch, double &p,
-                                                  double &e, double &prior, bool &use_inter) {
-    const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
-    const bool inter = c1 != c2;
-    long long d = (long long)m1 - (long long)m2;
-    d = d < 0 ? -d : d;
-    double b1 = 1.0, b2 = 1.0;
-    if (HAS_BIAS) {
-        b1 = bias_lookup(P, c1, m1);
-        b2 = bias_lookup(P, c2, m2);
-    }
-    const bool interOnly = P.mode == FHC_MODE_INTER_ONLY;
-    p = 1.0;
-    e = 0.0;
-    prior = 0.0;
-    use_inter = false;
-    if ((b1 < 0.0 || b2 < 0.0) && !inter) return kClsDone;  // discarded locus (:1057-1063)
-    int N;
-    if (!inter && !interOnly) {
-        if (!(d >= P.Llo && d <= P.Uhi)) return kClsDone;  // intraShort / intraLong: p = 1, ExpCC = 0 (:1081-1096)
-        const unsigned int slot = fastdiv((unsigned int)d, P.res);  // intraInRange (:1065-1079)
-        const double prior0 = ((long long)slot < P.D) ? __ldg(P.lut + slot) : NAN;
-        prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
-        N = P.N_intra;
-    } else if (P.mode != FHC_MODE_INTRA_ONLY) {
-        // inter lines, and under interOnly every line that was not discarded (:1098-1108)
-        prior = __dmul_rn(P.interChrProb, __dmul_rn(b1, b2));
-        N = P.N_inter;
-        use_inter = true;
-    } else {
-        return kClsDone;  // inter line in an intraOnly run (:1110-1115)
-    }
-    if (b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU) e = __dmul_rn((double)N, prior);
-    return bdtrc_classify(c, N, prior, p);
-}
-
-__device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, double p, unsigned int &flagged) {
-    if (p < P.outl_thres) {  // NaN compares false (:1215)
-        const unsigned char m = P.outl[i];
-        const unsigned char m2 = m == 255 ? 255 : m + 1;
-        P.outl[i] = m2;
-        flagged += 1;
-        if (m2 >= 2) atomicMin(P.outl_stats + 1, (unsigned long long)(P.line_base + i));
-    }
-}
 
 // claim the next entries of the work list for the lanes that need one (every lane of the warp must call);
 // returns the position in the list or -1
@@ -371,6 +279,34 @@ __global__ void bdtrc_kernel(const int *__restrict__ km1, int N, const double *_
     out[i] = bdtrc_dev(km1[i] + 1, N, prior[i], lbeta, ntab);
 }
 
+int pvalues_tile_launch(const PvalParams &P, cudaStream_t st) {
+    const long long n = P.n;
+    // resident CTAs per SM: 3 (80 registers, ~130 B of spills outside the loops; measured 15.6 ms at 300 M contacts) or
+    // 2 (116 registers, no spills; 18.5 ms).  FHC_PVAL_OCC=2 selects the latter for experiments.
+    static int occ = -1;
+    if (occ < 0) {
+        const char *e = getenv("FHC_PVAL_OCC");
+        occ = (e && atoi(e) == 2) ? 2 : 3;
+    }
+    long long blocks = (n + kPvalTile - 1) / kPvalTile;
+    const long long cap = (long long)kNumSMs * occ;  // persistent CTAs, grid-stride over tiles
+    if (blocks > cap) blocks = cap;
+    const size_t smem = sizeof(PvalSmem);
+#define FHC_LAUNCH_PVAL(B, O)                                                                                           \
+    do {                                                                                                                \
+        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        pvalues_kernel<B, O><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);                                     \
+    } while (0)
+    if (P.bias) {
+        if (occ == 3) FHC_LAUNCH_PVAL(true, 3); else FHC_LAUNCH_PVAL(true, 2);
+    } else {
+        if (occ == 3) FHC_LAUNCH_PVAL(false, 3); else FHC_LAUNCH_PVAL(false, 2);
+    }
+#undef FHC_LAUNCH_PVAL
+    FHC_LAUNCH_CHECK("pvalues_kernel");
+    return FHC_OK;
+}
+
 }  // namespace fhc
 
 extern "C" int fhc_lbeta_table(int64_t N, double *tab, int64_t ntab, void *stream) {
@@ -410,7 +346,7 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
                            int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
                            const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
                            uint8_t *outl, int64_t line_base, double outl_thres, uint64_t *outl_stats, double *p,
-                           double *expcc, void *stream) {
+                           double *expcc, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace fhc;
     FHC_REQUIRE(mode == FHC_MODE_INTRA_ONLY || mode == FHC_MODE_INTER_ONLY || mode == FHC_MODE_ALL, FHC_E_INVALID,
                 "fhc_pvalues: unknown mode %d", mode);
@@ -421,8 +357,7 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
                 FHC_E_INVALID, "fhc_pvalues: contact and output arrays must be 16-byte aligned");
     FHC_REQUIRE(mode == FHC_MODE_INTER_ONLY || (lut != nullptr && D > 0), FHC_E_INVALID,
                 "fhc_pvalues: the distance table is required unless mode is interOnly");
-    FHC_REQUIRE(bias == nullptr || (bias_mid && chr_off && nchr > 0), FHC_E_INVALID,
-                "fhc_pvalues: bias needs bias_mid, chr_off and nchr");
+    FHC_REQUIRE(bias == nullptr || (chr_off && nchr > 0), FHC_E_INVALID, "fhc_pvalues: bias needs chr_off and nchr");
     FHC_REQUIRE(N_intra >= 0 && N_intra < (1ll << 31) && N_inter >= 0 && N_inter < (1ll << 31), FHC_E_RANGE,
                 "fhc_pvalues: N_intra = %lld / N_inter = %lld do not fit the int32 scipy.special.bdtrc truncates n to "
                 "(the reference returns NaN or garbage there, SURVEY F5)",
@@ -463,35 +398,27 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;
     P.expcc = expcc;
-    // resident CTAs per SM: 3 (80 registers, ~130 B of spills outside the loops; measured 15.6 ms at 300 M contacts) or
-    // 2 (116 registers, no spills; 18.5 ms).  FHC_PVAL_OCC=2 selects the latter for experiments.
-    static int occ = -1;
-    if (occ < 0) {
-        const char *e = getenv("FHC_PVAL_OCC");
-        occ = (e && atoi(e) == 2) ? 2 : 3;
-    }
-    long long blocks = (n + kPvalTile - 1) / kPvalTile;
-    const long long cap = (long long)kNumSMs * occ;  // persistent CTAs, grid-stride over tiles
-    if (blocks > cap) blocks = cap;
+    // Two implementations (same arithmetic, parity-tested against each other and the oracle):
+    //   work lists (pvalue_lists.cu): needs the caller's workspace; default whenever one is passed
+    //   tile-phased single kernel (below): no workspace; FHC_PVAL_IMPL=tile forces it for experiments
+    const char *impl_env = getenv("FHC_PVAL_IMPL");  // read per call so a test can run both in one process
+    const int impl = (impl_env && impl_env[0] == 't') ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
-    const size_t smem = sizeof(PvalSmem);
-#define FHC_LAUNCH_PVAL(B, O)                                                                                           \
-    do {                                                                                                                \
-        FHC_CUDA(cudaFuncSetAttribute(pvalues_kernel<B, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        pvalues_kernel<B, O><<<(unsigned int)blocks, kPvalThreads, smem, st>>>(P);                                     \
-    } while (0)
-    if (bias) {
-        if (occ == 3) FHC_LAUNCH_PVAL(true, 3); else FHC_LAUNCH_PVAL(true, 2);
-    } else {
-        if (occ == 3) FHC_LAUNCH_PVAL(false, 3); else FHC_LAUNCH_PVAL(false, 2);
-    }
-#undef FHC_LAUNCH_PVAL
-    FHC_LAUNCH_CHECK("pvalues_kernel");
-    return FHC_OK;
+    if (workspace != nullptr && impl == 0) return pvalues_lists_launch(P, workspace, workspace_bytes, st);
+    return pvalues_tile_launch(P, st);
+}
+
+extern "C" size_t fhc_pvalues_workspace_bytes(int64_t n, int64_t ntab) {
+    return fhc::pvalues_lists_workspace_bytes(n < 0 ? 0 : n, ntab < 0 ? 0 : ntab);
 }
 
 // Host builds of the table arithmetic (same source as the device code) so CPU-only tests can pin log_cr against
 // libm's log and lbeta_cephes against scipy without a GPU.  Not used by the product path.
 extern "C" double fhc_host_log_cr(double x) { return fhc::log_cr(x); }
 extern "C" double fhc_host_lbeta(double a, double b) { return fhc::lbeta_cephes(a, b); }
+// scipy.special.bdtrc(count - 1, N, prior) through the arithmetic of the work-list pipeline / of the tile kernel
+extern "C" double fhc_host_bdtrc_lists(int32_t count, int64_t N, double prior) {
+    return fhc::bdtrc_lists_scalar(count, (int)N, prior);
+}
+extern "C" double fhc_host_one_minus_exp(double y) { return fhc::one_minus_exp(y); }

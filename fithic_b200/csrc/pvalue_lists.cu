@@ -1,0 +1,454 @@
+// K3 as a work-list pipeline -- the same arithmetic as pvalue.cu, organised so that every phase runs with full warps.
+//
+// Replaces the per-line loop of fit_Spline (reference fithic/fithic.py:1017-1123) and scipy.special.bdtrc (:1070, :1101).
+// K3 is bound by instruction issue, not by HBM (ncu on the tile-phased kernel: issue slots 53 %, DRAM 8 %): what costs
+// time is lanes that idle while their neighbours run another evaluation or a longer continued fraction.  The tile-phased
+// kernel fights that inside a 2048-contact tile, but a tile only holds ~2 iterative items per lane, so its work list
+// drains almost as soon as it starts (13 of 32 lanes active on average in the iteration loop).  Here the work lists live
+// in HBM instead (16 B per item: 8 % of the DRAM bandwidth was in use), which makes them as long as the input:
+//
+//   pval_front_kernel    every contact: classify, bias gather, prior, ExpCC; results known at once and the count == 1
+//                        closed form (65 % of a sparse map) are finished here; contacts that need a continued fraction or
+//                        a tail sum are appended to two lists (one CTA-wide scan + two global atomics per 2048 contacts)
+//   pval_iterate_kernel  persistent warps pull 64-item chunks from a list; a lane whose item has converged stores
+//                        numerator/denominator and takes the next item at once, so warps stay full until the list ends
+//   pval_finish_kernel   one thread per item, uniform: prefactor in log space (2 log + 1 exp, no division besides P/Q),
+//                        p scattered to its line, outlier flag
+#define FHC_PROFILE_STREAM st
+#include <stdlib.h>
+
+#include "pvalue_common.cuh"
+
+namespace fhc {
+
+constexpr int kFrontThreads = 256;
+constexpr int kFrontTile = 2048;  // contacts per CTA iteration (two groups of four per thread)
+constexpr int kIterThreads = 256;
+constexpr int kIterChunk = 64;    // items a warp claims with one global atomic
+constexpr int kFinishThreads = 256;
+
+struct __align__(16) WorkItem {
+    double x;          // prior
+    unsigned int idx;  // line (relative to this call)
+    int cnt;           // count; bit 31: scored against N_inter
+};
+
+struct ListsWs {
+    unsigned long long *ctr;  // [0] continued fractions, [1] tail sums, [2]/[3] the cursors of the iterate kernel
+    WorkItem *items;          // capacity n: continued fractions from the front, tail sums from the back
+    double2 *pq;              // numerator / denominator of the item at the same position
+    double2 *aux_intra, *aux_inter;  // per count: lbeta + log(count), lbeta + log(N - count + 1)
+    long long cap;
+};
+
+// priors of 2^-17 and above are rare (dense short-range bins): one out-of-line copy of the general closed form
+__device__ __noinline__ double bdtrc_k0_slow(int N, double prior) { return bdtrc_k0(N, prior); }
+
+__device__ __forceinline__ double bdtrc_k0_fast(int N, double prior) {
+    return k0_series_ok(prior) ? bdtrc_k0_series((double)N, prior) : bdtrc_k0_slow(N, prior);
+}
+
+// ---- the per-line branch order of fit_Spline (fithic/fithic.py:1057-1115) and the exits of scipy.special.bdtrc /
+// cephes incbet before any real work, written as selects instead of early returns: one straight instruction stream for
+// all 32 lanes (the early-return form of pvalue_common.cuh compiles to ~25 branches per contact).
+struct FrontConst {
+    unsigned int Llo, Uhi;  // in-range window clamped to what a 32-bit distance can reach
+    bool nothing_in_range;  // L beyond 2^32 - 1
+    double dN_intra, dN_inter, dNp1_intra, dNp1_inter;
+};
+
+__device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, unsigned int chr, int mid) {
+    bool ok = (int)chr < P.nchr && mid >= 0;
+    const unsigned int c = ok ? chr : 0u;
+    const long long lo = __ldg(P.chr_off + c), hi = __ldg(P.chr_off + c + 1);
+    const unsigned int k = fastdiv((unsigned int)mid, P.res);
+    long long s = lo + (long long)k;
+    ok = ok && s < hi;
+    s = ok ? s : 0;
+    if (P.bias_mid != nullptr)  // uniform
+        ok = ok && __ldg(P.bias_mid + s) == mid;
+    else
+        ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
+    const double b = __ldg(P.bias + s);
+    return ok ? b : -1.0;
+}
+
+template <bool HAS_BIAS>
+__device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, int m1, int m2, int c,
+                                                   unsigned int ch, bool in_file, double &p, double &e, double &prior,
+                                                   bool &use_inter) {
+    const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
+    const bool inter = c1 != c2;
+    const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    double b1 = 1.0, b2 = 1.0;
+    if (HAS_BIAS) {
+        b1 = bias_lookup_sel(P, c1, m1);
+        b2 = bias_lookup_sel(P, c2, m2);
+    }
+    const bool intra_path = !inter && P.mode != FHC_MODE_INTER_ONLY;
+    const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
+    const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
+    const bool scored = in_file && !discarded && (intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
+    use_inter = !intra_path;
+    const unsigned int slot = fastdiv(d, P.res);
+    const bool slot_ok = intra_path && (long long)slot < P.D;
+    double tabv = 0.0;
+    if (P.lut != nullptr) tabv = __ldg(P.lut + (slot_ok ? slot : 0u));  // uniform branch; the index is always valid
+    const double prior0 = intra_path ? (slot_ok ? tabv : NAN) : P.interChrProb;
+    prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
+    const double dN = intra_path ? F.dN_intra : F.dN_inter;
+    const long long N = intra_path ? P.N_intra : P.N_inter;
+    const bool b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
+    e = (scored && b_ok) ? __dmul_rn(dN, prior) : 0.0;
+    // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
+    // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first
+    const long long k = (long long)c - 1;
+    const bool bad_prior = !(prior >= 0.0 && prior <= 1.0);  // NaN or outside [0, 1]
+    PvalClass cls = kClsDone;
+    double v = 1.0;  // not scored: p = 1
+    if (scored) {
+        v = prior >= 1.0 ? 1.0 : 0.0;  // incbet: xx == 1 -> 1, xx == 0 -> 0 (the values in between are iterated)
+        cls = k == 0 ? kClsK0 : kClsDone;
+        if (k == N) { v = 0.0; cls = kClsDone; }
+        if (k > N) { v = NAN; cls = kClsDone; }
+        if (k < 0) v = 1.0;
+        if (bad_prior) { v = NAN; cls = kClsDone; }
+        if (k >= 1 && k < N && prior > 0.0 && prior < 1.0) {
+            const double dNp1 = intra_path ? F.dNp1_intra : F.dNp1_inter;
+            cls = __dmul_rn(prior, dNp1) > (double)c ? kClsTail : kClsCf;  // x > a / (a + b), a + b = N + 1
+        }
+    }
+    p = v;
+    return cls;
+}
+
+// ---- front ------------------------------------------------------------------------------------------------------------
+struct FrontSmem {
+    double x[kFrontTile];
+    int cnt[kFrontTile];  // count | inter << 31
+    unsigned int warp_tot[kFrontThreads / 32];
+    unsigned long long base_cf, base_tail;
+};
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(kFrontThreads, 3) pval_front_kernel(const PvalParams P, const FrontConst F,
+                                                                      const ListsWs W) {
+    __shared__ FrontSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long ntiles = (P.n + kFrontTile - 1) / kFrontTile;
+    unsigned int flagged = 0;
+    const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
+    const int *cs = reinterpret_cast<const int *>(P.cnt);
+    const unsigned int *hs = reinterpret_cast<const unsigned int *>(P.chrs);
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * kFrontTile;
+        const bool full = base + kFrontTile <= P.n;
+        unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l0 = (h * kFrontThreads + tid) * 4;
+            int m1[4], m2[4], cc[4];
+            unsigned int ch[4];
+            if (full) {
+                const long long g = (base + l0) >> 2;
+                const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
+                const int4 ah = ldg_stream(P.chrs + g);
+                m1[0] = a1.x; m1[1] = a1.y; m1[2] = a1.z; m1[3] = a1.w;
+                m2[0] = a2.x; m2[1] = a2.y; m2[2] = a2.z; m2[3] = a2.w;
+                cc[0] = ac.x; cc[1] = ac.y; cc[2] = ac.z; cc[3] = ac.w;
+                ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y; ch[2] = (unsigned int)ah.z; ch[3] = (unsigned int)ah.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long i = base + l0 + k;
+                    const bool ok = i < P.n;
+                    m1[k] = ok ? m1s[i] : 0;
+                    m2[k] = ok ? m2s[i] : 0;
+                    cc[k] = ok ? cs[i] : 0;
+                    ch[k] = ok ? hs[i] : 0x00010000u;  // padding: an inter line
+                }
+            }
+            double e[4], pv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int li = l0 + k;
+                double prior;
+                bool use_inter;
+                const bool in_file = full || base + li < P.n;
+                const PvalClass cls = front_prepare<HAS_BIAS>(P, F, m1[k], m2[k], cc[k], ch[k], in_file, pv[k], e[k], prior,
+                                                              use_inter);
+                if (cls == kClsK0) {
+                    pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
+                } else if (cls != kClsDone) {
+                    S.x[li] = prior;
+                    S.cnt[li] = cc[k] | (use_inter ? (int)0x80000000u : 0);
+                    pv[k] = 0.0;  // overwritten by pval_finish_kernel
+                }
+                codes |= (unsigned int)cls << (2 * (h * 4 + k));
+            }
+            if (full) {
+                double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
+                __stcs(ee, make_double2(e[0], e[1]));
+                __stcs(ee + 1, make_double2(e[2], e[3]));
+                double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
+                pp[0] = make_double2(pv[0], pv[1]);  // default caching: the finish kernel writes into these lines soon
+                pp[1] = make_double2(pv[2], pv[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (base + l0 + k < P.n) {
+                        P.expcc[base + l0 + k] = e[k];
+                        P.p[base + l0 + k] = pv[k];
+                    }
+            }
+            if (P.outl != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int c = (codes >> (2 * (h * 4 + k))) & 3u;
+                    if ((c == kClsDone || c == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
+                }
+            }
+        }
+        // positions in the two lists: CTA-wide exclusive scan of (continued fractions | tail sums << 16) per thread
+        unsigned int mine = 0;
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+            const unsigned int c = (codes >> (2 * s8)) & 3u;
+            mine += (c == kClsCf ? 1u : 0u) + (c == kClsTail ? 0x10000u : 0u);
+        }
+        unsigned int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) S.warp_tot[warp] = inc;
+        __syncthreads();
+        unsigned int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kFrontThreads / 32; ++w) {
+            const unsigned int t = S.warp_tot[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        if (tid == 0) {
+            const unsigned int nCf = tot & 0xffffu, nTail = tot >> 16;
+            S.base_cf = nCf ? atomicAdd(W.ctr + 0, (unsigned long long)nCf) : 0ull;
+            S.base_tail = nTail ? atomicAdd(W.ctr + 1, (unsigned long long)nTail) : 0ull;
+        }
+        __syncthreads();
+        if (mine) {
+            const unsigned int ex = pre + inc - mine;
+            long long oCf = (long long)S.base_cf + (ex & 0xffffu);
+            long long oTail = W.cap - 1 - ((long long)S.base_tail + (ex >> 16));
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const unsigned int c = (codes >> (2 * s8)) & 3u;
+                if (c == kClsCf || c == kClsTail) {
+                    const int li = ((s8 >> 2) * kFrontThreads + tid) * 4 + (s8 & 3);
+                    WorkItem it;
+                    it.x = S.x[li];
+                    it.idx = (unsigned int)(base + li);
+                    it.cnt = S.cnt[li];
+                    if (c == kClsCf)
+                        W.items[oCf++] = it;
+                    else
+                        W.items[oTail--] = it;
+                }
+            }
+        }
+        __syncthreads();  // S.x / S.cnt / warp_tot are reused by the next tile
+    }
+    if (P.outl != nullptr) {
+        const unsigned long long f = warp_sum((unsigned long long)flagged);
+        if (lane == 0 && f) atomicAdd(P.outl_stats, f);
+    }
+}
+
+// ---- iterate ----------------------------------------------------------------------------------------------------------
+// One list, one kind of recurrence.  A warp owns a chunk [lo, hi) of list positions; lanes that need an item take the next
+// positions of the chunk in lane order; an empty chunk is refilled with one global atomic by lane 0.
+template <bool TAIL>
+__device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs &W, unsigned long long total,
+                                             unsigned long long *cursor, int lane) {
+    if (total == 0) return;
+    CfState st;
+    long long pos = -1;
+    unsigned long long lo = 0, hi = 0;
+    bool drained = false;
+    while (true) {
+        const unsigned int m = __ballot_sync(0xffffffffu, pos < 0);
+        if (m != 0 && !drained) {
+            if (lo >= hi) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(cursor, (unsigned long long)kIterChunk);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                lo = b < total ? b : total;
+                hi = b + kIterChunk < total ? b + kIterChunk : total;
+                if (lo >= hi) drained = true;
+            }
+            if (pos < 0) {
+                const unsigned long long k = lo + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                if (k < hi) {
+                    pos = TAIL ? (W.cap - 1 - (long long)k) : (long long)k;
+                    const WorkItem it = W.items[pos];
+                    const bool ui = it.cnt < 0;
+                    const int c = it.cnt & 0x7fffffff;
+                    const int N = ui ? P.N_inter : P.N_intra;
+                    const double aa = (double)c;
+                    if (TAIL) {
+                        double cN;
+                        int M;
+                        const double invN = ui ? P.invN_inter : P.invN_intra;
+                        tail_prepare(aa, (double)N, invN, it.x, __dsub_rn(1.0, it.x), cN, M);
+                        tail_load(st, aa, (double)N, invN, cN, M);
+                    } else {
+                        const double bb = (double)((long long)N - c + 1);
+                        cf_init(st, aa, bb, it.x, cf_uses_d(aa, bb, it.x));
+                    }
+                }
+            }
+            const unsigned long long adv = lo + (unsigned long long)__popc(m);
+            lo = adv < hi ? adv : hi;
+        }
+        if (__ballot_sync(0xffffffffu, pos >= 0) == 0) {
+            if (drained) break;
+            continue;
+        }
+        if (pos >= 0) {
+            const bool done = TAIL ? tail_step(st) : cf_step(st);
+            if (done) {
+                W.pq[pos] = make_double2(st.pkm1, st.qkm1);
+                pos = -1;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kIterThreads, 3) pval_iterate_kernel(const PvalParams P, const ListsWs W) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
+    iterate_list<false>(P, W, nCf, W.ctr + 2, lane);
+    iterate_list<true>(P, W, nTail, W.ctr + 3, lane);
+}
+
+// ---- finish -----------------------------------------------------------------------------------------------------------
+// aux[c] = {lbeta(c, N-c+1) + log(c), lbeta(c, N-c+1) + log(N-c+1)} from the lbeta table of the run
+__global__ void lbeta_aux_kernel(const double *__restrict__ tab, long long ntab, int N, double2 *__restrict__ aux) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ntab) return;
+    double2 v = make_double2(NAN, NAN);
+    if (c >= 1 && c <= (long long)N) {
+        const double lb = tab[c];
+        v = make_double2(lb + log((double)c), lb + log((double)((long long)N - c + 1)));
+    }
+    aux[c] = v;
+}
+
+__global__ void __launch_bounds__(kFinishThreads) pval_finish_kernel(const PvalParams P, const ListsWs W) {
+    const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
+    const unsigned long long total = nCf + nTail;
+    unsigned int flagged = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * kFinishThreads + threadIdx.x; k < total;
+         k += (unsigned long long)gridDim.x * kFinishThreads) {
+        const bool tail = k >= nCf;
+        const long long pos = tail ? (W.cap - 1 - (long long)(k - nCf)) : (long long)k;
+        const WorkItem it = W.items[pos];
+        const double2 pq = W.pq[pos];
+        const bool ui = it.cnt < 0;
+        const int c = it.cnt & 0x7fffffff;
+        const int N = ui ? P.N_inter : P.N_intra;
+        const double aa = (double)c, bb = (double)((long long)N - c + 1);
+        const double2 *aux = ui ? W.aux_inter : W.aux_intra;
+        const long long ntab = ui ? P.ntab_inter : P.ntab_intra;
+        double2 a;
+        if (aux != nullptr && c < ntab) {
+            a = __ldg(aux + c);
+        } else {
+            const double lb = lbeta_cephes(aa, bb);
+            a = make_double2(lb + log(aa), lb + log(bb));
+        }
+        const double p = incbet_finish_folded(tail, aa, bb, it.x, a.x, a.y, pq.x / pq.y);
+        P.p[it.idx] = p;
+        if (P.outl != nullptr) outlier_mark(P, (long long)it.idx, p, flagged);
+    }
+    if (P.outl != nullptr) {
+        const unsigned long long f = warp_sum((unsigned long long)flagged);
+        if ((threadIdx.x & 31) == 0 && f) atomicAdd(P.outl_stats, f);
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------------------
+static size_t lists_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t lists_layout(long long n, long long ntab_intra, long long ntab_inter, char *base, ListsWs *ws) {
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t off = 0;
+    if (ws) ws->ctr = reinterpret_cast<unsigned long long *>(base + off);
+    off += 256;
+    if (ws) ws->items = reinterpret_cast<WorkItem *>(base + off);
+    off += lists_align(nn * sizeof(WorkItem));
+    if (ws) ws->pq = reinterpret_cast<double2 *>(base + off);
+    off += lists_align(nn * sizeof(double2));
+    if (ws) ws->aux_intra = ntab_intra > 0 ? reinterpret_cast<double2 *>(base + off) : nullptr;
+    off += lists_align((size_t)(ntab_intra > 0 ? ntab_intra : 0) * sizeof(double2));
+    if (ws) ws->aux_inter = ntab_inter > 0 ? reinterpret_cast<double2 *>(base + off) : nullptr;
+    off += lists_align((size_t)(ntab_inter > 0 ? ntab_inter : 0) * sizeof(double2));
+    if (ws) ws->cap = (long long)nn;
+    return off;
+}
+
+size_t pvalues_lists_workspace_bytes(long long n, long long ntab) {
+    // the split of ntab between the two tables is not known here: reserve it for both
+    return lists_layout(n, ntab, ntab, nullptr, nullptr);
+}
+
+int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const long long n = P.n;
+    FHC_REQUIRE(n < (1ll << 32), FHC_E_INVALID, "fhc_pvalues: the work-list path takes at most 2^32 - 1 contacts per call");
+    const size_t need = lists_layout(n, P.ntab_intra, P.ntab_inter, nullptr, nullptr);
+    FHC_REQUIRE(workspace_bytes >= need, FHC_E_WORKSPACE, "fhc_pvalues: workspace of %zu bytes, need %zu", workspace_bytes,
+                need);
+    FHC_REQUIRE(aligned16(workspace), FHC_E_INVALID, "fhc_pvalues: workspace must be 16-byte aligned");
+    ListsWs W;
+    lists_layout(n, P.ntab_intra, P.ntab_inter, reinterpret_cast<char *>(workspace), &W);
+    FHC_CUDA(cudaMemsetAsync(W.ctr, 0, 256, st));
+    if (W.aux_intra != nullptr) {
+        lbeta_aux_kernel<<<(unsigned int)((P.ntab_intra + 127) / 128), 128, 0, st>>>(P.lbeta_intra, P.ntab_intra, P.N_intra,
+                                                                                  W.aux_intra);
+        FHC_LAUNCH_CHECK("lbeta_aux_kernel");
+    }
+    if (W.aux_inter != nullptr) {
+        lbeta_aux_kernel<<<(unsigned int)((P.ntab_inter + 127) / 128), 128, 0, st>>>(P.lbeta_inter, P.ntab_inter, P.N_inter,
+                                                                                  W.aux_inter);
+        FHC_LAUNCH_CHECK("lbeta_aux_kernel");
+    }
+    FrontConst F;
+    F.nothing_in_range = P.Llo > 0xffffffffll;
+    F.Llo = (unsigned int)(P.Llo > 0xffffffffll ? 0xffffffffll : P.Llo);
+    F.Uhi = (unsigned int)(P.Uhi > 0xffffffffll ? 0xffffffffll : P.Uhi);
+    F.dN_intra = (double)P.N_intra;
+    F.dN_inter = (double)P.N_inter;
+    F.dNp1_intra = (double)P.N_intra + 1.0;
+    F.dNp1_inter = (double)P.N_inter + 1.0;
+    long long tiles = (n + kFrontTile - 1) / kFrontTile;
+    long long blocks = tiles < (long long)kNumSMs * 3 ? tiles : (long long)kNumSMs * 3;
+    if (P.bias)
+        pval_front_kernel<true><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);
+    else
+        pval_front_kernel<false><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);
+    FHC_LAUNCH_CHECK("pval_front_kernel");
+    // the list lengths are only known on the device: both follow-up kernels are persistent and read them there
+    long long iblocks = (n + kIterThreads * 4 - 1) / (kIterThreads * 4);
+    if (iblocks > (long long)kNumSMs * 3) iblocks = (long long)kNumSMs * 3;
+    pval_iterate_kernel<<<(unsigned int)iblocks, kIterThreads, 0, st>>>(P, W);
+    FHC_LAUNCH_CHECK("pval_iterate_kernel");
+    long long fblocks = (n + kFinishThreads * 4 - 1) / (kFinishThreads * 4);
+    if (fblocks > (long long)kNumSMs * 4) fblocks = (long long)kNumSMs * 4;
+    pval_finish_kernel<<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
+    FHC_LAUNCH_CHECK("pval_finish_kernel");
+    return FHC_OK;
+}
+
+}  // namespace fhc

@@ -95,8 +95,17 @@ class Engine:
         self._bias_host = biases
         self._bias_dev = None
         if biases is not None:
+            # fixed-size bins on the regular grid (every slot holds mid = k * res + res / 2 or nothing): K3 can check the
+            # mid point arithmetically and skips the gather of the stored mid points
+            regular = False
+            if settings.resolution > 0 and len(biases.mids):
+                nslot = np.diff(biases.chr_off)
+                k = np.arange(len(biases.mids), dtype=np.int64) - np.repeat(biases.chr_off[:-1], nslot)
+                want = k * settings.resolution + settings.resolution // 2
+                empty = biases.mids < 0
+                regular = bool(np.all(empty | (biases.mids == want)) and np.all(biases.values[empty] == -1.0))
             self._bias_dev = (torch.from_numpy(biases.values).to(self.device),
-                              torch.from_numpy(biases.mids).to(self.device),
+                              None if regular else torch.from_numpy(biases.mids).to(self.device),
                               torch.from_numpy(biases.chr_off).to(self.device))
         self._ws = {}
         self.contacts = None
@@ -318,6 +327,8 @@ class Engine:
             bias, bmid, boff = self._bias_dev
             nchr = boff.numel() - 1
         step = n if nchunks <= 1 else max(((n + nchunks - 1) // nchunks + 4095) // 4096 * 4096, 4096)
+        wsb = int(self.lib.fhc_pvalues_workspace_bytes(min(step, n), max(nta, ntb)))
+        ws = self._buf("pval_ws", wsb)  # work lists of the contacts that need an iterative evaluation
         lo = 0
         while True:
             hi = min(lo + step, n)
@@ -327,7 +338,7 @@ class Engine:
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
                                        nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),
-                                       dptr(e[lo:hi]), self._stream()))
+                                       dptr(e[lo:hi]), dptr(ws), wsb, self._stream()))
             if after_chunk is not None:
                 after_chunk(lo, hi, p, e)
             lo = hi

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 1
+#define FHC_ABI_VERSION 2
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -124,6 +124,10 @@ int fhc_lbeta_table(int64_t N, double *tab, int64_t ntab, void *stream);
  * lgam/lbeta with explicit round-to-nearest steps): lets CPU-only tests pin the table arithmetic.  Not a product path. */
 double fhc_host_log_cr(double x);
 double fhc_host_lbeta(double a, double b);
+/* scipy.special.bdtrc(count - 1, N, prior) evaluated on the host by the source the work-list kernels of K3 run
+ * (classification, division-free continued fraction / tail sum, prefactor with folded divisions), and its 1 - exp(y). */
+double fhc_host_bdtrc_lists(int32_t count, int64_t N, double prior);
+double fhc_host_one_minus_exp(double y);
 
 /* ---- K3: per-contact p-value ---------------------------------------------------------------------------------
  * Replaces the per-line loop of fit_Spline (fithic/fithic.py:1017-1123) including scipy.special.bdtrc (:1070,:1101).
@@ -139,13 +143,21 @@ double fhc_host_lbeta(double a, double b);
  *              >= 2) -- the caller initialises outl_stats to {0, UINT64_MAX} before the first pass
  *   line_base  index in the whole file of the first contact passed (a caller may score the file slice by slice; the
  *              index is only used for outl_stats[1])
- *   p, expcc   outputs, one double per line (:1119-1122) */
+ *   p, expcc   outputs, one double per line (:1119-1122)
+ *   bias_mid   may be NULL when every slot s of chromosome c holds the locus at mid = (s - chr_off[c]) * res + res / 2
+ *              (fixed-size bins on the regular grid): the mid point is then checked arithmetically, one gather less
+ *   workspace  [dev, nullable] fhc_pvalues_workspace_bytes(n, ntab) bytes, ntab = max(ntab_intra, ntab_inter).  With a
+ *              workspace the contacts that need an iterative evaluation (continued fraction / tail sum) are compacted
+ *              into work lists in HBM and the call runs as three kernels with full warps (pvalue_lists.cu); without one
+ *              a single tile-phased kernel does everything (pvalue.cu; also forced by FHC_PVAL_IMPL=tile).  Both give
+ *              the same p-values to ~1e-13 relative. */
+size_t fhc_pvalues_workspace_bytes(int64_t n, int64_t ntab);
 int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
                 int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
                 int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
                 double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
                 const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, int64_t line_base, double outl_thres,
-                uint64_t *outl_stats, double *p, double *expcc, void *stream);
+                uint64_t *outl_stats, double *p, double *expcc, void *workspace, size_t workspace_bytes, void *stream);
 
 /* scipy.special.bdtrc(k, n, prior) element-wise on device arrays (the arithmetic core of K3, exposed for parity
  * tests against the oracle; call sites fithic/fithic.py:1070,:1101).  lbeta nullable. */

@@ -20,3 +20,11 @@ def lib():
     if not os.path.exists(_capi.LIB_PATH):
         build.build()
     return _capi.load()
+
+
+@pytest.fixture(params=["lists", "tile"])
+def pval_impl(request, monkeypatch):
+    """K3 has two implementations behind fhc_pvalues (work-list pipeline / tile-phased kernel); the library reads
+    FHC_PVAL_IMPL on every call, so a module that uses this fixture runs each of its tests through both."""
+    monkeypatch.setenv("FHC_PVAL_IMPL", request.param)
+    return request.param

@@ -10,7 +10,7 @@ from tests.test_gpu_pipeline import run_engine
 from tests.util import compare_pass, oracle_inputs
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
 
 
 def both(contacts, frags, biases, st):

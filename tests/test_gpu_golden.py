@@ -11,7 +11,7 @@ from tests.test_gpu_pipeline import run_engine
 from tests.util import GOLDEN_CASES, REAL_CASES, compare_pass, load_golden, load_kat
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES + REAL_CASES)

@@ -8,7 +8,7 @@ from oracle import fithic_oracle as O
 from tests.util import compare_pass, oracle_inputs
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
 
 
 def run_engine(contacts, frags, biases, st):

@@ -11,7 +11,7 @@ from fithic_b200 import synth
 from tests.util import load_golden, load_kat, rel_err
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
 
 
 def test_benjamini_hochberg_correction_docstring_example(lib):

@@ -38,7 +38,7 @@ def test_errors_are_reported_not_swallowed(lib):
         _capi.check(rc)
     # device entry points validate their arguments before touching the GPU
     assert lib.fhc_pvalues(7, None, None, None, None, 1, None, None, None, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
-                           None, 0, None, 0, None, 0, 0.0, None, None, None, None) == _capi.FHC_E_INVALID
+                           None, 0, None, 0, None, 0, 0.0, None, None, None, None, 0, None) == _capi.FHC_E_INVALID
     assert lib.fhc_lbeta_table(1 << 31, ctypes.c_void_p(16), 4, None) == _capi.FHC_E_RANGE
 
 
@@ -329,3 +329,45 @@ def test_bh_cut_from_value_histogram_is_exact(lib, case):
         assert 0.5 < cut < p_cut0  # ranks start at 3e6 of T = 5e6: p T / rank reaches 1 near p = 0.6
     if case == "T_small":
         assert cut == p_cut0 or np.all(q[p >= cut] == 1.0)
+
+
+def test_one_minus_exp_is_minus_expm1(lib):
+    """The single-path 1 - exp(y) of the work-list kernels (cephes_dev.cuh) against libm's -expm1, including where
+    the result saturates to exactly 1.0 and the sign of zero."""
+    rng = np.random.default_rng(1)
+    ys = -np.exp(rng.uniform(np.log(1e-300), np.log(120), 50_000))
+    ys = np.concatenate([ys, [-0.0, -1e-320, -0.3465, -0.34657359, -0.346574, -1.0, -36.7, -37.0, -37.42, -37.43,
+                              -37.44, -38, -745, -1e9]])
+    got = np.array([lib.fhc_host_one_minus_exp(float(y)) for y in ys])
+    want = -np.expm1(ys)
+    assert np.array_equal(got == 1.0, want == 1.0)
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-320)) < 4e-16
+    assert lib.fhc_host_one_minus_exp(-0.0) == 0.0 and not np.signbit(lib.fhc_host_one_minus_exp(-0.0))
+
+
+@pytest.mark.parametrize("N", [100, 171, 5000, 4219169, 300_000_000, 900_000_000, (1 << 31) - 1])
+def test_list_pipeline_arithmetic_matches_oracle(lib, N):
+    """fhc_host_bdtrc_lists = the source pval_front / pval_iterate / pval_finish run for one contact (series log1p +
+    single-path expm1 for count 1, division-free classification, continued fraction / tail sum, prefactor with the
+    divisions folded into the exponent), compiled for the host, against scipy.special.bdtrc as restated by the oracle."""
+    rng = np.random.default_rng(N % 9973)
+    n = 20_000
+    cmax = min(N, 4000)
+    cnt = np.minimum(np.floor(np.exp(rng.uniform(0, np.log(cmax + 1), n))).astype(np.int64), cmax)
+    ratio = np.exp(rng.uniform(np.log(0.01), np.log(100), n))
+    prior = np.minimum(cnt * ratio / N, 1.0)
+    prior[::97] = np.exp(rng.uniform(np.log(1e-14), 0, len(prior[::97])))
+    cnt[::5] = 1
+    cnt[7::1000] = 0
+    prior[3::1000] = np.nan
+    prior[5::1000] = 0.0
+    prior[9::1000] = -0.25
+    want = O.bdtrc(cnt - 1.0, N, prior)
+    got = np.array([lib.fhc_host_bdtrc_lists(int(c), N, float(x)) for c, x in zip(cnt, prior)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got == 1.0, want == 1.0) and np.array_equal(got == 0.0, want == 0.0)
+    ok = ~np.isnan(want) & ~((np.abs(want) < 1e-290) & (np.abs(got) < 1e-290)) & (want != 0)
+    rel = np.abs(got[ok] - want[ok]) / np.abs(want[ok])
+    assert rel.max() <= 1e-6  # the contract; count == 1 is at 4e-16
+    k0 = ok & (cnt == 1)
+    assert np.max(np.abs(got[k0] - want[k0]) / np.abs(want[k0])) < 2e-15
