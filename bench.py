@@ -336,12 +336,19 @@ def main():
     barrier()
     if rank == 0:
         sampler.resume()
+    ms0 = torch.cuda.memory_stats(device)
     e0.record()
+    e2e_each = []
     for _ in range(e2e_steps):
-        res = api.significance(host, frags, st, biases, engine=eng, out=out)
+        tc = time.perf_counter()
+        res = api.significance(host, frags, st, biases, engine=eng, out=out)  # returns with the results on the host
+        e2e_each.append((time.perf_counter() - tc) * 1e3)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    ms1 = torch.cuda.memory_stats(device)
+    alloc_diag = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
+    alloc_diag["reserved_gb"] = ms1.get("reserved_bytes.all.current", 0) / 1e9
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
@@ -403,7 +410,7 @@ def main():
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 16 * args.pairs,
                     "d2h_bytes_per_step": 24 * args.pairs * args.passes, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps, "ms_each_host_clock": e2e_each, "allocator": alloc_diag},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb, "kernels": breakdown,
             "host_ms_per_pass": {k: v * 1e3 for k, v in eng.timings.get(1, {}).items()},
             "sorted_pairs": n_sorted, "pairs_below_rank_bound": n_below_rank_bound, "bh_p_cut": p_cut,

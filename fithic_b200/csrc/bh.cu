@@ -355,24 +355,24 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const u64 *
                                                                     int shift, u32 *__restrict__ counts) {
     __shared__ u32 hist[kSortWarps][kRadix];
     const u32 ntiles = live_tiles(d_n);
-    if (blockIdx.x >= ntiles) return;
     const long long n = (long long)*d_n;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * kSortTile;
-    if (base < n) {
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // persistent CTAs: the grid does not follow n_max
+        for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        const long long base = (long long)tile * kSortTile;
 #pragma unroll
         for (int r = 0; r < kSortIPT; ++r) {
             const long long i = base + r * kSortThreads + threadIdx.x;
             if (i < n) atomicAdd(&hist[warp][(u32)(keys[i] >> shift) & 255u], 1u);
         }
-    }
-    __syncthreads();
-    u32 s = 0;
+        __syncthreads();
+        u32 s = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) s += hist[w][threadIdx.x];
-    counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = s;  // digit-major so one flat scan gives global offsets
+        for (int w = 0; w < kSortWarps; ++w) s += hist[w][threadIdx.x];
+        counts[(size_t)threadIdx.x * ntiles + tile] = s;  // digit-major so one flat scan gives global offsets
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -386,10 +386,11 @@ radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ 
     u32 *gbase = tile_off + kRadix;                                               // [kRadix]
     u32 *sw = gbase + kRadix;                                                     // [33]
     const long long n = (long long)*d_n;
-    const long long base = (long long)blockIdx.x * kSortTile;
-    if (base >= n) return;
     const u32 ntiles = live_tiles(d_n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // persistent CTAs
+    const long long base = (long long)tile * kSortTile;
+    if (base >= n) break;
     const int tile_n = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
     for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
     __syncthreads();
@@ -431,7 +432,7 @@ radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ 
     u32 total;
     const u32 ex = block_exclusive_scan_u32(cnt, sw, total);
     tile_off[threadIdx.x] = ex;
-    gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * ntiles + blockIdx.x];
+    gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * ntiles + tile];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortIPT; ++r) {
@@ -455,6 +456,8 @@ radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ 
             vals_out[dst] = svals[i];
         }
     }
+    __syncthreads();  // shared memory is reused by the next tile
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -470,23 +473,25 @@ __global__ void __launch_bounds__(kSortThreads) bh_tilemax_kernel(const u64 *__r
                                                                  long long rank_offset, double *__restrict__ tilemax) {
     __shared__ double sm[kSortWarps];
     const long long n = (long long)*d_n;
-    const long long base = (long long)blockIdx.x * kSortTile;
-    double m = 0.0;
-    if (base < n) {
+    const u32 ntiles = live_tiles(d_n);
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = (long long)tile * kSortTile;
+        double m = 0.0;
 #pragma unroll 4
         for (int r = 0; r < kSortIPT; ++r) {
             const long long i = base + r * kSortThreads + threadIdx.x;
             if (i < n) m = fmax(m, bh_value(keys[i], T, rank_offset + i + 1));
         }
-    }
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = sm[0];
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = sm[0];
 #pragma unroll
-        for (int w = 1; w < kSortWarps; ++w) t = fmax(t, sm[w]);
-        tilemax[blockIdx.x] = t;
+            for (int w = 1; w < kSortWarps; ++w) t = fmax(t, sm[w]);
+            tilemax[tile] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -533,10 +538,12 @@ bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, co
                   long long rank_offset, const double *__restrict__ tilepre, double floor_in, double *__restrict__ q) {
     __shared__ double sw[kSortWarps];
     const long long n = (long long)*d_n;
-    const long long base = (long long)blockIdx.x * kSortTile;
-    if (base >= n) return;
+    const u32 ntiles = live_tiles(d_n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double carry = fmax(tilepre[blockIdx.x], floor_in);
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = (long long)tile * kSortTile;
+    if (base >= n) break;
+    double carry = fmax(tilepre[tile], floor_in);
     for (int r = 0; r < kSortIPT; ++r) {
         const long long i = base + r * kSortThreads + threadIdx.x;
         const bool valid = i < n;
@@ -560,6 +567,7 @@ bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, co
         carry = all;
         __syncthreads();
     }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -574,6 +582,12 @@ struct SortWs {
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// persistent grids: at most `per_sm` CTAs per SM loop over the tiles that hold keys (known on the device only)
+static unsigned int sort_grid(u32 ntiles, int per_sm) {
+    const u32 cap = (u32)kNumSMs * (u32)per_sm;
+    return ntiles < cap ? (ntiles ? ntiles : 1u) : cap;
+}
 
 static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
     const u32 ntiles = (u32)((n + kSortTile - 1) / kSortTile);
@@ -602,7 +616,7 @@ static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_
                                   (int)kDownsweepSmem));
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
-        radix_upsweep_kernel<<<ws.ntiles, kSortThreads, 0, st>>>(kin, d_n, shift, ws.counts);
+        radix_upsweep_kernel<<<sort_grid(ws.ntiles, 8), kSortThreads, 0, st>>>(kin, d_n, shift, ws.counts);
         FHC_LAUNCH_CHECK("radix_upsweep_kernel");
         scan_reduce_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, d_n, ws.blocksums);
         FHC_LAUNCH_CHECK("scan_reduce_kernel");
@@ -610,7 +624,7 @@ static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_
         FHC_LAUNCH_CHECK("scan_blocksums_kernel");
         scan_apply_kernel<<<ws.nb, kScanThreads, 0, st>>>(ws.counts, d_n, ws.blocksums);
         FHC_LAUNCH_CHECK("scan_apply_kernel");
-        radix_downsweep_kernel<<<ws.ntiles, kSortThreads, kDownsweepSmem, st>>>(kin, vin, kout, vout, d_n, shift, ws.counts);
+        radix_downsweep_kernel<<<sort_grid(ws.ntiles, 3), kSortThreads, kDownsweepSmem, st>>>(kin, vin, kout, vout, d_n, shift, ws.counts);
         FHC_LAUNCH_CHECK("radix_downsweep_kernel");
         u64 *tk = kin; kin = kout; kout = tk;
         u32 *tv = vin; vin = vout; vout = tv;
@@ -732,7 +746,7 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
         FHC_LAUNCH_CHECK("bh_compact_kernel");
         const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st);
         if (rc != FHC_OK) return rc;
-        bh_tilemax_kernel<<<ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
+        bh_tilemax_kernel<<<sort_grid((u32)ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
         FHC_LAUNCH_CHECK("bh_tilemax_kernel");
     }
     bh_tilescan_kernel<<<1, kScanThreads, 0, st>>>(ws.tilemax, n > 0 ? ntiles : 0, carry_in, carry_out, ws.d_n,
@@ -745,7 +759,7 @@ static int bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, 
                      cudaStream_t st) {
     using namespace fhc;
     if (n > 0) {
-        bh_scatter_kernel<<<(int)ws.sort.ntiles, kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
+        bh_scatter_kernel<<<sort_grid(ws.sort.ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
                                                                         ws.tilemax, floor_in, q);
         FHC_LAUNCH_CHECK("bh_scatter_kernel");
     }

@@ -281,7 +281,9 @@ FHC_HD void cf_init(CfState &s, double a, double b, double x, bool use_d) {
     s.fi = 0.0;
     s.pkm2 = 0.0; s.qkm2 = 1.0; s.pkm1 = 1.0; s.qkm1 = 1.0; s.dprev = 1.0;
 }
-// the same from a precomputed z (pvalue.cu prepares z for a whole work list in one uniform pass)
+// z by a reciprocal instead of a full division (the work-list pipeline prepares it for a whole chunk at once)
+FHC_HD double cf_z(double x, bool use_d) { return use_d ? x * (1.0 / (1.0 - x)) : x; }
+// the same from a precomputed z
 FHC_HD void cf_load(CfState &s, double a, double b, double z, bool use_d) {
     s.a = a; s.apb = a + b; s.bm1 = b - 1.0; s.use_d = use_d;
     s.z = z;
@@ -434,6 +436,39 @@ FHC_HD double incbet_finish(bool tail, double aa, double bb, double xx, double l
     return t;
 }
 
+// The same lower tail summed FORWARD from its largest term, for the work-list pipeline: no term count is needed up front
+// (tail_prepare's log and square root ran on one lane in thirty), the sum simply stops when a term no longer matters.
+//   T_0 = 1, T_i = T_{i-1} s_{k-i+1}, S = sum T_i;   s_j = n_j / d_j, n_j = j cN, d_j = (N-j+1)/N, cN = (1-x)/(x N)
+// carried division free as A (numerator of the current term), Q (common denominator), P (numerator of the sum):
+//   A <- A n_j,  Q <- Q d_j,  P <- P d_j + A,   S = P / Q.
+// n_j < 1 throughout (the count is below its expectation in this branch) and d_j ~ 1, so nothing grows.  The terms fall at
+// least like r (r - 1/lambda) (r - 2/lambda) ..., r = k / lambda < 1: what is left after a term A is below ~1.3 sqrt(lambda)
+// A, so stopping at A < 1e-21 P leaves a relative error below 1e-17 for every lambda < 2^31.
+// State in a CfState: P = pkm1, Q = qkm1 (value = pkm1 / qkm1 as for the fractions), A = pkm2, j = fi, d_j = dprev, cN = z,
+// 1/N = a.
+FHC_HD double tail_cn(double N, double x, double one_minus_x) { return one_minus_x * (1.0 / (x * N)); }
+FHC_HD void tail_fwd_load(CfState &s, double count, double N, double invN, double cN) {
+    s.a = invN;
+    s.z = cN;
+    s.pkm1 = 1.0; s.qkm1 = 1.0; s.pkm2 = 1.0;
+    s.fi = count - 1.0;                        // k: the first ratio is s_k
+    s.dprev = (N - s.fi + 1.0) * invN;         // d_k
+}
+FHC_HD bool tail_fwd_step(CfState &s) {  // one term; returns true when the sum is complete
+    if (s.fi <= 0.0) return true;
+    s.pkm2 *= s.fi * s.z;
+    s.qkm1 *= s.dprev;
+    s.pkm1 = fma(s.pkm1, s.dprev, s.pkm2);
+    s.fi -= 1.0;
+    s.dprev += s.a;
+    if (s.qkm1 < 7.8886090522101181e-31) {  // 2^-100: only reachable when the count is a sizeable fraction of N
+        s.pkm2 *= 1.2676506002282294e30;
+        s.pkm1 *= 1.2676506002282294e30;
+        s.qkm1 *= 1.2676506002282294e30;
+    }
+    return s.fi <= 0.0 || s.pkm2 < 1e-21 * s.pkm1;
+}
+
 // ---- the forms used by the work-list pipeline (pvalue_lists.cu) -------------------------------------------------------
 // Taylor coefficients of (expm1(r) - r) / r^2, highest degree first (1/14! ... 1/2!).  On the device they sit in constant
 // memory so that each DFMA takes its coefficient as an operand instead of two moves of a 64-bit immediate.
@@ -514,11 +549,12 @@ FHC_HD double bdtrc_lists_scalar(int count, int N, double prior) {
     const double lb = lbeta_cephes(aa, bb);
     CfState s;
     if (tail) {
-        tail_init(s, aa, (double)N, prior, rn_sub(1.0, prior));
-        while (!tail_step(s)) {
+        tail_fwd_load(s, aa, (double)N, 1.0 / (double)N, tail_cn((double)N, prior, rn_sub(1.0, prior)));
+        while (!tail_fwd_step(s)) {
         }
     } else {
-        cf_init(s, aa, bb, prior, cf_uses_d(aa, bb, prior));
+        const bool use_d = cf_uses_d(aa, bb, prior);
+        cf_load(s, aa, bb, cf_z(prior, use_d), use_d);
         while (!cf_step(s)) {
         }
     }

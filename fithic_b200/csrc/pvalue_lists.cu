@@ -24,7 +24,7 @@ namespace fhc {
 constexpr int kFrontThreads = 256;
 constexpr int kFrontTile = 2048;  // contacts per CTA iteration (two groups of four per thread)
 constexpr int kIterThreads = 256;
-constexpr int kIterChunk = 64;    // items a warp claims with one global atomic
+constexpr int kIterChunk = 128;   // items a warp claims with one global atomic and stages in shared memory
 constexpr int kFinishThreads = 256;
 
 struct __align__(16) WorkItem {
@@ -57,43 +57,62 @@ struct FrontConst {
     double dN_intra, dN_inter, dNp1_intra, dNp1_inter;
 };
 
-__device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, unsigned int chr, int mid) {
+constexpr int kChrSmem = 1024;  // chromosome slot ranges kept in shared memory (more chromosomes: read from global memory)
+
+// REGULAR: the slots hold the loci of the regular grid (P.bias_mid == nullptr): the mid point is checked arithmetically
+template <bool REGULAR>
+__device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, const longlong2 *chr_rng, unsigned int chr, int mid) {
     bool ok = (int)chr < P.nchr && mid >= 0;
     const unsigned int c = ok ? chr : 0u;
-    const long long lo = __ldg(P.chr_off + c), hi = __ldg(P.chr_off + c + 1);
-    const unsigned int k = fastdiv((unsigned int)mid, P.res);
-    long long s = lo + (long long)k;
-    ok = ok && s < hi;
-    s = ok ? s : 0;
-    if (P.bias_mid != nullptr)  // uniform
-        ok = ok && __ldg(P.bias_mid + s) == mid;
+    longlong2 rng;
+    if (P.nchr <= kChrSmem)  // uniform
+        rng = chr_rng[c];
     else
+        rng = make_longlong2(__ldg(P.chr_off + c), __ldg(P.chr_off + c + 1));
+    const unsigned int k = fastdiv((unsigned int)mid, P.res);
+    long long s = rng.x + (long long)k;
+    ok = ok && s < rng.y;
+    s = ok ? s : 0;
+    if (REGULAR)
         ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
+    else
+        ok = ok && __ldg(P.bias_mid + s) == mid;
     const double b = __ldg(P.bias + s);
     return ok ? b : -1.0;
 }
 
-template <bool HAS_BIAS>
+// phase A of a contact: the three gathers (two bias values, the distance table), issued for all four contacts of a group
+// before anything consumes them so that their L2 latencies overlap
+template <bool HAS_BIAS, bool REGULAR>
+__device__ __forceinline__ void front_gather(const PvalParams &P, const longlong2 *chr_rng, int m1, int m2, unsigned int ch,
+                                             double &b1, double &b2, double &tabv) {
+    const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
+    const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    b1 = 1.0;
+    b2 = 1.0;
+    if (HAS_BIAS) {
+        b1 = bias_lookup_sel<REGULAR>(P, chr_rng, c1, m1);
+        b2 = bias_lookup_sel<REGULAR>(P, chr_rng, c2, m2);
+    }
+    const unsigned int slot = fastdiv(d, P.res);
+    const bool slot_ok = c1 == c2 && (long long)slot < P.D;
+    tabv = 0.0;
+    if (P.lut != nullptr) tabv = __ldg(P.lut + (slot_ok ? slot : 0u));  // uniform branch; the index is always valid
+}
+
+// phase B: classification from the gathered values
 __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, int m1, int m2, int c,
-                                                   unsigned int ch, bool in_file, double &p, double &e, double &prior,
-                                                   bool &use_inter) {
+                                                   unsigned int ch, bool in_file, double b1, double b2, double tabv,
+                                                   double &p, double &e, double &prior, bool &use_inter) {
     const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
     const bool inter = c1 != c2;
     const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
-    double b1 = 1.0, b2 = 1.0;
-    if (HAS_BIAS) {
-        b1 = bias_lookup_sel(P, c1, m1);
-        b2 = bias_lookup_sel(P, c2, m2);
-    }
     const bool intra_path = !inter && P.mode != FHC_MODE_INTER_ONLY;
     const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
     const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
     const bool scored = in_file && !discarded && (intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
     use_inter = !intra_path;
-    const unsigned int slot = fastdiv(d, P.res);
-    const bool slot_ok = intra_path && (long long)slot < P.D;
-    double tabv = 0.0;
-    if (P.lut != nullptr) tabv = __ldg(P.lut + (slot_ok ? slot : 0u));  // uniform branch; the index is always valid
+    const bool slot_ok = intra_path && (long long)fastdiv(d, P.res) < P.D;
     const double prior0 = intra_path ? (slot_ok ? tabv : NAN) : P.interChrProb;
     prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
     const double dN = intra_path ? F.dN_intra : F.dN_inter;
@@ -124,17 +143,22 @@ __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const Fr
 
 // ---- front ------------------------------------------------------------------------------------------------------------
 struct FrontSmem {
+    longlong2 chr_rng[kChrSmem];  // [first slot, end) of each chromosome in the dense bias table
     double x[kFrontTile];
     int cnt[kFrontTile];  // count | inter << 31
     unsigned int warp_tot[kFrontThreads / 32];
     unsigned long long base_cf, base_tail;
 };
 
-template <bool HAS_BIAS>
-__global__ void __launch_bounds__(kFrontThreads, 3) pval_front_kernel(const PvalParams P, const FrontConst F,
-                                                                      const ListsWs W) {
+template <bool HAS_BIAS, bool REGULAR, int kMinCtas>
+__global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(const PvalParams P, const FrontConst F,
+                                                                             const ListsWs W) {
     __shared__ FrontSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (HAS_BIAS && P.nchr <= kChrSmem) {
+        for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_longlong2(P.chr_off[c], P.chr_off[c + 1]);
+        __syncthreads();
+    }
     const long long ntiles = (P.n + kFrontTile - 1) / kFrontTile;
     unsigned int flagged = 0;
     const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
@@ -169,15 +193,17 @@ __global__ void __launch_bounds__(kFrontThreads, 3) pval_front_kernel(const Pval
                     ch[k] = ok ? hs[i] : 0x00010000u;  // padding: an inter line
                 }
             }
-            double e[4], pv[4];
+            double e[4], pv[4], gb1[4], gb2[4], gtv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) front_gather<HAS_BIAS, REGULAR>(P, S.chr_rng, m1[k], m2[k], ch[k], gb1[k], gb2[k], gtv[k]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int li = l0 + k;
                 double prior;
                 bool use_inter;
                 const bool in_file = full || base + li < P.n;
-                const PvalClass cls = front_prepare<HAS_BIAS>(P, F, m1[k], m2[k], cc[k], ch[k], in_file, pv[k], e[k], prior,
-                                                              use_inter);
+                const PvalClass cls = front_prepare(P, F, m1[k], m2[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k],
+                                                    e[k], prior, use_inter);
                 if (cls == kClsK0) {
                     pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
                 } else if (cls != kClsDone) {
@@ -267,15 +293,25 @@ __global__ void __launch_bounds__(kFrontThreads, 3) pval_front_kernel(const Pval
 }
 
 // ---- iterate ----------------------------------------------------------------------------------------------------------
-// One list, one kind of recurrence.  A warp owns a chunk [lo, hi) of list positions; lanes that need an item take the next
-// positions of the chunk in lane order; an empty chunk is refilled with one global atomic by lane 0.
+// One list, one kind of recurrence.  A warp claims a chunk of kIterChunk list positions with one global atomic, loads the
+// chunk coalesced and prepares every item's set-up (the reciprocal behind z or cN) with all 32 lanes into its own slice of
+// shared memory; a lane whose item has converged stores numerator/denominator and starts the next prepared item of the
+// chunk at once, so the lanes stay busy until the list ends.  (First version: set-up inside the refill and the item read
+// from global memory there -- 15 of 32 lanes active, 37 % of the stall samples on that load.)
+struct __align__(16) Staged {
+    double zc;  // continued fraction: z = x or x / (1 - x); tail sum: cN = (1 - x) / (x N)
+    int cnt;    // count | inter << 31
+    int use_d;  // continued fraction: cephes incbd instead of incbcf
+};
+
 template <bool TAIL>
 __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs &W, unsigned long long total,
-                                             unsigned long long *cursor, int lane) {
+                                             unsigned long long *cursor, int lane, Staged *stage) {
     if (total == 0) return;
     CfState st;
     long long pos = -1;
-    unsigned long long lo = 0, hi = 0;
+    unsigned long long base = 0;
+    unsigned int lo = 0, hi = 0;  // positions of the chunk not handed out yet: base + [lo, hi)
     bool drained = false;
     while (true) {
         const unsigned int m = __ballot_sync(0xffffffffu, pos < 0);
@@ -284,32 +320,53 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
                 unsigned long long b = 0;
                 if (lane == 0) b = atomicAdd(cursor, (unsigned long long)kIterChunk);
                 b = __shfl_sync(0xffffffffu, b, 0);
-                lo = b < total ? b : total;
-                hi = b + kIterChunk < total ? b + kIterChunk : total;
-                if (lo >= hi) drained = true;
-            }
-            if (pos < 0) {
-                const unsigned long long k = lo + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-                if (k < hi) {
-                    pos = TAIL ? (W.cap - 1 - (long long)k) : (long long)k;
-                    const WorkItem it = W.items[pos];
-                    const bool ui = it.cnt < 0;
-                    const int c = it.cnt & 0x7fffffff;
-                    const int N = ui ? P.N_inter : P.N_intra;
-                    const double aa = (double)c;
-                    if (TAIL) {
-                        double cN;
-                        int M;
-                        const double invN = ui ? P.invN_inter : P.invN_intra;
-                        tail_prepare(aa, (double)N, invN, it.x, __dsub_rn(1.0, it.x), cN, M);
-                        tail_load(st, aa, (double)N, invN, cN, M);
-                    } else {
-                        const double bb = (double)((long long)N - c + 1);
-                        cf_init(st, aa, bb, it.x, cf_uses_d(aa, bb, it.x));
+                base = b;
+                lo = 0;
+                hi = b < total ? (unsigned int)(total - b < (unsigned long long)kIterChunk ? total - b : kIterChunk) : 0u;
+                if (hi == 0) {
+                    drained = true;
+                } else {
+                    __syncwarp();  // every lane has read what it needed from the previous chunk
+#pragma unroll
+                    for (int r = 0; r < kIterChunk / 32; ++r) {
+                        const unsigned int i = r * 32 + lane;
+                        if (i < hi) {
+                            const long long ip = TAIL ? (W.cap - 1 - (long long)(base + i)) : (long long)(base + i);
+                            const WorkItem it = W.items[ip];
+                            const bool ui = it.cnt < 0;
+                            const double dN = (double)(ui ? P.N_inter : P.N_intra);
+                            Staged sg;
+                            sg.cnt = it.cnt;
+                            if (TAIL) {
+                                sg.zc = tail_cn(dN, it.x, __dsub_rn(1.0, it.x));
+                                sg.use_d = 0;
+                            } else {
+                                const double aa = (double)(it.cnt & 0x7fffffff);
+                                const bool use_d = cf_uses_d(aa, dN - aa + 1.0, it.x);
+                                sg.zc = cf_z(it.x, use_d);
+                                sg.use_d = use_d ? 1 : 0;
+                            }
+                            stage[i] = sg;
+                        }
                     }
+                    __syncwarp();
                 }
             }
-            const unsigned long long adv = lo + (unsigned long long)__popc(m);
+            if (pos < 0 && !drained) {
+                const unsigned int k = lo + (unsigned int)__popc(m & ((1u << lane) - 1u));
+                if (k < hi) {
+                    const Staged sg = stage[k];
+                    pos = TAIL ? (W.cap - 1 - (long long)(base + k)) : (long long)(base + k);
+                    const bool ui = sg.cnt < 0;
+                    const double dN = (double)(ui ? P.N_inter : P.N_intra);
+                    const double aa = (double)(sg.cnt & 0x7fffffff);
+                    if (TAIL)
+                        tail_fwd_load(st, aa, dN, ui ? P.invN_inter : P.invN_intra, sg.zc);
+                    else
+                        cf_load(st, aa, dN - aa + 1.0, sg.zc, sg.use_d != 0);
+                }
+            }
+            const unsigned int adv = lo + (unsigned int)__popc(m);
             lo = adv < hi ? adv : hi;
         }
         if (__ballot_sync(0xffffffffu, pos >= 0) == 0) {
@@ -317,7 +374,7 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
             continue;
         }
         if (pos >= 0) {
-            const bool done = TAIL ? tail_step(st) : cf_step(st);
+            const bool done = TAIL ? tail_fwd_step(st) : cf_step(st);
             if (done) {
                 W.pq[pos] = make_double2(st.pkm1, st.qkm1);
                 pos = -1;
@@ -326,11 +383,13 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
     }
 }
 
-__global__ void __launch_bounds__(kIterThreads, 3) pval_iterate_kernel(const PvalParams P, const ListsWs W) {
+__global__ void __launch_bounds__(kIterThreads, 4) pval_iterate_kernel(const PvalParams P, const ListsWs W) {
+    __shared__ Staged stage_all[kIterThreads / 32][kIterChunk];
     const int lane = threadIdx.x & 31;
+    Staged *stage = stage_all[threadIdx.x >> 5];
     const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
-    iterate_list<false>(P, W, nCf, W.ctr + 2, lane);
-    iterate_list<true>(P, W, nTail, W.ctr + 3, lane);
+    iterate_list<false>(P, W, nCf, W.ctr + 2, lane, stage);
+    iterate_list<true>(P, W, nTail, W.ctr + 3, lane, stage);
 }
 
 // ---- finish -----------------------------------------------------------------------------------------------------------
@@ -346,7 +405,8 @@ __global__ void lbeta_aux_kernel(const double *__restrict__ tab, long long ntab,
     aux[c] = v;
 }
 
-__global__ void __launch_bounds__(kFinishThreads) pval_finish_kernel(const PvalParams P, const ListsWs W) {
+template <int kMinCtas>
+__global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(const PvalParams P, const ListsWs W) {
     const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
     const unsigned long long total = nCf + nTail;
     unsigned int flagged = 0;
@@ -433,20 +493,33 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     F.dNp1_intra = (double)P.N_intra + 1.0;
     F.dNp1_inter = (double)P.N_inter + 1.0;
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
-    long long blocks = tiles < (long long)kNumSMs * 3 ? tiles : (long long)kNumSMs * 3;
-    if (P.bias)
-        pval_front_kernel<true><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);
-    else
-        pval_front_kernel<false><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);
+    long long blocks = tiles;
+    // resident CTAs per SM: FHC_PVAL_FRONT_OCC=3 keeps 80 registers, 4 (default) squeezes to 64 for more loads in flight
+    const char *focc = getenv("FHC_PVAL_FRONT_OCC");
+    const int occ = (focc && focc[0] == '3') ? 3 : 4;
+    if (blocks > (long long)kNumSMs * occ) blocks = (long long)kNumSMs * occ;
+#define FHC_FRONT(B, R, O) pval_front_kernel<B, R, O><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W)
+    if (!P.bias) {
+        if (occ == 3) FHC_FRONT(false, true, 3); else FHC_FRONT(false, true, 4);
+    } else if (P.bias_mid == nullptr) {
+        if (occ == 3) FHC_FRONT(true, true, 3); else FHC_FRONT(true, true, 4);
+    } else {
+        if (occ == 3) FHC_FRONT(true, false, 3); else FHC_FRONT(true, false, 4);
+    }
+#undef FHC_FRONT
     FHC_LAUNCH_CHECK("pval_front_kernel");
     // the list lengths are only known on the device: both follow-up kernels are persistent and read them there
     long long iblocks = (n + kIterThreads * 4 - 1) / (kIterThreads * 4);
-    if (iblocks > (long long)kNumSMs * 3) iblocks = (long long)kNumSMs * 3;
+    if (iblocks > (long long)kNumSMs * 4) iblocks = (long long)kNumSMs * 4;
     pval_iterate_kernel<<<(unsigned int)iblocks, kIterThreads, 0, st>>>(P, W);
     FHC_LAUNCH_CHECK("pval_iterate_kernel");
     long long fblocks = (n + kFinishThreads * 4 - 1) / (kFinishThreads * 4);
-    if (fblocks > (long long)kNumSMs * 4) fblocks = (long long)kNumSMs * 4;
-    pval_finish_kernel<<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
+    if (fblocks > (long long)kNumSMs * 8) fblocks = (long long)kNumSMs * 8;
+    const char *nocc = getenv("FHC_PVAL_FINISH_OCC");  // 3: 80 registers without spills; 4 (default): 64 with ~100 B spilled
+    if (nocc && nocc[0] == '3')
+        pval_finish_kernel<3><<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
+    else
+        pval_finish_kernel<4><<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
     FHC_LAUNCH_CHECK("pval_finish_kernel");
     return FHC_OK;
 }

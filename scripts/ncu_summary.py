@@ -37,7 +37,9 @@ if len(sys.argv) > 2:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + sys.argv[2]], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    hdr, data = rows[1], rows[2:]
+    hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
+    hdr = rows[hi]
+    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
     isrc, isamp, iex, ith = (hdr.index(k) for k in ("Source", "# Samples", "Instructions Executed",
                                                     "Thread Instructions Executed"))
     tot_ex = sum(int(r[iex]) for r in data) or 1
