@@ -7,8 +7,8 @@
 Workload (BASELINE.json `metric`, config[3]): synthetic whole-genome intraOnly, 5 kb bins, ICE-like bias vector,
 ~300 M contact pairs, 1 spline pass.  A "step" is the whole path over that input: K1 histogram -> host binning + spline
 fit -> K2 table -> K3 p-values -> K4 q-values.  `value` = contact pairs scored per second with the contacts resident in
-HBM; `e2e` = the same through fithic_b200.api.significance with pinned HOST arrays in and out (16 B/pair H2D, 24 B/pair
-D2H inside the timed region).  With N GPUs the same 300 M pairs are sharded by chromosome (strong scaling).
+HBM; `e2e` = the same through fithic_b200.api.significance with pinned HOST arrays in and out (16 B/pair H2D; D2H: p and
+ExpCC whole, q as the (line, value) pairs that differ from 1.0 -- all inside the timed region).  With N GPUs the same 300 M pairs are sharded by chromosome (strong scaling).
 """
 import argparse
 import ctypes
@@ -356,6 +356,14 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = args.pairs * args.passes / (e2e_ms / e2e_steps * 1e-3)
     checksum = float(np.nansum(res[-1]["q"][:1000]))
+    # bytes that crossed the link per step: p and ExpCC whole; q as (line, value) pairs where it is not 1.0, or whole
+    n_ex = int(res[-1].get("q_exceptions", -1))
+    q_bytes = 8 + 12 * n_ex if 0 <= n_ex <= max(n_local // 128, 1024) else 8 * n_local
+    d2h_bytes = (16 * n_local + q_bytes) * args.passes
+    if world > 1:
+        t = torch.tensor([d2h_bytes], dtype=torch.int64, device=device)
+        dist.all_reduce(t)
+        d2h_bytes = int(t.item())
 
     if rank != 0:
         if world > 1:
@@ -409,7 +417,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 16 * args.pairs,
-                    "d2h_bytes_per_step": 24 * args.pairs * args.passes, "steps": e2e_steps,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "q_exceptions": n_ex,
                     "ms_per_step": e2e_ms / e2e_steps, "ms_each_host_clock": e2e_each, "allocator": alloc_diag},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb, "kernels": breakdown,
             "host_ms_per_pass": {k: v * 1e3 for k, v in eng.timings.get(1, {}).items()},

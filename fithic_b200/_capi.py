@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fhc_bh_partition_scatter": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p,
                                                  c_void_p, c_void_p, c_void_p]),
     "fhc_scatter_f64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_gather_ne_one": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                            c_void_p]),

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(const u64 *
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 3)
 radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u64 *__restrict__ keys_out,
                        u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ offsets) {
     extern __shared__ __align__(16) unsigned char dsmem[];
@@ -1052,6 +1052,87 @@ extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64
     bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(cursors), send,
                                                                  idx, q);
     FHC_LAUNCH_CHECK("bh_part_scatter_kernel");
+    return FHC_OK;
+}
+
+// q-values that are not exactly 1.0 (ranked lines and NaN), as (line, value) pairs: on a sparse map that is all a caller
+// has to copy to the host -- the rest of the 8 B per line is the constant 1.0.
+namespace fhc {
+__global__ void __launch_bounds__(256) gather_ne_one_kernel(const double *__restrict__ q, long long n, u64 capacity,
+                                                           u32 *__restrict__ idx, double *__restrict__ val, u64 *count) {
+    __shared__ u32 warp_tot[8];
+    __shared__ u64 block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long per_iter = 256ll * 4;
+    for (long long b0 = (long long)blockIdx.x * per_iter; b0 < n; b0 += (long long)gridDim.x * per_iter) {
+        const long long i0 = b0 + (long long)threadIdx.x * 4;
+        double v[4];
+        if (i0 + 3 < n) {
+            const double2 a = __ldcs(reinterpret_cast<const double2 *>(q + i0));
+            const double2 b = __ldcs(reinterpret_cast<const double2 *>(q + i0 + 2));
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? q[i0 + k] : 1.0;
+        }
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mine += (v[k] == 1.0) ? 0 : 1;  // NaN != 1.0
+        const u32 any = __ballot_sync(0xffffffffu, mine != 0);
+        int inc = mine;
+        if (any) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+        }
+        if (lane == 31) warp_tot[warp] = (u32)inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const u32 c = warp_tot[w];
+                warp_tot[w] = tot;
+                tot += c;
+            }
+            block_base = tot ? atomicAdd(count, (u64)tot) : 0;
+        }
+        __syncthreads();
+        if (mine) {
+            u64 dst = block_base + warp_tot[warp] + (u64)(inc - mine);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(v[k] == 1.0)) {
+                    if (dst < capacity) {
+                        idx[dst] = (u32)(i0 + k);
+                        val[dst] = v[k];
+                    }
+                    ++dst;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+}  // namespace fhc
+
+extern "C" int fhc_gather_ne_one(const double *q, int64_t n, int64_t capacity, uint32_t *idx, double *val, uint64_t *count,
+                                 void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && n < (1ll << 32) && capacity >= 0, FHC_E_INVALID, "fhc_gather_ne_one: need 0 <= n < 2^32, capacity >= 0");
+    FHC_REQUIRE(count != nullptr, FHC_E_INVALID, "fhc_gather_ne_one: null count");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    FHC_CUDA(cudaMemsetAsync(count, 0, sizeof(u64), st));
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(q != nullptr && aligned16(q) && (capacity == 0 || (idx && val)), FHC_E_INVALID,
+                "fhc_gather_ne_one: null or misaligned array");
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    gather_ne_one_kernel<<<(unsigned int)blocks, 256, 0, st>>>(q, n, (u64)capacity, idx, val, reinterpret_cast<u64 *>(count));
+    FHC_LAUNCH_CHECK("gather_ne_one_kernel");
     return FHC_OK;
 }
 

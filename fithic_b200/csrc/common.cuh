@@ -73,4 +73,10 @@ __device__ __forceinline__ int4 ldg_stream(const int4 *p) {
     return v;
 }
 
+__device__ __forceinline__ int2 ldg_stream2(const int2 *p) {
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 }  // namespace fhc

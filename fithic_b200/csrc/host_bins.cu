@@ -5,6 +5,11 @@
 // so they are plain C++ mirroring the reference's evaluation order:
 //   fhc_host_make_bins   <- makeBinsFromInteractions   (reference fithic/fithic.py:463-553)
 //   fhc_host_frag_pairs  <- generate_FragPairs, fixed-size branch (fithic/fithic.py:596-689)
+#include <stdlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -92,7 +97,13 @@ extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxm
             inrange_once += n * cntk - (kLo + k1) * cntk / 2;
         }
     }
-    for (int b = 0; b < nbins; ++b) {
+    // float(dist / 1e6) once per distance step instead of once per (chromosome, step): the division is the slowest
+    // operation of the inner loop
+    int64_t max_steps = 0;
+    for (int c = 0; c < nchr; ++c) max_steps = nsteps[c] > max_steps ? nsteps[c] : max_steps;
+    std::vector<double> dist_mb((size_t)max_steps);
+    for (int64_t k = 0; k < max_steps; ++k) dist_mb[(size_t)k] = (double)(k * (int64_t)res) / 1000000.0;
+    auto fill_bin = [&](int b) {
         // distances of bin b: lb <= k*res <= ub; the last bin also takes everything beyond its ub (tracker clamp), and a
         // distance below bin_lb[0] cannot occur (bin_lb[0] == 0)
         int64_t kb0 = (bin_lb[b] + res - 1) / res;
@@ -107,13 +118,54 @@ extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxm
             const int64_t k1 = nsteps[c] - 1 < kb1 ? nsteps[c] - 1 : kb1;
             for (int64_t k = kb0; k <= k1; ++k) {
                 const int64_t npairs = n - k;  // may go negative when loci are unmappable
-                const int64_t dist = k * res;
-                pairs += npairs;                                               // [7] and [1] (:639-640)
-                sumdist += ((double)dist / 1000000.0) * (double)npairs;        // :641
+                pairs += npairs;                                           // [7] and [1] (:639-640)
+                sumdist += dist_mb[(size_t)k] * (double)npairs;            // :641  float(dist / 1e6) * npairs
             }
         }
         bin_pairs[b] = pairs;
         bin_sumdist[b] = sumdist;
+    };
+    // bins are independent and each keeps the reference's (chromosome, distance) order, so they can be filled
+    // concurrently without changing a bit; the wide long-distance bins hold most of the steps, hence the work-balanced
+    // split.  Small tables stay on the calling thread.
+    std::vector<int64_t> work((size_t)(nbins > 0 ? nbins : 0), 0);
+    int64_t total_work = 0;
+    for (int b = 0; b < nbins; ++b) {
+        int64_t kb0 = (bin_lb[b] + res - 1) / res;
+        int64_t kb1 = (b == nbins - 1) ? INT64_MAX : bin_ub[b] / res;
+        if (kb0 < kLo) kb0 = kLo;
+        if (kb1 > kHi) kb1 = kHi;
+        for (int c = 0; c < nchr; ++c) {
+            if (chr_n[c] <= 0) continue;
+            const int64_t k1 = nsteps[c] - 1 < kb1 ? nsteps[c] - 1 : kb1;
+            if (k1 >= kb0) work[(size_t)b] += k1 - kb0 + 1;
+        }
+        total_work += work[(size_t)b];
+    }
+    // FHC_HOST_THREADS = n fills the bins with n threads (default 1: on the build container thread start-up cost as much
+    // as it saved; the option stays for hosts where it pays)
+    int nthreads = 1;
+    if (const char *e = getenv("FHC_HOST_THREADS")) nthreads = atoi(e) > 0 ? (atoi(e) > 64 ? 64 : atoi(e)) : 1;
+    if (total_work < 200000 || nbins < 2) nthreads = 1;
+    if (nthreads <= 1) {
+        for (int b = 0; b < nbins; ++b) fill_bin(b);
+    } else {
+        // dynamic hand-out, heaviest bins first
+        std::vector<int> order((size_t)nbins);
+        for (int b = 0; b < nbins; ++b) order[(size_t)b] = b;
+        std::sort(order.begin(), order.end(), [&](int a, int b2) { return work[(size_t)a] > work[(size_t)b2]; });
+        std::atomic<int> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                const int i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= nbins) break;
+                fill_bin(order[(size_t)i]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
     }
     int64_t interpairs2 = 0, intraall2 = 0;
     for (int c = 0; c < nchr; ++c) {

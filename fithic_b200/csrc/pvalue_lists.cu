@@ -55,23 +55,29 @@ struct FrontConst {
     unsigned int Llo, Uhi;  // in-range window clamped to what a 32-bit distance can reach
     bool nothing_in_range;  // L beyond 2^32 - 1
     double dN_intra, dN_inter, dNp1_intra, dNp1_inter;
+    // n / res for n < 2^31 by one 32-bit multiply-high: m = ceil(2^(31 + l) / res), l = ceil(log2 res), q = hi32(n m) >> (l - 1)
+    // (e = m res - 2^(31 + l) < res <= 2^l and n < 2^31 give n e < 2^(31 + l): exact); res == 1 is flagged
+    unsigned int div_m, div_sh;
+    unsigned int D32;  // table length clamped to 2^32 - 1
 };
 
-constexpr int kChrSmem = 1024;  // chromosome slot ranges kept in shared memory (more chromosomes: read from global memory)
+__device__ __forceinline__ unsigned int fastdiv31(unsigned int n, const PvalParams &P, const FrontConst &F) {
+    return P.res.d == 1 ? n : (__umulhi(n, F.div_m) >> F.div_sh);
+}
 
-// REGULAR: the slots hold the loci of the regular grid (P.bias_mid == nullptr): the mid point is checked arithmetically
+constexpr int kChrSmem = 1024;  // chromosome slot ranges kept in shared memory
+
+// REGULAR: the slots hold the loci of the regular grid (P.bias_mid == nullptr): the mid point is checked arithmetically.
+// chr_rng[c] = [first slot, end) of chromosome c as 32-bit values (the caller falls back to bias_lookup of
+// pvalue_common.cuh when there are more than kChrSmem chromosomes or 2^31 slots).
 template <bool REGULAR>
-__device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, const longlong2 *chr_rng, unsigned int chr, int mid) {
-    bool ok = (int)chr < P.nchr && mid >= 0;
-    const unsigned int c = ok ? chr : 0u;
-    longlong2 rng;
-    if (P.nchr <= kChrSmem)  // uniform
-        rng = chr_rng[c];
-    else
-        rng = make_longlong2(__ldg(P.chr_off + c), __ldg(P.chr_off + c + 1));
-    const unsigned int k = fastdiv((unsigned int)mid, P.res);
-    long long s = rng.x + (long long)k;
-    ok = ok && s < rng.y;
+__device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, const FrontConst &F, const int2 *chr_rng,
+                                                  unsigned int chr, int mid) {
+    bool ok = chr < (unsigned int)P.nchr && mid >= 0;
+    const int2 rng = chr_rng[ok ? chr : 0u];
+    const unsigned int k = fastdiv31((unsigned int)mid, P, F);  // garbage for mid < 0, masked by ok
+    int s = rng.x + (int)k;
+    ok = ok && s < rng.y && s >= rng.x;
     s = ok ? s : 0;
     if (REGULAR)
         ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
@@ -84,55 +90,61 @@ __device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, const lon
 // phase A of a contact: the three gathers (two bias values, the distance table), issued for all four contacts of a group
 // before anything consumes them so that their L2 latencies overlap
 template <bool HAS_BIAS, bool REGULAR>
-__device__ __forceinline__ void front_gather(const PvalParams &P, const longlong2 *chr_rng, int m1, int m2, unsigned int ch,
-                                             double &b1, double &b2, double &tabv) {
+__device__ __forceinline__ void front_gather(const PvalParams &P, const FrontConst &F, const int2 *chr_rng, bool rng32, int m1,
+                                             int m2, unsigned int ch, double &b1, double &b2, double &tabv, unsigned int &d) {
     const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
-    const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
     b1 = 1.0;
     b2 = 1.0;
     if (HAS_BIAS) {
-        b1 = bias_lookup_sel<REGULAR>(P, chr_rng, c1, m1);
-        b2 = bias_lookup_sel<REGULAR>(P, chr_rng, c2, m2);
+        if (rng32) {  // uniform
+            b1 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c1, m1);
+            b2 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c2, m2);
+        } else {
+            b1 = bias_lookup(P, c1, m1);
+            b2 = bias_lookup(P, c2, m2);
+        }
     }
-    const unsigned int slot = fastdiv(d, P.res);
-    const bool slot_ok = c1 == c2 && (long long)slot < P.D;
-    tabv = 0.0;
-    if (P.lut != nullptr) tabv = __ldg(P.lut + (slot_ok ? slot : 0u));  // uniform branch; the index is always valid
+    const unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
+    const bool slot_ok = c1 == c2 && slot < F.D32;
+    tabv = NAN;  // beyond the table (or an inter line, which never uses it)
+    if (P.lut != nullptr) {  // uniform branch; the index is always valid
+        const double t = __ldg(P.lut + (slot_ok ? slot : 0u));
+        tabv = slot_ok ? t : NAN;
+    }
 }
 
 // phase B: classification from the gathered values
-__device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, int m1, int m2, int c,
+__device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, unsigned int d, int c,
                                                    unsigned int ch, bool in_file, double b1, double b2, double tabv,
                                                    double &p, double &e, double &prior, bool &use_inter) {
-    const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
-    const bool inter = c1 != c2;
-    const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    const bool inter = (ch & 0xffffu) != (ch >> 16);
     const bool intra_path = !inter && P.mode != FHC_MODE_INTER_ONLY;
     const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
     const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
     const bool scored = in_file && !discarded && (intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
     use_inter = !intra_path;
-    const bool slot_ok = intra_path && (long long)fastdiv(d, P.res) < P.D;
-    const double prior0 = intra_path ? (slot_ok ? tabv : NAN) : P.interChrProb;
+    const double prior0 = intra_path ? tabv : P.interChrProb;  // tabv is NaN beyond the table
     prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
     const double dN = intra_path ? F.dN_intra : F.dN_inter;
-    const long long N = intra_path ? P.N_intra : P.N_inter;
+    const unsigned int N = (unsigned int)(intra_path ? P.N_intra : P.N_inter);  // 0 <= N < 2^31
     const bool b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
     e = (scored && b_ok) ? __dmul_rn(dN, prior) : 0.0;
     // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
-    // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first
-    const long long k = (long long)c - 1;
+    // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first.  For c >= 1,
+    // k = c - 1 is compared as an unsigned 32-bit value (c <= 0, i.e. k < 0, is handled on its own).
+    const unsigned int k = (unsigned int)c - 1u;
     const bool bad_prior = !(prior >= 0.0 && prior <= 1.0);  // NaN or outside [0, 1]
     PvalClass cls = kClsDone;
     double v = 1.0;  // not scored: p = 1
     if (scored) {
         v = prior >= 1.0 ? 1.0 : 0.0;  // incbet: xx == 1 -> 1, xx == 0 -> 0 (the values in between are iterated)
-        cls = k == 0 ? kClsK0 : kClsDone;
+        cls = c == 1 ? kClsK0 : kClsDone;
         if (k == N) { v = 0.0; cls = kClsDone; }
         if (k > N) { v = NAN; cls = kClsDone; }
-        if (k < 0) v = 1.0;
+        if (c <= 0) { v = 1.0; cls = kClsDone; }
         if (bad_prior) { v = NAN; cls = kClsDone; }
-        if (k >= 1 && k < N && prior > 0.0 && prior < 1.0) {
+        if (c >= 2 && k < N && prior > 0.0 && prior < 1.0) {
             const double dNp1 = intra_path ? F.dNp1_intra : F.dNp1_inter;
             cls = __dmul_rn(prior, dNp1) > (double)c ? kClsTail : kClsCf;  // x > a / (a + b), a + b = N + 1
         }
@@ -143,21 +155,27 @@ __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const Fr
 
 // ---- front ------------------------------------------------------------------------------------------------------------
 struct FrontSmem {
-    longlong2 chr_rng[kChrSmem];  // [first slot, end) of each chromosome in the dense bias table
+    int2 chr_rng[kChrSmem];  // [first slot, end) of each chromosome in the dense bias table
     double x[kFrontTile];
     int cnt[kFrontTile];  // count | inter << 31
     unsigned int warp_tot[kFrontThreads / 32];
     unsigned long long base_cf, base_tail;
 };
 
-template <bool HAS_BIAS, bool REGULAR, int kMinCtas>
+// kG contacts per thread and load (4: 128-bit loads and stores, 80 registers, 3 CTAs per SM; 2: 64-bit loads, 128-bit
+// stores of two doubles, fits 64 registers, 4 CTAs per SM); a thread handles 8 contacts of a tile either way.
+template <bool HAS_BIAS, bool REGULAR, int kMinCtas, int kG>
 __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(const PvalParams P, const FrontConst F,
                                                                              const ListsWs W) {
     __shared__ FrontSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (HAS_BIAS && P.nchr <= kChrSmem) {
-        for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_longlong2(P.chr_off[c], P.chr_off[c + 1]);
-        __syncthreads();
+    bool rng32 = false;
+    if (HAS_BIAS) {
+        rng32 = P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
+        if (rng32) {
+            for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
+            __syncthreads();
+        }
     }
     const long long ntiles = (P.n + kFrontTile - 1) / kFrontTile;
     unsigned int flagged = 0;
@@ -170,21 +188,34 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
         const bool full = base + kFrontTile <= P.n;
         unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l0 = (h * kFrontThreads + tid) * 4;
-            int m1[4], m2[4], cc[4];
-            unsigned int ch[4];
+        for (int h = 0; h < 8 / kG; ++h) {
+            const int l0 = (h * kFrontThreads + tid) * kG;
+            int m1[kG], m2[kG], cc[kG];
+            unsigned int ch[kG];
             if (full) {
-                const long long g = (base + l0) >> 2;
-                const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
-                const int4 ah = ldg_stream(P.chrs + g);
-                m1[0] = a1.x; m1[1] = a1.y; m1[2] = a1.z; m1[3] = a1.w;
-                m2[0] = a2.x; m2[1] = a2.y; m2[2] = a2.z; m2[3] = a2.w;
-                cc[0] = ac.x; cc[1] = ac.y; cc[2] = ac.z; cc[3] = ac.w;
-                ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y; ch[2] = (unsigned int)ah.z; ch[3] = (unsigned int)ah.w;
+                if (kG == 4) {
+                    const long long g = (base + l0) >> 2;
+                    const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
+                    const int4 ah = ldg_stream(P.chrs + g);
+                    m1[0] = a1.x; m1[1] = a1.y; m1[kG - 2] = a1.z; m1[kG - 1] = a1.w;
+                    m2[0] = a2.x; m2[1] = a2.y; m2[kG - 2] = a2.z; m2[kG - 1] = a2.w;
+                    cc[0] = ac.x; cc[1] = ac.y; cc[kG - 2] = ac.z; cc[kG - 1] = ac.w;
+                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
+                    ch[kG - 2] = (unsigned int)ah.z; ch[kG - 1] = (unsigned int)ah.w;
+                } else {
+                    const long long g = (base + l0) >> 1;
+                    const int2 a1 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid1) + g);
+                    const int2 a2 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid2) + g);
+                    const int2 ac = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + g);
+                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + g);
+                    m1[0] = a1.x; m1[1] = a1.y;
+                    m2[0] = a2.x; m2[1] = a2.y;
+                    cc[0] = ac.x; cc[1] = ac.y;
+                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
+                }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < kG; ++k) {
                     const long long i = base + l0 + k;
                     const bool ok = i < P.n;
                     m1[k] = ok ? m1s[i] : 0;
@@ -193,17 +224,19 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
                     ch[k] = ok ? hs[i] : 0x00010000u;  // padding: an inter line
                 }
             }
-            double e[4], pv[4], gb1[4], gb2[4], gtv[4];
+            double e[kG], pv[kG], gb1[kG], gb2[kG], gtv[kG];
+            unsigned int dd[kG];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) front_gather<HAS_BIAS, REGULAR>(P, S.chr_rng, m1[k], m2[k], ch[k], gb1[k], gb2[k], gtv[k]);
+            for (int k = 0; k < kG; ++k)
+                front_gather<HAS_BIAS, REGULAR>(P, F, S.chr_rng, rng32, m1[k], m2[k], ch[k], gb1[k], gb2[k], gtv[k], dd[k]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kG; ++k) {
                 const int li = l0 + k;
                 double prior;
                 bool use_inter;
                 const bool in_file = full || base + li < P.n;
-                const PvalClass cls = front_prepare(P, F, m1[k], m2[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k],
-                                                    e[k], prior, use_inter);
+                const PvalClass cls = front_prepare(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k],
+                                                    prior, use_inter);
                 if (cls == kClsK0) {
                     pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
                 } else if (cls != kClsDone) {
@@ -211,18 +244,19 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
                     S.cnt[li] = cc[k] | (use_inter ? (int)0x80000000u : 0);
                     pv[k] = 0.0;  // overwritten by pval_finish_kernel
                 }
-                codes |= (unsigned int)cls << (2 * (h * 4 + k));
+                codes |= (unsigned int)cls << (2 * (h * kG + k));
             }
             if (full) {
                 double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
-                __stcs(ee, make_double2(e[0], e[1]));
-                __stcs(ee + 1, make_double2(e[2], e[3]));
                 double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
-                pp[0] = make_double2(pv[0], pv[1]);  // default caching: the finish kernel writes into these lines soon
-                pp[1] = make_double2(pv[2], pv[3]);
+#pragma unroll
+                for (int k = 0; k < kG; k += 2) {
+                    __stcs(ee + k / 2, make_double2(e[k], e[k + 1]));
+                    pp[k / 2] = make_double2(pv[k], pv[k + 1]);  // default caching: the finish kernel writes into these lines soon
+                }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < kG; ++k)
                     if (base + l0 + k < P.n) {
                         P.expcc[base + l0 + k] = e[k];
                         P.p[base + l0 + k] = pv[k];
@@ -230,8 +264,8 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
             }
             if (P.outl != nullptr) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned int c = (codes >> (2 * (h * 4 + k))) & 3u;
+                for (int k = 0; k < kG; ++k) {
+                    const unsigned int c = (codes >> (2 * (h * kG + k))) & 3u;
                     if ((c == kClsDone || c == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
                 }
             }
@@ -272,7 +306,7 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
             for (int s8 = 0; s8 < 8; ++s8) {
                 const unsigned int c = (codes >> (2 * s8)) & 3u;
                 if (c == kClsCf || c == kClsTail) {
-                    const int li = ((s8 >> 2) * kFrontThreads + tid) * 4 + (s8 & 3);
+                    const int li = ((s8 / kG) * kFrontThreads + tid) * kG + (s8 % kG);
                     WorkItem it;
                     it.x = S.x[li];
                     it.idx = (unsigned int)(base + li);
@@ -405,33 +439,47 @@ __global__ void lbeta_aux_kernel(const double *__restrict__ tab, long long ntab,
     aux[c] = v;
 }
 
+// Two items per thread and iteration: their four 16-byte loads are issued before the first logarithm starts (the kernel
+// waits on memory, not on arithmetic: two thirds of its stall samples sat on these loads with one item per thread).
 template <int kMinCtas>
 __global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(const PvalParams P, const ListsWs W) {
     const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
     const unsigned long long total = nCf + nTail;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kFinishThreads;
     unsigned int flagged = 0;
-    for (unsigned long long k = (unsigned long long)blockIdx.x * kFinishThreads + threadIdx.x; k < total;
-         k += (unsigned long long)gridDim.x * kFinishThreads) {
-        const bool tail = k >= nCf;
-        const long long pos = tail ? (W.cap - 1 - (long long)(k - nCf)) : (long long)k;
-        const WorkItem it = W.items[pos];
-        const double2 pq = W.pq[pos];
-        const bool ui = it.cnt < 0;
-        const int c = it.cnt & 0x7fffffff;
-        const int N = ui ? P.N_inter : P.N_intra;
-        const double aa = (double)c, bb = (double)((long long)N - c + 1);
-        const double2 *aux = ui ? W.aux_inter : W.aux_intra;
-        const long long ntab = ui ? P.ntab_inter : P.ntab_intra;
-        double2 a;
-        if (aux != nullptr && c < ntab) {
-            a = __ldg(aux + c);
-        } else {
-            const double lb = lbeta_cephes(aa, bb);
-            a = make_double2(lb + log(aa), lb + log(bb));
+    for (unsigned long long k0 = (unsigned long long)blockIdx.x * kFinishThreads + threadIdx.x; k0 < total; k0 += 2 * stride) {
+        WorkItem it[2];
+        double2 pq[2];
+        bool tail[2], live[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned long long k = k0 + j * stride;
+            live[j] = k < total;
+            tail[j] = k >= nCf;
+            const long long pos = live[j] ? (tail[j] ? (W.cap - 1 - (long long)(k - nCf)) : (long long)k) : 0;
+            it[j] = W.items[pos];
+            pq[j] = W.pq[pos];
         }
-        const double p = incbet_finish_folded(tail, aa, bb, it.x, a.x, a.y, pq.x / pq.y);
-        P.p[it.idx] = p;
-        if (P.outl != nullptr) outlier_mark(P, (long long)it.idx, p, flagged);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!live[j]) continue;
+            const bool ui = it[j].cnt < 0;
+            const int c = it[j].cnt & 0x7fffffff;
+            const int N = ui ? P.N_inter : P.N_intra;
+            const double aa = (double)c, bb = (double)((long long)N - c + 1);
+            const double2 *aux = ui ? W.aux_inter : W.aux_intra;
+            const long long ntab = ui ? P.ntab_inter : P.ntab_intra;
+            double2 a;
+            if (aux != nullptr && c < ntab) {
+                a = __ldg(aux + c);
+            } else {
+                const double lb = lbeta_cephes(aa, bb);
+                a = make_double2(lb + log(aa), lb + log(bb));
+            }
+            const double p = incbet_finish_folded(tail[j], aa, bb, it[j].x, a.x, a.y, pq[j].x / pq[j].y);
+            P.p[it[j].idx] = p;
+            if (P.outl != nullptr) outlier_mark(P, (long long)it[j].idx, p, flagged);
+        }
     }
     if (P.outl != nullptr) {
         const unsigned long long f = warp_sum((unsigned long long)flagged);
@@ -492,21 +540,38 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     F.dN_inter = (double)P.N_inter;
     F.dNp1_intra = (double)P.N_intra + 1.0;
     F.dNp1_inter = (double)P.N_inter + 1.0;
+    {
+        const unsigned int d = P.res.d;
+        unsigned int l = 0;
+        while ((1ull << l) < d) ++l;  // ceil(log2 d)
+        F.div_sh = l ? l - 1 : 0;
+        F.div_m = d > 1 ? (unsigned int)(((1ull << (31 + l)) + d - 1) / d) : 0u;
+    }
+    F.D32 = (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
     long long blocks = tiles;
-    // resident CTAs per SM: FHC_PVAL_FRONT_OCC=3 keeps 80 registers, 4 (default) squeezes to 64 for more loads in flight
-    const char *focc = getenv("FHC_PVAL_FRONT_OCC");
-    const int occ = (focc && focc[0] == '3') ? 3 : 4;
+    // FHC_PVAL_FRONT=g2 selects two contacts per load in 64 registers and 4 CTAs per SM instead of the default four
+    // contacts per load in 80 registers and 3 CTAs per SM (g4x4: four per load squeezed to 64 registers with spills)
+    const char *fv = getenv("FHC_PVAL_FRONT");
+    const int variant = (fv && fv[0] == 'g' && fv[1] == '2') ? 2 : ((fv && fv[0] == 'g' && fv[1] == '4' && fv[2] == 'x') ? 1 : 0);
+    const int occ = variant == 0 ? 3 : 4;
     if (blocks > (long long)kNumSMs * occ) blocks = (long long)kNumSMs * occ;
-#define FHC_FRONT(B, R, O) pval_front_kernel<B, R, O><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W)
-    if (!P.bias) {
-        if (occ == 3) FHC_FRONT(false, true, 3); else FHC_FRONT(false, true, 4);
-    } else if (P.bias_mid == nullptr) {
-        if (occ == 3) FHC_FRONT(true, true, 3); else FHC_FRONT(true, true, 4);
-    } else {
-        if (occ == 3) FHC_FRONT(true, false, 3); else FHC_FRONT(true, false, 4);
-    }
-#undef FHC_FRONT
+#define FHC_FRONT_V(B, R)                                                                                         \
+    do {                                                                                                          \
+        if (variant == 2)                                                                                         \
+            pval_front_kernel<B, R, 4, 2><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+        else if (variant == 1)                                                                                    \
+            pval_front_kernel<B, R, 4, 4><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+        else                                                                                                      \
+            pval_front_kernel<B, R, 3, 4><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+    } while (0)
+    if (!P.bias)
+        FHC_FRONT_V(false, true);
+    else if (P.bias_mid == nullptr)
+        FHC_FRONT_V(true, true);
+    else
+        FHC_FRONT_V(true, false);
+#undef FHC_FRONT_V
     FHC_LAUNCH_CHECK("pval_front_kernel");
     // the list lengths are only known on the device: both follow-up kernels are persistent and read them there
     long long iblocks = (n + kIterThreads * 4 - 1) / (kIterThreads * 4);

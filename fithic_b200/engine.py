@@ -139,14 +139,22 @@ class Engine:
         self.contacts = (mid1, mid2, cnt, chrs)
         self.n = n
         self.D = None
+        self._own_contacts = False
 
     def upload_contacts(self, c, non_blocking=False):
         """Host SoA -> HBM (the only per-contact host->device traffic of a run: 16 B per contact)."""
         ts = []
-        for a in (c.mid1, c.mid2, c.cnt, c.chrs.view(np.int32)):
+        reuse = self.contacts if (self.contacts is not None and getattr(self, "_own_contacts", False)
+                                  and self.n == len(c)) else None
+        for j, a in enumerate((c.mid1, c.mid2, c.cnt, c.chrs.view(np.int32))):
             h = torch.from_numpy(np.ascontiguousarray(a))
-            ts.append(h.to(self.device, non_blocking=non_blocking))
+            if reuse is not None:  # same size as the previous upload: no new device allocation
+                reuse[j].copy_(h, non_blocking=non_blocking)
+                ts.append(reuse[j])
+            else:
+                ts.append(h.to(self.device, non_blocking=non_blocking))
         self.set_contacts_device(*ts)
+        self._own_contacts = True
 
     def distance_slots(self):
         """D = number of distance slots: every |mid1 - mid2| of an intra line is < D * res."""

@@ -218,6 +218,14 @@ int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitte
                              uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream);
 int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n, double *dst, void *stream);
 
+/* The q-values that are not exactly 1.0 (ranked lines and NaN) as (line, value) pairs, in no particular order:
+ * *count [dev] receives how many there are (it may exceed `capacity`, in which case only the first `capacity` slots of
+ * idx / val [dev] were written and the caller should fall back to copying q whole).  On a sparse map almost every
+ * line of the reference's q column (fithic/fithic.py:1134-1163) is the constant 1.0, so a caller that needs q on the host
+ * fills its array with 1.0 and copies only these pairs. */
+int fhc_gather_ne_one(const double *q, int64_t n, int64_t capacity, uint32_t *idx, double *val, uint64_t *count,
+                      void *stream);
+
 /* Device radix sort of 64-bit keys with 32-bit payloads (ascending, stable), the sort inside K4, exposed for tests
  * and for the multi-GPU range-partitioned BH.  Sorted data ends in keys_out/vals_out; *_in are clobbered.
  * workspace: fhc_sort_workspace_bytes(n). */

@@ -20,7 +20,7 @@ name = rows[0][1]
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
 hdr = rows[hi]
 ix = {k: hdr.index(k) for k in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed")}
-data = [r for r in rows[hi + 1:] if len(r) > max(ix.values())]
+data = [r for r in rows[hi + 1:] if len(r) > max(ix.values()) and r[ix["Source"]] != "Source"]
 # line table
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, capture_output=True)
@@ -28,11 +28,18 @@ cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 short = re.sub(r"\(.*", "", name).replace("void ", "").replace("fhc::", "")
 short = re.sub(r"<.*", "", short)
-lines, cur, inside, tmpl = [], "?", False, None
-want_b = re.search(r"<\(bool\)(\d)>", name)
+lines, cur, inside = [], "?", False
+targs = re.search(r"<([^>]*)>", name.split("(fhc::")[0] if "(fhc::" in name else name)
+mangled_args = ""
+if targs:  # (bool)1, (int)4 -> ILb1ELi4EE
+    for a in targs.group(1).split(","):
+        m = re.match(r"\s*\((bool|int)\)(-?\d+)", a)
+        if m:
+            mangled_args += ("Lb" if m.group(1) == "bool" else "Li") + m.group(2) + "E"
+    mangled_args = "I" + mangled_args + "E"
 for ln in dis.splitlines():
     if ln.startswith(".text."):
-        inside = short in ln and (want_b is None or ("ILb%sE" % want_b.group(1)) in ln)
+        inside = (short + mangled_args) in ln
         continue
     if not inside:
         continue

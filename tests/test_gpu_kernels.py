@@ -268,6 +268,30 @@ def test_bh_cut_hist_matches_numpy(lib, n):
             assert np.all(q[(p >= cut) & ~np.isnan(p)] == 1.0)
 
 
+@pytest.mark.parametrize("n", [0, 3, 1025, 300_001])
+def test_gather_ne_one(lib, n):
+    rng = np.random.default_rng(n + 1)
+    q = np.ones(n)
+    k = n // 7
+    where = rng.choice(n, k, replace=False) if n else np.zeros(0, dtype=np.int64)
+    q[where] = rng.random(k)
+    q[where[: k // 5]] = np.nan
+    for cap in (max(k, 1), max(k // 2, 1)):
+        idx = torch.zeros(cap, dtype=torch.int32, device=DEV)
+        val = torch.zeros(cap, dtype=torch.float64, device=DEV)
+        cnt = torch.zeros(1, dtype=torch.int64, device=DEV)
+        qd = dev(q) if n else None
+        check(lib.fhc_gather_ne_one(dptr(qd), n, cap, dptr(idx), dptr(val), dptr(cnt), stream()))
+        torch.cuda.synchronize()
+        assert int(cnt.item()) == k
+        if k <= cap and k:
+            i = idx.cpu().numpy().view(np.uint32)[:k].astype(np.int64)
+            v = val.cpu().numpy()[:k]
+            o = np.argsort(i)
+            assert np.array_equal(i[o], np.sort(where))
+            assert np.array_equal(v[o], q[np.sort(where)], equal_nan=True)
+
+
 def test_bh_chained_partitions(lib):
     """rank_offset / carry_in: q of a key range computed separately equals the global result (multi-GPU contract)."""
     rng = np.random.default_rng(99)

@@ -86,3 +86,31 @@ def test_api_sliced_pvalues_match_single_launch(lib):
     for k in ("p", "q", "expcc"):
         assert np.array_equal(got[-1][k], want[k], equal_nan=True), k
     assert got[-1]["N"] == ref["N"] and got[-1]["T"] == ref["T"]
+
+
+def test_api_q_dense_and_sparse_paths(lib):
+    """api.significance brings q to the host as (line, value) pairs where q != 1.0, or whole when those are more than
+    n / 128 of the lines; both routes must reproduce the device array (NaN included)."""
+    from fithic_b200 import api
+    # allReg with bias: inter lines with a discarded locus give p = q = NaN (fithic/fithic.py:1099-1108) -> dense route
+    name, n, res, chroms, mean_count, bias, inter, sk = CASES[3]
+    contacts, frags, biases, _ = synth.make_intra(n, res, seed=1000 + len(name), chroms=chroms, mean_count=mean_count,
+                                                  with_bias=bias, inter_fraction=inter)
+    st = Settings(resolution=res, **sk)
+    want = run_engine(contacts, frags, biases, st)
+    got = api.significance(contacts, frags, st, biases)
+    assert got[-1]["q_exceptions"] > max(n // 128, 1024)
+    for k in ("p", "q", "expcc"):
+        assert np.array_equal(got[-1][k], want[-1][k], equal_nan=True), k
+    assert got[-1]["q_exceptions"] == int(np.sum(want[-1]["q"] != 1.0))
+    # a sparse high-resolution map: possible pairs >> lines, next to nothing is ranked -> sparse route
+    n, res = 400_000, 5000
+    contacts, frags, biases, _ = synth.make_intra(n, res, seed=4242, mean_count=3.0, with_bias=True)
+    st = Settings(resolution=res, noOfBins=100)
+    want = run_engine(contacts, frags, biases, st)
+    got = api.significance(contacts, frags, st, biases)
+    n_ex = int(np.sum(want[-1]["q"] != 1.0))  # NaN != 1.0
+    assert got[-1]["q_exceptions"] == n_ex
+    assert n_ex <= max(n // 128, 1024), "this data set was meant to take the sparse route"
+    for k in ("p", "q", "expcc"):
+        assert np.array_equal(got[-1][k], want[-1][k], equal_nan=True), k
