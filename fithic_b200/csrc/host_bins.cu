@@ -142,9 +142,9 @@ extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxm
         }
         total_work += work[(size_t)b];
     }
-    // FHC_HOST_THREADS = n fills the bins with n threads (default 1: on the build container thread start-up cost as much
-    // as it saved; the option stays for hosts where it pays)
-    int nthreads = 1;
+    // 4 threads by default (B200 host, 5 kb whole genome: 0.22 ms against 0.41 ms on one thread; 8 threads gain nothing
+    // more); FHC_HOST_THREADS overrides
+    int nthreads = 4;
     if (const char *e = getenv("FHC_HOST_THREADS")) nthreads = atoi(e) > 0 ? (atoi(e) > 64 ? 64 : atoi(e)) : 1;
     if (total_work < 200000 || nbins < 2) nthreads = 1;
     if (nthreads <= 1) {

@@ -550,10 +550,11 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     F.D32 = (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
     long long blocks = tiles;
-    // FHC_PVAL_FRONT=g2 selects two contacts per load in 64 registers and 4 CTAs per SM instead of the default four
-    // contacts per load in 80 registers and 3 CTAs per SM (g4x4: four per load squeezed to 64 registers with spills)
+    // Default: two contacts per load in 64 registers, 4 CTAs per SM.  FHC_PVAL_FRONT=g4 selects four contacts per load in
+    // 80 registers and 3 CTAs per SM, g4x4 the same squeezed to 64 registers with spills (B200, 300 M contacts: 4.63 ms
+    // against 5.25 ms and 5.40 ms).
     const char *fv = getenv("FHC_PVAL_FRONT");
-    const int variant = (fv && fv[0] == 'g' && fv[1] == '2') ? 2 : ((fv && fv[0] == 'g' && fv[1] == '4' && fv[2] == 'x') ? 1 : 0);
+    const int variant = (fv && fv[0] == 'g' && fv[1] == '4') ? (fv[2] == 'x' ? 1 : 0) : 2;
     const int occ = variant == 0 ? 3 : 4;
     if (blocks > (long long)kNumSMs * occ) blocks = (long long)kNumSMs * occ;
 #define FHC_FRONT_V(B, R)                                                                                         \
@@ -580,11 +581,11 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     FHC_LAUNCH_CHECK("pval_iterate_kernel");
     long long fblocks = (n + kFinishThreads * 4 - 1) / (kFinishThreads * 4);
     if (fblocks > (long long)kNumSMs * 8) fblocks = (long long)kNumSMs * 8;
-    const char *nocc = getenv("FHC_PVAL_FINISH_OCC");  // 3: 80 registers without spills; 4 (default): 64 with ~100 B spilled
-    if (nocc && nocc[0] == '3')
-        pval_finish_kernel<3><<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
-    else
+    const char *nocc = getenv("FHC_PVAL_FINISH_OCC");  // 3 (default): 80 registers; 4: 64 registers with ~150 B spilled
+    if (nocc && nocc[0] == '4')                        // (B200, 300 M contacts: 1.61 ms against 1.83 ms)
         pval_finish_kernel<4><<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
+    else
+        pval_finish_kernel<3><<<(unsigned int)fblocks, kFinishThreads, 0, st>>>(P, W);
     FHC_LAUNCH_CHECK("pval_finish_kernel");
     return FHC_OK;
 }

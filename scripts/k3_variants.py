@@ -18,11 +18,11 @@ st = Settings(resolution=5000, noOfBins=100)
 eng = Engine(st, frags, biases, device=dev)
 eng.set_contacts_device(m1, m2, c, ch)
 VARIANTS = [
-    ("lists g4 occ3 (default)", {}),
-    ("lists g2 occ4", {"FHC_PVAL_FRONT": "g2"}),
-    ("lists g4 occ4 (spills)", {"FHC_PVAL_FRONT": "g4x4"}),
-    ("lists g2 occ4, finish3", {"FHC_PVAL_FRONT": "g2", "FHC_PVAL_FINISH_OCC": "3"}),
+    ("lists: g2 front, finish occ 3 (default)", {}),
+    ("lists: g4 front", {"FHC_PVAL_FRONT": "g4"}),
+    ("lists: finish occ 4", {"FHC_PVAL_FINISH_OCC": "4"}),
     ("tile", {"FHC_PVAL_IMPL": "tile"}),
+    ("lists, rank-bound cut only", {"FHC_BH_TIGHTEN": "0"}),
 ]
 KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN")
 ref = None
