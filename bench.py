@@ -200,6 +200,8 @@ def workload_config(args):
     return {"workload": "synthetic whole-genome intraOnly %d bp + ICE-like bias vector, %d contact pairs, %d spline "
                         "pass(es), sharded by chromosome" % (args.res, args.pairs, args.passes),
             "pairs": args.pairs, "resolution": args.res, "bins": 100, "passes": args.passes,
+            "line_order": "sorted by (chromosome, mid1, mid2) like a contact file" if args.order == "file"
+                          else "random inside each chromosome",
             "l2_policy": "inputs (16 B/pair) are far larger than the 126 MB L2; no explicit flush"}
 
 
@@ -217,6 +219,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=3_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default="file", choices=["file", "random"],
+                    help="line order inside a chromosome: sorted by (mid1, mid2) as contact files are, or as drawn")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 0)
@@ -259,7 +263,7 @@ def main():
     names, sizes = synth.genome(None)
     shards = synth.lpt_shards([int(s) for s in sizes], world)
     (mid1, mid2, cnt, chrs), frags, biases, per = synth.make_intra_device(
-        args.pairs, args.res, args.seed, device, mean_count=3.0, with_bias=True, only=shards[rank])
+        args.pairs, args.res, args.seed, device, mean_count=3.0, with_bias=True, only=shards[rank], order=args.order)
     n_local = mid1.numel()
     st = Settings(resolution=args.res, noOfBins=100, noOfPasses=args.passes)
     eng = Engine(st, frags, biases, device=device, dist_ctx=dctx)

@@ -58,7 +58,7 @@ def significance(contacts, fragments, settings, biases=None, engine=None, out=No
 
         # q is 1.0 on almost every line of a sparse map: a host thread fills the pinned array with 1.0 while the GPU works
         # and only the (line, q) pairs that differ cross the PCIe link (dense copy when they are more than n / 128)
-        filler = threading.Thread(target=out.q.fill_, args=(1.0,))
+        filler = threading.Thread(target=eng.lib.fhc_host_fill_f64, args=(_capi.dptr(out.q), n, 1.0, 4))
         filler.start()
         r = eng.run_pass(passNo, outl, stats, pvalue_chunks=8 if n >= (1 << 22) else 1, after_chunk=copy_slice)
         cap = max(n // 128, 1024)

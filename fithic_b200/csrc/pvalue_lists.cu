@@ -551,8 +551,10 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
     long long blocks = tiles;
     // Default: two contacts per load in 64 registers, 4 CTAs per SM.  FHC_PVAL_FRONT=g4 selects four contacts per load in
-    // 80 registers and 3 CTAs per SM, g4x4 the same squeezed to 64 registers with spills (B200, 300 M contacts: 4.63 ms
-    // against 5.25 ms and 5.40 ms).
+    // 80 registers and 3 CTAs per SM, g4x4 the same squeezed to 64 registers with spills (B200, 300 M contacts in random
+    // order: 4.63 ms against 5.25 ms and 5.40 ms).  Also measured and dropped: the contact arrays of the next tile staged
+    // in shared memory by cp.async with the gathers issued one pair ahead (6.65 ms: the kernel waits on its scattered
+    // gathers -- 21 sectors per warp request, L1TEX at 70 % -- not on the streaming loads, and the extra barriers cost).
     const char *fv = getenv("FHC_PVAL_FRONT");
     const int variant = (fv && fv[0] == 'g' && fv[1] == '4') ? (fv[2] == 'x' ? 1 : 0) : 2;
     const int occ = variant == 0 ? 3 : 4;

@@ -202,7 +202,7 @@ class Engine:
             skip_limit = self.n if first_dup == _U64_MAX else first_dup
         hist_d, present_d, scal_d = self.hist_distance(skip, skip_limit)
         if self.dist is not None:
-            self.dist.allreduce_hist(hist_d, present_d, scal_d)
+            self.dist.allreduce_hist(hist_d, present_d, scal_d, fused=self._ws["k1buf"][:self.D + _capi.N_SCALARS])
         D = self.D
         hbuf = self._ws["k1buf"][:D + _capi.N_SCALARS + ((D + 31) // 32 + 1) // 2].cpu().numpy()
         hist = hbuf[:D]

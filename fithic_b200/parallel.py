@@ -112,6 +112,7 @@ class CudaOps:
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
         check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, float(p_cut), dptr(cursors), dptr(send),
                                                 dptr(idx), dptr(q), self._stream()))
+        self.last_cursors = cursors  # after the call: one past the last slot used by each part
         return send, idx
 
     def _bh_ws(self, n):
@@ -136,9 +137,22 @@ class CudaOps:
     def scatter(self, src, idx, dst):
         check(self.lib.fhc_scatter_f64(dptr(src), dptr(idx), src.numel(), dptr(dst), self._stream()))
 
+    def bh_qvalues(self, p, T):
+        """q-values of one array on this GPU (the whole of K4)."""
+        n = p.numel()
+        q = self.empty(n, torch.float64)
+        ws, wsb = self._bh_ws(n)
+        check(self.lib.fhc_bh_qvalues(dptr(p), n, float(T), 0, 0.0, dptr(q), None, None, dptr(ws), wsb, self._stream()))
+        return q
+
+    def cut_bucket(self, p_cut):
+        return int(self.lib.fhc_host_bh_cut_bucket(float(p_cut)))
+
 
 class DistCtx:
     """Collective choreography of one rank.  `ops` defaults to the CUDA library."""
+
+    SMALL_SET = 1 << 22  # at most this many p-values below the cut: every GPU ranks the gathered set itself
 
     def __init__(self, device=None, ops=None, group=None, samples_per_rank=1 << 16):
         self.group = group
@@ -149,27 +163,27 @@ class DistCtx:
         self.samples_per_rank = samples_per_rank
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
-    def allreduce_hist(self, hist, present, scal):
-        """Sum the per-distance histogram, the 'distance seen' bits and the totals over ranks (in place).
-        One all-reduce(sum) of [hist | totals | seen flags] and one all-reduce(max) for the largest count."""
+    def allreduce_hist(self, hist, present, scal, fused=None):
+        """Sum the per-distance histogram and the totals over ranks, OR the 'distance seen' bitmaps, take the largest
+        count (all in place).  One all-reduce(sum) and one all-gather of the small bitmap; `fused` is the caller's single
+        buffer holding [hist | totals] back to back (engine.hist_distance), which saves a concatenation."""
         D = hist.numel()
-        slots = torch.arange(D, device=hist.device)
-        flags = (present.to(torch.int64)[slots >> 5] >> (slots & 31)) & 1
-        mx = scal[_capi.S_MAX_COUNT:_capi.S_MAX_COUNT + 1].clone()
-        buf = torch.cat([hist, scal, flags])
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-        hist.copy_(buf[:D])
-        scal.copy_(buf[D:D + scal.numel()])
-        scal[_capi.S_MAX_COUNT] = mx[0]
-        seen = buf[D + scal.numel():] > 0
-        # re-pack the seen flags into the uint32 bitmap layout of fhc_hist_distance
-        pad = (-D) % 32
-        bits = torch.cat([seen, torch.zeros(pad, dtype=torch.bool, device=seen.device)]).view(-1, 32).to(torch.int64)
-        weights = (1 << torch.arange(32, device=seen.device, dtype=torch.int64))
-        words = (bits * weights).sum(dim=1)
-        words = torch.where(words >= (1 << 31), words - (1 << 32), words).to(torch.int32)
-        present.copy_(words)
+        if fused is None:
+            fused = torch.cat([hist, scal])
+            own = False
+        else:
+            own = True
+        small = torch.cat([present, scal[_capi.S_MAX_COUNT:_capi.S_MAX_COUNT + 1].to(torch.int32)])
+        dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
+        g = self._all_gather(small).view(self.world, -1)
+        if not own:
+            hist.copy_(fused[:D])
+            scal.copy_(fused[D:D + scal.numel()])
+        ored = g[0, :-1]
+        for w in range(1, self.world):
+            ored = torch.bitwise_or(ored, g[w, :-1])
+        present.copy_(ored)
+        scal[_capi.S_MAX_COUNT] = g[:, -1].max().to(scal.dtype)
 
     def max_int(self, v):
         t = torch.tensor([int(v)], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
@@ -201,7 +215,31 @@ class DistCtx:
         #    on sparse maps this leaves only the few candidates for significance to exchange and sort
         hist = ops.cut_hist(p, p_cut0)
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-        p_cut = ops.cut_find(hist.cpu().numpy(), T, p_cut0)
+        hh = hist.cpu().numpy()
+        p_cut = ops.cut_find(hh, T, p_cut0)
+        # 0b. few survivors (the usual case on a sparse map): no range partition -- every rank compacts its survivors,
+        #     the survivors are all-gathered (padded to the largest share), every rank ranks the small global set itself
+        #     and keeps the q-values of its own lines.  Three collectives in all.
+        n_below = int(hh[:ops.cut_bucket(p_cut)].sum()) if p_cut < p_cut0 else int(hh.sum())
+        if n_below <= self.SMALL_SET:
+            send, idx = ops.partition_scatter(p, np.zeros(0, dtype=np.uint64), np.zeros(1, dtype=np.int64), q, p_cut)
+            counts = self._all_gather(ops.last_cursors[:1].to(torch.int64)).cpu().numpy()
+            mine = int(counts[r])
+            tot, mx = int(counts.sum()), int(counts.max())
+            if tot:
+                pad = ops.empty(mx, torch.float64)
+                pad[:mine] = send[:mine]
+                if mine < mx:
+                    pad[mine:] = 1.0
+                allp = self._all_gather(pad).view(G, mx)
+                glob = torch.cat([allp[g, :int(counts[g])] for g in range(G)]) if G > 1 else allp[0, :mine]
+                qg = ops.bh_qvalues(glob.contiguous(), T)
+                off = int(counts[:r].sum())
+                if mine:
+                    ops.scatter(qg[off:off + mine].contiguous(), idx[:mine], q)
+            self.last_plan = dict(splitters=np.zeros(0, dtype=np.uint64), count_matrix=counts.reshape(G, 1), rank_offset=0,
+                                  floor=0.0, p_cut=p_cut, p_cut0=p_cut0, small_set=True)
+            return q
         # 1. splitters from a sorted sample of everybody's keys
         sample = ops.sample_keys(p, self.samples_per_rank, p_cut)
         allsamp = ops.sort_keys(self._all_gather(sample))
@@ -225,5 +263,5 @@ class DistCtx:
         dist.all_to_all_single(q_back, q_recv, send_splits, recv_splits, group=self.group)
         ops.scatter(q_back, idx[:n_send], q)
         self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor, p_cut=p_cut,
-                              p_cut0=p_cut0)
+                              p_cut0=p_cut0, small_set=False)
         return q

@@ -118,11 +118,13 @@ def lpt_shards(weights, nshards):
     return [sorted(o) for o in out]
 
 
-def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, only=None, chunk=1 << 26):
+def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, only=None, chunk=1 << 26, order="file"):
     """torch generator on the GPU for bench-sized inputs (300 M pairs in seconds).  Same law as make_intra; every
     chromosome has its own seeded stream, so a rank that generates only the chromosomes in `only` (indices) gets exactly
-    the lines the single-GPU run has for them.  Returns ((mid1, mid2, cnt, chrs) int32 device tensors, Fragments,
-    Biases, per-chromosome pair counts of the WHOLE data set)."""
+    the lines the single-GPU run has for them.  order = "file": the lines of a chromosome are sorted by (mid1, mid2), the
+    order fixed-size-bin contact files come in (e.g. the reference's fithic/tests/data/contactCounts/*_w40000_chr1.gz:
+    all partners of one locus on consecutive lines); "random": the order the pairs were drawn in.  Returns ((mid1, mid2,
+    cnt, chrs) int32 device tensors, Fragments, Biases, per-chromosome pair counts of the WHOLE data set)."""
     import torch
     names, sizes = genome(None)
     nb = n_bins(sizes, res)
@@ -151,6 +153,7 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
         g = torch.Generator(device=device)
         g.manual_seed(seed * 1000 + ci)
         done = 0
+        first = pos
         while done < n:
             m = min(chunk, n - done)
             u = torch.rand(m, generator=g, device=device, dtype=torch.float64)
@@ -172,6 +175,13 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
             chrs[s] = ci | (ci << 16)
             pos += m
             done += m
+        if order == "file" and pos > first:
+            key = mid1[first:pos].long() * (nbc * res + res) + mid2[first:pos].long()
+            perm = torch.argsort(key)
+            del key
+            for t in (mid1, mid2, cnt):
+                t[first:pos] = t[first:pos][perm]
+            del perm
     return (mid1, mid2, cnt, chrs), frags, biases, per
 
 

@@ -92,6 +92,10 @@ int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxmid, int32_t
                         int64_t U, const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs,
                         double *bin_sumdist, int64_t *totals);
 
+/* dst[i] = v for i < n with nthreads host threads (the end-to-end call fills its pinned q array with 1.0 while the GPU
+ * works, see fhc_gather_ne_one). */
+int fhc_host_fill_f64(double *dst, int64_t n, double v, int32_t nthreads);
+
 /* ---- K2: spline table ------------------------------------------------------------------------------------------
  * Replaces ius(splineX) + IsotonicRegression(increasing=False) of fit_Spline (fithic/fithic.py:952-966) and bakes
  * the clamp + bisect lookup of :1066-1068 into a dense table:

@@ -11,20 +11,21 @@ from fithic_b200 import _capi, synth  # noqa: E402
 from fithic_b200.engine import Engine, Settings  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000_000
+order = sys.argv[2] if len(sys.argv) > 2 else "file"
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-(m1, m2, c, ch), frags, biases, per = synth.make_intra_device(pairs, 5000, 1004, dev, mean_count=3.0, with_bias=True)
+(m1, m2, c, ch), frags, biases, per = synth.make_intra_device(pairs, 5000, 1004, dev, mean_count=3.0, with_bias=True, order=order)
 st = Settings(resolution=5000, noOfBins=100)
 eng = Engine(st, frags, biases, device=dev)
 eng.set_contacts_device(m1, m2, c, ch)
 VARIANTS = [
-    ("lists: g2 front, finish occ 3 (default)", {}),
+    ("lists: g2 front (default)", {}),
     ("lists: g4 front", {"FHC_PVAL_FRONT": "g4"}),
-    ("lists: finish occ 4", {"FHC_PVAL_FINISH_OCC": "4"}),
     ("tile", {"FHC_PVAL_IMPL": "tile"}),
     ("lists, rank-bound cut only", {"FHC_BH_TIGHTEN": "0"}),
 ]
 KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN")
+print("line order:", order)
 ref = None
 for name, env in VARIANTS:
     for k in KEYS:

@@ -81,7 +81,15 @@ class NumpyOps:
         idx = np.zeros(len(p), dtype=np.int32)
         send[:len(ok)] = p[ok][order]
         idx[:len(ok)] = ok[order]
+        ends = np.asarray(send_offsets, dtype=np.int64) + np.bincount(part, minlength=len(splitters) + 1)
+        self.last_cursors = torch.from_numpy(ends.astype(np.int64))
         return torch.from_numpy(send), torch.from_numpy(idx)
+
+    def bh_qvalues(self, p, T):
+        return torch.from_numpy(O.benjamini_hochberg(p.numpy(), T))
+
+    def cut_bucket(self, p_cut):
+        return int(_capi.load().fhc_host_bh_cut_bucket(float(p_cut)))
 
     def bh_prepare(self, p, T, rank_offset, q):
         self._p, self._T = p.numpy().copy(), T
@@ -113,9 +121,17 @@ def _worker(rank, world, port, tmp):
         cut = 41_000  # uneven shards
         mine = p_all[:cut] if rank == 0 else p_all[cut:]
         q = torch.full((len(mine),), -1.0, dtype=torch.float64)
-        ctx.global_bh(None, torch.from_numpy(mine.copy()), float(T), q=q)
         want = O.benjamini_hochberg(p_all, T)
         want = want[:cut] if rank == 0 else want[cut:]
+        # few survivors: every rank ranks the gathered set itself
+        ctx.global_bh(None, torch.from_numpy(mine.copy()), float(T), q=q)
+        assert ctx.last_plan["small_set"]
+        assert np.array_equal(q.numpy(), want, equal_nan=True), "global BH (small set) differs on rank %d" % rank
+        # many survivors: range partition over the ranks
+        ctx.SMALL_SET = 100
+        q = torch.full((len(mine),), -1.0, dtype=torch.float64)
+        ctx.global_bh(None, torch.from_numpy(mine.copy()), float(T), q=q)
+        assert not ctx.last_plan["small_set"]
         assert np.array_equal(q.numpy(), want, equal_nan=True), "global BH differs on rank %d" % rank
         cm = ctx.last_plan["count_matrix"]
         with np.errstate(invalid="ignore"):
