@@ -6,6 +6,7 @@
 This is the call a user (or the `fithic` CLI) makes; bench.py times it end to end ("e2e"): every call copies the
 contact arrays host -> device and the three result arrays device -> host.
 """
+import os
 import threading
 
 import numpy as np
@@ -16,6 +17,16 @@ from . import _capi
 from .engine import Biases, Contacts, Engine, Fragments, Settings  # noqa: F401  (re-exported)
 
 
+def _fill_threads():
+    """Host threads for the q fill: the cores this rank can call its own (all of them on one GPU, a share under torchrun)."""
+    env = os.environ.get("FHC_FILL_THREADS")
+    if env:
+        return max(1, int(env))
+    cores = os.cpu_count() or 4
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(2, min(16, cores // max(local, 1)))
+
+
 class HostBuffers:
     """Reusable pinned host buffers for the results of one run (3 x 8 B per contact)."""
 
@@ -24,6 +35,12 @@ class HostBuffers:
         self.p = torch.empty(n, dtype=torch.float64).pin_memory()
         self.q = torch.empty(n, dtype=torch.float64).pin_memory()
         self.expcc = torch.empty(n, dtype=torch.float64).pin_memory()
+        # what significance() knows about q from its previous call with these buffers: None = nothing (fill it), else the
+        # lines that differ from 1.0 (only those have to be reset).  A caller that writes into q calls invalidate().
+        self.q_not_one = None
+
+    def invalidate(self):
+        self.q_not_one = None
 
 
 def significance(contacts, fragments, settings, biases=None, engine=None, out=None):
@@ -58,7 +75,10 @@ def significance(contacts, fragments, settings, biases=None, engine=None, out=No
 
         # q is 1.0 on almost every line of a sparse map: a host thread fills the pinned array with 1.0 while the GPU works
         # and only the (line, q) pairs that differ cross the PCIe link (dense copy when they are more than n / 128)
-        filler = threading.Thread(target=eng.lib.fhc_host_fill_f64, args=(_capi.dptr(out.q), n, 1.0, 4))
+        if out.q_not_one is None:
+            filler = threading.Thread(target=eng.lib.fhc_host_fill_f64, args=(_capi.dptr(out.q), n, 1.0, _fill_threads()))
+        else:  # the buffers come from an earlier call: everything is 1.0 already except the lines recorded then
+            filler = threading.Thread(target=out.q.numpy().__setitem__, args=(out.q_not_one, 1.0))
         filler.start()
         r = eng.run_pass(passNo, outl, stats, pvalue_chunks=8 if n >= (1 << 22) else 1, after_chunk=copy_slice)
         cap = max(n // 128, 1024)
@@ -70,10 +90,13 @@ def significance(contacts, fragments, settings, biases=None, engine=None, out=No
         n_ex = int(ex_cnt.item())
         filler.join()
         if n_ex <= cap:
+            lines = ex_idx[:n_ex].cpu().numpy().view(np.uint32).astype(np.int64)
             if n_ex:
-                out.q.numpy()[ex_idx[:n_ex].cpu().numpy().view(np.uint32)] = ex_val[:n_ex].cpu().numpy()
+                out.q.numpy()[lines] = ex_val[:n_ex].cpu().numpy()
+            out.q_not_one = lines
         else:
             out.q.copy_(r["q"], non_blocking=True)
+            out.q_not_one = None
         r["q_exceptions"] = n_ex
         main.synchronize()
         copy.synchronize()

@@ -5,6 +5,7 @@
 // so they are plain C++ mirroring the reference's evaluation order:
 //   fhc_host_make_bins   <- makeBinsFromInteractions   (reference fithic/fithic.py:463-553)
 //   fhc_host_frag_pairs  <- generate_FragPairs, fixed-size branch (fithic/fithic.py:596-689)
+#include <emmintrin.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -182,22 +183,32 @@ extern "C" int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxm
     return FHC_OK;
 }
 
-// dst[i] = v with `nthreads` threads (host).  The end-to-end call fills its pinned q array with 1.0 while the GPU works;
-// torch's own fill runs on one thread under torchrun (OMP_NUM_THREADS=1), 0.1 s per GB.
+// dst[i] = v with `nthreads` threads and streaming (non-temporal) stores (host).  The end-to-end call fills its pinned q
+// array with 1.0 while the GPU works; torch's own fill runs on one thread under torchrun (OMP_NUM_THREADS=1), 0.1 s per GB.
 extern "C" int fhc_host_fill_f64(double *dst, int64_t n, double v, int32_t nthreads) {
     FHC_REQUIRE(n >= 0 && (n == 0 || dst != nullptr), FHC_E_INVALID, "fhc_host_fill_f64: null array or n < 0");
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     if (n < (1 << 20)) nthreads = 1;
     auto fill = [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) dst[i] = v;
+        int64_t i = lo;
+        while (i < hi && (reinterpret_cast<uintptr_t>(dst + i) & 15u)) dst[i++] = v;
+        const __m128d vv = _mm_set1_pd(v);
+        for (; i + 8 <= hi; i += 8) {
+            _mm_stream_pd(dst + i, vv);
+            _mm_stream_pd(dst + i + 2, vv);
+            _mm_stream_pd(dst + i + 4, vv);
+            _mm_stream_pd(dst + i + 6, vv);
+        }
+        for (; i < hi; ++i) dst[i] = v;
+        _mm_sfence();
     };
     if (nthreads == 1) {
         fill(0, n);
         return FHC_OK;
     }
     std::vector<std::thread> pool;
-    const int64_t per = (n + nthreads - 1) / nthreads;
+    const int64_t per = ((n + nthreads - 1) / nthreads + 7) & ~(int64_t)7;
     for (int t = 1; t < nthreads; ++t) pool.emplace_back(fill, per * t < n ? per * t : n, per * (t + 1) < n ? per * (t + 1) : n);
     fill(0, per < n ? per : n);
     for (auto &th : pool) th.join();

@@ -29,6 +29,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=
 short = re.sub(r"\(.*", "", name).replace("void ", "").replace("fhc::", "")
 short = re.sub(r"<.*", "", short)
 lines, cur, inside = [], "?", False
+paths = {}
 targs = re.search(r"<([^>]*)>", name.split("(fhc::")[0] if "(fhc::" in name else name)
 mangled_args = ""
 if targs:  # (bool)1, (int)4 -> ILb1ELi4EE
@@ -46,6 +47,7 @@ for ln in dis.splitlines():
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = "%s:%s" % (os.path.basename(m.group(1)), m.group(2))
+        paths[os.path.basename(m.group(1))] = m.group(1)
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", ln):
         lines.append(cur)
@@ -66,7 +68,7 @@ print("%7s %7s %6s  %s" % ("exec %", "samp %", "lanes", "source line"))
 src_cache = {}
 for l, (ex, s, th) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     f, n = l.rsplit(":", 1) if ":" in l else (l, "0")
-    path = os.path.join(os.path.dirname(obj), "..", "csrc", f)
+    path = paths.get(f, os.path.join(os.path.dirname(obj), "..", "csrc", f))
     if f not in src_cache:
         src_cache[f] = open(path).read().splitlines() if os.path.exists(path) else []
     text = src_cache[f][int(n) - 1].strip()[:90] if 0 < int(n) <= len(src_cache[f]) else ""

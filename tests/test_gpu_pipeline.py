@@ -113,3 +113,21 @@ def test_api_q_dense_and_sparse_paths(lib):
     assert 0 < n_ex <= 1024 and got[-1]["q_exceptions"] == n_ex
     for k in ("p", "q", "expcc"):
         assert np.array_equal(got[-1][k], want[-1][k], equal_nan=True), k
+
+
+def test_api_reused_host_buffers(lib):
+    """HostBuffers remember which lines of q differed from 1.0; a second call with other data must reset exactly those."""
+    from fithic_b200 import api
+    n, res = 900, 40000
+    out = api.HostBuffers(n)
+    for seed in (1, 2, 3):
+        contacts, frags, biases, _ = synth.make_intra(n, res, seed=seed, chroms=["chr1"], mean_count=6.0, with_bias=True)
+        st = Settings(resolution=res, noOfBins=20)
+        want = run_engine(contacts, frags, biases, st)
+        got = api.significance(contacts, frags, st, biases, out=out)
+        for k in ("p", "q", "expcc"):
+            assert np.array_equal(got[-1][k], want[-1][k], equal_nan=True), (seed, k)
+    out.q.fill_(0.5)  # the caller scribbles over q ...
+    out.invalidate()  # ... and says so
+    got = api.significance(contacts, frags, st, biases, out=out)
+    assert np.array_equal(got[-1]["q"], want[-1]["q"], equal_nan=True)
