@@ -60,6 +60,8 @@ _SIGNATURES = {
     "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
+    "fhc_bh_qvalues_hostcount": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_bh_prepare": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "fhc_bh_p_cut": (c_double, [c_double, c_double]),

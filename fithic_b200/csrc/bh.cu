@@ -609,9 +609,15 @@ static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
 // sorts n_max-capacity buffers holding *d_n valid pairs; result ends in (keys_b, vals_b) after 8 passes -> we run an
 // even number of passes so the result is back in (keys_a, vals_a)
 static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_b, int64_t n_max, const u64 *d_n,
-                               const SortWs &ws, cudaStream_t st) {
+                               const SortWs &ws_full, cudaStream_t st, long long known_n = -1) {
     u64 *kin = keys_a, *kout = keys_b;
     u32 *vin = vals_a, *vout = vals_b;
+    SortWs ws = ws_full;
+    if (known_n >= 0) {  // the caller read the key count back: size the grids for it instead of for the capacity
+        const u32 t = (u32)((known_n + kSortTile - 1) / kSortTile);
+        ws.ntiles = t ? t : 1;
+        ws.nb = (int)(((size_t)kRadix * ws.ntiles + kScanTile - 1) / kScanTile);
+    }
     FHC_CUDA(cudaFuncSetAttribute(radix_downsweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kDownsweepSmem));
     for (int pass = 0; pass < 8; ++pass) {
@@ -724,11 +730,15 @@ static int cut_hist_launch(const double *p, int64_t n, double p_cut0, fhc::u64 *
 
 // tighten: derive the cut from the value histogram (single-GPU path); otherwise p_cut is used as given (the multi-GPU
 // path tightens globally before the exchange, fhc_bh_cut_hist + fhc_host_bh_cut_find)
+// host_ns (nullable): synchronise the stream once after the compaction, read the number of ranked keys into *host_ns and
+// launch only what that number needs (nothing when no key is ranked: 40 near-empty launches cost 0.35 ms).
 static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double p_cut, bool tighten,
-                      double *q, double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st) {
+                      double *q, double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st,
+                      long long *host_ns = nullptr) {
     using namespace fhc;
     FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 4 * sizeof(u64), st));
-    const int ntiles = (int)ws.sort.ntiles;
+    int ntiles = (int)ws.sort.ntiles;
+    if (host_ns) *host_ns = -1;
     if (n > 0) {
         const char *tenv = getenv("FHC_BH_TIGHTEN");  // =0: rank-bound cut only (experiments, worst-case timing)
         if (tenv && tenv[0] == '0') tighten = false;
@@ -744,10 +754,21 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
         bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, d_p_cut, q, ws.keys_a, ws.vals_a, ws.d_n);
         FHC_LAUNCH_CHECK("bh_compact_kernel");
-        const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st);
-        if (rc != FHC_OK) return rc;
-        bh_tilemax_kernel<<<sort_grid((u32)ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
-        FHC_LAUNCH_CHECK("bh_tilemax_kernel");
+        long long known = -1;
+        if (host_ns) {
+            u64 h = 0;
+            FHC_CUDA(cudaMemcpyAsync(&h, ws.d_n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+            FHC_CUDA(cudaStreamSynchronize(st));
+            known = (long long)h;
+            *host_ns = known;
+            ntiles = (int)((known + kSortTile - 1) / kSortTile);
+        }
+        if (known != 0) {
+            const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st, known);
+            if (rc != FHC_OK) return rc;
+            bh_tilemax_kernel<<<sort_grid((u32)ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
+            FHC_LAUNCH_CHECK("bh_tilemax_kernel");
+        }
     }
     bh_tilescan_kernel<<<1, kScanThreads, 0, st>>>(ws.tilemax, n > 0 ? ntiles : 0, carry_in, carry_out, ws.d_n,
                                                    reinterpret_cast<u64 *>(n_sorted_out));
@@ -756,10 +777,11 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
 }
 
 static int bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, double *q, const fhc::BhWs &ws,
-                     cudaStream_t st) {
+                     cudaStream_t st, long long known_n = -1) {
     using namespace fhc;
-    if (n > 0) {
-        bh_scatter_kernel<<<sort_grid(ws.sort.ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
+    if (n > 0 && known_n != 0) {
+        const u32 tiles = known_n > 0 ? (u32)((known_n + kSortTile - 1) / kSortTile) : ws.sort.ntiles;
+        bh_scatter_kernel<<<sort_grid(tiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
                                                                         ws.tilemax, floor_in, q);
         FHC_LAUNCH_CHECK("bh_scatter_kernel");
     }
@@ -789,6 +811,24 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
                     n_sorted_out, ws, st);
     if (rc != FHC_OK) return rc;
     return bh_finish(n, T, rank_offset, 0.0, q, ws, st);  // carry_in is already folded into the tile prefixes
+}
+
+extern "C" int fhc_bh_qvalues_hostcount(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                                        double *carry_out, int64_t *n_sorted_out, int64_t *n_ranked_host, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    int rc = bh_check_args("fhc_bh_qvalues_hostcount", p, n, q, workspace, workspace_bytes);
+    if (rc != FHC_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    BhWs ws;
+    bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
+    long long ns = -1;
+    rc = bh_prepare(p, n, T, rank_offset, carry_in, bh_p_cut(T, (double)rank_offset + (double)n), true, q, carry_out,
+                    n_sorted_out, ws, st, &ns);
+    if (rc != FHC_OK) return rc;
+    if (n_ranked_host) *n_ranked_host = ns < 0 ? 0 : ns;
+    return bh_finish(n, T, rank_offset, 0.0, q, ws, st, ns);
 }
 
 extern "C" int fhc_bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double p_cut, double *q,

@@ -361,8 +361,12 @@ class Engine:
             q = self._tensor("q", n, torch.float64)
         wsb = int(self.lib.fhc_bh_workspace_bytes(n))
         ws = self._buf("bh_ws", wsb)
-        check(self.lib.fhc_bh_qvalues(dptr(p), n, float(T), int(rank_offset), float(carry_in), dptr(q), dptr(carry_out),
-                                      dptr(n_sorted_out), dptr(ws), wsb, self._stream()))
+        # one host sync after the compaction: only the radix passes the number of ranked keys needs are launched
+        ranked = ctypes.c_int64(0)
+        check(self.lib.fhc_bh_qvalues_hostcount(dptr(p), n, float(T), int(rank_offset), float(carry_in), dptr(q),
+                                                dptr(carry_out), dptr(n_sorted_out), ctypes.byref(ranked), dptr(ws), wsb,
+                                                self._stream()))
+        self.last_ranked = int(ranked.value)
         return q
 
     # K5  (makeBinsFromInteractions outlier decrements, fithic/fithic.py:528-548)

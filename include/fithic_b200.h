@@ -135,7 +135,8 @@ double fhc_host_one_minus_exp(double y);
 
 /* ---- K3: per-contact p-value ---------------------------------------------------------------------------------
  * Replaces the per-line loop of fit_Spline (fithic/fithic.py:1017-1123) including scipy.special.bdtrc (:1070,:1101).
- *   bias       nullable dense per-locus bias (-1 = discarded by read_biases, :818-832) with bias_mid the mid point
+ *   bias       nullable dense per-locus bias (-1 = discarded by read_biases, :818-832; never NaN -- read_biases turns
+ *              NaN into -1 as well) with bias_mid the mid point
  *              each slot was read for and chr_off[nchr+1] the first slot of each chromosome id; the slot of
  *              (chr, mid) is chr_off[chr] + mid / res; a slot outside the chromosome or with another mid is "missing"
  *              (-1, :1026-1054)
@@ -178,6 +179,14 @@ int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *prior, int64_
 size_t fhc_bh_workspace_bytes(int64_t n);
 int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
                    double *carry_out, int64_t *n_sorted_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* fhc_bh_qvalues with ONE host synchronisation of `stream` in the middle: the number of ranked keys is read back after the
+ * compaction (*n_ranked_host [host, nullable]) and only the passes that number needs are launched -- none at all when no
+ * p-value is below the cut, the usual case on a sparse map, where the 40 launches of 8 radix passes over nothing cost
+ * 0.35 ms.  Same results; for callers that are not capturing a CUDA graph. */
+int fhc_bh_qvalues_hostcount(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
+                             double *carry_out, int64_t *n_sorted_out, int64_t *n_ranked_host, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* The same in two halves, for a caller that has to fetch the running max of smaller keys from other GPUs in between:
  * prepare = compaction + sort + per-tile maxima (local_max_out [dev] = max bh value of this call, 0 if none);
