@@ -128,7 +128,7 @@ __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const Fr
     prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
     const double dN = intra_path ? F.dN_intra : F.dN_inter;
     const unsigned int N = (unsigned int)(intra_path ? P.N_intra : P.N_inter);  // 0 <= N < 2^31
-    const bool b_ok = fmin(b1, b2) >= P.tL && fmax(b1, b2) <= P.tU;  // both biases inside [tL, tU] (never NaN: -1 or a value)
+    const bool b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
     e = (scored && b_ok) ? __dmul_rn(dN, prior) : 0.0;
     // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
     // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first.  For c >= 1,
@@ -187,13 +187,6 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
         const long long base = tile * kFrontTile;
         const bool full = base + kFrontTile <= P.n;
         unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
-        unsigned int valid = 0xffu;  // which of this thread's 8 contacts exist (all of them except in the last tile)
-        if (!full) {
-            valid = 0;
-#pragma unroll
-            for (int s8 = 0; s8 < 8; ++s8)
-                if (base + ((s8 / kG) * kFrontThreads + tid) * kG + (s8 % kG) < P.n) valid |= 1u << s8;
-        }
 #pragma unroll
         for (int h = 0; h < 8 / kG; ++h) {
             const int l0 = (h * kFrontThreads + tid) * kG;
@@ -241,7 +234,7 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
                 const int li = l0 + k;
                 double prior;
                 bool use_inter;
-                const bool in_file = (valid >> (h * kG + k)) & 1u;
+                const bool in_file = full || base + li < P.n;
                 const PvalClass cls = front_prepare(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k],
                                                     prior, use_inter);
                 if (cls == kClsK0) {

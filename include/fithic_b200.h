@@ -135,8 +135,7 @@ double fhc_host_one_minus_exp(double y);
 
 /* ---- K3: per-contact p-value ---------------------------------------------------------------------------------
  * Replaces the per-line loop of fit_Spline (fithic/fithic.py:1017-1123) including scipy.special.bdtrc (:1070,:1101).
- *   bias       nullable dense per-locus bias (-1 = discarded by read_biases, :818-832; never NaN -- read_biases turns
- *              NaN into -1 as well) with bias_mid the mid point
+ *   bias       nullable dense per-locus bias (-1 = discarded by read_biases, :818-832) with bias_mid the mid point
  *              each slot was read for and chr_off[nchr+1] the first slot of each chromosome id; the slot of
  *              (chr, mid) is chr_off[chr] + mid / res; a slot outside the chromosome or with another mid is "missing"
  *              (-1, :1026-1054)
