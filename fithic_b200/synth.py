@@ -185,6 +185,42 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
     return (mid1, mid2, cnt, chrs), frags, biases, per
 
 
+def make_inter_device(n_pairs, res, seed, device, intra_fraction=0.1, chunk=1 << 26):
+    """BASELINE config 5 on the GPU: whole-genome interOnly input -- chromosome pairs drawn with probability proportional to
+    the product of their lengths, loci uniform, count = 1 + Poisson(0.3), no bias; `intra_fraction` of the lines are intra
+    pairs (under -x interOnly the reference scores those against the inter prior as well, fithic/fithic.py:1098-1108).
+    Returns ((mid1, mid2, cnt, chrs) int32 device tensors, Fragments)."""
+    import torch
+    names, sizes = genome(None)
+    nb = n_bins(sizes, res)
+    frags = fragments_for(names, sizes, res)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    w = torch.from_numpy(sizes / sizes.sum()).to(device)
+    nbt = torch.from_numpy(nb).to(device)
+    mid1 = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    mid2 = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    cnt = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    chrs = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    done = 0
+    while done < n_pairs:
+        m = min(chunk, n_pairs - done)
+        c1 = torch.multinomial(w, m, replacement=True, generator=g)
+        c2 = torch.multinomial(w, m, replacement=True, generator=g)
+        same = torch.rand(m, generator=g, device=device) < intra_fraction
+        c2 = torch.where(same, c1, torch.where(c2 == c1, (c1 + 1) % len(names), c2))
+        i = torch.floor(torch.rand(m, generator=g, device=device, dtype=torch.float64) * nbt[c1]).long()
+        j = torch.floor(torch.rand(m, generator=g, device=device, dtype=torch.float64) * nbt[c2]).long()
+        c = 1 + torch.poisson(torch.full((m,), 0.3, device=device), generator=g).long()
+        s = slice(done, done + m)
+        mid1[s] = (i * res + res // 2).int()
+        mid2[s] = (j * res + res // 2).int()
+        cnt[s] = c.int()
+        chrs[s] = (c1 | (c2 << 16)).int()
+        done += m
+    return (mid1, mid2, cnt, chrs), frags
+
+
 def write_inputs(outdir, contacts, frags, res, raw_bias=None, biases=None, prefix="synth"):
     """Write gz TSV files in the reference's input formats (for CLI-level tests and the CPU baseline)."""
     import gzip

@@ -18,7 +18,9 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n_pairs,res,passes", [(20_000_000, 10000, 2), (30_000_000, 5000, 1)])
+# the last two are BASELINE.json's configs 3 and 4 at their full sizes (80 M pairs, 10 kb, 2 passes; 300 M pairs, 5 kb + bias)
+@pytest.mark.parametrize("n_pairs,res,passes", [(20_000_000, 10000, 2), (30_000_000, 5000, 1), (80_000_000, 10000, 2),
+                                                (300_000_000, 5000, 1)])
 def test_full_size_invariants(lib, n_pairs, res, passes):
     dev = torch.device("cuda", 0)
     (mid1, mid2, cnt, chrs), frags, biases, per = synth.make_intra_device(n_pairs, res, 4242, dev, mean_count=3.0,
@@ -94,3 +96,38 @@ def test_full_size_invariants(lib, n_pairs, res, passes):
     assert np.all(got[~g] == 1.0)
     rel = np.abs(got[g] - want[g]) / np.maximum(np.abs(want[g]), 1e-290)
     assert rel.max() <= 1e-6, rel.max()
+
+
+def test_inter_only_full_size(lib):
+    """BASELINE.json config 5 at full size: 100 M lines, 25 kb, -x interOnly (constant prior, global BH).  Without a bias
+    file p depends on the count alone -- every count is checked against the oracle's bdtrc -- and q obeys the same order
+    properties as above."""
+    dev = torch.device("cuda", 0)
+    n, res = 100_000_000, 25000
+    (mid1, mid2, cnt, chrs), frags = synth.make_inter_device(n, res, 1005, dev)
+    st = Settings(resolution=res, noOfBins=100, interOnly=True)
+    eng = Engine(st, frags, None, device=dev)
+    eng.set_contacts_device(mid1, mid2, cnt, chrs)
+    outl, stats = eng.new_outlier_state()
+    r = eng.run_pass(1, outl, stats)
+    torch.cuda.synchronize()
+    p, q, e = r["p"], r["q"], r["expcc"]
+    inter = (chrs & 0xffff) != ((chrs >> 16) & 0xffff)
+    n_inter = int(inter.sum().item())
+    s_inter = int(cnt[inter].long().sum().item())
+    assert r["observedInterAllCount"] == n_inter and r["observedInterAllSum"] == s_inter and r["T"] == n_inter
+    prior = 1.0 / n_inter
+    counts = torch.unique(cnt).cpu().numpy()
+    want = O.bdtrc(counts.astype(np.float64) - 1.0, s_inter, np.full(len(counts), prior))
+    for c, w in zip(counts, want):
+        got = torch.unique(p[cnt == int(c)]).cpu().numpy()
+        assert len(got) == 1 and abs(got[0] - w) <= 1e-6 * abs(w), (c, got, w)  # intra lines take the same branch (:1098)
+    assert bool((e == s_inter * prior).all())
+    order = torch.argsort(p)
+    ps, qs = p[order], q[order]
+    assert bool((qs[1:] >= qs[:-1]).all())
+    rank = torch.arange(1, n + 1, device=dev, dtype=torch.float64)
+    assert bool((qs >= torch.clamp(ps * float(r["T"]) / rank, max=1.0) * (1 - 1e-15)).all())
+    # ties share one q: the running max over a tie run is the value of its first rank (fithic/myStats.py:35-43)
+    for c in counts[:6]:
+        assert torch.unique(q[cnt == int(c)]).numel() == 1
