@@ -7,7 +7,8 @@
 Workload (BASELINE.json `metric`, config[3]): synthetic whole-genome intraOnly, 5 kb bins, ICE-like bias vector,
 ~300 M contact pairs, 1 spline pass.  A "step" is the whole path over that input: K1 histogram -> host binning + spline
 fit -> K2 table -> K3 p-values -> K4 q-values.  `value` = contact pairs scored per second with the contacts resident in
-HBM; `e2e` = the same through fithic_b200.api.significance with pinned HOST arrays in and out (16 B/pair H2D; D2H: p and
+HBM; `e2e` = the same through fithic_b200.api.significance with pinned HOST arrays in and out (12 B/pair H2D: mid1, mid2,
+count; the chromosome ids travel run-length encoded, as the reader delivers them; D2H: p and
 ExpCC whole, q as the (line, value) pairs that differ from 1.0 -- all inside the timed region).  With N GPUs the same 300 M pairs are sharded by chromosome (strong scaling).
 """
 import argparse
@@ -332,8 +333,13 @@ def main():
     value = args.pairs * args.passes / (ms_per_step * 1e-3)
 
     # ---- e2e through the public API with pinned host buffers (H2D + D2H inside the timed region) ----
-    host = Contacts(*(t.cpu().pin_memory().numpy() for t in (mid1, mid2, cnt)),
-                    chrs.cpu().pin_memory().numpy().view(np.uint32), list(names))
+    from fithic_b200.engine import chr_runs_of
+    host_chrs = chrs.cpu().pin_memory().numpy().view(np.uint32)
+    # a contact file is grouped by chromosome: the reader hands the ids over in run-length form as well (io.read_contacts),
+    # and then the 4 B per line of `chrs` stay on the host
+    host = Contacts(*(t.cpu().pin_memory().numpy() for t in (mid1, mid2, cnt)), host_chrs, list(names),
+                    None if os.environ.get("FHC_BENCH_DENSE_CHRS") else chr_runs_of(host_chrs))
+    h2d_per_pair = 12 if (host.chr_runs is not None and len(host.chr_runs[0]) <= Engine.MAX_CHR_RUNS) else 16
     out = api.HostBuffers(n_local)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     api.significance(host, frags, st, biases, engine=eng, out=out)  # warm-up
@@ -420,7 +426,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 16 * args.pairs,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_per_pair * args.pairs,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "q_exceptions": n_ex,
                     "ms_per_step": e2e_ms / e2e_steps, "ms_each_host_clock": e2e_each, "allocator": alloc_diag},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb, "kernels": breakdown,

@@ -56,9 +56,23 @@ class Contacts:
     cnt: np.ndarray    # int32, int(float(text)) (fithic/fithic.py:415, myUtils.py:123-124)
     chrs: np.ndarray   # uint32, chr1 | chr2 << 16 (ids into `chroms`)
     chroms: list = field(default_factory=list)
+    # Optional run-length form of `chrs`: (values uint32 [r], lengths int64 [r]).  Contact files are grouped by
+    # chromosome, so this is a few dozen numbers; when it is present the 4 bytes per line of `chrs` never cross the PCIe
+    # link (Engine.upload_contacts expands the runs on the device).  io.read_contacts and chr_runs_of() produce it.
+    chr_runs: tuple = None
 
     def __len__(self):
         return int(self.mid1.shape[0])
+
+
+def chr_runs_of(chrs):
+    """Run-length encoding of a chrs array: (values uint32, lengths int64)."""
+    chrs = np.asarray(chrs)
+    if len(chrs) == 0:
+        return np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.int64)
+    cut = np.flatnonzero(chrs[1:] != chrs[:-1]) + 1
+    starts = np.concatenate([[0], cut])
+    return chrs[starts].astype(np.uint32), np.diff(np.concatenate([starts, [len(chrs)]])).astype(np.int64)
 
 
 @dataclass
@@ -146,7 +160,19 @@ class Engine:
         ts = []
         reuse = self.contacts if (self.contacts is not None and getattr(self, "_own_contacts", False)
                                   and self.n == len(c)) else None
-        for j, a in enumerate((c.mid1, c.mid2, c.cnt, c.chrs.view(np.int32))):
+        runs = c.chr_runs if (c.chr_runs is not None and len(c.chr_runs[0]) <= self.MAX_CHR_RUNS) else None
+        for j, a in enumerate((c.mid1, c.mid2, c.cnt, c.chrs.view(np.int32) if runs is None else None)):
+            if a is None:
+                # chromosome ids from their run-length form: nothing over the link instead of 4 B per line; one fill per run
+                # (torch.repeat_interleave parallelises over the runs, not over the output: 30 ms for 24 runs of 12 M)
+                assert int(np.sum(runs[1])) == len(c), "chr_runs do not cover the contacts"
+                d = reuse[j] if reuse is not None else torch.empty(len(c), dtype=torch.int32, device=self.device)
+                pos = 0
+                for v, ln in zip(np.asarray(runs[0]).view(np.int32).tolist(), np.asarray(runs[1]).tolist()):
+                    d[pos:pos + ln].fill_(v)
+                    pos += ln
+                ts.append(d)
+                continue
             h = torch.from_numpy(np.ascontiguousarray(a))
             if reuse is not None:  # same size as the previous upload: no new device allocation
                 reuse[j].copy_(h, non_blocking=non_blocking)
@@ -275,6 +301,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     # K2
+    MAX_CHR_RUNS = 256  # more chromosome runs than this: the dense chrs array is uploaded instead
+
     HOST_PAVA_MIN_POINTS = 4096  # above this the pooling runs on the host (see csrc/spline.cu)
 
     def spline_table(self, tck, splineX, xmin, xmax):

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pandas as pd
 
-from .engine import Biases, Contacts, Fragments
+from .engine import Biases, Contacts, Fragments, chr_runs_of
 
 _I32_MAX = (1 << 31) - 1
 
@@ -38,7 +38,7 @@ def read_contacts(path):
         _capi.check(lib.fhc_io_contacts_copy(h, _capi.dptr(m1), _capi.dptr(m2), _capi.dptr(cnt), _capi.dptr(chrs)))
     finally:
         lib.fhc_io_free(h)
-    return Contacts(m1, m2, cnt, chrs, chroms)
+    return Contacts(m1, m2, cnt, chrs, chroms, chr_runs_of(chrs))
 
 
 def read_contacts_pandas(path):

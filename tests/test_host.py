@@ -371,3 +371,16 @@ def test_list_pipeline_arithmetic_matches_oracle(lib, N):
     assert rel.max() <= 1e-6  # the contract; count == 1 is at 4e-16
     k0 = ok & (cnt == 1)
     assert np.max(np.abs(got[k0] - want[k0]) / np.abs(want[k0])) < 2e-15
+
+
+def test_chr_runs_round_trip():
+    from fithic_b200.engine import chr_runs_of
+    rng = np.random.default_rng(5)
+    vals = rng.integers(0, 1 << 20, 40).astype(np.uint32)
+    lens = rng.integers(1, 1000, 40)
+    chrs = np.repeat(vals, lens)
+    v, l = chr_runs_of(chrs)
+    assert np.array_equal(np.repeat(v, l), chrs) and int(l.sum()) == len(chrs)
+    assert np.all(v[1:] != v[:-1])
+    v, l = chr_runs_of(np.zeros(0, dtype=np.uint32))
+    assert len(v) == 0 and len(l) == 0
