@@ -79,6 +79,18 @@ _SIGNATURES = {
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                            c_void_p]),
+    "fhc_kr_partials": (c_int32, []),
+    "fhc_kr_spmv": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_kr_mul": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_kr_residual": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_kr_first": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_kr_direction": (ctypes.c_int, [c_void_p, c_double, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_kr_w": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_kr_ynew_minmax": (ctypes.c_int, [c_void_p, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_kr_gamma": (ctypes.c_int, [c_void_p, c_double, c_void_p, c_double, c_int32, c_int64, c_void_p, c_void_p]),
+    "fhc_kr_axpy": (ctypes.c_int, [c_void_p, c_double, c_double, c_void_p, c_int64, c_void_p]),
+    "fhc_kr_update": (ctypes.c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                      c_void_p]),
     "fhc_io_format_double": (ctypes.c_int, [c_double, ctypes.c_int, c_char_p]),
     "fhc_io_read_contacts": (c_void_p, [c_char_p]),
     "fhc_io_contacts_n": (c_int64, [c_void_p]),

@@ -252,6 +252,39 @@ int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out,
 int fhc_outlier_bin_decrements(const int32_t *mid1, const int32_t *mid2, const uint8_t *outl, int64_t n,
                                const int64_t *bin_ub, int32_t nbins, uint64_t *dec, void *stream);
 
+/* ---- KR bias computation ---------------------------------------------------------------------------
+ * The kernels behind fithic_b200/hickry.py, the replacement of the reference's bias generator fithic/utils/HiCKRy.py (the
+ * producer of the -t file).  The contact lines are the matrix: (rows[e], cols[e], vals[e]) in file order stand for
+ * coo(z, (x, y)) + its transpose (HiCKRy.py:46-50); remap[locus] is the locus' index after the sparsest rows were dropped
+ * (:76-96), or -1.  All arrays [dev]; every reduction writes fhc_kr_partials() partial results that the caller adds up.
+ *   fhc_kr_spmv         y = (M + M^T) x over the kept loci (y is zeroed by the callee)
+ *   fhc_kr_residual     v = x * Ax; rk = 1 - v; partial sums of rk^2                       (knightRuizAlg :155-157, :208-211)
+ *   fhc_kr_first        Z = rk / v; p = Z; partial sums of rk * Z                          (:178-182)
+ *   fhc_kr_direction    p = first ? p : Z + beta p; xp = x * p                            (:184-185, argument of :191)
+ *   fhc_kr_w            w = x * Axp + v * p; partial sums of p * w                         (:191-193)
+ *   fhc_kr_ynew_minmax  partial[0..P) = min(y + alpha p), partial[P..2P) = -max(y + alpha p)   (:196-197, :206)
+ *   fhc_kr_gamma        partial minima of (bound - y) / (alpha p) over alpha p < 0 (mode 0, :201-203) or over
+ *                       y + alpha p > bound (mode 1, :207-209)
+ *   fhc_kr_axpy         y += gamma (alpha p)                                               (:204, :210)
+ *   fhc_kr_update       y += alpha p; rk -= alpha w; Z = rk / v; partial sums of rk * Z     (:213-218)
+ *   fhc_kr_mul          out = a * b                                                        (x *= y, :219) */
+int32_t fhc_kr_partials(void);
+int fhc_kr_spmv(const int32_t *rows, const int32_t *cols, const double *vals, int64_t nnz, const int32_t *remap,
+                const double *x, double *y, int64_t n, void *stream);
+int fhc_kr_mul(const double *a, const double *b, double *out, int64_t n, void *stream);
+int fhc_kr_residual(const double *x, const double *Ax, double *v, double *rk, int64_t n, double *partial, void *stream);
+int fhc_kr_first(const double *rk, const double *v, double *Z, double *p, int64_t n, double *partial, void *stream);
+int fhc_kr_direction(const double *Z, double beta, int32_t first, double *p, const double *x, double *xp, int64_t n,
+                     void *stream);
+int fhc_kr_w(const double *x, const double *Axp, const double *v, const double *p, double *w, int64_t n, double *partial,
+             void *stream);
+int fhc_kr_ynew_minmax(const double *y, double alpha, const double *p, int64_t n, double *partial, void *stream);
+int fhc_kr_gamma(const double *y, double alpha, const double *p, double bound, int32_t mode, int64_t n, double *partial,
+                 void *stream);
+int fhc_kr_axpy(double *y, double gamma, double alpha, const double *p, int64_t n, void *stream);
+int fhc_kr_update(double *y, double alpha, const double *p, double *rk, const double *w, const double *v, double *Z, int64_t n,
+                  double *partial, void *stream);
+
 /* ---- text boundary (host) ---------------------------------------------------------------------------------------------
  * Native replacements of the two text loops that dominate the reference's wall time once the kernels are fast:
  * `for lines in gzip.open(contactCountsFile)` + split/int/float (fithic/fithic.py:406-417, :1017-1023) and the
