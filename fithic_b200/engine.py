@@ -83,6 +83,7 @@ class Fragments:
     chroms: list
     n_mappable: np.ndarray  # int64 per chromosome
     max_mid: np.ndarray     # int64 per chromosome
+    mids: list = None       # -r 0 only: per chromosome, the ascending mid points of its mappable fragments (int64 arrays)
 
 
 @dataclass

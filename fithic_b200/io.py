@@ -61,9 +61,10 @@ def read_contacts_pandas(path):
                     chroms)
 
 
-def read_fragments(path, chroms, mappThres):
+def read_fragments(path, chroms, mappThres, keep_mids=False):
     """fragments file: uses column 0 (chr), 2 (mid) and 3 (hit count >= mappThres means mappable; :583-590).
-    `chroms` (list) is extended in place by chromosomes that only occur here."""
+    `chroms` (list) is extended in place by chromosomes that only occur here.  keep_mids: also keep every chromosome's
+    sorted mappable mid points (restriction-fragment mode, -r 0, enumerates fragment pairs, :691-778)."""
     df = pd.read_csv(path, sep=r"\s+", header=None, engine="c", usecols=[0, 2, 3], names=["c", "m", "h"],
                      dtype={"c": str, "m": np.int64, "h": np.int64}, compression="gzip")
     cid = {c: i for i, c in enumerate(chroms)}
@@ -76,7 +77,11 @@ def read_fragments(path, chroms, mappThres):
     n = np.bincount(ids, minlength=len(chroms)).astype(np.int64)
     mx = np.full(len(chroms), -1, dtype=np.int64)
     np.maximum.at(mx, ids, ok.m.to_numpy(np.int64))
-    return Fragments(list(chroms), n, mx)
+    mids = None
+    if keep_mids:
+        allm = ok.m.to_numpy(np.int64)
+        mids = [np.sort(allm[ids == ci]) for ci in range(len(chroms))]
+    return Fragments(list(chroms), n, mx, mids)
 
 
 def read_biases(path, chroms, resolution, biasLowerBound, biasUpperBound):

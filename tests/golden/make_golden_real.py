@@ -25,6 +25,9 @@ CASES = {
     "real_pfal_10kb": ("Ay_Rings_MboI_Pfal_w10000", 10000, 25, ["-b", "200", "-x", "All"]),
     "real_hesc_40kb_bias": ("Dixon_hESC_HindIII_hg18_w40000_chr1", 40000, 12,
                             ["-L", "50000", "-U", "5000000", "-b", "50", "-x", "intraOnly", "-p", "2", "-t", "BIAS"]),
+    # restriction-fragment mode (-r 0), run_tests-git.sh:28-30, two passes instead of one to cover the outlier bookkeeping
+    "real_hesc_refrags_r0": ("Dixon_hESC_HindIII_hg18_combineFrags10_chr1", 0, 12,
+                             ["-L", "50000", "-U", "5000000", "-b", "200", "-x", "intraOnly", "-p", "2"]),
 }
 
 
@@ -33,6 +36,8 @@ def main():
         raise SystemExit("needs /root/reference")
     with tempfile.TemporaryDirectory() as tmp:
         for name, (ds, res, k, flags) in CASES.items():
+            if len(sys.argv) > 1 and name not in sys.argv[1:]:
+                continue
             src = os.path.join(DATA, "contactCounts", ds + ".gz")
             sub = os.path.join(tmp, name + ".contacts.gz")
             with gzip.open(src, "rt") as f, gzip.open(sub, "wt", compresslevel=1) as g:
@@ -46,11 +51,13 @@ def main():
             passes = R.run_reference(argv)
             contacts = fio.read_contacts(sub)
             chroms = list(contacts.chroms)
-            frags = fio.read_fragments(frag, chroms, 1)
+            frags = fio.read_fragments(frag, chroms, 1, keep_mids=(res == 0))
             contacts.chroms = chroms
             out = dict(mid1=contacts.mid1, mid2=contacts.mid2, cnt=contacts.cnt, chrs=contacts.chrs,
                        chroms=np.array(chroms), res=res, flags=np.array([str(x) for x in flags if x not in ("-t", "BIAS")]),
                        frag_n=frags.n_mappable, frag_maxmid=frags.max_mid, npasses=len(passes))
+            if res == 0:  # the fragment mid points themselves, concatenated chromosome by chromosome (frag_n gives the split)
+                out["frag_mids"] = np.concatenate([np.asarray(m, dtype=np.int64) for m in frags.mids])
             if "BIAS" in flags:
                 b, _ = fio.read_biases(bias, chroms, res, 0.5, 2.0)
                 out.update(bias_values=b.values, bias_mids=b.mids, bias_chr_off=b.chr_off)
@@ -67,8 +74,8 @@ def main():
                 out[pre + "dists"] = np.array([d for d, _ in md], dtype=np.int64)
                 out[pre + "sums"] = np.array([s for _, s in md], dtype=np.int64)
                 bn = p["bins"]
-                for key, dt in (("lb", np.int64), ("ub", np.int64), ("pairs", np.int64), ("sumcc", np.int64),
-                                ("sumdist", np.float64)):
+                for key, dt in (("lb", np.int64), ("ub", np.int64), ("pairs", np.int64), ("pairs7", np.int64),
+                                ("sumcc", np.int64), ("sumdist", np.float64)):
                     out[pre + "bin_" + key] = np.array([x[key] for x in bn], dtype=dt)
                 out[pre + "x"] = np.array(p["x"], dtype=np.float64)
                 out[pre + "y"] = np.array(p["y"], dtype=np.float64)
@@ -79,7 +86,8 @@ def main():
                 out[pre + "q"] = np.array(p["q"], dtype=np.float64)
                 out[pre + "outliersline"] = np.array(p["outliersline"], dtype=np.int64)
                 out[pre + "outliersdist"] = np.array(p["outliersdist"], dtype=np.int64)
-            sig = os.path.join(tmp, name + "_out", "%s.spline_pass%d.res%d.significances.txt.gz" % (name, len(passes), res))
+            sig = os.path.join(tmp, name + "_out", "%s.spline_pass%d%s.significances.txt.gz" %
+                               (name, len(passes), ".res%d" % res if res else ""))
             with gzip.open(sig, "rt") as f:
                 lines = f.readlines()
             out["sig_head"] = np.array(lines[:200])

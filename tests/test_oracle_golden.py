@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import fithic_oracle as O
-from tests.util import GOLDEN_CASES, load_golden, load_kat, oracle_inputs, rel_err
+from tests.util import GOLDEN_CASES, R0_CASES, load_golden, load_kat, oracle_inputs, rel_err
 
 
 def ulps(a, b):
@@ -32,7 +32,7 @@ def test_bh_against_reference_vectors():
                               np.array(want, dtype=np.float64), equal_nan=True)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + R0_CASES)
 def test_oracle_pipeline_against_reference(name):
     contacts, frags, biases, st, ref, _ = load_golden(name)
     oc, fchr, fmid, fh, ost, ob = oracle_inputs(contacts, frags, st, biases)
@@ -48,6 +48,7 @@ def test_oracle_pipeline_against_reference(name):
         assert len(g["bins"]) == len(r["bins"])
         for a, b in zip(g["bins"], r["bins"]):
             assert (a["lb"], a["ub"], a["pairs"], a["sumcc"]) == (b["lb"], b["ub"], b["pairs"], b["sumcc"])
+            assert a["pairs7"] == b["pairs7"]  # differs from `pairs` only in restriction-fragment mode (:733-734)
             assert a["sumdist"] == b["sumdist"]
         assert list(g["x"]) == list(r["x"]) and list(g["y"]) == list(r["y"])
         if r["splineX"] is not None:

@@ -16,8 +16,11 @@ def oracle_inputs(contacts, frags, st, biases=None):
         n = int(frags.n_mappable[ci])
         if n == 0:
             continue
-        # synthetic fragments: n loci, the last one at max_mid, spaced by res
-        mids = frags.max_mid[ci] - (n - 1 - np.arange(n, dtype=np.int64)) * res
+        if getattr(frags, "mids", None) is not None:
+            mids = np.asarray(frags.mids[ci], dtype=np.int64)  # restriction fragments: the mid points themselves
+        else:
+            # synthetic fragments: n loci, the last one at max_mid, spaced by res
+            mids = frags.max_mid[ci] - (n - 1 - np.arange(n, dtype=np.int64)) * res
         fchr.append(np.full(n, ci, dtype=np.int32))
         fmid.append(mids)
     fchr = np.concatenate(fchr) if fchr else np.zeros(0, np.int32)
@@ -103,6 +106,8 @@ GOLDEN_CASES = ["intra_40kb", "intra_bias_LU_p2", "all_bias", "inter_only_bias",
 # every k-th line of the reference's own bundled data sets (tests/golden/make_golden_real.py): real count distributions,
 # real ICE biases, real (irregular) fragment lists
 REAL_CASES = ["real_pfal_10kb", "real_hesc_40kb_bias"]
+# restriction-fragment mode (-r 0) on the reference's bundled HindIII fragments
+R0_CASES = ["real_hesc_refrags_r0"]
 
 
 def load_kat():
@@ -117,6 +122,9 @@ def load_golden(name):
     chroms = [str(c) for c in z["chroms"]]
     contacts = Contacts(z["mid1"], z["mid2"], z["cnt"], z["chrs"], chroms)
     frags = Fragments(chroms, z["frag_n"], z["frag_maxmid"])
+    if "frag_mids" in z:  # restriction-fragment mode: the mid points themselves
+        cuts = np.concatenate([[0], np.cumsum(z["frag_n"])]).astype(np.int64)
+        frags.mids = [z["frag_mids"][cuts[i]:cuts[i + 1]] for i in range(len(chroms))]
     biases = None
     if "bias_values" in z:
         biases = Biases(z["bias_values"], z["bias_mids"], z["bias_chr_off"])
@@ -142,8 +150,10 @@ def load_golden(name):
         pre = "p%d_" % k
         sc = z[pre + "scalars"]
         nb = len(z[pre + "bin_lb"])
+        p7 = z[pre + "bin_pairs7"] if (pre + "bin_pairs7") in z else z[pre + "bin_pairs"]
         bins = [dict(lb=int(z[pre + "bin_lb"][i]), ub=int(z[pre + "bin_ub"][i]), pairs=int(z[pre + "bin_pairs"][i]),
-                     sumcc=int(z[pre + "bin_sumcc"][i]), sumdist=float(z[pre + "bin_sumdist"][i])) for i in range(nb)]
+                     pairs7=int(p7[i]), sumcc=int(z[pre + "bin_sumcc"][i]), sumdist=float(z[pre + "bin_sumdist"][i]))
+                for i in range(nb)]
         has_spline = (pre + "splineX") in z
         passes.append(dict(N=int(z[pre + "N"]), T=int(z[pre + "T"]), observedInterAllCount=int(sc[0]),
                            observedInterAllSum=int(sc[1]), observedIntraAllSum=int(sc[2]),
