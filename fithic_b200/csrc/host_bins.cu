@@ -214,3 +214,64 @@ extern "C" int fhc_host_fill_f64(double *dst, int64_t n, double v, int32_t nthre
     for (auto &th : pool) th.join();
     return FHC_OK;
 }
+
+// generate_FragPairs, restriction-fragment branch (-r 0), fithic/fithic.py:691-778.  mids: the ascending mid points of the
+// mappable fragments, chromosome after chromosome in the reference's sorted-name order (chr_off[nchr + 1]).  Every pair
+// (x < y) of one chromosome with L <= mid_y - mid_x <= U counts once in bin_pairs1 (`[1] += 1`, :734), adds
+// npairs = templen - d to bin_pairs7 (`[7]`, :733; d = in-range partners of x seen so far, :723-724 -- the reference's own
+// quirk) and float(dist / 1e6) * npairs to bin_sumdist (:735), in the reference's order (x ascending, y ascending), so the
+// double sums are bit identical.  The reference walks all y > x and skips the out-of-range ones; the mids are sorted, so
+// the partners in range are one window per x, found by binary search.  bin_pairs1 / bin_pairs7 carry the pass >= 2 outlier
+// decrements on entry.  totals: [0] possibleIntraInRangeCount, [1] possibleIntraAllCount, [2] sum n (noOfFrags - n)
+// (= 2 possibleInterAllCount), [3] noOfFrags, [4] maxPossibleGenomicDist.
+extern "C" int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
+                                           const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
+                                           int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals) {
+    FHC_REQUIRE(nchr >= 0 && nbins >= 0 && totals != nullptr, FHC_E_INVALID, "fhc_host_frag_pairs_varsize: bad nchr / nbins / totals");
+    FHC_REQUIRE(nchr == 0 || (mids && chr_off), FHC_E_INVALID, "fhc_host_frag_pairs_varsize: null fragment arrays");
+    FHC_REQUIRE(nbins == 0 || (bin_lb && bin_ub && bin_pairs1 && bin_pairs7 && bin_sumdist), FHC_E_INVALID,
+                "fhc_host_frag_pairs_varsize: null bin arrays");
+    const int64_t noOfFrags = nchr > 0 ? chr_off[nchr] - chr_off[0] : 0;
+    int64_t inrange = 0, intra_all = 0, inter2 = 0, maxdist = 0;
+    for (int c = 0; c < nchr; ++c) {
+        const int64_t *f = mids + chr_off[c];
+        const int64_t n = chr_off[c + 1] - chr_off[c];
+        if (n <= 0) continue;
+        for (int64_t i = 1; i < n; ++i)
+            FHC_REQUIRE(f[i] >= f[i - 1], FHC_E_INVALID, "fhc_host_frag_pairs_varsize: mid points of chromosome %d are not sorted", c);
+        inter2 += (noOfFrags - n) * n;  // :701
+        for (int64_t x = 0; x < n; ++x) {
+            // window of partners in range (in_range_check, myUtils.py: L == -1 / U == -1 mean unbounded)
+            const int64_t *lo = L < 0 ? f + x + 1 : std::lower_bound(f + x + 1, f + n, f[x] + L);
+            const int64_t *hi = U < 0 ? f + n : std::upper_bound(f + x + 1, f + n, f[x] + U);
+            int tr = 0;
+            int64_t d = 0;
+            for (const int64_t *y = lo; y < hi; ++y) {
+                const int64_t di = *y - f[x];
+                inrange += 1;                       // :708
+                if (di > maxdist) maxdist = di;     // :711
+                const int64_t npairs = n - d;       // :713
+                d += 1;
+                if (nbins > 0) {
+                    while (!(bin_lb[tr] <= di && di <= bin_ub[tr])) {  // :719-731 forward tracker, clamped to the last bin
+                        tr += 1;
+                        if (tr >= nbins) {
+                            tr -= 1;
+                            break;
+                        }
+                    }
+                    bin_pairs7[tr] += npairs;
+                    bin_pairs1[tr] += 1;
+                    bin_sumdist[tr] += ((double)di / 1000000.0) * (double)npairs;
+                    intra_all += 1;                 // :736
+                }
+            }
+        }
+    }
+    totals[0] = inrange;
+    totals[1] = intra_all;
+    totals[2] = inter2;
+    totals[3] = noOfFrags;
+    totals[4] = maxdist;
+    return FHC_OK;
+}

@@ -103,6 +103,15 @@ class Engine:
         if not torch.cuda.is_available():
             raise RuntimeError("fithic_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.st = settings
+        # Restriction-fragment mode (-r 0): distances are arbitrary integers.  The kernels work on a grid of `grid` bp; with
+        # grid = 1 every distance is its own slot, so K1 (dense histogram), K2 (lookup table by slot) and K3 run unchanged --
+        # the slot arrays just get as long as the largest in-range distance (5 M entries for -U 5000000, 40 MB each).
+        self.grid = settings.resolution if settings.resolution > 0 else 1
+        if settings.resolution == 0:
+            if fragments.mids is None:
+                raise ValueError("restriction-fragment mode (-r 0) needs the fragment mid points (io.read_fragments(..., keep_mids=True))")
+            if biases is not None:
+                raise ValueError("a bias file together with -r 0 is not supported yet (the dense per-locus bias table needs a grid)")
         self.frags = fragments
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dist = dist_ctx
@@ -113,7 +122,7 @@ class Engine:
             # fixed-size bins on the regular grid (every slot holds mid = k * res + res / 2 or nothing): K3 can check the
             # mid point arithmetically and skips the gather of the stored mid points
             regular = False
-            if settings.resolution > 0 and len(biases.mids):
+            if settings.resolution > 0 and len(biases.mids):  # (always true here: -r 0 with biases was refused above)
                 nslot = np.diff(biases.chr_off)
                 k = np.arange(len(biases.mids), dtype=np.int64) - np.repeat(biases.chr_off[:-1], nslot)
                 want = k * settings.resolution + settings.resolution // 2
@@ -193,7 +202,9 @@ class Engine:
                 mx = int(torch.maximum(mid1.max(), mid2.max()).item()) - int(torch.minimum(mid1.min(), mid2.min()).item())
             if len(self.frags.max_mid):
                 mx = max(mx, int(self.frags.max_mid.max()))
-            self.D = mx // self.st.resolution + 2
+            if self.st.resolution == 0 and self.st.U >= 0:
+                mx = min(mx, self.st.U)  # on the 1 bp grid only in-range distances need a slot
+            self.D = mx // self.grid + 2
             if self.dist is not None:
                 self.D = self.dist.max_int(self.D)  # the histogram is all-reduced: every rank needs the same length
         return self.D
@@ -210,7 +221,7 @@ class Engine:
         scal = buf[D:D + _capi.N_SCALARS]
         present = buf[D + _capi.N_SCALARS:].view(torch.int32)[:nwords]
         check(self.lib.fhc_hist_distance(dptr(mid1), dptr(mid2), dptr(cnt), dptr(chrs), dptr(skip), int(skip_limit),
-                                         self.n, self.st.L, self.st.U, self.st.resolution, dptr(hist), dptr(present), D,
+                                         self.n, self.st.L, self.st.U, self.grid, dptr(hist), dptr(present), D,
                                          dptr(scal), self._stream()))
         return hist, present, scal
 
@@ -218,7 +229,7 @@ class Engine:
     def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
         st, lib = self.st, self.lib
-        res = st.resolution
+        res = self.grid
         ev = {}
         t0 = time.perf_counter()
         # ---- K1 ----
@@ -319,7 +330,7 @@ class Engine:
         nt = len(t)
         table = self._tensor("table", m, torch.float64)
         lut = self._tensor("lut", D, torch.float64)
-        res = self.st.resolution
+        res = self.grid
         if m < self.HOST_PAVA_MIN_POINTS:
             wsb = int(self.lib.fhc_spline_workspace_bytes(m))
             ws = self._buf("spline_ws", wsb)
@@ -371,7 +382,7 @@ class Engine:
             hi = min(lo + step, n)
             o = None if outl is None else outl[lo:hi]
             check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]), dptr(chrs[lo:hi]),
-                                       hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr, st.resolution, st.L, st.U,
+                                       hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr, self.grid, st.L, st.U,
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
                                        nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),
@@ -443,20 +454,34 @@ def make_bins(lib, dists, sums, noOfBins, N):
 
 
 def frag_pairs(lib, frags, st, bins, dec=None):
-    """generate_FragPairs fixed-size branch (fithic/fithic.py:596-689).  Mutates `bins` (adds pairs, sumdist)."""
+    """generate_FragPairs (fithic/fithic.py:596-689 fixed-size bins, :691-778 restriction fragments).  Mutates `bins`
+    (adds pairs = `[1]`, pairs7 = `[7]`, sumdist = `[3]`; the two pair counts differ only for restriction fragments)."""
     order = sorted(range(len(frags.chroms)), key=lambda i: frags.chroms[i])  # sorted chromosome NAMES (:606)
     order = [i for i in order if frags.n_mappable[i] > 0]
-    chr_n = np.ascontiguousarray(frags.n_mappable[order], dtype=np.int64)
-    chr_mm = np.ascontiguousarray(frags.max_mid[order], dtype=np.int64)
     nb = bins["n"]
     pairs = np.zeros(max(nb, 1), dtype=np.int64)
     if dec is not None:
         pairs[:nb] -= np.asarray(dec, dtype=np.int64)[:nb]
     sumdist = np.zeros(max(nb, 1), dtype=np.float64)
+    if st.resolution == 0:
+        mids = np.ascontiguousarray(np.concatenate([np.asarray(frags.mids[i], dtype=np.int64) for i in order])
+                                    if order else np.zeros(0, dtype=np.int64))
+        off = np.zeros(len(order) + 1, dtype=np.int64)
+        np.cumsum([len(frags.mids[i]) for i in order], out=off[1:])
+        pairs7 = pairs.copy()  # the outlier decrements hit [1] and [7] alike (:544-545)
+        totals = np.zeros(5, dtype=np.int64)
+        check(lib.fhc_host_frag_pairs_varsize(dptr(mids), dptr(off), len(order), st.L, st.U, dptr(bins["lb"]), dptr(bins["ub"]),
+                                              nb, dptr(pairs), dptr(pairs7), dptr(sumdist), dptr(totals)))
+        bins["pairs"], bins["pairs7"], bins["sumdist"] = pairs[:nb], pairs7[:nb], sumdist[:nb]
+        return dict(possibleIntraInRangeCount=int(totals[0]), possibleIntraAllCount=int(totals[1]),
+                    possibleInterAllCount=totals[2] / 2, noOfFrags=int(totals[3]))
+    chr_n = np.ascontiguousarray(frags.n_mappable[order], dtype=np.int64)
+    chr_mm = np.ascontiguousarray(frags.max_mid[order], dtype=np.int64)
     totals = np.zeros(4, dtype=np.int64)
     check(lib.fhc_host_frag_pairs(dptr(chr_n), dptr(chr_mm), len(order), int(st.resolution), st.L, st.U,
                                   dptr(bins["lb"]), dptr(bins["ub"]), nb, dptr(pairs), dptr(sumdist), dptr(totals)))
     bins["pairs"] = pairs[:nb]
+    bins["pairs7"] = bins["pairs"]
     bins["sumdist"] = sumdist[:nb]
     return dict(possibleIntraInRangeCount=int(totals[0]), possibleIntraAllCount=totals[1] / 2,
                 possibleInterAllCount=totals[2] / 2, noOfFrags=int(totals[3]))
@@ -465,11 +490,12 @@ def frag_pairs(lib, frags, st, bins, dec=None):
 def calculate_probabilities(bins, N):
     """calculateProbabilities (fithic/fithic.py:869-908): x = avgDist, y = avgCC per bin (vectorised, same IEEE ops)."""
     nb = bins["n"]
-    pairs = bins["pairs"].astype(np.float64)
+    pairs = bins["pairs"].astype(np.float64)     # [1] (:877)
+    pairs7 = bins["pairs7"].astype(np.float64)   # [7] (:885)
     sumcc = bins["sumcc"].astype(np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         y = np.where((bins["pairs"] > 0) & (N > 0), (1.0 * sumcc / pairs) / float(N) if N > 0 else 0.0, 0.0)
-        x = np.where(bins["pairs"] != 0, 1000000.0 * (bins["sumdist"] / pairs), 0.0)
+        x = np.where(bins["pairs7"] != 0, 1000000.0 * (bins["sumdist"] / pairs7), 0.0)
     return [float(v) for v in x[:nb]], [float(v) for v in y[:nb]]
 
 

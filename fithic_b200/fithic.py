@@ -29,7 +29,7 @@ def parse_args(args):
     parser.add_argument("-o", "--outdir", dest="outdir", required=True,
                         help="REQUIRED: where the output files will be written")
     parser.add_argument("-r", "--resolution", dest="resolution", type=int, required=True,
-                        help="REQUIRED: resolution of the fixed-size dataset (0 = non fixed size: not supported here)")
+                        help="REQUIRED: resolution of the fixed-size dataset; 0 = restriction-fragment (non fixed size) data")
     parser.add_argument("-t", "--biases", dest="biasfile", required=False,
                         help="RECOMMENDED: biases calculated by ICE or KR norm for each locus are read from BIASFILE")
     parser.add_argument("-p", "--passes", dest="noOfPasses", type=int, required=False,
@@ -82,14 +82,16 @@ def settings_from_args(args):
     if not os.path.isdir(args.outdir):
         os.makedirs(args.outdir)
     print("Output path being used from %s" % args.outdir)
-    if args.resolution == 0:
-        print("Fixed size option: the B200 path only supports fixed-size data (-r > 0); "
-              "restriction-fragment mode (-r 0) is not accelerated")
-        sys.exit(2)
     if args.resolution < 0:
         print("Resolution must be a positive integer")
         sys.exit(2)
-    print("Fixed size data being used with resolution: %s" % args.resolution)
+    if args.resolution == 0:
+        print("Non-fixed size data being used.")  # restriction fragments (fithic/fithic.py:166-170)
+        if args.biasfile:
+            print("A bias file together with -r 0 is not supported by the B200 path yet")
+            sys.exit(2)
+    else:
+        print("Fixed size data being used with resolution: %s" % args.resolution)
     if args.biasfile:
         if not os.path.exists(args.biasfile):
             print("Bias file not found")
@@ -158,7 +160,7 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
     chroms = list(contacts.chroms)
     say("Interactions file read. Time took %s" % (time.time() - t0))
     t1 = time.time()
-    frags = fio.read_fragments(frags_path, chroms, st.mappThres)
+    frags = fio.read_fragments(frags_path, chroms, st.mappThres, keep_mids=(st.resolution == 0))
     say("Fragments file read. Time took %s" % (time.time() - t1))
     biases, bias_log = None, []
     if bias_path:
@@ -185,7 +187,7 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
         e = r["expcc"].cpu().numpy()
         r.update(p=p, q=q, expcc=e, n_outliers_total=int(stats[0].item()))
         say("Outlier threshold is... %s" % r["outlierThres"])
-        suffix = ".res" + str(st.resolution)
+        suffix = ".res" + str(st.resolution) if st.resolution else ""  # -r 0 omits the part (:851, :1171)
         # log (re-opened 'w' in every pass like the reference, fithic/fithic.py:444)
         with open(logfile, "w") as log:
             log.write("\n\nInteractions file read successfully\n")

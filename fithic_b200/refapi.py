@@ -155,7 +155,7 @@ def generate_FragPairs(observedInterAllCount, observedInterAllSum, binStats, fra
     fp = frag_pairs(lib, frags, st, bins, dec)
     for i in range(nb):
         binStats[i][1] = int(bins["pairs"][i])
-        binStats[i][7] = int(bins["pairs"][i])
+        binStats[i][7] = int(bins["pairs7"][i])
         binStats[i][3] = float(bins["sumdist"][i])
     ok = frags.n_mappable > 0
     maxd = float((frags.max_mid[ok] - resolution / 2).max()) if ok.any() else 0
@@ -183,6 +183,7 @@ def calculateProbabilities(mainDic, binStats, resolution, outfilename, observedI
     """fithic/fithic.py:843-918.  Returns [x, y, yerr] and writes `${outfilename}.res${R}.txt`."""
     nb = len(binStats)
     bins = dict(n=nb, pairs=np.array([binStats[i][1] for i in range(nb)], dtype=np.int64),
+                pairs7=np.array([binStats[i][7] for i in range(nb)], dtype=np.int64),
                 sumcc=np.array([binStats[i][2] for i in range(nb)], dtype=np.int64),
                 sumdist=np.array([binStats[i][3] for i in range(nb)], dtype=np.float64))
     x, y = calculate_probabilities(bins, observedIntraInRangeSum)

@@ -92,6 +92,15 @@ int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxmid, int32_t
                         int64_t U, const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs,
                         double *bin_sumdist, int64_t *totals);
 
+/* generate_FragPairs, restriction-fragment branch (-r 0), fithic/fithic.py:691-778.  mids [host]: ascending mid points of
+ * the mappable fragments, chromosome after chromosome in sorted-name order (chr_off[nchr+1]).  bin_pairs1 (`[1]`: one per
+ * pair in range) and bin_pairs7 (`[7]`: npairs = templen - d per pair, the reference's quirk) carry the pass>=2 outlier
+ * decrements on entry.  totals[5]: possibleIntraInRangeCount, possibleIntraAllCount, sum n*(noOfFrags-n), noOfFrags,
+ * maxPossibleGenomicDist.  Same accumulation order as the reference: bit exact. */
+int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
+                                const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
+                                int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals);
+
 /* dst[i] = v for i < n with nthreads host threads (the end-to-end call fills its pinned q array with 1.0 while the GPU
  * works, see fhc_gather_ne_one). */
 int fhc_host_fill_f64(double *dst, int64_t n, double v, int32_t nthreads);

@@ -8,13 +8,13 @@ import pytest
 from fithic_b200 import io as fio
 from fithic_b200 import synth
 from tests.test_gpu_pipeline import run_engine
-from tests.util import GOLDEN_CASES, REAL_CASES, compare_pass, load_golden, load_kat
+from tests.util import GOLDEN_CASES, R0_CASES, REAL_CASES, compare_pass, load_golden, load_kat
 
 torch = pytest.importorskip("torch")
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES + REAL_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + REAL_CASES + R0_CASES)
 def test_engine_matches_reference_fixture(lib, name):
     contacts, frags, biases, st, ref, _ = load_golden(name)
     got = run_engine(contacts, frags, biases, st)
@@ -81,3 +81,38 @@ def test_cli_output_file_matches_reference(lib, name, tmp_path):
         for x, y in zip(fa[5:], fb[5:]):
             x, y = float(x), float(y)
             assert (np.isnan(x) and np.isnan(y)) or abs(x - y) <= 2e-6 * max(abs(y), 1e-300) + 1e-6 * (abs(y) < 1e-290), (a, b)
+
+
+def test_cli_restriction_fragment_mode(lib, tmp_path):
+    """`fithic -r 0` on restriction-fragment data (fithic/tests/run_tests-git.sh:28-30): file names without the `.res` part
+    (fithic/fithic.py:851, :1171) and the rows of the reference's own output."""
+    from fithic_b200 import fithic as cli
+    name = R0_CASES[0]
+    contacts, frags, biases, st, ref, extra = load_golden(name)
+    cpath = str(tmp_path / "contacts.gz")
+    fpath = str(tmp_path / "frags.gz")
+    with gzip.open(cpath, "wt") as f:
+        c1, c2 = contacts.chrs & 0xffff, contacts.chrs >> 16
+        for i in range(len(contacts)):
+            f.write("%s\t%d\t%s\t%d\t%d\n" % (contacts.chroms[c1[i]], contacts.mid1[i], contacts.chroms[c2[i]],
+                                              contacts.mid2[i], contacts.cnt[i]))
+    with gzip.open(fpath, "wt") as f:
+        for ci, ch in enumerate(frags.chroms):
+            for m in frags.mids[ci]:
+                f.write("%s\t0\t%d\t1\t1\n" % (ch, m))
+    cli.main(["-i", cpath, "-f", fpath, "-o", str(tmp_path / "out"), "-r", "0", "-l", name, "-b", str(st.noOfBins), "-p",
+              str(st.noOfPasses), "-L", str(st.L), "-U", str(st.U)])
+    npass = len(ref)
+    sig = tmp_path / "out" / ("%s.spline_pass%d.significances.txt.gz" % (name, npass))
+    assert sig.exists() and (tmp_path / "out" / ("%s.fithic_pass%d.txt" % (name, npass))).exists()
+    with gzip.open(sig, "rt") as f:
+        lines = f.readlines()
+    assert len(lines) - 1 == extra["sig_nrows"]
+    want = extra["sig_head"]
+    assert lines[0] == want[0]
+    for a, b in zip(lines[1:len(want)], want[1:]):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:5] == fb[:5], (a, b)
+        for x, y in zip(fa[5:], fb[5:]):
+            x, y = float(x), float(y)
+            assert abs(x - y) <= 2e-6 * max(abs(y), 1e-300) + 1e-6 * (abs(y) < 1e-290), (a, b)

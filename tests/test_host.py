@@ -200,7 +200,16 @@ def test_cli_argument_handling(tmp_path, capsys):
         cli.settings_from_args(a)
     assert e.value.code == 2
     a.contactType = None
-    a.resolution = 0
+    a.resolution = 0  # restriction-fragment mode: accepted, but not together with a bias file yet
+    st, _ = cli.settings_from_args(a)
+    assert st.resolution == 0
+    open(tmp_path / "b.gz", "w").close()
+    a.biasfile = str(tmp_path / "b.gz")
+    with pytest.raises(SystemExit) as e:
+        cli.settings_from_args(a)
+    assert e.value.code == 2
+    a.biasfile = None
+    a.resolution = -5
     with pytest.raises(SystemExit) as e:
         cli.settings_from_args(a)
     assert e.value.code == 2
@@ -384,3 +393,31 @@ def test_chr_runs_round_trip():
     assert np.all(v[1:] != v[:-1])
     v, l = chr_runs_of(np.zeros(0, dtype=np.uint32))
     assert len(v) == 0 and len(l) == 0
+
+
+def test_varsize_frag_pairs_bit_exact_against_reference_fixture(lib):
+    """fhc_host_frag_pairs_varsize (generate_FragPairs, restriction-fragment branch, fithic/fithic.py:691-778) on the
+    bundled HindIII fragments: `[1]`, `[7]`, `[3]` of every bin and possibleIntraInRangeCount as the unmodified reference
+    computed them, first and second pass (the second carries the outlier decrements)."""
+    from tests.util import R0_CASES
+    contacts, frags, biases, st, ref, _ = load_golden(R0_CASES[0])
+    assert st.resolution == 0 and frags.mids is not None
+    for k, r in enumerate(ref):
+        nb = len(r["bins"])
+        bins = dict(n=nb, lb=np.array([b["lb"] for b in r["bins"]], dtype=np.int64),
+                    ub=np.array([b["ub"] for b in r["bins"]], dtype=np.int64),
+                    sumcc=np.array([b["sumcc"] for b in r["bins"]], dtype=np.int64))
+        dec = None
+        if k > 0:  # outlier distances of the previous pass, binned like makeBinsFromInteractions :528-548
+            dec = np.zeros(nb, dtype=np.int64)
+            for d in ref[k - 1]["outliersdist"]:
+                i = int(np.searchsorted(bins["ub"], d, side="left"))
+                dec[min(i, nb - 1)] += 1
+        fp = frag_pairs(lib, frags, st, bins, dec)
+        assert fp["possibleIntraInRangeCount"] == r["possibleIntraInRangeCount"] == r["T"]
+        assert [int(v) for v in bins["pairs"]] == [b["pairs"] for b in r["bins"]]
+        assert [int(v) for v in bins["pairs7"]] == [b["pairs7"] for b in r["bins"]]
+        assert [float(v) for v in bins["sumdist"]] == [b["sumdist"] for b in r["bins"]]
+        x, y = calculate_probabilities(bins, r["N"])
+        assert sorted(x) == list(r["x"])
+        assert [v for _, v in sorted(zip(x, y))] == list(r["y"])
