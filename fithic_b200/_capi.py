@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 2
+FHC_ABI_VERSION = 3
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
 N_SCALARS = 8
@@ -54,7 +54,7 @@ _SIGNATURES = {
     "fhc_host_bdtrc_lists": (c_double, [c_int32, c_int64, c_double]),
     "fhc_host_one_minus_exp": (c_double, [c_double]),
     "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                                    c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                    c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                     c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_pvalues_workspace_bytes": (c_size_t, [c_int64, c_int64]),

@@ -342,7 +342,7 @@ extern "C" int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *pr
 
 extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt,
                            const uint32_t *chrs, int64_t n, const double *bias, const int32_t *bias_mid,
-                           const int64_t *chr_off, int32_t nchr, int32_t res, int64_t L, int64_t U, const double *lut,
+                           const int64_t *chr_off, int32_t nchr, int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut,
                            int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
                            const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
                            uint8_t *outl, int64_t line_base, double outl_thres, uint64_t *outl_stats, double *p,
@@ -373,6 +373,9 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.n = n;
     P.bias = bias;
     P.bias_mid = bias_mid;
+    P.bias_sparse = bias_sparse ? 1 : 0;
+    FHC_REQUIRE(!(bias && bias_sparse) || bias_mid != nullptr, FHC_E_INVALID,
+                "fhc_pvalues: the sparse bias layout needs bias_mid (the sorted mid points)");
     P.chr_off = reinterpret_cast<const long long *>(chr_off);
     P.nchr = nchr;
     P.res.d = (unsigned int)res;

@@ -20,6 +20,8 @@ struct PvalParams {
     long long n;
     const double *bias;
     const int *bias_mid;  // nullptr: every slot holds the locus at mid = slot * res + res / 2 (regular grid)
+    int bias_sparse;      // 1: no grid (restriction fragments): bias_mid holds each chromosome's mid points in ascending
+                          //    order, a locus is found by binary search
     const long long *chr_off;
     int nchr;
     FastDiv res;
@@ -42,6 +44,17 @@ struct PvalParams {
 __device__ __forceinline__ double bias_lookup(const PvalParams &P, unsigned int chr, int mid) {
     if ((int)chr >= P.nchr || mid < 0) return -1.0;
     const long long lo = __ldg(P.chr_off + chr), hi = __ldg(P.chr_off + chr + 1);
+    if (P.bias_sparse) {
+        long long a = lo, b = hi;  // lower bound of mid in bias_mid[lo, hi)
+        while (a < b) {
+            const long long m = (a + b) >> 1;
+            if (__ldg(P.bias_mid + m) < mid)
+                a = m + 1;
+            else
+                b = m;
+        }
+        return (a < hi && __ldg(P.bias_mid + a) == mid) ? __ldg(P.bias + a) : -1.0;
+    }
     const unsigned int k = fastdiv((unsigned int)mid, P.res);
     const long long s = lo + (long long)k;
     if (s >= hi) return -1.0;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool rng32 = false;
     if (HAS_BIAS) {
-        rng32 = P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
+        rng32 = !P.bias_sparse && P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
         if (rng32) {
             for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
             __syncthreads();
@@ -572,7 +572,7 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     } while (0)
     if (!P.bias)
         FHC_FRONT_V(false, true);
-    else if (P.bias_mid == nullptr)
+    else if (P.bias_mid == nullptr && !P.bias_sparse)
         FHC_FRONT_V(true, true);
     else
         FHC_FRONT_V(true, false);

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -399,8 +400,8 @@ extern "C" int64_t fhc_io_write_significances(const char *path, const char *cons
     FHC_REQUIRE(path && chrom_names && nchrom >= 0 && n >= 0, FHC_E_INVALID, "fhc_io_write_significances: bad arguments");
     FHC_REQUIRE(n == 0 || (mid1 && mid2 && cnt && chrs && p && q && expcc), FHC_E_INVALID,
                 "fhc_io_write_significances: null array");
-    FHC_REQUIRE(bias == nullptr || (bias_mid && chr_off && res > 0), FHC_E_INVALID,
-                "fhc_io_write_significances: bias needs bias_mid, chr_off, res");
+    FHC_REQUIRE(bias == nullptr || (bias_mid && chr_off && res >= 0), FHC_E_INVALID,
+                "fhc_io_write_significances: bias needs bias_mid, chr_off, res >= 0");
     FILE *fp = fopen(path, "wb");
     FHC_REQUIRE(fp != nullptr, FHC_E_INVALID, "cannot create %s", path);
     init_pow10();
@@ -413,6 +414,11 @@ extern "C" int64_t fhc_io_write_significances(const char *path, const char *cons
     auto bias_of = [&](uint32_t chr, int32_t mid) -> double {
         if (!bias) return 1.0;
         if ((int32_t)chr >= nbias_chr || mid < 0) return -1.0;
+        if (res == 0) {  // restriction fragments: each chromosome's loci in ascending mid order, binary search
+            const int32_t *lo = bias_mid + chr_off[chr], *hi = bias_mid + chr_off[chr + 1];
+            const int32_t *it = std::lower_bound(lo, hi, mid);
+            return (it < hi && *it == mid) ? bias[it - bias_mid] : -1.0;
+        }
         const int64_t s = chr_off[chr] + mid / res;
         if (s >= chr_off[chr + 1] || bias_mid[s] != mid) return -1.0;
         return bias[s];

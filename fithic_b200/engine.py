@@ -92,6 +92,8 @@ class Biases:
     values: np.ndarray   # float64 [nslots]
     mids: np.ndarray     # int32 [nslots], the mid point stored in the slot (-1 = empty)
     chr_off: np.ndarray  # int64 [nchr + 1]
+    sparse: bool = False  # restriction-fragment mode (-r 0): no grid -- per chromosome the loci of the bias file in ascending
+                          # mid order; a locus is found by binary search
 
 
 class Engine:
@@ -110,8 +112,9 @@ class Engine:
         if settings.resolution == 0:
             if fragments.mids is None:
                 raise ValueError("restriction-fragment mode (-r 0) needs the fragment mid points (io.read_fragments(..., keep_mids=True))")
-            if biases is not None:
-                raise ValueError("a bias file together with -r 0 is not supported yet (the dense per-locus bias table needs a grid)")
+            if biases is not None and not biases.sparse:
+                raise ValueError("restriction-fragment mode (-r 0) needs the bias table in its sparse layout "
+                                 "(io.read_biases(..., resolution=0))")
         self.frags = fragments
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dist = dist_ctx
@@ -122,7 +125,7 @@ class Engine:
             # fixed-size bins on the regular grid (every slot holds mid = k * res + res / 2 or nothing): K3 can check the
             # mid point arithmetically and skips the gather of the stored mid points
             regular = False
-            if settings.resolution > 0 and len(biases.mids):  # (always true here: -r 0 with biases was refused above)
+            if settings.resolution > 0 and len(biases.mids) and not biases.sparse:
                 nslot = np.diff(biases.chr_off)
                 k = np.arange(len(biases.mids), dtype=np.int64) - np.repeat(biases.chr_off[:-1], nslot)
                 want = k * settings.resolution + settings.resolution // 2
@@ -131,6 +134,7 @@ class Engine:
             self._bias_dev = (torch.from_numpy(biases.values).to(self.device),
                               None if regular else torch.from_numpy(biases.mids).to(self.device),
                               torch.from_numpy(biases.chr_off).to(self.device))
+            self._bias_sparse = 1 if biases.sparse else 0
         self._ws = {}
         self.contacts = None
         self.n = 0
@@ -382,7 +386,8 @@ class Engine:
             hi = min(lo + step, n)
             o = None if outl is None else outl[lo:hi]
             check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]), dptr(chrs[lo:hi]),
-                                       hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr, self.grid, st.L, st.U,
+                                       hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr,
+                                       getattr(self, "_bias_sparse", 0), self.grid, st.L, st.U,
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
                                        nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),

@@ -87,9 +87,6 @@ def settings_from_args(args):
         sys.exit(2)
     if args.resolution == 0:
         print("Non-fixed size data being used.")  # restriction fragments (fithic/fithic.py:166-170)
-        if args.biasfile:
-            print("A bias file together with -r 0 is not supported by the B200 path yet")
-            sys.exit(2)
     else:
         print("Fixed size data being used with resolution: %s" % args.resolution)
     if args.biasfile:

@@ -112,6 +112,18 @@ def read_biases(path, chroms, resolution, biasLowerBound, biasUpperBound):
     if len(mids) and (mids.min() < 0 or mids.max() > _I32_MAX):
         raise ValueError("bias mid points outside int32")
     nchr = len(chroms)
+    if resolution == 0:
+        # restriction fragments: no grid.  Per chromosome the loci in ascending mid order, first occurrence of a repeated
+        # (chr, mid) wins (:823-829); K3 and the writer find a locus by binary search.
+        order = np.lexsort((np.arange(len(mids)), mids, ids))  # by chromosome, mid, then file order
+        ids_s, mids_s, b_s = ids[order], mids[order], b[order]
+        first = np.ones(len(order), dtype=bool)
+        first[1:] = (ids_s[1:] != ids_s[:-1]) | (mids_s[1:] != mids_s[:-1])
+        ids_s, mids_s, b_s = ids_s[first], mids_s[first], b_s[first]
+        chr_off = np.zeros(nchr + 1, dtype=np.int64)
+        np.cumsum(np.bincount(ids_s, minlength=nchr), out=chr_off[1:])
+        return Biases(np.ascontiguousarray(b_s, dtype=np.float64), np.ascontiguousarray(mids_s, dtype=np.int32), chr_off,
+                      True), log
     nslot = np.zeros(nchr, dtype=np.int64)
     if len(mids):
         np.maximum.at(nslot, ids, mids // resolution + 1)
@@ -138,6 +150,16 @@ def lookup_biases(biases, chr_ids, mids, resolution):
     chr_ids = chr_ids.astype(np.int64)
     ok = chr_ids < nchr
     cidc = np.where(ok, chr_ids, 0)
+    if biases.sparse:
+        out = np.full(len(mids), -1.0)
+        for c in np.unique(cidc[ok]):
+            lo, hi = int(biases.chr_off[c]), int(biases.chr_off[c + 1])
+            sel = np.nonzero(ok & (cidc == c))[0]
+            if hi > lo and len(sel):
+                pos = np.minimum(np.searchsorted(biases.mids[lo:hi], mids[sel]), hi - lo - 1)
+                hit = biases.mids[lo:hi][pos] == mids[sel]
+                out[sel[hit]] = biases.values[lo:hi][pos[hit]]
+        return out
     slot = biases.chr_off[cidc] + mids.astype(np.int64) // resolution
     ok &= slot < biases.chr_off[cidc + 1]
     slot = np.where(ok, slot, 0)

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 2
+#define FHC_ABI_VERSION 3
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -157,6 +157,8 @@ double fhc_host_one_minus_exp(double y);
  *   line_base  index in the whole file of the first contact passed (a caller may score the file slice by slice; the
  *              index is only used for outl_stats[1])
  *   p, expcc   outputs, one double per line (:1119-1122)
+ *   bias_sparse  1 = no grid (restriction-fragment mode, -r 0): bias / bias_mid hold, per chromosome, the loci of the bias
+ *              file in ascending mid order (chr_off[c] .. chr_off[c+1]) and a locus is found by binary search
  *   bias_mid   may be NULL when every slot s of chromosome c holds the locus at mid = (s - chr_off[c]) * res + res / 2
  *              (fixed-size bins on the regular grid): the mid point is then checked arithmetically, one gather less
  *   workspace  [dev, nullable] fhc_pvalues_workspace_bytes(n, ntab) bytes, ntab = max(ntab_intra, ntab_inter).  With a
@@ -167,7 +169,7 @@ double fhc_host_one_minus_exp(double y);
 size_t fhc_pvalues_workspace_bytes(int64_t n, int64_t ntab);
 int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
                 int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
-                int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
+                int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
                 double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
                 const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, int64_t line_base, double outl_thres,
                 uint64_t *outl_stats, double *p, double *expcc, void *workspace, size_t workspace_bytes, void *stream);

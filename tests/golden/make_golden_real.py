@@ -28,6 +28,10 @@ CASES = {
     # restriction-fragment mode (-r 0), run_tests-git.sh:28-30, two passes instead of one to cover the outlier bookkeeping
     "real_hesc_refrags_r0": ("Dixon_hESC_HindIII_hg18_combineFrags10_chr1", 0, 12,
                              ["-L", "50000", "-U", "5000000", "-b", "200", "-x", "intraOnly", "-p", "2"]),
+    # the same with a bias file: there is none for the restriction fragments among the bundled data, so the reference's own
+    # HiCKRy (unmodified) computes one from the sub-sampled contacts first
+    "real_mesc_refrags_r0_bias": ("Dixon_mESC_HindIII_mm9_combineFrags10_chr1", 0, 16,
+                                  ["-L", "50000", "-U", "5000000", "-b", "100", "-x", "intraOnly", "-p", "1", "-t", "KRBIAS"]),
 }
 
 
@@ -46,7 +50,13 @@ def main():
                         g.write(line)
             frag = os.path.join(DATA, "fragmentLists", ds + ".gz")
             bias = os.path.join(DATA, "biasPerLocus", ds + ".gz")
-            fl = [bias if x == "BIAS" else x for x in flags]
+            if "KRBIAS" in flags:
+                sys.path.insert(0, "/root/reference/fithic/utils")
+                import HiCKRy as H  # the reference's bias generator, unmodified
+                bias = os.path.join(tmp, name + ".bias.gz")
+                matrix, rev = H.loadfastfithicInteractions(sub, frag)
+                H.outputBias(H.returnBias(matrix, 0.05), rev, bias)
+            fl = [bias if x in ("BIAS", "KRBIAS") else x for x in flags]
             argv = ["-i", sub, "-f", frag, "-o", os.path.join(tmp, name + "_out"), "-r", res, "-l", name] + fl
             passes = R.run_reference(argv)
             contacts = fio.read_contacts(sub)
@@ -54,11 +64,12 @@ def main():
             frags = fio.read_fragments(frag, chroms, 1, keep_mids=(res == 0))
             contacts.chroms = chroms
             out = dict(mid1=contacts.mid1, mid2=contacts.mid2, cnt=contacts.cnt, chrs=contacts.chrs,
-                       chroms=np.array(chroms), res=res, flags=np.array([str(x) for x in flags if x not in ("-t", "BIAS")]),
+                       chroms=np.array(chroms), res=res,
+                       flags=np.array([str(x) for x in flags if x not in ("-t", "BIAS", "KRBIAS")]),
                        frag_n=frags.n_mappable, frag_maxmid=frags.max_mid, npasses=len(passes))
             if res == 0:  # the fragment mid points themselves, concatenated chromosome by chromosome (frag_n gives the split)
                 out["frag_mids"] = np.concatenate([np.asarray(m, dtype=np.int64) for m in frags.mids])
-            if "BIAS" in flags:
+            if "BIAS" in flags or "KRBIAS" in flags:
                 b, _ = fio.read_biases(bias, chroms, res, 0.5, 2.0)
                 out.update(bias_values=b.values, bias_mids=b.mids, bias_chr_off=b.chr_off)
                 out["frag_n"], out["frag_maxmid"] = frags.n_mappable, frags.max_mid

@@ -37,7 +37,7 @@ def test_errors_are_reported_not_swallowed(lib):
     with pytest.raises(_capi.FithicB200Error):
         _capi.check(rc)
     # device entry points validate their arguments before touching the GPU
-    assert lib.fhc_pvalues(7, None, None, None, None, 1, None, None, None, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
+    assert lib.fhc_pvalues(7, None, None, None, None, 1, None, None, None, 0, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
                            None, 0, None, 0, None, 0, 0.0, None, None, None, None, 0, None) == _capi.FHC_E_INVALID
     assert lib.fhc_lbeta_table(1 << 31, ctypes.c_void_p(16), 4, None) == _capi.FHC_E_RANGE
 
@@ -200,15 +200,9 @@ def test_cli_argument_handling(tmp_path, capsys):
         cli.settings_from_args(a)
     assert e.value.code == 2
     a.contactType = None
-    a.resolution = 0  # restriction-fragment mode: accepted, but not together with a bias file yet
+    a.resolution = 0  # restriction-fragment mode
     st, _ = cli.settings_from_args(a)
     assert st.resolution == 0
-    open(tmp_path / "b.gz", "w").close()
-    a.biasfile = str(tmp_path / "b.gz")
-    with pytest.raises(SystemExit) as e:
-        cli.settings_from_args(a)
-    assert e.value.code == 2
-    a.biasfile = None
     a.resolution = -5
     with pytest.raises(SystemExit) as e:
         cli.settings_from_args(a)
@@ -421,3 +415,36 @@ def test_varsize_frag_pairs_bit_exact_against_reference_fixture(lib):
         x, y = calculate_probabilities(bins, r["N"])
         assert sorted(x) == list(r["x"])
         assert [v for _, v in sorted(zip(x, y))] == list(r["y"])
+
+
+def test_sparse_bias_layout_for_restriction_fragments(tmp_path):
+    """-r 0: io.read_biases builds the grid-free layout (per chromosome the loci in ascending mid order, FIRST occurrence of
+    a repeated locus wins, fithic/fithic.py:823-829); lookup_biases and the native writer find loci by binary search."""
+    from fithic_b200.engine import Contacts
+    lines = [("chrB", 900, 1.5), ("chrA", 5000, 0.8), ("chrA", 120, 1.1), ("chrA", 5000, 1.9), ("chrB", 17, 3.0),
+             ("chrA", 77777, float("nan")), ("chrB", 901, 0.7)]
+    path = str(tmp_path / "bias.gz")
+    with gzip.open(path, "wt") as f:
+        for c, m, b in lines:
+            f.write("%s\t%d\t%s\n" % (c, m, b))
+    chroms = ["chrA", "chrB"]
+    b, _ = fio.read_biases(path, chroms, 0, 0.5, 2.0)
+    assert b.sparse and b.chr_off.tolist() == [0, 3, 6]
+    assert b.mids.tolist() == [120, 5000, 77777, 17, 900, 901]
+    assert b.values.tolist() == [1.1, 0.8, -1.0, -1.0, 1.5, 0.7]  # 5000 keeps its first value; NaN and 3.0 -> -1
+    cid = np.array([0, 0, 0, 1, 1, 1, 5], dtype=np.int64)
+    mids = np.array([5000, 121, 77777, 901, 17, 5000, 120], dtype=np.int32)
+    assert fio.lookup_biases(b, cid, mids, 0).tolist() == [0.8, -1.0, -1.0, 0.7, -1.0, -1.0, -1.0]
+    # the native writer against the Python writer on the same sparse table
+    n = 6
+    contacts = Contacts(np.array([120, 5000, 900, 17, 5000, 901], dtype=np.int32),
+                        np.array([5000, 77777, 901, 900, 5001, 901], dtype=np.int32), np.arange(1, n + 1, dtype=np.int32),
+                        np.array([0, 0, 1 | (1 << 16), 1 | (1 << 16), 0, 1 | (1 << 16)], dtype=np.uint32), chroms)
+    st = Settings(resolution=0)
+    p, q, e = np.linspace(0.1, 0.9, n), np.linspace(0.2, 1.0, n), np.linspace(0, 5, n)
+    c1, c2 = contacts.chrs & 0xffff, contacts.chrs >> 16
+    b1 = fio.lookup_biases(b, c1, contacts.mid1, 0)
+    b2 = fio.lookup_biases(b, c2, contacts.mid2, 0)
+    fio.write_significances(str(tmp_path / "py.gz"), contacts, p, q, e, b1, b2, st)
+    fio.write_significances_native(str(tmp_path / "native.gz"), contacts, p, q, e, b, st, nthreads=2)
+    assert gzip.open(tmp_path / "py.gz").read() == gzip.open(tmp_path / "native.gz").read()

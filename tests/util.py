@@ -107,7 +107,7 @@ GOLDEN_CASES = ["intra_40kb", "intra_bias_LU_p2", "all_bias", "inter_only_bias",
 # real ICE biases, real (irregular) fragment lists
 REAL_CASES = ["real_pfal_10kb", "real_hesc_40kb_bias"]
 # restriction-fragment mode (-r 0) on the reference's bundled HindIII fragments
-R0_CASES = ["real_hesc_refrags_r0"]
+R0_CASES = ["real_hesc_refrags_r0", "real_mesc_refrags_r0_bias"]
 
 
 def load_kat():
@@ -127,7 +127,7 @@ def load_golden(name):
         frags.mids = [z["frag_mids"][cuts[i]:cuts[i + 1]] for i in range(len(chroms))]
     biases = None
     if "bias_values" in z:
-        biases = Biases(z["bias_values"], z["bias_mids"], z["bias_chr_off"])
+        biases = Biases(z["bias_values"], z["bias_mids"], z["bias_chr_off"], int(z["res"]) == 0)
     st = Settings(resolution=int(z["res"]))
     flags = [str(f) for f in z["flags"]]
     i = 0
