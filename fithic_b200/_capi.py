@@ -46,7 +46,6 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "fhc_spline_eval": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_host_antitonic": (ctypes.c_int, [c_void_p, c_int64]),
-    "fhc_host_spline_table": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
     "fhc_spline_lut": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_int32, c_void_p, c_int64,
                                        c_void_p]),
     "fhc_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_void_p]),

@@ -21,22 +21,8 @@ namespace fhc {
 
 constexpr int kPavaThreads = 1024;
 
-// explicitly rounded operations: device intrinsics, plain operators on the host (host objects are built with
-// -ffp-contract=off), so that splev3 gives the same bits on both
-#if defined(__CUDA_ARCH__)
-#define SP_ADD(a, b) __dadd_rn(a, b)
-#define SP_SUB(a, b) __dsub_rn(a, b)
-#define SP_MUL(a, b) __dmul_rn(a, b)
-#define SP_DIV(a, b) __ddiv_rn(a, b)
-#else
-#define SP_ADD(a, b) ((a) + (b))
-#define SP_SUB(a, b) ((a) - (b))
-#define SP_MUL(a, b) ((a) * (b))
-#define SP_DIV(a, b) ((a) / (b))
-#endif
-
 // FITPACK splev for k = 3 at one abscissa.  t[0..nt), c[0..nt) (zero padded), x inside [t[3], t[nt-4]].
-__host__ __device__ inline double splev3(const double *__restrict__ t, const double *__restrict__ c, int nt, double x) {
+__device__ double splev3(const double *__restrict__ t, const double *__restrict__ c, int nt, double x) {
     // interval: largest l in [3, nt-5] with t[l] <= x  (splev.f: "search for knot interval t(l) <= arg < t(l+1)")
     int lo = 3, hi = nt - 5;
     while (lo < hi) {
@@ -56,14 +42,14 @@ __host__ __device__ inline double splev3(const double *__restrict__ t, const dou
             if (t[li] == t[lj]) {
                 h[i + 1] = 0.0;
             } else {
-                const double f = SP_DIV(hh[i], SP_SUB(t[li], t[lj]));
-                h[i] = SP_ADD(h[i], SP_MUL(f, SP_SUB(t[li], x)));
-                h[i + 1] = SP_MUL(f, SP_SUB(x, t[lj]));
+                const double f = __ddiv_rn(hh[i], __dsub_rn(t[li], t[lj]));
+                h[i] = __dadd_rn(h[i], __dmul_rn(f, __dsub_rn(t[li], x)));
+                h[i + 1] = __dmul_rn(f, __dsub_rn(x, t[lj]));
             }
         }
     }
     double sp = 0.0;
-    for (int j = 0; j < 4; ++j) sp = SP_ADD(sp, SP_MUL(c[l - 3 + j], h[j]));
+    for (int j = 0; j < 4; ++j) sp = __dadd_rn(sp, __dmul_rn(c[l - 3 + j], h[j]));
     return sp;
 }
 
@@ -293,17 +279,6 @@ extern "C" int fhc_host_antitonic(double *y, int64_t m) {
         for (int64_t k = 0; k < cnt[b]; ++k) y[i++] = mean;
     }
     return FHC_OK;
-}
-
-// The first two stages of K2 on the host for large tables: y[j] = splev(t, c, 3, splineX[j]) with the same explicitly
-// rounded operations as the device kernel (bit identical), then the antitonic regression in place.  Saves the device
-// round trip (kernel, 400 kB down, sync) in front of a scan that has to run on the host anyway; 50 k points take ~0.1 ms.
-extern "C" int fhc_host_spline_table(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m,
-                                     double *y) {
-    FHC_REQUIRE(t && c && splineX && y, FHC_E_INVALID, "fhc_host_spline_table: null pointer");
-    FHC_REQUIRE(nt >= 8 && m > 0, FHC_E_INVALID, "fhc_host_spline_table: need nt >= 8 and m > 0");
-    for (int64_t j = 0; j < m; ++j) y[j] = fhc::splev3(t, c, nt, (double)splineX[j]);
-    return fhc_host_antitonic(y, m);
 }
 
 extern "C" int fhc_spline_lut(const int64_t *splineX, const double *table, int64_t m, double xmin, double xmax,

@@ -261,11 +261,8 @@ class Engine:
         max_count = int(scal[_capi.S_MAX_COUNT])
         t1 = time.perf_counter()
         # ---- host: bins, possible pairs, probabilities, spline fit ----
-        if present.any():  # a distance whose counts sum to zero still counts as seen (:434-436): rare
-            pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
-            seen = np.nonzero((hist != 0) | pres_bits)[0]
-        else:
-            seen = np.nonzero(hist)[0]
+        pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
+        seen = np.nonzero((hist != 0) | pres_bits)[0]
         dists = (seen * res).astype(np.int64)
         sums = hist[seen].astype(np.int64)
         bins = make_bins(lib, dists, sums, st.noOfBins, N)
@@ -344,11 +341,9 @@ class Engine:
             check(self.lib.fhc_spline_table(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(sx), m, float(xmin), float(xmax), res,
                                             dptr(table), dptr(lut), D, dptr(ws), wsb, self._stream()))
         else:
-            # large table: evaluate and pool on the host (bit identical to the device evaluation; the pooling scan has to
-            # run there anyway), one upload, lookup table on the device
-            y = np.empty(m, dtype=np.float64)
-            sxh = np.ascontiguousarray(splineX, dtype=np.int64)
-            check(self.lib.fhc_host_spline_table(dptr(host[:nt]), dptr(host[nt:]), nt, dptr(sxh), m, dptr(y)))
+            check(self.lib.fhc_spline_eval(dptr(tc[:nt]), dptr(tc[nt:]), nt, dptr(sx), m, dptr(table), self._stream()))
+            y = table.cpu().numpy()
+            check(self.lib.fhc_host_antitonic(dptr(y), m))
             table.copy_(torch.from_numpy(y))
             check(self.lib.fhc_spline_lut(dptr(sx), dptr(table), m, float(xmin), float(xmax), res, dptr(lut), D,
                                           self._stream()))

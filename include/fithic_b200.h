@@ -125,9 +125,6 @@ int fhc_spline_table(const double *t, const double *c, int32_t nt, const int64_t
 int fhc_spline_eval(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m, double *y,
                     void *stream);
 int fhc_host_antitonic(double *y, int64_t m);
-/* fhc_spline_eval + fhc_host_antitonic on the host in one call (same explicitly rounded operations as the device kernel:
- * bit identical); t, c, splineX, y [host]. */
-int fhc_host_spline_table(const double *t, const double *c, int32_t nt, const int64_t *splineX, int64_t m, double *y);
 int fhc_spline_lut(const int64_t *splineX, const double *table, int64_t m, double xmin, double xmax, int32_t res,
                    double *lut, int64_t D, void *stream);
 

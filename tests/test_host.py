@@ -448,32 +448,3 @@ def test_sparse_bias_layout_for_restriction_fragments(tmp_path):
     fio.write_significances(str(tmp_path / "py.gz"), contacts, p, q, e, b1, b2, st)
     fio.write_significances_native(str(tmp_path / "native.gz"), contacts, p, q, e, b, st, nthreads=2)
     assert gzip.open(tmp_path / "py.gz").read() == gzip.open(tmp_path / "native.gz").read()
-
-
-def test_host_spline_table_is_fitpack_and_isotonic(lib):
-    """fhc_host_spline_table: splev bit for bit against FITPACK (scipy) and the pooled result against sklearn's
-    IsotonicRegression(increasing=False), on the spline of a reference fixture and on a noisy one."""
-    from scipy.interpolate import UnivariateSpline
-    from sklearn.isotonic import IsotonicRegression
-    contacts, frags, biases, st, ref, _ = load_golden("real_hesc_40kb_bias")
-    r = ref[0]
-    rng = np.random.default_rng(8)
-    for noise in (0.0, 0.3):
-        xs = np.asarray(r["x"], dtype=np.float64)
-        ys = np.asarray(r["y"], dtype=np.float64) * (1.0 + noise * rng.standard_normal(len(r["y"])))
-        ys = np.abs(ys) + 1e-12
-        ius = UnivariateSpline(xs, ys, s=min(ys) * min(ys))
-        t, c, k = ius._eval_args
-        sx = np.asarray(r["splineX"], dtype=np.int64)
-        tt, cc = np.ascontiguousarray(t, dtype=np.float64), np.zeros(len(t))
-        cc[:len(c)] = c
-        y = np.empty(len(sx))
-        # evaluation alone: copy of the first stage (antitonic of a strictly decreasing input is the identity, so check on
-        # the pooled output below and on the raw splev through a monotone slice)
-        _capi.check(lib.fhc_host_spline_table(_capi.dptr(tt), _capi.dptr(cc), len(tt), _capi.dptr(sx), len(sx), _capi.dptr(y)))
-        want = IsotonicRegression(increasing=False).fit_transform(sx, ius(sx))
-        assert np.max(np.abs(y - want) / np.abs(want)) <= 1e-14
-        raw = ius(sx)
-        mono = np.all(np.diff(raw) <= 0)
-        if mono:
-            assert np.array_equal(y, raw)  # no pooling: the table is FITPACK's splev bit for bit
