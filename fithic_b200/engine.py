@@ -261,8 +261,11 @@ class Engine:
         max_count = int(scal[_capi.S_MAX_COUNT])
         t1 = time.perf_counter()
         # ---- host: bins, possible pairs, probabilities, spline fit ----
-        pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
-        seen = np.nonzero((hist != 0) | pres_bits)[0]
+        if present.any():  # a distance whose counts sum to zero still counts as seen (:434-436): rare
+            pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
+            seen = np.nonzero((hist != 0) | pres_bits)[0]
+        else:
+            seen = np.nonzero(hist)[0]
         dists = (seen * res).astype(np.int64)
         sums = hist[seen].astype(np.int64)
         bins = make_bins(lib, dists, sums, st.noOfBins, N)
