@@ -482,7 +482,7 @@ def frag_pairs(lib, frags, st, bins, dec=None):
                                               nb, dptr(pairs), dptr(pairs7), dptr(sumdist), dptr(totals)))
         bins["pairs"], bins["pairs7"], bins["sumdist"] = pairs[:nb], pairs7[:nb], sumdist[:nb]
         return dict(possibleIntraInRangeCount=int(totals[0]), possibleIntraAllCount=int(totals[1]),
-                    possibleInterAllCount=totals[2] / 2, noOfFrags=int(totals[3]))
+                    possibleInterAllCount=totals[2] / 2, noOfFrags=int(totals[3]), maxPossibleGenomicDist=int(totals[4]))
     chr_n = np.ascontiguousarray(frags.n_mappable[order], dtype=np.int64)
     chr_mm = np.ascontiguousarray(frags.max_mid[order], dtype=np.int64)
     totals = np.zeros(4, dtype=np.int64)

@@ -56,8 +56,11 @@ def _engine(s, resolution, frags=None, biases=None):
     """(Re)build the engine of a session when the resolution, the fragments or the biases become known."""
     key = (int(resolution), id(frags), id(biases))
     if s.get("engine_key") != key:
-        fr = frags if frags is not None else Fragments(list(s["chroms"]), np.zeros(len(s["chroms"]), np.int64),
-                                                       np.full(len(s["chroms"]), -1, np.int64))
+        fr = frags
+        if fr is None:  # read_Interactions comes before generate_FragPairs: K1 does not look at the fragments
+            fr = Fragments(list(s["chroms"]), np.zeros(len(s["chroms"]), np.int64), np.full(len(s["chroms"]), -1, np.int64))
+            if not int(resolution):
+                fr.mids = [np.zeros(0, np.int64) for _ in s["chroms"]]
         eng = Engine(_settings(resolution), fr, biases)
         eng.upload_contacts(s["contacts"])
         s["engine"], s["engine_key"] = eng, key
@@ -95,7 +98,7 @@ def read_Interactions(contactCountsFile, biasFile, outliers=None):
     if int(sc[_capi.S_OFFGRID]):
         raise ValueError("contact distances off the %d bp grid are not supported" % res)
     seen = np.nonzero((h != 0) | bits)[0]
-    mainDic = {int(k) * res: [0, int(h[k])] for k in seen}
+    mainDic = {int(k) * eng.grid: [0, int(h[k])] for k in seen}
     _log("\n\nInteractions file read successfully\n" + "-" * 84 + "\n"
          "Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" % (sc[_capi.S_INTRA_INRANGE_LINES], sc[0]) +
          "Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" % (sc[_capi.S_INTRA_ALL_LINES], sc[1]) +
@@ -134,16 +137,15 @@ def makeBinsFromInteractions(mainDic, noOfBins_, observedIntraInRangeSum, outlie
 
 
 def generate_FragPairs(observedInterAllCount, observedInterAllSum, binStats, fragsfile, resolution):
-    """fithic/fithic.py:561-793, fixed-size branch.  Returns (binStats, noOfFrags, maxPossibleGenomicDist,
-    possibleIntraInRangeCount, possibleInterAllCount, interChrProb, baselineIntraChrProb)."""
-    if not resolution:
-        raise NotImplementedError("restriction-fragment mode (-r 0) is outside the accelerated path")
+    """fithic/fithic.py:561-793, both branches (fixed-size bins :596-689, restriction fragments with resolution 0
+    :691-778).  Returns (binStats, noOfFrags, maxPossibleGenomicDist, possibleIntraInRangeCount, possibleInterAllCount,
+    interChrProb, baselineIntraChrProb)."""
     lib = _capi.load()
     chroms = []
     for s in _session.values():
         chroms = s["chroms"]
         break
-    frags = fio.read_fragments(fragsfile, chroms, mappThres)
+    frags = fio.read_fragments(fragsfile, chroms, mappThres, keep_mids=not resolution)
     for s in _session.values():
         s["frags"] = frags
     st = _settings(resolution)
@@ -158,7 +160,10 @@ def generate_FragPairs(observedInterAllCount, observedInterAllSum, binStats, fra
         binStats[i][7] = int(bins["pairs7"][i])
         binStats[i][3] = float(bins["sumdist"][i])
     ok = frags.n_mappable > 0
-    maxd = float((frags.max_mid[ok] - resolution / 2).max()) if ok.any() else 0
+    if not resolution:
+        maxd = float(fp["maxPossibleGenomicDist"])  # the largest in-range fragment distance (:712)
+    else:
+        maxd = float((frags.max_mid[ok] - resolution / 2).max()) if ok.any() else 0
     interChrProb = 1.0 / observedInterAllCount if observedInterAllCount > 0 else 0
     pia = fp["possibleIntraAllCount"]
     return (binStats, fp["noOfFrags"], maxd, fp["possibleIntraInRangeCount"], fp["possibleInterAllCount"], interChrProb,

@@ -237,9 +237,14 @@ def write_inputs(outdir, contacts, frags, res, raw_bias=None, biases=None, prefi
                             contacts.cnt.tolist())))
     with gzip.open(fpath, "wt", compresslevel=1) as f:
         for ci, name in enumerate(frags.chroms):
+            if getattr(frags, "mids", None) is not None:  # restriction fragments: the mid points as they are
+                f.write("".join("%s\t0\t%d\t1\t1\n" % (name, m) for m in np.asarray(frags.mids[ci]).tolist()))
+                continue
             n = int(frags.n_mappable[ci])
             f.write("".join("%s\t0\t%d\t1\t1\n" % (name, k * res + res // 2) for k in range(n)))
     bpath = None
+    if raw_bias is None and biases is not None and getattr(biases, "sparse", False):
+        raw_bias = biases.values  # a sparse table lists only what the bias file held (out-of-bounds values already -1)
     if raw_bias is not None:
         bpath = os.path.join(outdir, prefix + ".bias.gz")
         with gzip.open(bpath, "wt", compresslevel=1) as f:

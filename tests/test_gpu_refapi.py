@@ -8,7 +8,7 @@ import pytest
 from sortedcontainers import SortedList
 
 from fithic_b200 import synth
-from tests.util import load_golden, load_kat, rel_err
+from tests.util import R0_CASES, load_golden, load_kat, rel_err
 
 torch = pytest.importorskip("torch")
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
@@ -22,7 +22,7 @@ def test_benjamini_hochberg_correction_docstring_example(lib):
         assert np.array_equal(np.array(got), np.array(want, dtype=np.float64), equal_nan=True)
 
 
-@pytest.mark.parametrize("name", ["intra_bias_LU_p2", "all_bias", "intra_p3"])
+@pytest.mark.parametrize("name", ["intra_bias_LU_p2", "all_bias", "intra_p3"] + R0_CASES)
 def test_reference_main_loop_on_refapi(lib, name, tmp_path):
     from fithic_b200 import refapi as F
     contacts, frags, biases, st, ref, extra = load_golden(name)
@@ -36,6 +36,7 @@ def test_reference_main_loop_on_refapi(lib, name, tmp_path):
     F.noOfBins = st.noOfBins
     F.logfile = str(tmp_path / "run.log")
     res, out = st.resolution, str(tmp_path / "lib")
+    tag = ".res%d" % res if res else ""  # restriction-fragment mode (resolution 0) drops the `.res` part (:851, :1171)
     F.set_resolution(cpath, res)
     outliersline, outliersdist = SortedList(), SortedList()
     for passNo in range(1, st.noOfPasses + 1):
@@ -57,7 +58,7 @@ def test_reference_main_loop_on_refapi(lib, name, tmp_path):
         assert len(binStats) == len(o["bins"])
         for i, b in enumerate(o["bins"]):
             assert (binStats[i][0], binStats[i][1], binStats[i][2], binStats[i][3], binStats[i][7]) == \
-                ((b["lb"], b["ub"]), b["pairs"], b["sumcc"], b["sumdist"], b["pairs"])
+                ((b["lb"], b["ub"]), b["pairs"], b["sumcc"], b["sumdist"], b["pairs7"])
         assert T_intra == o["possibleIntraInRangeCount"]
         assert sorted(x) == list(o["x"])
         assert r[0] == o["splineX"].tolist()
@@ -67,7 +68,7 @@ def test_reference_main_loop_on_refapi(lib, name, tmp_path):
         assert rel_err(last["p"], o["p"]) <= 1e-6 and rel_err(last["q"], o["q"]) <= 1e-6
         assert list(outliersline) == o["outliersline"].tolist()
         assert list(outliersdist) == o["outliersdist"].tolist()
-        assert os.path.exists(out + ".spline_pass%d.res%d.significances.txt.gz" % (passNo, res))
-        assert os.path.exists(out + ".fithic_pass%d.res%d.txt" % (passNo, res))
-    with gzip.open(out + ".spline_pass%d.res%d.significances.txt.gz" % (st.noOfPasses, res), "rt") as f:
+        assert os.path.exists(out + ".spline_pass%d%s.significances.txt.gz" % (passNo, tag))
+        assert os.path.exists(out + ".fithic_pass%d%s.txt" % (passNo, tag))
+    with gzip.open(out + ".spline_pass%d%s.significances.txt.gz" % (st.noOfPasses, tag), "rt") as f:
         assert len(f.readlines()) - 1 == extra["sig_nrows"]

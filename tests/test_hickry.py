@@ -55,6 +55,34 @@ def test_host_side_of_hickry_matches_reference_fixture(tmp_path):
         H.KRDevice(g["x"], g["y"], g["z"], n)  # no CPU fallback
 
 
+def write_files(g, tmp_path):
+    """The fixture's loci and lines as the two gz files HiCKRy reads (fragments: chr, 0, mid, hits, mappable)."""
+    chroms, mids = g["chroms"].tolist(), g["mids"].tolist()
+    fpath, ipath = str(tmp_path / "frags.gz"), str(tmp_path / "contacts.gz")
+    with gzip.open(fpath, "wt", compresslevel=1) as f:
+        f.write("".join("%s\t0\t%d\t1\t1\n" % (c, m) for c, m in zip(chroms, mids)))
+    with gzip.open(ipath, "wt", compresslevel=1) as f:
+        f.write("".join("%s\t%d\t%s\t%d\t%d\n" % (chroms[a], mids[a], chroms[b], mids[b], z) for a, b, z in
+                        zip(g["x"].tolist(), g["y"].tolist(), g["z"].tolist())))
+    return ipath, fpath
+
+
+def test_loader_numbers_loci_in_fragment_file_order(tmp_path):
+    """loadfastfithicInteractions (HiCKRy.py:18-52): files -> the (x, y, z, n) the fixture was captured with; a contact on a
+    locus the fragments file does not list is a KeyError like in the reference."""
+    pytest.importorskip("torch")
+    from fithic_b200 import hickry as H
+    g = load("hickry_pfal_10kb")
+    ipath, fpath = write_files(g, tmp_path)
+    (x, y, z, n), rev = H.loadfastfithicInteractions(ipath, fpath)
+    assert n == int(g["n"]) and rev == list(zip(g["chroms"].tolist(), g["mids"].tolist()))
+    assert np.array_equal(x, g["x"]) and np.array_equal(y, g["y"]) and np.array_equal(z, g["z"])
+    with gzip.open(ipath, "at") as f:
+        f.write("chrNowhere\t5\tchrNowhere\t15\t1\n")
+    with pytest.raises(KeyError):
+        H.loadfastfithicInteractions(ipath, fpath)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_kr_spmv_matches_scipy(lib):
@@ -107,3 +135,22 @@ def test_gpu_bias_matches_reference(lib, name):
     else:  # the reference stopped at its iteration cap: an unconverged, ill-conditioned iterate -- same path, looser match
         assert info["outer"] == int(g["outer"])
         assert rel < 1e-4
+
+
+@pytest.mark.gpu
+def test_cli_from_files_to_bias_file(lib, tmp_path, capsys):
+    """`HiCKRy.py -i -f -o -x` (HiCKRy.py:264-283) end to end: the bias file a `fithic -t` run would read."""
+    pytest.importorskip("torch")
+    from fithic_b200 import hickry as H
+    g = load("hickry_pfal_10kb")
+    ipath, fpath = write_files(g, tmp_path)
+    out = str(tmp_path / "bias.gz")
+    H.main(["-i", ipath, "-f", fpath, "-o", out, "-x", str(float(g["perc"]))])
+    rows = [line.split("\t") for line in gzip.open(out, "rt").read().splitlines()]
+    assert [(r[0], int(r[1])) for r in rows] == list(zip(g["chroms"].tolist(), g["mids"].tolist()))
+    got, ref = np.array([float(r[2]) for r in rows]), g["bias"]
+    assert np.array_equal(got == -1.0, ref == -1.0)
+    m = ref > 0
+    assert np.max(np.abs(got[m] - ref[m]) / ref[m]) < 1e-9
+    text = capsys.readouterr().out
+    assert "Creating sparse matrix..." in text and "WARNING" not in text  # mean and median inside (0.5, 2): no warning (:243-250)

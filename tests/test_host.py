@@ -417,6 +417,36 @@ def test_varsize_frag_pairs_bit_exact_against_reference_fixture(lib):
         assert [v for _, v in sorted(zip(x, y))] == list(r["y"])
 
 
+def test_refapi_generate_fragpairs_restriction_fragments(lib, tmp_path):
+    """refapi.generate_FragPairs / calculateProbabilities with resolution 0 (fithic/fithic.py:691-778, :851): the
+    reference's return tuple and binStats rows from files, first pass of the bundled HindIII case (host stages only)."""
+    from fithic_b200 import refapi as F, synth
+    from tests.util import R0_CASES
+    for name in R0_CASES:
+        contacts, frags, biases, st, ref, extra = load_golden(name)
+        cpath, fpath, bpath = synth.write_inputs(str(tmp_path), contacts, frags, 0, extra["bias_raw"], biases, prefix=name)
+        assert (bpath is None) == (biases is None)
+        F.reset()
+        F.distLowThres, F.distUpThres, F.mappThres, F.noOfBins = st.distLowThres, st.distUpThres, 1, st.noOfBins
+        F.interOnly, F.allReg, F.logfile = False, False, None
+        F.set_resolution(cpath, 0)
+        r = ref[0]
+        binStats = {i: [(b["lb"], b["ub"]), 0, b["sumcc"], 0, 0, 0, [], 0] for i, b in enumerate(r["bins"])}
+        (binStats, noOfFrags, maxd, T, possInter, interChrProb, base) = F.generate_FragPairs(
+            r["observedInterAllCount"], r["observedInterAllSum"], binStats, fpath, 0)
+        assert T == r["possibleIntraInRangeCount"] and noOfFrags == int(frags.n_mappable.sum())
+        assert st.distLowThres < maxd <= st.distUpThres
+        for i, b in enumerate(r["bins"]):
+            assert (binStats[i][1], binStats[i][7], binStats[i][3]) == (b["pairs"], b["pairs7"], b["sumdist"])
+        x, y, _ = F.calculateProbabilities({}, binStats, 0, str(tmp_path / (name + ".fithic_pass1")), r["N"])
+        assert sorted(x) == list(r["x"])
+        assert (tmp_path / (name + ".fithic_pass1.txt")).exists()
+        if bpath:
+            b = F.read_biases(bpath)
+            assert b.sparse and np.array_equal(b.values, biases.values) and np.array_equal(b.mids, biases.mids)
+    F.reset()
+
+
 def test_sparse_bias_layout_for_restriction_fragments(tmp_path):
     """-r 0: io.read_biases builds the grid-free layout (per chromosome the loci in ascending mid order, FIRST occurrence of
     a repeated locus wins, fithic/fithic.py:823-829); lookup_biases and the native writer find loci by binary search."""
