@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 3
+FHC_ABI_VERSION = 4
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
 N_SCALARS = 8
@@ -81,6 +81,16 @@ _SIGNATURES = {
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_sort_pairs_u64": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t,
                                            c_void_p]),
+    "fhc_merge_workspace_bytes": (c_size_t, [c_int64]),
+    "fhc_merge_components": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_void_p]),
+    "fhc_merge_select": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                         c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fhc_host_merge_components": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fhc_host_merge_select": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                              c_int32, c_int32, c_void_p, c_void_p]),
     "fhc_kr_partials": (c_int32, []),
     "fhc_kr_spmv": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fhc_kr_mul": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 3
+#define FHC_ABI_VERSION 4
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -295,6 +295,40 @@ int fhc_kr_gamma(const double *y, double alpha, const double *p, double bound, i
 int fhc_kr_axpy(double *y, double gamma, double alpha, const double *p, int64_t n, void *stream);
 int fhc_kr_update(double *y, double alpha, const double *p, double *rk, const double *w, const double *v, double *Z, int64_t n,
                   double *partial, void *stream);
+
+/* ---- merge-filter step ------------------------------------------------------------------------------
+ * fithic/utils/CombineNearbyInteraction.py (driven by fithic/utils/merge-filter.sh:22-23) groups the significant bin pairs
+ * of a chromosome into connected components (-c 8: both bins differ by <= 1; -c 4: by <= 1 in total; :313-333), reports the
+ * bounding box, the sum of counts and the share of box cells that hold a significant pair (:362-406), and keeps the pairs of
+ * a component in (q, -count, bin1, bin2) order unless both bins lie within `Neigh` bins of a pair already kept (:585-712).
+ * The reference tests all pairs of nodes (O(n^2)) and walks every box cell by cell; here the pairs are sorted once.
+ *
+ * Inputs [dev], one element per input LINE (intra-chromosomal lines only, in file order): chr = rank of the chromosome in
+ * the output order (< 65536), b1 <= b2 the bin numbers int(mid + res/2) / res (1 <= bin < 2^24 - 1), cc the count
+ * (0 <= cc < 2^31), q the q-value.  "Entry" i below is the i-th line in (chr, b1, b2) order; a repeated bin pair keeps the
+ * values of its first line (:306) and its later lines get label -1.
+ *   fhc_merge_components   keys[i] = chr << 48 | b1 << 24 | b2, order[i] = line of entry i, label[i] = ROOT entry of the
+ *                          component (its smallest entry) or -1; indexed by root entry: size (nodes), first_line (smallest
+ *                          line), box[4 i ..] = min b1, max b1, min b2, max b2, sum_cc, have = nodes of any component inside
+ *                          the box.  Synchronises the stream (it reads an overflow flag back).
+ *   fhc_merge_select       ranked[w] = entries grouped by component and, inside one, in the order of the reference's heap
+ *                          (:611-625; sort_order 1 = `-s 1`: descending q); keep[w] = 1 for the pairs that survive the
+ *                          neighbourhood rule, with the top-K % cut of :458-577 when 0 < top_pct < 100 (top_pct 100: :585-712)
+ *   fhc_host_merge_*       the same per-entry code run serially on HOST arrays (tests; no GPU involved)
+ * workspace: fhc_merge_workspace_bytes(n) for either call. */
+size_t fhc_merge_workspace_bytes(int64_t n);
+int fhc_merge_components(const int32_t *chr, const int32_t *b1, const int32_t *b2, const int64_t *cc, int64_t n, int32_t conn,
+                         uint64_t *keys, uint32_t *order, int32_t *label, int32_t *size, uint32_t *first_line, int32_t *box,
+                         int64_t *sum_cc, int64_t *have, void *workspace, size_t workspace_bytes, void *stream);
+int fhc_merge_select(const uint64_t *keys, const uint32_t *order, const int32_t *label, const int32_t *size, const int64_t *cc,
+                     const double *q, int64_t n, int32_t top_pct, int32_t neigh, int32_t sort_order, uint32_t *ranked,
+                     uint8_t *keep, void *workspace, size_t workspace_bytes, void *stream);
+int fhc_host_merge_components(const int32_t *chr, const int32_t *b1, const int32_t *b2, const int64_t *cc, int64_t n,
+                              int32_t conn, uint64_t *keys, uint32_t *order, int32_t *label, int32_t *size,
+                              uint32_t *first_line, int32_t *box, int64_t *sum_cc, int64_t *have);
+int fhc_host_merge_select(const uint64_t *keys, const uint32_t *order, const int32_t *label, const int32_t *size,
+                          const int64_t *cc, const double *q, int64_t n, int32_t top_pct, int32_t neigh, int32_t sort_order,
+                          uint32_t *ranked, uint8_t *keep);
 
 /* ---- text boundary (host) ---------------------------------------------------------------------------------------------
  * Native replacements of the two text loops that dominate the reference's wall time once the kernels are fast:

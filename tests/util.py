@@ -179,3 +179,30 @@ def cut_hist_numpy(p, p_cut0):
     v = p[ok]
     b = np.where(v > 0, np.minimum(v.view(np.uint64) >> np.uint64(47), np.uint64(_capi.BH_CUT_BUCKETS - 1)), 0)
     return np.bincount(b.astype(np.int64), minlength=_capi.BH_CUT_BUCKETS).astype(np.uint64)
+
+
+def merge_components_host(chr_rank, b1, b2, cc, q, conn, top_pct, neigh, sort_order):
+    """fhc_host_merge_*: the per-entry code of csrc/merge.cu run serially on host arrays (what the CPU tests check)."""
+    from fithic_b200 import _capi
+    lib = _capi.load()
+    n = len(b1)
+    m = max(n, 1)
+    a = dict(keys=np.zeros(m, np.uint64), order=np.zeros(m, np.uint32), label=np.zeros(m, np.int32), size=np.zeros(m, np.int32),
+             first_line=np.zeros(m, np.uint32), box=np.zeros(4 * m, np.int32), sum_cc=np.zeros(m, np.int64),
+             have=np.zeros(m, np.int64), ranked=np.zeros(m, np.uint32), keep=np.zeros(m, np.uint8))
+    ins = [np.ascontiguousarray(chr_rank, np.int32), np.ascontiguousarray(b1, np.int32), np.ascontiguousarray(b2, np.int32),
+           np.ascontiguousarray(cc, np.int64)]
+    qq = np.ascontiguousarray(q, np.float64)
+    p = _capi.dptr
+    _capi.check(lib.fhc_host_merge_components(p(ins[0]), p(ins[1]), p(ins[2]), p(ins[3]), n, int(conn), p(a["keys"]),
+                                              p(a["order"]), p(a["label"]), p(a["size"]), p(a["first_line"]), p(a["box"]),
+                                              p(a["sum_cc"]), p(a["have"])))
+    select = 0 < top_pct <= 100
+    if select:
+        _capi.check(lib.fhc_host_merge_select(p(a["keys"]), p(a["order"]), p(a["label"]), p(a["size"]), p(ins[3]), p(qq), n,
+                                              int(top_pct), int(neigh), int(sort_order), p(a["ranked"]), p(a["keep"])))
+    out = {k: v[:n] for k, v in a.items() if k != "box"}
+    out["box"] = a["box"][:4 * n].reshape(-1, 4)
+    if not select:
+        del out["ranked"], out["keep"]
+    return out
