@@ -137,6 +137,61 @@ def test_union_find_on_long_chains_and_blocks(lib):
     assert len(set(zip(lab[ys, xs].tolist(), by_line.tolist()))) == ncomp  # the two labellings are the same partition
 
 
+def random_case(seed, nmax):
+    """Random rows on a small grid (many ties, repeated and mirrored pairs, inter lines, q = 0) and a random option set,
+    legal or not (-c 5 adds no edges, -p 101 prints nothing, -n -1 keeps everything)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, nmax))
+    res = int(rng.choice([2, 1000, 5000, 40000]))
+    nb = int(rng.integers(3, 60))
+    names = ["chr" + str(i) for i in rng.permutation(12)[: int(rng.integers(1, 5))]]
+    c1 = rng.choice(names, n)
+    c2 = np.where(rng.random(n) < 0.9, c1, rng.choice(names, n))
+    a = rng.integers(0, nb, n)
+    b = np.clip(a + rng.integers(-3, 8, n), 0, nb - 1)
+    q = rng.choice([0.0, 1e-30, 2.5e-12, 1e-7, 3e-4, 0.004, 0.5], n)
+    rows = dict(chr1=c1.astype(object), chr2=c2.astype(object), mid1=(a * res + res // 2).astype(np.float64),
+                mid2=(b * res + res // 2).astype(np.float64), cc=rng.integers(0, 5, n).astype(np.int64),
+                p=q * rng.choice([0.01, 0.1, 1.0], n), q=q)
+    kw = dict(conn=int(rng.choice([8, 8, 4, 5])), top_pct=int(rng.choice([100, 100, 0, 1, 25, 50, 99, 101, -3])),
+              neigh=int(rng.choice([2, 0, 1, 3, -1])), sort_order=int(rng.choice([0, 0, 1])))
+    return rows, res, kw
+
+
+def oracle_text(rows, res, kw):
+    return M.merge_rows(rows["chr1"].tolist(), rows["mid1"].tolist(), rows["chr2"].tolist(), rows["mid2"].tolist(),
+                        rows["cc"].tolist(), rows["p"].tolist(), rows["q"].tolist(), res, **kw)
+
+
+def test_library_code_on_host_against_oracle_on_random_rows(lib):
+    from fithic_b200 import merge as G
+    from tests.util import merge_components_host
+    for seed in range(60):
+        rows, res, kw = random_case(seed, 1200)
+        assert G.merge_rows(rows, res, components=merge_components_host, **kw) == oracle_text(rows, res, kw), (seed, kw)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/fithic/utils/CombineNearbyInteraction.py"),
+                    reason="needs the reference checkout (build container only)")
+def test_oracle_against_the_reference_script_on_random_rows(tmp_path):
+    """Container only: the unmodified script run on random rows and option sets (120 further seeds were run once by hand)."""
+    import subprocess
+    import sys
+    for seed in range(1000, 1006):
+        rows, res, kw = random_case(seed, 300)
+        src = str(tmp_path / ("in%d.gz" % seed))
+        with gzip.open(src, "wt") as f:
+            f.write("".join("%s\t%d\t%s\t%d\t%d\t%r\t%r\t1\t1\t1\n" % r for r in
+                            zip(rows["chr1"].tolist(), rows["mid1"].astype(np.int64).tolist(), rows["chr2"].tolist(),
+                                rows["mid2"].astype(np.int64).tolist(), rows["cc"].tolist(), rows["p"].tolist(),
+                                rows["q"].tolist())))
+        out = str(tmp_path / ("o%d" % seed) / "m.gz")
+        subprocess.run([sys.executable, "/root/reference/fithic/utils/CombineNearbyInteraction.py", "-i", src, "-H", "0", "-r",
+                        str(res), "-o", out, "-c", str(kw["conn"]), "-p", str(kw["top_pct"]), "-n", str(kw["neigh"]), "-s",
+                        str(kw["sort_order"])], check=True, stdout=subprocess.DEVNULL)
+        assert gzip.open(out, "rt").read() == oracle_text(rows, res, kw), (seed, kw)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,variant", ALL, ids=["%s-%s" % nv for nv in ALL])
