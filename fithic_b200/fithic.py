@@ -8,12 +8,9 @@ Differences that are deliberate: `-r 0` (restriction-fragment mode) and `-v` (pl
 and are refused / ignored with a message; everything numeric is computed on the GPU (no CPU fallback).
 """
 import argparse
-import gzip
 import os
 import sys
 import time
-
-import numpy as np
 
 from . import __version__
 from . import io as fio

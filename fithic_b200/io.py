@@ -4,7 +4,6 @@ Formats follow the reference (fithic/fithic.py:413, :580-590, :807-832, :1166-12
 work (the reference spends most of its wall time here); the arrays they produce are what the kernels consume.
 """
 import gzip
-import io as _io
 import math
 import os
 

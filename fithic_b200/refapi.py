@@ -8,9 +8,6 @@ settings (distLowThres, distUpThres, mappThres, interOnly, allReg, biasLowerBoun
 on this module the way main() sets its globals.  Contacts are parsed and copied to the GPU once per file and stay
 there across calls and passes.
 """
-import math
-import os
-
 import numpy as np
 import torch
 

@@ -5,8 +5,6 @@ utils/createFitHiCFragments-fixedsize.py:57-76 (start = k*res, mid = start + res
 Contacts: locus pairs (i <= j) on one chromosome with P(j - i = k) ~ 1/(k+1); count = 1 + Poisson(lam0 (k+1)^-1.08 b_i b_j).
 `numpy` generator for tests (small n, bit reproducible), `torch` generator on the GPU for the 300 M pair bench input.
 """
-import math
-
 import numpy as np
 
 from .engine import Biases, Contacts, Fragments

@@ -1,6 +1,5 @@
 """Time the spline pass on the bench input under the library's experiment switches (read per call from the environment):
 per-kernel device ms for each variant.  One process, one data set.  Usage: python scripts/k3_variants.py [pairs]"""
-import json
 import os
 import sys
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from fithic_b200 import _capi, synth
-from fithic_b200.engine import Biases, Contacts, Engine, Fragments, Settings
+from fithic_b200.engine import Biases, Contacts, Engine, Settings
 from oracle import fithic_oracle as O
 from tests.test_gpu_pipeline import run_engine
 from tests.util import compare_pass, oracle_inputs

@@ -1,11 +1,9 @@
 """GPU parity against fixtures captured from the UNMODIFIED reference (tests/golden/, no oracle in the loop)."""
 import gzip
-import os
 
 import numpy as np
 import pytest
 
-from fithic_b200 import io as fio
 from fithic_b200 import synth
 from tests.test_gpu_pipeline import run_engine
 from tests.util import GOLDEN_CASES, R0_CASES, REAL_CASES, compare_pass, load_golden, load_kat

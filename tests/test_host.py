@@ -13,7 +13,7 @@ from fithic_b200 import _capi, synth
 from fithic_b200 import io as fio
 from fithic_b200.engine import Settings, calculate_probabilities, fit_spline, frag_pairs, make_bins
 from oracle import fithic_oracle as O
-from tests.util import GOLDEN_CASES, REAL_CASES, cut_hist_numpy, load_golden, oracle_inputs
+from tests.util import GOLDEN_CASES, REAL_CASES, cut_hist_numpy, load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
