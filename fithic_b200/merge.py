@@ -281,7 +281,15 @@ def merge_filter(inputFile, resolution, outputFile, fdr, log=None, components=No
 
 
 def main(argv=None):
-    o = parse_args(sys.argv[1:] if argv is None else argv)
+    """`python -m fithic_b200.merge -i ... -o ... -r ...` is CombineNearbyInteraction.py; with positional arguments
+    `inputFile resolution outputFile fdr [utilityFolder]` it is merge-filter.sh (the last argument is accepted and ignored)."""
+    argv = sys.argv[1:] if argv is None else list(argv)
+    if argv and not argv[0].startswith("-"):
+        if len(argv) not in (4, 5):
+            sys.exit("usage: python -m fithic_b200.merge inputFile resolution outputFile fdr [utilityFolder]")
+        merge_filter(argv[0], int(argv[1]), argv[2], float(argv[3]), log=print)
+        return
+    o = parse_args(argv)
     combine_nearby_interactions(o.InpFile, o.OutFile, o.resolution, o.headerInp, o.connectivity_rule, o.TopPctElem,
                                 o.NeighborHoodBin, o.SortOrder)
 

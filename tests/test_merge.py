@@ -104,6 +104,23 @@ def test_reader_and_refusals(tmp_path):
             G.merge_rows(rows, 5000)
 
 
+def test_merge_filter_command_line_with_fdr(lib, tmp_path, monkeypatch):
+    """merge-filter.sh's arguments: header dropped, rows with q <= fdr kept (awk's numeric compare), default options."""
+    from fithic_b200 import merge as G
+    from tests.util import merge_components_host
+    monkeypatch.setattr(G, "components_device", merge_components_host)  # no GPU in the CPU suite
+    z = load("merge_synth")
+    full, out = str(tmp_path / "sig.gz"), str(tmp_path / "deep" / "dir" / "merged.gz")
+    write_rows(z, full, header=True)
+    G.main([full, str(int(z["res"])), out, "1e-7"])
+    keep = z["q"] <= 1e-7
+    want = M.merge_rows(z["chr1"][keep].tolist(), z["mid1"][keep].tolist(), z["chr2"][keep].tolist(), z["mid2"][keep].tolist(),
+                        z["cc"][keep].tolist(), z["p"][keep].tolist(), z["q"][keep].tolist(), int(z["res"]))
+    assert gzip.open(out, "rt").read() == want and want.count("\n") > 10
+    with pytest.raises(SystemExit):
+        G.main([full, "5000"])
+
+
 def test_union_find_on_long_chains_and_blocks(lib):
     """Shapes the data sets do not have: one 20000-node diagonal chain (a deep union-find tree without path halving), a
     filled block, isolated nodes, a repeated pair; components, boxes and the box census against a scipy labelling."""
@@ -238,4 +255,7 @@ def test_gpu_cli_and_merge_filter_on_files(lib, tmp_path):
     G.main(["-i", full, "-r", str(int(z["res"])), "-o", out, "-c", "4", "-n", "1"])
     assert gzip.open(out, "rt").read() == z["out_c4_n1"].tobytes().decode()
     G.merge_filter(full, int(z["res"]), out, 1.0)
+    assert gzip.open(out, "rt").read() == z["out_default"].tobytes().decode()
+    os.remove(out)
+    G.main([full, str(int(z["res"])), out, "1.0", "unused/utility/folder/"])  # merge-filter.sh's positional arguments
     assert gzip.open(out, "rt").read() == z["out_default"].tobytes().decode()
