@@ -1,7 +1,8 @@
 """Per-CUDA-source-line cost of one kernel: joins the SASS page of an .ncu-rep (instructions executed, stall samples, active
 threads per instruction) with the line table of the object file the report was taken from (nvdisasm -g), heaviest lines
 first.  Run on the CPU box; the object must be the build that ran.
-Usage: python scripts/ncu_source.py REPORT.ncu-rep OBJECT.o KERNEL_REGEX [top_n]"""
+Usage: python scripts/ncu_source.py REPORT.ncu-rep OBJECT.o KERNEL_REGEX [top_n] [exec]   (exec: heaviest by instructions
+executed instead of by stall samples)"""
 import collections
 import csv
 import io
@@ -13,6 +14,7 @@ import tempfile
 
 rep, obj, kern = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by_exec = len(sys.argv) > 5 and sys.argv[5] == "exec"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -66,7 +68,7 @@ for r, l in zip(data, lines):
 print("%s: %d warp-level instructions executed, %d stall samples" % (name.split("(")[0], tot_ex, tot_s))
 print("%7s %7s %6s  %s" % ("exec %", "samp %", "lanes", "source line"))
 src_cache = {}
-for l, (ex, s, th) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for l, (ex, s, th) in sorted(agg.items(), key=lambda kv: -kv[1][0 if by_exec else 1])[:top]:
     f, n = l.rsplit(":", 1) if ":" in l else (l, "0")
     path = paths.get(f, os.path.join(os.path.dirname(obj), "..", "csrc", f))
     if f not in src_cache:
