@@ -26,26 +26,21 @@ MAX_BIN = (1 << 24) - 2
 
 
 def parse_args(args):
-    """CombineNearbyInteraction.py:83-109 (same flags, defaults and help)."""
-    parser = argparse.ArgumentParser(description="Check the help flag")
-    parser.add_argument("-i", "--InpFile", help="Input gzipped interaction Fit-Hi-C output file.", required=True)
-    parser.add_argument("-H", "--headerInp", dest="headerInp", type=int,
-                        help="If 1, indicates that input interaction file has a header line (such as field names). Default 1.",
-                        default=1)
-    parser.add_argument("-o", "--OutFile", help="Output merged gzipped interaction file.", required=True)
-    parser.add_argument("-r", "--resolution", help="Resolution of Fit-Hi-C run.", required=True)
-    parser.add_argument("-c", "--conn", help="Rule of connectivity (8 or 4). Default is 8.", required=False, default=8, type=int,
-                        dest="connectivity_rule")
+    """The flags, destinations, types and defaults of CombineNearbyInteraction.py:83-109."""
+    parser = argparse.ArgumentParser(description="Merge nearby significant Fit-Hi-C interactions (connected components) on the GPU")
+    parser.add_argument("-i", "--InpFile", required=True, help="significances file (.gz or plain text)")
+    parser.add_argument("-H", "--headerInp", dest="headerInp", type=int, default=1, help="1: the input has a header line (default)")
+    parser.add_argument("-o", "--OutFile", required=True, help="merged interactions, gzipped")
+    parser.add_argument("-r", "--resolution", required=True, help="bin size of the Fit-Hi-C run")
+    parser.add_argument("-c", "--conn", dest="connectivity_rule", type=int, default=8, required=False,
+                        help="8 (default) or 4: which neighbouring bin pairs are connected")
     parser.add_argument("-p", "--percent", dest="TopPctElem", type=int, default=100,
-                        help="Percentage of elements to be selected from each connected component. Default: 100, means all "
-                             "loops would be considered. If specified as 0, only the most significant loops from each "
-                             "component would be selected.")
+                        help="100 (default): every loop of a component is a candidate; 0: only the most significant one; "
+                             "x in between: the top x %% by q-value")
     parser.add_argument("-n", "--Neigh", dest="NeighborHoodBin", type=int, default=2,
-                        help="Positive integer (default: 2 with 5 Kb bin size) means that if a loop is included in the final "
-                             "set, loops involving within 2x2 neighborhood of both the bins would be discarded.")
+                        help="a candidate is dropped when both its bins lie within this many bins of a loop already kept")
     parser.add_argument("-s", "--order", dest="SortOrder", type=int, default=0,
-                        help="Binary variable indicating the sorting order of the given significance values. Default 0, means "
-                             "sorting is done by ascending order. If specified 1, sorting is done by descending (reverse) order.")
+                        help="0 (default): smaller significance values are better; 1: larger are better")
     return parser.parse_args(args)
 
 
