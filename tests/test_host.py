@@ -376,6 +376,54 @@ def test_list_pipeline_arithmetic_matches_oracle(lib, N):
     assert np.max(np.abs(got[k0] - want[k0]) / np.abs(want[k0])) < 2e-15
 
 
+def test_known_deviation_where_glibc_log_is_not_correctly_rounded(lib):
+    """lbeta cancels two terms of size N log N, so one ulp of log(N - c + 1) moves the p-value by ulp(lgam(N)) ~ 4e-6 ... 8e-6
+    (SURVEY F8).  The table kernel evaluates log correctly rounded; glibc's log (what scipy's cephes calls) is not, for about
+    one argument in 15,000 at some magnitudes.  Those entries -- and only those -- differ from scipy by that one ulp; the
+    reference itself would change there with another libm.  Characterised here so that it is a known, bounded deviation."""
+    import decimal
+    import math
+    ol = O._lib()
+    ol.oracle_lbeta.restype = ctypes.c_double
+    ol.oracle_lbeta.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.fhc_host_log_cr.restype = ctypes.c_double
+    lib.fhc_host_log_cr.argtypes = [ctypes.c_double]
+    decimal.getcontext().prec = 60
+    N = 300_000_000
+    differ = [c for c in range(1, 40_001) if lib.fhc_host_lbeta(float(c), float(N - c + 1)) !=
+              ol.oracle_lbeta(float(c), float(N - c + 1))]
+    assert len(differ) <= 6  # 3 with the glibc of this image (12660, 17560, 30040); 0 at N = 9e8, the bench workload
+    for c in differ:
+        x = N - c + 1
+        ours, libm = lib.fhc_host_log_cr(float(x)), math.log(float(x))
+        assert ours != libm  # the whole difference comes from log(b)
+        exact = decimal.Decimal(x).ln()
+        assert abs(decimal.Decimal(ours) - exact) < abs(decimal.Decimal(libm) - exact)  # and ours is the rounded one
+        d = abs(lib.fhc_host_lbeta(float(c), float(N - c + 1)) - ol.oracle_lbeta(float(c), float(N - c + 1)))
+        assert d <= 2 * math.ulp(N * math.log(N))  # one rounding step of the big terms: 3.8e-6 here
+
+
+def test_known_deviation_for_huge_counts_at_the_mode(lib):
+    """Where the observed count sits on its expectation (prior ~ count / N), cephes evaluates the swapped continued fraction
+    and stops after 300 iterations; from counts of ~2e5 on that is not enough (1e-3 off at 1e6).  K3 sums the short lower
+    tail instead (cephes_dev.cuh), which stays at the true value.  Up to counts of 1e5 -- beyond any Hi-C bin pair -- the two
+    agree within the 1e-6 contract; above, K3 follows Boost's binomial survival function, not cephes' truncated fraction."""
+    import scipy.special as sp
+    import scipy.stats as ss
+    N = 900_000_000
+    for c in (100, 1000, 10_000, 30_000, 100_000):
+        for r in (0.5, 0.9, 0.99, 0.999, 1.0, 1.001, 1.01, 1.1, 2.0):
+            x = r * c / N
+            w, g = float(sp.bdtrc(c - 1, N, x)), lib.fhc_host_bdtrc_lists(c, N, x)
+            assert abs(g - w) <= 1e-6 * abs(w) or (abs(w) < 1e-290 and abs(g) < 1e-290), (c, r, w, g)
+    for c in (300_000, 1_000_000, 2_000_000):
+        x = c / N
+        cephes, ours, boost = float(sp.bdtrc(c - 1, N, x)), lib.fhc_host_bdtrc_lists(c, N, x), float(ss.binom.sf(c - 1, N, x))
+        assert abs(ours - boost) <= 1e-5 * boost  # (the lbeta rounding noise both implementations share)
+        assert abs(cephes - boost) > abs(ours - boost)
+    assert abs(float(sp.bdtrc(10 ** 6 - 1, N, 10 ** 6 / N)) - float(ss.binom.sf(10 ** 6 - 1, N, 10 ** 6 / N))) > 1e-3 * 0.5
+
+
 def test_chr_runs_round_trip():
     from fithic_b200.engine import chr_runs_of
     rng = np.random.default_rng(5)
