@@ -41,6 +41,7 @@ _SIGNATURES = {
     "fhc_host_frag_pairs_varsize": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int32,
                                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_host_fill_f64": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int32]),
+    "fhc_host_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_int32]),
     "fhc_spline_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_spline_table": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_double, c_double, c_int32,
                                          c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

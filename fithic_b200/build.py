@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))] + [
         os.path.join(HERE, "..", "include", "fithic_b200.h"), os.path.abspath(__file__)]
     hdr_t = max(os.path.getmtime(h) for h in hdrs)
 

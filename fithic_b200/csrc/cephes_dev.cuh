@@ -182,84 +182,9 @@ double log_cr(double x) {
     return rn_add(r.hi, r.lo);
 }
 
-// ---- cephes lgam / lbeta restated (Moshier, cephes/cprob/gamma.c; scipy xsf/cephes/{gamma,beta}.h) -------------------
-FHC_HD double horner(double x, const double *c, int n) {  // cephes polevl
-    double a = c[0];
-    for (int i = 1; i <= n; ++i) a = rn_add(rn_mul(a, x), c[i]);
-    return a;
-}
-FHC_HD double horner1(double x, const double *c, int n) {  // cephes p1evl (implicit leading 1)
-    double a = rn_add(x, c[0]);
-    for (int i = 1; i < n; ++i) a = rn_add(rn_mul(a, x), c[i]);
-    return a;
-}
-
-FHC_HD double lgam_pos(double x) {  // x > 0 finite (bdtrc only reaches positive arguments)
-    const double A[5] = {8.11614167470508450300E-4, -5.95061904284301438324E-4, 7.93650340457716943945E-4,
-                         -2.77777777730099687205E-3, 8.33333333333331927722E-2};
-    const double B[6] = {-1.37825152569120859100E3, -3.88016315134637840924E4, -3.31612992738871184744E5,
-                         -1.16237097492762307383E6, -1.72173700820839662146E6, -8.53555664245765465627E5};
-    const double C[6] = {-3.51815701436523470549E2, -1.70642106651881159223E4, -2.20528590553854454839E5,
-                         -1.13933444367982507207E6, -2.53252307177582951285E6, -2.01889141433532773231E6};
-    if (x < 13.0) {
-        double z = 1.0, p = 0.0, u = x;
-        while (u >= 3.0) {
-            p = rn_sub(p, 1.0);
-            u = rn_add(x, p);
-            z = rn_mul(z, u);
-        }
-        while (u < 2.0) {
-            if (u == 0.0) return INFINITY;
-            z = rn_div(z, u);
-            p = rn_add(p, 1.0);
-            u = rn_add(x, p);
-        }
-        if (z < 0.0) z = -z;
-        if (u == 2.0) return log_cr(z);
-        p = rn_sub(p, 2.0);
-        x = rn_add(x, p);
-        p = rn_div(rn_mul(x, horner(x, B, 5)), horner1(x, C, 6));
-        return rn_add(log_cr(z), p);
-    }
-    double q = rn_add(rn_sub(rn_mul(rn_sub(x, 0.5), log_cr(x)), x), kLS2PI);
-    if (x > 1.0e8) return q;
-    const double p = rn_div(1.0, rn_mul(x, x));
-    if (x >= 1000.0)
-        q = rn_add(q, rn_div(rn_add(rn_mul(rn_sub(rn_mul(7.9365079365079365079365e-4, p), 2.7777777777777777777778e-3), p),
-                                    0.0833333333333333333333),
-                             x));
-    else
-        q = rn_add(q, rn_div(horner(p, A, 4), x));
-    return q;
-}
-
-// lbeta(a, b), a, b > 0.  (For a + b <= MAXGAM cephes divides Gamma values instead; that differs from the lgam form
-// by ~1e-15 relative and only occurs for N <= 170, so the lgam form is used throughout.)
-#if defined(__CUDA_ARCH__)
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-double lbeta_cephes(double a, double b) {
-    if (a < b) {
-        const double t = a;
-        a = b;
-        b = t;
-    }
-    if (a > kASYMP * b && a > kASYMP) {  // lbeta_asymp: a >> b
-        double r = lgam_pos(b);
-        r = rn_sub(r, rn_mul(b, log_cr(a)));
-        r = rn_add(r, rn_div(rn_mul(b, rn_sub(1.0, b)), rn_mul(2.0, a)));
-        r = rn_add(r, rn_div(rn_mul(rn_mul(b, rn_sub(1.0, b)), rn_sub(1.0, rn_mul(2.0, b))), rn_mul(rn_mul(12.0, a), a)));
-        r = rn_add(r, rn_div(rn_mul(rn_mul(rn_mul(-b, b), rn_sub(1.0, b)), rn_sub(1.0, b)),
-                             rn_mul(rn_mul(rn_mul(12.0, a), a), a)));
-        return r;
-    }
-    double y = lgam_pos(rn_add(a, b));
-    y = rn_sub(lgam_pos(b), y);
-    y = rn_add(lgam_pos(a), y);
-    return y;
-}
+#define FHC_LOG_FN log_cr
+#include "cephes_lbeta.inc"
+#undef FHC_LOG_FN
 
 #if defined(__CUDACC__)
 // ---- continued fractions of the incomplete beta function, division free ---------------------------------------------

@@ -136,6 +136,11 @@ int fhc_lbeta_table(int64_t N, double *tab, int64_t ntab, void *stream);
 /* Host builds of the same source the device table kernel runs (log evaluated in double-double and rounded once, cephes
  * lgam/lbeta with explicit round-to-nearest steps): lets CPU-only tests pin the table arithmetic.  Not a product path. */
 double fhc_host_log_cr(double x);
+/* fhc_lbeta_table on the HOST with the C library's log -- the one scipy's cephes calls on this machine -- instead of the
+ * correctly rounded log of the device kernel: identical except where the library's log is misrounded (about one argument in
+ * 15,000 at some magnitudes), where it follows scipy by one ulp of lgam(N) (4e-6 ... 8e-6 in p).  A caller that wants
+ * scipy's value there too uploads this table instead of running fhc_lbeta_table (engine: FHC_LBETA_TABLE=host). */
+int fhc_host_lbeta_table(int64_t N, double *tab, int64_t ntab, int32_t nthreads);
 double fhc_host_lbeta(double a, double b);
 /* scipy.special.bdtrc(count - 1, N, prior) evaluated on the host by the source the work-list kernels of K3 run
  * (classification, division-free continued fraction / tail sum, prefactor with folded divisions), and its 1 - exp(y). */

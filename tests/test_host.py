@@ -403,6 +403,23 @@ def test_known_deviation_where_glibc_log_is_not_correctly_rounded(lib):
         assert d <= 2 * math.ulp(N * math.log(N))  # one rounding step of the big terms: 3.8e-6 here
 
 
+def test_host_lbeta_table_with_the_c_library_log_is_scipys(lib):
+    """fhc_host_lbeta_table: the same cephes source with the C library's log -- bit for bit the oracle's (= scipy's) lbeta,
+    the entries of the previous test included; elsewhere identical to the device table's arithmetic."""
+    ol = O._lib()
+    ol.oracle_lbeta.restype = ctypes.c_double
+    ol.oracle_lbeta.argtypes = [ctypes.c_double, ctypes.c_double]
+    for N, ntab in ((300_000_000, 40_001), ((1 << 31) - 1, 40_001), (900_000_000, 5000), (4219169, 3000), (1000, 1200)):
+        tab = np.full(ntab, -7.0)
+        assert lib.fhc_host_lbeta_table(N, _capi.dptr(tab), ntab, 4) == 0
+        assert np.isnan(tab[0]) and (ntab <= N + 1 or np.isnan(tab[N + 1:]).all())
+        hi = min(ntab, N + 1)
+        want = np.array([ol.oracle_lbeta(float(c), float(N - c + 1)) for c in range(1, hi)])
+        assert np.array_equal(tab[1:hi], want), N
+        ours = np.array([lib.fhc_host_lbeta(float(c), float(N - c + 1)) for c in range(1, hi)])
+        assert (ours != tab[1:hi]).sum() <= 6  # the misrounded-log entries (3 and 4 for the first two N, 0 otherwise)
+
+
 def test_known_deviation_for_huge_counts_at_the_mode(lib):
     """Where the observed count sits on its expectation (prior ~ count / N), cephes evaluates the swapped continued fraction
     and stops after 300 iterations; from counts of ~2e5 on that is not enough (1e-3 off at 1e6).  K3 sums the short lower
