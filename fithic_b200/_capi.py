@@ -12,12 +12,28 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 4
+FHC_ABI_VERSION = 5
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
- S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES) = range(8)
-N_SCALARS = 8
+ S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES, S_NONPOS_LINES) = range(9)
+N_SCALARS = 9
 MODE_INTRA_ONLY, MODE_INTER_ONLY, MODE_ALL = 0, 1, 2
 BH_CUT_BUCKETS = 32768
+
+
+class StageIO(ctypes.Structure):
+    """fhc_stage_io of include/fithic_b200.h (the host stage between K1 and K3)."""
+    _fields_ = [
+        ("k1buf", c_void_p), ("D", c_int64), ("grid", c_int32), ("noOfBins", c_int32), ("L", c_int64), ("U", c_int64),
+        ("chr_n", c_void_p), ("chr_maxmid", c_void_p), ("nchr", c_int32), ("want_spline", c_int32), ("nthreads", c_int32),
+        ("pad0", c_int32), ("dec", c_void_p), ("lbeta_tab", c_void_p * 2), ("lbeta_cap", c_int64 * 2),
+        ("dists", c_void_p), ("sums", c_void_p), ("nseen", c_int64),
+        ("bin_lb", c_void_p), ("bin_ub", c_void_p), ("bin_sumcc", c_void_p), ("bin_pairs", c_void_p),
+        ("bin_sumdist", c_void_p), ("x_bins", c_void_p), ("y_bins", c_void_p), ("xs", c_void_p), ("ys", c_void_p),
+        ("t", c_void_p), ("c", c_void_p), ("splineX", c_void_p), ("table", c_void_p), ("lut", c_void_p), ("m", c_int64),
+        ("totals", c_int64 * 4), ("lbeta_ntab", c_int64 * 2),
+        ("nb", c_int32), ("nt", c_int32), ("ier", c_int32), ("calls", c_int32), ("status", c_int32), ("bad_index", c_int32),
+        ("fp", c_double), ("timings", c_double * 8),
+    ]
 
 
 class FithicB200Error(RuntimeError):
@@ -33,6 +49,8 @@ _SIGNATURES = {
     "fhc_launch_count": (c_int64, []),
     "fhc_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "fhc_profile_collect": (ctypes.c_int, [c_char_p, c_size_t]),
+    "fhc_copy_async": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fhc_stream_synchronize": (ctypes.c_int, [c_void_p]),
     "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                           c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_host_make_bins": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -42,6 +60,11 @@ _SIGNATURES = {
                                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_host_fill_f64": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int32]),
     "fhc_host_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_int32]),
+    "fhc_host_stage": (ctypes.c_int, [ctypes.POINTER(StageIO), c_int32]),
+    "fhc_host_pool_prewarm": (ctypes.c_int, [c_int32]),
+    "fhc_host_pool_selftest": (c_double, [c_int32, c_int32, c_int32, c_void_p]),
+    "fhc_host_curfit": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "fhc_spline_workspace_bytes": (c_size_t, [c_int64]),
     "fhc_spline_table": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_double, c_double, c_int32,
                                          c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

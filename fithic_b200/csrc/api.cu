@@ -96,3 +96,18 @@ extern "C" int fhc_profile_collect(char *buf, size_t buf_bytes) {
     memcpy(buf, out.c_str(), out.size() + 1);
     return (int)out.size();
 }
+
+// ---- plumbing for hosts without a CUDA binding of their own ------------------------------------------------------------
+// The Python host holds device buffers as torch tensors; these two calls let it move the small per-pass tables between
+// pinned host memory and the device on the pass's stream without going through a tensor operation (8 us each in Python).
+extern "C" int fhc_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
+    FHC_REQUIRE(bytes == 0 || (dst && src), FHC_E_INVALID, "fhc_copy_async: null pointer");
+    if (bytes == 0) return FHC_OK;
+    FHC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return FHC_OK;
+}
+
+extern "C" int fhc_stream_synchronize(void *stream) {
+    FHC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return FHC_OK;
+}

@@ -22,7 +22,7 @@ constexpr int kHistFlushTiles = 256;        // 256 tiles x 4096 contacts x 4095 
 
 struct HistAcc {
     unsigned long long inrange_sum = 0, intra_sum = 0, inter_sum = 0;
-    unsigned int inter_n = 0, inrange_n = 0, intra_n = 0, offgrid = 0;
+    unsigned int inter_n = 0, inrange_n = 0, intra_n = 0, offgrid = 0, nonpos = 0;
     int maxc = 0;
 };
 
@@ -54,7 +54,10 @@ __device__ __forceinline__ void hist_one(int m1, int m2, int c, unsigned int ch,
         atomicAdd(&sh[slot], (unsigned int)c);
     } else {
         if (c != 0) atomicAdd(&hist[slot], (unsigned long long)cs);
-        if (c <= 0) atomicOr(&present[slot >> 5], 1u << (slot & 31));
+        if (c <= 0) {
+            atomicOr(&present[slot >> 5], 1u << (slot & 31));
+            a.nonpos += 1;
+        }
     }
 }
 
@@ -129,6 +132,7 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
     v[FHC_S_OFFGRID] = warp_sum((unsigned long long)a.offgrid);
     v[FHC_S_INTRA_INRANGE_LINES] = warp_sum((unsigned long long)a.inrange_n);
     v[FHC_S_INTRA_ALL_LINES] = warp_sum((unsigned long long)a.intra_n);
+    v[FHC_S_NONPOS_LINES] = warp_sum((unsigned long long)a.nonpos);
     int mc = a.maxc;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));

@@ -17,6 +17,7 @@
 
 #include "cephes_dev.cuh"
 #include "common.cuh"
+#include "fitpack_host.cuh"
 
 extern "C" int fhc_host_make_bins(const int64_t *dists, const int64_t *sums, int64_t m, int32_t noOfBins, int64_t N,
                                   int64_t *bin_lb, int64_t *bin_ub, int64_t *bin_sumcc) {
@@ -310,5 +311,27 @@ extern "C" int fhc_host_lbeta_table(int64_t N, double *tab, int64_t ntab, int32_
     for (int t = 1; t < nthreads; ++t) pool.emplace_back(run, per * t < ntab ? per * t : ntab, per * (t + 1) < ntab ? per * (t + 1) : ntab);
     run(0, per < ntab ? per : ntab);
     for (auto &th : pool) th.join();
+    return FHC_OK;
+}
+
+// ---- smoothing-spline fit ---------------------------------------------------------------------------------------------
+// UnivariateSpline(x, y, s=s) of fit_Spline (fithic/fithic.py:951; scipy FITPACK curfit, see fitpack_host.cuh): cubic, unit
+// weights, boundary knots at x[0] and x[m-1].  t, c [host]: room for m + 4 doubles each; the first *n_out are the knots and
+// the zero-padded b-spline coefficients (`ius._eval_args`).  *ier_out is FITPACK's ier of the last run (<= 0: fine, 1..3:
+// the warnings scipy prints), *calls_out 1 or 2 (2: the first run hit its storage limit, as _reset_nest handles it).
+extern "C" int fhc_host_curfit(const double *x, const double *y, int32_t m, double s, double *t, double *c, int32_t *n_out,
+                               double *fp_out, int32_t *ier_out, int32_t *calls_out) {
+    FHC_REQUIRE(x && y && t && c && n_out && ier_out, FHC_E_INVALID, "fhc_host_curfit: null pointer");
+    FHC_REQUIRE(m > 3, FHC_E_INVALID, "fhc_host_curfit: a cubic spline needs more than 3 points (m = %d)", m);
+    FHC_REQUIRE(s >= 0.0, FHC_E_INVALID, "fhc_host_curfit: s must be >= 0");
+    for (int i = 1; i < m; ++i)
+        FHC_REQUIRE(s > 0.0 ? x[i] >= x[i - 1] : x[i] > x[i - 1], FHC_E_INVALID, "fhc_host_curfit: x must be increasing");
+    int n = 0, calls = 0;
+    double fp = 0.0;
+    const int ier = fhc::fitpack::univariate_spline(x, y, m, 3, s, t, c, &n, &fp, &calls);
+    *n_out = n;
+    *ier_out = ier;
+    if (fp_out) *fp_out = fp;
+    if (calls_out) *calls_out = calls;
     return FHC_OK;
 }

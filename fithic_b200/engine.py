@@ -97,6 +97,110 @@ class Biases:
                           # mid order; a locus is found by binary search
 
 
+def host_threads():
+    """Host threads of this rank for the stages between the kernels: FHC_HOST_THREADS, else the cores this rank can call
+    its own (all of them on one GPU, a share under torchrun), at most 8."""
+    env = os.environ.get("FHC_HOST_THREADS")
+    if env:
+        return max(1, min(64, int(env)))
+    cores = os.cpu_count() or 4
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(8, cores // max(local, 1)))
+
+
+class PassResult(dict):
+    """The dict run_pass returns.  `table_dev` (the spline table at the observed distances on the device) is uploaded on
+    first use: K3 only needs the dense lookup table, and the native host stage leaves the table itself on the host."""
+
+    def __missing__(self, key):
+        if key == "table_dev" and "table" in self and getattr(self, "_device", None) is not None:
+            t = torch.from_numpy(np.ascontiguousarray(self["table"])).to(self._device)
+            self[key] = t
+            return t
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (key == "table_dev" and dict.__contains__(self, "table")
+                                                and getattr(self, "_device", None) is not None)
+
+
+class _HostStage:
+    """Buffers and the fhc_stage_io block of fhc_host_stage (csrc/hoststage.cu) for one engine: pinned staging buffers for
+    K1's histogram, the lookup table and the lbeta tables; per-pass output arrays are fresh numpy arrays (they end up in
+    the pass's result dict)."""
+
+    LBETA_CAP0 = 1 << 14
+
+    def __init__(self, eng):
+        st, frags = eng.st, eng.frags
+        order = sorted(range(len(frags.chroms)), key=lambda i: frags.chroms[i])  # sorted chromosome NAMES (:606)
+        order = [i for i in order if frags.n_mappable[i] > 0]
+        self.chr_n = np.ascontiguousarray(frags.n_mappable[order], dtype=np.int64)
+        self.chr_mm = np.ascontiguousarray(frags.max_mid[order], dtype=np.int64)
+        self.nthreads = host_threads()
+        io = self.io = _capi.StageIO()
+        io.grid = eng.grid
+        io.noOfBins = int(st.noOfBins)
+        io.L, io.U = st.L, st.U
+        io.chr_n, io.chr_maxmid, io.nchr = self.chr_n.ctypes.data, self.chr_mm.ctypes.data, len(order)
+        io.want_spline = 0 if st.interOnly else 1
+        io.nthreads = self.nthreads
+        self.D = 0
+        self.lbeta = [None, None]  # pinned tensors
+
+    def ensure(self, D):
+        if D == self.D:
+            return
+        self.D = D
+        nwords = (D + 31) // 32
+        self.k1 = torch.empty(D + _capi.N_SCALARS + (nwords + 1) // 2, dtype=torch.int64).pin_memory()
+        self.k1_np = self.k1.numpy()
+        self.lut = torch.empty(D, dtype=torch.float64).pin_memory()
+        self.io.k1buf = self.k1.data_ptr()
+        self.io.D = D
+        self.io.lut = self.lut.data_ptr()
+
+    def ensure_lbeta(self, which, cap):
+        cur = self.lbeta[which]
+        if cur is None or cur.numel() < cap:
+            cur = self.lbeta[which] = torch.empty(int(cap), dtype=torch.float64).pin_memory()
+        self.io.lbeta_tab[which] = cur.data_ptr()
+        self.io.lbeta_cap[which] = cur.numel()
+        return cur
+
+    def new_outputs(self):
+        """Fresh arrays for the outputs that go into the pass's result dict."""
+        D, nb = self.D, int(self.io.noOfBins)
+        io = self.io
+        self.i64 = i64 = np.empty(3 * D + 4 * nb, dtype=np.int64)
+        self.f64 = f64 = np.empty(D + 5 * nb + 2 * (nb + 4), dtype=np.float64)
+        b = i64.ctypes.data
+        io.dists, io.sums, io.splineX = b, b + 8 * D, b + 16 * D
+        b += 24 * D
+        io.bin_lb, io.bin_ub, io.bin_sumcc, io.bin_pairs = b, b + 8 * nb, b + 16 * nb, b + 24 * nb
+        b = f64.ctypes.data
+        io.table = b
+        b += 8 * D
+        io.bin_sumdist, io.x_bins, io.y_bins, io.xs, io.ys = (b + 8 * nb * k for k in range(5))
+        b += 40 * nb
+        io.t, io.c = b, b + 8 * (nb + 4)
+
+    def views(self):
+        D, nb = self.D, int(self.io.noOfBins)
+        i64, f64, io = self.i64, self.f64, self.io
+        n, ns, m, nt = int(io.nb), int(io.nseen), int(io.m), int(io.nt)
+        o = 3 * D
+        v = dict(dists=i64[:ns], sums=i64[D:D + ns], splineX=i64[2 * D:2 * D + m],
+                 lb=i64[o:o + n], ub=i64[o + nb:o + nb + n], sumcc=i64[o + 2 * nb:o + 2 * nb + n],
+                 pairs=i64[o + 3 * nb:o + 3 * nb + n], table=f64[:m])
+        o = D
+        for k, name in enumerate(("sumdist", "x_bins", "y_bins", "xs", "ys")):
+            v[name] = f64[o + k * nb:o + k * nb + n]
+        o = D + 5 * nb
+        v["t"], v["c"] = f64[o:o + nt], f64[o + nb + 4:o + nb + 4 + nt]
+        return v
+
+
 class Engine:
     """Runs spline passes on one GPU.  With `dist_ctx` set (parallel.DistCtx), histograms/totals are all-reduced so that
     every rank fits the same spline, and q-values come from the range-partitioned global BH."""
@@ -231,11 +335,13 @@ class Engine:
         return hist, present, scal
 
     # ------------------------------------------------------------------------------------------------------------
+    # the native host stage covers fixed-size bins with a distance axis of at most this many slots (-r 0 on its 1 bp grid
+    # and anything larger keep the staged path: evaluation and lookup table on the device)
+    NATIVE_STAGE_MAX_SLOTS = 1 << 20
+
     def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
-        st, lib = self.st, self.lib
-        res = self.grid
-        ev = {}
+        st = self.st
         t0 = time.perf_counter()
         # ---- K1 ----
         skip, skip_limit = None, -1
@@ -246,53 +352,13 @@ class Engine:
         hist_d, present_d, scal_d = self.hist_distance(skip, skip_limit)
         if self.dist is not None:
             self.dist.allreduce_hist(hist_d, present_d, scal_d, fused=self._ws["k1buf"][:self.D + _capi.N_SCALARS])
-        D = self.D
-        hbuf = self._ws["k1buf"][:D + _capi.N_SCALARS + ((D + 31) // 32 + 1) // 2].cpu().numpy()
-        hist = hbuf[:D]
-        scal = hbuf[D:D + _capi.N_SCALARS]
-        present = hbuf[D + _capi.N_SCALARS:].view(np.uint32)[:(D + 31) // 32]
-        if int(scal[_capi.S_OFFGRID]) != 0:
-            raise ValueError("%d in-range intra contacts have a distance that is not a multiple of the resolution %d "
-                             "(or beyond the fragment list); only fixed-size bins on a common grid are supported"
-                             % (int(scal[_capi.S_OFFGRID]), res))
-        N = int(scal[_capi.S_INTRA_INRANGE_SUM])
-        obsInterAllCount = int(scal[_capi.S_INTER_ALL_COUNT])
-        obsInterAllSum = int(scal[_capi.S_INTER_ALL_SUM])
-        obsIntraAllSum = int(scal[_capi.S_INTRA_ALL_SUM])
-        max_count = int(scal[_capi.S_MAX_COUNT])
-        t1 = time.perf_counter()
-        # ---- host: bins, possible pairs, probabilities, spline fit ----
-        if present.any():  # a distance whose counts sum to zero still counts as seen (:434-436): rare
-            pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
-            seen = np.nonzero((hist != 0) | pres_bits)[0]
-        else:
-            seen = np.nonzero(hist)[0]
-        dists = (seen * res).astype(np.int64)
-        sums = hist[seen].astype(np.int64)
-        bins = make_bins(lib, dists, sums, st.noOfBins, N)
-        dec = None
-        if passNo > 1 and outl is not None and bins["n"] > 0:
-            dec = self.outlier_bin_decrements(outl, bins["ub"])
-            if self.dist is not None:
-                dec = self.dist.allreduce_small(dec)
-        fp = frag_pairs(lib, self.frags, st, bins, dec)
-        x, y = calculate_probabilities(bins, N)
-        out = dict(passNo=passNo, N=N, dists=dists, sums=sums, bins=bins, x=x, y=y, x_bins=x, y_bins=y,
-                   observedInterAllCount=obsInterAllCount, observedInterAllSum=obsInterAllSum,
-                   observedIntraAllSum=obsIntraAllSum, observedIntraInRangeLines=int(scal[_capi.S_INTRA_INRANGE_LINES]),
-                   observedIntraAllLines=int(scal[_capi.S_INTRA_ALL_LINES]), max_count=max_count, **fp)
+        native = (st.resolution > 0 and self.D <= self.NATIVE_STAGE_MAX_SLOTS
+                  and os.environ.get("FHC_HOST_STAGE", "native") != "legacy")
+        tables = self._tables_native if native else self._tables_legacy
+        out, lut, lbeta, ev = tables(passNo, outl if passNo > 1 else None, t0)
+        N, obsInterAllCount, obsInterAllSum = out["N"], out["observedInterAllCount"], out["observedInterAllSum"]
         interChrProb = 1.0 / obsInterAllCount if obsInterAllCount > 0 else 0.0   # :669-672
         out["interChrProb"] = interChrProb
-        lut = None
-        if not st.interOnly:
-            xs, ys, tck = fit_spline(x, y)
-            splineX = dists[(dists >= min(xs)) & (dists <= max(xs))]
-            out.update(x=xs, y=ys, tck=tck, splineX=splineX)
-            t2 = time.perf_counter()
-            table, lut = self.spline_table(tck, splineX, min(xs), max(xs))
-            out["table_dev"] = table
-        else:
-            t2 = time.perf_counter()
         # ---- T (fithic/fithic.py:1128-1163) ----
         if st.allReg:
             T = out["possibleIntraInRangeCount"] + obsInterAllCount
@@ -304,8 +370,8 @@ class Engine:
         # ---- K3 ----
         thres = (1.0 / T) if T != 0 else float("inf")
         out["outlierThres"] = thres
-        p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, max_count, outl, thres, outl_stats, pvalue_chunks,
-                            after_chunk)
+        p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, out["max_count"], outl, thres, outl_stats, pvalue_chunks,
+                            after_chunk, lbeta=lbeta)
         if after_pvalues is not None:
             after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
         # ---- K4 ----
@@ -314,10 +380,151 @@ class Engine:
         else:
             q = self.bh_qvalues(p, float(T))
         out.update(p=p, q=q, expcc=e)
-        ev["k1_and_d2h"] = t1 - t0     # K1 launch + wait + histogram D2H (includes the device time of K1)
-        ev["host_bins_fit"] = t2 - t1  # make_bins + frag_pairs + probabilities + scipy spline fit
         self.timings[passNo] = ev
         return out
+
+    def _pass_scalars(self, passNo, scal):
+        if int(scal[_capi.S_OFFGRID]) != 0:
+            raise ValueError("%d in-range intra contacts have a distance that is not a multiple of the resolution %d "
+                             "(or beyond the fragment list); only fixed-size bins on a common grid are supported"
+                             % (int(scal[_capi.S_OFFGRID]), self.grid))
+        return PassResult(passNo=passNo, N=int(scal[_capi.S_INTRA_INRANGE_SUM]),
+                          observedInterAllCount=int(scal[_capi.S_INTER_ALL_COUNT]),
+                          observedInterAllSum=int(scal[_capi.S_INTER_ALL_SUM]),
+                          observedIntraAllSum=int(scal[_capi.S_INTRA_ALL_SUM]),
+                          observedIntraInRangeLines=int(scal[_capi.S_INTRA_INRANGE_LINES]),
+                          observedIntraAllLines=int(scal[_capi.S_INTRA_ALL_LINES]), max_count=int(scal[_capi.S_MAX_COUNT]))
+
+    def _tables_native(self, passNo, outl, t0):
+        """Histogram -> lookup table through fhc_host_stage: one device->host copy of K1's buffer, one C call for bins,
+        possible pairs, probabilities, spline fit, table and lbeta tables, and host->device copies of the lookup table and
+        the lbeta tables on the pass's stream."""
+        st, lib, D = self.st, self.lib, self.D
+        hs = getattr(self, "_stage", None)
+        if hs is None:
+            hs = self._stage = _HostStage(self)
+        hs.ensure(D)
+        io = hs.io
+        stream = self._stream()
+        k1buf = self._ws["k1buf"]
+        nk = D + _capi.N_SCALARS
+        check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
+        lib.fhc_host_pool_prewarm(hs.nthreads)
+        hs.new_outputs()
+        use_host_lbeta = os.environ.get("FHC_LBETA_TABLE", "host") != "device"
+        want = (not st.interOnly, st.interOnly or st.allReg)
+        for w in (0, 1):
+            if use_host_lbeta and want[w]:
+                hs.ensure_lbeta(w, hs.LBETA_CAP0)
+            else:
+                io.lbeta_tab[w] = None
+                io.lbeta_cap[w] = 0
+        check(lib.fhc_stream_synchronize(stream))
+        scal = hs.k1_np[D:nk]
+        if int(scal[_capi.S_NONPOS_LINES]) != 0:  # distances seen only through lines with a count <= 0 (:434-436): rare
+            nw = (D + 31) // 32
+            check(lib.fhc_copy_async(hs.k1.data_ptr() + 8 * nk, k1buf.data_ptr() + 8 * nk, 4 * nw, stream))
+            check(lib.fhc_stream_synchronize(stream))
+        out = self._pass_scalars(passNo, scal)
+        t1 = time.perf_counter()
+        io.dec = None
+        if outl is not None:
+            check(lib.fhc_host_stage(ctypes.byref(io), 1))
+            dec = None
+            if io.nb > 0:
+                dec = self.outlier_bin_decrements(outl, hs.views()["ub"])
+                if self.dist is not None:
+                    dec = self.dist.allreduce_small(dec)
+                dec = np.ascontiguousarray(dec, dtype=np.int64)
+                io.dec = dec.ctypes.data
+            check(lib.fhc_host_stage(ctypes.byref(io), 6))
+            io.dec = None
+        else:
+            check(lib.fhc_host_stage(ctypes.byref(io), 7))
+        if io.status == 3:  # counts larger than the lbeta staging buffers: enlarge and fill them
+            for w in (0, 1):
+                if io.lbeta_cap[w] and io.lbeta_ntab[w] > io.lbeta_cap[w]:
+                    hs.ensure_lbeta(w, int(io.lbeta_ntab[w]))
+            check(lib.fhc_host_stage(ctypes.byref(io), 8))
+        v = hs.views()
+        if io.status == 1:
+            i = int(io.bad_index)
+            print("ERROR in spline fitting. Distances do not decrease across bins. Ensure interaction file is correct.")
+            print("Avg. distance of bin(i-1)... %s" % v["xs"][i - 1])
+            print("Avg. distance of bin(i)... %s" % v["xs"][i])
+            raise SystemExit(2)
+        if io.status == 2:
+            raise ValueError("no observed distance falls inside the fitted range")
+        if io.status == 4:
+            raise ValueError("the spline fit needs more than 3 bins (got %d)" % int(io.nb))
+        bins = dict(n=int(io.nb), lb=v["lb"], ub=v["ub"], sumcc=v["sumcc"], pairs=v["pairs"], pairs7=v["pairs"],
+                    sumdist=v["sumdist"])
+        x_bins, y_bins = v["x_bins"].tolist(), v["y_bins"].tolist()
+        tot = io.totals
+        out.update(dists=v["dists"], sums=v["sums"], bins=bins, x=x_bins, y=y_bins, x_bins=x_bins, y_bins=y_bins,
+                   possibleIntraInRangeCount=int(tot[0]), possibleIntraAllCount=tot[1] / 2, possibleInterAllCount=tot[2] / 2,
+                   noOfFrags=int(tot[3]))
+        lut = None
+        if not st.interOnly:
+            out.update(x=v["xs"].tolist(), y=v["ys"].tolist(), tck=(v["t"], v["c"], 3), splineX=v["splineX"], table=v["table"],
+                       spline_ier=int(io.ier), spline_calls=int(io.calls))
+            out._device = self.device
+            lut = self._tensor("lut", D, torch.float64)
+            check(lib.fhc_copy_async(lut.data_ptr(), hs.lut.data_ptr(), 8 * D, stream))
+        lbeta = None
+        if use_host_lbeta:
+            lbeta = [None, 0, None, 0]
+            for w, name in ((0, "lbeta_intra"), (1, "lbeta_inter")):
+                if want[w]:
+                    ntab = int(io.lbeta_ntab[w])
+                    tab = self._tensor(name, ntab, torch.float64)
+                    check(lib.fhc_copy_async(tab.data_ptr(), hs.lbeta[w].data_ptr(), 8 * ntab, stream))
+                    lbeta[2 * w], lbeta[2 * w + 1] = tab, ntab
+        t2 = time.perf_counter()
+        tm = io.timings
+        ev = {"k1_and_d2h": t1 - t0, "host_bins_fit": t2 - t1, "stage_bins": tm[0] * 1e-3, "stage_pairs_lbeta": tm[1] * 1e-3,
+              "stage_fit": tm[2] * 1e-3, "stage_eval": tm[3] * 1e-3, "stage_antitonic": tm[4] * 1e-3, "stage_lut": tm[5] * 1e-3}
+        return out, lut, lbeta, ev
+
+    def _tables_legacy(self, passNo, outl, t0):
+        """The same through the stage-by-stage entry points (restriction-fragment mode and very long distance axes):
+        bins and possible pairs in C, the fit in C, evaluation and lookup table on the device."""
+        st, lib, res, D = self.st, self.lib, self.grid, self.D
+        hbuf = self._ws["k1buf"][:D + _capi.N_SCALARS + ((D + 31) // 32 + 1) // 2].cpu().numpy()
+        hist = hbuf[:D]
+        scal = hbuf[D:D + _capi.N_SCALARS]
+        present = hbuf[D + _capi.N_SCALARS:].view(np.uint32)[:(D + 31) // 32]
+        out = self._pass_scalars(passNo, scal)
+        N = out["N"]
+        t1 = time.perf_counter()
+        # ---- host: bins, possible pairs, probabilities, spline fit ----
+        if int(scal[_capi.S_NONPOS_LINES]) != 0:  # a distance whose counts sum to zero still counts as seen (:434-436): rare
+            pres_bits = np.unpackbits(present.view(np.uint8), bitorder="little")[:D].astype(bool)
+            seen = np.nonzero((hist != 0) | pres_bits)[0]
+        else:
+            seen = np.nonzero(hist)[0]
+        dists = (seen * res).astype(np.int64)
+        sums = hist[seen].astype(np.int64)
+        bins = make_bins(lib, dists, sums, st.noOfBins, N)
+        dec = None
+        if outl is not None and bins["n"] > 0:
+            dec = self.outlier_bin_decrements(outl, bins["ub"])
+            if self.dist is not None:
+                dec = self.dist.allreduce_small(dec)
+        fp = frag_pairs(lib, self.frags, st, bins, dec)
+        x, y = calculate_probabilities(bins, N)
+        out.update(dists=dists, sums=sums, bins=bins, x=x, y=y, x_bins=x, y_bins=y, **fp)
+        lut = None
+        if not st.interOnly:
+            xs, ys, tck = fit_spline(x, y)
+            splineX = dists[(dists >= min(xs)) & (dists <= max(xs))]
+            out.update(x=xs, y=ys, tck=tck, splineX=splineX)
+            t2 = time.perf_counter()
+            table, lut = self.spline_table(tck, splineX, min(xs), max(xs))
+            out["table_dev"] = table
+        else:
+            t2 = time.perf_counter()
+        return out, lut, None, {"k1_and_d2h": t1 - t0, "host_bins_fit": t2 - t1}
 
     # ------------------------------------------------------------------------------------------------------------
     # K2
@@ -358,11 +565,12 @@ class Engine:
     def lbeta_table(self, name, N, max_count):
         ntab = int(min(max(max_count, 1), min(N, (1 << 22) - 1)) + 1)
         tab = self._tensor(name, ntab, torch.float64)
-        if os.environ.get("FHC_LBETA_TABLE") == "host":
-            # the table from the C library's log (scipy's own) instead of the device kernel's correctly
-            # rounded one: follows scipy in the rare entries where the two logs differ.  Opt-in until timed on the GPU.
+        if os.environ.get("FHC_LBETA_TABLE", "host") != "device":
+            # Default: the table from the C library's log -- the function scipy's cephes calls -- so that K3 follows scipy
+            # also in the rare entries where that log is not correctly rounded (one ulp of lgam(N) = 4e-6 ... 8e-6 in p,
+            # DESIGN.md section 2).  FHC_LBETA_TABLE=device runs the device kernel (correctly rounded log) instead.
             host = np.empty(ntab, dtype=np.float64)
-            check(self.lib.fhc_host_lbeta_table(int(N), dptr(host), ntab, int(os.environ.get("FHC_HOST_THREADS", "8"))))
+            check(self.lib.fhc_host_lbeta_table(int(N), dptr(host), ntab, host_threads()))
             tab.copy_(torch.from_numpy(host))
             return tab, ntab
         check(self.lib.fhc_lbeta_table(int(N), dptr(tab), ntab, self._stream()))
@@ -370,7 +578,7 @@ class Engine:
 
     # K3  (fit_Spline per-line loop, fithic/fithic.py:1017-1123)
     def pvalues(self, lut, N_intra, N_inter, interChrProb, max_count, outl=None, outl_thres=0.0, outl_stats=None,
-                nchunks=1, after_chunk=None):
+                nchunks=1, after_chunk=None, lbeta=None):
         """nchunks > 1 launches K3 once per contiguous slice of the contacts and calls after_chunk(lo, hi, p, e) after
         each launch, so that a caller can start moving finished slices to the host while the next one is computed."""
         st = self.st
@@ -380,10 +588,13 @@ class Engine:
         e = self._tensor("expcc", n, torch.float64)
         tab_a = tab_b = None
         nta = ntb = 0
-        if not st.interOnly:
-            tab_a, nta = self.lbeta_table("lbeta_intra", N_intra, max_count)
-        if st.interOnly or st.allReg:
-            tab_b, ntb = self.lbeta_table("lbeta_inter", N_inter, max_count)
+        if lbeta is not None:  # tables of this pass already on their way to the device (fhc_host_stage)
+            tab_a, nta, tab_b, ntb = lbeta
+        else:
+            if not st.interOnly:
+                tab_a, nta = self.lbeta_table("lbeta_intra", N_intra, max_count)
+            if st.interOnly or st.allReg:
+                tab_b, ntb = self.lbeta_table("lbeta_inter", N_inter, max_count)
         bias = bmid = boff = None
         nchr = 0
         if self._bias_dev is not None:
@@ -517,8 +728,8 @@ def calculate_probabilities(bins, N):
 
 def fit_spline(x, y):
     """fit_Spline fit stage (fithic/fithic.py:936-951): sort by x, require strictly increasing x, cubic
-    UnivariateSpline with s = min(y)^2 (scipy FITPACK on <= noOfBins points; the per-distance evaluation is K2)."""
-    from scipy.interpolate import UnivariateSpline
+    UnivariateSpline with s = min(y)^2 -- FITPACK's curfit restated in C (fhc_host_curfit: knots and coefficients equal
+    scipy's bit for bit); the per-distance evaluation is K2."""
     y = [f for _, f in sorted(zip(x, y), key=lambda pair: pair[0])]
     x = sorted(x)
     for i in range(1, len(x)):
@@ -527,6 +738,13 @@ def fit_spline(x, y):
             print("Avg. distance of bin(i-1)... %s" % x[i - 1])
             print("Avg. distance of bin(i)... %s" % x[i])
             raise SystemExit(2)
-    ius = UnivariateSpline(x, y, s=min(y) * min(y))
-    t, c, k = ius._eval_args
-    return x, y, (np.asarray(t, np.float64), np.asarray(c, np.float64), int(k))
+    m = len(x)
+    if m <= 3:
+        raise ValueError("the spline fit needs more than 3 bins (got %d)" % m)
+    xa, ya = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    t, c = np.zeros(m + 4, dtype=np.float64), np.zeros(m + 4, dtype=np.float64)
+    n, ier, calls = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    fp = ctypes.c_double(0.0)
+    check(_capi.load().fhc_host_curfit(dptr(xa), dptr(ya), m, float(min(y) * min(y)), dptr(t), dptr(c), ctypes.byref(n),
+                                       ctypes.byref(fp), ctypes.byref(ier), ctypes.byref(calls)))
+    return x, y, (t[:n.value].copy(), c[:n.value].copy(), 3)

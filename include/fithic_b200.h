@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 4
+#define FHC_ABI_VERSION 5
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -45,7 +45,8 @@ extern "C" {
 #define FHC_S_OFFGRID 5           /* in-range intra lines whose distance is not k*res with k < D (must be 0) */
 #define FHC_S_INTRA_INRANGE_LINES 6 /* observedIntraInRangeCount fithic/fithic.py:440 */
 #define FHC_S_INTRA_ALL_LINES 7   /* observedIntraAllCount    fithic/fithic.py:425 */
-#define FHC_N_SCALARS 8
+#define FHC_S_NONPOS_LINES 8     /* in-range intra lines with cnt <= 0: only then the `present` bitmap says more than hist */
+#define FHC_N_SCALARS 9
 
 /* fhc_pvalues mode bits (fithic/fithic.py:232-248) */
 #define FHC_MODE_INTRA_ONLY 0
@@ -62,6 +63,12 @@ int64_t fhc_launch_count(void);
  * {"<kernel>": {"ms": total, "launches": n}, ...} into buf and clears the log; returns the string length. */
 int fhc_profile_enable(int on);
 int fhc_profile_collect(char *buf, size_t buf_bytes);
+
+/* Plumbing for hosts that hold device memory but have no CUDA binding of their own (the Python host keeps torch tensors
+ * as buffers): cudaMemcpyAsync(cudaMemcpyDefault) on `stream` -- host memory should be pinned -- and
+ * cudaStreamSynchronize. */
+int fhc_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+int fhc_stream_synchronize(void *stream);
 
 /* ---- K1: distance histogram + totals ------------------------------------------------------------------------
  * Replaces the accumulation loop of read_Interactions (fithic/fithic.py:406-441) with the classification of
@@ -100,6 +107,50 @@ int fhc_host_frag_pairs(const int64_t *chr_n, const int64_t *chr_maxmid, int32_t
 int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
                                 const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
                                 int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals);
+
+/* ---- the whole host stage between K1 and K3 in one call ----------------------------------------------------------
+ * k1buf [host]: fhc_hist_distance's outputs back to back as the engine keeps them, [hist (D) | scalars (FHC_N_SCALARS) |
+ * present words]; the present words are only read when scalars[FHC_S_NONPOS_LINES] != 0.  phases (bit mask):
+ *   1  observed distances (dists, sums: capacity D) and makeBinsFromInteractions (bin_lb / bin_ub / bin_sumcc: noOfBins)
+ *   2  generate_FragPairs fixed-size branch (bin_pairs, bin_sumdist, totals as fhc_host_frag_pairs; `dec` [nullable] holds
+ *      the pass >= 2 outlier decrements per bin) and calculateProbabilities (x_bins, y_bins in bin order); the lbeta tables
+ *      (fhc_host_lbeta_table; [0]: N = scalars[INTRA_INRANGE_SUM], [1]: N = scalars[INTER_ALL_SUM]; nullable; ntab from
+ *      scalars[MAX_COUNT] as fhc_pvalues wants it) are built by the same worker threads
+ *   4  fit_Spline's fit stage when want_spline != 0: (xs, ys) sorted by x, fhc_host_curfit (t, c: capacity noOfBins + 4),
+ *      splineX / table (capacity D), lut (capacity D): what fhc_spline_table produces on the device
+ *   8  the lbeta tables alone (status 3 of an earlier call: lbeta_cap was below lbeta_ntab)
+ * status: 0 fine; 1 x of the bins not strictly increasing at bad_index (the reference prints an error and exits 2,
+ * fithic/fithic.py:940-945); 2 no observed distance inside [min x, max x]; 3 an lbeta table is too small; 4 fewer than 4
+ * bins (scipy refuses the fit).  timings [ms]: bins, pairs + lbeta, fit, evaluation, antitonic, lut, -, total.
+ * nthreads: the calling thread + (nthreads - 1) pooled workers (fhc_host_pool_prewarm wakes them ahead of the call). */
+typedef struct fhc_stage_io {
+    const uint64_t *k1buf;
+    int64_t D;
+    int32_t grid, noOfBins;
+    int64_t L, U;
+    const int64_t *chr_n, *chr_maxmid;
+    int32_t nchr, want_spline, nthreads, pad0;
+    const int64_t *dec;
+    double *lbeta_tab[2];
+    int64_t lbeta_cap[2];
+    /* outputs */
+    int64_t *dists, *sums;
+    int64_t nseen;
+    int64_t *bin_lb, *bin_ub, *bin_sumcc, *bin_pairs;
+    double *bin_sumdist, *x_bins, *y_bins, *xs, *ys, *t, *c;
+    int64_t *splineX;
+    double *table, *lut;
+    int64_t m;
+    int64_t totals[4];
+    int64_t lbeta_ntab[2];
+    int32_t nb, nt, ier, calls, status, bad_index;
+    double fp;
+    double timings[8];
+} fhc_stage_io;
+int fhc_host_stage(fhc_stage_io *io, int32_t phases);
+int fhc_host_pool_prewarm(int32_t nthreads);
+/* diagnostic: njobs jobs spinning job_us microseconds each on nthreads threads -> elapsed ms */
+double fhc_host_pool_selftest(int32_t nthreads, int32_t njobs, int32_t job_us, int32_t *distinct_threads);
 
 /* dst[i] = v for i < n with nthreads host threads (the end-to-end call fills its pinned q array with 1.0 while the GPU
  * works, see fhc_gather_ne_one). */
@@ -141,6 +192,15 @@ double fhc_host_log_cr(double x);
  * 15,000 at some magnitudes), where it follows scipy by one ulp of lgam(N) (4e-6 ... 8e-6 in p).  A caller that wants
  * scipy's value there too uploads this table instead of running fhc_lbeta_table (engine: FHC_LBETA_TABLE=host). */
 int fhc_host_lbeta_table(int64_t N, double *tab, int64_t ntab, int32_t nthreads);
+
+/* ---- smoothing-spline fit (host) -------------------------------------------------------------------------------
+ * `ius = UnivariateSpline(x, y, s=min(y)**2)` of fit_Spline, fithic/fithic.py:951 (scipy FITPACK curfit, third party):
+ * cubic, unit weights, the same sequence of IEEE operations as Dierckx's fpcurf, so t / c equal `ius._eval_args` bit for
+ * bit.  x, y [host]: m > 3 points, x increasing.  t, c [host]: room for m + 4 doubles; *n_out knots are returned.
+ * *ier_out: FITPACK's ier (<= 0 fine; 1, 2, 3 = the warnings scipy prints); *calls_out: 1, or 2 when the first run hit
+ * its storage limit nest = max(m / 2, 8) and was continued with nest = m + 4 (UnivariateSpline._reset_nest). */
+int fhc_host_curfit(const double *x, const double *y, int32_t m, double s, double *t, double *c, int32_t *n_out,
+                    double *fp_out, int32_t *ier_out, int32_t *calls_out);
 double fhc_host_lbeta(double a, double b);
 /* scipy.special.bdtrc(count - 1, N, prior) evaluated on the host by the source the work-list kernels of K3 run
  * (classification, division-free continued fraction / tail sum, prefactor with folded divisions), and its 1 - exp(y). */
