@@ -12,12 +12,13 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 5
+FHC_ABI_VERSION = 6
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES, S_NONPOS_LINES) = range(9)
 N_SCALARS = 9
 MODE_INTRA_ONLY, MODE_INTER_ONLY, MODE_ALL = 0, 1, 2
 BH_CUT_BUCKETS = 32768
+MAX_CHR_RUNS = 1024
 
 
 class StageIO(ctypes.Structure):
@@ -25,7 +26,7 @@ class StageIO(ctypes.Structure):
     _fields_ = [
         ("k1buf", c_void_p), ("D", c_int64), ("grid", c_int32), ("noOfBins", c_int32), ("L", c_int64), ("U", c_int64),
         ("chr_n", c_void_p), ("chr_maxmid", c_void_p), ("nchr", c_int32), ("want_spline", c_int32), ("nthreads", c_int32),
-        ("pad0", c_int32), ("dec", c_void_p), ("lbeta_tab", c_void_p * 2), ("lbeta_cap", c_int64 * 2),
+        ("n_rank_slots", c_int32), ("dec", c_void_p), ("lbeta_tab", c_void_p * 2), ("lbeta_cap", c_int64 * 2),
         ("dists", c_void_p), ("sums", c_void_p), ("nseen", c_int64),
         ("bin_lb", c_void_p), ("bin_ub", c_void_p), ("bin_sumcc", c_void_p), ("bin_pairs", c_void_p),
         ("bin_sumdist", c_void_p), ("x_bins", c_void_p), ("y_bins", c_void_p), ("xs", c_void_p), ("ys", c_void_p),
@@ -51,8 +52,10 @@ _SIGNATURES = {
     "fhc_profile_collect": (ctypes.c_int, [c_char_p, c_size_t]),
     "fhc_copy_async": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_stream_synchronize": (ctypes.c_int, [c_void_p]),
-    "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                          c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "fhc_peak_fp64": (ctypes.c_int, [c_double, c_void_p, c_void_p, c_void_p]),
+    "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                                          c_int32, c_int32, c_void_p]),
     "fhc_host_make_bins": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "fhc_host_frag_pairs": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
                                             c_int32, c_void_p, c_void_p, c_void_p]),
@@ -77,7 +80,8 @@ _SIGNATURES = {
     "fhc_host_lbeta": (c_double, [c_double, c_double]),
     "fhc_host_bdtrc_lists": (c_double, [c_int32, c_int64, c_double]),
     "fhc_host_one_minus_exp": (c_double, [c_double]),
-    "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+    "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+                                    c_void_p, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                     c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -92,6 +96,7 @@ _SIGNATURES = {
                                        c_void_p, c_size_t, c_void_p]),
     "fhc_bh_p_cut": (c_double, [c_double, c_double]),
     "fhc_bh_cut_hist": (ctypes.c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "fhc_bh_cut_from_hists": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_double, c_double, c_void_p, c_void_p]),
     "fhc_host_bh_cut_find": (c_double, [c_void_p, c_double, c_double, c_double]),
     "fhc_host_bh_cut_bucket": (c_int32, [c_double]),
     "fhc_bh_finish": (ctypes.c_int, [c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -136,7 +141,8 @@ _SIGNATURES = {
     "fhc_io_free": (None, [c_void_p]),
     "fhc_io_write_significances": (c_int64, [c_char_p, ctypes.POINTER(c_char_p), c_int32, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64,
-                                             c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32]),
+                                             c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "fhc_digest_lines": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "fhc_outlier_bin_decrements": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                                    c_void_p]),
 }

@@ -253,6 +253,74 @@ __global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict
     }
 }
 
+// Multi-GPU: every rank's value histogram (all-gathered, nranks x kCutBuckets) -> the global cut, and how many p-values
+// each rank holds below it.  Same rule as bh_cut_find_kernel on the summed histogram; one CTA.  info (8 + nranks words):
+// [0] the cut (double), [1] p-values below it on all ranks, [2] on this rank, [3] the largest share of one rank,
+// [8 + r] the share of rank r.
+__global__ void __launch_bounds__(1024) bh_cut_from_hists_kernel(const u64 *__restrict__ hists, int nranks, int my_rank,
+                                                                double T, double p_cut0, u64 *__restrict__ info) {
+    __shared__ u64 wsum[32];
+    __shared__ int best;
+    __shared__ u64 share[64];
+    const int per = kCutBuckets / 1024;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) best = kCutBuckets;
+    if (threadIdx.x < 64) share[threadIdx.x] = 0;
+    u64 mine = 0;
+    for (int k = 0; k < per; ++k) {
+        const int j = threadIdx.x * per + k;
+        for (int r = 0; r < nranks; ++r) mine += hists[(size_t)r * kCutBuckets + j];
+    }
+    u64 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (T > 0.0) {
+        u64 pre = inc - mine;
+        for (int w = 0; w < warp; ++w) pre += wsum[w];
+        int found = kCutBuckets;
+        for (int k = 0; k < per; ++k) {
+            const int j = threadIdx.x * per + k;
+            u64 c = 0;
+            for (int r = 0; r < nranks; ++r) c += hists[(size_t)r * kCutBuckets + j];
+            pre += c;
+            if (c && found == kCutBuckets && cut_bucket_closes(j, pre, T, 0.0)) found = j;
+        }
+        if (found < kCutBuckets) atomicMin(&best, found);
+    }
+    __syncthreads();
+    // shares: the buckets below the closing one (all of them when none closes: the histograms only hold p < p_cut0)
+    const int upto = best;
+    for (int r = 0; r < nranks; ++r) {
+        u64 c = 0;
+        for (int k = 0; k < per; ++k) {
+            const int j = threadIdx.x * per + k;
+            if (j < upto) c += hists[(size_t)r * kCutBuckets + j];
+        }
+        c = warp_sum(c);
+        if (lane == 0 && c) atomicAdd(&share[r], c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cut = p_cut0;
+        if (best < kCutBuckets) cut = fmin(cut, cut_edge(best));
+        info[0] = (u64)__double_as_longlong(cut);
+        u64 tot = 0, mx = 0;
+        for (int r = 0; r < nranks; ++r) {
+            tot += share[r];
+            mx = share[r] > mx ? share[r] : mx;
+            info[8 + r] = share[r];
+        }
+        info[1] = tot;
+        info[2] = share[my_rank];
+        info[3] = mx;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // exclusive scan of a uint32 array (three phases)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1032,6 +1100,19 @@ extern "C" int fhc_bh_cut_hist(const double *p, int64_t n, double p_cut0, uint64
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     return cut_hist_launch(p, n, p_cut0, reinterpret_cast<u64 *>(hist), st);
+}
+
+extern "C" int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int32_t my_rank, double T, double p_cut0,
+                                     uint64_t *info, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(hists && info && nranks >= 1 && nranks <= 64 && my_rank >= 0 && my_rank < nranks, FHC_E_INVALID,
+                "fhc_bh_cut_from_hists: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    bh_cut_from_hists_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const u64 *>(hists), nranks, my_rank, T, p_cut0,
+                                                 reinterpret_cast<u64 *>(info));
+    FHC_LAUNCH_CHECK("bh_cut_from_hists_kernel");
+    return FHC_OK;
 }
 
 extern "C" int32_t fhc_host_bh_cut_bucket(double p) { return fhc::cut_bucket(p); }

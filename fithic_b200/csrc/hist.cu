@@ -19,6 +19,7 @@ constexpr int kHistPairsPerTile = kHistThreads * 4;
 constexpr int kHistSmemSlotsMax = 53248;    // 208 KB of uint32 slots (227 KB usable per CTA)
 constexpr int kHistSmallCount = 4096;       // counts below this go through shared memory
 constexpr int kHistFlushTiles = 256;        // 256 tiles x 4096 contacts x 4095 < 2^32
+constexpr int kHistMaxRuns = FHC_MAX_CHR_RUNS;
 
 struct HistAcc {
     unsigned long long inrange_sum = 0, intra_sum = 0, inter_sum = 0;
@@ -75,11 +76,21 @@ __device__ __forceinline__ void hist_flush(unsigned int *sh, int S, unsigned lon
 
 __global__ void __launch_bounds__(kHistThreads, 1)
 hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid2, const int4 *__restrict__ cnt,
-                     const int4 *__restrict__ chrs, const unsigned int *__restrict__ skip, long long skip_limit,
+                     const int4 *__restrict__ chrs, const long long *__restrict__ run_start,
+                     const unsigned int *__restrict__ run_val, int nruns, const unsigned int *__restrict__ skip,
+                     long long skip_limit,
                      long long n, long long Llo, long long Uhi, unsigned int res, unsigned long long *hist,
-                     unsigned int *present, long long D, int S, unsigned long long *scalars) {
+                     unsigned int *present, long long D, int S, unsigned long long *scalars, int max_slot) {
     extern __shared__ unsigned int sh[];
     __shared__ unsigned long long red[FHC_N_SCALARS];
+    // chromosome ids as runs (contact files are grouped by chromosome): run r covers lines [rs[r], rs[r + 1])
+    __shared__ long long rs[kHistMaxRuns + 1];
+    __shared__ unsigned int rv[kHistMaxRuns];
+    if (chrs == nullptr) {
+        for (int r = threadIdx.x; r <= nruns; r += kHistThreads) rs[r] = run_start[r];
+        for (int r = threadIdx.x; r < nruns; r += kHistThreads) rv[r] = run_val[r];
+    }
+    int run = 0;  // this thread's lines only move forward, so does its position in the run table
     for (int s = threadIdx.x; s < S; s += kHistThreads) sh[s] = 0;
     if (threadIdx.x < FHC_N_SCALARS) red[threadIdx.x] = 0;
     __syncthreads();
@@ -90,9 +101,25 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const long long g = t * kHistThreads + threadIdx.x;  // index of this thread's group of 4 contacts
         const int4 a1 = ldg_stream(mid1 + g), a2 = ldg_stream(mid2 + g), ac = ldg_stream(cnt + g);
-        const int4 ah = ldg_stream(chrs + g);
-        unsigned int sk = 0;
         const long long i0 = g * 4;
+        int4 ah;
+        if (chrs != nullptr) {
+            ah = ldg_stream(chrs + g);
+        } else {
+            while (rs[run + 1] <= i0) ++run;
+            const int v = (int)rv[run];
+            ah = make_int4(v, v, v, v);
+            if (rs[run + 1] < i0 + 4) {  // the group of four straddles a run boundary
+                int r2 = run;
+                while (rs[r2 + 1] <= i0 + 1) ++r2;
+                ah.y = (int)rv[r2];
+                while (rs[r2 + 1] <= i0 + 2) ++r2;
+                ah.z = (int)rv[r2];
+                while (rs[r2 + 1] <= i0 + 3) ++r2;
+                ah.w = (int)rv[r2];
+            }
+        }
+        unsigned int sk = 0;
         if (skip != nullptr) {
             sk = __ldg(skip + g);
             // a line is dropped when flagged and not past the reference's stalled pointer (:408-412)
@@ -118,7 +145,21 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
         const unsigned char *sb = reinterpret_cast<const unsigned char *>(skip);
         for (long long i = ntiles * kHistPairsPerTile + threadIdx.x; i < n; i += kHistThreads) {
             const bool skipped = sb != nullptr && sb[i] != 0 && i <= skip_limit;
-            hist_one(m1[i], m2[i], cc[i], hh[i], skipped, Llo, Uhi, res, D, S, sh, hist, present, a);
+            unsigned int ch;
+            if (chrs != nullptr) {
+                ch = hh[i];
+            } else {
+                int lo = 0, hi = nruns - 1;  // last run that starts at or before i
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (rs[mid] <= i)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                ch = rv[lo];
+            }
+            hist_one(m1[i], m2[i], cc[i], ch, skipped, Llo, Uhi, res, D, S, sh, hist, present, a);
         }
     }
     hist_flush(sh, S, hist);
@@ -146,7 +187,7 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
     if (threadIdx.x < FHC_N_SCALARS) {
         const unsigned long long r = red[threadIdx.x];
         if (threadIdx.x == FHC_S_MAX_COUNT)
-            atomicMax(&scalars[threadIdx.x], r);
+            atomicMax(&scalars[max_slot], r);
         else if (r)
             atomicAdd(&scalars[threadIdx.x], r);
     }
@@ -155,21 +196,26 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
 }  // namespace fhc
 
 extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
-                                 const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
-                                 uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, void *stream) {
+                                 const int64_t *run_start, const uint32_t *run_val, int32_t nruns, const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
+                                 uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, int32_t n_rank_slots,
+                                 int32_t my_slot, void *stream) {
     using namespace fhc;
     FHC_REQUIRE(n >= 0 && D > 0 && res > 0, FHC_E_INVALID, "fhc_hist_distance: need n >= 0, D > 0, res > 0 (got %lld, %lld, %d)",
                 (long long)n, (long long)D, res);
     FHC_REQUIRE(hist && present && scalars, FHC_E_INVALID, "fhc_hist_distance: null output pointer");
-    FHC_REQUIRE(n == 0 || (mid1 && mid2 && cnt && chrs), FHC_E_INVALID, "fhc_hist_distance: null input pointer");
+    FHC_REQUIRE(n == 0 || (mid1 && mid2 && cnt), FHC_E_INVALID, "fhc_hist_distance: null input pointer");
+    FHC_REQUIRE(n == 0 || chrs != nullptr || (run_start && run_val && nruns >= 1 && nruns <= FHC_MAX_CHR_RUNS), FHC_E_INVALID,
+                "fhc_hist_distance: need chrs or 1 <= nruns <= %d chromosome runs", FHC_MAX_CHR_RUNS);
     FHC_REQUIRE(aligned16(mid1) && aligned16(mid2) && aligned16(cnt) && aligned16(chrs) && aligned16(skip), FHC_E_INVALID,
                 "fhc_hist_distance: input arrays must be 16-byte aligned");
     FHC_REQUIRE(L >= -1 && U >= -1, FHC_E_INVALID, "fhc_hist_distance: L and U must be >= -1");
+    FHC_REQUIRE(n_rank_slots >= 0 && (n_rank_slots == 0 || (my_slot >= 0 && my_slot < n_rank_slots)), FHC_E_INVALID,
+                "fhc_hist_distance: bad rank slots (%d of %d)", my_slot, n_rank_slots);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     FHC_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * D, st));
     FHC_CUDA(cudaMemsetAsync(present, 0, sizeof(uint32_t) * ((D + 31) / 32), st));
-    FHC_CUDA(cudaMemsetAsync(scalars, 0, sizeof(uint64_t) * FHC_N_SCALARS, st));
+    FHC_CUDA(cudaMemsetAsync(scalars, 0, sizeof(uint64_t) * (FHC_N_SCALARS + n_rank_slots), st));
     if (n == 0) return FHC_OK;
     const int S = (int)(D < kHistSmemSlotsMax ? D : kHistSmemSlotsMax);
     const size_t smem = sizeof(unsigned int) * (size_t)S;
@@ -181,9 +227,10 @@ extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const
     const long long Uhi = U < 0 ? INT64_MAX : U;
     hist_distance_kernel<<<grid, kHistThreads, smem, st>>>(
         reinterpret_cast<const int4 *>(mid1), reinterpret_cast<const int4 *>(mid2), reinterpret_cast<const int4 *>(cnt),
-        reinterpret_cast<const int4 *>(chrs), reinterpret_cast<const unsigned int *>(skip), skip_limit, n, Llo, Uhi,
+        reinterpret_cast<const int4 *>(chrs), reinterpret_cast<const long long *>(run_start), run_val, nruns,
+        reinterpret_cast<const unsigned int *>(skip), skip_limit, n, Llo, Uhi,
         (unsigned int)res, reinterpret_cast<unsigned long long *>(hist), present, D, S,
-        reinterpret_cast<unsigned long long *>(scalars));
+        reinterpret_cast<unsigned long long *>(scalars), n_rank_slots > 0 ? FHC_N_SCALARS + my_slot : FHC_S_MAX_COUNT);
     FHC_LAUNCH_CHECK("hist_distance_kernel");
     return FHC_OK;
 }

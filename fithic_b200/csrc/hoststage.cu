@@ -134,7 +134,7 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
                     "fhc_host_stage: null buffer (phase 1)");
         const uint64_t *hist = io->k1buf;
         const uint64_t *scal = io->k1buf + D;
-        const uint32_t *present = reinterpret_cast<const uint32_t *>(io->k1buf + D + FHC_N_SCALARS);
+        const uint32_t *present = reinterpret_cast<const uint32_t *>(io->k1buf + D + FHC_N_SCALARS + io->n_rank_slots);
         const bool any_present = scal[FHC_S_NONPOS_LINES] != 0;
         int64_t m = 0;
         if (!any_present) {
@@ -245,7 +245,9 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         const int ngroups = (nb + 3) / 4;
         // lbeta tables
         int64_t lb_N[2] = {0, 0}, lb_n[2] = {0, 0};
-        const int64_t max_count = (int64_t)scal[FHC_S_MAX_COUNT];
+        int64_t max_count = (int64_t)scal[FHC_S_MAX_COUNT];
+        for (int r = 0; r < io->n_rank_slots; ++r)  // multi-GPU: every rank's maximum arrives in its own slot
+            if ((int64_t)scal[FHC_N_SCALARS + r] > max_count) max_count = (int64_t)scal[FHC_N_SCALARS + r];
         for (int w = 0; w < 2; ++w) {
             if (io->lbeta_tab[w] == nullptr) continue;
             const int64_t Nw = w == 0 ? N : (int64_t)scal[FHC_S_INTER_ALL_SUM];

@@ -341,7 +341,8 @@ extern "C" int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *pr
 }
 
 extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt,
-                           const uint32_t *chrs, int64_t n, const double *bias, const int32_t *bias_mid,
+                           const uint32_t *chrs, const int64_t *run_start, const uint32_t *run_val, int32_t nruns,
+                           int64_t n, const double *bias, const int32_t *bias_mid,
                            const int64_t *chr_off, int32_t nchr, int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut,
                            int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
                            const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
@@ -352,7 +353,9 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
                 "fhc_pvalues: unknown mode %d", mode);
     FHC_REQUIRE(n >= 0 && res > 0, FHC_E_INVALID, "fhc_pvalues: need n >= 0 and res > 0");
     if (n == 0) return FHC_OK;
-    FHC_REQUIRE(mid1 && mid2 && cnt && chrs && p && expcc, FHC_E_INVALID, "fhc_pvalues: null pointer");
+    FHC_REQUIRE(mid1 && mid2 && cnt && p && expcc, FHC_E_INVALID, "fhc_pvalues: null pointer");
+    FHC_REQUIRE(chrs != nullptr || (run_start && run_val && nruns >= 1 && nruns <= FHC_MAX_CHR_RUNS), FHC_E_INVALID,
+                "fhc_pvalues: need chrs or 1 <= nruns <= %d chromosome runs", FHC_MAX_CHR_RUNS);
     FHC_REQUIRE(aligned16(mid1) && aligned16(mid2) && aligned16(cnt) && aligned16(chrs) && aligned16(p) && aligned16(expcc),
                 FHC_E_INVALID, "fhc_pvalues: contact and output arrays must be 16-byte aligned");
     FHC_REQUIRE(mode == FHC_MODE_INTER_ONLY || (lut != nullptr && D > 0), FHC_E_INVALID,
@@ -370,6 +373,9 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.mid2 = reinterpret_cast<const int4 *>(mid2);
     P.cnt = reinterpret_cast<const int4 *>(cnt);
     P.chrs = reinterpret_cast<const int4 *>(chrs);
+    P.run_start = reinterpret_cast<const long long *>(run_start);
+    P.run_val = run_val;
+    P.nruns = chrs ? 0 : nruns;
     P.n = n;
     P.bias = bias;
     P.bias_mid = bias_mid;
@@ -409,6 +415,8 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     if (workspace != nullptr && impl == 0) return pvalues_lists_launch(P, workspace, workspace_bytes, st);
+    FHC_REQUIRE(chrs != nullptr, FHC_E_INVALID, "fhc_pvalues: the tile-phased kernel needs the chrs array (chromosome runs are "
+                "read by the work-list pipeline: pass a workspace)");
     return pvalues_tile_launch(P, st);
 }
 

@@ -16,7 +16,10 @@ __device__ __forceinline__ unsigned int fastdiv(unsigned int n, const FastDiv &f
 
 struct PvalParams {
     int mode;  // FHC_MODE_*
-    const int4 *mid1, *mid2, *cnt, *chrs;
+    const int4 *mid1, *mid2, *cnt, *chrs;  // chrs == nullptr: the chromosome ids come as runs (work-list pipeline only)
+    const long long *run_start;            // run r covers lines [run_start[r], run_start[r + 1]) of the caller's arrays,
+    const unsigned int *run_val;           // counted like line_base (this call starts at line_base); all have chrs = run_val[r]
+    int nruns;
     long long n;
     const double *bias;
     const int *bias_mid;  // nullptr: every slot holds the locus at mid = slot * res + res / 2 (regular grid)

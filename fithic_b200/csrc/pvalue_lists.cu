@@ -87,26 +87,50 @@ __device__ __forceinline__ double bias_lookup_sel(const PvalParams &P, const Fro
     return ok ? b : -1.0;
 }
 
+// the same when the chromosome -- and with it the slot range -- is known for the whole tile
+template <bool REGULAR>
+__device__ __forceinline__ double bias_lookup_rng(const PvalParams &P, const FrontConst &F, int2 rng, bool chr_ok, int mid) {
+    bool ok = chr_ok && mid >= 0;
+    const unsigned int k = fastdiv31((unsigned int)mid, P, F);  // garbage for mid < 0, masked by ok
+    int s = rng.x + (int)k;
+    ok = ok && s < rng.y && s >= rng.x;
+    s = ok ? s : 0;
+    if (REGULAR)
+        ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
+    else
+        ok = ok && __ldg(P.bias_mid + s) == mid;
+    const double b = __ldg(P.bias + s);
+    return ok ? b : -1.0;
+}
+
 // phase A of a contact: the three gathers (two bias values, the distance table), issued for all four contacts of a group
 // before anything consumes them so that their L2 latencies overlap
-template <bool HAS_BIAS, bool REGULAR>
-__device__ __forceinline__ void front_gather(const PvalParams &P, const FrontConst &F, const int2 *chr_rng, bool rng32, int m1,
-                                             int m2, unsigned int ch, double &b1, double &b2, double &tabv, unsigned int &d) {
+// INTRA: every contact of the tile lies on one chromosome (known from the chromosome runs): `ch` is that chromosome's
+// id pair, `rng` / `chr_ok` its slot range in the bias table, and nothing per contact depends on chromosome ids.
+template <bool HAS_BIAS, bool REGULAR, bool INTRA>
+__device__ __forceinline__ void front_gather(const PvalParams &P, const FrontConst &F, const int2 *chr_rng, bool rng32, int2 rng,
+                                             bool chr_ok, int m1, int m2, unsigned int ch, double &b1, double &b2, double &tabv,
+                                             unsigned int &d) {
     const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
     d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
     b1 = 1.0;
     b2 = 1.0;
     if (HAS_BIAS) {
         if (rng32) {  // uniform
-            b1 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c1, m1);
-            b2 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c2, m2);
+            if (INTRA) {
+                b1 = bias_lookup_rng<REGULAR>(P, F, rng, chr_ok, m1);
+                b2 = bias_lookup_rng<REGULAR>(P, F, rng, chr_ok, m2);
+            } else {
+                b1 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c1, m1);
+                b2 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c2, m2);
+            }
         } else {
             b1 = bias_lookup(P, c1, m1);
             b2 = bias_lookup(P, c2, m2);
         }
     }
     const unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
-    const bool slot_ok = c1 == c2 && slot < F.D32;
+    const bool slot_ok = (INTRA || c1 == c2) && slot < F.D32;
     tabv = NAN;  // beyond the table (or an inter line, which never uses it)
     if (P.lut != nullptr) {  // uniform branch; the index is always valid
         const double t = __ldg(P.lut + (slot_ok ? slot : 0u));
@@ -115,11 +139,13 @@ __device__ __forceinline__ void front_gather(const PvalParams &P, const FrontCon
 }
 
 // phase B: classification from the gathered values
+// INTRA: an intra tile of a run that is not interOnly (the caller checks the mode): the intra branch with constants folded
+template <bool INTRA>
 __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, unsigned int d, int c,
                                                    unsigned int ch, bool in_file, double b1, double b2, double tabv,
                                                    double &p, double &e, double &prior, bool &use_inter) {
-    const bool inter = (ch & 0xffffu) != (ch >> 16);
-    const bool intra_path = !inter && P.mode != FHC_MODE_INTER_ONLY;
+    const bool inter = INTRA ? false : (ch & 0xffffu) != (ch >> 16);
+    const bool intra_path = INTRA ? true : (!inter && P.mode != FHC_MODE_INTER_ONLY);
     const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
     const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
     const bool scored = in_file && !discarded && (intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
@@ -155,6 +181,8 @@ __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const Fr
 
 // ---- front ------------------------------------------------------------------------------------------------------------
 struct FrontSmem {
+    long long run_start[FHC_MAX_CHR_RUNS + 1];  // chromosome ids as runs (P.chrs == nullptr): run r = lines [rs[r], rs[r+1])
+    unsigned int run_val[FHC_MAX_CHR_RUNS];
     int2 chr_rng[kChrSmem];  // [first slot, end) of each chromosome in the dense bias table
     double x[kFrontTile];
     int cnt[kFrontTile];  // count | inter << 31
@@ -162,114 +190,176 @@ struct FrontSmem {
     unsigned long long base_cf, base_tail;
 };
 
+// chromosome id pair of one line from the run table (binary search; only tiles that straddle a run boundary come here)
+__device__ __forceinline__ unsigned int run_lookup(const FrontSmem &S, int nruns, long long line) {
+    int lo = 0, hi = nruns - 1;  // last run that starts at or before `line`
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (S.run_start[mid] <= line)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return S.run_val[lo];
+}
+
+// One tile of kFrontTile contacts: loads, gathers, classification, closed forms, stores of p and ExpCC; the contacts that
+// need iterating are parked in S.x / S.cnt.  Returns the 2-bit classes of this thread's 8 contacts.
 // kG contacts per thread and load (4: 128-bit loads and stores, 80 registers, 3 CTAs per SM; 2: 64-bit loads, 128-bit
 // stores of two doubles, fits 64 registers, 4 CTAs per SM); a thread handles 8 contacts of a tile either way.
+// INTRA: the whole (full) tile lies in one intra chromosome run: no chromosome ids per contact at all.
+template <bool HAS_BIAS, bool REGULAR, int kG, bool INTRA>
+__device__ __forceinline__ unsigned int front_tile(const PvalParams &P, const FrontConst &F, FrontSmem &S, bool rng32,
+                                                   long long base, bool full, bool tile_one_run, unsigned int tile_ch,
+                                                   unsigned int &flagged) {
+    const int tid = threadIdx.x;
+    const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
+    const int *cs = reinterpret_cast<const int *>(P.cnt);
+    const unsigned int *hs = reinterpret_cast<const unsigned int *>(P.chrs);
+    int2 rng = make_int2(0, 0);
+    bool chr_ok = false;
+    if (INTRA && HAS_BIAS && rng32) {
+        const unsigned int c = tile_ch & 0xffffu;
+        chr_ok = c < (unsigned int)P.nchr;
+        rng = S.chr_rng[chr_ok ? c : 0u];
+    }
+    unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
+#pragma unroll
+    for (int h = 0; h < 8 / kG; ++h) {
+        const int l0 = (h * kFrontThreads + tid) * kG;
+        int m1[kG], m2[kG], cc[kG];
+        unsigned int ch[kG];
+        if (full) {
+            if (kG == 4) {
+                const long long g = (base + l0) >> 2;
+                const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
+                m1[0] = a1.x; m1[1] = a1.y; m1[kG - 2] = a1.z; m1[kG - 1] = a1.w;
+                m2[0] = a2.x; m2[1] = a2.y; m2[kG - 2] = a2.z; m2[kG - 1] = a2.w;
+                cc[0] = ac.x; cc[1] = ac.y; cc[kG - 2] = ac.z; cc[kG - 1] = ac.w;
+                if (!INTRA && P.chrs != nullptr) {
+                    const int4 ah = ldg_stream(P.chrs + g);
+                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
+                    ch[kG - 2] = (unsigned int)ah.z; ch[kG - 1] = (unsigned int)ah.w;
+                }
+            } else {
+                const long long g = (base + l0) >> 1;
+                const int2 a1 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid1) + g);
+                const int2 a2 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid2) + g);
+                const int2 ac = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + g);
+                m1[0] = a1.x; m1[1] = a1.y;
+                m2[0] = a2.x; m2[1] = a2.y;
+                cc[0] = ac.x; cc[1] = ac.y;
+                if (!INTRA && P.chrs != nullptr) {
+                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + g);
+                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
+                }
+            }
+            if (INTRA || P.chrs == nullptr) {
+#pragma unroll
+                for (int k = 0; k < kG; ++k)
+                    ch[k] = (INTRA || tile_one_run) ? tile_ch : run_lookup(S, P.nruns, P.line_base + base + l0 + k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kG; ++k) {
+                const long long i = base + l0 + k;
+                const bool ok = i < P.n;
+                m1[k] = ok ? m1s[i] : 0;
+                m2[k] = ok ? m2s[i] : 0;
+                cc[k] = ok ? cs[i] : 0;
+                ch[k] = 0x00010000u;  // padding: an inter line
+                if (ok) ch[k] = P.chrs != nullptr ? hs[i] : (tile_one_run ? tile_ch : run_lookup(S, P.nruns, P.line_base + i));
+            }
+        }
+        double e[kG], pv[kG], gb1[kG], gb2[kG], gtv[kG];
+        unsigned int dd[kG];
+#pragma unroll
+        for (int k = 0; k < kG; ++k)
+            front_gather<HAS_BIAS, REGULAR, INTRA>(P, F, S.chr_rng, rng32, rng, chr_ok, m1[k], m2[k], ch[k], gb1[k], gb2[k],
+                                                   gtv[k], dd[k]);
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {
+            const int li = l0 + k;
+            double prior;
+            bool use_inter;
+            const bool in_file = full || base + li < P.n;
+            const PvalClass cls = front_prepare<INTRA>(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k],
+                                                       prior, use_inter);
+            if (cls == kClsK0) {
+                pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
+            } else if (cls != kClsDone) {
+                S.x[li] = prior;
+                S.cnt[li] = cc[k] | (use_inter ? (int)0x80000000u : 0);
+                pv[k] = 0.0;  // overwritten by pval_finish_kernel
+            }
+            codes |= (unsigned int)cls << (2 * (h * kG + k));
+        }
+        if (full) {
+            double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
+            double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
+#pragma unroll
+            for (int k = 0; k < kG; k += 2) {
+                __stcs(ee + k / 2, make_double2(e[k], e[k + 1]));
+                pp[k / 2] = make_double2(pv[k], pv[k + 1]);  // default caching: the finish kernel writes into these lines soon
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kG; ++k)
+                if (base + l0 + k < P.n) {
+                    P.expcc[base + l0 + k] = e[k];
+                    P.p[base + l0 + k] = pv[k];
+                }
+        }
+        if (P.outl != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kG; ++k) {
+                const unsigned int c = (codes >> (2 * (h * kG + k))) & 3u;
+                if ((c == kClsDone || c == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
+            }
+        }
+    }
+    return codes;
+}
+
 template <bool HAS_BIAS, bool REGULAR, int kMinCtas, int kG>
 __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(const PvalParams P, const FrontConst F,
                                                                              const ListsWs W) {
-    __shared__ FrontSmem S;
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    FrontSmem &S = *reinterpret_cast<FrontSmem *>(front_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool rng32 = false;
     if (HAS_BIAS) {
         rng32 = !P.bias_sparse && P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
-        if (rng32) {
+        if (rng32)
             for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
-            __syncthreads();
-        }
     }
+    const bool runs = P.chrs == nullptr;
+    if (runs) {
+        for (int r = tid; r <= P.nruns; r += kFrontThreads) S.run_start[r] = P.run_start[r];
+        for (int r = tid; r < P.nruns; r += kFrontThreads) S.run_val[r] = P.run_val[r];
+    }
+    __syncthreads();
     const long long ntiles = (P.n + kFrontTile - 1) / kFrontTile;
     unsigned int flagged = 0;
-    const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
-    const int *cs = reinterpret_cast<const int *>(P.cnt);
-    const unsigned int *hs = reinterpret_cast<const unsigned int *>(P.chrs);
+    int run = 0;  // the tiles of this CTA only move forward, so does its position in the run table
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * kFrontTile;
         const bool full = base + kFrontTile <= P.n;
-        unsigned int codes = 0;  // 2 bits per contact of this thread: PvalClass
-#pragma unroll
-        for (int h = 0; h < 8 / kG; ++h) {
-            const int l0 = (h * kFrontThreads + tid) * kG;
-            int m1[kG], m2[kG], cc[kG];
-            unsigned int ch[kG];
-            if (full) {
-                if (kG == 4) {
-                    const long long g = (base + l0) >> 2;
-                    const int4 a1 = ldg_stream(P.mid1 + g), a2 = ldg_stream(P.mid2 + g), ac = ldg_stream(P.cnt + g);
-                    const int4 ah = ldg_stream(P.chrs + g);
-                    m1[0] = a1.x; m1[1] = a1.y; m1[kG - 2] = a1.z; m1[kG - 1] = a1.w;
-                    m2[0] = a2.x; m2[1] = a2.y; m2[kG - 2] = a2.z; m2[kG - 1] = a2.w;
-                    cc[0] = ac.x; cc[1] = ac.y; cc[kG - 2] = ac.z; cc[kG - 1] = ac.w;
-                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
-                    ch[kG - 2] = (unsigned int)ah.z; ch[kG - 1] = (unsigned int)ah.w;
-                } else {
-                    const long long g = (base + l0) >> 1;
-                    const int2 a1 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid1) + g);
-                    const int2 a2 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid2) + g);
-                    const int2 ac = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + g);
-                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + g);
-                    m1[0] = a1.x; m1[1] = a1.y;
-                    m2[0] = a2.x; m2[1] = a2.y;
-                    cc[0] = ac.x; cc[1] = ac.y;
-                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kG; ++k) {
-                    const long long i = base + l0 + k;
-                    const bool ok = i < P.n;
-                    m1[k] = ok ? m1s[i] : 0;
-                    m2[k] = ok ? m2s[i] : 0;
-                    cc[k] = ok ? cs[i] : 0;
-                    ch[k] = ok ? hs[i] : 0x00010000u;  // padding: an inter line
-                }
-            }
-            double e[kG], pv[kG], gb1[kG], gb2[kG], gtv[kG];
-            unsigned int dd[kG];
-#pragma unroll
-            for (int k = 0; k < kG; ++k)
-                front_gather<HAS_BIAS, REGULAR>(P, F, S.chr_rng, rng32, m1[k], m2[k], ch[k], gb1[k], gb2[k], gtv[k], dd[k]);
-#pragma unroll
-            for (int k = 0; k < kG; ++k) {
-                const int li = l0 + k;
-                double prior;
-                bool use_inter;
-                const bool in_file = full || base + li < P.n;
-                const PvalClass cls = front_prepare(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k],
-                                                    prior, use_inter);
-                if (cls == kClsK0) {
-                    pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
-                } else if (cls != kClsDone) {
-                    S.x[li] = prior;
-                    S.cnt[li] = cc[k] | (use_inter ? (int)0x80000000u : 0);
-                    pv[k] = 0.0;  // overwritten by pval_finish_kernel
-                }
-                codes |= (unsigned int)cls << (2 * (h * kG + k));
-            }
-            if (full) {
-                double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
-                double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
-#pragma unroll
-                for (int k = 0; k < kG; k += 2) {
-                    __stcs(ee + k / 2, make_double2(e[k], e[k + 1]));
-                    pp[k / 2] = make_double2(pv[k], pv[k + 1]);  // default caching: the finish kernel writes into these lines soon
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < kG; ++k)
-                    if (base + l0 + k < P.n) {
-                        P.expcc[base + l0 + k] = e[k];
-                        P.p[base + l0 + k] = pv[k];
-                    }
-            }
-            if (P.outl != nullptr) {
-#pragma unroll
-                for (int k = 0; k < kG; ++k) {
-                    const unsigned int c = (codes >> (2 * (h * kG + k))) & 3u;
-                    if ((c == kClsDone || c == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
-                }
-            }
+        bool one_run = false;
+        unsigned int tile_ch = 0;
+        if (runs) {
+            const long long g0 = P.line_base + base;
+            while (S.run_start[run + 1] <= g0) ++run;
+            const long long g1 = P.line_base + (full ? base + kFrontTile : P.n);
+            one_run = S.run_start[run + 1] >= g1;
+            tile_ch = S.run_val[run];
         }
+        unsigned int codes;
+        if (one_run && full && (tile_ch & 0xffffu) == (tile_ch >> 16) && P.mode != FHC_MODE_INTER_ONLY)
+            codes = front_tile<HAS_BIAS, REGULAR, kG, true>(P, F, S, rng32, base, full, one_run, tile_ch, flagged);
+        else
+            codes = front_tile<HAS_BIAS, REGULAR, kG, false>(P, F, S, rng32, base, full, one_run, tile_ch, flagged);
         // positions in the two lists: CTA-wide exclusive scan of (continued fractions | tail sums << 16) per thread
         unsigned int mine = 0;
 #pragma unroll
@@ -325,6 +415,8 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
         if (lane == 0 && f) atomicAdd(P.outl_stats, f);
     }
 }
+
+static_assert(sizeof(FrontSmem) <= 48 * 1024, "the front kernel's shared memory must fit the default 48 KB");
 
 // ---- iterate ----------------------------------------------------------------------------------------------------------
 // One list, one kind of recurrence.  A warp claims a chunk of kIterChunk list positions with one global atomic, loads the
@@ -564,11 +656,11 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
 #define FHC_FRONT_V(B, R)                                                                                         \
     do {                                                                                                          \
         if (variant == 2)                                                                                         \
-            pval_front_kernel<B, R, 4, 2><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+            pval_front_kernel<B, R, 4, 2><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
         else if (variant == 1)                                                                                    \
-            pval_front_kernel<B, R, 4, 4><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+            pval_front_kernel<B, R, 4, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
         else                                                                                                      \
-            pval_front_kernel<B, R, 3, 4><<<(unsigned int)blocks, kFrontThreads, 0, st>>>(P, F, W);               \
+            pval_front_kernel<B, R, 3, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
     } while (0)
     if (!P.bias)
         FHC_FRONT_V(false, true);

@@ -396,7 +396,7 @@ extern "C" int64_t fhc_io_write_significances(const char *path, const char *cons
                                               const uint32_t *chrs, const double *p, const double *q, const double *expcc,
                                               int64_t n, int32_t mode, int64_t L, int64_t U, const double *bias,
                                               const int32_t *bias_mid, const int64_t *chr_off, int32_t nbias_chr,
-                                              int32_t res, int32_t nthreads, int32_t level) {
+                                              int32_t res, int32_t nthreads, int32_t level, int32_t header) {
     FHC_REQUIRE(path && chrom_names && nchrom >= 0 && n >= 0, FHC_E_INVALID, "fhc_io_write_significances: bad arguments");
     FHC_REQUIRE(n == 0 || (mid1 && mid2 && cnt && chrs && p && q && expcc), FHC_E_INVALID,
                 "fhc_io_write_significances: null array");
@@ -441,7 +441,7 @@ extern "C" int64_t fhc_io_write_significances(const char *path, const char *cons
             }
             text.clear();
             int64_t rows = 0;
-            if (b == 0) {
+            if (b == 0 && header) {
                 const char *hdr = "chr1\tfragmentMid1\tchr2\tfragmentMid2\tcontactCount\tp-value\tq-value\tbias1\tbias2\tExpCC\n";
                 text.insert(text.end(), hdr, hdr + strlen(hdr));
             }

@@ -153,7 +153,7 @@ class _HostStage:
             return
         self.D = D
         nwords = (D + 31) // 32
-        self.k1 = torch.empty(D + _capi.N_SCALARS + (nwords + 1) // 2, dtype=torch.int64).pin_memory()
+        self.k1 = torch.empty(D + _capi.N_SCALARS + 64 + (nwords + 1) // 2, dtype=torch.int64).pin_memory()
         self.k1_np = self.k1.numpy()
         self.lut = torch.empty(D, dtype=torch.float64).pin_memory()
         self.io.k1buf = self.k1.data_ptr()
@@ -169,11 +169,16 @@ class _HostStage:
         return cur
 
     def new_outputs(self):
-        """Fresh arrays for the outputs that go into the pass's result dict."""
+        """The stage writes into two blocks that live as long as the engine (fresh arrays would cost a page fault per
+        4 kB on the critical path: 0.3 ms per pass at 5 kb); run_pass copies what goes into the result dict out of them
+        after it has launched K3 and K4, while the GPU is busy."""
         D, nb = self.D, int(self.io.noOfBins)
         io = self.io
-        self.i64 = i64 = np.empty(3 * D + 4 * nb, dtype=np.int64)
-        self.f64 = f64 = np.empty(D + 5 * nb + 2 * (nb + 4), dtype=np.float64)
+        if getattr(self, "_blk_shape", None) == (D, nb):
+            return
+        self._blk_shape = (D, nb)
+        self.i64 = i64 = np.zeros(3 * D + 4 * nb, dtype=np.int64)
+        self.f64 = f64 = np.zeros(D + 5 * nb + 2 * (nb + 4), dtype=np.float64)
         b = i64.ctypes.data
         io.dists, io.sums, io.splineX = b, b + 8 * D, b + 16 * D
         b += 24 * D
@@ -242,6 +247,7 @@ class Engine:
             self._bias_sparse = 1 if biases.sparse else 0
         self._ws = {}
         self.contacts = None
+        self.chr_runs_dev = None
         self.n = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -264,41 +270,73 @@ class Engine:
         return cur[:n]
 
     # ------------------------------------------------------------------------------------------------------------
-    def set_contacts_device(self, mid1, mid2, cnt, chrs):
-        """Adopt device-resident int32 tensors (chrs holds the uint32 bit pattern)."""
+    def set_contacts_device(self, mid1, mid2, cnt, chrs, chr_runs=None):
+        """Adopt device-resident int32 tensors (chrs holds the uint32 bit pattern).  chr_runs = (values uint32 [r], lengths
+        int64 [r]), the run-length form of chrs (see Contacts.chr_runs): with it K1 and K3 never read a chrs array, and
+        `chrs` may be None."""
         n = mid1.numel()
-        for t in (mid1, mid2, cnt, chrs):
+        for t in (mid1, mid2, cnt) + ((chrs,) if chrs is not None else ()):
             assert t.is_cuda and t.dtype == torch.int32 and t.numel() == n and t.is_contiguous()
-        self.contacts = (mid1, mid2, cnt, chrs)
         self.n = n
         self.D = None
         self._own_contacts = False
+        self.chr_runs_dev = None
+        self._chr_runs_host = None
+        if chr_runs is not None and 1 <= len(chr_runs[0]) <= _capi.MAX_CHR_RUNS and n > 0 \
+                and os.environ.get("FHC_CHR_RUNS", "1") != "0":
+            vals = np.ascontiguousarray(chr_runs[0], dtype=np.uint32)
+            starts = np.zeros(len(vals) + 1, dtype=np.int64)
+            np.cumsum(np.asarray(chr_runs[1], dtype=np.int64), out=starts[1:])
+            assert int(starts[-1]) == n, "chr_runs do not cover the contacts"
+            self._chr_runs_host = (vals, starts)
+            self.chr_runs_dev = (torch.from_numpy(starts).to(self.device), torch.from_numpy(vals.view(np.int32)).to(self.device),
+                                 len(vals))
+        elif chrs is None:
+            if chr_runs is None:
+                raise ValueError("need the chrs array or its run-length form")
+            chrs = self._expand_runs(chr_runs, n)
+        self.contacts = (mid1, mid2, cnt, chrs)
+
+    def _expand_runs(self, chr_runs, n, into=None):
+        """chrs array from its run-length form (one fill per run; torch.repeat_interleave parallelises over the runs, not over
+        the output: 30 ms for 24 runs of 12 M)."""
+        d = into if into is not None else torch.empty(n, dtype=torch.int32, device=self.device)
+        pos = 0
+        for v, ln in zip(np.asarray(chr_runs[0]).view(np.int32).tolist(), np.asarray(chr_runs[1]).tolist()):
+            d[pos:pos + ln].fill_(v)
+            pos += ln
+        assert pos == n, "chr_runs do not cover the contacts"
+        return d
+
+    def chrs_array(self):
+        """The per-line chrs array on the device; built from the runs on first use when the contacts came without one (only
+        the tile-phased K3 and callers outside the hot path ask for it)."""
+        mid1, mid2, cnt, chrs = self.contacts
+        if chrs is None:
+            vals, starts = self._chr_runs_host
+            chrs = self._expand_runs((vals, np.diff(starts)), self.n)
+            self.contacts = (mid1, mid2, cnt, chrs)
+        return chrs
 
     def upload_contacts(self, c, non_blocking=False):
-        """Host SoA -> HBM (the only per-contact host->device traffic of a run: 16 B per contact)."""
+        """Host SoA -> HBM (the only per-contact host->device traffic of a run: 12 B per contact when the chromosome ids
+        come as runs, 16 B otherwise)."""
         ts = []
         reuse = self.contacts if (self.contacts is not None and getattr(self, "_own_contacts", False)
                                   and self.n == len(c)) else None
-        runs = c.chr_runs if (c.chr_runs is not None and len(c.chr_runs[0]) <= self.MAX_CHR_RUNS) else None
+        runs = c.chr_runs if (c.chr_runs is not None and 1 <= len(c.chr_runs[0]) <= _capi.MAX_CHR_RUNS
+                              and os.environ.get("FHC_CHR_RUNS", "1") != "0") else None
         for j, a in enumerate((c.mid1, c.mid2, c.cnt, c.chrs.view(np.int32) if runs is None else None)):
             if a is None:
-                # chromosome ids from their run-length form: nothing over the link instead of 4 B per line; one fill per run
-                # (torch.repeat_interleave parallelises over the runs, not over the output: 30 ms for 24 runs of 12 M)
-                assert int(np.sum(runs[1])) == len(c), "chr_runs do not cover the contacts"
-                d = reuse[j] if reuse is not None else torch.empty(len(c), dtype=torch.int32, device=self.device)
-                pos = 0
-                for v, ln in zip(np.asarray(runs[0]).view(np.int32).tolist(), np.asarray(runs[1]).tolist()):
-                    d[pos:pos + ln].fill_(v)
-                    pos += ln
-                ts.append(d)
+                ts.append(None)  # chromosome ids from their run-length form: nothing over the link, nothing in HBM
                 continue
             h = torch.from_numpy(np.ascontiguousarray(a))
-            if reuse is not None:  # same size as the previous upload: no new device allocation
+            if reuse is not None and reuse[j] is not None:  # same size as the previous upload: no new device allocation
                 reuse[j].copy_(h, non_blocking=non_blocking)
                 ts.append(reuse[j])
             else:
                 ts.append(h.to(self.device, non_blocking=non_blocking))
-        self.set_contacts_device(*ts)
+        self.set_contacts_device(*ts, chr_runs=runs)
         self._own_contacts = True
 
     def distance_slots(self):
@@ -323,15 +361,20 @@ class Engine:
     def hist_distance(self, skip=None, skip_limit=-1):
         D = self.distance_slots()
         mid1, mid2, cnt, chrs = self.contacts
-        # one buffer [hist | totals | seen bitmap] so that the host needs a single device->host copy per pass
+        # one buffer [hist | totals | one slot per rank for the largest count | seen bitmap]: a single all-reduce(sum) between
+        # GPUs and a single device->host copy per pass
         nwords = (D + 31) // 32
-        buf = self._tensor("k1buf", D + _capi.N_SCALARS + (nwords + 1) // 2, torch.int64)
+        slots = self.dist.world if self.dist is not None else 0
+        my = self.dist.rank if self.dist is not None else 0
+        ns = _capi.N_SCALARS + slots
+        buf = self._tensor("k1buf", D + ns + (nwords + 1) // 2, torch.int64)
         hist = buf[:D]
-        scal = buf[D:D + _capi.N_SCALARS]
-        present = buf[D + _capi.N_SCALARS:].view(torch.int32)[:nwords]
-        check(self.lib.fhc_hist_distance(dptr(mid1), dptr(mid2), dptr(cnt), dptr(chrs), dptr(skip), int(skip_limit),
-                                         self.n, self.st.L, self.st.U, self.grid, dptr(hist), dptr(present), D,
-                                         dptr(scal), self._stream()))
+        scal = buf[D:D + ns]
+        present = buf[D + ns:].view(torch.int32)[:nwords]
+        rs, rv, nruns = self.chr_runs_dev if self.chr_runs_dev is not None else (None, None, 0)
+        check(self.lib.fhc_hist_distance(dptr(mid1), dptr(mid2), dptr(cnt), None if nruns else dptr(self.chrs_array()), dptr(rs), dptr(rv),
+                                         nruns, dptr(skip), int(skip_limit), self.n, self.st.L, self.st.U, self.grid,
+                                         dptr(hist), dptr(present), D, dptr(scal), slots, my, self._stream()))
         return hist, present, scal
 
     # ------------------------------------------------------------------------------------------------------------
@@ -348,10 +391,16 @@ class Engine:
         if passNo > 1 and outl is not None:
             skip = outl
             first_dup = int(outl_stats[1].item()) & _U64_MAX
-            skip_limit = self.n if first_dup == _U64_MAX else first_dup
+            if self.dist is not None and passNo > 2:
+                # The reference stops skipping outlier lines after the first duplicated entry of its sorted outlier list
+                # (from pass 3 on, fithic/fithic.py:408-412), a position in FILE order: the ranks agree on the smallest
+                # global line number of a first duplicate and translate it back into their own lines.
+                skip_limit = self._global_skip_limit(first_dup)
+            else:
+                skip_limit = self.n if first_dup == _U64_MAX else first_dup
         hist_d, present_d, scal_d = self.hist_distance(skip, skip_limit)
-        if self.dist is not None:
-            self.dist.allreduce_hist(hist_d, present_d, scal_d, fused=self._ws["k1buf"][:self.D + _capi.N_SCALARS])
+        if self.dist is not None:  # exchange 1: [hist | totals | rank slots] summed over the GPUs in one collective
+            self.dist.allreduce_k1(self._ws["k1buf"][:self.D + scal_d.numel()])
         native = (st.resolution > 0 and self.D <= self.NATIVE_STAGE_MAX_SLOTS
                   and os.environ.get("FHC_HOST_STAGE", "native") != "legacy")
         tables = self._tables_native if native else self._tables_legacy
@@ -380,8 +429,59 @@ class Engine:
         else:
             q = self.bh_qvalues(p, float(T))
         out.update(p=p, q=q, expcc=e)
+        late = getattr(out, "_late", None)
+        if late:  # the per-distance arrays of the native host stage leave its buffers now, while the GPU works
+            for k, a in late.items():
+                out[k] = a.copy()
+            out._late = None
         self.timings[passNo] = ev
         return out
+
+    def set_line_runs(self, starts, lengths):
+        """Where this rank's lines sit in the whole file: local lines come as runs, run j = `lengths[j]` consecutive lines
+        of the file starting at global line `starts[j]` (ascending).  Needed by multi-GPU runs with more than two spline
+        passes (the reference's outlier skipping stalls at a position in file order) and by writers that restore file order."""
+        starts, lengths = np.asarray(starts, dtype=np.int64), np.asarray(lengths, dtype=np.int64)
+        assert len(starts) == len(lengths) and int(lengths.sum()) == self.n, "line runs do not cover this rank's contacts"
+        assert np.all(starts[1:] >= starts[:-1] + lengths[:-1]), "line runs must be ascending and disjoint"
+        self.line_runs = (starts, lengths)
+
+    def digest(self, p, q):
+        """Order-independent digest (two uint64 sums of hashes) of (file line, p bits, q bits) over this rank's lines
+        (fhc_digest_lines); shards' digests add up mod 2^64.  Without set_line_runs() the local lines count as file lines."""
+        runs = getattr(self, "line_runs", None)
+        if runs is None:
+            runs = (np.zeros(1, dtype=np.int64), np.array([self.n], dtype=np.int64))
+        starts, lens = runs
+        keep = lens > 0
+        starts, lens = starts[keep], lens[keep]
+        if len(starts) == 0:
+            return 0, 0
+        loc = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=loc[1:])
+        rl = torch.from_numpy(loc).to(self.device)
+        rg = torch.from_numpy(np.ascontiguousarray(starts)).to(self.device)
+        out = torch.zeros(2, dtype=torch.int64, device=self.device)
+        check(self.lib.fhc_digest_lines(dptr(p), dptr(q), self.n, dptr(rl), dptr(rg), len(lens), dptr(out), self._stream()))
+        a, b = out.cpu().numpy().view(np.uint64).tolist()
+        return int(a), int(b)
+
+    def _global_skip_limit(self, first_dup_local):
+        runs = getattr(self, "line_runs", None)
+        if runs is None:
+            raise ValueError("a multi-GPU run with more than 2 spline passes needs Engine.set_line_runs(): from pass 3 on the "
+                             "reference stops skipping outliers at a position in file order")
+        starts, lens = runs
+        ends = np.cumsum(lens)
+        big = (1 << 63) - 1
+        g = big
+        if first_dup_local != _U64_MAX:
+            j = int(np.searchsorted(ends, first_dup_local, side="right"))
+            g = int(starts[j] + (first_dup_local - (ends[j] - lens[j])))
+        g = self.dist.min_int(g)
+        if g == big:
+            return self.n
+        return int(np.clip(g - starts + 1, 0, lens).sum()) - 1  # local lines whose global number is <= g form a prefix
 
     def _pass_scalars(self, passNo, scal):
         if int(scal[_capi.S_OFFGRID]) != 0:
@@ -407,7 +507,9 @@ class Engine:
         io = hs.io
         stream = self._stream()
         k1buf = self._ws["k1buf"]
-        nk = D + _capi.N_SCALARS
+        slots = self.dist.world if self.dist is not None else 0
+        io.n_rank_slots = slots
+        nk = D + _capi.N_SCALARS + slots
         check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
         lib.fhc_host_pool_prewarm(hs.nthreads)
         hs.new_outputs()
@@ -421,8 +523,12 @@ class Engine:
                 io.lbeta_cap[w] = 0
         check(lib.fhc_stream_synchronize(stream))
         scal = hs.k1_np[D:nk]
+        if slots:
+            scal[_capi.S_MAX_COUNT] = scal[_capi.N_SCALARS:].max()
         if int(scal[_capi.S_NONPOS_LINES]) != 0:  # distances seen only through lines with a count <= 0 (:434-436): rare
             nw = (D + 31) // 32
+            if self.dist is not None:  # (every rank sees the same summed total, so every rank comes here)
+                self.dist.or_present(k1buf[nk:].view(torch.int32)[:nw])
             check(lib.fhc_copy_async(hs.k1.data_ptr() + 8 * nk, k1buf.data_ptr() + 8 * nk, 4 * nw, stream))
             check(lib.fhc_stream_synchronize(stream))
         out = self._pass_scalars(passNo, scal)
@@ -457,17 +563,20 @@ class Engine:
             raise ValueError("no observed distance falls inside the fitted range")
         if io.status == 4:
             raise ValueError("the spline fit needs more than 3 bins (got %d)" % int(io.nb))
-        bins = dict(n=int(io.nb), lb=v["lb"], ub=v["ub"], sumcc=v["sumcc"], pairs=v["pairs"], pairs7=v["pairs"],
-                    sumdist=v["sumdist"])
+        pairs = v["pairs"].copy()
+        bins = dict(n=int(io.nb), lb=v["lb"].copy(), ub=v["ub"].copy(), sumcc=v["sumcc"].copy(), pairs=pairs, pairs7=pairs,
+                    sumdist=v["sumdist"].copy())
         x_bins, y_bins = v["x_bins"].tolist(), v["y_bins"].tolist()
         tot = io.totals
-        out.update(dists=v["dists"], sums=v["sums"], bins=bins, x=x_bins, y=y_bins, x_bins=x_bins, y_bins=y_bins,
+        out.update(bins=bins, x=x_bins, y=y_bins, x_bins=x_bins, y_bins=y_bins,
                    possibleIntraInRangeCount=int(tot[0]), possibleIntraAllCount=tot[1] / 2, possibleInterAllCount=tot[2] / 2,
                    noOfFrags=int(tot[3]))
+        out._late = dict(dists=v["dists"], sums=v["sums"])  # copied out after K3 / K4 are launched (run_pass)
         lut = None
         if not st.interOnly:
-            out.update(x=v["xs"].tolist(), y=v["ys"].tolist(), tck=(v["t"], v["c"], 3), splineX=v["splineX"], table=v["table"],
+            out.update(x=v["xs"].tolist(), y=v["ys"].tolist(), tck=(v["t"].copy(), v["c"].copy(), 3),
                        spline_ier=int(io.ier), spline_calls=int(io.calls))
+            out._late.update(splineX=v["splineX"], table=v["table"])
             out._device = self.device
             lut = self._tensor("lut", D, torch.float64)
             check(lib.fhc_copy_async(lut.data_ptr(), hs.lut.data_ptr(), 8 * D, stream))
@@ -490,10 +599,17 @@ class Engine:
         """The same through the stage-by-stage entry points (restriction-fragment mode and very long distance axes):
         bins and possible pairs in C, the fit in C, evaluation and lookup table on the device."""
         st, lib, res, D = self.st, self.lib, self.grid, self.D
-        hbuf = self._ws["k1buf"][:D + _capi.N_SCALARS + ((D + 31) // 32 + 1) // 2].cpu().numpy()
+        slots = self.dist.world if self.dist is not None else 0
+        ns = _capi.N_SCALARS + slots
+        nw = (D + 31) // 32
+        if self.dist is not None:  # rare and cheap enough here: always OR the "distance seen" bitmaps
+            self.dist.or_present(self._ws["k1buf"][D + ns:].view(torch.int32)[:nw])
+        hbuf = self._ws["k1buf"][:D + ns + (nw + 1) // 2].cpu().numpy()
         hist = hbuf[:D]
-        scal = hbuf[D:D + _capi.N_SCALARS]
-        present = hbuf[D + _capi.N_SCALARS:].view(np.uint32)[:(D + 31) // 32]
+        scal = hbuf[D:D + ns]
+        if slots:
+            scal[_capi.S_MAX_COUNT] = scal[_capi.N_SCALARS:].max()
+        present = hbuf[D + ns:].view(np.uint32)[:nw]
         out = self._pass_scalars(passNo, scal)
         N = out["N"]
         t1 = time.perf_counter()
@@ -528,7 +644,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     # K2
-    MAX_CHR_RUNS = 256  # more chromosome runs than this: the dense chrs array is uploaded instead
+    MAX_CHR_RUNS = _capi.MAX_CHR_RUNS  # more chromosome runs than this: the dense chrs array is uploaded instead
 
     HOST_PAVA_MIN_POINTS = 4096  # above this the pooling runs on the host (see csrc/spline.cu)
 
@@ -583,6 +699,12 @@ class Engine:
         each launch, so that a caller can start moving finished slices to the host while the next one is computed."""
         st = self.st
         mid1, mid2, cnt, chrs = self.contacts
+        rs, rv, nruns = self.chr_runs_dev if self.chr_runs_dev is not None else (None, None, 0)
+        if nruns and os.environ.get("FHC_PVAL_IMPL", "lists")[:1] != "t":
+            chrs = None  # the work-list pipeline reads the runs; a tile inside one intra run needs no chromosome ids at all
+        else:
+            chrs = self.chrs_array()  # the tile-phased kernel reads the per-line array
+            rs, rv, nruns = None, None, 0
         n = self.n
         p = self._tensor("p", n, torch.float64)
         e = self._tensor("expcc", n, torch.float64)
@@ -607,7 +729,8 @@ class Engine:
         while True:
             hi = min(lo + step, n)
             o = None if outl is None else outl[lo:hi]
-            check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]), dptr(chrs[lo:hi]),
+            check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]),
+                                       None if chrs is None else dptr(chrs[lo:hi]), dptr(rs), dptr(rv), nruns,
                                        hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr,
                                        getattr(self, "_bias_sparse", 0), self.grid, st.L, st.U,
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),

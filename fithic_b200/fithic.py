@@ -4,13 +4,20 @@
     fithic -i CONTACTS.gz -f FRAGS.gz -o OUTDIR -r RES [-t BIAS.gz] [-p N] [-b N] [-m N] [-l LIB] [-U bp] [-L bp]
            [-x intraOnly|interOnly|All] [-tL f] [-tU f] [-V]
 
-Differences that are deliberate: `-r 0` (restriction-fragment mode) and `-v` (plots) are outside the accelerated path
-and are refused / ignored with a message; everything numeric is computed on the GPU (no CPU fallback).
+`-r 0` (restriction-fragment mode) is supported; `-v` (plots) is outside the accelerated path and ignored with a message;
+everything numeric is computed on the GPU (no CPU fallback).
+
+Several GPUs of one box:  torchrun --nproc-per-node N -m fithic_b200 <the same flags>
+Every rank scores a contiguous slice of the contact file (cut at chromosome boundaries where one is near: "contacts shard
+by chromosome"), the distance histogram and the BH ranks are global (fithic_b200/parallel.py), every rank writes the gzip
+members of its own rows and rank 0 joins them in file order -- the output file has the same rows as a single-GPU run.
 """
 import argparse
 import os
 import sys
 import time
+
+import numpy as np
 
 from . import __version__
 from . import io as fio
@@ -60,7 +67,12 @@ def parse_args(args):
 
 
 def _is_gz(path):
-    return path.endswith(".gz")
+    """The reference probes the content (gzip.open(path).readline(), fithic/fithic.py:139-141), not the name."""
+    try:
+        with open(path, "rb") as f:
+            return f.read(2) == b"\x1f\x8b"
+    except OSError:
+        return False
 
 
 def settings_from_args(args):
@@ -144,15 +156,47 @@ def settings_from_args(args):
     return st, libName
 
 
+def shard_lines(chr_runs, n, world, snap=0.05):
+    """Cut n file lines into `world` contiguous slices of about n / world lines; a cut moves to a chromosome boundary when
+    one lies within snap * n / world lines of the even position.  Returns world + 1 cut positions."""
+    bounds = np.cumsum(np.asarray(chr_runs[1], dtype=np.int64)) if chr_runs is not None and len(chr_runs[1]) else np.zeros(0)
+    cuts = [0]
+    for r in range(1, world):
+        ideal = (n * r) // world
+        if len(bounds):
+            j = int(np.argmin(np.abs(bounds - ideal)))
+            if abs(int(bounds[j]) - ideal) <= snap * n / world:
+                ideal = int(bounds[j])
+        cuts.append(max(cuts[-1], min(ideal, n)))
+    cuts.append(n)
+    return cuts
+
+
 def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=False):
-    """Everything main() does after argument parsing.  Returns the per-pass result dicts (host numpy p/q/expcc)."""
+    """Everything main() does after argument parsing.  Returns the per-pass result dicts (host numpy p/q/expcc of this
+    rank's lines; under torchrun every rank runs this and rank 0 writes the tables and joins the output)."""
     import torch
-    say = (lambda *a: None) if quiet else print
+    from .engine import Contacts, chr_runs_of
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dctx = None
+    if world > 1:
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from .parallel import DistCtx
+        dctx = DistCtx(torch.device("cuda", local))
+    say = (lambda *a: None) if (quiet or rank != 0) else print
+    t_run = time.time()
     t0 = time.time()
     say("Reading the contact counts file to generate bins...")
     contacts = fio.read_contacts(contacts_path)
     chroms = list(contacts.chroms)
     say("Interactions file read. Time took %s" % (time.time() - t0))
+    t_read = time.time() - t0
     t1 = time.time()
     frags = fio.read_fragments(frags_path, chroms, st.mappThres, keep_mids=(st.resolution == 0))
     say("Fragments file read. Time took %s" % (time.time() - t1))
@@ -163,11 +207,21 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
         say("Bias file read. Time took %s" % (time.time() - t1))
     contacts.chroms = chroms
     logfile = os.path.join(outdir, libName + ".fithic.log")
+    n_file = len(contacts)
+    lo, hi = 0, n_file
+    if world > 1:  # this rank's slice of the file (every rank parsed the whole file: parsing is not the sharded part)
+        cuts = shard_lines(contacts.chr_runs, n_file, world)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        sl = slice(lo, hi)
+        contacts = Contacts(contacts.mid1[sl], contacts.mid2[sl], contacts.cnt[sl], contacts.chrs[sl], chroms,
+                            chr_runs_of(contacts.chrs[sl]))
 
-    eng = Engine(st, frags, biases)
+    eng = Engine(st, frags, biases, dist_ctx=dctx)
     eng.upload_contacts(contacts)
+    eng.set_line_runs([lo], [hi - lo])
     outl, stats = eng.new_outlier_state()
     results = []
+    metrics = {"world_size": world, "lines": n_file, "read_contacts_s": t_read, "passes": []}
     for passNo in range(1, st.noOfPasses + 1):
         if passNo > 1 and st.interOnly:
             say("Extra spline fits will not help with interOnly spline fit... Bypassing option")
@@ -176,44 +230,80 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
         say("Spline fit Pass %s starting..." % passNo)
         r = eng.run_pass(passNo, outl, stats)
         torch.cuda.synchronize()
+        t_gpu = time.time() - ts
         p = r["p"].cpu().numpy()
         q = r["q"].cpu().numpy()
         e = r["expcc"].cpu().numpy()
-        r.update(p=p, q=q, expcc=e, n_outliers_total=int(stats[0].item()))
+        n_out = int(stats[0].item())
+        if dctx is not None:
+            n_out = int(dctx.allreduce_small(np.array([n_out]))[0])
+        r.update(p=p, q=q, expcc=e, n_outliers_total=n_out)
         say("Outlier threshold is... %s" % r["outlierThres"])
         suffix = ".res" + str(st.resolution) if st.resolution else ""  # -r 0 omits the part (:851, :1171)
-        # log (re-opened 'w' in every pass like the reference, fithic/fithic.py:444)
-        with open(logfile, "w") as log:
-            log.write("\n\nInteractions file read successfully\n")
-            log.write("------------------------------------------------------------------------------------\n")
-            log.write("Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" %
-                      (r["observedIntraInRangeLines"], r["N"]))
-            log.write("Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" %
-                      (r["observedIntraAllLines"], r["observedIntraAllSum"]))
-            log.write("Observed, Inter-chr all: pairs= %d\t totalCount= %d\n" %
-                      (r["observedInterAllCount"], r["observedInterAllSum"]))
-            log.write("\nPossible, Intra-chr in range: pairs= %d\n" % r["possibleIntraInRangeCount"])
-            log.write("Possible, Inter-chr all: pairs= %s\n" % r["possibleInterAllCount"])
-            for line in bias_log:
-                log.write(line + "\n")
-            log.write("Spline successfully fit\n\n\n")
-        # bin table
         tab = os.path.join(outdir, libName + ".fithic_pass" + str(passNo) + suffix + ".txt")
-        say("Writing %s" % tab)
-        with open(tab, "w") as out:
-            out.write("avgGenomicDist\tcontactProbability\tstandardError\tnoOfLocusPairs\ttotalOfContactCounts\n")
-            b = r["bins"]
-            for i in range(b["n"]):
-                out.write("%d\t%.2e\t%.2e\t%d\t%d\n" % (r["x_bins"][i], r["y_bins"][i], 0, b["pairs"][i], b["sumcc"][i]))
+        if rank == 0:
+            # log (re-opened 'w' in every pass like the reference, fithic/fithic.py:444); the reference also lists every
+            # bin and chromosome here, this log keeps the totals
+            with open(logfile, "w") as log:
+                log.write("\n\nInteractions file read successfully\n")
+                log.write("------------------------------------------------------------------------------------\n")
+                log.write("Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" %
+                          (r["observedIntraInRangeLines"], r["N"]))
+                log.write("Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" %
+                          (r["observedIntraAllLines"], r["observedIntraAllSum"]))
+                log.write("Observed, Inter-chr all: pairs= %d\t totalCount= %d\n" %
+                          (r["observedInterAllCount"], r["observedInterAllSum"]))
+                log.write("\nPossible, Intra-chr in range: pairs= %d\n" % r["possibleIntraInRangeCount"])
+                log.write("Possible, Inter-chr all: pairs= %s\n" % r["possibleInterAllCount"])
+                for line in bias_log:
+                    log.write(line + "\n")
+                log.write("Spline successfully fit\n\n\n")
+            # bin table
+            say("Writing %s" % tab)
+            with open(tab, "w") as out:
+                out.write("avgGenomicDist\tcontactProbability\tstandardError\tnoOfLocusPairs\ttotalOfContactCounts\n")
+                b = r["bins"]
+                for i in range(b["n"]):
+                    out.write("%d\t%.2e\t%.2e\t%d\t%d\n" % (r["x_bins"][i], r["y_bins"][i], 0, b["pairs"][i], b["sumcc"][i]))
         sig = os.path.join(outdir, libName + ".spline_pass" + str(passNo) + suffix + ".significances.txt.gz")
         say("Writing p-values and q-values to file %s" % sig[:-3])
         # gzip level 2 by default: deflate, not formatting, bounds the writer (0.5 M rows/s/thread at level 2, 0.12 M at
         # level 6; the reference's level 9 manages 0.04 M rows/s); FITHIC_GZIP_LEVEL overrides
-        fio.write_significances_native(sig, contacts, p, q, e, biases, st,
-                                       level=int(os.environ.get("FITHIC_GZIP_LEVEL", "2")))
+        tw = time.time()
+        level = int(os.environ.get("FITHIC_GZIP_LEVEL", "2"))
+        if world == 1:
+            rows = fio.write_significances_native(sig, contacts, p, q, e, biases, st, level=level)
+        else:
+            import torch.distributed as dist
+            part = "%s.part%04d" % (sig, rank)
+            rows = fio.write_significances_native(part, contacts, p, q, e, biases, st, level=level, header=(rank == 0))
+            rows = int(dctx.allreduce_small(np.array([rows]))[0])
+            dist.barrier()
+            if rank == 0:  # concatenated gzip members are one gzip file; the slices are in file order
+                with open(sig, "wb") as out:
+                    for k in range(world):
+                        pk = "%s.part%04d" % (sig, k)
+                        with open(pk, "rb") as f:
+                            while True:
+                                blk = f.read(1 << 24)
+                                if not blk:
+                                    break
+                                out.write(blk)
+                        os.remove(pk)
+            dist.barrier()
+        t_write = time.time() - tw
         say("Number of outliers is... %s" % r["n_outliers_total"])
         say("Spline fit Pass %s completed. Time took %s" % (passNo, time.time() - ts))
+        metrics["passes"].append({"pass": passNo, "N": int(r["N"]), "T": r["T"], "bins": int(r["bins"]["n"]),
+                                  "outlier_threshold": r["outlierThres"], "outliers_total": int(n_out), "rows_written": int(rows),
+                                  "gpu_pass_s": t_gpu, "write_s": t_write,
+                                  "host_ms": {k: v * 1e3 for k, v in eng.timings.get(passNo, {}).items()}})
         results.append(r)
+    metrics["wall_s"] = time.time() - t_run
+    if rank == 0:  # machine-readable run summary next to the log (the reference only has the text log)
+        import json
+        with open(os.path.join(outdir, libName + ".fithic_metrics.json"), "w") as f:
+            json.dump(metrics, f, indent=1, default=float)
     say("=========================")
     say("Fit-Hi-C completed successfully")
     say("\n")
@@ -222,8 +312,18 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
 
 def main(argv=None):
     args = parse_args(sys.argv[1:] if argv is None else argv)
-    st, libName = settings_from_args(args)
+    if int(os.environ.get("RANK", "0")) != 0:  # under torchrun only rank 0 talks
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            st, libName = settings_from_args(args)
+    else:
+        st, libName = settings_from_args(args)
     run(args.intersfile, args.fragsfile, args.outdir, st, libName, args.biasfile)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

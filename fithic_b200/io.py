@@ -168,7 +168,7 @@ def lookup_biases(biases, chr_ids, mids, resolution):
     return np.full(len(mids), -1.0)
 
 
-def write_significances_native(path, contacts, p, q, expcc, biases, settings, nthreads=None, level=6):
+def write_significances_native(path, contacts, p, q, expcc, biases, settings, nthreads=None, level=6, header=True):
     """`.significances.txt.gz` (fithic/fithic.py:1166-1212) through the native multi-threaded formatter + gzip
     (csrc/textio.cu).  Returns the number of rows written."""
     import ctypes
@@ -193,7 +193,7 @@ def write_significances_native(path, contacts, p, q, expcc, biases, settings, nt
     rows = lib.fhc_io_write_significances(os.fsencode(path), names, len(contacts.chroms), _capi.dptr(m1), _capi.dptr(m2),
                                           _capi.dptr(cnt), _capi.dptr(chrs), _capi.dptr(p), _capi.dptr(q), _capi.dptr(e),
                                           n, mode, int(st.distLowThres), U, _capi.dptr(bv), _capi.dptr(bm), _capi.dptr(bo),
-                                          nb, int(st.resolution), int(nthreads), int(level))
+                                          nb, int(st.resolution), int(nthreads), int(level), 1 if header else 0)
     return _capi.check(rows)
 
 

@@ -1,10 +1,14 @@
 """Multi-GPU execution: one process per GPU, contacts sharded by chromosome, torch.distributed (NCCL over NVLink /
 NVSwitch) for the two exchange steps of a spline pass.
 
-  exchange 1  all-reduce (sum) of the distance histogram + observed totals (<= 400 kB, latency bound).  Every rank then
-              runs the identical host binning / spline fit on identical inputs, so tables are bit-identical everywhere.
-  exchange 2  global BH: an all-reduce of a 32768-bucket value histogram fixes the cut above which every q is 1.0;
-              the p-values below it are range-partitioned by value so that rank r ranks one contiguous key range:
+  exchange 1  ONE all-reduce (sum) of [distance histogram | observed totals | one slot per rank for the largest count]
+              (<= 400 kB, latency bound).  Every rank then runs the identical host binning / spline fit on identical
+              inputs, so tables are bit-identical everywhere.
+  exchange 2  global BH: ONE all-gather of every rank's 32768-bucket value histogram; a kernel sums them, finds the cut
+              above which every q is 1.0 and each rank's number of p-values below it, and ONE small read-back tells the
+              host how to go on: nothing below the cut (sparse maps without signal) -> done; few -> all-gather of the
+              survivors, every rank ranks the small global set itself; many -> the p-values below the cut are
+              range-partitioned by value so that rank r ranks one contiguous key range:
               sample keys -> all-gather -> splitters; count per part -> all-gather -> offsets; scatter into send
               buffers (kernel) -> all-to-all(v) of p -> local compaction/sort/tile maxima (kernels) -> all-gather of the
               per-range maxima (carry) -> scan + scatter (kernels) -> all-to-all(v) of q back -> scatter to line order.
@@ -14,6 +18,7 @@ implemented by the CUDA library in production (CudaOps) -- world_size-2 gloo tes
 numpy stand-in to check the bookkeeping (offsets, splits, carries) without a GPU.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -77,6 +82,13 @@ class CudaOps:
         check(self.lib.fhc_bh_cut_hist(dptr(p), p.numel(), float(p_cut0), dptr(hist), self._stream()))
         return hist
 
+    def cut_from_hists(self, hists, nranks, my_rank, T, p_cut0):
+        """Every rank's histogram (nranks x BH_CUT_BUCKETS, device) -> info block on the device (see bh.cu)."""
+        info = self.empty(8 + nranks, torch.int64)
+        check(self.lib.fhc_bh_cut_from_hists(dptr(hists), int(nranks), int(my_rank), float(T), float(p_cut0), dptr(info),
+                                             self._stream()))
+        return info
+
     def cut_find(self, hist_host, T, p_cut0):
         h = np.ascontiguousarray(hist_host, dtype=np.uint64)
         return float(self.lib.fhc_host_bh_cut_find(dptr(h), float(T), 0.0, float(p_cut0)))
@@ -103,12 +115,13 @@ class CudaOps:
                                               self._stream()))
         return counts
 
-    def partition_scatter(self, p, splitters, send_offsets, q, p_cut):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None):
         nparts = len(splitters) + 1
         n = p.numel()
         cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
-        send = self.empty(n, torch.float64)
-        idx = self.empty(n, torch.int32)
+        cap = n if capacity is None else int(capacity)  # the caller knows how many p-values lie below the cut
+        send = self.empty(cap, torch.float64)
+        idx = self.empty(cap, torch.int32)
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
         check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, float(p_cut), dptr(cursors), dptr(send),
                                                 dptr(idx), dptr(q), self._stream()))
@@ -161,33 +174,34 @@ class DistCtx:
         self.device = device
         self.ops = ops if ops is not None else CudaOps(device)
         self.samples_per_rank = samples_per_rank
+        self._n_global = None
+        env = os.environ.get("FHC_BH_SMALL_SET")  # e.g. 0: always take the range-partitioned route (tests, timing)
+        if env is not None:
+            self.SMALL_SET = int(env)
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
-    def allreduce_hist(self, hist, present, scal, fused=None):
-        """Sum the per-distance histogram and the totals over ranks, OR the 'distance seen' bitmaps, take the largest
-        count (all in place).  One all-reduce(sum) and one all-gather of the small bitmap; `fused` is the caller's single
-        buffer holding [hist | totals] back to back (engine.hist_distance), which saves a concatenation."""
-        D = hist.numel()
-        if fused is None:
-            fused = torch.cat([hist, scal])
-            own = False
-        else:
-            own = True
-        small = torch.cat([present, scal[_capi.S_MAX_COUNT:_capi.S_MAX_COUNT + 1].to(torch.int32)])
+    def allreduce_k1(self, fused):
+        """Sum K1's [hist | totals | rank slots] over the ranks, in place: one collective, no host synchronisation (the
+        largest count travels in the rank slots, see fhc_hist_distance)."""
         dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
-        g = self._all_gather(small).view(self.world, -1)
-        if not own:
-            hist.copy_(fused[:D])
-            scal.copy_(fused[D:D + scal.numel()])
-        ored = g[0, :-1]
+
+    def or_present(self, present):
+        """OR the 'distance seen with counts <= 0' bitmaps of all ranks, in place.  Only needed when the summed totals
+        say that such lines exist at all (scalars[S_NONPOS_LINES] != 0): rare."""
+        g = self._all_gather(present).view(self.world, -1)
+        ored = g[0]
         for w in range(1, self.world):
-            ored = torch.bitwise_or(ored, g[w, :-1])
+            ored = torch.bitwise_or(ored, g[w])
         present.copy_(ored)
-        scal[_capi.S_MAX_COUNT] = g[:, -1].max().to(scal.dtype)
 
     def max_int(self, v):
         t = torch.tensor([int(v)], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def min_int(self, v):
+        t = torch.tensor([int(v)], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return int(t.item())
 
     def allreduce_small(self, arr):
@@ -202,31 +216,37 @@ class DistCtx:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
+    def n_global(self, n):
+        """Lines of the whole file (sum over ranks); the shard sizes do not change between passes, so one collective per
+        shard size."""
+        if self._n_global is None or self._n_global[0] != n:
+            t = torch.tensor([n], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self._n_global = (n, int(t.item()))
+        return self._n_global[1]
+
     def global_bh(self, engine, p, T, q=None):
         """q-values of the union of every rank's p-values (myStats.benjamini_hochberg_correction over the whole file)."""
         ops, G, r = self.ops, self.world, self.rank
         n = p.numel()
         if q is None:
             q = engine._tensor("q", n, torch.float64) if engine is not None else ops.empty(n, torch.float64)
-        # 0. p-values that are certain to end with q = 1.0 are neither exchanged nor ranked (bh.cu: bh_p_cut)
-        n_global = int(self._all_gather(torch.tensor([n], dtype=torch.int64, device=p.device)).sum().item())
-        p_cut0 = ops.p_cut(T, n_global)
-        #    ... and the summed value histogram of what is left says where q reaches 1.0 for good (bh.cu: cut_bucket_closes);
-        #    on sparse maps this leaves only the few candidates for significance to exchange and sort
+        # 0. p-values that are certain to end with q = 1.0 are neither exchanged nor ranked (bh.cu: bh_p_cut) ...
+        p_cut0 = ops.p_cut(T, self.n_global(n))
+        #    ... and the value histograms of what is left say where q reaches 1.0 for good (bh.cu: cut_bucket_closes): one
+        #    all-gather of the histograms, one kernel, one read-back of a few numbers
         hist = ops.cut_hist(p, p_cut0)
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-        hh = hist.cpu().numpy()
-        p_cut = ops.cut_find(hh, T, p_cut0)
+        info = ops.cut_from_hists(self._all_gather(hist), G, r, T, p_cut0).cpu().numpy()
+        p_cut = float(info[:1].view(np.float64)[0])
+        n_below, mine, mx = int(info[1]), int(info[2]), int(info[3])
+        counts = info[8:8 + G].astype(np.int64)
         # 0b. few survivors (the usual case on a sparse map): no range partition -- every rank compacts its survivors,
         #     the survivors are all-gathered (padded to the largest share), every rank ranks the small global set itself
-        #     and keeps the q-values of its own lines.  Three collectives in all.
-        n_below = int(hh[:ops.cut_bucket(p_cut)].sum()) if p_cut < p_cut0 else int(hh.sum())
+        #     and keeps the q-values of its own lines.  Nothing below the cut: one kernel writes q = 1 / NaN and that is it.
         if n_below <= self.SMALL_SET:
-            send, idx = ops.partition_scatter(p, np.zeros(0, dtype=np.uint64), np.zeros(1, dtype=np.int64), q, p_cut)
-            counts = self._all_gather(ops.last_cursors[:1].to(torch.int64)).cpu().numpy()
-            mine = int(counts[r])
-            tot, mx = int(counts.sum()), int(counts.max())
-            if tot:
+            send, idx = ops.partition_scatter(p, np.zeros(0, dtype=np.uint64), np.zeros(1, dtype=np.int64), q, p_cut,
+                                              capacity=mine)
+            if n_below:
                 pad = ops.empty(mx, torch.float64)
                 pad[:mine] = send[:mine]
                 if mine < mx:
@@ -238,7 +258,7 @@ class DistCtx:
                 if mine:
                     ops.scatter(qg[off:off + mine].contiguous(), idx[:mine], q)
             self.last_plan = dict(splitters=np.zeros(0, dtype=np.uint64), count_matrix=counts.reshape(G, 1), rank_offset=0,
-                                  floor=0.0, p_cut=p_cut, p_cut0=p_cut0, small_set=True)
+                                  floor=0.0, p_cut=p_cut, p_cut0=p_cut0, small_set=True, n_below=n_below)
             return q
         # 1. splitters from a sorted sample of everybody's keys
         sample = ops.sample_keys(p, self.samples_per_rank, p_cut)
@@ -249,7 +269,7 @@ class DistCtx:
         cm = self._all_gather(counts).cpu().numpy().reshape(G, G)
         send_splits, recv_splits, rank_offset, send_off = exchange_plan(cm, r)
         # 3. group by destination, exchange
-        send, idx = ops.partition_scatter(p, splitters, send_off, q, p_cut)
+        send, idx = ops.partition_scatter(p, splitters, send_off, q, p_cut, capacity=mine)
         n_send, n_recv = int(sum(send_splits)), int(sum(recv_splits))
         recv = ops.empty(n_recv, torch.float64)
         dist.all_to_all_single(recv, send[:n_send], recv_splits, send_splits, group=self.group)
@@ -263,5 +283,5 @@ class DistCtx:
         dist.all_to_all_single(q_back, q_recv, send_splits, recv_splits, group=self.group)
         ops.scatter(q_back, idx[:n_send], q)
         self.last_plan = dict(splitters=splitters, count_matrix=cm, rank_offset=rank_offset, floor=floor, p_cut=p_cut,
-                              p_cut0=p_cut0, small_set=False)
+                              p_cut0=p_cut0, small_set=False, n_below=n_below)
         return q

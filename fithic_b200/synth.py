@@ -116,15 +116,19 @@ def lpt_shards(weights, nshards):
     return [sorted(o) for o in out]
 
 
-def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, only=None, chunk=1 << 26, order="file"):
+def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True, only=None, chunk=1 << 26, order="file",
+                      chroms=None, signal_frac=0.0):
     """torch generator on the GPU for bench-sized inputs (300 M pairs in seconds).  Same law as make_intra; every
     chromosome has its own seeded stream, so a rank that generates only the chromosomes in `only` (indices) gets exactly
     the lines the single-GPU run has for them.  order = "file": the lines of a chromosome are sorted by (mid1, mid2), the
     order fixed-size-bin contact files come in (e.g. the reference's fithic/tests/data/contactCounts/*_w40000_chr1.gz:
     all partners of one locus on consecutive lines); "random": the order the pairs were drawn in.  Returns ((mid1, mid2,
-    cnt, chrs) int32 device tensors, Fragments, Biases, per-chromosome pair counts of the WHOLE data set)."""
+    cnt, chrs) int32 device tensors, Fragments, Biases, per-chromosome pair counts of the WHOLE data set).
+    chroms: restrict the genome (e.g. ["chr1"]).  signal_frac: this share of the lines (drawn per line, independent of its
+    distance) gets 4 + Poisson(6) extra reads -- planted interactions, so that a comparable share of the lines ends with
+    q < 1 like on real maps (the reference's bundled data: 3 ... 48 % of the lines), instead of none under the null model."""
     import torch
-    names, sizes = genome(None)
+    names, sizes = genome(chroms)
     nb = n_bins(sizes, res)
     frags = fragments_for(names, sizes, res)
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -166,6 +170,10 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
                 bj = bvals[off + j]
                 lam = lam * torch.where(bi > 0, bi, torch.ones_like(bi)) * torch.where(bj > 0, bj, torch.ones_like(bj))
             c = 1 + torch.poisson(lam, generator=g).long()
+            if signal_frac > 0.0:
+                hit = torch.rand(m, generator=g, device=device) < signal_frac
+                extra = 4 + torch.poisson(torch.full((m,), 6.0, device=device), generator=g).long()
+                c = torch.where(hit, c + extra, c)
             s = slice(pos, pos + m)
             mid1[s] = (i * res + res // 2).int()
             mid2[s] = (j * res + res // 2).int()
@@ -183,26 +191,33 @@ def make_intra_device(n_pairs, res, seed, device, mean_count=3.0, with_bias=True
     return (mid1, mid2, cnt, chrs), frags, biases, per
 
 
-def make_inter_device(n_pairs, res, seed, device, intra_fraction=0.1, chunk=1 << 26):
+def make_inter_device(n_pairs, res, seed, device, intra_fraction=0.1, chunk=1 << 24, only_chunks=None):
     """BASELINE config 5 on the GPU: whole-genome interOnly input -- chromosome pairs drawn with probability proportional to
     the product of their lengths, loci uniform, count = 1 + Poisson(0.3), no bias; `intra_fraction` of the lines are intra
     pairs (under -x interOnly the reference scores those against the inter prior as well, fithic/fithic.py:1098-1108).
-    Returns ((mid1, mid2, cnt, chrs) int32 device tensors, Fragments)."""
+    The file is a sequence of chunks of `chunk` lines, each with its own seeded stream: a rank that generates only the
+    chunks in `only_chunks` (a range) gets exactly the lines the single-GPU run has there.
+    Returns ((mid1, mid2, cnt, chrs) int32 device tensors, Fragments, first file line of this rank's lines)."""
     import torch
     names, sizes = genome(None)
     nb = n_bins(sizes, res)
     frags = fragments_for(names, sizes, res)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
     w = torch.from_numpy(sizes / sizes.sum()).to(device)
     nbt = torch.from_numpy(nb).to(device)
-    mid1 = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    mid2 = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    cnt = torch.empty(n_pairs, dtype=torch.int32, device=device)
-    chrs = torch.empty(n_pairs, dtype=torch.int32, device=device)
+    nchunks = (n_pairs + chunk - 1) // chunk
+    which = range(nchunks) if only_chunks is None else only_chunks
+    lo = min(which.start * chunk, n_pairs) if len(which) else 0
+    hi = min(which.stop * chunk, n_pairs) if len(which) else 0
+    n_local = hi - lo
+    mid1 = torch.empty(n_local, dtype=torch.int32, device=device)
+    mid2 = torch.empty(n_local, dtype=torch.int32, device=device)
+    cnt = torch.empty(n_local, dtype=torch.int32, device=device)
+    chrs = torch.empty(n_local, dtype=torch.int32, device=device)
     done = 0
-    while done < n_pairs:
-        m = min(chunk, n_pairs - done)
+    for ck in which:
+        m = min(chunk, n_pairs - ck * chunk)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 100003 + ck)
         c1 = torch.multinomial(w, m, replacement=True, generator=g)
         c2 = torch.multinomial(w, m, replacement=True, generator=g)
         same = torch.rand(m, generator=g, device=device) < intra_fraction
@@ -216,7 +231,7 @@ def make_inter_device(n_pairs, res, seed, device, intra_fraction=0.1, chunk=1 <<
         cnt[s] = c.int()
         chrs[s] = (c1 | (c2 << 16)).int()
         done += m
-    return (mid1, mid2, cnt, chrs), frags
+    return (mid1, mid2, cnt, chrs), frags, lo
 
 
 def write_inputs(outdir, contacts, frags, res, raw_bias=None, biases=None, prefix="synth"):

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 5
+#define FHC_ABI_VERSION 6
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -47,6 +47,7 @@ extern "C" {
 #define FHC_S_INTRA_ALL_LINES 7   /* observedIntraAllCount    fithic/fithic.py:425 */
 #define FHC_S_NONPOS_LINES 8     /* in-range intra lines with cnt <= 0: only then the `present` bitmap says more than hist */
 #define FHC_N_SCALARS 9
+#define FHC_MAX_CHR_RUNS 1024      /* chromosome ids as runs: at most this many (fhc_hist_distance, fhc_pvalues) */
 
 /* fhc_pvalues mode bits (fithic/fithic.py:232-248) */
 #define FHC_MODE_INTRA_ONLY 0
@@ -70,6 +71,12 @@ int fhc_profile_collect(char *buf, size_t buf_bytes);
 int fhc_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int fhc_stream_synchronize(void *stream);
 
+/* FP64 FMA throughput of the current device in TFLOP/s (2 flops per FMA, 16 independent chains per thread): the compute
+ * roofline bench.py reports K3 against (K3 is bound by FP64 latency and instruction issue, not by HBM).  seconds <= 0: best
+ * of five bursts of ~10 ms; otherwise back-to-back launches for about that long (sustained clocks).  scratch [dev]: one
+ * double.  Synchronises the stream. */
+int fhc_peak_fp64(double seconds, double *scratch, double *tflops_out, void *stream);
+
 /* ---- K1: distance histogram + totals ------------------------------------------------------------------------
  * Replaces the accumulation loop of read_Interactions (fithic/fithic.py:406-441) with the classification of
  * myUtils.Interaction.getType (fithic/myUtils.py:135-148).
@@ -78,10 +85,18 @@ int fhc_stream_synchronize(void *stream);
  *   skip       nullable per-line outlier multiplicity (pass >= 2, :408-412); line i is dropped when
  *              skip[i] != 0 and i <= skip_limit (the reference's pointer walk stalls at the first duplicate)
  *   L, U       distLowThres / distUpThres; -1 = unbounded
- * hist, present and scalars are zeroed by the callee.  present has (D+31)/32 words. */
+ * hist, present and scalars are zeroed by the callee.  present has (D+31)/32 words.
+ * chrs may be NULL when the chromosome ids come as runs instead (contact files are grouped by chromosome; 4 B per line
+ * less to read): run r of nruns <= FHC_MAX_CHR_RUNS covers lines [run_start[r], run_start[r+1]) (run_start[0] = 0,
+ * run_start[nruns] = n) and all of them have chrs = run_val[r]  [dev].
+ * n_rank_slots / my_slot: every total is a sum and survives a sum over GPUs, the largest count does not.  With
+ * n_rank_slots > 0, scalars has FHC_N_SCALARS + n_rank_slots entries and the largest count goes to
+ * scalars[FHC_N_SCALARS + my_slot] (scalars[FHC_S_MAX_COUNT] stays 0): after ONE all-reduce(sum) of [hist | scalars]
+ * every rank holds every rank's maximum.  n_rank_slots = 0: scalars[FHC_S_MAX_COUNT] as before. */
 int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
-                      const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
-                      uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, void *stream);
+                      const int64_t *run_start, const uint32_t *run_val, int32_t nruns, const uint8_t *skip, int64_t skip_limit, int64_t n, int64_t L, int64_t U, int32_t res,
+                      uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, int32_t n_rank_slots,
+                      int32_t my_slot, void *stream);
 
 /* ---- host helpers for the O(D) sequential stages (bit-exact integer/float bookkeeping) ------------------------
  * makeBinsFromInteractions, fithic/fithic.py:463-553.  dists/sums [host]: the m distinct in-range distances
@@ -109,8 +124,9 @@ int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int
                                 int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals);
 
 /* ---- the whole host stage between K1 and K3 in one call ----------------------------------------------------------
- * k1buf [host]: fhc_hist_distance's outputs back to back as the engine keeps them, [hist (D) | scalars (FHC_N_SCALARS) |
- * present words]; the present words are only read when scalars[FHC_S_NONPOS_LINES] != 0.  phases (bit mask):
+ * k1buf [host]: fhc_hist_distance's outputs back to back as the engine keeps them, [hist (D) | scalars (FHC_N_SCALARS +
+ * n_rank_slots) | present words]; the present words are only read when scalars[FHC_S_NONPOS_LINES] != 0; with
+ * n_rank_slots > 0 the largest count is the largest of the rank slots (see fhc_hist_distance).  phases (bit mask):
  *   1  observed distances (dists, sums: capacity D) and makeBinsFromInteractions (bin_lb / bin_ub / bin_sumcc: noOfBins)
  *   2  generate_FragPairs fixed-size branch (bin_pairs, bin_sumdist, totals as fhc_host_frag_pairs; `dec` [nullable] holds
  *      the pass >= 2 outlier decrements per bin) and calculateProbabilities (x_bins, y_bins in bin order); the lbeta tables
@@ -129,7 +145,7 @@ typedef struct fhc_stage_io {
     int32_t grid, noOfBins;
     int64_t L, U;
     const int64_t *chr_n, *chr_maxmid;
-    int32_t nchr, want_spline, nthreads, pad0;
+    int32_t nchr, want_spline, nthreads, n_rank_slots;
     const int64_t *dec;
     double *lbeta_tab[2];
     int64_t lbeta_cap[2];
@@ -226,6 +242,10 @@ double fhc_host_one_minus_exp(double y);
  *              file in ascending mid order (chr_off[c] .. chr_off[c+1]) and a locus is found by binary search
  *   bias_mid   may be NULL when every slot s of chromosome c holds the locus at mid = (s - chr_off[c]) * res + res / 2
  *              (fixed-size bins on the regular grid): the mid point is then checked arithmetically, one gather less
+ *   chrs       may be NULL (with a workspace) when the chromosome ids come as runs, as in fhc_hist_distance: run r covers
+ *              lines [run_start[r], run_start[r+1]) COUNTED LIKE line_base (the first contact passed is line line_base of
+ *              the run table's numbering) and all of them have chrs = run_val[r].  4 B per line less to read, and a tile of
+ *              contacts inside one intra run is scored without any per-contact chromosome logic.
  *   workspace  [dev, nullable] fhc_pvalues_workspace_bytes(n, ntab) bytes, ntab = max(ntab_intra, ntab_inter).  With a
  *              workspace the contacts that need an iterative evaluation (continued fraction / tail sum) are compacted
  *              into work lists in HBM and the call runs as three kernels with full warps (pvalue_lists.cu); without one
@@ -233,7 +253,7 @@ double fhc_host_one_minus_exp(double y);
  *              the same p-values to ~1e-13 relative. */
 size_t fhc_pvalues_workspace_bytes(int64_t n, int64_t ntab);
 int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs,
-                int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
+                const int64_t *run_start, const uint32_t *run_val, int32_t nruns, int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
                 int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
                 double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
                 const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, int64_t line_base, double outl_thres,
@@ -298,6 +318,12 @@ double fhc_bh_p_cut(double T, double rank_bound);
 int fhc_bh_cut_hist(const double *p, int64_t n, double p_cut0, uint64_t *hist, void *stream);
 double fhc_host_bh_cut_find(const uint64_t *hist, double T, double rank_offset, double p_cut0);
 int32_t fhc_host_bh_cut_bucket(double p);
+/* Multi-GPU: hists [dev] = every rank's fhc_bh_cut_hist histogram back to back (all-gathered, nranks x
+ * FHC_BH_CUT_BUCKETS).  Writes info [dev, 8 + nranks words]: [0] the global cut (double: the rule of fhc_host_bh_cut_find
+ * on the summed histogram), [1] p-values below it on all ranks, [2] on rank my_rank, [3] the largest share of one rank,
+ * [8 + r] the share of rank r -- what a rank needs to size the exchange of its survivors, in ONE small read-back. */
+int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int32_t my_rank, double T, double p_cut0, uint64_t *info,
+                          void *stream);
 int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out, void *stream);
 uint64_t fhc_bh_key_of(double p);
 int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
@@ -327,6 +353,13 @@ int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t *keys_out,
  * over its sorted outlier distances (taken for inter lines too, :1217). */
 int fhc_outlier_bin_decrements(const int32_t *mid1, const int32_t *mid2, const uint8_t *outl, int64_t n,
                                const int64_t *bin_ub, int32_t nbins, uint64_t *dec, void *stream);
+
+/* Order-independent digest of (file line, p bits, q bits) over n lines: out[0], out[1] [dev] = two 64-bit sums of hashes,
+ * so the digests of disjoint shards add up (mod 2^64) to the digest of the whole file -- a run on N GPUs has computed the
+ * same p and q for every line as a run on one GPU iff the digests agree.  Local lines [run_local[j], run_local[j+1]) are
+ * the file lines run_global[j], run_global[j] + 1, ... (nruns <= FHC_MAX_CHR_RUNS; run_local[nruns] = n)  [dev]. */
+int fhc_digest_lines(const double *p, const double *q, int64_t n, const int64_t *run_local, const int64_t *run_global,
+                     int32_t nruns, uint64_t *out, void *stream);
 
 /* ---- KR bias computation ---------------------------------------------------------------------------
  * The kernels behind fithic_b200/hickry.py, the replacement of the reference's bias generator fithic/utils/HiCKRy.py (the
@@ -403,7 +436,9 @@ int fhc_host_merge_select(const uint64_t *keys, const uint32_t *order, const int
  *                          returns a handle (NULL on error); chromosome ids are assigned in order of first appearance
  *   fhc_io_contacts_*      size / chromosome names / copy into caller arrays; fhc_io_free releases the handle
  *   fhc_io_write_significances  formats and gzips the reported rows with `nthreads` threads (multi-member gzip, `level`
- *                          0-9); returns the number of rows written or a negative error code */
+ *                          0-9); header = 0 leaves the column header out (a rank of a multi-GPU run writes the rows of its
+ *                          lines, and the parts are concatenated in file order: concatenated gzip members are one gzip
+ *                          file); returns the number of rows written or a negative error code */
 int fhc_io_format_double(double v, int kind /* 'e' or 'f' */, char *out /* >= 400 bytes */); /* the writer's "%e" / "%f" */
 void *fhc_io_read_contacts(const char *path);
 int64_t fhc_io_contacts_n(void *handle);
@@ -415,7 +450,7 @@ int64_t fhc_io_write_significances(const char *path, const char *const *chrom_na
                                    const int32_t *mid2, const int32_t *cnt, const uint32_t *chrs, const double *p,
                                    const double *q, const double *expcc, int64_t n, int32_t mode, int64_t L, int64_t U,
                                    const double *bias, const int32_t *bias_mid, const int64_t *chr_off,
-                                   int32_t nbias_chr, int32_t res, int32_t nthreads, int32_t level);
+                                   int32_t nbias_chr, int32_t res, int32_t nthreads, int32_t level, int32_t header);
 
 #ifdef __cplusplus
 }

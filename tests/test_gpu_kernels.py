@@ -103,7 +103,8 @@ def test_lbeta_table_bit_exact(lib):
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 3, 4097, 1_000_003])
 @pytest.mark.parametrize("LU", [(0, -1), (20000, 2_000_000), (-1, 50000)])
-def test_hist_distance(lib, n, LU):
+@pytest.mark.parametrize("as_runs", [False, True], ids=["chrs", "runs"])
+def test_hist_distance(lib, n, LU, as_runs):
     rng = np.random.default_rng(n + 17)
     res = 10000
     nb = 5000
@@ -119,20 +120,40 @@ def test_hist_distance(lib, n, LU):
         cnt[rng.integers(0, n, 5)] = 100_000     # large counts take the global-atomic path
     c1 = rng.integers(0, 3, n).astype(np.uint32)
     c2 = np.where(rng.random(n) < 0.8, c1, rng.integers(0, 3, n)).astype(np.uint32)
+    run_start = run_val = None
+    nruns = 0
+    if as_runs and n:
+        # chromosome ids as runs (a contact file grouped by chromosome): a few long runs, some of length 1 ... 3 so that
+        # groups of four lines straddle boundaries, one run boundary inside the scalar tail
+        cuts = np.unique(np.concatenate([[0], rng.integers(0, n, 9), [min(n - 1, 5), min(n - 1, 6), min(n - 1, 8), n - 1]]))
+        vals = np.array([(a | (b << 16)) for a, b in zip(rng.integers(0, 3, len(cuts)), rng.integers(0, 3, len(cuts)))],
+                        dtype=np.uint32)
+        vals[::2] = (vals[::2] & 0xffff) * 0x10001  # every other run intra
+        lens = np.diff(np.concatenate([cuts, [n]]))
+        chrs_full = np.repeat(vals, lens).astype(np.uint32)
+        c1, c2 = chrs_full & 0xffff, chrs_full >> 16
+        run_start = dev(np.concatenate([cuts, [n]]).astype(np.int64))
+        run_val = dev(vals.view(np.int32))
+        nruns = len(vals)
     chrs = (c1 | (c2 << 16)).astype(np.uint32)
     skip = (rng.random(n) < 0.1).astype(np.uint8) * rng.integers(1, 3, n).astype(np.uint8)
     skip_limit = n // 2
     L, U = LU
     D = nb + 1
+    slots, my = (3, 1) if (n % 2) else (0, 0)  # multi-GPU layout: the largest count goes to this rank's slot
     hist = torch.empty(D, dtype=torch.int64, device=DEV)
     present = torch.empty((D + 31) // 32, dtype=torch.int32, device=DEV)
-    scal = torch.empty(8, dtype=torch.int64, device=DEV)
+    scal = torch.full((_capi.N_SCALARS + slots,), -1, dtype=torch.int64, device=DEV)
     pad = lambda a: dev(a) if n else torch.empty(4, dtype=torch.from_numpy(a).dtype, device=DEV)
-    bufs = [pad(m1), pad(m2), pad(cnt), pad(chrs.view(np.int32)), pad(skip)]
-    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), dptr(bufs[4]), skip_limit,
-                                n, L, U, res, dptr(hist), dptr(present), D, dptr(scal), stream()))
+    bufs = [pad(m1), pad(m2), pad(cnt), None if nruns else pad(chrs.view(np.int32)), pad(skip)]
+    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), dptr(run_start), dptr(run_val),
+                                nruns, dptr(bufs[4]), skip_limit, n, L, U, res, dptr(hist), dptr(present), D, dptr(scal),
+                                slots, my, stream()))
     torch.cuda.synchronize()
     h, pr, s = hist.cpu().numpy(), present.cpu().numpy().view(np.uint32), scal.cpu().numpy()
+    if slots:
+        assert s[_capi.S_MAX_COUNT] == 0 and s[_capi.N_SCALARS] == 0 and s[_capi.N_SCALARS + 2] == 0
+        s[_capi.S_MAX_COUNT] = s[_capi.N_SCALARS + my]
     kept = ~((skip != 0) & (np.arange(n) <= skip_limit))
     intra = (c1 == c2) & kept
     d = np.abs(m1.astype(np.int64) - m2.astype(np.int64))
@@ -153,6 +174,7 @@ def test_hist_distance(lib, n, LU):
     assert s[_capi.S_INTRA_ALL_LINES] == intra.sum()
     assert s[_capi.S_MAX_COUNT] == (cnt.max() if n else 0)
     assert s[_capi.S_OFFGRID] == 0
+    assert s[_capi.S_NONPOS_LINES] == (inr & (cnt <= 0)).sum()
 
 
 def test_hist_offgrid_is_reported(lib):
@@ -162,10 +184,10 @@ def test_hist_offgrid_is_reported(lib):
     chrs = np.zeros(4, dtype=np.int32)
     hist = torch.empty(8, dtype=torch.int64, device=DEV)
     present = torch.empty(1, dtype=torch.int32, device=DEV)
-    scal = torch.empty(8, dtype=torch.int64, device=DEV)
+    scal = torch.empty(_capi.N_SCALARS, dtype=torch.int64, device=DEV)
     bufs = [dev(m1), dev(m2), dev(cnt), dev(chrs)]
-    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), None, -1, 4, 0, -1, 10000,
-                                dptr(hist), dptr(present), 8, dptr(scal), stream()))
+    check(lib.fhc_hist_distance(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), dptr(bufs[3]), None, None, 0, None, -1, 4, 0, -1,
+                                10000, dptr(hist), dptr(present), 8, dptr(scal), 0, 0, stream()))
     torch.cuda.synchronize()
     assert scal.cpu().numpy()[_capi.S_OFFGRID] == 1
 

@@ -104,7 +104,7 @@ def test_inter_only_full_size(lib):
     properties as above."""
     dev = torch.device("cuda", 0)
     n, res = 100_000_000, 25000
-    (mid1, mid2, cnt, chrs), frags = synth.make_inter_device(n, res, 1005, dev)
+    (mid1, mid2, cnt, chrs), frags, _ = synth.make_inter_device(n, res, 1005, dev)
     st = Settings(resolution=res, noOfBins=100, interOnly=True)
     eng = Engine(st, frags, None, device=dev)
     eng.set_contacts_device(mid1, mid2, cnt, chrs)

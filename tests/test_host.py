@@ -37,7 +37,7 @@ def test_errors_are_reported_not_swallowed(lib):
     with pytest.raises(_capi.FithicB200Error):
         _capi.check(rc)
     # device entry points validate their arguments before touching the GPU
-    assert lib.fhc_pvalues(7, None, None, None, None, 1, None, None, None, 0, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
+    assert lib.fhc_pvalues(7, None, None, None, None, None, None, 0, 1, None, None, None, 0, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
                            None, 0, None, 0, None, 0, 0.0, None, None, None, None, 0, None) == _capi.FHC_E_INVALID
     assert lib.fhc_lbeta_table(1 << 31, ctypes.c_void_p(16), 4, None) == _capi.FHC_E_RANGE
 
@@ -543,3 +543,20 @@ def test_sparse_bias_layout_for_restriction_fragments(tmp_path):
     fio.write_significances(str(tmp_path / "py.gz"), contacts, p, q, e, b1, b2, st)
     fio.write_significances_native(str(tmp_path / "native.gz"), contacts, p, q, e, b, st, nthreads=2)
     assert gzip.open(tmp_path / "py.gz").read() == gzip.open(tmp_path / "native.gz").read()
+
+
+def test_cli_shards_lines_at_chromosome_boundaries_and_probes_gzip_content(tmp_path):
+    from fithic_b200 import fithic as cli
+    runs = (np.zeros(4, dtype=np.uint32), np.array([400, 350, 150, 100]))
+    assert cli.shard_lines(runs, 1000, 2) == [0, 500, 1000]          # no boundary within 5 % of the even cut
+    assert cli.shard_lines(runs, 1000, 4) == [0, 250, 500, 750, 1000]
+    runs = (np.zeros(4, dtype=np.uint32), np.array([260, 245, 240, 255]))
+    assert cli.shard_lines(runs, 1000, 4) == [0, 260, 505, 745, 1000]  # cuts snapped to the chromosome boundaries
+    assert cli.shard_lines(None, 10, 3) == [0, 3, 6, 10]
+    assert cli.shard_lines(runs, 0, 2) == [0, 0, 0]
+    # the reference opens the file with gzip and reads a line (fithic/fithic.py:139-141): content decides, not the name
+    good, bad = tmp_path / "contacts.txt", tmp_path / "contacts.gz"
+    with gzip.open(good, "wt") as f:
+        f.write("chr1\t5000\tchr1\t15000\t3\n")
+    bad.write_text("chr1\t5000\tchr1\t15000\t3\n")
+    assert cli._is_gz(str(good)) and not cli._is_gz(str(bad)) and not cli._is_gz(str(tmp_path / "missing"))

@@ -37,6 +37,19 @@ class NumpyOps:
         b = np.where(v > 0, np.minimum(v.view(np.uint64) >> np.uint64(47), np.uint64(_capi.BH_CUT_BUCKETS - 1)), 0)
         return torch.from_numpy(np.bincount(b.astype(np.int64), minlength=_capi.BH_CUT_BUCKETS).astype(np.int64))
 
+    def cut_from_hists(self, hists, nranks, my_rank, T, p_cut0):
+        lib = _capi.load()
+        h = hists.numpy().reshape(nranks, _capi.BH_CUT_BUCKETS)
+        tot = np.ascontiguousarray(h.sum(axis=0), dtype=np.uint64)
+        cut = float(lib.fhc_host_bh_cut_find(_capi.dptr(tot), float(T), 0.0, float(p_cut0)))
+        upto = int(lib.fhc_host_bh_cut_bucket(cut)) if cut < p_cut0 else _capi.BH_CUT_BUCKETS
+        share = h[:, :upto].sum(axis=1)
+        info = np.zeros(8 + nranks, dtype=np.int64)
+        info[:1].view(np.float64)[0] = cut
+        info[1], info[2], info[3] = share.sum(), share[my_rank], share.max()
+        info[8:] = share
+        return torch.from_numpy(info)
+
     def cut_find(self, hist_host, T, p_cut0):
         h = np.ascontiguousarray(hist_host, dtype=np.uint64)
         return float(_capi.load().fhc_host_bh_cut_find(_capi.dptr(h), float(T), 0.0, float(p_cut0)))
@@ -67,7 +80,7 @@ class NumpyOps:
             ok = ~((p == 1.0) | np.isnan(p) | (p >= p_cut))
         return torch.from_numpy(np.bincount(self._part(p[ok], splitters), minlength=len(splitters) + 1).astype(np.int64))
 
-    def partition_scatter(self, p, splitters, send_offsets, q, p_cut):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None):
         p = p.numpy()
         qn = q.numpy()
         with np.errstate(invalid="ignore"):
@@ -140,11 +153,20 @@ def _worker(rank, world, port, tmp):
         assert ctx.last_plan["p_cut"] <= ctx.last_plan["p_cut0"]
         assert abs(cm[:, 0].sum() - cm[:, 1].sum()) < 0.1 * cm.sum()  # the sample balances the two key ranges
 
-        # exchange 1: histogram + seen bits + totals
+        assert ctx.last_plan["n_below"] == cm.sum()
+        # nothing below the cut: no exchange at all
+        ones = np.where(rng.random(5000) < 0.3, 1.0, 0.9 + 0.1 * rng.random(5000))
+        q = torch.full((5000,), -1.0, dtype=torch.float64)
+        ctx.global_bh(None, torch.from_numpy(ones.copy()), 20000.0, q=q)
+        assert ctx.last_plan["n_below"] == 0 and np.all(q.numpy() == 1.0)
+
+        # exchange 1: [histogram | totals | one slot per rank for the largest count] in one all-reduce; the seen bits are
+        # only exchanged when some rank counted lines with a count <= 0
         D = 70
-        hist = torch.zeros(D, dtype=torch.int64)
+        ns = _capi.N_SCALARS + world
+        fused = torch.zeros(D + ns, dtype=torch.int64)
+        hist, scal = fused[:D], fused[D:]
         present = torch.zeros((D + 31) // 32, dtype=torch.int32)
-        scal = torch.zeros(_capi.N_SCALARS, dtype=torch.int64)
         hist[rank::2] = rank + 1
         seen = [3, 40] if rank == 0 else [40, 63, 69]
         words = np.zeros((D + 31) // 32, dtype=np.uint32)
@@ -152,15 +174,19 @@ def _worker(rank, world, port, tmp):
             words[b >> 5] |= np.uint32(1 << (b & 31))
         present.copy_(torch.from_numpy(words.view(np.int32)))
         scal[_capi.S_INTRA_INRANGE_SUM] = 100 + rank
-        scal[_capi.S_MAX_COUNT] = 7 if rank == 0 else 19
-        ctx.allreduce_hist(hist, present, scal)
+        scal[_capi.S_NONPOS_LINES] = len(seen)
+        scal[_capi.N_SCALARS + rank] = 7 if rank == 0 else 19  # what fhc_hist_distance does with n_rank_slots = world
+        ctx.allreduce_k1(fused)
+        ctx.or_present(present)
         exp = np.zeros(D, dtype=np.int64)
         exp[0::2] = 1
         exp[1::2] = 2
         assert np.array_equal(hist.numpy(), exp)
         got_bits = np.unpackbits(present.numpy().view(np.uint8), bitorder="little")[:D]
         assert sorted(np.nonzero(got_bits)[0].tolist()) == [3, 40, 63, 69]
-        assert int(scal[_capi.S_INTRA_INRANGE_SUM]) == 201 and int(scal[_capi.S_MAX_COUNT]) == 19
+        assert int(scal[_capi.S_INTRA_INRANGE_SUM]) == 201 and int(scal[_capi.S_NONPOS_LINES]) == 5
+        assert scal[_capi.N_SCALARS:].tolist() == [7, 19] and int(scal[_capi.S_MAX_COUNT]) == 0
+        assert ctx.n_global(10 + rank) == 21 and ctx.n_global(10 + rank) == 21
         assert ctx.max_int(5 + rank) == 6
         assert ctx.allreduce_small(np.array([1, 2 + rank])).tolist() == [2, 5]
         open(os.path.join(tmp, "ok%d" % rank), "w").close()
