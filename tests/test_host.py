@@ -188,8 +188,9 @@ def test_cli_argument_handling(tmp_path, capsys):
     from fithic_b200 import fithic as cli
     a = cli.parse_args(["-i", "x.gz", "-f", "y.gz", "-o", str(tmp_path), "-r", "5000", "-p", "0", "-b", "0", "-L", "0",
                         "-x", "All", "-tL", "0.4"])
-    open(tmp_path / "x.gz", "w").close()
-    open(tmp_path / "y.gz", "w").close()
+    for name in ("x.gz", "y.gz"):  # the files are probed for gzip content like the reference does
+        with gzip.open(tmp_path / name, "wt") as f:
+            f.write("chr1\t0\t5000\t1\t1\n")
     a.intersfile, a.fragsfile = str(tmp_path / "x.gz"), str(tmp_path / "y.gz")
     st, lib_name = cli.settings_from_args(a)
     # the reference's falsy-zero idiom: 0 means default (fithic/fithic.py:194-220)
