@@ -56,6 +56,7 @@ _SIGNATURES = {
     "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_int32, c_int32, c_void_p]),
+    "fhc_mid_range": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_host_make_bins": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "fhc_host_frag_pairs": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
                                             c_int32, c_void_p, c_void_p, c_void_p]),

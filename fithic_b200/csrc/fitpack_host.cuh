@@ -14,6 +14,9 @@
 // Arrays are 1-based inside (index 0 unused) so that the recurrences read like the published ones.
 #pragma once
 #include <math.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <vector>
 
@@ -24,7 +27,8 @@ struct Work {
     int m = 0, nest = 0, k = 0;
     std::vector<double> fpint, z, a, b, g, q, t, c;
     std::vector<int> nrdata, row_l, col_time, op_time, op_list, bucket;
-    std::vector<double> row_h, row_y;
+    std::vector<double> row_h, row_y, row_knots;
+    bool row_knots_valid = false;
     void size(int m_, int nest_, int k_) {
         m = m_;
         nest = nest_;
@@ -43,6 +47,8 @@ struct Work {
         row_l.assign(rows, 0);
         row_h.assign(rows * 8, 0.0);
         row_y.assign(rows, 0.0);
+        row_knots.assign(rows * 8, 0.0);
+        row_knots_valid = false;
         col_time.assign((size_t)nest + 2, 0);
         op_time.assign((size_t)m * (k1 + 1) + 8, 0);
         op_list.assign((size_t)m * (k1 + 1) + 8, 0);
@@ -344,7 +350,17 @@ static inline int fpcurf(const double *x, const double *y, int m, int k, double 
                         const double xi = x[it];
                         while (!(xi < t[l + 1] || l == nk1)) l += 1;
                         W.row_l[(size_t)it] = l;
-                        fpbspl(t, k, xi, l, h);
+                        // the b-splines at x(it) depend on the 2k knots around its interval only: when those are the ones
+                        // of the previous knot set (one more knot changes a handful of rows), the stored values are reused
+                        double *kn = &W.row_knots[(size_t)it * 8];
+                        bool same = W.row_knots_valid;
+                        for (int u = 0; u < 2 * k && same; ++u) same = kn[u] == t[l - k + 1 + u];
+                        if (same) {
+                            for (int i = 1; i <= k1; ++i) h[i] = FHC_Q(it, i);
+                        } else {
+                            fpbspl(t, k, xi, l, h);
+                            for (int u = 0; u < 2 * k; ++u) kn[u] = t[l - k + 1 + u];
+                        }
                         double *hr = &W.row_h[(size_t)it * 8];
                         for (int i = 1; i <= k1; ++i) {
                             FHC_Q(it, i) = h[i];
@@ -352,6 +368,11 @@ static inline int fpcurf(const double *x, const double *y, int m, int k, double 
                         }
                         W.row_y[(size_t)it] = y[it] * 1.0;
                     }
+#ifdef FHC_FIT_STATS
+                    g_ta += wall_ms() - t_lsq0;
+                    const double t_s0 = wall_ms();
+#endif
+                    W.row_knots_valid = true;
                     // schedule: time of step (it, i) = 1 + max(time of (it, i - 1), last time column j was touched)
                     const int nops = m * k1;
                     for (int j = 0; j <= nk1; ++j) W.col_time[(size_t)j] = 0;
@@ -373,25 +394,28 @@ static inline int fpcurf(const double *x, const double *y, int m, int k, double 
                     for (int tt = 1; tt <= tmax + 1; ++tt) W.bucket[(size_t)tt] += W.bucket[(size_t)tt - 1];
                     for (int o = 0; o < nops; ++o) W.op_list[(size_t)W.bucket[(size_t)W.op_time[(size_t)o]]++] = o;
                     // (bucket[tt] now marks the end of wavefront tt; the ops of a row/column stay in row order inside it)
+#ifdef FHC_FIT_STATS
+                    g_tb += wall_ms() - t_s0;
+#endif
                     int pos = 0;
+                    auto op1 = [&](int o) {
+                        const int it = o / k1 + 1, i = o % k1 + 1;
+                        double *hr = &W.row_h[(size_t)it * 8];
+                        const double piv = hr[i];
+                        if (piv == 0.0) return;
+                        const int j = W.row_l[(size_t)it] - k1 + i;
+                        double cs, sn;
+                        fpgivs(piv, FHC_A(j, 1), cs, sn);
+                        fprota(cs, sn, W.row_y[(size_t)it], z[j]);
+                        int i2 = 1;
+                        for (int i1 = i + 1; i1 <= k1; ++i1) {
+                            i2 += 1;
+                            fprota(cs, sn, hr[i1], FHC_A(j, i2));
+                        }
+                    };
                     for (int tt = 1; tt <= tmax; ++tt) {
                         const int end = W.bucket[(size_t)tt];
-                        for (; pos < end; ++pos) {
-                            const int o = W.op_list[(size_t)pos];
-                            const int it = o / k1 + 1, i = o % k1 + 1;
-                            double *hr = &W.row_h[(size_t)it * 8];
-                            const double piv = hr[i];
-                            if (piv == 0.0) continue;
-                            const int j = W.row_l[(size_t)it] - k1 + i;
-                            double cs, sn;
-                            fpgivs(piv, FHC_A(j, 1), cs, sn);
-                            fprota(cs, sn, W.row_y[(size_t)it], z[j]);
-                            int i2 = 1;
-                            for (int i1 = i + 1; i1 <= k1; ++i1) {
-                                i2 += 1;
-                                fprota(cs, sn, hr[i1], FHC_A(j, i2));
-                            }
-                        }
+                        for (; pos < end; ++pos) op1(W.op_list[(size_t)pos]);
                     }
                     for (int it = 1; it <= m; ++it) fp = fp + W.row_y[(size_t)it] * W.row_y[(size_t)it];
                 }
@@ -522,31 +546,73 @@ static inline int fpcurf(const double *x, const double *y, int m, int k, double 
                 for (int j = 1; j <= k1; ++j) FHC_G(i, j) = FHC_A(i, j);
             }
             // the rows of b (weight 1 / p) are rotated into the triangle: row `it` works on column j at time it + j, after
-            // row it - 1 has left that column -- the rotations of one time step are independent (see the note above)
-            for (int it = 1; it <= n8; ++it) {
-                double *hr = &W.row_h[(size_t)it * 8];
-                for (int i = 1; i <= k2; ++i) hr[i] = FHC_BB(it, i) * pinv;
-                W.row_y[(size_t)it] = 0.0;
-            }
-            for (int tau = 2; tau <= n8 + nk1; ++tau) {
-                const int lo = tau - nk1 > 1 ? tau - nk1 : 1;
-                const int hi = tau / 2 < n8 ? tau / 2 : n8;
-                for (int it = lo; it <= hi; ++it) {
-                    const int j = tau - it;
-                    double *hr = &W.row_h[(size_t)it * 8];
-                    const double piv = hr[1];
+            // row it - 1 has left that column -- the rotations of one time step are independent (see the note above), and
+            // two of them at a time go through the SSE2 unit (same IEEE operations per lane; division and square root are
+            // what the step costs, and the packed forms have twice the throughput).  Row state is kept transposed and in
+            // reverse row order so that the rows it, it - 1 and their columns j, j + 1 are both adjacent in memory.
+            {
+                const int hs = n8 + 2;  // stride of the transposed row state: hT[i * hs + (n8 - it)]
+                double *hT = W.row_h.data();
+                double *yT = W.row_y.data();
+                for (int it = 1; it <= n8; ++it) {
+                    const int r = n8 - it;
+                    for (int i = 1; i <= k2; ++i) hT[(size_t)i * hs + r] = FHC_BB(it, i) * pinv;
+                    yT[r] = 0.0;
+                }
+                auto step1 = [&](int it, int j) {
+                    const int r = n8 - it;
+                    const double piv = hT[(size_t)1 * hs + r];
                     double cs, sn;
                     fpgivs(piv, FHC_G(j, 1), cs, sn);
-                    fprota(cs, sn, W.row_y[(size_t)it], c[j]);
-                    if (j == nk1) continue;
+                    fprota(cs, sn, yT[r], c[j]);
+                    if (j == nk1) return;
                     int i2 = k1;
                     if (j > n8) i2 = nk1 - j;
                     for (int i = 1; i <= i2; ++i) {
                         const int i1 = i + 1;
-                        fprota(cs, sn, hr[i1], FHC_G(j, i1));
-                        hr[i] = hr[i1];
+                        double hv = hT[(size_t)i1 * hs + r];
+                        fprota(cs, sn, hv, FHC_G(j, i1));
+                        hT[(size_t)i1 * hs + r] = hv;
+                        hT[(size_t)i * hs + r] = hv;
                     }
-                    hr[i2 + 1] = 0.0;
+                    hT[(size_t)(i2 + 1) * hs + r] = 0.0;
+                };
+                for (int tau = 2; tau <= n8 + nk1; ++tau) {
+                    const int lo = tau - nk1 > 1 ? tau - nk1 : 1;
+                    const int hi = tau / 2 < n8 ? tau / 2 : n8;
+                    int it = hi;
+#if defined(__SSE2__)
+                    for (; it - 1 >= lo; it -= 2) {
+                        const int j = tau - it;  // lane 0: row it, column j; lane 1: row it - 1, column j + 1
+                        if (j + 1 >= nk1 || j + 1 > n8) break;  // the last columns have shorter rows: one at a time
+                        const int r = n8 - it;
+                        const __m128d sign = _mm_set1_pd(-0.0), one = _mm_set1_pd(1.0);
+                        const __m128d piv = _mm_loadu_pd(&hT[(size_t)1 * hs + r]);
+                        const __m128d ww = _mm_loadu_pd(&FHC_G(j, 1));
+                        const __m128d store = _mm_andnot_pd(sign, piv);
+                        const __m128d ge = _mm_cmpge_pd(store, ww);
+                        const __m128d num = _mm_or_pd(_mm_and_pd(ge, ww), _mm_andnot_pd(ge, piv));
+                        const __m128d den = _mm_or_pd(_mm_and_pd(ge, piv), _mm_andnot_pd(ge, ww));
+                        const __m128d base = _mm_or_pd(_mm_and_pd(ge, store), _mm_andnot_pd(ge, ww));
+                        const __m128d rr = _mm_div_pd(num, den);
+                        const __m128d dd = _mm_mul_pd(base, _mm_sqrt_pd(_mm_add_pd(one, _mm_mul_pd(rr, rr))));
+                        const __m128d cs = _mm_div_pd(ww, dd), sn = _mm_div_pd(piv, dd);
+                        _mm_storeu_pd(&FHC_G(j, 1), dd);
+                        {
+                            const __m128d a0 = _mm_loadu_pd(&yT[r]), b0 = _mm_loadu_pd(&c[j]);
+                            _mm_storeu_pd(&c[j], _mm_add_pd(_mm_mul_pd(cs, b0), _mm_mul_pd(sn, a0)));
+                            _mm_storeu_pd(&yT[r], _mm_sub_pd(_mm_mul_pd(cs, a0), _mm_mul_pd(sn, b0)));
+                        }
+                        for (int i = 1; i <= k1; ++i) {
+                            const int i1 = i + 1;
+                            const __m128d a0 = _mm_loadu_pd(&hT[(size_t)i1 * hs + r]), b0 = _mm_loadu_pd(&FHC_G(j, i1));
+                            _mm_storeu_pd(&FHC_G(j, i1), _mm_add_pd(_mm_mul_pd(cs, b0), _mm_mul_pd(sn, a0)));
+                            _mm_storeu_pd(&hT[(size_t)i * hs + r], _mm_sub_pd(_mm_mul_pd(cs, a0), _mm_mul_pd(sn, b0)));
+                        }
+                        _mm_storeu_pd(&hT[(size_t)k2 * hs + r], _mm_setzero_pd());
+                    }
+#endif
+                    for (; it >= lo; --it) step1(it, tau - it);
                 }
             }
             fpback(W.g.data(), lda, c, nk1, k2, c);

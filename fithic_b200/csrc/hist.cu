@@ -234,3 +234,55 @@ extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const
     FHC_LAUNCH_CHECK("hist_distance_kernel");
     return FHC_OK;
 }
+
+// ---- span of the mid points -----------------------------------------------------------------------------------------------
+// The length of the distance axis (D) follows from the largest |mid1 - mid2| an intra line can have, which is bounded by
+// max(mid) - min(mid): one streaming pass over the two mid-point arrays when contacts arrive (8 B per line), instead of
+// four library reductions.  out[0] = min over both arrays, out[1] = max (int64; INT64_MAX / INT64_MIN when n == 0).
+namespace fhc {
+__global__ void __launch_bounds__(256) mid_range_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid2, long long n,
+                                                       long long *out) {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    const long long ng = n >> 2;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ng; g += (long long)gridDim.x * 256) {
+        const int4 a = ldg_stream(mid1 + g), b = ldg_stream(mid2 + g);
+        lo = min(min(min(a.x, a.y), min(a.z, a.w)), min(lo, min(min(b.x, b.y), min(b.z, b.w))));
+        hi = max(max(max(a.x, a.y), max(a.z, a.w)), max(hi, max(max(b.x, b.y), max(b.z, b.w))));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+        const long long i = (ng << 2) + threadIdx.x;
+        const int a = reinterpret_cast<const int *>(mid1)[i], b = reinterpret_cast<const int *>(mid2)[i];
+        lo = min(lo, min(a, b));
+        hi = max(hi, max(a, b));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(out, (long long)lo);
+        atomicMax(out + 1, (long long)hi);
+    }
+}
+}  // namespace fhc
+
+extern "C" int fhc_mid_range(const int32_t *mid1, const int32_t *mid2, int64_t n, int64_t *out, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && out != nullptr, FHC_E_INVALID, "fhc_mid_range: n < 0 or null output");
+    FHC_REQUIRE(n == 0 || (mid1 && mid2 && aligned16(mid1) && aligned16(mid2)), FHC_E_INVALID,
+                "fhc_mid_range: null or misaligned array");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    const long long init[2] = {INT64_MAX, INT64_MIN};
+    FHC_CUDA(cudaMemcpyAsync(out, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (n == 0) return FHC_OK;
+    long long blocks = ((n >> 2) + 255) / 256;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    mid_range_kernel<<<(unsigned int)blocks, 256, 0, st>>>(reinterpret_cast<const int4 *>(mid1),
+                                                           reinterpret_cast<const int4 *>(mid2), n,
+                                                           reinterpret_cast<long long *>(out));
+    FHC_LAUNCH_CHECK("mid_range_kernel");
+    return FHC_OK;
+}

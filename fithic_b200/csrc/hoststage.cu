@@ -27,6 +27,9 @@
 #include <vector>
 
 #include <math.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "cephes_dev.cuh"
 #include "common.cuh"
@@ -74,6 +77,55 @@ static inline double splev3_host(const double *t, const double *c, int nt, doubl
     return sp;
 }
 
+#if defined(__SSE2__)
+// Two abscissae of the same knot interval l at once, the recurrence of fpbspl written out for k = 3 (lane by lane the
+// operations of splev3_host; t[l] < t[l + 1], so none of the knot differences below is zero and the "coincident knots"
+// branch of fpbspl is never taken).
+struct SplevInterval {
+    __m128d tm2, tm1, t0, t1, t2, t3;        // t[l - 2] ... t[l + 3]
+    __m128d d10, d1m1, d20, d1m2, d2m1, d30;  // t[l+1]-t[l], t[l+1]-t[l-1], t[l+2]-t[l], t[l+1]-t[l-2], t[l+2]-t[l-1], t[l+3]-t[l]
+    __m128d c0, c1, c2, c3;
+    void set(const double *t, const double *c, int l) {
+        tm2 = _mm_set1_pd(t[l - 2]); tm1 = _mm_set1_pd(t[l - 1]); t0 = _mm_set1_pd(t[l]);
+        t1 = _mm_set1_pd(t[l + 1]); t2 = _mm_set1_pd(t[l + 2]); t3 = _mm_set1_pd(t[l + 3]);
+        d10 = _mm_set1_pd(t[l + 1] - t[l]); d1m1 = _mm_set1_pd(t[l + 1] - t[l - 1]); d20 = _mm_set1_pd(t[l + 2] - t[l]);
+        d1m2 = _mm_set1_pd(t[l + 1] - t[l - 2]); d2m1 = _mm_set1_pd(t[l + 2] - t[l - 1]); d30 = _mm_set1_pd(t[l + 3] - t[l]);
+        c0 = _mm_set1_pd(c[l - 3]); c1 = _mm_set1_pd(c[l - 2]); c2 = _mm_set1_pd(c[l - 1]); c3 = _mm_set1_pd(c[l]);
+    }
+    __m128d eval(__m128d x) const {
+        const __m128d zero = _mm_setzero_pd(), one = _mm_set1_pd(1.0);
+        // j = 1
+        __m128d f = _mm_div_pd(one, d10);
+        __m128d h0 = _mm_add_pd(zero, _mm_mul_pd(f, _mm_sub_pd(t1, x)));
+        __m128d h1 = _mm_mul_pd(f, _mm_sub_pd(x, t0));
+        // j = 2
+        __m128d g0 = h0, g1 = h1;
+        f = _mm_div_pd(g0, d1m1);
+        h0 = _mm_add_pd(zero, _mm_mul_pd(f, _mm_sub_pd(t1, x)));
+        h1 = _mm_mul_pd(f, _mm_sub_pd(x, tm1));
+        f = _mm_div_pd(g1, d20);
+        h1 = _mm_add_pd(h1, _mm_mul_pd(f, _mm_sub_pd(t2, x)));
+        __m128d h2 = _mm_mul_pd(f, _mm_sub_pd(x, t0));
+        // j = 3
+        g0 = h0; g1 = h1;
+        const __m128d g2 = h2;
+        f = _mm_div_pd(g0, d1m2);
+        h0 = _mm_add_pd(zero, _mm_mul_pd(f, _mm_sub_pd(t1, x)));
+        h1 = _mm_mul_pd(f, _mm_sub_pd(x, tm2));
+        f = _mm_div_pd(g1, d2m1);
+        h1 = _mm_add_pd(h1, _mm_mul_pd(f, _mm_sub_pd(t2, x)));
+        h2 = _mm_mul_pd(f, _mm_sub_pd(x, tm1));
+        f = _mm_div_pd(g2, d30);
+        h2 = _mm_add_pd(h2, _mm_mul_pd(f, _mm_sub_pd(t3, x)));
+        const __m128d h3 = _mm_mul_pd(f, _mm_sub_pd(x, t0));
+        __m128d sp = _mm_add_pd(zero, _mm_mul_pd(c0, h0));
+        sp = _mm_add_pd(sp, _mm_mul_pd(c1, h1));
+        sp = _mm_add_pd(sp, _mm_mul_pd(c2, h2));
+        return _mm_add_pd(sp, _mm_mul_pd(c3, h3));
+    }
+};
+#endif
+
 // possible-pair terms of one bin in the reference's order (chromosome, distance): a generator that hands out blocks
 struct BinTerms {
     const int64_t *chr_n, *nsteps;
@@ -102,7 +154,18 @@ struct BinTerms {
             if (take > cap - n) take = cap - n;
             const double *dm = dist_mb + k;
             const int64_t base = nn - k;
-            for (int64_t i = 0; i < take; ++i) out[n + i] = dm[i] * (double)(base - i);  // float(dist / 1e6) * npairs (:641)
+            // float(dist / 1e6) * npairs (:641); npairs = base - i as a double without a conversion per element (exact:
+            // integers far below 2^53)
+            int64_t i = 0;
+#if defined(__SSE2__)
+            __m128d v = _mm_set_pd((double)(base - 1), (double)base);
+            const __m128d two = _mm_set1_pd(2.0);
+            for (; i + 1 < take; i += 2) {
+                _mm_storeu_pd(out + n + i, _mm_mul_pd(_mm_loadu_pd(dm + i), v));
+                v = _mm_sub_pd(v, two);
+            }
+#endif
+            for (; i < take; ++i) out[n + i] = dm[i] * (double)(base - i);
             n += (int)take;
             k += take;
         }
@@ -240,9 +303,10 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
             jobs[(size_t)b] = {b, kb0, kb1, work};
         }
         std::sort(jobs.begin(), jobs.end(), [](const BinJob &a, const BinJob &b2) { return a.work > b2.work; });
-        // the double sums: a bin is one chain of dependent additions (the order is the reference's); four bins of similar
-        // length are summed side by side so that the adder pipeline stays full
-        const int ngroups = (nb + 3) / 4;
+        // the double sums: a bin is one chain of dependent additions (the order is the reference's); eight bins of similar
+        // length are summed side by side so that the adder pipelines stay full
+        constexpr int kChains = 8;  // two FP adders x four cycles of latency
+        const int ngroups = (nb + kChains - 1) / kChains;
         // lbeta tables
         int64_t lb_N[2] = {0, 0}, lb_n[2] = {0, 0};
         int64_t max_count = (int64_t)scal[FHC_S_MAX_COUNT];
@@ -273,21 +337,25 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         const double *dist_mb_p = dist_mb.data();  // (a thread_local named inside the lambda would be the worker's own)
         auto run_job = [&](int j) {
             if (j < ngroups) {
-                const int g0 = j * 4;
-                const int ng = nb - g0 < 4 ? nb - g0 : 4;
-                constexpr int kBlk = 512;
-                double buf[4][kBlk];
-                int len[4] = {0, 0, 0, 0}, pos[4] = {0, 0, 0, 0};
-                double s[4] = {0.0, 0.0, 0.0, 0.0};
-                bool live[4] = {false, false, false, false};
-                BinTerms gen[4];
-                for (int q = 0; q < ng; ++q) {
-                    gen[q].chr_n = chr_n;
-                    gen[q].nsteps = nsteps.data();
-                    gen[q].dist_mb = dist_mb_p;
-                    gen[q].nchr = nchr;
-                    gen[q].start(jobs[(size_t)(g0 + q)].kb0, jobs[(size_t)(g0 + q)].kb1);
-                    live[q] = true;
+                const int g0 = j * kChains;
+                const int ng = nb - g0 < kChains ? nb - g0 : kChains;
+                constexpr int kBlk = 256;
+                double buf[kChains][kBlk];
+                int len[kChains], pos[kChains];
+                double s[kChains];
+                bool live[kChains];
+                BinTerms gen[kChains];
+                for (int q = 0; q < kChains; ++q) {
+                    len[q] = pos[q] = 0;
+                    s[q] = 0.0;
+                    live[q] = q < ng;
+                    if (q < ng) {
+                        gen[q].chr_n = chr_n;
+                        gen[q].nsteps = nsteps.data();
+                        gen[q].dist_mb = dist_mb_p;
+                        gen[q].nchr = nchr;
+                        gen[q].start(jobs[(size_t)(g0 + q)].kb0, jobs[(size_t)(g0 + q)].kb1);
+                    }
                 }
                 for (;;) {
                     int mn = INT32_MAX, nlive = 0;
@@ -305,25 +373,43 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
                         if (len[q] - pos[q] < mn) mn = len[q] - pos[q];
                     }
                     if (nlive == 0) break;
-                    if (live[0] && live[1] && live[2] && live[3]) {
+                    if (nlive == kChains) {
                         const double *b0 = buf[0] + pos[0], *b1 = buf[1] + pos[1], *b2 = buf[2] + pos[2], *b3 = buf[3] + pos[3];
-                        double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3];
+                        const double *b4 = buf[4] + pos[4], *b5 = buf[5] + pos[5], *b6 = buf[6] + pos[6], *b7 = buf[7] + pos[7];
+                        double s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4], s5 = s[5], s6 = s[6], s7 = s[7];
                         for (int i = 0; i < mn; ++i) {
-                            s0 += b0[i];
-                            s1 += b1[i];
-                            s2 += b2[i];
-                            s3 += b3[i];
+                            s0 += b0[i]; s1 += b1[i]; s2 += b2[i]; s3 += b3[i];
+                            s4 += b4[i]; s5 += b5[i]; s6 += b6[i]; s7 += b7[i];
                         }
-                        s[0] = s0; s[1] = s1; s[2] = s2; s[3] = s3;
-                        for (int q = 0; q < 4; ++q) pos[q] += mn;
+                        s[0] = s0; s[1] = s1; s[2] = s2; s[3] = s3; s[4] = s4; s[5] = s5; s[6] = s6; s[7] = s7;
+                        for (int q = 0; q < kChains; ++q) pos[q] += mn;
                     } else {
+                        // the chains that are left, two at a time
+                        int qa = -1;
                         for (int q = 0; q < ng; ++q) {
                             if (!live[q]) continue;
-                            const double *bq = buf[q] + pos[q];
-                            double sq = s[q];
-                            for (int i = 0; i < mn; ++i) sq += bq[i];
-                            s[q] = sq;
+                            if (qa < 0) {
+                                qa = q;
+                                continue;
+                            }
+                            const double *ba = buf[qa] + pos[qa], *bb = buf[q] + pos[q];
+                            double sa = s[qa], sb = s[q];
+                            for (int i = 0; i < mn; ++i) {
+                                sa += ba[i];
+                                sb += bb[i];
+                            }
+                            s[qa] = sa;
+                            s[q] = sb;
+                            pos[qa] += mn;
                             pos[q] += mn;
+                            qa = -1;
+                        }
+                        if (qa >= 0) {
+                            const double *ba = buf[qa] + pos[qa];
+                            double sa = s[qa];
+                            for (int i = 0; i < mn; ++i) sa += ba[i];
+                            s[qa] = sa;
+                            pos[qa] += mn;
                         }
                     }
                 }
@@ -412,7 +498,27 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
             pool.parallel_for(nj, nworkers, [&](int j) {
                 const int64_t a = (int64_t)j * kChunk, b = a + kChunk < m ? a + kChunk : m;
                 int l = 3;
-                for (int64_t i = a; i < b; ++i) tab[i] = splev3_host(t, c, n, (double)sx[i], l);
+                int64_t i = a;
+#if defined(__SSE2__)
+                const int lmax = n - 5;
+                SplevInterval iv;
+                int l_set = -1;
+                for (; i + 1 < b; i += 2) {
+                    const double x0 = (double)sx[i], x1 = (double)sx[i + 1];
+                    while (l < lmax && t[l + 1] <= x0) ++l;
+                    if ((l < lmax && t[l + 1] <= x1) || !(t[l] < t[l + 1])) {  // the pair straddles a knot: one at a time
+                        tab[i] = splev3_host(t, c, n, x0, l);
+                        tab[i + 1] = splev3_host(t, c, n, x1, l);
+                        continue;
+                    }
+                    if (l != l_set) {
+                        iv.set(t, c, l);
+                        l_set = l;
+                    }
+                    _mm_storeu_pd(tab + i, iv.eval(_mm_set_pd(x1, x0)));
+                }
+#endif
+                for (; i < b; ++i) tab[i] = splev3_host(t, c, n, (double)sx[i], l);
             });
         }
         io->timings[3] = wall_ms() - t0;

@@ -256,27 +256,33 @@ extern "C" int fhc_spline_eval(const double *t, const double *c, int32_t nt, con
 extern "C" int fhc_host_antitonic(double *y, int64_t m) {
     FHC_REQUIRE(m >= 0 && (m == 0 || y != nullptr), FHC_E_INVALID, "fhc_host_antitonic: bad arguments");
     if (m == 0) return FHC_OK;
-    std::vector<double> sum;
-    std::vector<int64_t> cnt;
-    sum.reserve((size_t)m);
-    cnt.reserve((size_t)m);
+    // stack of blocks (sum, number of points); the counts are kept as doubles (exact integers) so that the comparison
+    // below needs no conversion per step; the buffers live as long as the calling thread
+    static thread_local std::vector<double> sum_buf, cnt_buf;
+    if ((int64_t)sum_buf.size() < m) {
+        sum_buf.resize((size_t)m);
+        cnt_buf.resize((size_t)m);
+    }
+    double *sum = sum_buf.data(), *cnt = cnt_buf.data();
+    int64_t top = -1;
     for (int64_t i = 0; i < m; ++i) {
         double s = y[i];
-        int64_t c = 1;
+        double c = 1.0;
         // non-increasing: the previous block violates when its mean is below the new block's mean
-        while (!sum.empty() && sum.back() * (double)c < s * (double)cnt.back()) {
-            s += sum.back();
-            c += cnt.back();
-            sum.pop_back();
-            cnt.pop_back();
+        while (top >= 0 && sum[top] * c < s * cnt[top]) {
+            s += sum[top];
+            c += cnt[top];
+            --top;
         }
-        sum.push_back(s);
-        cnt.push_back(c);
+        ++top;
+        sum[top] = s;
+        cnt[top] = c;
     }
     int64_t i = 0;
-    for (size_t b = 0; b < sum.size(); ++b) {
-        const double mean = sum[b] / (double)cnt[b];
-        for (int64_t k = 0; k < cnt[b]; ++k) y[i++] = mean;
+    for (int64_t b = 0; b <= top; ++b) {
+        const double mean = sum[b] / cnt[b];
+        const int64_t n = (int64_t)cnt[b];
+        for (int64_t k = 0; k < n; ++k) y[i++] = mean;
     }
     return FHC_OK;
 }

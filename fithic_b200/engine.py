@@ -346,7 +346,10 @@ class Engine:
             if self.n == 0:
                 mx = 0
             else:
-                mx = int(torch.maximum(mid1.max(), mid2.max()).item()) - int(torch.minimum(mid1.min(), mid2.min()).item())
+                rng = self._tensor("mid_range", 2, torch.int64)
+                check(self.lib.fhc_mid_range(dptr(mid1), dptr(mid2), self.n, dptr(rng), self._stream()))
+                lo, hi = rng.cpu().tolist()
+                mx = int(hi) - int(lo)
             if len(self.frags.max_mid):
                 mx = max(mx, int(self.frags.max_mid.max()))
             if self.st.resolution == 0 and self.st.U >= 0:

@@ -98,6 +98,10 @@ int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const int32_t *c
                       uint64_t *hist, uint32_t *present, int64_t D, uint64_t *scalars, int32_t n_rank_slots,
                       int32_t my_slot, void *stream);
 
+/* Smallest and largest mid point over both arrays: out[0] = min, out[1] = max (int64 [dev]; INT64_MAX / INT64_MIN when
+ * n == 0).  Every |mid1 - mid2| is at most out[1] - out[0], which sizes the distance axis D of fhc_hist_distance. */
+int fhc_mid_range(const int32_t *mid1, const int32_t *mid2, int64_t n, int64_t *out, void *stream);
+
 /* ---- host helpers for the O(D) sequential stages (bit-exact integer/float bookkeeping) ------------------------
  * makeBinsFromInteractions, fithic/fithic.py:463-553.  dists/sums [host]: the m distinct in-range distances
  * ascending with their count sums.  outl_dec [host, nullable]: not used here (see fhc_host_frag_pairs).
