@@ -61,9 +61,15 @@ __device__ __forceinline__ double p_of(u64 k) {
 constexpr int kCompactPerThread = 8;
 __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n,
                                                         const double *__restrict__ d_p_cut, double *__restrict__ q,
-                                                        u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel) {
+                                                        u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel,
+                                                        u32 *__restrict__ ghist) {
     __shared__ u32 warp_tot[8];
     __shared__ u64 block_base;
+    __shared__ u32 dhist[8 * 256];  // digit histograms of the ranked keys for the one-sweep sort (ghist != nullptr)
+    if (ghist != nullptr) {
+        for (int i = threadIdx.x; i < 8 * 256; i += 256) dhist[i] = 0;
+        __syncthreads();
+    }
     const double p_cut = *d_p_cut;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long per_iter = 256ll * kCompactPerThread;
@@ -128,15 +134,25 @@ __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restric
 #pragma unroll
         for (int j = 0; j < kCompactPerThread; ++j) {
             if (selmask & (1u << j)) {
-                keys[dst] = key_of(v[j]);
+                const u64 k = key_of(v[j]);
+                keys[dst] = k;
                 vals[dst] = (u32)(b0 + (long long)((j >> 2) * 256 + threadIdx.x) * 4 + (j & 3));
                 ++dst;
+                if (ghist != nullptr) {
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) atomicAdd(&dhist[d * 256 + ((u32)(k >> (8 * d)) & 255u)], 1u);
+                }
             }
         }
         __syncthreads();
     }
     const u32 cut = (u32)warp_sum((unsigned long long)cut_total);
     if (lane == 0 && cut) atomicAdd(nsel + 1, (u64)cut);  // rankable but known to end at q = 1.0
+    if (ghist != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 256; i += 256)
+            if (dhist[i]) atomicAdd(&ghist[i], dhist[i]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -529,6 +545,167 @@ radix_downsweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// one-sweep passes: the same stable rank + scatter per tile, but the position of a tile's digit groups in the output comes
+// from a decoupled look-back over the tiles before it instead of a separate histogram pass and a three-kernel scan
+// ---------------------------------------------------------------------------------------------------------------------
+// Digit histograms of all eight passes in one read of the keys (ghist[pass * 256 + digit]); the BH path gets them for free
+// from the compaction kernel, which holds every key in registers anyway.
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const u64 *__restrict__ keys, const u64 *d_n,
+                                                                 u32 *__restrict__ ghist) {
+    __shared__ u32 hist[8 * kRadix];
+    for (int i = threadIdx.x; i < 8 * kRadix; i += kSortThreads) hist[i] = 0;
+    __syncthreads();
+    const long long n = (long long)*d_n;
+    for (long long i = (long long)blockIdx.x * kSortThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kSortThreads) {
+        const u64 k = keys[i];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&hist[p * kRadix + ((u32)(k >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * kRadix; i += kSortThreads)
+        if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+}
+
+// gbase[pass * 256 + digit] = keys with a smaller digit in that pass; uniform[pass] = 1 when every key has the same digit
+// there (the pass would move nothing).  One CTA of 256 threads.
+__global__ void __launch_bounds__(kRadix) radix_digit_scan_kernel(const u32 *__restrict__ ghist, const u64 *d_n,
+                                                                 u32 *__restrict__ gbase, u32 *__restrict__ uniform) {
+    __shared__ u32 sw[33];
+    const u64 n = *d_n;
+    for (int p = 0; p < 8; ++p) {
+        const u32 c = ghist[p * kRadix + threadIdx.x];
+        u32 total;
+        const u32 ex = block_exclusive_scan_u32(c, sw, total);
+        gbase[p * kRadix + threadIdx.x] = ex;
+        if (threadIdx.x == 0) uniform[p] = 0;
+        __syncthreads();
+        if (c != 0 && (u64)c == n) uniform[p] = 1;
+        __syncthreads();
+    }
+}
+
+constexpr u32 kStatusAggregate = 1u, kStatusPrefix = 2u;  // low two bits of a status word; the count sits above them
+constexpr int kLookbackSpinLimit = 1 << 22;
+
+// status[tile * 256 + digit]: 0 = nothing yet, (count << 2) | 1 = this tile's own count, (count << 2) | 2 = count of this
+// tile and all tiles before it.  Tiles are handed out by an atomic counter, so every tile before a running one has been
+// claimed by a running CTA and publishes its own count without waiting for anybody: the look-back cannot dead-lock.  The
+// spin is bounded all the same (err is raised instead of hanging the GPU).
+__global__ void __launch_bounds__(kSortThreads, 3)
+radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u64 *__restrict__ keys_out,
+                      u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ gbase_pass,
+                      volatile u32 *status, u32 *tile_counter, u32 *err) {
+    extern __shared__ __align__(16) unsigned char dsmem[];
+    u64 *skeys = reinterpret_cast<u64 *>(dsmem);                                  // [kSortTile]
+    u32 *svals = reinterpret_cast<u32 *>(skeys + kSortTile);                      // [kSortTile]
+    u32(*whist)[kRadix] = reinterpret_cast<u32(*)[kRadix]>(svals + kSortTile);    // [kSortWarps][kRadix]
+    u32 *tile_off = reinterpret_cast<u32 *>(whist + kSortWarps);                  // [kRadix]
+    u32 *gpos = tile_off + kRadix;                                                // [kRadix]
+    u32 *sw = gpos + kRadix;                                                      // [33] + the tile number
+    const long long n = (long long)*d_n;
+    const u32 ntiles = n > 0 ? live_tiles(d_n) : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) sw[34] = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const u32 tile = sw[34];
+        if (tile >= ntiles) break;
+        const long long base = (long long)tile * kSortTile;
+        const int tile_n = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
+        for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
+        __syncthreads();
+
+        u64 key[kSortIPT];
+        unsigned short rank[kSortIPT];
+        const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int r = 0; r < kSortIPT; ++r) {  // warp `warp` owns [warp*512, warp*512+512) of the tile, 32 at a time
+            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+            key[r] = li < tile_n ? keys_in[base + li] : ~0ull;
+        }
+#pragma unroll
+        for (int r = 0; r < kSortIPT; ++r) {
+            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+            const bool valid = li < tile_n;
+            const u32 d = valid ? ((u32)(key[r] >> shift) & 255u) : 256u;
+            const u32 m = __match_any_sync(0xffffffffu, d);
+            u32 pre = 0;
+            if (valid) pre = whist[warp][d];
+            __syncwarp();
+            if (valid && lane == (__ffs(m) - 1)) whist[warp][d] = pre + __popc(m);
+            __syncwarp();
+            rank[r] = (unsigned short)(pre + __popc(m & lt));
+        }
+        __syncthreads();
+        // per digit (thread = digit): exclusive prefix over warps, tile total
+        u32 cnt = 0;
+        {
+            const int d = threadIdx.x;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const u32 c = whist[w][d];
+                whist[w][d] = cnt;
+                cnt += c;
+            }
+        }
+        // publish this tile's count of the digit, then add up the tiles before it
+        u32 excl = 0;
+        {
+            volatile u32 *mine = status + (size_t)tile * kRadix + threadIdx.x;
+            if (tile == 0) {
+                *mine = (cnt << 2) | kStatusPrefix;
+            } else {
+                *mine = (cnt << 2) | kStatusAggregate;
+                for (long long t = (long long)tile - 1; t >= 0; --t) {
+                    const volatile u32 *theirs = status + (size_t)t * kRadix + threadIdx.x;
+                    u32 v = *theirs;
+                    int spins = 0;
+                    while ((v & 3u) == 0u) {
+                        if (++spins > kLookbackSpinLimit) {
+                            atomicExch(err, 1u);
+                            v = kStatusPrefix;
+                            break;
+                        }
+                        v = *theirs;
+                    }
+                    excl += v >> 2;
+                    if ((v & 3u) == kStatusPrefix) break;
+                }
+                *mine = ((excl + cnt) << 2) | kStatusPrefix;
+            }
+        }
+        u32 total;
+        const u32 ex = block_exclusive_scan_u32(cnt, sw, total);
+        tile_off[threadIdx.x] = ex;
+        gpos[threadIdx.x] = gbase_pass[threadIdx.x] + excl;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSortIPT; ++r) {
+            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+            if (li < tile_n) {
+                const u32 d = (u32)(key[r] >> shift) & 255u;
+                const u32 pos = tile_off[d] + whist[warp][d] + rank[r];
+                skeys[pos] = key[r];
+                svals[pos] = vals_in[base + li];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSortIPT; ++r) {
+            const int i = r * kSortThreads + threadIdx.x;
+            if (i < tile_n) {
+                const u64 k = skeys[i];
+                const u32 d = (u32)(k >> shift) & 255u;
+                const u32 dst = gpos[d] + ((u32)i - tile_off[d]);
+                keys_out[dst] = k;
+                vals_out[dst] = svals[i];
+            }
+        }
+        __syncthreads();  // shared memory is reused by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // running max of min((p*T)/rank, 1) over the sorted keys and scatter
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bh_value(u64 key, double T, long long rank) {
@@ -537,9 +714,12 @@ __device__ __forceinline__ double bh_value(u64 key, double T, long long rank) {
     return v > 1.0 ? 1.0 : v;
 }
 
-__global__ void __launch_bounds__(kSortThreads) bh_tilemax_kernel(const u64 *__restrict__ keys, const u64 *d_n, double T,
-                                                                 long long rank_offset, double *__restrict__ tilemax) {
+// d_n[3] != 0: the sort left its result in the second pair of buffers (an odd number of passes ran)
+__global__ void __launch_bounds__(kSortThreads) bh_tilemax_kernel(const u64 *__restrict__ keys_a, const u64 *__restrict__ keys_b,
+                                                                 const u64 *d_n, double T, long long rank_offset,
+                                                                 double *__restrict__ tilemax) {
     __shared__ double sm[kSortWarps];
+    const u64 *__restrict__ keys = d_n[3] ? keys_b : keys_a;
     const long long n = (long long)*d_n;
     const u32 ntiles = live_tiles(d_n);
     for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -602,9 +782,12 @@ __global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilem
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, const u64 *d_n, double T,
-                  long long rank_offset, const double *__restrict__ tilepre, double floor_in, double *__restrict__ q) {
+bh_scatter_kernel(const u64 *__restrict__ keys_a, const u32 *__restrict__ vals_a, const u64 *__restrict__ keys_b,
+                  const u32 *__restrict__ vals_b, const u64 *d_n, double T, long long rank_offset,
+                  const double *__restrict__ tilepre, double floor_in, double *__restrict__ q) {
     __shared__ double sw[kSortWarps];
+    const u64 *__restrict__ keys = d_n[3] ? keys_b : keys_a;
+    const u32 *__restrict__ vals = d_n[3] ? vals_b : vals_a;
     const long long n = (long long)*d_n;
     const u32 ntiles = live_tiles(d_n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -642,12 +825,15 @@ bh_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, co
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 struct SortWs {
-    u32 *counts;
+    u32 *counts;     // LSD passes: per-tile digit counts; one-sweep passes: the look-back status words (same size)
     u32 *blocksums;
+    u32 *onesweep;   // [0, 2048) digit histograms of the 8 passes, [2048, 4096) their exclusive scans, [4096, 4104) "every
+                     // key has the same digit" per pass, [4104, 4112) tile counters per pass, [4112] look-back error flag
     size_t counts_len;
     int nb;
     u32 ntiles;
 };
+constexpr int kOsHist = 0, kOsBase = 2048, kOsUniform = 4096, kOsCounter = 4104, kOsErr = 4112, kOsWords = 4128;
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -666,6 +852,8 @@ static size_t sort_ws_layout(int64_t n, char *base, SortWs *ws) {
     off += align_up(counts_len * sizeof(u32) + 16);
     if (ws) ws->blocksums = reinterpret_cast<u32 *>(base + off);
     off += align_up((size_t)nb * sizeof(u32));
+    if (ws) ws->onesweep = reinterpret_cast<u32 *>(base + off);
+    off += align_up((size_t)kOsWords * sizeof(u32));
     if (ws) {
         ws->counts_len = counts_len;
         ws->nb = nb;
@@ -707,6 +895,54 @@ static int sort_pairs_device_n(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_
     return FHC_OK;
 }
 
+// One-sweep LSD sort of n_max-capacity buffers holding *d_n valid pairs (n < 2^30: a status word keeps a count in 30 bits).
+// have_hist: the digit histograms are already in ws.onesweep (bh_compact_kernel); otherwise one pass over the keys builds
+// them.  scanned: radix_digit_scan_kernel has run on them.  skip[pass] (host, nullable): passes the caller knows to be
+// uniform are not launched.  Returns the buffer that
+// holds the result in *result_in_a (1: keys_a / vals_a, 0: keys_b / vals_b).
+static int sort_pairs_onesweep(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_b, const u64 *d_n, const SortWs &ws_full,
+                               cudaStream_t st, long long known_n, bool have_hist, bool scanned, const unsigned char *skip,
+                               int *result_in_a) {
+    SortWs ws = ws_full;
+    if (known_n >= 0) {
+        const u32 t = (u32)((known_n + kSortTile - 1) / kSortTile);
+        ws.ntiles = t ? t : 1;
+    }
+    u32 *os = ws.onesweep;
+    if (!have_hist) {
+        FHC_CUDA(cudaMemsetAsync(os + kOsHist, 0, 2048 * sizeof(u32), st));
+        radix_hist_kernel<<<sort_grid(ws.ntiles, 8), kSortThreads, 0, st>>>(keys_a, d_n, os + kOsHist);
+        FHC_LAUNCH_CHECK("radix_hist_kernel");
+    }
+    if (!scanned) {
+        radix_digit_scan_kernel<<<1, kRadix, 0, st>>>(os + kOsHist, d_n, os + kOsBase, os + kOsUniform);
+        FHC_LAUNCH_CHECK("radix_digit_scan_kernel");
+    }
+    FHC_CUDA(cudaMemsetAsync(os + kOsCounter, 0, (kOsWords - kOsCounter) * sizeof(u32), st));
+    FHC_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDownsweepSmem));
+    u64 *kin = keys_a, *kout = keys_b;
+    u32 *vin = vals_a, *vout = vals_b;
+    int in_a = 1;
+    for (int pass = 0; pass < 8; ++pass) {
+        if (skip != nullptr && skip[pass]) continue;
+        FHC_CUDA(cudaMemsetAsync(ws.counts, 0, (size_t)ws.ntiles * kRadix * sizeof(u32), st));
+        radix_onesweep_kernel<<<sort_grid(ws.ntiles, 3), kSortThreads, kDownsweepSmem, st>>>(
+            kin, vin, kout, vout, d_n, pass * 8, os + kOsBase + pass * kRadix, ws.counts, os + kOsCounter + pass, os + kOsErr);
+        FHC_LAUNCH_CHECK("radix_onesweep_kernel");
+        u64 *tk = kin; kin = kout; kout = tk;
+        u32 *tv = vin; vin = vout; vout = tv;
+        in_a ^= 1;
+    }
+    *result_in_a = in_a;
+    return FHC_OK;
+}
+
+static bool use_onesweep(int64_t n) {
+    const char *e = getenv("FHC_SORT");  // lsd: the histogram / scan / scatter passes of round 1 (also taken for n >= 2^30)
+    if (e && e[0] == 'l') return false;
+    return n < (1ll << 30);
+}
+
 }  // namespace fhc
 
 extern "C" size_t fhc_sort_workspace_bytes(int64_t n) {
@@ -730,12 +966,19 @@ extern "C" int fhc_sort_pairs_u64(uint64_t *keys_in, uint32_t *vals_in, uint64_t
     sort_ws_layout(n, base + 256, &ws);
     const u64 hn = (u64)n;
     FHC_CUDA(cudaMemcpyAsync(d_n, &hn, sizeof(u64), cudaMemcpyHostToDevice, st));
-    const int rc = sort_pairs_device_n(reinterpret_cast<u64 *>(keys_in), vals_in, reinterpret_cast<u64 *>(keys_out),
-                                       vals_out, n, d_n, ws, st);
+    int in_a = 1;
+    int rc;
+    if (use_onesweep(n))
+        rc = sort_pairs_onesweep(reinterpret_cast<u64 *>(keys_in), vals_in, reinterpret_cast<u64 *>(keys_out), vals_out, d_n,
+                                 ws, st, n, false, false, nullptr, &in_a);
+    else
+        rc = sort_pairs_device_n(reinterpret_cast<u64 *>(keys_in), vals_in, reinterpret_cast<u64 *>(keys_out), vals_out, n,
+                                 d_n, ws, st);
     if (rc != FHC_OK) return rc;
-    // 8 passes: the result is back in keys_in / vals_in; move it where the caller asked for it
-    FHC_CUDA(cudaMemcpyAsync(keys_out, keys_in, sizeof(u64) * n, cudaMemcpyDeviceToDevice, st));
-    FHC_CUDA(cudaMemcpyAsync(vals_out, vals_in, sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+    if (in_a) {  // an even number of passes: the result is back in keys_in / vals_in; move it where the caller asked for it
+        FHC_CUDA(cudaMemcpyAsync(keys_out, keys_in, sizeof(u64) * n, cudaMemcpyDeviceToDevice, st));
+        FHC_CUDA(cudaMemcpyAsync(vals_out, vals_in, sizeof(u32) * n, cudaMemcpyDeviceToDevice, st));
+    }
     return FHC_OK;
 }
 
@@ -820,21 +1063,38 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
         FHC_LAUNCH_CHECK("bh_cut_find_kernel");
         long long blocks = (n + 256 * kCompactPerThread - 1) / (256 * kCompactPerThread);
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, d_p_cut, q, ws.keys_a, ws.vals_a, ws.d_n);
+        const bool onesweep = use_onesweep(n);
+        u32 *os = ws.sort.onesweep;
+        if (onesweep) FHC_CUDA(cudaMemsetAsync(os + kOsHist, 0, 2048 * sizeof(u32), st));
+        bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, d_p_cut, q, ws.keys_a, ws.vals_a, ws.d_n,
+                                                                onesweep ? os + kOsHist : nullptr);
         FHC_LAUNCH_CHECK("bh_compact_kernel");
+        if (onesweep) {  // digit offsets of all eight passes, and which passes would move nothing
+            radix_digit_scan_kernel<<<1, kRadix, 0, st>>>(os + kOsHist, ws.d_n, os + kOsBase, os + kOsUniform);
+            FHC_LAUNCH_CHECK("radix_digit_scan_kernel");
+        }
         long long known = -1;
+        unsigned char skip[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (host_ns) {
             u64 h = 0;
+            u32 uni[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             FHC_CUDA(cudaMemcpyAsync(&h, ws.d_n, sizeof(u64), cudaMemcpyDeviceToHost, st));
+            if (onesweep) FHC_CUDA(cudaMemcpyAsync(uni, os + kOsUniform, sizeof(uni), cudaMemcpyDeviceToHost, st));
             FHC_CUDA(cudaStreamSynchronize(st));
             known = (long long)h;
             *host_ns = known;
             ntiles = (int)((known + kSortTile - 1) / kSortTile);
+            for (int k = 0; k < 8; ++k) skip[k] = uni[k] ? 1 : 0;
         }
         if (known != 0) {
-            const int rc = sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st, known);
+            int in_a = 1;
+            const int rc = onesweep ? sort_pairs_onesweep(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, ws.d_n, ws.sort, st, known,
+                                                          true, true, skip, &in_a)
+                                    : sort_pairs_device_n(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, n, ws.d_n, ws.sort, st, known);
             if (rc != FHC_OK) return rc;
-            bh_tilemax_kernel<<<sort_grid((u32)ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.d_n, T, rank_offset, ws.tilemax);
+            if (!in_a) FHC_CUDA(cudaMemsetAsync(ws.d_n + 3, 0xff, sizeof(u64), st));  // the result sits in keys_b / vals_b
+            bh_tilemax_kernel<<<sort_grid((u32)ntiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.keys_b, ws.d_n, T, rank_offset,
+                                                                                  ws.tilemax);
             FHC_LAUNCH_CHECK("bh_tilemax_kernel");
         }
     }
@@ -849,8 +1109,8 @@ static int bh_finish(int64_t n, double T, int64_t rank_offset, double floor_in, 
     using namespace fhc;
     if (n > 0 && known_n != 0) {
         const u32 tiles = known_n > 0 ? (u32)((known_n + kSortTile - 1) / kSortTile) : ws.sort.ntiles;
-        bh_scatter_kernel<<<sort_grid(tiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.d_n, T, rank_offset,
-                                                                        ws.tilemax, floor_in, q);
+        bh_scatter_kernel<<<sort_grid(tiles, 8), kSortThreads, 0, st>>>(ws.keys_a, ws.vals_a, ws.keys_b, ws.vals_b, ws.d_n, T,
+                                                                        rank_offset, ws.tilemax, floor_in, q);
         FHC_LAUNCH_CHECK("bh_scatter_kernel");
     }
     return FHC_OK;

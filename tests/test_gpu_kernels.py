@@ -195,8 +195,16 @@ def test_hist_offgrid_is_reported(lib):
 # ---------------------------------------------------------------------------------------------------------------------
 # K4: sort and q-values
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(params=["onesweep", "lsd"])
+def sort_impl(request, monkeypatch):
+    """The radix sort has two implementations (one-sweep passes with decoupled look-back / histogram + scan + scatter
+    passes); the library reads FHC_SORT on every call."""
+    monkeypatch.setenv("FHC_SORT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n", [1, 31, 4096, 4097, 250_001, 3_000_000])
-def test_sort_pairs(lib, n):
+def test_sort_pairs(lib, n, sort_impl):
     rng = np.random.default_rng(n)
     keys = rng.integers(0, 1 << 63, n, dtype=np.uint64) * 2 + rng.integers(0, 2, n).astype(np.uint64)
     if n > 100:
@@ -211,6 +219,14 @@ def test_sort_pairs(lib, n):
     torch.cuda.synchronize()
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(ko.cpu().numpy().view(np.uint64), keys[order])
+    assert np.array_equal(vo.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+    # keys that differ in two digits only (p-values of one binade): the other passes are uniform
+    keys2 = (np.uint64(0x3f50000000000000) | (rng.integers(0, 1 << 16, n, dtype=np.uint64) << np.uint64(20)))
+    ki = dev(keys2.view(np.int64))
+    check(lib.fhc_sort_pairs_u64(dptr(ki), dptr(vi), dptr(ko), dptr(vo), n, dptr(ws), wsb, stream()))
+    torch.cuda.synchronize()
+    order = np.argsort(keys2, kind="stable")
+    assert np.array_equal(ko.cpu().numpy().view(np.uint64), keys2[order])
     assert np.array_equal(vo.cpu().numpy().view(np.uint32), order.astype(np.uint32))
 
 
@@ -229,7 +245,7 @@ def gpu_bh(lib, p, T, rank_offset=0, carry_in=0.0):
     return q.cpu().numpy()[:n], float(carry.item()), int(ns.item())
 
 
-def test_bh_known_answers(lib):
+def test_bh_known_answers(lib, sort_impl):
     """SURVEY.md Appendix B (outputs of the unmodified myStats.benjamini_hochberg_correction)."""
     nan = float("nan")
     kat = [([0.03, 0.4, 0.7, 0.01], 10, [0.15, 1, 1, 0.1]),
@@ -245,7 +261,7 @@ def test_bh_known_answers(lib):
 
 
 @pytest.mark.parametrize("n", [0, 1, 5, 4096, 100_003, 2_000_000])
-def test_bh_matches_oracle_bit_exact(lib, n):
+def test_bh_matches_oracle_bit_exact(lib, n, sort_impl):
     rng = np.random.default_rng(n + 5)
     p = rng.random(n) ** 3
     if n > 4:
@@ -398,6 +414,63 @@ def test_outlier_bin_decrements(lib):
     want = np.zeros(len(ub), dtype=np.int64)
     np.add.at(want, b, outl.astype(np.int64))
     assert np.array_equal(dec.cpu().numpy(), want)
+
+
+def test_outlier_bin_decrements_beyond_the_shared_memory_table(lib):
+    """-b above 2048 bins (the reference has no limit): edges and counters stay in global memory."""
+    rng = np.random.default_rng(9)
+    n, nb = 200_001, 5000
+    m1 = rng.integers(0, 10_000_000, n).astype(np.int32)
+    m2 = rng.integers(0, 10_000_000, n).astype(np.int32)
+    outl = ((rng.random(n) < 0.05) * rng.integers(1, 4, n)).astype(np.uint8)
+    ub = np.sort(rng.choice(np.arange(1, 6_000_000), nb, replace=False)).astype(np.int64)
+    dec = torch.empty(nb, dtype=torch.int64, device=DEV)
+    bufs = [dev(m1), dev(m2), dev(outl), dev(ub)]
+    check(lib.fhc_outlier_bin_decrements(dptr(bufs[0]), dptr(bufs[1]), dptr(bufs[2]), n, dptr(bufs[3]), nb, dptr(dec), stream()))
+    torch.cuda.synchronize()
+    d = np.abs(m1.astype(np.int64) - m2.astype(np.int64))
+    b = np.minimum(np.searchsorted(ub, d, side="left"), nb - 1)
+    want = np.zeros(nb, dtype=np.int64)
+    np.add.at(want, b, outl.astype(np.int64))
+    assert np.array_equal(dec.cpu().numpy(), want)
+
+
+def test_mid_range_and_digest(lib):
+    rng = np.random.default_rng(10)
+    for n in (1, 3, 4, 1_000_003):
+        m1 = rng.integers(5000, 200_000_000, n).astype(np.int32)
+        m2 = rng.integers(5000, 200_000_000, n).astype(np.int32)
+        out = torch.empty(2, dtype=torch.int64, device=DEV)
+        bufs = [dev(m1), dev(m2)]
+        check(lib.fhc_mid_range(dptr(bufs[0]), dptr(bufs[1]), n, dptr(out), stream()))
+        assert out.cpu().tolist() == [int(min(m1.min(), m2.min())), int(max(m1.max(), m2.max()))]
+    # digest: shards of a file add up to the digest of the whole file, whatever the split; any change of p or q shows
+    n = 300_007
+    p, q = rng.random(n), rng.random(n)
+    p[::97] = np.nan
+
+    def digest(lo, hi, pp=p, qq=q):
+        rl = dev(np.array([0, hi - lo], dtype=np.int64))
+        rg = dev(np.array([lo], dtype=np.int64))
+        out = torch.empty(2, dtype=torch.int64, device=DEV)
+        a, b = dev(pp[lo:hi].copy()), dev(qq[lo:hi].copy())
+        check(lib.fhc_digest_lines(dptr(a), dptr(b), hi - lo, dptr(rl), dptr(rg), 1, dptr(out), stream()))
+        return out.cpu().numpy().view(np.uint64)
+
+    whole = digest(0, n)
+    with np.errstate(over="ignore"):
+        parts = digest(0, 100_000) + digest(100_000, 100_001) + digest(100_001, n)
+    assert np.array_equal(whole, parts)
+    q2 = q.copy()
+    q2[12345] = np.nextafter(q2[12345], 1.0)
+    assert not np.array_equal(whole, digest(0, n, p, q2))
+    # two runs: lines [0, 1000) are file lines 5000 ..., the rest file lines 0 ...
+    rl = dev(np.array([0, 1000, n], dtype=np.int64))
+    rg = dev(np.array([5000, 0], dtype=np.int64))
+    out = torch.empty(2, dtype=torch.int64, device=DEV)
+    a, b = dev(p), dev(q)
+    check(lib.fhc_digest_lines(dptr(a), dptr(b), n, dptr(rl), dptr(rg), 2, dptr(out), stream()))
+    assert not np.array_equal(out.cpu().numpy().view(np.uint64), whole)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
