@@ -27,34 +27,43 @@ struct HistAcc {
     int maxc = 0;
 };
 
-__device__ __forceinline__ void hist_one(int m1, int m2, int c, unsigned int ch, bool skipped, long long Llo,
-                                         long long Uhi, unsigned int res, long long D, int S, unsigned int *sh,
-                                         unsigned long long *hist, unsigned int *present, HistAcc &a) {
+// what a contact needs besides its own fields, in 32-bit form (mid points are int32, so every distance fits 32 bits)
+struct HistConst {
+    unsigned int Llo, Uhi;   // in-range window clamped to 32 bits
+    unsigned int none;       // 1: L beyond 2^32 - 1 (nothing is in range)
+    unsigned int res;
+    unsigned int div_m, div_sh;  // d / res for d < 2^31 by one multiply-high (see pvalue_lists.cu: FrontConst)
+    unsigned int D32;        // number of slots clamped to 32 bits
+    unsigned int S;          // slots kept in shared memory
+};
+
+// INTRA: the caller knows the line is intra-chromosomal (chromosome runs), so no chromosome ids are looked at
+template <bool INTRA>
+__device__ __forceinline__ void hist_one(int m1, int m2, int c, unsigned int ch, bool skipped, const HistConst &K,
+                                         unsigned int *sh, unsigned long long *hist, unsigned int *present, HistAcc &a) {
     a.maxc = max(a.maxc, c);
     if (skipped) return;
-    const long long cs = c;
-    if ((ch & 0xffffu) != (ch >> 16)) {  // inter (fithic/fithic.py:420-422)
-        a.inter_sum += (unsigned long long)cs;
+    const unsigned long long cs = (unsigned long long)(long long)c;
+    if (!INTRA && (ch & 0xffffu) != (ch >> 16)) {  // inter (fithic/fithic.py:420-422)
+        a.inter_sum += cs;
         a.inter_n += 1;
         return;
     }
-    a.intra_sum += (unsigned long long)cs;  // any type of intra (:423-425)
+    a.intra_sum += cs;  // any type of intra (:423-425)
     a.intra_n += 1;
-    long long d = (long long)m1 - (long long)m2;
-    d = d < 0 ? -d : d;
-    if (d < Llo || d > Uhi) return;  // intraShort / intraLong
-    a.inrange_sum += (unsigned long long)cs;  // :439
+    const unsigned int d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    if (d < K.Llo || d > K.Uhi || K.none) return;  // intraShort / intraLong
+    a.inrange_sum += cs;  // :439
     a.inrange_n += 1;
-    const unsigned int du = (unsigned int)d;  // d < 2^32 always (int32 mids)
-    const unsigned int slot = du / res;
-    if (slot * res != du || (long long)slot >= D) {
+    const unsigned int slot = K.res == 1 ? d : (d < 0x80000000u ? (__umulhi(d, K.div_m) >> K.div_sh) : d / K.res);
+    if (slot * K.res != d || slot >= K.D32) {
         a.offgrid += 1;
         return;
     }
-    if (c > 0 && c < kHistSmallCount && slot < (unsigned int)S) {
+    if ((unsigned int)(c - 1) < (unsigned int)(kHistSmallCount - 1) && slot < K.S) {  // 0 < c < kHistSmallCount
         atomicAdd(&sh[slot], (unsigned int)c);
     } else {
-        if (c != 0) atomicAdd(&hist[slot], (unsigned long long)cs);
+        if (c != 0) atomicAdd(&hist[slot], cs);
         if (c <= 0) {
             atomicOr(&present[slot >> 5], 1u << (slot & 31));
             a.nonpos += 1;
@@ -78,9 +87,9 @@ __global__ void __launch_bounds__(kHistThreads, 1)
 hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid2, const int4 *__restrict__ cnt,
                      const int4 *__restrict__ chrs, const long long *__restrict__ run_start,
                      const unsigned int *__restrict__ run_val, int nruns, const unsigned int *__restrict__ skip,
-                     long long skip_limit,
-                     long long n, long long Llo, long long Uhi, unsigned int res, unsigned long long *hist,
-                     unsigned int *present, long long D, int S, unsigned long long *scalars, int max_slot) {
+                     long long skip_limit, long long n, const HistConst K, unsigned long long *hist,
+                     unsigned int *present, unsigned long long *scalars, int max_slot) {
+    const int S = (int)K.S;
     extern __shared__ unsigned int sh[];
     __shared__ unsigned long long red[FHC_N_SCALARS];
     // chromosome ids as runs (contact files are grouped by chromosome): run r covers lines [rs[r], rs[r + 1])
@@ -102,7 +111,8 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
         const long long g = t * kHistThreads + threadIdx.x;  // index of this thread's group of 4 contacts
         const int4 a1 = ldg_stream(mid1 + g), a2 = ldg_stream(mid2 + g), ac = ldg_stream(cnt + g);
         const long long i0 = g * 4;
-        int4 ah;
+        int4 ah = make_int4(0, 0, 0, 0);
+        bool all_intra = false;  // the four lines lie in one intra-chromosomal run: no chromosome ids to look at
         if (chrs != nullptr) {
             ah = ldg_stream(chrs + g);
         } else {
@@ -117,6 +127,8 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
                 ah.z = (int)rv[r2];
                 while (rs[r2 + 1] <= i0 + 3) ++r2;
                 ah.w = (int)rv[r2];
+            } else {
+                all_intra = ((unsigned int)v & 0xffffu) == ((unsigned int)v >> 16);
             }
         }
         unsigned int sk = 0;
@@ -128,10 +140,17 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
             if (i0 + 2 > skip_limit) sk &= ~0x00ff0000u;
             if (i0 + 3 > skip_limit) sk &= ~0xff000000u;
         }
-        hist_one(a1.x, a2.x, ac.x, (unsigned int)ah.x, (sk & 0x000000ffu) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
-        hist_one(a1.y, a2.y, ac.y, (unsigned int)ah.y, (sk & 0x0000ff00u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
-        hist_one(a1.z, a2.z, ac.z, (unsigned int)ah.z, (sk & 0x00ff0000u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
-        hist_one(a1.w, a2.w, ac.w, (unsigned int)ah.w, (sk & 0xff000000u) != 0, Llo, Uhi, res, D, S, sh, hist, present, a);
+        if (all_intra) {
+            hist_one<true>(a1.x, a2.x, ac.x, 0u, (sk & 0x000000ffu) != 0, K, sh, hist, present, a);
+            hist_one<true>(a1.y, a2.y, ac.y, 0u, (sk & 0x0000ff00u) != 0, K, sh, hist, present, a);
+            hist_one<true>(a1.z, a2.z, ac.z, 0u, (sk & 0x00ff0000u) != 0, K, sh, hist, present, a);
+            hist_one<true>(a1.w, a2.w, ac.w, 0u, (sk & 0xff000000u) != 0, K, sh, hist, present, a);
+        } else {
+            hist_one<false>(a1.x, a2.x, ac.x, (unsigned int)ah.x, (sk & 0x000000ffu) != 0, K, sh, hist, present, a);
+            hist_one<false>(a1.y, a2.y, ac.y, (unsigned int)ah.y, (sk & 0x0000ff00u) != 0, K, sh, hist, present, a);
+            hist_one<false>(a1.z, a2.z, ac.z, (unsigned int)ah.z, (sk & 0x00ff0000u) != 0, K, sh, hist, present, a);
+            hist_one<false>(a1.w, a2.w, ac.w, (unsigned int)ah.w, (sk & 0xff000000u) != 0, K, sh, hist, present, a);
+        }
         if (++since_flush == kHistFlushTiles) {
             hist_flush(sh, S, hist);
             since_flush = 0;
@@ -159,7 +178,7 @@ hist_distance_kernel(const int4 *__restrict__ mid1, const int4 *__restrict__ mid
                 }
                 ch = rv[lo];
             }
-            hist_one(m1[i], m2[i], cc[i], ch, skipped, Llo, Uhi, res, D, S, sh, hist, present, a);
+            hist_one<false>(m1[i], m2[i], cc[i], ch, skipped, K, sh, hist, present, a);
         }
     }
     hist_flush(sh, S, hist);
@@ -225,11 +244,23 @@ extern "C" int fhc_hist_distance(const int32_t *mid1, const int32_t *mid2, const
     int grid = (int)(ntiles < kNumSMs ? (ntiles > 0 ? ntiles : 1) : kNumSMs);
     const long long Llo = L < 0 ? 0 : L;
     const long long Uhi = U < 0 ? INT64_MAX : U;
+    HistConst K;
+    K.none = Llo > 0xffffffffll ? 1u : 0u;
+    K.Llo = (unsigned int)(Llo > 0xffffffffll ? 0xffffffffll : Llo);
+    K.Uhi = (unsigned int)(Uhi > 0xffffffffll ? 0xffffffffll : Uhi);
+    K.res = (unsigned int)res;
+    {
+        unsigned int l = 0;
+        while ((1ull << l) < (unsigned long long)res) ++l;  // ceil(log2 res)
+        K.div_sh = l ? l - 1 : 0;
+        K.div_m = res > 1 ? (unsigned int)(((1ull << (31 + l)) + (unsigned long long)res - 1) / (unsigned long long)res) : 0u;
+    }
+    K.D32 = (unsigned int)(D > 0xffffffffll ? 0xffffffffll : D);
+    K.S = (unsigned int)S;
     hist_distance_kernel<<<grid, kHistThreads, smem, st>>>(
         reinterpret_cast<const int4 *>(mid1), reinterpret_cast<const int4 *>(mid2), reinterpret_cast<const int4 *>(cnt),
         reinterpret_cast<const int4 *>(chrs), reinterpret_cast<const long long *>(run_start), run_val, nruns,
-        reinterpret_cast<const unsigned int *>(skip), skip_limit, n, Llo, Uhi,
-        (unsigned int)res, reinterpret_cast<unsigned long long *>(hist), present, D, S,
+        reinterpret_cast<const unsigned int *>(skip), skip_limit, n, K, reinterpret_cast<unsigned long long *>(hist), present,
         reinterpret_cast<unsigned long long *>(scalars), n_rank_slots > 0 ? FHC_N_SCALARS + my_slot : FHC_S_MAX_COUNT);
     FHC_LAUNCH_CHECK("hist_distance_kernel");
     return FHC_OK;

@@ -120,8 +120,8 @@ class CudaOps:
         n = p.numel()
         cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
         cap = n if capacity is None else int(capacity)  # the caller knows how many p-values lie below the cut
-        send = self.empty(cap, torch.float64)
-        idx = self.empty(cap, torch.int32)
+        send = torch.empty(max(cap, 1), dtype=torch.float64, device=self.device)  # (never empty: a null pointer is refused)
+        idx = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
         check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, float(p_cut), dptr(cursors), dptr(send),
                                                 dptr(idx), dptr(q), self._stream()))

@@ -222,7 +222,7 @@ def test_sort_pairs(lib, n, sort_impl):
     assert np.array_equal(vo.cpu().numpy().view(np.uint32), order.astype(np.uint32))
     # keys that differ in two digits only (p-values of one binade): the other passes are uniform
     keys2 = (np.uint64(0x3f50000000000000) | (rng.integers(0, 1 << 16, n, dtype=np.uint64) << np.uint64(20)))
-    ki = dev(keys2.view(np.int64))
+    ki, vi = dev(keys2.view(np.int64)), dev(vals.view(np.int32))  # (the sort uses its input buffers as scratch)
     check(lib.fhc_sort_pairs_u64(dptr(ki), dptr(vi), dptr(ko), dptr(vo), n, dptr(ws), wsb, stream()))
     torch.cuda.synchronize()
     order = np.argsort(keys2, kind="stable")
