@@ -52,6 +52,13 @@ _SIGNATURES = {
     "fhc_profile_collect": (ctypes.c_int, [c_char_p, c_size_t]),
     "fhc_copy_async": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_stream_synchronize": (ctypes.c_int, [c_void_p]),
+    "fhc_comm_handle_bytes": (c_int64, []),
+    "fhc_comm_create": (ctypes.c_int, [c_int32, c_int32, c_int64, c_void_p, c_void_p]),
+    "fhc_comm_connect": (ctypes.c_int, [c_void_p, c_void_p]),
+    "fhc_comm_allreduce_u64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_comm_allgather": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_comm_failed": (ctypes.c_int, [c_void_p]),
+    "fhc_comm_destroy": (ctypes.c_int, [c_void_p]),
     "fhc_peak_fp64": (ctypes.c_int, [c_double, c_void_p, c_void_p, c_void_p]),
     "fhc_hist_distance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                           c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p,

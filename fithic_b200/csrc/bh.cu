@@ -229,101 +229,96 @@ __host__ __device__ inline bool cut_bucket_closes(int j, u64 c_incl, double T, d
     return lhs >= rank_offset + (double)c_incl;  // both sides exact integers below 2^53 or a correctly rounded product
 }
 
-// single CTA: inclusive counts over the buckets, first non-empty bucket that closes; tighten == 0 just forwards p_cut0
-__global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict__ hist, double T, double rank_offset,
-                                                          double p_cut0, int tighten, double *__restrict__ p_cut_out) {
-    __shared__ u64 wsum[32];
-    __shared__ int best;
-    const int per = kCutBuckets / 1024;  // 32 consecutive buckets per thread
+// inclusive scan of one u64 per thread over a 1024-thread CTA; returns the inclusive value, *total = sum over the CTA
+__device__ __forceinline__ u64 block_inclusive_scan_u64(u64 v, u64 *wsum /*32*/, u64 *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) best = kCutBuckets;
-    if (!tighten || !(T > 0.0)) {
-        if (threadIdx.x == 0) *p_cut_out = p_cut0;
-        return;
-    }
-    u64 mine = 0;
-    for (int k = 0; k < per; ++k) mine += hist[threadIdx.x * per + k];
-    u64 inc = mine;
+    u64 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
+    __syncthreads();  // wsum may still be read from the previous call
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    u64 pre = inc - mine;
-    for (int w = 0; w < warp; ++w) pre += wsum[w];
+    u64 pre = 0, tot = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+        const u64 x = wsum[w];
+        if (w < warp) pre += x;
+        tot += x;
+    }
+    *total = tot;
+    return inc + pre;
+}
+
+// The cut from `nranks` value histograms laid out back to back (one on a single GPU): the smallest bucket edge from which
+// on every q is 1.0 (cut_bucket_closes on the summed histogram), or p_cut0.  One CTA of 1024 threads; the buckets are
+// walked in 32 rounds of 1024 consecutive buckets (thread = bucket: coalesced loads, the next round's loads in flight while
+// this round is scanned), with the running count carried from round to round.  Returns the closing bucket (kCutBuckets:
+// none) to every thread.
+__device__ __forceinline__ int cut_find_block(const u64 *__restrict__ hists, int nranks, double T, double rank_offset,
+                                              u64 *wsum, int *best) {
+    if (threadIdx.x == 0) *best = kCutBuckets;
+    u64 carry = 0;
     int found = kCutBuckets;
-    for (int k = 0; k < per; ++k) {
-        const int j = threadIdx.x * per + k;
-        const u64 c = hist[j];
-        pre += c;
-        if (c && found == kCutBuckets && cut_bucket_closes(j, pre, T, rank_offset)) found = j;
+    u64 cur = 0;
+    for (int r = 0; r < nranks; ++r) cur += hists[(size_t)r * kCutBuckets + threadIdx.x];
+    for (int k = 0; k < kCutBuckets / 1024; ++k) {
+        u64 nxt = 0;
+        if (k + 1 < kCutBuckets / 1024)
+            for (int r = 0; r < nranks; ++r) nxt += hists[(size_t)r * kCutBuckets + (k + 1) * 1024 + threadIdx.x];
+        u64 total;
+        const u64 inc = block_inclusive_scan_u64(cur, wsum, &total);
+        const int j = k * 1024 + threadIdx.x;
+        if (cur && found == kCutBuckets && cut_bucket_closes(j, carry + inc, T, rank_offset)) found = j;
+        carry += total;
+        cur = nxt;
     }
-    if (found < kCutBuckets) atomicMin(&best, found);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double cut = p_cut0;
-        if (best < kCutBuckets) cut = fmin(cut, cut_edge(best));
-        *p_cut_out = cut;
+    if (found < kCutBuckets) atomicMin(best, found);
+    __syncthreads();
+    return *best;
+}
+
+// single GPU: tighten == 0 just forwards p_cut0
+__global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict__ hist, double T, double rank_offset,
+                                                          double p_cut0, int tighten, double *__restrict__ p_cut_out) {
+    __shared__ u64 wsum[32];
+    __shared__ int best;
+    if (!tighten || !(T > 0.0)) {
+        if (threadIdx.x == 0) *p_cut_out = p_cut0;
+        return;
     }
+    const int b = cut_find_block(hist, 1, T, rank_offset, wsum, &best);
+    if (threadIdx.x == 0) *p_cut_out = b < kCutBuckets ? fmin(p_cut0, cut_edge(b)) : p_cut0;
 }
 
 // Multi-GPU: every rank's value histogram (all-gathered, nranks x kCutBuckets) -> the global cut, and how many p-values
-// each rank holds below it.  Same rule as bh_cut_find_kernel on the summed histogram; one CTA.  info (8 + nranks words):
-// [0] the cut (double), [1] p-values below it on all ranks, [2] on this rank, [3] the largest share of one rank,
-// [8 + r] the share of rank r.
+// each rank holds below it.  info (8 + nranks words): [0] the cut (double), [1] p-values below it on all ranks, [2] on this
+// rank, [3] the largest share of one rank, [8 + r] the share of rank r.
 __global__ void __launch_bounds__(1024) bh_cut_from_hists_kernel(const u64 *__restrict__ hists, int nranks, int my_rank,
                                                                 double T, double p_cut0, u64 *__restrict__ info) {
     __shared__ u64 wsum[32];
     __shared__ int best;
     __shared__ u64 share[64];
-    const int per = kCutBuckets / 1024;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) best = kCutBuckets;
-    if (threadIdx.x < 64) share[threadIdx.x] = 0;
-    u64 mine = 0;
-    for (int k = 0; k < per; ++k) {
-        const int j = threadIdx.x * per + k;
-        for (int r = 0; r < nranks; ++r) mine += hists[(size_t)r * kCutBuckets + j];
-    }
-    u64 inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (T > 0.0) {
-        u64 pre = inc - mine;
-        for (int w = 0; w < warp; ++w) pre += wsum[w];
-        int found = kCutBuckets;
-        for (int k = 0; k < per; ++k) {
-            const int j = threadIdx.x * per + k;
-            u64 c = 0;
-            for (int r = 0; r < nranks; ++r) c += hists[(size_t)r * kCutBuckets + j];
-            pre += c;
-            if (c && found == kCutBuckets && cut_bucket_closes(j, pre, T, 0.0)) found = j;
-        }
-        if (found < kCutBuckets) atomicMin(&best, found);
-    }
-    __syncthreads();
+    int upto = kCutBuckets;
+    if (T > 0.0) upto = cut_find_block(hists, nranks, T, 0.0, wsum, &best);
     // shares: the buckets below the closing one (all of them when none closes: the histograms only hold p < p_cut0)
-    const int upto = best;
     for (int r = 0; r < nranks; ++r) {
         u64 c = 0;
-        for (int k = 0; k < per; ++k) {
-            const int j = threadIdx.x * per + k;
+        for (int k = 0; k < kCutBuckets / 1024; ++k) {
+            const int j = k * 1024 + threadIdx.x;
             if (j < upto) c += hists[(size_t)r * kCutBuckets + j];
         }
-        c = warp_sum(c);
-        if (lane == 0 && c) atomicAdd(&share[r], c);
+        u64 total;
+        block_inclusive_scan_u64(c, wsum, &total);
+        if (threadIdx.x == 0) share[r] = total;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double cut = p_cut0;
-        if (best < kCutBuckets) cut = fmin(cut, cut_edge(best));
+        if (upto < kCutBuckets) cut = fmin(cut, cut_edge(upto));
         info[0] = (u64)__double_as_longlong(cut);
         u64 tot = 0, mx = 0;
         for (int r = 0; r < nranks; ++r) {
@@ -781,6 +776,8 @@ __global__ void __launch_bounds__(kScanThreads) bh_tilescan_kernel(double *tilem
     }
 }
 
+// Every thread takes kSortIPT CONSECUTIVE sorted keys: a running max in registers, one exclusive max-scan of the thread
+// totals per tile (instead of one block scan per 256 keys), then the scattered stores of q.
 __global__ void __launch_bounds__(kSortThreads)
 bh_scatter_kernel(const u64 *__restrict__ keys_a, const u32 *__restrict__ vals_a, const u64 *__restrict__ keys_b,
                   const u32 *__restrict__ vals_b, const u64 *d_n, double T, long long rank_offset,
@@ -792,32 +789,60 @@ bh_scatter_kernel(const u64 *__restrict__ keys_a, const u32 *__restrict__ vals_a
     const u32 ntiles = live_tiles(d_n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long base = (long long)tile * kSortTile;
-    if (base >= n) break;
-    double carry = fmax(tilepre[tile], floor_in);
-    for (int r = 0; r < kSortIPT; ++r) {
-        const long long i = base + r * kSortThreads + threadIdx.x;
-        const bool valid = i < n;
-        double inc = valid ? bh_value(keys[i], T, rank_offset + i + 1) : 0.0;
+        const long long base = (long long)tile * kSortTile;
+        if (base >= n) break;
+        const long long i0 = base + (long long)threadIdx.x * kSortIPT;
+        double v[kSortIPT];
+        double run = 0.0;
+        if (i0 + kSortIPT <= n) {
+            const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(keys + i0);  // i0 is a multiple of 16: aligned
+#pragma unroll
+            for (int k = 0; k < kSortIPT; k += 2) {
+                const ulonglong2 kk = k2[k >> 1];
+                run = fmax(run, bh_value(kk.x, T, rank_offset + i0 + k + 1));
+                v[k] = run;
+                run = fmax(run, bh_value(kk.y, T, rank_offset + i0 + k + 2));
+                v[k + 1] = run;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSortIPT; ++k) {
+                if (i0 + k < n) run = fmax(run, bh_value(keys[i0 + k], T, rank_offset + i0 + k + 1));
+                v[k] = run;
+            }
+        }
+        // exclusive running max over the threads of the tile
+        double inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc = fmax(inc, t);
         }
+        double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0.0;
         if (lane == 31) sw[warp] = inc;
         __syncthreads();
-        double wpre = carry;
-        double all = carry;
+        double pre = fmax(tilepre[tile], floor_in);
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const double s = sw[w];
-            if (w < warp) wpre = fmax(wpre, s);
-            all = fmax(all, s);
+        for (int w = 0; w < kSortWarps; ++w)
+            if (w < warp) pre = fmax(pre, sw[w]);
+        pre = fmax(pre, excl);
+        if (i0 + kSortIPT <= n) {
+            const uint4 *v4 = reinterpret_cast<const uint4 *>(vals + i0);
+#pragma unroll
+            for (int k = 0; k < kSortIPT; k += 4) {
+                const uint4 ii = v4[k >> 2];
+                q[ii.x] = fmax(v[k], pre);  // bh = max(bh, prev)   (fithic/myStats.py:43)
+                q[ii.y] = fmax(v[k + 1], pre);
+                q[ii.z] = fmax(v[k + 2], pre);
+                q[ii.w] = fmax(v[k + 3], pre);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSortIPT; ++k)
+                if (i0 + k < n) q[vals[i0 + k]] = fmax(v[k], pre);
         }
-        if (valid) q[vals[i]] = fmax(inc, wpre);  // bh = max(bh, prev)   (fithic/myStats.py:43)
-        carry = all;
-        __syncthreads();
-    }
+        __syncthreads();  // sw is reused by the next tile
     }
 }
 

@@ -361,13 +361,21 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     # K1  (read_Interactions, fithic/fithic.py:389-454)
+    def _rank_slots(self):
+        """Slots behind K1's totals, one per rank for the largest count (plus one of padding when that makes the summed
+        part [hist | totals | slots] an even number of words: the library's own all-reduce moves 16-byte words)."""
+        if self.dist is None:
+            return 0
+        w = self.dist.world
+        return w + ((self.distance_slots() + _capi.N_SCALARS + w) & 1)
+
     def hist_distance(self, skip=None, skip_limit=-1):
         D = self.distance_slots()
         mid1, mid2, cnt, chrs = self.contacts
         # one buffer [hist | totals | one slot per rank for the largest count | seen bitmap]: a single all-reduce(sum) between
         # GPUs and a single device->host copy per pass
         nwords = (D + 31) // 32
-        slots = self.dist.world if self.dist is not None else 0
+        slots = self._rank_slots()
         my = self.dist.rank if self.dist is not None else 0
         ns = _capi.N_SCALARS + slots
         buf = self._tensor("k1buf", D + ns + (nwords + 1) // 2, torch.int64)
@@ -510,7 +518,7 @@ class Engine:
         io = hs.io
         stream = self._stream()
         k1buf = self._ws["k1buf"]
-        slots = self.dist.world if self.dist is not None else 0
+        slots = self._rank_slots()
         io.n_rank_slots = slots
         nk = D + _capi.N_SCALARS + slots
         check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
@@ -602,7 +610,7 @@ class Engine:
         """The same through the stage-by-stage entry points (restriction-fragment mode and very long distance axes):
         bins and possible pairs in C, the fit in C, evaluation and lookup table on the device."""
         st, lib, res, D = self.st, self.lib, self.grid, self.D
-        slots = self.dist.world if self.dist is not None else 0
+        slots = self._rank_slots()
         ns = _capi.N_SCALARS + slots
         nw = (D + 31) // 32
         if self.dist is not None:  # rare and cheap enough here: always OR the "distance seen" bitmaps

@@ -175,15 +175,49 @@ class DistCtx:
         self.ops = ops if ops is not None else CudaOps(device)
         self.samples_per_rank = samples_per_rank
         self._n_global = None
+        # The two small exchanges of a pass go through the library's own NVLink collectives (csrc/comm.cu: peer windows
+        # shared by CUDA IPC, two kernels per collective) when every rank can set them up; FHC_COMM=nccl keeps NCCL.
+        self.comm = None
+        self.comm_slot_bytes = 0
+        if isinstance(self.ops, CudaOps) and self.world > 1 and os.environ.get("FHC_COMM", "p2p") != "nccl":
+            self._init_p2p()
         env = os.environ.get("FHC_BH_SMALL_SET")  # e.g. 0: always take the range-partitioned route (tests, timing)
         if env is not None:
             self.SMALL_SET = int(env)
+
+    def _init_p2p(self, slot_bytes=1 << 20):
+        lib = self.ops.lib
+        ok, comm = 1, ctypes.c_void_p()
+        hb = int(lib.fhc_comm_handle_bytes())
+        mine = ctypes.create_string_buffer(hb)
+        if self.world > 16 or lib.fhc_comm_create(self.rank, self.world, slot_bytes, ctypes.byref(comm), mine) != 0:
+            ok = 0
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(self.device)
+        allh = self._all_gather(t).cpu().numpy().tobytes()
+        if ok and lib.fhc_comm_connect(comm, allh) != 0:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # all ranks or none
+        if int(flag.item()) == 1:
+            self.comm, self.comm_slot_bytes = comm, slot_bytes
+        elif comm:
+            lib.fhc_comm_destroy(comm)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.comm is not None:
+            self.ops.lib.fhc_comm_destroy(self.comm)
+            self.comm = None
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
     def allreduce_k1(self, fused):
         """Sum K1's [hist | totals | rank slots] over the ranks, in place: one collective, no host synchronisation (the
         largest count travels in the rank slots, see fhc_hist_distance)."""
-        dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
+        n = fused.numel()
+        if self.comm is not None and n % 2 == 0 and 8 * n <= self.comm_slot_bytes and fused.dtype == torch.int64:
+            check(self.ops.lib.fhc_comm_allreduce_u64(self.comm, dptr(fused), n, self.ops._stream()))
+        else:
+            dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
 
     def or_present(self, present):
         """OR the 'distance seen with counts <= 0' bitmaps of all ranks, in place.  Only needed when the summed totals
@@ -213,7 +247,12 @@ class DistCtx:
     # ---- exchange 2 -------------------------------------------------------------------------------------------------
     def _all_gather(self, t):
         out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        nbytes = t.numel() * t.element_size()
+        if self.comm is not None and nbytes % 16 == 0 and 0 < nbytes <= self.comm_slot_bytes and t.is_contiguous() \
+                and t.data_ptr() % 16 == 0:
+            check(self.ops.lib.fhc_comm_allgather(self.comm, dptr(t), dptr(out), nbytes, self.ops._stream()))
+        else:
+            dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
     def n_global(self, n):

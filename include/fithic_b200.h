@@ -77,6 +77,27 @@ int fhc_stream_synchronize(void *stream);
  * double.  Synchronises the stream. */
 int fhc_peak_fp64(double seconds, double *scratch, double *tflops_out, void *stream);
 
+/* ---- single-node collectives over NVLink peer memory (csrc/comm.cu) ---------------------------------------------------
+ * The two small exchanges of a multi-GPU spline pass (the sum of [histogram | totals] over the GPUs, and the
+ * gathering of every rank's value histogram) without a communication library: one process per GPU, every rank owns a window
+ * in device memory that its peers map through CUDA IPC; a collective is two small kernels on the caller's stream (push the
+ * payload into every peer's window, then wait for everybody's flag and sum / copy locally) and never synchronises the host.
+ *   fhc_comm_create    allocates this rank's window (slot_bytes = largest payload of one rank) and writes its handle
+ *                      (fhc_comm_handle_bytes() bytes) for the host to pass to every other rank (any transport)
+ *   fhc_comm_connect   all_handles = the handles of ranks 0 .. world-1 back to back
+ *   fhc_comm_allreduce_u64  data[i] <- sum over ranks, in place (n even: the payload moves in 16-byte words)
+ *   fhc_comm_allgather dst[r * bytes ...] <- src of rank r (bytes a multiple of 16)
+ *   fhc_comm_failed    1 when a bounded wait inside a collective gave up (a peer never arrived)
+ * Every rank must issue the same collectives in the same order.  world <= 16, one node. */
+typedef struct fhc_comm fhc_comm;
+int64_t fhc_comm_handle_bytes(void);
+int fhc_comm_create(int32_t rank, int32_t world, int64_t slot_bytes, fhc_comm **comm_out, void *handle_out);
+int fhc_comm_connect(fhc_comm *comm, const void *all_handles);
+int fhc_comm_allreduce_u64(fhc_comm *comm, uint64_t *data, int64_t n, void *stream);
+int fhc_comm_allgather(fhc_comm *comm, const void *src, void *dst, int64_t bytes, void *stream);
+int fhc_comm_failed(fhc_comm *comm);
+int fhc_comm_destroy(fhc_comm *comm);
+
 /* ---- K1: distance histogram + totals ------------------------------------------------------------------------
  * Replaces the accumulation loop of read_Interactions (fithic/fithic.py:406-441) with the classification of
  * myUtils.Interaction.getType (fithic/myUtils.py:135-148).

@@ -1,9 +1,11 @@
 """Host-side timeline of one spline pass (wall-clock between synchronisation points), for tuning fixed costs.
-Run alone or under torchrun; prints per-stage milliseconds averaged over a few passes on rank 0."""
+Run alone or under torchrun; prints per-stage milliseconds averaged over a few passes on rank 0: first the pass as the
+bench runs it (no extra synchronisation), then with a device sync around every stage."""
 import os
 import sys
 import time
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,7 +29,40 @@ shards = synth.lpt_shards([int(s) for s in sizes], world)
 (m1, m2, c, ch), frags, biases, per = synth.make_intra_device(pairs, 5000, 1004, dev, only=shards[rank])
 st = E.Settings(resolution=5000, noOfBins=100)
 eng = E.Engine(st, frags, biases, device=dev, dist_ctx=ctx)
-eng.set_contacts_device(m1, m2, c, ch)
+mine = [k for k in shards[rank] if per[k] > 0]
+eng.set_contacts_device(m1, m2, c, ch, chr_runs=(np.array([k | (k << 16) for k in mine], dtype=np.uint32),
+                                                 np.array([per[k] for k in mine], dtype=np.int64)))
+
+
+def one_pass():
+    o, s = eng.new_outlier_state()
+    return eng.run_pass(1, o, s)
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+for _ in range(3):
+    one_pass()
+barrier()
+reps = 10
+t0 = time.perf_counter()
+for _ in range(reps):
+    one_pass()
+barrier()
+free = (time.perf_counter() - t0) / reps * 1e3
+# host time of run_pass alone (how long the host needs to enqueue a pass, GPU waits included where the host blocks)
+ts = []
+for _ in range(reps):
+    barrier()
+    t = time.perf_counter()
+    one_pass()
+    ts.append((time.perf_counter() - t) * 1e3)
+    barrier()
+stage = {k: v * 1e3 for k, v in eng.timings.get(1, {}).items()}
 
 marks = {}
 
@@ -46,33 +81,30 @@ def wrap(obj, name, label):
 
 
 wrap(eng, "hist_distance", "K1")
-wrap(eng, "spline_table", "K2 (eval + host pooling + lut)")
-wrap(eng, "pvalues", "K3 (+ lbeta table)")
+wrap(eng, "_tables_native", "D2H + host stage + H2D (fhc_host_stage)")
+wrap(eng, "pvalues", "K3")
 wrap(eng, "bh_qvalues", "K4 local")
-wrap(E, "make_bins", "host make_bins")
-wrap(E, "frag_pairs", "host frag_pairs")
-wrap(E, "calculate_probabilities", "host probabilities")
-wrap(E, "fit_spline", "host spline fit")
 if ctx is not None:
-    wrap(ctx, "allreduce_hist", "all-reduce hist")
-    wrap(ctx, "global_bh", "global BH (exchange + K4)")
-    for nme in ("sample_keys", "sort_keys", "partition_count", "partition_scatter", "bh_prepare", "bh_finish", "scatter"):
+    wrap(ctx, "allreduce_k1", "exchange 1: all-reduce [hist | totals | slots]")
+    wrap(ctx, "global_bh", "exchange 2 + K4 (global_bh)")
+    for nme in ("cut_hist", "cut_from_hists", "partition_scatter", "bh_qvalues", "scatter"):
         wrap(ctx.ops, nme, "  bh." + nme)
-    wrap(ctx, "_all_gather", "  bh.all_gather (x3-4)")
-reps = 6
-for i in range(reps + 2):
-    if i == 2:
-        marks.clear()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-    o, s = eng.new_outlier_state()
-    eng.run_pass(1, o, s)
-torch.cuda.synchronize()
+    wrap(ctx, "_all_gather", "  bh.all_gather")
+marks.clear()
+barrier()
+t0 = time.perf_counter()
+for _ in range(reps):
+    one_pass()
+barrier()
 tot = (time.perf_counter() - t0) / reps * 1e3
 if rank == 0:
-    print("world %d: %.2f ms per pass (with a device sync around every stage)" % (world, tot))
+    print("world %d, %d pairs, %d host threads: %.3f ms per pass back to back; run_pass on an idle GPU returns after %.3f ms "
+          "(median); %.3f ms per pass with a device sync around every stage" % (world, pairs, E.host_threads(), free,
+                                                                               float(np.median(ts)), tot))
+    print("  stage timers of the last pass: " + ", ".join("%s %.3f" % kv for kv in stage.items()))
     for k, v in marks.items():
-        print("  %-38s %7.3f ms" % (k, v / reps * 1e3))
-    print("  %-38s %7.3f ms" % ("unaccounted", tot - sum(v for k, v in marks.items() if not k.startswith("  ")) / reps * 1e3))
+        print("  %-48s %7.3f ms" % (k, v / reps * 1e3))
+    print("  %-48s %7.3f ms" % ("unaccounted (python, allocations, launches)",
+                                tot - sum(v for k, v in marks.items() if not k.startswith("  ")) / reps * 1e3))
 if world > 1:
     dist.destroy_process_group()

@@ -306,6 +306,32 @@ def test_bh_cut_hist_matches_numpy(lib, n):
             assert np.all(q[(p >= cut) & ~np.isnan(p)] == 1.0)
 
 
+@pytest.mark.parametrize("nranks", [1, 2, 8])
+def test_bh_cut_from_hists(lib, nranks):
+    """The multi-GPU cut kernel on gathered histograms against the host rule on their sum, shares per rank included."""
+    rng = np.random.default_rng(nranks)
+    B = _capi.BH_CUT_BUCKETS
+    for T, scale in ((5e6, 40), (3e9, 3), (1e3, 1000), (0.0, 5)):
+        h = np.zeros((nranks, B), dtype=np.uint64)
+        lo, hi = int(lib.fhc_host_bh_cut_bucket(1e-12)), int(lib.fhc_host_bh_cut_bucket(0.02))
+        for r in range(nranks):
+            idx = rng.integers(lo, hi, 4000)
+            np.add.at(h[r], idx, rng.integers(1, scale + 1, 4000).astype(np.uint64))
+        p_cut0 = 0.02
+        tot = np.ascontiguousarray(h.sum(axis=0), dtype=np.uint64)
+        want_cut = float(lib.fhc_host_bh_cut_find(dptr(tot), float(T), 0.0, p_cut0))
+        upto = int(lib.fhc_host_bh_cut_bucket(want_cut)) if want_cut < p_cut0 else B
+        want_share = h[:, :upto].sum(axis=1)
+        hd = dev(h.view(np.int64).reshape(-1))
+        info = torch.zeros(8 + nranks, dtype=torch.int64, device=DEV)
+        my = nranks - 1
+        check(lib.fhc_bh_cut_from_hists(dptr(hd), nranks, my, float(T), p_cut0, dptr(info), stream()))
+        got = info.cpu().numpy()
+        assert float(got[:1].view(np.float64)[0]) == want_cut, (T, want_cut)
+        assert got[8:].view(np.uint64).tolist() == want_share.tolist()
+        assert int(got[1]) == int(want_share.sum()) and int(got[2]) == int(want_share[my]) and int(got[3]) == int(want_share.max())
+
+
 @pytest.mark.parametrize("n", [0, 3, 1025, 300_001])
 def test_gather_ne_one(lib, n):
     rng = np.random.default_rng(n + 1)
