@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 6
+FHC_ABI_VERSION = 7
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES, S_NONPOS_LINES) = range(9)
 N_SCALARS = 9
@@ -52,6 +52,10 @@ _SIGNATURES = {
     "fhc_profile_collect": (ctypes.c_int, [c_char_p, c_size_t]),
     "fhc_copy_async": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "fhc_stream_synchronize": (ctypes.c_int, [c_void_p]),
+    "fhc_event_create": (ctypes.c_int, [c_void_p]),
+    "fhc_event_record": (ctypes.c_int, [c_void_p, c_void_p]),
+    "fhc_event_synchronize": (ctypes.c_int, [c_void_p]),
+    "fhc_event_destroy": (ctypes.c_int, [c_void_p]),
     "fhc_comm_handle_bytes": (c_int64, []),
     "fhc_comm_create": (ctypes.c_int, [c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "fhc_comm_connect": (ctypes.c_int, [c_void_p, c_void_p]),
@@ -92,7 +96,11 @@ _SIGNATURES = {
                                     c_void_p, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                     c_double, c_double, c_double, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
-                                    c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
+    "fhc_pvalues_prepass": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+                                            c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64,
+                                            c_double, c_double, c_int64, c_void_p, c_void_p, c_void_p]),
     "fhc_pvalues_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "fhc_bdtrc": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_bh_workspace_bytes": (c_size_t, [c_int64]),

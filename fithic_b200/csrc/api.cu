@@ -111,3 +111,25 @@ extern "C" int fhc_stream_synchronize(void *stream) {
     FHC_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return FHC_OK;
 }
+
+// A CUDA event for hosts without a CUDA binding: the engine waits for the device->host copy of K1's histogram alone while
+// the kernels it launched behind that copy (the pre-pass of K3) keep running.
+extern "C" int fhc_event_create(void **event_out) {
+    FHC_REQUIRE(event_out != nullptr, FHC_E_INVALID, "fhc_event_create: null pointer");
+    cudaEvent_t ev;
+    FHC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    *event_out = ev;
+    return FHC_OK;
+}
+extern "C" int fhc_event_record(void *event, void *stream) {
+    FHC_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+    return FHC_OK;
+}
+extern "C" int fhc_event_synchronize(void *event) {
+    FHC_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+    return FHC_OK;
+}
+extern "C" int fhc_event_destroy(void *event) {
+    if (event != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+    return FHC_OK;
+}

@@ -19,6 +19,8 @@
 #define FHC_PROFILE_STREAM st
 #include <stdlib.h>
 
+#include <string.h>
+
 #include "pvalue_common.cuh"
 
 namespace fhc {
@@ -340,34 +342,27 @@ extern "C" int fhc_bdtrc(const int32_t *cnt_minus_1, int64_t N, const double *pr
     return FHC_OK;
 }
 
-extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt,
-                           const uint32_t *chrs, const int64_t *run_start, const uint32_t *run_val, int32_t nruns,
-                           int64_t n, const double *bias, const int32_t *bias_mid,
-                           const int64_t *chr_off, int32_t nchr, int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut,
-                           int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
-                           const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
-                           uint8_t *outl, int64_t line_base, double outl_thres, uint64_t *outl_stats, double *p,
-                           double *expcc, void *workspace, size_t workspace_bytes, void *stream) {
+// shared argument checks and parameter block of fhc_pvalues / fhc_pvalues_prepass
+static int pval_params(fhc::PvalParams &P, const char *who, int32_t mode, const int32_t *mid1, const int32_t *mid2,
+                       const int32_t *cnt, const uint32_t *chrs, const int64_t *run_start, const uint32_t *run_val, int32_t nruns,
+                       int64_t n, const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
+                       int32_t bias_sparse, int32_t res, int64_t L, int64_t U, double tL, double tU, int64_t line_base,
+                       bool need_contacts) {
     using namespace fhc;
     FHC_REQUIRE(mode == FHC_MODE_INTRA_ONLY || mode == FHC_MODE_INTER_ONLY || mode == FHC_MODE_ALL, FHC_E_INVALID,
-                "fhc_pvalues: unknown mode %d", mode);
-    FHC_REQUIRE(n >= 0 && res > 0, FHC_E_INVALID, "fhc_pvalues: need n >= 0 and res > 0");
-    if (n == 0) return FHC_OK;
-    FHC_REQUIRE(mid1 && mid2 && cnt && p && expcc, FHC_E_INVALID, "fhc_pvalues: null pointer");
-    FHC_REQUIRE(chrs != nullptr || (run_start && run_val && nruns >= 1 && nruns <= FHC_MAX_CHR_RUNS), FHC_E_INVALID,
-                "fhc_pvalues: need chrs or 1 <= nruns <= %d chromosome runs", FHC_MAX_CHR_RUNS);
-    FHC_REQUIRE(aligned16(mid1) && aligned16(mid2) && aligned16(cnt) && aligned16(chrs) && aligned16(p) && aligned16(expcc),
-                FHC_E_INVALID, "fhc_pvalues: contact and output arrays must be 16-byte aligned");
-    FHC_REQUIRE(mode == FHC_MODE_INTER_ONLY || (lut != nullptr && D > 0), FHC_E_INVALID,
-                "fhc_pvalues: the distance table is required unless mode is interOnly");
-    FHC_REQUIRE(bias == nullptr || (chr_off && nchr > 0), FHC_E_INVALID, "fhc_pvalues: bias needs chr_off and nchr");
-    FHC_REQUIRE(N_intra >= 0 && N_intra < (1ll << 31) && N_inter >= 0 && N_inter < (1ll << 31), FHC_E_RANGE,
-                "fhc_pvalues: N_intra = %lld / N_inter = %lld do not fit the int32 scipy.special.bdtrc truncates n to "
-                "(the reference returns NaN or garbage there, SURVEY F5)",
-                (long long)N_intra, (long long)N_inter);
-    FHC_REQUIRE(outl == nullptr || outl_stats != nullptr, FHC_E_INVALID, "fhc_pvalues: outl needs outl_stats");
-    FHC_REQUIRE(L >= -1 && U >= -1, FHC_E_INVALID, "fhc_pvalues: L and U must be >= -1");
-    PvalParams P;
+                "%s: unknown mode %d", who, mode);
+    FHC_REQUIRE(n >= 0 && res > 0, FHC_E_INVALID, "%s: need n >= 0 and res > 0", who);
+    FHC_REQUIRE(n == 0 || !need_contacts || (mid1 && mid2), FHC_E_INVALID, "%s: null pointer", who);
+    FHC_REQUIRE(n == 0 || !need_contacts || chrs != nullptr ||
+                    (run_start && run_val && nruns >= 1 && nruns <= FHC_MAX_CHR_RUNS),
+                FHC_E_INVALID, "%s: need chrs or 1 <= nruns <= %d chromosome runs", who, FHC_MAX_CHR_RUNS);
+    FHC_REQUIRE(aligned16(mid1) && aligned16(mid2) && aligned16(cnt) && aligned16(chrs), FHC_E_INVALID,
+                "%s: contact arrays must be 16-byte aligned", who);
+    FHC_REQUIRE(bias == nullptr || (chr_off && nchr > 0), FHC_E_INVALID, "%s: bias needs chr_off and nchr", who);
+    FHC_REQUIRE(!(bias && bias_sparse) || bias_mid != nullptr, FHC_E_INVALID,
+                "%s: the sparse bias layout needs bias_mid (the sorted mid points)", who);
+    FHC_REQUIRE(L >= -1 && U >= -1, FHC_E_INVALID, "%s: L and U must be >= -1", who);
+    memset(&P, 0, sizeof(P));
     P.mode = mode;
     P.mid1 = reinterpret_cast<const int4 *>(mid1);
     P.mid2 = reinterpret_cast<const int4 *>(mid2);
@@ -380,14 +375,68 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.bias = bias;
     P.bias_mid = bias_mid;
     P.bias_sparse = bias_sparse ? 1 : 0;
-    FHC_REQUIRE(!(bias && bias_sparse) || bias_mid != nullptr, FHC_E_INVALID,
-                "fhc_pvalues: the sparse bias layout needs bias_mid (the sorted mid points)");
     P.chr_off = reinterpret_cast<const long long *>(chr_off);
     P.nchr = nchr;
     P.res.d = (unsigned int)res;
     P.res.M = res == 1 ? 0ull : (~0ull) / (unsigned long long)res + 1ull;  // ceil(2^64 / res)
     P.Llo = L < 0 ? 0 : L;
     P.Uhi = U < 0 ? INT64_MAX : U;
+    P.tL = tL;
+    P.tU = tU;
+    P.line_base = line_base;
+    return FHC_OK;
+}
+
+extern "C" int fhc_pvalues_prepass(int32_t mode, const int32_t *mid1, const int32_t *mid2, const uint32_t *chrs,
+                                   const int64_t *run_start, const uint32_t *run_val, int32_t nruns, int64_t n,
+                                   const double *bias, const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr,
+                                   int32_t bias_sparse, int32_t res, int64_t L, int64_t U, double tL, double tU,
+                                   int64_t line_base, uint32_t *code, double *b12, void *stream) {
+    using namespace fhc;
+    PvalParams P;
+    const int rc = pval_params(P, "fhc_pvalues_prepass", mode, mid1, mid2, nullptr, chrs, run_start, run_val, nruns, n, bias,
+                               bias_mid, chr_off, nchr, bias_sparse, res, L, U, tL, tU, line_base, true);
+    if (rc != FHC_OK) return rc;
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(code && b12 && aligned16(code) && aligned16(b12), FHC_E_INVALID,
+                "fhc_pvalues_prepass: code and b12 must be 16-byte aligned device arrays");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    return pvalues_prepass_launch(P, code, b12, st);
+}
+
+extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const int32_t *cnt,
+                           const uint32_t *chrs, const int64_t *run_start, const uint32_t *run_val, int32_t nruns,
+                           int64_t n, const double *bias, const int32_t *bias_mid,
+                           const int64_t *chr_off, int32_t nchr, int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut,
+                           int64_t D, int64_t N_intra, int64_t N_inter, double interChrProb, double tL, double tU,
+                           const double *lbeta_intra, int64_t ntab_intra, const double *lbeta_inter, int64_t ntab_inter,
+                           uint8_t *outl, int64_t line_base, double outl_thres, uint64_t *outl_stats, double *p,
+                           double *expcc, const uint32_t *pre_code, const double *pre_b12, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    using namespace fhc;
+    PvalParams P;
+    const bool pre = pre_code != nullptr;
+    {
+        const int rc = pval_params(P, "fhc_pvalues", mode, mid1, mid2, cnt, chrs, run_start, run_val, nruns, n, bias, bias_mid,
+                                   chr_off, nchr, bias_sparse, res, L, U, tL, tU, line_base, !pre);
+        if (rc != FHC_OK) return rc;
+    }
+    if (n == 0) return FHC_OK;
+    FHC_REQUIRE(cnt && p && expcc, FHC_E_INVALID, "fhc_pvalues: null pointer");
+    FHC_REQUIRE(aligned16(p) && aligned16(expcc), FHC_E_INVALID, "fhc_pvalues: output arrays must be 16-byte aligned");
+    FHC_REQUIRE((pre_code == nullptr) == (pre_b12 == nullptr) && aligned16(pre_code) && aligned16(pre_b12), FHC_E_INVALID,
+                "fhc_pvalues: pre_code and pre_b12 come together (fhc_pvalues_prepass), 16-byte aligned");
+    FHC_REQUIRE(!pre || D < (1ll << 30), FHC_E_INVALID, "fhc_pvalues: the pre-pass layout holds distance slots below 2^30");
+    FHC_REQUIRE(mode == FHC_MODE_INTER_ONLY || (lut != nullptr && D > 0), FHC_E_INVALID,
+                "fhc_pvalues: the distance table is required unless mode is interOnly");
+    FHC_REQUIRE(N_intra >= 0 && N_intra < (1ll << 31) && N_inter >= 0 && N_inter < (1ll << 31), FHC_E_RANGE,
+                "fhc_pvalues: N_intra = %lld / N_inter = %lld do not fit the int32 scipy.special.bdtrc truncates n to "
+                "(the reference returns NaN or garbage there, SURVEY F5)",
+                (long long)N_intra, (long long)N_inter);
+    FHC_REQUIRE(outl == nullptr || outl_stats != nullptr, FHC_E_INVALID, "fhc_pvalues: outl needs outl_stats");
+    P.pre_code = pre_code;
+    P.pre_b12 = pre_b12;
     P.lut = lut;
     P.D = lut ? D : 0;
     P.N_intra = (int)N_intra;
@@ -395,14 +444,11 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     P.invN_intra = N_intra > 0 ? 1.0 / (double)N_intra : 0.0;
     P.invN_inter = N_inter > 0 ? 1.0 / (double)N_inter : 0.0;
     P.interChrProb = interChrProb;
-    P.tL = tL;
-    P.tU = tU;
     P.lbeta_intra = lbeta_intra;
     P.ntab_intra = lbeta_intra ? ntab_intra : 0;
     P.lbeta_inter = lbeta_inter;
     P.ntab_inter = lbeta_inter ? ntab_inter : 0;
     P.outl = outl;
-    P.line_base = line_base;
     P.outl_thres = outl_thres;
     P.outl_stats = reinterpret_cast<unsigned long long *>(outl_stats);
     P.p = p;
@@ -415,8 +461,10 @@ extern "C" int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     if (workspace != nullptr && impl == 0) return pvalues_lists_launch(P, workspace, workspace_bytes, st);
-    FHC_REQUIRE(chrs != nullptr, FHC_E_INVALID, "fhc_pvalues: the tile-phased kernel needs the chrs array (chromosome runs are "
-                "read by the work-list pipeline: pass a workspace)");
+    FHC_REQUIRE(!pre, FHC_E_INVALID, "fhc_pvalues: the tile-phased kernel does not read a pre-pass (pass a workspace)");
+    FHC_REQUIRE(chrs != nullptr && mid1 != nullptr && mid2 != nullptr, FHC_E_INVALID,
+                "fhc_pvalues: the tile-phased kernel needs the mid1 / mid2 / chrs arrays (chromosome runs are read by the "
+                "work-list pipeline: pass a workspace)");
     return pvalues_tile_launch(P, st);
 }
 

@@ -41,6 +41,10 @@ struct PvalParams {
     double outl_thres;
     unsigned long long *outl_stats;
     double *p, *expcc;
+    // output of fhc_pvalues_prepass for the same contacts (both or neither; work-list pipeline only): with them the front
+    // kernel touches neither mid points, chromosome ids nor the bias table
+    const unsigned int *pre_code;
+    const double *pre_b12;
 };
 
 // bias dictionary lookup of fithic/fithic.py:1026-1054: missing chromosome or mid point -> -1
@@ -122,5 +126,6 @@ __device__ __forceinline__ void outlier_mark(const PvalParams &P, long long i, d
 int pvalues_tile_launch(const PvalParams &P, cudaStream_t st);
 size_t pvalues_lists_workspace_bytes(long long n, long long ntab);
 int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int pvalues_prepass_launch(const PvalParams &P, unsigned int *code, double *b12, cudaStream_t st);
 
 }  // namespace fhc

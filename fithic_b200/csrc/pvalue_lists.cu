@@ -138,24 +138,34 @@ __device__ __forceinline__ void front_gather(const PvalParams &P, const FrontCon
     }
 }
 
-// phase B: classification from the gathered values
+// phase B, first half: what a contact is before any table value is known (the branch order of fithic/fithic.py:1057-1115)
 // INTRA: an intra tile of a run that is not interOnly (the caller checks the mode): the intra branch with constants folded
+struct FrontFlags {
+    bool scored, intra_path, b_ok;
+};
 template <bool INTRA>
-__device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, unsigned int d, int c,
-                                                   unsigned int ch, bool in_file, double b1, double b2, double tabv,
-                                                   double &p, double &e, double &prior, bool &use_inter) {
+__device__ __forceinline__ FrontFlags front_flags(const PvalParams &P, const FrontConst &F, unsigned int d, unsigned int ch,
+                                                  bool in_file, double b1, double b2) {
     const bool inter = INTRA ? false : (ch & 0xffffu) != (ch >> 16);
-    const bool intra_path = INTRA ? true : (!inter && P.mode != FHC_MODE_INTER_ONLY);
+    FrontFlags f;
+    f.intra_path = INTRA ? true : (!inter && P.mode != FHC_MODE_INTER_ONLY);
     const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
     const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
-    const bool scored = in_file && !discarded && (intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
+    f.scored = in_file && !discarded && (f.intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
+    f.b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
+    return f;
+}
+
+// phase B, second half: prior, ExpCC and the exits of bdtrc / incbet before any real work.  b12 = rn(b1 b2).
+__device__ __forceinline__ PvalClass front_score(const PvalParams &P, const FrontConst &F, const FrontFlags f, int c, double b12,
+                                                 double tabv, double &p, double &e, double &prior, bool &use_inter) {
+    const bool intra_path = f.intra_path, scored = f.scored;
     use_inter = !intra_path;
     const double prior0 = intra_path ? tabv : P.interChrProb;  // tabv is NaN beyond the table
-    prior = __dmul_rn(prior0, __dmul_rn(b1, b2));
+    prior = __dmul_rn(prior0, b12);
     const double dN = intra_path ? F.dN_intra : F.dN_inter;
     const unsigned int N = (unsigned int)(intra_path ? P.N_intra : P.N_inter);  // 0 <= N < 2^31
-    const bool b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
-    e = (scored && b_ok) ? __dmul_rn(dN, prior) : 0.0;
+    e = (scored && f.b_ok) ? __dmul_rn(dN, prior) : 0.0;
     // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
     // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first.  For c >= 1,
     // k = c - 1 is compared as an unsigned 32-bit value (c <= 0, i.e. k < 0, is handled on its own).
@@ -178,6 +188,19 @@ __device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const Fr
     p = v;
     return cls;
 }
+
+template <bool INTRA>
+__device__ __forceinline__ PvalClass front_prepare(const PvalParams &P, const FrontConst &F, unsigned int d, int c,
+                                                   unsigned int ch, bool in_file, double b1, double b2, double tabv,
+                                                   double &p, double &e, double &prior, bool &use_inter) {
+    const FrontFlags f = front_flags<INTRA>(P, F, d, ch, in_file, b1, b2);
+    return front_score(P, F, f, c, __dmul_rn(b1, b2), tabv, p, e, prior, use_inter);
+}
+
+// What the pre-pass leaves per contact (fhc_pvalues_prepass): everything of the per-line branch order that does not need
+// the spline table, computed while the host bins and fits.  code: kPreNotScored, or b_ok << 31 | scored-against-the-inter-
+// prior << 30 | distance slot (intra path; kPreSlotMask = beyond any table); b12 = rn(bias1 bias2).
+constexpr unsigned int kPreNotScored = 0xffffffffu, kPreBok = 0x80000000u, kPreInter = 0x40000000u, kPreSlotMask = 0x3fffffffu;
 
 // ---- front ------------------------------------------------------------------------------------------------------------
 struct FrontSmem {
@@ -208,6 +231,91 @@ __device__ __forceinline__ unsigned int run_lookup(const FrontSmem &S, int nruns
 // kG contacts per thread and load (4: 128-bit loads and stores, 80 registers, 3 CTAs per SM; 2: 64-bit loads, 128-bit
 // stores of two doubles, fits 64 registers, 4 CTAs per SM); a thread handles 8 contacts of a tile either way.
 // INTRA: the whole (full) tile lies in one intra chromosome run: no chromosome ids per contact at all.
+// One tile of the kernel that follows a pre-pass (P.pre_code / P.pre_b12): the classification and the bias product come
+// from there, what is left is the table lookup, the prior and everything behind it.
+template <int kG>
+__device__ __forceinline__ unsigned int front_tile_pre(const PvalParams &P, const FrontConst &F, FrontSmem &S, long long base,
+                                                       bool full, unsigned int &flagged) {
+    const int tid = threadIdx.x;
+    const int *cs = reinterpret_cast<const int *>(P.cnt);
+    unsigned int codes = 0;
+#pragma unroll
+    for (int h = 0; h < 8 / kG; ++h) {
+        const int l0 = (h * kFrontThreads + tid) * kG;
+        int cc[kG];
+        unsigned int pc[kG];
+        double b12[kG];
+        if (full) {
+            static_assert(kG == 2, "the pre-pass variant loads two contacts per thread and step");
+            const long long g = (base + l0) >> 1;
+            const int2 ac = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + g);
+            const int2 ap = ldg_stream2(reinterpret_cast<const int2 *>(P.pre_code) + g);
+            const double2 ab = __ldcs(reinterpret_cast<const double2 *>(P.pre_b12) + g);
+            cc[0] = ac.x; cc[1] = ac.y;
+            pc[0] = (unsigned int)ap.x; pc[1] = (unsigned int)ap.y;
+            b12[0] = ab.x; b12[1] = ab.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kG; ++k) {
+                const long long i = base + l0 + k;
+                const bool ok = i < P.n;
+                cc[k] = ok ? cs[i] : 0;
+                pc[k] = ok ? P.pre_code[i] : kPreNotScored;
+                b12[k] = ok ? P.pre_b12[i] : 1.0;
+            }
+        }
+        double gtv[kG];
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {  // the one gather that is left
+            const unsigned int slot = pc[k] & kPreSlotMask;
+            const bool want = pc[k] != kPreNotScored && !(pc[k] & kPreInter) && slot < F.D32 && P.lut != nullptr;
+            const double t = P.lut != nullptr ? __ldg(P.lut + (want ? slot : 0u)) : 0.0;
+            gtv[k] = want ? t : NAN;
+        }
+        double e[kG], pv[kG];
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {
+            const int li = l0 + k;
+            FrontFlags f;
+            f.scored = pc[k] != kPreNotScored;
+            f.intra_path = !(pc[k] & kPreInter);
+            f.b_ok = (pc[k] & kPreBok) != 0;
+            double prior;
+            bool use_inter;
+            const PvalClass cls = front_score(P, F, f, cc[k], b12[k], gtv[k], pv[k], e[k], prior, use_inter);
+            if (cls == kClsK0) {
+                pv[k] = bdtrc_k0_fast(use_inter ? P.N_inter : P.N_intra, prior);
+            } else if (cls != kClsDone) {
+                S.x[li] = prior;
+                S.cnt[li] = cc[k] | (use_inter ? (int)0x80000000u : 0);
+                pv[k] = 0.0;  // overwritten by pval_finish_kernel
+            }
+            codes |= (unsigned int)cls << (2 * (h * kG + k));
+        }
+        if (full) {
+            double2 *ee = reinterpret_cast<double2 *>(P.expcc + base + l0);
+            double2 *pp = reinterpret_cast<double2 *>(P.p + base + l0);
+            __stcs(ee, make_double2(e[0], e[1]));
+            pp[0] = make_double2(pv[0], pv[1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kG; ++k)
+                if (base + l0 + k < P.n) {
+                    P.expcc[base + l0 + k] = e[k];
+                    P.p[base + l0 + k] = pv[k];
+                }
+        }
+        if (P.outl != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kG; ++k) {
+                const unsigned int c = (codes >> (2 * (h * kG + k))) & 3u;
+                if ((c == kClsDone || c == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
+            }
+        }
+    }
+    return codes;
+}
+
 template <bool HAS_BIAS, bool REGULAR, int kG, bool INTRA>
 __device__ __forceinline__ unsigned int front_tile(const PvalParams &P, const FrontConst &F, FrontSmem &S, bool rng32,
                                                    long long base, bool full, bool tile_one_run, unsigned int tile_ch,
@@ -321,19 +429,19 @@ __device__ __forceinline__ unsigned int front_tile(const PvalParams &P, const Fr
     return codes;
 }
 
-template <bool HAS_BIAS, bool REGULAR, int kMinCtas, int kG>
+template <bool HAS_BIAS, bool REGULAR, int kMinCtas, int kG, bool PRE = false>
 __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(const PvalParams P, const FrontConst F,
                                                                              const ListsWs W) {
     extern __shared__ __align__(16) unsigned char front_smem[];
     FrontSmem &S = *reinterpret_cast<FrontSmem *>(front_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool rng32 = false;
-    if (HAS_BIAS) {
+    if (HAS_BIAS && !PRE) {
         rng32 = !P.bias_sparse && P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
         if (rng32)
             for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
     }
-    const bool runs = P.chrs == nullptr;
+    const bool runs = !PRE && P.chrs == nullptr;
     if (runs) {
         for (int r = tid; r <= P.nruns; r += kFrontThreads) S.run_start[r] = P.run_start[r];
         for (int r = tid; r < P.nruns; r += kFrontThreads) S.run_val[r] = P.run_val[r];
@@ -356,7 +464,9 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
             tile_ch = S.run_val[run];
         }
         unsigned int codes;
-        if (one_run && full && (tile_ch & 0xffffu) == (tile_ch >> 16) && P.mode != FHC_MODE_INTER_ONLY)
+        if (PRE)
+            codes = front_tile_pre<2>(P, F, S, base, full, flagged);
+        else if (one_run && full && (tile_ch & 0xffffu) == (tile_ch >> 16) && P.mode != FHC_MODE_INTER_ONLY)
             codes = front_tile<HAS_BIAS, REGULAR, kG, true>(P, F, S, rng32, base, full, one_run, tile_ch, flagged);
         else
             codes = front_tile<HAS_BIAS, REGULAR, kG, false>(P, F, S, rng32, base, full, one_run, tile_ch, flagged);
@@ -417,6 +527,124 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
 }
 
 static_assert(sizeof(FrontSmem) <= 48 * 1024, "the front kernel's shared memory must fit the default 48 KB");
+
+// ---- pre-pass ---------------------------------------------------------------------------------------------------------
+// Everything of the front kernel that does not depend on the spline table -- the two bias gathers, their product and
+// window test, the class of the line (fithic/fithic.py:1057-1115) and its distance slot -- for every contact, 12 bytes out.
+// It is launched right after K1 and runs while the host bins and fits (the GPU idles there otherwise); later spline passes
+// of the same run reuse its output.
+struct PreSmem {
+    long long run_start[FHC_MAX_CHR_RUNS + 1];
+    unsigned int run_val[FHC_MAX_CHR_RUNS];
+    int2 chr_rng[kChrSmem];
+};
+
+template <bool HAS_BIAS, bool REGULAR, bool INTRA>
+__device__ __forceinline__ void prepass_pair(const PvalParams &P, const FrontConst &F, const PreSmem &S, bool rng32, int2 rng,
+                                             bool chr_ok, const int *m1, const int *m2, const unsigned int *ch, bool in_file0,
+                                             bool in_file1, unsigned int *code, double *b12) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const unsigned int c1 = ch[k] & 0xffffu, c2 = ch[k] >> 16;
+        const unsigned int d = m1[k] > m2[k] ? (unsigned int)m1[k] - (unsigned int)m2[k] : (unsigned int)m2[k] - (unsigned int)m1[k];
+        double b1 = 1.0, b2 = 1.0;
+        if (HAS_BIAS) {
+            if (rng32) {
+                if (INTRA) {
+                    b1 = bias_lookup_rng<REGULAR>(P, F, rng, chr_ok, m1[k]);
+                    b2 = bias_lookup_rng<REGULAR>(P, F, rng, chr_ok, m2[k]);
+                } else {
+                    b1 = bias_lookup_sel<REGULAR>(P, F, S.chr_rng, c1, m1[k]);
+                    b2 = bias_lookup_sel<REGULAR>(P, F, S.chr_rng, c2, m2[k]);
+                }
+            } else {
+                b1 = bias_lookup(P, c1, m1[k]);
+                b2 = bias_lookup(P, c2, m2[k]);
+            }
+        }
+        const FrontFlags f = front_flags<INTRA>(P, F, d, ch[k], k == 0 ? in_file0 : in_file1, b1, b2);
+        unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
+        slot = slot < kPreSlotMask ? slot : kPreSlotMask;
+        code[k] = !f.scored ? kPreNotScored : ((f.b_ok ? kPreBok : 0u) | (f.intra_path ? slot : kPreInter));
+        b12[k] = __dmul_rn(b1, b2);
+    }
+}
+
+template <bool HAS_BIAS, bool REGULAR>
+__global__ void __launch_bounds__(256, 4) pval_prepass_kernel(const PvalParams P, const FrontConst F,
+                                                              unsigned int *__restrict__ code_out, double *__restrict__ b12_out) {
+    __shared__ PreSmem S;
+    const int tid = threadIdx.x;
+    bool rng32 = false;
+    if (HAS_BIAS) {
+        rng32 = !P.bias_sparse && P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
+        if (rng32)
+            for (int c = tid; c < P.nchr; c += 256) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
+    }
+    const bool runs = P.chrs == nullptr;
+    if (runs) {
+        for (int r = tid; r <= P.nruns; r += 256) S.run_start[r] = P.run_start[r];
+        for (int r = tid; r < P.nruns; r += 256) S.run_val[r] = P.run_val[r];
+    }
+    __syncthreads();
+    const int *m1s = reinterpret_cast<const int *>(P.mid1), *m2s = reinterpret_cast<const int *>(P.mid2);
+    const unsigned int *hs = reinterpret_cast<const unsigned int *>(P.chrs);
+    const long long npairs = (P.n + 1) >> 1;
+    int run = 0;
+    for (long long g = (long long)blockIdx.x * 256 + tid; g < npairs; g += (long long)gridDim.x * 256) {
+        const long long i0 = g << 1;
+        const bool two = i0 + 1 < P.n;
+        int m1[2], m2[2];
+        unsigned int ch[2];
+        bool one_run = false;
+        if (two) {
+            const int2 a1 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid1) + g);
+            const int2 a2 = ldg_stream2(reinterpret_cast<const int2 *>(P.mid2) + g);
+            m1[0] = a1.x; m1[1] = a1.y;
+            m2[0] = a2.x; m2[1] = a2.y;
+        } else {
+            m1[0] = m1s[i0]; m2[0] = m2s[i0];
+            m1[1] = 0; m2[1] = 0;
+        }
+        if (!runs) {
+            ch[0] = hs[i0];
+            ch[1] = two ? hs[i0 + 1] : 0x00010000u;
+        } else {
+            const long long gl = P.line_base + i0;
+            while (S.run_start[run + 1] <= gl) ++run;
+            ch[0] = S.run_val[run];
+            one_run = S.run_start[run + 1] > gl + 1;
+            ch[1] = one_run ? ch[0] : (two ? S.run_val[run + 1 < P.nruns ? run + 1 : run] : 0x00010000u);
+            if (!one_run && two) {  // (runs may be empty in theory: find the run of the second line properly)
+                int r2 = run;
+                while (S.run_start[r2 + 1] <= gl + 1) ++r2;
+                ch[1] = S.run_val[r2];
+            }
+        }
+        unsigned int code[2];
+        double b12[2];
+        const bool intra = runs && one_run && (ch[0] & 0xffffu) == (ch[0] >> 16) && P.mode != FHC_MODE_INTER_ONLY;
+        if (intra) {
+            int2 rng = make_int2(0, 0);
+            bool chr_ok = false;
+            if (HAS_BIAS && rng32) {
+                const unsigned int c = ch[0] & 0xffffu;
+                chr_ok = c < (unsigned int)P.nchr;
+                rng = S.chr_rng[chr_ok ? c : 0u];
+            }
+            prepass_pair<HAS_BIAS, REGULAR, true>(P, F, S, rng32, rng, chr_ok, m1, m2, ch, true, two, code, b12);
+        } else {
+            prepass_pair<HAS_BIAS, REGULAR, false>(P, F, S, rng32, make_int2(0, 0), false, m1, m2, ch, true, two, code, b12);
+        }
+        if (two) {
+            reinterpret_cast<uint2 *>(code_out)[g] = make_uint2(code[0], code[1]);
+            reinterpret_cast<double2 *>(b12_out)[g] = make_double2(b12[0], b12[1]);
+        } else {
+            code_out[i0] = code[0];
+            b12_out[i0] = b12[0];
+        }
+    }
+}
 
 // ---- iterate ----------------------------------------------------------------------------------------------------------
 // One list, one kind of recurrence.  A warp claims a chunk of kIterChunk list positions with one global atomic, loads the
@@ -580,6 +808,39 @@ __global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(c
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------------
+static FrontConst make_front_const(const PvalParams &P) {
+    FrontConst F;
+    F.nothing_in_range = P.Llo > 0xffffffffll;
+    F.Llo = (unsigned int)(P.Llo > 0xffffffffll ? 0xffffffffll : P.Llo);
+    F.Uhi = (unsigned int)(P.Uhi > 0xffffffffll ? 0xffffffffll : P.Uhi);
+    F.dN_intra = (double)P.N_intra;
+    F.dN_inter = (double)P.N_inter;
+    F.dNp1_intra = (double)P.N_intra + 1.0;
+    F.dNp1_inter = (double)P.N_inter + 1.0;
+    const unsigned int d = P.res.d;
+    unsigned int l = 0;
+    while ((1ull << l) < d) ++l;  // ceil(log2 d)
+    F.div_sh = l ? l - 1 : 0;
+    F.div_m = d > 1 ? (unsigned int)(((1ull << (31 + l)) + d - 1) / d) : 0u;
+    F.D32 = (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
+    return F;
+}
+
+int pvalues_prepass_launch(const PvalParams &P, unsigned int *code, double *b12, cudaStream_t st) {
+    const FrontConst F = make_front_const(P);
+    long long blocks = (((P.n + 1) >> 1) + 255) / 256;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    if (!P.bias)
+        pval_prepass_kernel<false, true><<<(unsigned int)blocks, 256, 0, st>>>(P, F, code, b12);
+    else if (P.bias_mid == nullptr && !P.bias_sparse)
+        pval_prepass_kernel<true, true><<<(unsigned int)blocks, 256, 0, st>>>(P, F, code, b12);
+    else
+        pval_prepass_kernel<true, false><<<(unsigned int)blocks, 256, 0, st>>>(P, F, code, b12);
+    FHC_LAUNCH_CHECK("pval_prepass_kernel");
+    return FHC_OK;
+}
+
 static size_t lists_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t lists_layout(long long n, long long ntab_intra, long long ntab_inter, char *base, ListsWs *ws) {
@@ -624,22 +885,7 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
                                                                                   W.aux_inter);
         FHC_LAUNCH_CHECK("lbeta_aux_kernel");
     }
-    FrontConst F;
-    F.nothing_in_range = P.Llo > 0xffffffffll;
-    F.Llo = (unsigned int)(P.Llo > 0xffffffffll ? 0xffffffffll : P.Llo);
-    F.Uhi = (unsigned int)(P.Uhi > 0xffffffffll ? 0xffffffffll : P.Uhi);
-    F.dN_intra = (double)P.N_intra;
-    F.dN_inter = (double)P.N_inter;
-    F.dNp1_intra = (double)P.N_intra + 1.0;
-    F.dNp1_inter = (double)P.N_inter + 1.0;
-    {
-        const unsigned int d = P.res.d;
-        unsigned int l = 0;
-        while ((1ull << l) < d) ++l;  // ceil(log2 d)
-        F.div_sh = l ? l - 1 : 0;
-        F.div_m = d > 1 ? (unsigned int)(((1ull << (31 + l)) + d - 1) / d) : 0u;
-    }
-    F.D32 = (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
+    const FrontConst F = make_front_const(P);
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
     long long blocks = tiles;
     // Default: two contacts per load in 64 registers, 4 CTAs per SM.  FHC_PVAL_FRONT=g4 selects four contacts per load in
@@ -662,7 +908,9 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
         else                                                                                                      \
             pval_front_kernel<B, R, 3, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
     } while (0)
-    if (!P.bias)
+    if (P.pre_code != nullptr)
+        pval_front_kernel<false, true, 4, 2, true><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W);
+    else if (!P.bias)
         FHC_FRONT_V(false, true);
     else if (P.bias_mid == nullptr && !P.bias_sparse)
         FHC_FRONT_V(true, true);

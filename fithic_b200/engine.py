@@ -146,6 +146,7 @@ class _HostStage:
         io.want_spline = 0 if st.interOnly else 1
         io.nthreads = self.nthreads
         self.D = 0
+        self.event = None
         self.lbeta = [None, None]  # pinned tensors
 
     def ensure(self, D):
@@ -431,7 +432,7 @@ class Engine:
         thres = (1.0 / T) if T != 0 else float("inf")
         out["outlierThres"] = thres
         p, e = self.pvalues(lut, N, obsInterAllSum, interChrProb, out["max_count"], outl, thres, outl_stats, pvalue_chunks,
-                            after_chunk, lbeta=lbeta)
+                            after_chunk, lbeta=lbeta, use_prepass=native)
         if after_pvalues is not None:
             after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
         # ---- K4 ----
@@ -522,6 +523,13 @@ class Engine:
         io.n_rank_slots = slots
         nk = D + _capi.N_SCALARS + slots
         check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
+        if hs.event is None:
+            ev = ctypes.c_void_p()
+            check(lib.fhc_event_create(ctypes.byref(ev)))
+            hs.event = ev
+        check(lib.fhc_event_record(hs.event, stream))
+        # behind the copy, while the host bins and fits: the part of K3 that does not need the spline table
+        self.prepass(passNo)
         lib.fhc_host_pool_prewarm(hs.nthreads)
         hs.new_outputs()
         use_host_lbeta = os.environ.get("FHC_LBETA_TABLE", "host") != "device"
@@ -532,7 +540,7 @@ class Engine:
             else:
                 io.lbeta_tab[w] = None
                 io.lbeta_cap[w] = 0
-        check(lib.fhc_stream_synchronize(stream))
+        check(lib.fhc_event_synchronize(hs.event))  # the histogram is on the host (the pre-pass may still be running)
         scal = hs.k1_np[D:nk]
         if slots:
             scal[_capi.S_MAX_COUNT] = scal[_capi.N_SCALARS:].max()
@@ -703,9 +711,37 @@ class Engine:
         check(self.lib.fhc_lbeta_table(int(N), dptr(tab), ntab, self._stream()))
         return tab, ntab
 
+    def prepass(self, passNo):
+        """fhc_pvalues_prepass over all contacts (work-list K3 only): bias products, line classes and distance slots, 12 B
+        per contact.  Computed in the first pass of a run -- launched right behind K1, so it runs while the host bins and
+        fits -- and reused by the later passes (it depends on nothing a pass changes)."""
+        self._pre_live = False
+        if os.environ.get("FHC_PREPASS", "1") == "0" or os.environ.get("FHC_PVAL_IMPL", "lists")[:1] == "t" \
+                or self.distance_slots() >= (1 << 30) or self.n == 0:
+            return
+        code = self._tensor("pre_code", self.n, torch.int32)
+        b12 = self._tensor("pre_b12", self.n, torch.float64)
+        key = (self.contacts[0].data_ptr(), self.n, id(self._bias_dev))
+        if passNo == 1 or getattr(self, "_pre_key", None) != key:
+            st = self.st
+            mid1, mid2, cnt, chrs = self.contacts
+            rs, rv, nruns = self.chr_runs_dev if self.chr_runs_dev is not None else (None, None, 0)
+            bias = bmid = boff = None
+            nchr = 0
+            if self._bias_dev is not None:
+                bias, bmid, boff = self._bias_dev
+                nchr = boff.numel() - 1
+            check(self.lib.fhc_pvalues_prepass(st.mode, dptr(mid1), dptr(mid2), None if nruns else dptr(self.chrs_array()),
+                                               dptr(rs), dptr(rv), nruns, self.n, dptr(bias), dptr(bmid), dptr(boff), nchr,
+                                               getattr(self, "_bias_sparse", 0), self.grid, st.L, st.U,
+                                               float(st.biasLowerBound), float(st.biasUpperBound), 0, dptr(code), dptr(b12),
+                                               self._stream()))
+            self._pre_key = key
+        self._pre_live = True
+
     # K3  (fit_Spline per-line loop, fithic/fithic.py:1017-1123)
     def pvalues(self, lut, N_intra, N_inter, interChrProb, max_count, outl=None, outl_thres=0.0, outl_stats=None,
-                nchunks=1, after_chunk=None, lbeta=None):
+                nchunks=1, after_chunk=None, lbeta=None, use_prepass=False):
         """nchunks > 1 launches K3 once per contiguous slice of the contacts and calls after_chunk(lo, hi, p, e) after
         each launch, so that a caller can start moving finished slices to the host while the next one is computed."""
         st = self.st
@@ -717,6 +753,9 @@ class Engine:
             chrs = self.chrs_array()  # the tile-phased kernel reads the per-line array
             rs, rv, nruns = None, None, 0
         n = self.n
+        pre_code = pre_b12 = None
+        if use_prepass and getattr(self, "_pre_live", False):
+            pre_code, pre_b12 = self._ws["pre_code"][:n], self._ws["pre_b12"][:n]
         p = self._tensor("p", n, torch.float64)
         e = self._tensor("expcc", n, torch.float64)
         tab_a = tab_b = None
@@ -747,7 +786,8 @@ class Engine:
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
                                        nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),
-                                       dptr(e[lo:hi]), dptr(ws), wsb, self._stream()))
+                                       dptr(e[lo:hi]), None if pre_code is None else dptr(pre_code[lo:hi]),
+                                       None if pre_b12 is None else dptr(pre_b12[lo:hi]), dptr(ws), wsb, self._stream()))
             if after_chunk is not None:
                 after_chunk(lo, hi, p, e)
             lo = hi

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 6
+#define FHC_ABI_VERSION 7
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -70,6 +70,11 @@ int fhc_profile_collect(char *buf, size_t buf_bytes);
  * cudaStreamSynchronize. */
 int fhc_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int fhc_stream_synchronize(void *stream);
+/* ... and a CUDA event (no timing): record it behind a copy, go on launching, wait for the copy alone. */
+int fhc_event_create(void **event_out);
+int fhc_event_record(void *event, void *stream);
+int fhc_event_synchronize(void *event);
+int fhc_event_destroy(void *event);
 
 /* FP64 FMA throughput of the current device in TFLOP/s (2 flops per FMA, 16 independent chains per thread): the compute
  * roofline bench.py reports K3 against (K3 is bound by FP64 latency and instruction issue, not by HBM).  seconds <= 0: best
@@ -271,6 +276,7 @@ double fhc_host_one_minus_exp(double y);
  *              lines [run_start[r], run_start[r+1]) COUNTED LIKE line_base (the first contact passed is line line_base of
  *              the run table's numbering) and all of them have chrs = run_val[r].  4 B per line less to read, and a tile of
  *              contacts inside one intra run is scored without any per-contact chromosome logic.
+ *   pre_code, pre_b12  nullable (both or neither): the output of fhc_pvalues_prepass for the same contacts
  *   workspace  [dev, nullable] fhc_pvalues_workspace_bytes(n, ntab) bytes, ntab = max(ntab_intra, ntab_inter).  With a
  *              workspace the contacts that need an iterative evaluation (continued fraction / tail sum) are compacted
  *              into work lists in HBM and the call runs as three kernels with full warps (pvalue_lists.cu); without one
@@ -282,7 +288,22 @@ int fhc_pvalues(int32_t mode, const int32_t *mid1, const int32_t *mid2, const in
                 int32_t bias_sparse, int32_t res, int64_t L, int64_t U, const double *lut, int64_t D, int64_t N_intra, int64_t N_inter,
                 double interChrProb, double tL, double tU, const double *lbeta_intra, int64_t ntab_intra,
                 const double *lbeta_inter, int64_t ntab_inter, uint8_t *outl, int64_t line_base, double outl_thres,
-                uint64_t *outl_stats, double *p, double *expcc, void *workspace, size_t workspace_bytes, void *stream);
+                uint64_t *outl_stats, double *p, double *expcc, const uint32_t *pre_code, const double *pre_b12,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/* The part of fhc_pvalues that does not need the spline table, for every contact: the two bias lookups, their product and
+ * window test, the class of the line (the branch order of fithic/fithic.py:1057-1115) and its distance slot.  Launched right
+ * after fhc_hist_distance it runs while the host bins and fits; fhc_pvalues (work-list pipeline) then takes the two arrays
+ * as pre_code / pre_b12 and reads neither mid points, chromosome ids nor the bias table (mid1 / mid2 / chrs may be NULL
+ * there).  The output depends on the contacts, the bias table, res, L, U, tL, tU and the mode only: later spline passes of
+ * a run reuse it.  code [dev, uint32 n]: 0xffffffff = not scored (p = 1, ExpCC = 0), else bit 31 = both biases inside
+ * [tL, tU], bit 30 = scored against the inter-chromosomal prior, low bits = distance slot; b12 [dev, double n] = rn(bias1 *
+ * bias2).  Arguments as in fhc_pvalues. */
+int fhc_pvalues_prepass(int32_t mode, const int32_t *mid1, const int32_t *mid2, const uint32_t *chrs,
+                        const int64_t *run_start, const uint32_t *run_val, int32_t nruns, int64_t n, const double *bias,
+                        const int32_t *bias_mid, const int64_t *chr_off, int32_t nchr, int32_t bias_sparse, int32_t res,
+                        int64_t L, int64_t U, double tL, double tU, int64_t line_base, uint32_t *code, double *b12,
+                        void *stream);
 
 /* scipy.special.bdtrc(k, n, prior) element-wise on device arrays (the arithmetic core of K3, exposed for parity
  * tests against the oracle; call sites fithic/fithic.py:1070,:1101).  lbeta nullable. */

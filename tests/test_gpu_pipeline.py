@@ -134,3 +134,33 @@ def test_api_reused_host_buffers(lib):
     out.invalidate()  # ... and says so
     got = api.significance(contacts, frags, st, biases, out=out)
     assert np.array_equal(got[-1]["q"], want[-1]["q"], equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", ["intra_bias", "all", "inter_only"])
+def test_prepass_changes_nothing(lib, monkeypatch, mode):
+    """K3 behind a pre-pass (bias products, line classes and distance slots computed while the host fits) and K3 on its own
+    give the same p-values, ExpCC and outlier marks bit for bit; so do chromosome ids as runs and as an array."""
+    monkeypatch.setenv("FHC_PVAL_IMPL", "lists")
+    kw = dict(intra_bias=dict(with_bias=True, inter_fraction=0.0), all=dict(with_bias=True, inter_fraction=0.3),
+              inter_only=dict(with_bias=False, inter_fraction=0.9))[mode]
+    sk = dict(intra_bias=dict(noOfPasses=2, distLowThres=200000, distUpThres=30000000), all=dict(allReg=True),
+              inter_only=dict(interOnly=True))[mode]
+    contacts, frags, biases, _ = synth.make_intra(250_003, 100000, seed=91, mean_count=4.0, **kw)
+    order = np.argsort(contacts.chrs, kind="stable")  # grouped by chromosome pair: a few runs
+    from fithic_b200.engine import Contacts, chr_runs_of
+    contacts = Contacts(contacts.mid1[order], contacts.mid2[order], contacts.cnt[order], contacts.chrs[order], contacts.chroms)
+    contacts.chr_runs = chr_runs_of(contacts.chrs)
+    st = Settings(resolution=100000, noOfBins=100, **sk)
+    got = {}
+    for pre in ("1", "0"):
+        for runs in ("1", "0"):
+            monkeypatch.setenv("FHC_PREPASS", pre)
+            monkeypatch.setenv("FHC_CHR_RUNS", runs)
+            got[pre, runs] = run_engine(contacts, frags, biases, st)
+    ref = got["0", "0"]
+    for key, res in got.items():
+        assert len(res) == len(ref)
+        for a, b in zip(res, ref):
+            for k in ("p", "q", "expcc", "outl"):
+                assert np.array_equal(a[k], b[k], equal_nan=True), (key, k)
+            assert a["N"] == b["N"] and a["T"] == b["T"]

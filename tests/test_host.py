@@ -38,7 +38,7 @@ def test_errors_are_reported_not_swallowed(lib):
         _capi.check(rc)
     # device entry points validate their arguments before touching the GPU
     assert lib.fhc_pvalues(7, None, None, None, None, None, None, 0, 1, None, None, None, 0, 0, 10, 0, -1, None, 0, 1, 1, 0.0, 0.5, 2.0,
-                           None, 0, None, 0, None, 0, 0.0, None, None, None, None, 0, None) == _capi.FHC_E_INVALID
+                           None, 0, None, 0, None, 0, 0.0, None, None, None, None, None, None, 0, None) == _capi.FHC_E_INVALID
     assert lib.fhc_lbeta_table(1 << 31, ctypes.c_void_p(16), 4, None) == _capi.FHC_E_RANGE
 
 
