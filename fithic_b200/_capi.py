@@ -61,6 +61,8 @@ _SIGNATURES = {
     "fhc_comm_connect": (ctypes.c_int, [c_void_p, c_void_p]),
     "fhc_comm_allreduce_u64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "fhc_comm_allgather": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_comm_world": (c_int32, [c_void_p]),
+    "fhc_comm_rank": (c_int32, [c_void_p]),
     "fhc_comm_failed": (ctypes.c_int, [c_void_p]),
     "fhc_comm_destroy": (ctypes.c_int, [c_void_p]),
     "fhc_peak_fp64": (ctypes.c_int, [c_double, c_void_p, c_void_p, c_void_p]),
@@ -107,12 +109,14 @@ _SIGNATURES = {
     "fhc_bh_qvalues": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "fhc_bh_qvalues_hostcount": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
-                                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+                                                 c_void_p, c_void_p, c_size_t, c_int32, c_void_p]),
+    "fhc_fill_f64": (ctypes.c_int, [c_void_p, c_int64, c_double, c_void_p]),
     "fhc_bh_prepare": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "fhc_bh_p_cut": (c_double, [c_double, c_double]),
     "fhc_bh_cut_hist": (ctypes.c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "fhc_bh_cut_from_hists": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_double, c_double, c_void_p, c_void_p]),
+    "fhc_bh_dist_cut": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "fhc_host_bh_cut_find": (c_double, [c_void_p, c_double, c_double, c_double]),
     "fhc_host_bh_cut_bucket": (c_int32, [c_double]),
     "fhc_bh_finish": (ctypes.c_int, [c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -120,7 +124,7 @@ _SIGNATURES = {
     "fhc_bh_key_of": (ctypes.c_uint64, [c_double]),
     "fhc_bh_partition_count": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p]),
     "fhc_bh_partition_scatter": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_double, c_void_p, c_void_p,
-                                                 c_void_p, c_void_p, c_void_p]),
+                                                 c_void_p, c_void_p, c_int32, c_void_p]),
     "fhc_scatter_f64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_gather_ne_one": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_sort_workspace_bytes": (c_size_t, [c_int64]),

@@ -62,7 +62,7 @@ constexpr int kCompactPerThread = 8;
 __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restrict__ p, long long n,
                                                         const double *__restrict__ d_p_cut, double *__restrict__ q,
                                                         u64 *__restrict__ keys, u32 *__restrict__ vals, u64 *nsel,
-                                                        u32 *__restrict__ ghist) {
+                                                        u32 *__restrict__ ghist, int q_prefilled) {
     __shared__ u32 warp_tot[8];
     __shared__ u64 block_base;
     __shared__ u32 dhist[8 * 256];  // digit histograms of the ranked keys for the one-sweep sort (ghist != nullptr)
@@ -101,7 +101,12 @@ __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restric
                 mine += sel ? 1 : 0;
                 cut_total += (rankable && !sel) ? 1u : 0u;
             }
-            if (i0 + 3 < n) {
+            if (q_prefilled) {
+                // the caller filled q with 1.0 while the GPU had nothing else to do: only the NaN lines are left to write
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (i0 + k < n && isnan(v[h * 4 + k])) q[i0 + k] = qv[k];
+            } else if (i0 + 3 < n) {
                 // ranked lines get their q from bh_scatter_kernel later; writing 1.0 first is harmless
                 __stcs(reinterpret_cast<double2 *>(q + i0), make_double2(qv[0], qv[1]));
                 __stcs(reinterpret_cast<double2 *>(q + i0 + 2), make_double2(qv[2], qv[3]));
@@ -253,29 +258,42 @@ __device__ __forceinline__ u64 block_inclusive_scan_u64(u64 v, u64 *wsum /*32*/,
 }
 
 // The cut from `nranks` value histograms laid out back to back (one on a single GPU): the smallest bucket edge from which
-// on every q is 1.0 (cut_bucket_closes on the summed histogram), or p_cut0.  One CTA of 1024 threads; the buckets are
-// walked in 32 rounds of 1024 consecutive buckets (thread = bucket: coalesced loads, the next round's loads in flight while
-// this round is scanned), with the running count carried from round to round.  Returns the closing bucket (kCutBuckets:
-// none) to every thread.
+// on every q is 1.0 (cut_bucket_closes on the summed histogram), or none.  One CTA of 1024 threads with the summed histogram
+// in 128 KB of shared memory: coalesced loads (thread = bucket, 32 x nranks independent loads per thread), then every thread
+// walks its own 32 CONSECUTIVE buckets behind one block-wide scan of the thread totals.  sh[j + j / 32]: the padding keeps the
+// walk free of bank conflicts.  A bucket total that does not fit 32 bits switches the tightening off (always valid).
+// Returns the closing bucket (kCutBuckets: none) to every thread.
+constexpr int kCutPer = kCutBuckets / 1024;                               // 32 buckets per thread
+constexpr size_t kCutFindSmem = (size_t)(kCutBuckets + 1024) * sizeof(u32);
+
 __device__ __forceinline__ int cut_find_block(const u64 *__restrict__ hists, int nranks, double T, double rank_offset,
-                                              u64 *wsum, int *best) {
-    if (threadIdx.x == 0) *best = kCutBuckets;
-    u64 carry = 0;
-    int found = kCutBuckets;
-    u64 cur = 0;
-    for (int r = 0; r < nranks; ++r) cur += hists[(size_t)r * kCutBuckets + threadIdx.x];
-    for (int k = 0; k < kCutBuckets / 1024; ++k) {
-        u64 nxt = 0;
-        if (k + 1 < kCutBuckets / 1024)
-            for (int r = 0; r < nranks; ++r) nxt += hists[(size_t)r * kCutBuckets + (k + 1) * 1024 + threadIdx.x];
-        u64 total;
-        const u64 inc = block_inclusive_scan_u64(cur, wsum, &total);
-        const int j = k * 1024 + threadIdx.x;
-        if (cur && found == kCutBuckets && cut_bucket_closes(j, carry + inc, T, rank_offset)) found = j;
-        carry += total;
-        cur = nxt;
+                                              u32 *sh, u64 *wsum, int *best) {
+    __shared__ int overflow;
+    if (threadIdx.x == 0) {
+        *best = kCutBuckets;
+        overflow = 0;
     }
     __syncthreads();
+    for (int k = 0; k < kCutPer; ++k) {
+        const int j = k * 1024 + threadIdx.x;
+        u64 c = 0;
+        for (int r = 0; r < nranks; ++r) c += hists[(size_t)r * kCutBuckets + j];
+        if (c > 0xffffffffull) overflow = 1;
+        sh[j + (j >> 5)] = (u32)c;
+    }
+    __syncthreads();
+    if (overflow) return kCutBuckets;
+    u64 mine = 0;
+    const int j0 = threadIdx.x * kCutPer;
+    for (int k = 0; k < kCutPer; ++k) mine += sh[j0 + k + threadIdx.x];  // (j0 + k) + (j0 + k) / 32 = j0 + k + threadIdx.x
+    u64 total;
+    u64 pre = block_inclusive_scan_u64(mine, wsum, &total) - mine;
+    int found = kCutBuckets;
+    for (int k = 0; k < kCutPer; ++k) {
+        const u32 c = sh[j0 + k + threadIdx.x];
+        pre += c;
+        if (c && found == kCutBuckets && cut_bucket_closes(j0 + k, pre, T, rank_offset)) found = j0 + k;
+    }
     if (found < kCutBuckets) atomicMin(best, found);
     __syncthreads();
     return *best;
@@ -284,13 +302,14 @@ __device__ __forceinline__ int cut_find_block(const u64 *__restrict__ hists, int
 // single GPU: tighten == 0 just forwards p_cut0
 __global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict__ hist, double T, double rank_offset,
                                                           double p_cut0, int tighten, double *__restrict__ p_cut_out) {
+    extern __shared__ __align__(16) unsigned char cut_find_smem[];
     __shared__ u64 wsum[32];
     __shared__ int best;
     if (!tighten || !(T > 0.0)) {
         if (threadIdx.x == 0) *p_cut_out = p_cut0;
         return;
     }
-    const int b = cut_find_block(hist, 1, T, rank_offset, wsum, &best);
+    const int b = cut_find_block(hist, 1, T, rank_offset, reinterpret_cast<u32 *>(cut_find_smem), wsum, &best);
     if (threadIdx.x == 0) *p_cut_out = b < kCutBuckets ? fmin(p_cut0, cut_edge(b)) : p_cut0;
 }
 
@@ -299,21 +318,24 @@ __global__ void __launch_bounds__(1024) bh_cut_find_kernel(const u64 *__restrict
 // rank, [3] the largest share of one rank, [8 + r] the share of rank r.
 __global__ void __launch_bounds__(1024) bh_cut_from_hists_kernel(const u64 *__restrict__ hists, int nranks, int my_rank,
                                                                 double T, double p_cut0, u64 *__restrict__ info) {
+    extern __shared__ __align__(16) unsigned char cut_find_smem[];
     __shared__ u64 wsum[32];
     __shared__ int best;
     __shared__ u64 share[64];
+    if (threadIdx.x < 64) share[threadIdx.x] = 0;
     int upto = kCutBuckets;
-    if (T > 0.0) upto = cut_find_block(hists, nranks, T, 0.0, wsum, &best);
-    // shares: the buckets below the closing one (all of them when none closes: the histograms only hold p < p_cut0)
+    if (T > 0.0) upto = cut_find_block(hists, nranks, T, 0.0, reinterpret_cast<u32 *>(cut_find_smem), wsum, &best);
+    __syncthreads();
+    // shares: the buckets below the closing one (all of them when none closes: the histograms only hold p < p_cut0);
+    // coalesced loads, one shared-memory atomic per warp and rank
     for (int r = 0; r < nranks; ++r) {
         u64 c = 0;
-        for (int k = 0; k < kCutBuckets / 1024; ++k) {
+        for (int k = 0; k < kCutPer; ++k) {
             const int j = k * 1024 + threadIdx.x;
             if (j < upto) c += hists[(size_t)r * kCutBuckets + j];
         }
-        u64 total;
-        block_inclusive_scan_u64(c, wsum, &total);
-        if (threadIdx.x == 0) share[r] = total;
+        c = warp_sum(c);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&share[r], c);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1070,7 +1092,7 @@ static int cut_hist_launch(const double *p, int64_t n, double p_cut0, fhc::u64 *
 // launch only what that number needs (nothing when no key is ranked: 40 near-empty launches cost 0.35 ms).
 static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double p_cut, bool tighten,
                       double *q, double *carry_out, int64_t *n_sorted_out, const fhc::BhWs &ws, cudaStream_t st,
-                      long long *host_ns = nullptr) {
+                      long long *host_ns = nullptr, int q_prefilled = 0) {
     using namespace fhc;
     FHC_CUDA(cudaMemsetAsync(ws.d_n, 0, 4 * sizeof(u64), st));
     int ntiles = (int)ws.sort.ntiles;
@@ -1084,7 +1106,8 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
             const int rc = cut_hist_launch(p, n, p_cut, ws.cut_hist, st);
             if (rc != FHC_OK) return rc;
         }
-        bh_cut_find_kernel<<<1, 1024, 0, st>>>(ws.cut_hist, T, (double)rank_offset, p_cut, tighten ? 1 : 0, d_p_cut);
+        FHC_CUDA(cudaFuncSetAttribute(bh_cut_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCutFindSmem));
+        bh_cut_find_kernel<<<1, 1024, kCutFindSmem, st>>>(ws.cut_hist, T, (double)rank_offset, p_cut, tighten ? 1 : 0, d_p_cut);
         FHC_LAUNCH_CHECK("bh_cut_find_kernel");
         long long blocks = (n + 256 * kCompactPerThread - 1) / (256 * kCompactPerThread);
         if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
@@ -1092,7 +1115,7 @@ static int bh_prepare(const double *p, int64_t n, double T, int64_t rank_offset,
         u32 *os = ws.sort.onesweep;
         if (onesweep) FHC_CUDA(cudaMemsetAsync(os + kOsHist, 0, 2048 * sizeof(u32), st));
         bh_compact_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, d_p_cut, q, ws.keys_a, ws.vals_a, ws.d_n,
-                                                                onesweep ? os + kOsHist : nullptr);
+                                                                onesweep ? os + kOsHist : nullptr, q_prefilled);
         FHC_LAUNCH_CHECK("bh_compact_kernel");
         if (onesweep) {  // digit offsets of all eight passes, and which passes would move nothing
             radix_digit_scan_kernel<<<1, kRadix, 0, st>>>(os + kOsHist, ws.d_n, os + kOsBase, os + kOsUniform);
@@ -1168,7 +1191,7 @@ extern "C" int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank
 
 extern "C" int fhc_bh_qvalues_hostcount(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
                                         double *carry_out, int64_t *n_sorted_out, int64_t *n_ranked_host, void *workspace,
-                                        size_t workspace_bytes, void *stream) {
+                                        size_t workspace_bytes, int32_t q_prefilled, void *stream) {
     using namespace fhc;
     int rc = bh_check_args("fhc_bh_qvalues_hostcount", p, n, q, workspace, workspace_bytes);
     if (rc != FHC_OK) return rc;
@@ -1178,7 +1201,7 @@ extern "C" int fhc_bh_qvalues_hostcount(const double *p, int64_t n, double T, in
     bh_ws_layout(n, reinterpret_cast<char *>(workspace), &ws);
     long long ns = -1;
     rc = bh_prepare(p, n, T, rank_offset, carry_in, bh_p_cut(T, (double)rank_offset + (double)n), true, q, carry_out,
-                    n_sorted_out, ws, st, &ns);
+                    n_sorted_out, ws, st, &ns, q_prefilled ? 1 : 0);
     if (rc != FHC_OK) return rc;
     if (n_ranked_host) *n_ranked_host = ns < 0 ? 0 : ns;
     return bh_finish(n, T, rank_offset, 0.0, q, ws, st, ns);
@@ -1285,7 +1308,7 @@ __global__ void __launch_bounds__(256) bh_part_count_kernel(const double *__rest
 // then write.
 __global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__restrict__ p, long long n, const Splitters sp,
                                                              double p_cut, u64 *cursors, double *__restrict__ send,
-                                                             u32 *__restrict__ idx, double *__restrict__ q) {
+                                                             u32 *__restrict__ idx, double *__restrict__ q, int q_prefilled) {
     __shared__ u32 cnt[kMaxParts];
     __shared__ u64 base[kMaxParts];
     const int lane = threadIdx.x & 31;
@@ -1316,7 +1339,11 @@ __global__ void __launch_bounds__(256) bh_part_scatter_kernel(const double *__re
             first = __shfl_sync(0xffffffffu, first, leader);
             slot[k] = first + __popc(m & ((1u << lane) - 1u));
         }
-        if (i0 + 3 < n) {
+        if (q_prefilled) {  // q holds 1.0 already: only the NaN lines are written
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < n && isnan(v[k])) q[i0 + k] = qv[k];
+        } else if (i0 + 3 < n) {
             // ranked lines get their q back from the owning GPU later; writing 1.0 first is harmless
             __stcs(reinterpret_cast<double2 *>(q + i0), make_double2(qv[0], qv[1]));
             __stcs(reinterpret_cast<double2 *>(q + i0 + 2), make_double2(qv[2], qv[3]));
@@ -1394,9 +1421,38 @@ extern "C" int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int3
                 "fhc_bh_cut_from_hists: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
-    bh_cut_from_hists_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const u64 *>(hists), nranks, my_rank, T, p_cut0,
+    FHC_CUDA(cudaFuncSetAttribute(bh_cut_from_hists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCutFindSmem));
+    bh_cut_from_hists_kernel<<<1, 1024, kCutFindSmem, st>>>(reinterpret_cast<const u64 *>(hists), nranks, my_rank, T, p_cut0,
                                                  reinterpret_cast<u64 *>(info));
     FHC_LAUNCH_CHECK("bh_cut_from_hists_kernel");
+    return FHC_OK;
+}
+
+// The first half of the multi-GPU correction in one call: value histogram of this rank's p-values below p_cut0, all-gather
+// over the library's own collectives, global cut + every rank's share, read back.  work [dev]: (1 + world) histograms +
+// (8 + world) words; info_host [pinned host]: 8 + world words, valid on return (the call synchronises the stream once).
+extern "C" int fhc_bh_dist_cut(fhc_comm *comm, const double *p, int64_t n, double T, double p_cut0, uint64_t *work,
+                               uint64_t *info_host, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(comm && work && info_host && n >= 0 && (n == 0 || p != nullptr), FHC_E_INVALID, "fhc_bh_dist_cut: bad arguments");
+    const int world = fhc_comm_world(comm), rank = fhc_comm_rank(comm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    u64 *local = reinterpret_cast<u64 *>(work);
+    u64 *gathered = local + kCutBuckets;
+    u64 *info = gathered + (size_t)world * kCutBuckets;
+    FHC_CUDA(cudaMemsetAsync(local, 0, (size_t)kCutBuckets * sizeof(u64), st));
+    if (n > 0) {
+        const int rc = cut_hist_launch(p, n, p_cut0, local, st);
+        if (rc != FHC_OK) return rc;
+    }
+    int rc = fhc_comm_allgather(comm, local, gathered, (int64_t)kCutBuckets * (int64_t)sizeof(u64), stream);
+    if (rc != FHC_OK) return rc;
+    rc = fhc_bh_cut_from_hists(reinterpret_cast<const uint64_t *>(gathered), world, rank, T, p_cut0,
+                               reinterpret_cast<uint64_t *>(info), stream);
+    if (rc != FHC_OK) return rc;
+    FHC_CUDA(cudaMemcpyAsync(info_host, info, (size_t)(8 + world) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    FHC_CUDA(cudaStreamSynchronize(st));
     return FHC_OK;
 }
 
@@ -1443,7 +1499,7 @@ extern "C" int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t
 
 extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts,
                                         double p_cut, uint64_t *cursors, double *send, uint32_t *idx, double *q,
-                                        void *stream) {
+                                        int32_t q_prefilled, void *stream) {
     using namespace fhc;
     Splitters sp;
     const int rc = make_splitters(splitter_keys, nparts, &sp);
@@ -1456,7 +1512,7 @@ extern "C" int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64
     long long blocks = (n + 1023) / 1024;
     if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
     bh_part_scatter_kernel<<<(unsigned int)blocks, 256, 0, st>>>(p, n, sp, p_cut, reinterpret_cast<u64 *>(cursors), send,
-                                                                 idx, q);
+                                                                 idx, q, q_prefilled ? 1 : 0);
     FHC_LAUNCH_CHECK("bh_part_scatter_kernel");
     return FHC_OK;
 }
@@ -1551,5 +1607,31 @@ extern "C" int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n
     FHC_PROFILE_ENTRY(st);
     scatter_f64_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(src, idx, n, dst);
     FHC_LAUNCH_CHECK("scatter_f64_kernel");
+    return FHC_OK;
+}
+
+// dst[i] = v: the engine fills q with 1.0 while the host bins and fits (the GPU has nothing else to do then), after which
+// the kernels of K4 only write the lines whose q is not 1.0 (q_prefilled)
+namespace fhc {
+__global__ void __launch_bounds__(256) fill_f64_kernel(double *__restrict__ dst, long long n, double v) {
+    const long long n2 = n >> 1;
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n2; i += (long long)gridDim.x * 256)
+        __stcs(d2 + i, make_double2(v, v));
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = v;
+}
+}  // namespace fhc
+
+extern "C" int fhc_fill_f64(double *dst, int64_t n, double v, void *stream) {
+    using namespace fhc;
+    FHC_REQUIRE(n >= 0 && (n == 0 || (dst != nullptr && aligned16(dst))), FHC_E_INVALID, "fhc_fill_f64: null or misaligned array");
+    if (n == 0) return FHC_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FHC_PROFILE_ENTRY(st);
+    long long blocks = ((n >> 1) + 255) / 256;
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    fill_f64_kernel<<<(unsigned int)blocks, 256, 0, st>>>(dst, n, v);
+    FHC_LAUNCH_CHECK("fill_f64_kernel");
     return FHC_OK;
 }

@@ -230,6 +230,9 @@ extern "C" int fhc_comm_allgather(fhc_comm *comm, const void *src, void *dst, in
     return FHC_OK;
 }
 
+extern "C" int32_t fhc_comm_world(fhc_comm *comm) { return comm ? comm->c.world : 0; }
+extern "C" int32_t fhc_comm_rank(fhc_comm *comm) { return comm ? comm->c.rank : -1; }
+
 // 1 when a wait inside a collective gave up (a peer never arrived): results since then are not to be trusted
 extern "C" int fhc_comm_failed(fhc_comm *comm) {
     using namespace fhc;

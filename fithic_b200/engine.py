@@ -393,6 +393,7 @@ class Engine:
     # the native host stage covers fixed-size bins with a distance axis of at most this many slots (-r 0 on its 1 bp grid
     # and anything larger keep the staged path: evaluation and lookup table on the device)
     NATIVE_STAGE_MAX_SLOTS = 1 << 20
+    PREPASS_AUTO_MAX = 120_000_000  # FHC_PREPASS=auto: contacts per GPU up to which the pre-pass hides behind the host stage
 
     def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
@@ -436,10 +437,12 @@ class Engine:
         if after_pvalues is not None:
             after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
         # ---- K4 ----
+        pre_q = getattr(self, "_q_prefilled", False)  # _tables_native filled q with 1.0 while the host was fitting
+        self._q_prefilled = False
         if self.dist is not None:
-            q = self.dist.global_bh(self, p, float(T))
+            q = self.dist.global_bh(self, p, float(T), q_prefilled=pre_q)
         else:
-            q = self.bh_qvalues(p, float(T))
+            q = self.bh_qvalues(p, float(T), q_prefilled=pre_q)
         out.update(p=p, q=q, expcc=e)
         late = getattr(out, "_late", None)
         if late:  # the per-distance arrays of the native host stage leave its buffers now, while the GPU works
@@ -528,7 +531,12 @@ class Engine:
             check(lib.fhc_event_create(ctypes.byref(ev)))
             hs.event = ev
         check(lib.fhc_event_record(hs.event, stream))
-        # behind the copy, while the host bins and fits: the part of K3 that does not need the spline table
+        # behind the copy, while the host bins and fits: q = 1.0 everywhere (K4 then only writes the lines that differ), and
+        # the part of K3 that does not need the spline table
+        self._q_prefilled = False
+        if os.environ.get("FHC_Q_PREFILL", "1") != "0" and self.n > 0:
+            check(lib.fhc_fill_f64(dptr(self._tensor("q", self.n, torch.float64)), self.n, 1.0, stream))
+            self._q_prefilled = True
         self.prepass(passNo)
         lib.fhc_host_pool_prewarm(hs.nthreads)
         hs.new_outputs()
@@ -716,8 +724,14 @@ class Engine:
         per contact.  Computed in the first pass of a run -- launched right behind K1, so it runs while the host bins and
         fits -- and reused by the later passes (it depends on nothing a pass changes)."""
         self._pre_live = False
-        if os.environ.get("FHC_PREPASS", "1") == "0" or os.environ.get("FHC_PVAL_IMPL", "lists")[:1] == "t" \
-                or self.distance_slots() >= (1 << 30) or self.n == 0:
+        mode = os.environ.get("FHC_PREPASS", "auto")
+        if mode == "0" or os.environ.get("FHC_PVAL_IMPL", "lists")[:1] == "t" or self.distance_slots() >= (1 << 30) \
+                or self.n == 0:
+            return
+        # The pre-pass costs more instructions than it takes out of the front kernel (it re-reads the mid points and stores
+        # 12 B per contact): it pays where it hides behind the host stage (about 0.6 ms: shards up to ~100 M contacts, i.e.
+        # every multi-GPU run of a whole genome) and in runs with several spline passes, which reuse it.
+        if mode == "auto" and self.n > self.PREPASS_AUTO_MAX and self.st.noOfPasses < 2:
             return
         code = self._tensor("pre_code", self.n, torch.int32)
         b12 = self._tensor("pre_b12", self.n, torch.float64)
@@ -796,7 +810,7 @@ class Engine:
         return p, e
 
     # K4  (myStats.benjamini_hochberg_correction, fithic/myStats.py:24-48)
-    def bh_qvalues(self, p, T, rank_offset=0, carry_in=0.0, carry_out=None, n_sorted_out=None, q=None):
+    def bh_qvalues(self, p, T, rank_offset=0, carry_in=0.0, carry_out=None, n_sorted_out=None, q=None, q_prefilled=False):
         n = p.numel()
         if q is None:
             q = self._tensor("q", n, torch.float64)
@@ -806,7 +820,7 @@ class Engine:
         ranked = ctypes.c_int64(0)
         check(self.lib.fhc_bh_qvalues_hostcount(dptr(p), n, float(T), int(rank_offset), float(carry_in), dptr(q),
                                                 dptr(carry_out), dptr(n_sorted_out), ctypes.byref(ranked), dptr(ws), wsb,
-                                                self._stream()))
+                                                1 if q_prefilled else 0, self._stream()))
         self.last_ranked = int(ranked.value)
         return q
 

@@ -66,6 +66,7 @@ class CudaOps:
         self.lib = _capi.load()
         self.device = device
         self._ws = None
+        self._cursor1 = None
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -115,16 +116,23 @@ class CudaOps:
                                               self._stream()))
         return counts
 
-    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None, q_prefilled=False):
         nparts = len(splitters) + 1
         n = p.numel()
-        cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
+        if nparts == 1 and int(send_offsets[0]) == 0:  # one part from slot 0: no host->device copy
+            if self._cursor1 is None:
+                self._cursor1 = torch.zeros(1, dtype=torch.int64, device=self.device)
+            else:
+                self._cursor1.zero_()
+            cursors = self._cursor1
+        else:
+            cursors = torch.from_numpy(np.ascontiguousarray(send_offsets, dtype=np.int64)).to(self.device)
         cap = n if capacity is None else int(capacity)  # the caller knows how many p-values lie below the cut
         send = torch.empty(max(cap, 1), dtype=torch.float64, device=self.device)  # (never empty: a null pointer is refused)
         idx = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
         sp = np.ascontiguousarray(splitters, dtype=np.uint64)
         check(self.lib.fhc_bh_partition_scatter(dptr(p), n, dptr(sp), nparts, float(p_cut), dptr(cursors), dptr(send),
-                                                dptr(idx), dptr(q), self._stream()))
+                                                dptr(idx), dptr(q), 1 if q_prefilled else 0, self._stream()))
         self.last_cursors = cursors  # after the call: one past the last slot used by each part
         return send, idx
 
@@ -179,6 +187,7 @@ class DistCtx:
         # shared by CUDA IPC, two kernels per collective) when every rank can set them up; FHC_COMM=nccl keeps NCCL.
         self.comm = None
         self.comm_slot_bytes = 0
+        self._cut_work = self._cut_info = None
         if isinstance(self.ops, CudaOps) and self.world > 1 and os.environ.get("FHC_COMM", "p2p") != "nccl":
             self._init_p2p()
         env = os.environ.get("FHC_BH_SMALL_SET")  # e.g. 0: always take the range-partitioned route (tests, timing)
@@ -264,8 +273,9 @@ class DistCtx:
             self._n_global = (n, int(t.item()))
         return self._n_global[1]
 
-    def global_bh(self, engine, p, T, q=None):
-        """q-values of the union of every rank's p-values (myStats.benjamini_hochberg_correction over the whole file)."""
+    def global_bh(self, engine, p, T, q=None, q_prefilled=False):
+        """q-values of the union of every rank's p-values (myStats.benjamini_hochberg_correction over the whole file).
+        q_prefilled: q holds 1.0 everywhere already, so only the other values are written."""
         ops, G, r = self.ops, self.world, self.rank
         n = p.numel()
         if q is None:
@@ -274,8 +284,16 @@ class DistCtx:
         p_cut0 = ops.p_cut(T, self.n_global(n))
         #    ... and the value histograms of what is left say where q reaches 1.0 for good (bh.cu: cut_bucket_closes): one
         #    all-gather of the histograms, one kernel, one read-back of a few numbers
-        hist = ops.cut_hist(p, p_cut0)
-        info = ops.cut_from_hists(self._all_gather(hist), G, r, T, p_cut0).cpu().numpy()
+        if self.comm is not None:  # histogram, all-gather, cut kernel and read-back in one library call
+            if self._cut_work is None:
+                self._cut_work = torch.empty((1 + G) * _capi.BH_CUT_BUCKETS + 8 + G, dtype=torch.int64, device=self.device)
+                self._cut_info = torch.empty(8 + G, dtype=torch.int64).pin_memory()
+            check(ops.lib.fhc_bh_dist_cut(self.comm, dptr(p), n, float(T), float(p_cut0), dptr(self._cut_work),
+                                          dptr(self._cut_info), ops._stream()))
+            info = self._cut_info.numpy().copy()
+        else:
+            hist = ops.cut_hist(p, p_cut0)
+            info = ops.cut_from_hists(self._all_gather(hist), G, r, T, p_cut0).cpu().numpy()
         p_cut = float(info[:1].view(np.float64)[0])
         n_below, mine, mx = int(info[1]), int(info[2]), int(info[3])
         counts = info[8:8 + G].astype(np.int64)
@@ -284,7 +302,7 @@ class DistCtx:
         #     and keeps the q-values of its own lines.  Nothing below the cut: one kernel writes q = 1 / NaN and that is it.
         if n_below <= self.SMALL_SET:
             send, idx = ops.partition_scatter(p, np.zeros(0, dtype=np.uint64), np.zeros(1, dtype=np.int64), q, p_cut,
-                                              capacity=mine)
+                                              capacity=mine, q_prefilled=q_prefilled)
             if n_below:
                 pad = ops.empty(mx, torch.float64)
                 pad[:mine] = send[:mine]
@@ -308,7 +326,7 @@ class DistCtx:
         cm = self._all_gather(counts).cpu().numpy().reshape(G, G)
         send_splits, recv_splits, rank_offset, send_off = exchange_plan(cm, r)
         # 3. group by destination, exchange
-        send, idx = ops.partition_scatter(p, splitters, send_off, q, p_cut, capacity=mine)
+        send, idx = ops.partition_scatter(p, splitters, send_off, q, p_cut, capacity=mine, q_prefilled=q_prefilled)
         n_send, n_recv = int(sum(send_splits)), int(sum(recv_splits))
         recv = ops.empty(n_recv, torch.float64)
         dist.all_to_all_single(recv, send[:n_send], recv_splits, send_splits, group=self.group)

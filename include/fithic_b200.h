@@ -100,6 +100,8 @@ int fhc_comm_create(int32_t rank, int32_t world, int64_t slot_bytes, fhc_comm **
 int fhc_comm_connect(fhc_comm *comm, const void *all_handles);
 int fhc_comm_allreduce_u64(fhc_comm *comm, uint64_t *data, int64_t n, void *stream);
 int fhc_comm_allgather(fhc_comm *comm, const void *src, void *dst, int64_t bytes, void *stream);
+int32_t fhc_comm_world(fhc_comm *comm);
+int32_t fhc_comm_rank(fhc_comm *comm);
 int fhc_comm_failed(fhc_comm *comm);
 int fhc_comm_destroy(fhc_comm *comm);
 
@@ -327,7 +329,10 @@ int fhc_bh_qvalues(const double *p, int64_t n, double T, int64_t rank_offset, do
  * 0.35 ms.  Same results; for callers that are not capturing a CUDA graph. */
 int fhc_bh_qvalues_hostcount(const double *p, int64_t n, double T, int64_t rank_offset, double carry_in, double *q,
                              double *carry_out, int64_t *n_sorted_out, int64_t *n_ranked_host, void *workspace,
-                             size_t workspace_bytes, void *stream);
+                             size_t workspace_bytes, int32_t q_prefilled, void *stream);
+/* q_prefilled (here and in fhc_bh_partition_scatter): the caller has set every q[i] to 1.0 already (fhc_fill_f64, e.g. while
+ * the GPU waited for the host's spline fit), so only the lines whose q is not 1.0 are written: 8 B per line less. */
+int fhc_fill_f64(double *dst, int64_t n, double v, void *stream);
 
 /* The same in two halves, for a caller that has to fetch the running max of smaller keys from other GPUs in between:
  * prepare = compaction + sort + per-tile maxima (local_max_out [dev] = max bh value of this call, 0 if none);
@@ -370,12 +375,17 @@ int32_t fhc_host_bh_cut_bucket(double p);
  * [8 + r] the share of rank r -- what a rank needs to size the exchange of its survivors, in ONE small read-back. */
 int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int32_t my_rank, double T, double p_cut0, uint64_t *info,
                           void *stream);
+/* fhc_bh_cut_hist + all-gather over `comm` + fhc_bh_cut_from_hists + read-back in one call: info_host [pinned host, 8 +
+ * world words] is valid on return (one stream synchronisation).  work [dev]: (1 + world) * FHC_BH_CUT_BUCKETS + 8 + world
+ * words of scratch. */
+int fhc_bh_dist_cut(fhc_comm *comm, const double *p, int64_t n, double T, double p_cut0, uint64_t *work, uint64_t *info_host,
+                    void *stream);
 int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out, void *stream);
 uint64_t fhc_bh_key_of(double p);
 int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
                            uint64_t *counts, void *stream);
 int fhc_bh_partition_scatter(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
-                             uint64_t *cursors, double *send, uint32_t *idx, double *q, void *stream);
+                             uint64_t *cursors, double *send, uint32_t *idx, double *q, int32_t q_prefilled, void *stream);
 int fhc_scatter_f64(const double *src, const uint32_t *idx, int64_t n, double *dst, void *stream);
 
 /* The q-values that are not exactly 1.0 (ranked lines and NaN) as (line, value) pairs, in no particular order:

@@ -529,7 +529,7 @@ def test_partition_kernels(lib, n, nparts):
     idx = torch.zeros(max(n, 1), dtype=torch.int32, device=DEV)
     q = torch.full((max(n, 1),), -7.0, dtype=torch.float64, device=DEV)
     check(lib.fhc_bh_partition_scatter(dptr(pd_), n, dptr(keys), nparts, p_cut, dptr(cursors), dptr(send), dptr(idx),
-                                       dptr(q), stream()))
+                                       dptr(q), 0, stream()))
     torch.cuda.synchronize()
     sh, ih, qh = send.cpu().numpy(), idx.cpu().numpy().view(np.uint32), q.cpu().numpy()[:n]
     tot = int(want.sum())

@@ -155,6 +155,7 @@ def test_prepass_changes_nothing(lib, monkeypatch, mode):
     for pre in ("1", "0"):
         for runs in ("1", "0"):
             monkeypatch.setenv("FHC_PREPASS", pre)
+            monkeypatch.setenv("FHC_Q_PREFILL", pre)  # (q = 1.0 written ahead of K4 or by K4 itself)
             monkeypatch.setenv("FHC_CHR_RUNS", runs)
             got[pre, runs] = run_engine(contacts, frags, biases, st)
     ref = got["0", "0"]

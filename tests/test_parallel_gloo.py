@@ -80,7 +80,7 @@ class NumpyOps:
             ok = ~((p == 1.0) | np.isnan(p) | (p >= p_cut))
         return torch.from_numpy(np.bincount(self._part(p[ok], splitters), minlength=len(splitters) + 1).astype(np.int64))
 
-    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None):
+    def partition_scatter(self, p, splitters, send_offsets, q, p_cut, capacity=None, q_prefilled=False):
         p = p.numpy()
         qn = q.numpy()
         with np.errstate(invalid="ignore"):
