@@ -33,7 +33,8 @@ class StageIO(ctypes.Structure):
         ("t", c_void_p), ("c", c_void_p), ("splineX", c_void_p), ("table", c_void_p), ("lut", c_void_p), ("m", c_int64),
         ("totals", c_int64 * 4), ("lbeta_ntab", c_int64 * 2),
         ("nb", c_int32), ("nt", c_int32), ("ier", c_int32), ("calls", c_int32), ("status", c_int32), ("bad_index", c_int32),
-        ("fp", c_double), ("timings", c_double * 8),
+        ("fp", c_double), ("timings", c_double * 8), ("pairs_rank", c_int32), ("pairs_world", c_int32),
+        ("shm", c_void_p),
     ]
 
 
@@ -78,6 +79,9 @@ _SIGNATURES = {
     "fhc_host_fill_f64": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int32]),
     "fhc_host_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_int32]),
     "fhc_host_stage": (ctypes.c_int, [ctypes.POINTER(StageIO), c_int32]),
+    "fhc_shm_open": (ctypes.c_int, [c_char_p, c_int32, c_int32, c_int64, c_void_p]),
+    "fhc_shm_allreduce_u64": (ctypes.c_int, [c_void_p, c_void_p, c_int32]),
+    "fhc_shm_close": (ctypes.c_int, [c_void_p]),
     "fhc_host_pool_prewarm": (ctypes.c_int, [c_int32]),
     "fhc_host_pool_selftest": (c_double, [c_int32, c_int32, c_int32, c_void_p]),
     "fhc_host_curfit": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "fitpack_host.cuh"
 #include "hostpool.cuh"
+#include "shmcomm.cuh"
 
 namespace fhc {
 
@@ -303,10 +304,29 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
             jobs[(size_t)b] = {b, kb0, kb1, work};
         }
         std::sort(jobs.begin(), jobs.end(), [](const BinJob &a, const BinJob &b2) { return a.work > b2.work; });
+        // Several GPUs: every rank would repeat the same sums, so each takes a share of the bins instead (heaviest first
+        // onto the least loaded rank: the same assignment on every rank) and leaves 0.0 in the others; the caller adds the
+        // arrays of all ranks up (x + 0.0 = x: the sums stay the bits one rank computed, in the reference's order).
+        if (io->pairs_world > 1) {
+            std::vector<int64_t> load((size_t)io->pairs_world, 0);
+            std::vector<BinJob> mine;
+            for (const BinJob &jb : jobs) {
+                int r = 0;
+                for (int q = 1; q < io->pairs_world; ++q)
+                    if (load[(size_t)q] < load[(size_t)r]) r = q;
+                load[(size_t)r] += jb.work;
+                if (r == io->pairs_rank)
+                    mine.push_back(jb);
+                else
+                    io->bin_sumdist[jb.b] = 0.0;
+            }
+            jobs.swap(mine);
+        }
+        const int nb_jobs = (int)jobs.size();
         // the double sums: a bin is one chain of dependent additions (the order is the reference's); eight bins of similar
         // length are summed side by side so that the adder pipelines stay full
         constexpr int kChains = 8;  // two FP adders x four cycles of latency
-        const int ngroups = (nb + kChains - 1) / kChains;
+        const int ngroups = (nb_jobs + kChains - 1) / kChains;
         // lbeta tables
         int64_t lb_N[2] = {0, 0}, lb_n[2] = {0, 0};
         int64_t max_count = (int64_t)scal[FHC_S_MAX_COUNT];
@@ -338,7 +358,7 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         auto run_job = [&](int j) {
             if (j < ngroups) {
                 const int g0 = j * kChains;
-                const int ng = nb - g0 < kChains ? nb - g0 : kChains;
+                const int ng = nb_jobs - g0 < kChains ? nb_jobs - g0 : kChains;
                 constexpr int kBlk = 256;
                 double buf[kChains][kBlk];
                 int len[kChains], pos[kChains];
@@ -426,7 +446,19 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
                 tab[c] = (c >= 1 && c <= Nw) ? libm2::lbeta_cephes((double)c, (double)(Nw - c + 1)) : NAN;
         };
         pool.parallel_for(ngroups + lbjobs0 + lbjobs1, nworkers, run_job);
+        if (io->pairs_world > 1 && io->shm != nullptr) {
+            // every entry of bin_sumdist is one rank's sum and zeros elsewhere: adding the bit patterns up is exact
+            fhc::ShmComm *sc = reinterpret_cast<fhc::ShmComm *>(io->shm);
+            static_assert(sizeof(double) == sizeof(unsigned long long), "bit patterns of doubles are added as integers");
+            const int rc = fhc::shm_allreduce_u64(*sc, reinterpret_cast<unsigned long long *>(io->bin_sumdist), nb, 20.0);
+            FHC_REQUIRE(rc == 0, FHC_E_INVALID, "fhc_host_stage: the exchange of the possible-pair sums between the ranks failed (%d)", rc);
+        }
+        io->timings[1] = wall_ms() - t0;
+    }
+    if (((phases & 2) && (io->pairs_world <= 1 || io->shm != nullptr)) || (phases & 16)) {
         // calculateProbabilities (:869-908): y = avgCC = (sumCC / pairs) / N, x = avgDist = 1e6 * (sumDist / pairs)
+        const int nb = io->nb;
+        const int64_t N = (int64_t)(io->k1buf + D)[FHC_S_INTRA_INRANGE_SUM];
         for (int b = 0; b < nb; ++b) {
             const int64_t pairs = io->bin_pairs[b];
             double y = 0.0, x = 0.0;
@@ -435,7 +467,6 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
             io->x_bins[b] = x;
             io->y_bins[b] = y;
         }
-        io->timings[1] = wall_ms() - t0;
     }
 
     // ---- phase 4: spline fit, table at the observed distances, antitonic regression, lookup table ----
@@ -578,4 +609,35 @@ extern "C" double fhc_host_pool_selftest(int32_t nthreads, int32_t njobs, int32_
     const double dt = wall_ms() - t0;
     if (distinct_threads) *distinct_threads = (int32_t)ids.size();
     return dt;
+}
+
+// Shared-memory exchange between the ranks of one node for the host stage (see shmcomm.cuh): rank 0 creates `name`, the
+// others open it; fhc_stage_io.shm takes the handle.
+extern "C" int fhc_shm_open(const char *name, int32_t rank, int32_t world, int64_t slot_bytes, void **handle_out) {
+    FHC_REQUIRE(name && handle_out, FHC_E_INVALID, "fhc_shm_open: null pointer");
+    fhc::ShmComm *c = new fhc::ShmComm();
+    const int rc = fhc::shm_open_comm(*c, name, rank, world, slot_bytes, 60.0);
+    if (rc != 0) {
+        delete c;
+        fhc::set_error("fhc_shm_open: cannot set up %s for rank %d of %d (%d)", name, rank, world, rc);
+        return FHC_E_INVALID;
+    }
+    *handle_out = c;
+    return FHC_OK;
+}
+
+extern "C" int fhc_shm_allreduce_u64(void *handle, uint64_t *data, int32_t n) {
+    FHC_REQUIRE(handle && data && n > 0, FHC_E_INVALID, "fhc_shm_allreduce_u64: bad arguments");
+    const int rc = fhc::shm_allreduce_u64(*reinterpret_cast<fhc::ShmComm *>(handle), reinterpret_cast<unsigned long long *>(data), n, 20.0);
+    FHC_REQUIRE(rc == 0, FHC_E_INVALID, "fhc_shm_allreduce_u64: a rank did not arrive (%d)", rc);
+    return FHC_OK;
+}
+
+extern "C" int fhc_shm_close(void *handle) {
+    if (handle != nullptr) {
+        fhc::ShmComm *c = reinterpret_cast<fhc::ShmComm *>(handle);
+        fhc::shm_close_comm(*c);
+        delete c;
+    }
+    return FHC_OK;
 }

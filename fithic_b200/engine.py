@@ -524,6 +524,11 @@ class Engine:
         k1buf = self._ws["k1buf"]
         slots = self._rank_slots()
         io.n_rank_slots = slots
+        shm = getattr(self.dist, "shm", None) if self.dist is not None else None
+        if shm is not None:  # the ranks of the node share the possible-pair sums (fhc_host_stage phase 2)
+            io.pairs_rank, io.pairs_world, io.shm = self.dist.rank, self.dist.world, shm
+        else:
+            io.pairs_rank, io.pairs_world, io.shm = 0, 1, None
         nk = D + _capi.N_SCALARS + slots
         check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
         if hs.event is None:
@@ -836,8 +841,10 @@ class Engine:
 
     def new_outlier_state(self):
         outl = torch.zeros(max(self.n, 1), dtype=torch.uint8, device=self.device)[:self.n]
-        stats = torch.tensor([0, -1], dtype=torch.int64, device=self.device)  # {flagged, first duplicate = UINT64_MAX}
-        return outl, stats
+        # {flagged, first duplicate = UINT64_MAX}; from a device-resident template: no host->device copy per run
+        if getattr(self, "_stats0", None) is None:
+            self._stats0 = torch.tensor([0, -1], dtype=torch.int64, device=self.device)
+        return outl, self._stats0.clone()
 
     # ------------------------------------------------------------------------------------------------------------
     def run(self):

@@ -190,6 +190,10 @@ class DistCtx:
         self._cut_work = self._cut_info = None
         if isinstance(self.ops, CudaOps) and self.world > 1 and os.environ.get("FHC_COMM", "p2p") != "nccl":
             self._init_p2p()
+        # host-side exchange (POSIX shared memory) for the sums the host stage shares among the ranks of a node
+        self.shm = None
+        if self.world > 1 and os.environ.get("FHC_PAIRS_SPLIT", "1") != "0":
+            self._init_shm()
         env = os.environ.get("FHC_BH_SMALL_SET")  # e.g. 0: always take the range-partitioned route (tests, timing)
         if env is not None:
             self.SMALL_SET = int(env)
@@ -213,10 +217,33 @@ class DistCtx:
             lib.fhc_comm_destroy(comm)
         dist.barrier(group=self.group)
 
+    def _init_shm(self, slot_bytes=1 << 16):
+        """Rank 0 names and creates the shared-memory object, the others open it (one node: torchrun --nnodes=1)."""
+        import time
+        lib = _capi.load()
+        dev = self.device if self.device is not None else "cpu"
+        name = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            raw = ("/fhc_b200_%d_%d" % (os.getpid(), time.time_ns() % 10 ** 12)).encode()
+            name[:len(raw)] = torch.tensor(list(raw), dtype=torch.uint8)
+        dist.broadcast(name, src=0, group=self.group)
+        raw = bytes(name.cpu().tolist()).rstrip(b"\0")
+        handle = ctypes.c_void_p()
+        ok = 1 if lib.fhc_shm_open(raw, self.rank, self.world, slot_bytes, ctypes.byref(handle)) == 0 else 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # all ranks or none
+        if int(flag.item()) == 1:
+            self.shm = handle
+        elif ok:
+            lib.fhc_shm_close(handle)
+
     def close(self):
         if self.comm is not None:
             self.ops.lib.fhc_comm_destroy(self.comm)
             self.comm = None
+        if getattr(self, "shm", None) is not None:
+            _capi.load().fhc_shm_close(self.shm)
+            self.shm = None
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
     def allreduce_k1(self, fused):

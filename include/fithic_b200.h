@@ -167,6 +167,9 @@ int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int
  *   4  fit_Spline's fit stage when want_spline != 0: (xs, ys) sorted by x, fhc_host_curfit (t, c: capacity noOfBins + 4),
  *      splineX / table (capacity D), lut (capacity D): what fhc_spline_table produces on the device
  *   8  the lbeta tables alone (status 3 of an earlier call: lbeta_cap was below lbeta_ntab)
+ *  16  calculateProbabilities alone.  With pairs_world > 1 phase 2 only sums the bins that rank pairs_rank owns (0.0 in
+ *      bin_sumdist elsewhere) and stops before the probabilities: the caller adds bin_sumdist over the ranks (every entry is
+ *      one rank's sum plus zeros, i.e. unchanged bits) and calls phase 16 (| 4)
  * status: 0 fine; 1 x of the bins not strictly increasing at bad_index (the reference prints an error and exits 2,
  * fithic/fithic.py:940-945); 2 no observed distance inside [min x, max x]; 3 an lbeta table is too small; 4 fewer than 4
  * bins (scipy refuses the fit).  timings [ms]: bins, pairs + lbeta, fit, evaluation, antitonic, lut, -, total.
@@ -194,8 +197,15 @@ typedef struct fhc_stage_io {
     int32_t nb, nt, ier, calls, status, bad_index;
     double fp;
     double timings[8];
+    int32_t pairs_rank, pairs_world; /* in: > 1 ranks share the possible-pair sums of phase 2 (see phases) */
+    void *shm;                       /* in, nullable: fhc_shm_open handle -- phase 2 then adds the sums of all ranks itself */
 } fhc_stage_io;
 int fhc_host_stage(fhc_stage_io *io, int32_t phases);
+/* A small all-reduce between the ranks of one node through POSIX shared memory, for data that lives on the HOST (the
+ * possible-pair sums of the host stage): rank 0 creates `name`, the others open it.  slot_bytes: largest payload. */
+int fhc_shm_open(const char *name, int32_t rank, int32_t world, int64_t slot_bytes, void **handle_out);
+int fhc_shm_allreduce_u64(void *handle, uint64_t *data, int32_t n);
+int fhc_shm_close(void *handle);
 int fhc_host_pool_prewarm(int32_t nthreads);
 /* diagnostic: njobs jobs spinning job_us microseconds each on nthreads threads -> elapsed ms */
 double fhc_host_pool_selftest(int32_t nthreads, int32_t njobs, int32_t job_us, int32_t *distinct_threads);

@@ -187,10 +187,36 @@ def _worker(rank, world, port, tmp):
         assert int(scal[_capi.S_INTRA_INRANGE_SUM]) == 201 and int(scal[_capi.S_NONPOS_LINES]) == 5
         assert scal[_capi.N_SCALARS:].tolist() == [7, 19] and int(scal[_capi.S_MAX_COUNT]) == 0
         assert ctx.n_global(10 + rank) == 21 and ctx.n_global(10 + rank) == 21
+        # the host stage shares its possible-pair sums through shared memory: same bits as one rank on its own
+        import ctypes
+        from fithic_b200 import synth
+        from tests.test_host_stage import _stage_io, _views
+        lib = _capi.load()
+        assert ctx.shm is not None
+        contacts, frags, _, _ = synth.make_intra(60_000, 100000, seed=5, mean_count=4.0)
+        d = np.abs(contacts.mid1.astype(np.int64) - contacts.mid2)
+        D = int(max(d.max(), frags.max_mid.max()) // 100000 + 2)
+        hist = np.bincount(d // 100000, weights=contacts.cnt, minlength=D).astype(np.int64)
+        scal = np.zeros(_capi.N_SCALARS, dtype=np.uint64)
+        scal[_capi.S_INTRA_INRANGE_SUM] = int(hist.sum())
+        scal[_capi.S_MAX_COUNT] = int(contacts.cnt.max())
+        io1, keep1 = _stage_io(lib, hist, scal, None, 100000, 100, frags, 0, -1, 1, 1)
+        _capi.check(lib.fhc_host_stage(ctypes.byref(io1), 7))
+        io2, keep2 = _stage_io(lib, hist, scal, None, 100000, 100, frags, 0, -1, 1, 2)
+        io2.pairs_rank, io2.pairs_world, io2.shm = rank, world, ctx.shm
+        for _ in range(3):  # several passes: the slots alternate
+            _capi.check(lib.fhc_host_stage(ctypes.byref(io2), 7))
+            a, b = _views(io1, keep1, 100), _views(io2, keep2, 100)
+            for k in ("sumdist", "x_bins", "y_bins", "t", "c", "table", "lut", "pairs"):
+                assert np.array_equal(a[k], b[k]), k
         assert ctx.max_int(5 + rank) == 6
         assert ctx.allreduce_small(np.array([1, 2 + rank])).tolist() == [2, 5]
         open(os.path.join(tmp, "ok%d" % rank), "w").close()
     finally:
+        try:
+            ctx.close()
+        except Exception:
+            pass
         dist.destroy_process_group()
 
 
