@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 7
+FHC_ABI_VERSION = 8
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES, S_NONPOS_LINES) = range(9)
 N_SCALARS = 9
@@ -120,7 +120,7 @@ _SIGNATURES = {
     "fhc_bh_p_cut": (c_double, [c_double, c_double]),
     "fhc_bh_cut_hist": (ctypes.c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "fhc_bh_cut_from_hists": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_double, c_double, c_void_p, c_void_p]),
-    "fhc_bh_dist_cut": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "fhc_bh_dist_cut": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_host_bh_cut_find": (c_double, [c_void_p, c_double, c_double, c_double]),
     "fhc_host_bh_cut_bucket": (c_int32, [c_double]),
     "fhc_bh_finish": (ctypes.c_int, [c_int64, c_double, c_int64, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -199,8 +199,10 @@ __host__ __device__ inline double cut_edge(int j) {
 
 // One CTA per SM with the whole histogram in shared memory (128 KB of uint32); flushed with one global atomic per
 // non-empty bucket.  Only p-values that bh_compact_kernel would rank at the first cut are counted.
+// q_nan (nullable): q is pre-filled with 1.0; the NaN lines get their q = NaN here, so that a pass with nothing to rank needs no
+// second sweep over p.
 __global__ void __launch_bounds__(kCutHistThreads) bh_cut_hist_kernel(const double *__restrict__ p, long long n, double p_cut0,
-                                                                     u64 *__restrict__ hist) {
+                                                                     u64 *__restrict__ hist, double *__restrict__ q_nan) {
     extern __shared__ __align__(16) unsigned char cut_smem[];
     u32 *sh = reinterpret_cast<u32 *>(cut_smem);
     for (int i = threadIdx.x; i < kCutBuckets; i += kCutHistThreads) sh[i] = 0;
@@ -212,10 +214,15 @@ __global__ void __launch_bounds__(kCutHistThreads) bh_cut_hist_kernel(const doub
         const double2 v = p2[i];
         if (!(v.x == 1.0) && !isnan(v.x) && !(v.x >= p_cut0)) atomicAdd(sh + cut_bucket(v.x), 1u);
         if (!(v.y == 1.0) && !isnan(v.y) && !(v.y >= p_cut0)) atomicAdd(sh + cut_bucket(v.y), 1u);
+        if (q_nan != nullptr) {
+            if (isnan(v.x)) q_nan[2 * i] = v.x;
+            if (isnan(v.y)) q_nan[2 * i + 1] = v.y;
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const double x = p[n - 1];
         if (!(x == 1.0) && !isnan(x) && !(x >= p_cut0)) atomicAdd(sh + cut_bucket(x), 1u);
+        if (q_nan != nullptr && isnan(x)) q_nan[n - 1] = x;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kCutBuckets; i += kCutHistThreads) {
@@ -351,6 +358,43 @@ __global__ void __launch_bounds__(1024) bh_cut_from_hists_kernel(const u64 *__re
         info[1] = tot;
         info[2] = share[my_rank];
         info[3] = mx;
+    }
+}
+
+// Multi-GPU, the lean form: the value histograms of all ranks already summed (all-reduce) + this rank's own histogram ->
+// the global cut, the number of p-values below it on all ranks and on this one.  info: [0] the cut (double), [1] below it
+// on all ranks, [2] on this rank.
+__global__ void __launch_bounds__(1024) bh_cut_from_sum_kernel(const u64 *__restrict__ summed, const u64 *__restrict__ local,
+                                                              double T, double p_cut0, u64 *__restrict__ info) {
+    extern __shared__ __align__(16) unsigned char cut_find_smem[];
+    __shared__ u64 wsum[32];
+    __shared__ int best;
+    __shared__ u64 share[2];
+    if (threadIdx.x < 2) share[threadIdx.x] = 0;
+    int upto = kCutBuckets;
+    if (T > 0.0) upto = cut_find_block(summed, 1, T, 0.0, reinterpret_cast<u32 *>(cut_find_smem), wsum, &best);
+    __syncthreads();
+    u64 ca = 0, cm = 0;
+    for (int k = 0; k < kCutPer; ++k) {
+        const int j = k * 1024 + threadIdx.x;
+        if (j < upto) {
+            ca += summed[j];
+            cm += local[j];
+        }
+    }
+    ca = warp_sum(ca);
+    cm = warp_sum(cm);
+    if ((threadIdx.x & 31) == 0) {
+        if (ca) atomicAdd(&share[0], ca);
+        if (cm) atomicAdd(&share[1], cm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cut = p_cut0;
+        if (upto < kCutBuckets) cut = fmin(cut, cut_edge(upto));
+        info[0] = (u64)__double_as_longlong(cut);
+        info[1] = share[0];
+        info[2] = share[1];
     }
 }
 
@@ -1074,14 +1118,15 @@ static double bh_p_cut(double T, double rank_bound) {
     return (rank_bound / T) * (1.0 + 1e-9);
 }
 
-static int cut_hist_launch(const double *p, int64_t n, double p_cut0, fhc::u64 *hist, cudaStream_t st) {
+static int cut_hist_launch(const double *p, int64_t n, double p_cut0, fhc::u64 *hist, cudaStream_t st,
+                           double *q_nan = nullptr) {
     using namespace fhc;
     const size_t smem = (size_t)kCutBuckets * sizeof(u32);
     FHC_CUDA(cudaFuncSetAttribute(bh_cut_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = (n / 2 + kCutHistThreads - 1) / kCutHistThreads;
     if (blocks > kNumSMs) blocks = kNumSMs;
     if (blocks < 1) blocks = 1;
-    bh_cut_hist_kernel<<<(unsigned int)blocks, kCutHistThreads, smem, st>>>(p, n, p_cut0, hist);
+    bh_cut_hist_kernel<<<(unsigned int)blocks, kCutHistThreads, smem, st>>>(p, n, p_cut0, hist, q_nan);
     FHC_LAUNCH_CHECK("bh_cut_hist_kernel");
     return FHC_OK;
 }
@@ -1428,30 +1473,33 @@ extern "C" int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int3
     return FHC_OK;
 }
 
-// The first half of the multi-GPU correction in one call: value histogram of this rank's p-values below p_cut0, all-gather
-// over the library's own collectives, global cut + every rank's share, read back.  work [dev]: (1 + world) histograms +
-// (8 + world) words; info_host [pinned host]: 8 + world words, valid on return (the call synchronises the stream once).
+// The first half of the multi-GPU correction in one call: value histogram of this rank's p-values below p_cut0, summed
+// over the ranks by the library's own all-reduce, global cut + how many p-values lie below it (on all ranks, on this one),
+// read back.  work [dev]: two histograms + 8 words; info_host [pinned host]: 8 words ([0] cut as a double, [1] below the
+// cut on all ranks, [2] on this rank), valid on return (the call synchronises the stream once).  q_nan (nullable): q, filled
+// with 1.0 by the caller; the lines whose p is NaN get q = NaN in the same sweep, so that q is final when nothing lies below
+// the cut.
 extern "C" int fhc_bh_dist_cut(fhc_comm *comm, const double *p, int64_t n, double T, double p_cut0, uint64_t *work,
-                               uint64_t *info_host, void *stream) {
+                               uint64_t *info_host, double *q_nan, void *stream) {
     using namespace fhc;
     FHC_REQUIRE(comm && work && info_host && n >= 0 && (n == 0 || p != nullptr), FHC_E_INVALID, "fhc_bh_dist_cut: bad arguments");
-    const int world = fhc_comm_world(comm), rank = fhc_comm_rank(comm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     u64 *local = reinterpret_cast<u64 *>(work);
-    u64 *gathered = local + kCutBuckets;
-    u64 *info = gathered + (size_t)world * kCutBuckets;
+    u64 *summed = local + kCutBuckets;
+    u64 *info = summed + kCutBuckets;
     FHC_CUDA(cudaMemsetAsync(local, 0, (size_t)kCutBuckets * sizeof(u64), st));
     if (n > 0) {
-        const int rc = cut_hist_launch(p, n, p_cut0, local, st);
+        const int rc = cut_hist_launch(p, n, p_cut0, local, st, q_nan);
         if (rc != FHC_OK) return rc;
     }
-    int rc = fhc_comm_allgather(comm, local, gathered, (int64_t)kCutBuckets * (int64_t)sizeof(u64), stream);
+    FHC_CUDA(cudaMemcpyAsync(summed, local, (size_t)kCutBuckets * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    const int rc = fhc_comm_allreduce_u64(comm, reinterpret_cast<uint64_t *>(summed), kCutBuckets, stream);
     if (rc != FHC_OK) return rc;
-    rc = fhc_bh_cut_from_hists(reinterpret_cast<const uint64_t *>(gathered), world, rank, T, p_cut0,
-                               reinterpret_cast<uint64_t *>(info), stream);
-    if (rc != FHC_OK) return rc;
-    FHC_CUDA(cudaMemcpyAsync(info_host, info, (size_t)(8 + world) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    FHC_CUDA(cudaFuncSetAttribute(bh_cut_from_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCutFindSmem));
+    bh_cut_from_sum_kernel<<<1, 1024, kCutFindSmem, st>>>(summed, local, T, p_cut0, info);
+    FHC_LAUNCH_CHECK("bh_cut_from_sum_kernel");
+    FHC_CUDA(cudaMemcpyAsync(info_host, info, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     FHC_CUDA(cudaStreamSynchronize(st));
     return FHC_OK;
 }

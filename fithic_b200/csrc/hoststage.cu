@@ -200,27 +200,43 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         const uint64_t *scal = io->k1buf + D;
         const uint32_t *present = reinterpret_cast<const uint32_t *>(io->k1buf + D + FHC_N_SCALARS + io->n_rank_slots);
         const bool any_present = scal[FHC_S_NONPOS_LINES] != 0;
-        int64_t m = 0;
-        if (!any_present) {
-            for (int64_t k = 0; k < D; ++k) {
-                const uint64_t v = hist[k];
-                io->dists[m] = k * (int64_t)res;
-                io->sums[m] = (int64_t)v;
-                m += v != 0;
+        // one sweep: the observed distances (a distance whose counts sum to zero still counts as seen, :434-436 -- rare, the
+        // bitmap is only read when K1 met such a line) and the equal-occupancy bins over them.  The bin logic is
+        // fhc_host_make_bins' (host_bins.cu, fithic/fithic.py:463-553), statement for statement.
+        const int64_t N = (int64_t)scal[FHC_S_INTRA_INRANGE_SUM];
+        double desired = (double)N / (double)noOfBins;
+        int64_t total = 0, acc = 0, binsum = 0, prev_ub = -1, m = 0;
+        int nb = 0;
+        for (int64_t k = 0; k < D; ++k) {
+            const uint64_t v = hist[k];
+            if (v == 0 && !(any_present && ((present[k >> 5] >> (k & 31)) & 1u))) continue;
+            const int64_t cc = (int64_t)v, dist = k * (int64_t)res;
+            io->dists[m] = dist;
+            io->sums[m] = cc;
+            ++m;
+            total += cc;
+            bool full = true;
+            if (!((double)cc >= desired) && !((double)(acc + cc) >= desired)) {
+                full = false;
+                acc += cc;
             }
-        } else {  // a distance whose counts sum to zero still counts as seen (:434-436): rare
-            for (int64_t k = 0; k < D; ++k) {
-                const uint64_t v = hist[k];
-                const bool seen = v != 0 || ((present[k >> 5] >> (k & 31)) & 1u);
-                io->dists[m] = k * (int64_t)res;
-                io->sums[m] = (int64_t)v;
-                m += seen;
+            binsum += cc;
+            if (full) {
+                if (nb >= noOfBins) {
+                    fhc::set_error("fhc_host_stage: more than noOfBins=%d bins closed", noOfBins);
+                    return FHC_E_RANGE;
+                }
+                io->bin_lb[nb] = nb == 0 ? 0 : prev_ub + 1;
+                io->bin_ub[nb] = dist;
+                io->bin_sumcc[nb] = binsum;
+                prev_ub = dist;
+                nb += 1;
+                if (nb < noOfBins) desired = 1.0 * (double)(N - total) / (double)(noOfBins - nb);
+                acc = 0;
+                binsum = 0;
             }
         }
         io->nseen = m;
-        const int64_t N = (int64_t)scal[FHC_S_INTRA_INRANGE_SUM];
-        const int nb = fhc_host_make_bins(io->dists, io->sums, m, noOfBins, N, io->bin_lb, io->bin_ub, io->bin_sumcc);
-        if (nb < 0) return nb;
         io->nb = nb;
         io->timings[0] = wall_ms() - t_begin;
     }
@@ -563,15 +579,30 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         t0 = wall_ms();
         // lut[k] = table[min(bisect_left(splineX, clamp(k * res, xmin, xmax)), m - 1)]  (:1066-1068)
         {
-            int64_t j = 0;
+            const int64_t kChunk = 8192;  // independent of the thread count: a chunk finds its first table entry by bisection
+            const int nj = (int)((D + kChunk - 1) / kChunk);
             const int64_t *sx = io->splineX;
-            for (int64_t k = 0; k < D; ++k) {
-                double dl = (double)(k * (int64_t)res);
-                dl = dl < xmin ? xmin : dl;
-                dl = dl > xmax ? xmax : dl;
-                while (j < m && (double)sx[j] < dl) ++j;
-                io->lut[k] = io->table[j < m ? j : m - 1];
-            }
+            const double *tab = io->table;
+            double *lut = io->lut;
+            pool.parallel_for(nj, nworkers, [&](int jb) {
+                const int64_t k0 = (int64_t)jb * kChunk, k1 = k0 + kChunk < D ? k0 + kChunk : D;
+                double d0 = (double)(k0 * (int64_t)res);
+                d0 = d0 < xmin ? xmin : d0;
+                d0 = d0 > xmax ? xmax : d0;
+                int64_t lo2 = 0, hi2 = m;  // first j with sx[j] >= d0
+                while (lo2 < hi2) {
+                    const int64_t mid = (lo2 + hi2) >> 1;
+                    if ((double)sx[mid] < d0) lo2 = mid + 1; else hi2 = mid;
+                }
+                int64_t j = lo2;
+                for (int64_t k = k0; k < k1; ++k) {
+                    double dl = (double)(k * (int64_t)res);
+                    dl = dl < xmin ? xmin : dl;
+                    dl = dl > xmax ? xmax : dl;
+                    while (j < m && (double)sx[j] < dl) ++j;
+                    lut[k] = tab[j < m ? j : m - 1];
+                }
+            });
         }
         io->timings[5] = wall_ms() - t0;
     }

@@ -264,22 +264,41 @@ extern "C" int fhc_host_antitonic(double *y, int64_t m) {
         cnt_buf.resize((size_t)m);
     }
     double *sum = sum_buf.data(), *cnt = cnt_buf.data();
-    int64_t top = -1;
-    for (int64_t i = 0; i < m; ++i) {
+    // The newest block lives in registers (ps, pc): a point that does not violate it costs one multiply and one compare
+    // with no load that depends on the previous store -- most of a decaying spline table is such points.  The additions
+    // happen in the order of the textbook loop (new point first, then the blocks below it, nearest first).
+    int64_t top = -1;  // blocks below the newest one
+    double ps = y[0], pc = 1.0;
+    for (int64_t i = 1; i < m; ++i) {
         double s = y[i];
-        double c = 1.0;
-        // non-increasing: the previous block violates when its mean is below the new block's mean
+        if (!(ps < s * pc)) {  // non-increasing so far: the newest block is final for now
+            ++top;
+            sum[top] = ps;
+            cnt[top] = pc;
+            ps = s;
+            pc = 1.0;
+            continue;
+        }
+        // the previous block violates when its mean is below the new block's mean
+        double c = 1.0 + pc;
+        s += ps;
         while (top >= 0 && sum[top] * c < s * cnt[top]) {
             s += sum[top];
             c += cnt[top];
             --top;
         }
-        ++top;
-        sum[top] = s;
-        cnt[top] = c;
+        ps = s;
+        pc = c;
     }
+    ++top;
+    sum[top] = ps;
+    cnt[top] = pc;
     int64_t i = 0;
     for (int64_t b = 0; b <= top; ++b) {
+        if (cnt[b] == 1.0) {
+            y[i++] = sum[b];
+            continue;
+        }
         const double mean = sum[b] / cnt[b];
         const int64_t n = (int64_t)cnt[b];
         for (int64_t k = 0; k < n; ++k) y[i++] = mean;

@@ -436,6 +436,10 @@ class Engine:
                             after_chunk, lbeta=lbeta, use_prepass=native)
         if after_pvalues is not None:
             after_pvalues(p, e)  # e.g. start the device->host copy of p and ExpCC while K4 runs
+        fin = getattr(out, "_finish", None)
+        if fin is not None:  # the native host stage's report on bins and fit leaves its buffers now, while K3 runs
+            fin()
+            out._finish = None
         # ---- K4 ----
         pre_q = getattr(self, "_q_prefilled", False)  # _tables_native filled q with 1.0 while the host was fitting
         self._q_prefilled = False
@@ -444,11 +448,6 @@ class Engine:
         else:
             q = self.bh_qvalues(p, float(T), q_prefilled=pre_q)
         out.update(p=p, q=q, expcc=e)
-        late = getattr(out, "_late", None)
-        if late:  # the per-distance arrays of the native host stage leave its buffers now, while the GPU works
-            for k, a in late.items():
-                out[k] = a.copy()
-            out._late = None
         self.timings[passNo] = ev
         return out
 
@@ -595,21 +594,12 @@ class Engine:
             raise ValueError("no observed distance falls inside the fitted range")
         if io.status == 4:
             raise ValueError("the spline fit needs more than 3 bins (got %d)" % int(io.nb))
-        pairs = v["pairs"].copy()
-        bins = dict(n=int(io.nb), lb=v["lb"].copy(), ub=v["ub"].copy(), sumcc=v["sumcc"].copy(), pairs=pairs, pairs7=pairs,
-                    sumdist=v["sumdist"].copy())
-        x_bins, y_bins = v["x_bins"].tolist(), v["y_bins"].tolist()
         tot = io.totals
-        out.update(bins=bins, x=x_bins, y=y_bins, x_bins=x_bins, y_bins=y_bins,
-                   possibleIntraInRangeCount=int(tot[0]), possibleIntraAllCount=tot[1] / 2, possibleInterAllCount=tot[2] / 2,
+        out.update(possibleIntraInRangeCount=int(tot[0]), possibleIntraAllCount=tot[1] / 2, possibleInterAllCount=tot[2] / 2,
                    noOfFrags=int(tot[3]))
-        out._late = dict(dists=v["dists"], sums=v["sums"])  # copied out after K3 / K4 are launched (run_pass)
+        # the tables K3 waits for leave first ...
         lut = None
         if not st.interOnly:
-            out.update(x=v["xs"].tolist(), y=v["ys"].tolist(), tck=(v["t"].copy(), v["c"].copy(), 3),
-                       spline_ier=int(io.ier), spline_calls=int(io.calls))
-            out._late.update(splineX=v["splineX"], table=v["table"])
-            out._device = self.device
             lut = self._tensor("lut", D, torch.float64)
             check(lib.fhc_copy_async(lut.data_ptr(), hs.lut.data_ptr(), 8 * D, stream))
         lbeta = None
@@ -621,6 +611,21 @@ class Engine:
                     tab = self._tensor(name, ntab, torch.float64)
                     check(lib.fhc_copy_async(tab.data_ptr(), hs.lbeta[w].data_ptr(), 8 * ntab, stream))
                     lbeta[2 * w], lbeta[2 * w + 1] = tab, ntab
+        nb, ier, calls = int(io.nb), int(io.ier), int(io.calls)
+
+        # ... and what the pass reports about bins and fit is copied out of the stage's buffers once K3 is launched (run_pass)
+        def finish():
+            pairs = v["pairs"].copy()
+            bins = dict(n=nb, lb=v["lb"].copy(), ub=v["ub"].copy(), sumcc=v["sumcc"].copy(), pairs=pairs, pairs7=pairs,
+                        sumdist=v["sumdist"].copy())
+            x_bins, y_bins = v["x_bins"].tolist(), v["y_bins"].tolist()
+            out.update(bins=bins, x=x_bins, y=y_bins, x_bins=x_bins, y_bins=y_bins, dists=v["dists"].copy(),
+                       sums=v["sums"].copy())
+            if not st.interOnly:
+                out.update(x=v["xs"].tolist(), y=v["ys"].tolist(), tck=(v["t"].copy(), v["c"].copy(), 3), spline_ier=ier,
+                           spline_calls=calls, splineX=v["splineX"].copy(), table=v["table"].copy())
+                out._device = self.device
+        out._finish = finish
         t2 = time.perf_counter()
         tm = io.timings
         ev = {"k1_and_d2h": t1 - t0, "host_bins_fit": t2 - t1, "stage_bins": tm[0] * 1e-3, "stage_pairs_lbeta": tm[1] * 1e-3,
@@ -797,16 +802,18 @@ class Engine:
         lo = 0
         while True:
             hi = min(lo + step, n)
-            o = None if outl is None else outl[lo:hi]
-            check(self.lib.fhc_pvalues(st.mode, dptr(mid1[lo:hi]), dptr(mid2[lo:hi]), dptr(cnt[lo:hi]),
-                                       None if chrs is None else dptr(chrs[lo:hi]), dptr(rs), dptr(rv), nruns,
+            whole = lo == 0 and hi == n  # (a slice of a tensor costs microseconds: the usual single launch takes none)
+            sl = (lambda t: t) if whole else (lambda t: t[lo:hi])
+            o = None if outl is None else sl(outl)
+            check(self.lib.fhc_pvalues(st.mode, dptr(sl(mid1)), dptr(sl(mid2)), dptr(sl(cnt)),
+                                       None if chrs is None else dptr(sl(chrs)), dptr(rs), dptr(rv), nruns,
                                        hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr,
                                        getattr(self, "_bias_sparse", 0), self.grid, st.L, st.U,
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
-                                       nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(p[lo:hi]),
-                                       dptr(e[lo:hi]), None if pre_code is None else dptr(pre_code[lo:hi]),
-                                       None if pre_b12 is None else dptr(pre_b12[lo:hi]), dptr(ws), wsb, self._stream()))
+                                       nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(sl(p)),
+                                       dptr(sl(e)), None if pre_code is None else dptr(sl(pre_code)),
+                                       None if pre_b12 is None else dptr(sl(pre_b12)), dptr(ws), wsb, self._stream()))
             if after_chunk is not None:
                 after_chunk(lo, hi, p, e)
             lo = hi

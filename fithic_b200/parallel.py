@@ -311,19 +311,32 @@ class DistCtx:
         p_cut0 = ops.p_cut(T, self.n_global(n))
         #    ... and the value histograms of what is left say where q reaches 1.0 for good (bh.cu: cut_bucket_closes): one
         #    all-gather of the histograms, one kernel, one read-back of a few numbers
-        if self.comm is not None:  # histogram, all-gather, cut kernel and read-back in one library call
+        counts = None
+        if self.comm is not None:  # histogram, all-reduce, cut kernel and read-back in one library call
             if self._cut_work is None:
-                self._cut_work = torch.empty((1 + G) * _capi.BH_CUT_BUCKETS + 8 + G, dtype=torch.int64, device=self.device)
-                self._cut_info = torch.empty(8 + G, dtype=torch.int64).pin_memory()
+                self._cut_work = torch.empty(2 * _capi.BH_CUT_BUCKETS + 8, dtype=torch.int64, device=self.device)
+                self._cut_info = torch.empty(8, dtype=torch.int64).pin_memory()
             check(ops.lib.fhc_bh_dist_cut(self.comm, dptr(p), n, float(T), float(p_cut0), dptr(self._cut_work),
-                                          dptr(self._cut_info), ops._stream()))
-            info = self._cut_info.numpy().copy()
+                                          dptr(self._cut_info), dptr(q) if q_prefilled else None, ops._stream()))
+            info = self._cut_info.numpy()
+            p_cut = float(info[:1].view(np.float64)[0])
+            n_below, mine = int(info[1]), int(info[2])
+            mx = mine
+            if n_below == 0 and q_prefilled:  # q is final: 1.0 from the fill, NaN from the histogram sweep
+                self.last_plan = dict(splitters=np.zeros(0, dtype=np.uint64), count_matrix=np.zeros((G, 1), dtype=np.int64),
+                                      rank_offset=0, floor=0.0, p_cut=p_cut, p_cut0=p_cut0, small_set=True, n_below=0)
+                return q
+            if 0 < n_below <= self.SMALL_SET:  # every rank's share, for the sizes of the exchange
+                counts = self._all_gather(torch.tensor([mine, 0], dtype=torch.int64, device=p.device)).cpu().numpy()[0::2]
+                mx = int(counts.max())
         else:
             hist = ops.cut_hist(p, p_cut0)
             info = ops.cut_from_hists(self._all_gather(hist), G, r, T, p_cut0).cpu().numpy()
-        p_cut = float(info[:1].view(np.float64)[0])
-        n_below, mine, mx = int(info[1]), int(info[2]), int(info[3])
-        counts = info[8:8 + G].astype(np.int64)
+            p_cut = float(info[:1].view(np.float64)[0])
+            n_below, mine, mx = int(info[1]), int(info[2]), int(info[3])
+            counts = info[8:8 + G].astype(np.int64)
+        if counts is None:
+            counts = np.zeros(G, dtype=np.int64)
         # 0b. few survivors (the usual case on a sparse map): no range partition -- every rank compacts its survivors,
         #     the survivors are all-gathered (padded to the largest share), every rank ranks the small global set itself
         #     and keeps the q-values of its own lines.  Nothing below the cut: one kernel writes q = 1 / NaN and that is it.

@@ -34,7 +34,7 @@ extern "C" {
 #define FHC_E_RANGE (-3)     /* value outside what the reference itself defines (e.g. N >= 2^31) */
 #define FHC_E_WORKSPACE (-4) /* workspace too small */
 
-#define FHC_ABI_VERSION 7
+#define FHC_ABI_VERSION 8
 
 /* fhc_hist_distance scalars[] layout (uint64 each, two's complement where signed) */
 #define FHC_S_INTRA_INRANGE_SUM 0 /* observedIntraInRangeSum  fithic/fithic.py:439 */
@@ -385,11 +385,12 @@ int32_t fhc_host_bh_cut_bucket(double p);
  * [8 + r] the share of rank r -- what a rank needs to size the exchange of its survivors, in ONE small read-back. */
 int fhc_bh_cut_from_hists(const uint64_t *hists, int32_t nranks, int32_t my_rank, double T, double p_cut0, uint64_t *info,
                           void *stream);
-/* fhc_bh_cut_hist + all-gather over `comm` + fhc_bh_cut_from_hists + read-back in one call: info_host [pinned host, 8 +
- * world words] is valid on return (one stream synchronisation).  work [dev]: (1 + world) * FHC_BH_CUT_BUCKETS + 8 + world
- * words of scratch. */
+/* fhc_bh_cut_hist + all-reduce over `comm` + cut + read-back in one call: info_host [pinned host, 8 words: [0] the global
+ * cut (double), [1] p-values below it on all ranks, [2] on this rank] is valid on return (one stream synchronisation).
+ * work [dev]: 2 * FHC_BH_CUT_BUCKETS + 8 words of scratch.  q_nan (nullable): q pre-filled with 1.0 by the caller; lines with a
+ * NaN p-value get q = NaN in the same sweep (q is then final whenever nothing lies below the cut). */
 int fhc_bh_dist_cut(fhc_comm *comm, const double *p, int64_t n, double T, double p_cut0, uint64_t *work, uint64_t *info_host,
-                    void *stream);
+                    double *q_nan, void *stream);
 int fhc_bh_sample_keys(const double *p, int64_t n, int64_t nsamples, double p_cut, uint64_t *keys_out, void *stream);
 uint64_t fhc_bh_key_of(double p);
 int fhc_bh_partition_count(const double *p, int64_t n, const uint64_t *splitter_keys, int32_t nparts, double p_cut,
