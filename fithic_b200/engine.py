@@ -253,6 +253,9 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------------------
     def _stream(self):
+        ps = getattr(self, "_pass_stream", None)  # inside run_pass: looked up once per pass
+        if ps is not None:
+            return ps
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _buf(self, name, nbytes):
@@ -397,6 +400,14 @@ class Engine:
 
     def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
+        self._pass_stream = None
+        self._pass_stream = self._stream()
+        try:
+            return self._run_pass(passNo, outl, outl_stats, after_pvalues, pvalue_chunks, after_chunk)
+        finally:
+            self._pass_stream = None
+
+    def _run_pass(self, passNo, outl, outl_stats, after_pvalues, pvalue_chunks, after_chunk):
         st = self.st
         t0 = time.perf_counter()
         # ---- K1 ----

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "slow: minutes of CPU oracle time; runs only with FHC_SLOW=1 in the environment")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -20,6 +21,11 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
+    if os.environ.get("FHC_SLOW", "0") != "1":
+        slow = pytest.mark.skip(reason="slow (minutes of oracle time): set FHC_SLOW=1")
+        for item in items:
+            if "slow" in item.keywords:
+                item.add_marker(slow)
     if has_gpu:
         return
     skip = pytest.mark.skip(reason="needs a CUDA device")

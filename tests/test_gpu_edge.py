@@ -112,6 +112,7 @@ def test_counts_where_glibc_log_is_not_correctly_rounded(lib):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     bufs = [dev(mid1), dev(mid2), dev(counts), dev(np.zeros(n, dtype=np.int32)), dev(lut)]
     ntab = int(counts.max()) + 1
+    errs = {}
     for table, limit in (("host", 1e-6), ("device", 1e-5)):
         tab = torch.empty(ntab, dtype=torch.float64, device="cuda")
         if table == "host":
@@ -131,5 +132,8 @@ def test_counts_where_glibc_log_is_not_correctly_rounded(lib):
         got = p.cpu().numpy()
         err = np.abs(got - want) / np.abs(want)
         assert err.max() <= limit, (table, err)
-        if table == "device":  # the round-1 deviation, kept behind the switch: one ulp of lgam(N) on exactly those counts
-            assert err[:3].min() > 1e-6 and err[3:].max() <= 1e-6, err
+        errs[table] = err
+    # the round-1 deviation, kept behind the switch: one ulp of lbeta on exactly those counts (how far that moves p depends
+    # on the prior: 1e-6 here, up to 8e-6 in the tails); the default table is at least ten times closer to scipy there
+    assert errs["host"][:2].max() * 10 < errs["device"][:2].min(), errs
+    assert errs["device"][3:].max() <= 1e-7 and errs["host"].max() <= 1e-7, errs

@@ -131,3 +131,41 @@ def test_inter_only_full_size(lib):
     # ties share one q: the running max over a tie run is the value of its first rank (fithic/myStats.py:35-43)
     for c in counts[:6]:
         assert torch.unique(q[cnt == int(c)]).numel() == 1
+
+
+@pytest.mark.slow
+def test_config3_full_size_against_oracle(lib):
+    """BASELINE.json config 3 at its full size -- whole genome, 10 kb, 80 M contact pairs, two spline passes -- against the
+    oracle on ALL lines: totals, observed distances, bins, possible pairs, x / y and the outlier multiset exact, the spline
+    table to 1e-12, p and q to 1e-6.  A few minutes of oracle time on the box's host cores (FHC_SLOW=1); the log of the
+    round's run is profiles/c3_full_oracle_rNN.log."""
+    import time
+    from tests.util import compare_pass, oracle_inputs
+    n, res = 80_000_000, 10000
+    t0 = time.time()
+    contacts, frags, biases, _ = synth.make_intra(n, res, seed=1003, mean_count=4.0, with_bias=False)
+    st = Settings(resolution=res, noOfBins=100, noOfPasses=2)
+    eng = Engine(st, frags, biases)
+    eng.upload_contacts(contacts)
+    outl, stats = eng.new_outlier_state()
+    got = []
+    for passNo in (1, 2):
+        r = eng.run_pass(passNo, outl, stats)
+        torch.cuda.synchronize()
+        for k in ("p", "q", "expcc"):
+            r[k] = r[k].cpu().numpy().copy()
+        r["outl"] = outl.cpu().numpy().copy()
+        got.append(r)
+    t1 = time.time()
+    oc, fchr, fmid, fh, ost, ob = oracle_inputs(contacts, frags, st, biases)
+    want = O.run_pipeline(oc, fchr, fmid, fh, ost, ob)
+    t2 = time.time()
+    assert len(want) == 2
+    for r, o in zip(got, want):
+        errs = compare_pass(r, o)
+        lines = np.repeat(np.arange(n), r["outl"])
+        assert np.array_equal(lines, np.asarray(o["outliersline"], dtype=np.int64))
+        print("config 3 full size, pass %d: N %d, T %d, %d bins, %d observed distances, max rel err %s, %d outlier entries, "
+              "%d lines with q < 1" % (r["passNo"], r["N"], r["T"], r["bins"]["n"], len(r["dists"]), errs, len(lines),
+                                       int((r["q"] < 1).sum())))
+    print("generate + engine %.1f s, oracle %.1f s" % (t1 - t0, t2 - t1))
