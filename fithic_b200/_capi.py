@@ -76,6 +76,10 @@ _SIGNATURES = {
                                             c_int32, c_void_p, c_void_p, c_void_p]),
     "fhc_host_frag_pairs_varsize": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int32,
                                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fhc_frag_pairs_varsize": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int32,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fhc_host_frag_pairs_varsize_prefix": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p,
+                                                           c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fhc_host_fill_f64": (ctypes.c_int, [c_void_p, c_int64, c_double, c_int32]),
     "fhc_host_lbeta_table": (ctypes.c_int, [c_int64, c_void_p, c_int64, c_int32]),
     "fhc_host_stage": (ctypes.c_int, [ctypes.POINTER(StageIO), c_int32]),

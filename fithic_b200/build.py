@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfithic_b200.so")
-SOURCES = ["api.cu", "hist.cu", "host_bins.cu", "hoststage.cu", "spline.cu", "pvalue.cu", "pvalue_lists.cu", "bh.cu", "outlier.cu", "kr.cu", "merge.cu", "textio.cu", "peaks.cu", "comm.cu"]
+SOURCES = ["api.cu", "hist.cu", "host_bins.cu", "hoststage.cu", "spline.cu", "pvalue.cu", "pvalue_lists.cu", "bh.cu", "outlier.cu", "kr.cu", "merge.cu", "textio.cu", "peaks.cu", "comm.cu", "fragpairs.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall", "-Xptxas", "-v",

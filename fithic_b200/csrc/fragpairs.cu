@@ -39,7 +39,7 @@ struct FragPairsArgs {
 };
 
 // first index in [a, b) with f[i] >= v
-__device__ __forceinline__ long long lower_bound_dev(const long long *__restrict__ f, long long a, long long b, long long v) {
+__host__ __device__ __forceinline__ long long lower_bound_dev(const long long *__restrict__ f, long long a, long long b, long long v) {
     while (a < b) {
         const long long m = (a + b) >> 1;
         if (f[m] < v) a = m + 1; else b = m;
@@ -48,12 +48,36 @@ __device__ __forceinline__ long long lower_bound_dev(const long long *__restrict
 }
 
 // first index in [a, b) with f[i] > v
-__device__ __forceinline__ long long upper_bound_dev(const long long *__restrict__ f, long long a, long long b, long long v) {
+__host__ __device__ __forceinline__ long long upper_bound_dev(const long long *__restrict__ f, long long a, long long b, long long v) {
     while (a < b) {
         const long long m = (a + b) >> 1;
         if (f[m] <= v) a = m + 1; else b = m;
     }
     return a;
+}
+
+// The partners [ya, yb) of fragment xi (mid point mx, first partner in range lo) of a chromosome with n fragments whose
+// prefix arrays start at `off`: how many, the sum of npairs = n - (y - lo), and the sum of (mid_y - mx) * npairs.
+__host__ __device__ __forceinline__ void frag_cell(const FragPairsArgs &a, long long off, long long n, long long lo,
+                                                   long long ya, long long yb, long long mx, u64 *cnt_out, u64 *s7_out,
+                                                   u128 *t_out) {
+    const u64 cnt = (u64)(yb - ya);
+    const u64 ja = (u64)(ya - lo);
+    const u64 s7 = cnt * (u64)n - ((2 * ja + cnt - 1) * cnt) / 2;  // sum over j = ja .. ja + cnt - 1 of (n - j)
+    const u64 s1 = a.p1[off + yb] - a.p1[off + ya];
+    const u128 s2 = (((u128)a.p2_hi[off + yb] << 64) | a.p2_lo[off + yb]) - (((u128)a.p2_hi[off + ya] << 64) | a.p2_lo[off + ya]);
+    *cnt_out = cnt;
+    *s7_out = s7;
+    *t_out = (u128)s1 * (u128)(u64)(n + lo) - s2 - (u128)(u64)mx * (u128)s7;
+}
+
+// the end of bin b's partner range for a fragment whose range so far ends at ya (window end hi)
+__host__ __device__ __forceinline__ long long frag_bin_end(const FragPairsArgs &a, const long long *f, int b, long long ya,
+                                                           long long hi, long long mx) {
+    if (ya >= hi) return ya;
+    if (b == a.nbins - 1) return hi;  // the tracker stops at the last bin
+    const long long ub = a.bin_ub[b];
+    return f[ya] - mx <= ub ? upper_bound_dev(f, ya + 1, hi, mx + ub) : ya;
 }
 
 __device__ __forceinline__ void add128(u64 *lo_hi, u64 lo, u64 hi) {
@@ -99,29 +123,18 @@ __global__ void __launch_bounds__(256) frag_pairs_varsize_kernel(const FragPairs
         long long ya = lo;
         for (int b = 0; b < a.nbins; ++b) {
             if (__all_sync(0xffffffffu, ya >= hi)) break;  // every lane's window is used up
-            long long yb = ya;
-            if (ya < hi) {
-                if (b == a.nbins - 1) yb = hi;  // the tracker stops at the last bin
-                else {
-                    const long long ub = a.bin_ub[b];
-                    if (f[ya] - mx <= ub) yb = upper_bound_dev(f, ya + 1, hi, mx + ub);
-                }
-            }
-            const u64 cnt = (u64)(yb - ya);
+            const long long yb = frag_bin_end(a, f, b, ya, hi, mx);
+            u64 cnt = (u64)(yb - ya);
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             u64 s7 = 0, t_lo = 0, t_hi = 0;
             if (cnt) {
-                const u64 ja = (u64)(ya - lo);
-                s7 = cnt * (u64)n - ((2 * ja + cnt - 1) * cnt) / 2;  // sum over j = ja .. ja + cnt - 1 of (n - j)
-                const u64 s1 = a.p1[off + yb] - a.p1[off + ya];
-                const u128 s2 = (((u128)a.p2_hi[off + yb] << 64) | a.p2_lo[off + yb]) -
-                                (((u128)a.p2_hi[off + ya] << 64) | a.p2_lo[off + ya]);
-                const u128 t = (u128)s1 * (u128)(u64)(n + lo) - s2 - (u128)(u64)mx * (u128)s7;
+                u128 t;
+                frag_cell(a, off, n, lo, ya, yb, mx, &cnt, &s7, &t);
                 t_lo = (u64)t;
                 t_hi = (u64)(t >> 64);
             }
             // 128-bit warp sum: low words with their carries
-            u64 c_sum = warp_sum(cnt), s7_sum = warp_sum(s7);
+            const u64 c_sum = warp_sum(cnt), s7_sum = warp_sum(s7);
             u64 lo_sum = t_lo, hi_sum = t_hi;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -154,48 +167,85 @@ __global__ void __launch_bounds__(256) frag_pairs_varsize_kernel(const FragPairs
 
 }  // namespace fhc
 
+namespace {
+struct FragPrefix {
+    std::vector<long long> off;
+    std::vector<fhc::u64> p1, p2_lo, p2_hi;
+    int64_t n_total = 0, inter2 = 0, base = 0;
+};
+
+// prefix sums on the host (one pass over the fragments); the argument checks ride along
+int frag_prefix(const char *who, const int64_t *mids, const int64_t *chr_off, int32_t nchr, const int64_t *bin_lb,
+                const int64_t *bin_ub, int32_t nbins, const int64_t *bin_pairs1, const int64_t *bin_pairs7,
+                const double *bin_sumdist, const int64_t *totals, FragPrefix *out) {
+    using namespace fhc;
+    FHC_REQUIRE(nchr >= 0 && nbins >= 0 && totals != nullptr, FHC_E_INVALID, "%s: bad nchr / nbins / totals", who);
+    FHC_REQUIRE(nchr == 0 || (mids && chr_off), FHC_E_INVALID, "%s: null fragment arrays", who);
+    FHC_REQUIRE(nbins == 0 || (bin_lb && bin_ub && bin_pairs1 && bin_pairs7 && bin_sumdist), FHC_E_INVALID, "%s: null bin arrays", who);
+    for (int b = 1; b < nbins; ++b)
+        FHC_REQUIRE(bin_lb[b] == bin_ub[b - 1] + 1, FHC_E_INVALID, "%s: bins are not contiguous at bin %d", who, b);
+    out->base = nchr > 0 ? chr_off[0] : 0;
+    const int64_t n_total = out->n_total = nchr > 0 ? chr_off[nchr] - out->base : 0;
+    out->off.assign((size_t)nchr + 1, 0);
+    out->p1.assign((size_t)n_total + 1, 0);
+    out->p2_lo.assign((size_t)n_total + 1, 0);
+    out->p2_hi.assign((size_t)n_total + 1, 0);
+    u64 s1 = 0;
+    u128 s2 = 0;
+    for (int c = 0; c < nchr; ++c) {
+        const int64_t *f = mids + chr_off[c];
+        const int64_t n = chr_off[c + 1] - chr_off[c];
+        FHC_REQUIRE(n >= 0, FHC_E_INVALID, "%s: chr_off decreases at chromosome %d", who, c);
+        out->off[(size_t)c] = chr_off[c] - out->base;
+        out->inter2 += (n_total - n) * n;  // :701
+        for (int64_t i = 0; i < n; ++i) {
+            FHC_REQUIRE(f[i] >= 0 && (i == 0 || f[i] >= f[i - 1]), FHC_E_INVALID,
+                        "%s: mid points of chromosome %d are not sorted (or negative)", who, c);
+            const size_t g = (size_t)(chr_off[c] - out->base + i);
+            out->p1[g] = s1;
+            out->p2_lo[g] = (u64)s2;
+            out->p2_hi[g] = (u64)(s2 >> 64);
+            s1 += (u64)f[i];
+            s2 += (u128)(u64)i * (u128)(u64)f[i];
+        }
+    }
+    out->off[(size_t)nchr] = n_total;
+    out->p1[(size_t)n_total] = s1;
+    out->p2_lo[(size_t)n_total] = (u64)s2;
+    out->p2_hi[(size_t)n_total] = (u64)(s2 >> 64);
+    return FHC_OK;
+}
+
+// acc: nbins x 4 words + [pairs in range, largest distance]
+void frag_finish(const std::vector<fhc::u64> &acc, int32_t nbins, const FragPrefix &pre, int64_t *bin_pairs1,
+                 int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals) {
+    using namespace fhc;
+    const size_t w_acc = 4 * (size_t)nbins;
+    for (int b = 0; b < nbins; ++b) {
+        bin_pairs1[b] += (int64_t)acc[4 * (size_t)b];
+        bin_pairs7[b] += (int64_t)acc[4 * (size_t)b + 1];
+        const u128 t = ((u128)acc[4 * (size_t)b + 3] << 64) | acc[4 * (size_t)b + 2];
+        bin_sumdist[b] += (double)t / 1000000.0;  // the conversion rounds the exact integer once
+    }
+    totals[0] = (int64_t)acc[w_acc];                  // possibleIntraInRangeCount
+    totals[1] = nbins > 0 ? (int64_t)acc[w_acc] : 0;  // possibleIntraAllCount (:736: counted only when bins exist)
+    totals[2] = pre.inter2;
+    totals[3] = pre.n_total;
+    totals[4] = (int64_t)acc[w_acc + 1];              // maxPossibleGenomicDist
+}
+}  // namespace
+
 // Same arguments and results as fhc_host_frag_pairs_varsize (host arrays in, host arrays out; bin_pairs1 / bin_pairs7 carry
 // the pass >= 2 outlier decrements on entry) plus the stream the copies and the kernel run on; synchronises that stream.
 extern "C" int fhc_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
                                       const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
                                       int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals, void *stream) {
     using namespace fhc;
-    FHC_REQUIRE(nchr >= 0 && nbins >= 0 && totals != nullptr, FHC_E_INVALID, "fhc_frag_pairs_varsize: bad nchr / nbins / totals");
-    FHC_REQUIRE(nchr == 0 || (mids && chr_off), FHC_E_INVALID, "fhc_frag_pairs_varsize: null fragment arrays");
-    FHC_REQUIRE(nbins == 0 || (bin_lb && bin_ub && bin_pairs1 && bin_pairs7 && bin_sumdist), FHC_E_INVALID,
-                "fhc_frag_pairs_varsize: null bin arrays");
-    const int64_t base = nchr > 0 ? chr_off[0] : 0;
-    const int64_t n_total = nchr > 0 ? chr_off[nchr] - base : 0;
-    int64_t inter2 = 0;
-    for (int b = 1; b < nbins; ++b)
-        FHC_REQUIRE(bin_lb[b] == bin_ub[b - 1] + 1, FHC_E_INVALID, "fhc_frag_pairs_varsize: bins are not contiguous at bin %d", b);
-    // prefix sums on the host (one pass over the fragments); the sortedness check rides along
-    std::vector<long long> off((size_t)nchr + 1, 0);
-    std::vector<u64> p1((size_t)n_total + 1, 0), p2_lo((size_t)n_total + 1, 0), p2_hi((size_t)n_total + 1, 0);
-    u64 s1 = 0;
-    u128 s2 = 0;
-    for (int c = 0; c < nchr; ++c) {
-        const int64_t *f = mids + chr_off[c];
-        const int64_t n = chr_off[c + 1] - chr_off[c];
-        FHC_REQUIRE(n >= 0, FHC_E_INVALID, "fhc_frag_pairs_varsize: chr_off decreases at chromosome %d", c);
-        off[(size_t)c] = chr_off[c] - base;
-        inter2 += (n_total - n) * n;  // :701
-        for (int64_t i = 0; i < n; ++i) {
-            FHC_REQUIRE(f[i] >= 0 && (i == 0 || f[i] >= f[i - 1]), FHC_E_INVALID,
-                        "fhc_frag_pairs_varsize: mid points of chromosome %d are not sorted (or negative)", c);
-            const size_t g = (size_t)(chr_off[c] - base + i);
-            p1[g] = s1;
-            p2_lo[g] = (u64)s2;
-            p2_hi[g] = (u64)(s2 >> 64);
-            s1 += (u64)f[i];
-            s2 += (u128)(u64)i * (u128)(u64)f[i];
-        }
-    }
-    off[(size_t)nchr] = n_total;
-    p1[(size_t)n_total] = s1;
-    p2_lo[(size_t)n_total] = (u64)s2;
-    p2_hi[(size_t)n_total] = (u64)(s2 >> 64);
-
+    FragPrefix pre;
+    int rc = frag_prefix("fhc_frag_pairs_varsize", mids, chr_off, nchr, bin_lb, bin_ub, nbins, bin_pairs1, bin_pairs7,
+                         bin_sumdist, totals, &pre);
+    if (rc != FHC_OK) return rc;
+    const int64_t n_total = pre.n_total;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FHC_PROFILE_ENTRY(st);
     // one device block: [mids | chr_off | p1 | p2_lo | p2_hi | bin_ub | acc | totals]
@@ -205,7 +255,6 @@ extern "C" int fhc_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_of
     FHC_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&dev), words * sizeof(u64), st));
     u64 *d_mids = dev, *d_off = d_mids + w_mids, *d_p1 = d_off + w_off, *d_p2l = d_p1 + w_p, *d_p2h = d_p2l + w_p;
     u64 *d_ub = d_p2h + w_p, *d_acc = d_ub + w_ub, *d_tot = d_acc + w_acc;
-    int rc = FHC_OK;
     std::vector<u64> acc(w_acc + 2, 0);
     do {
 #define FHC_TRY(expr)                                                                                      \
@@ -214,11 +263,11 @@ extern "C" int fhc_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_of
         rc = FHC_E_CUDA;                                                                                   \
         break;                                                                                             \
     }
-        if (n_total) FHC_TRY(cudaMemcpyAsync(d_mids, mids + base, w_mids * 8, cudaMemcpyHostToDevice, st));
-        FHC_TRY(cudaMemcpyAsync(d_off, off.data(), w_off * 8, cudaMemcpyHostToDevice, st));
-        FHC_TRY(cudaMemcpyAsync(d_p1, p1.data(), w_p * 8, cudaMemcpyHostToDevice, st));
-        FHC_TRY(cudaMemcpyAsync(d_p2l, p2_lo.data(), w_p * 8, cudaMemcpyHostToDevice, st));
-        FHC_TRY(cudaMemcpyAsync(d_p2h, p2_hi.data(), w_p * 8, cudaMemcpyHostToDevice, st));
+        if (n_total) FHC_TRY(cudaMemcpyAsync(d_mids, mids + pre.base, w_mids * 8, cudaMemcpyHostToDevice, st));
+        FHC_TRY(cudaMemcpyAsync(d_off, pre.off.data(), w_off * 8, cudaMemcpyHostToDevice, st));
+        FHC_TRY(cudaMemcpyAsync(d_p1, pre.p1.data(), w_p * 8, cudaMemcpyHostToDevice, st));
+        FHC_TRY(cudaMemcpyAsync(d_p2l, pre.p2_lo.data(), w_p * 8, cudaMemcpyHostToDevice, st));
+        FHC_TRY(cudaMemcpyAsync(d_p2h, pre.p2_hi.data(), w_p * 8, cudaMemcpyHostToDevice, st));
         if (nbins) FHC_TRY(cudaMemcpyAsync(d_ub, bin_ub, w_ub * 8, cudaMemcpyHostToDevice, st));
         FHC_TRY(cudaMemsetAsync(d_acc, 0, (w_acc + 2) * 8, st));
         if (n_total > 0) {
@@ -253,16 +302,67 @@ extern "C" int fhc_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_of
     } while (0);
     cudaFreeAsync(dev, st);
     if (rc != FHC_OK) return rc;
-    for (int b = 0; b < nbins; ++b) {
-        bin_pairs1[b] += (int64_t)acc[4 * (size_t)b];
-        bin_pairs7[b] += (int64_t)acc[4 * (size_t)b + 1];
-        const u128 t = ((u128)acc[4 * (size_t)b + 3] << 64) | acc[4 * (size_t)b + 2];
-        bin_sumdist[b] += (double)t / 1000000.0;  // the conversion rounds the exact integer once
+    frag_finish(acc, nbins, pre, bin_pairs1, bin_pairs7, bin_sumdist, totals);
+    return FHC_OK;
+}
+
+// The kernel's cells, one after the other on the host (what the CPU tests check against the pair-by-pair walk of
+// fhc_host_frag_pairs_varsize).
+extern "C" int fhc_host_frag_pairs_varsize_prefix(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
+                                                  const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins,
+                                                  int64_t *bin_pairs1, int64_t *bin_pairs7, double *bin_sumdist,
+                                                  int64_t *totals) {
+    using namespace fhc;
+    FragPrefix pre;
+    const int rc = frag_prefix("fhc_host_frag_pairs_varsize_prefix", mids, chr_off, nchr, bin_lb, bin_ub, nbins, bin_pairs1,
+                               bin_pairs7, bin_sumdist, totals, &pre);
+    if (rc != FHC_OK) return rc;
+    FragPairsArgs a;
+    a.mids = reinterpret_cast<const long long *>(mids + pre.base);
+    a.chr_off = pre.off.data();
+    a.p1 = pre.p1.data();
+    a.p2_lo = pre.p2_lo.data();
+    a.p2_hi = pre.p2_hi.data();
+    a.bin_ub = reinterpret_cast<const long long *>(bin_ub);
+    a.acc = nullptr;
+    a.totals = nullptr;
+    a.n_total = pre.n_total;
+    a.L = L;
+    a.U = U;
+    a.nchr = nchr;
+    a.nbins = nbins;
+    const size_t w_acc = 4 * (size_t)nbins;
+    std::vector<u64> acc(w_acc + 2, 0);
+    std::vector<u128> sums((size_t)nbins, 0);
+    for (int c = 0; c < nchr; ++c) {
+        const long long off = pre.off[(size_t)c], n = pre.off[(size_t)c + 1] - off;
+        const long long *f = a.mids + off;
+        for (long long xi = 0; xi < n; ++xi) {
+            const long long mx = f[xi];
+            const long long lo = L < 0 ? xi + 1 : lower_bound_dev(f, xi + 1, n, mx + L);
+            const long long hi = U < 0 ? n : upper_bound_dev(f, lo, n, mx + U);
+            if (hi <= lo) continue;
+            acc[w_acc] += (u64)(hi - lo);
+            const u64 d = (u64)(f[hi - 1] - mx);
+            acc[w_acc + 1] = d > acc[w_acc + 1] ? d : acc[w_acc + 1];
+            long long ya = lo;
+            for (int b = 0; b < nbins && ya < hi; ++b) {
+                const long long yb = frag_bin_end(a, f, b, ya, hi, mx);
+                if (yb == ya) continue;
+                u64 cnt, s7;
+                u128 t;
+                frag_cell(a, off, n, lo, ya, yb, mx, &cnt, &s7, &t);
+                acc[4 * (size_t)b] += cnt;
+                acc[4 * (size_t)b + 1] += s7;
+                sums[(size_t)b] += t;
+                ya = yb;
+            }
+        }
     }
-    totals[0] = (int64_t)acc[w_acc];                 // possibleIntraInRangeCount
-    totals[1] = nbins > 0 ? (int64_t)acc[w_acc] : 0; // possibleIntraAllCount (:736: counted only when bins exist)
-    totals[2] = inter2;
-    totals[3] = n_total;
-    totals[4] = (int64_t)acc[w_acc + 1];             // maxPossibleGenomicDist
+    for (int b = 0; b < nbins; ++b) {
+        acc[4 * (size_t)b + 2] = (u64)sums[(size_t)b];
+        acc[4 * (size_t)b + 3] = (u64)(sums[(size_t)b] >> 64);
+    }
+    frag_finish(acc, nbins, pre, bin_pairs1, bin_pairs7, bin_sumdist, totals);
     return FHC_OK;
 }

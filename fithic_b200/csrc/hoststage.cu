@@ -200,43 +200,76 @@ extern "C" int fhc_host_stage(fhc_stage_io *io, int32_t phases) {
         const uint64_t *scal = io->k1buf + D;
         const uint32_t *present = reinterpret_cast<const uint32_t *>(io->k1buf + D + FHC_N_SCALARS + io->n_rank_slots);
         const bool any_present = scal[FHC_S_NONPOS_LINES] != 0;
-        // one sweep: the observed distances (a distance whose counts sum to zero still counts as seen, :434-436 -- rare, the
-        // bitmap is only read when K1 met such a line) and the equal-occupancy bins over them.  The bin logic is
-        // fhc_host_make_bins' (host_bins.cu, fithic/fithic.py:463-553), statement for statement.
+        // The observed distances (a distance whose counts sum to zero still counts as seen, :434-436 -- rare, the bitmap is
+        // only read when K1 met such a line), compacted chunk by chunk on the pool together with the running sum of their
+        // counts; then the equal-occupancy bins (fhc_host_make_bins' logic, fithic/fithic.py:463-553) by bisection on that
+        // running sum: a bin closes at the first distance where the counts gathered since the last closure reach
+        // `desired` -- `(double)cc >= desired` (:481) implies `(double)(acc + cc) >= desired` (:486), counts being >= 0, so
+        // one monotone predicate decides.  All integers: the result does not depend on the chunking.
         const int64_t N = (int64_t)scal[FHC_S_INTRA_INRANGE_SUM];
-        double desired = (double)N / (double)noOfBins;
-        int64_t total = 0, acc = 0, binsum = 0, prev_ub = -1, m = 0;
-        int nb = 0;
-        for (int64_t k = 0; k < D; ++k) {
-            const uint64_t v = hist[k];
-            if (v == 0 && !(any_present && ((present[k >> 5] >> (k & 31)) & 1u))) continue;
-            const int64_t cc = (int64_t)v, dist = k * (int64_t)res;
-            io->dists[m] = dist;
-            io->sums[m] = cc;
-            ++m;
-            total += cc;
-            bool full = true;
-            if (!((double)cc >= desired) && !((double)(acc + cc) >= desired)) {
-                full = false;
-                acc += cc;
+        constexpr int64_t kChunk = 4096;
+        const int nchunks = (int)((D + kChunk - 1) / kChunk);
+        static thread_local std::vector<int64_t> chunk_cnt, chunk_sum, cum_buf;
+        chunk_cnt.assign((size_t)nchunks + 1, 0);
+        chunk_sum.assign((size_t)nchunks + 1, 0);
+        if ((int64_t)cum_buf.size() < D) cum_buf.resize((size_t)D);
+        int64_t *ccnt = chunk_cnt.data(), *csum = chunk_sum.data(), *cum = cum_buf.data();
+        auto is_seen = [&](int64_t k, uint64_t v) { return v != 0 || (any_present && ((present[k >> 5] >> (k & 31)) & 1u)); };
+        pool.parallel_for(nchunks, nworkers, [&](int j) {
+            const int64_t k0 = (int64_t)j * kChunk, k1 = k0 + kChunk < D ? k0 + kChunk : D;
+            int64_t c = 0, sum = 0;
+            for (int64_t k = k0; k < k1; ++k) {
+                const uint64_t v = hist[k];
+                c += is_seen(k, v) ? 1 : 0;
+                sum += (int64_t)v;
             }
-            binsum += cc;
-            if (full) {
-                if (nb >= noOfBins) {
-                    fhc::set_error("fhc_host_stage: more than noOfBins=%d bins closed", noOfBins);
-                    return FHC_E_RANGE;
-                }
-                io->bin_lb[nb] = nb == 0 ? 0 : prev_ub + 1;
-                io->bin_ub[nb] = dist;
-                io->bin_sumcc[nb] = binsum;
-                prev_ub = dist;
-                nb += 1;
-                if (nb < noOfBins) desired = 1.0 * (double)(N - total) / (double)(noOfBins - nb);
-                acc = 0;
-                binsum = 0;
-            }
+            ccnt[j + 1] = c;
+            csum[j + 1] = sum;
+        });
+        for (int j = 0; j < nchunks; ++j) {
+            ccnt[j + 1] += ccnt[j];
+            csum[j + 1] += csum[j];
         }
+        const int64_t m = ccnt[nchunks];
+        int64_t *dists = io->dists, *sums = io->sums;
+        pool.parallel_for(nchunks, nworkers, [&](int j) {
+            const int64_t k0 = (int64_t)j * kChunk, k1 = k0 + kChunk < D ? k0 + kChunk : D;
+            int64_t at = ccnt[j], run = csum[j];
+            int64_t sink[3];  // where the stores of an unobserved distance go (never into another chunk's share)
+            for (int64_t k = k0; k < k1; ++k) {
+                const uint64_t v = hist[k];
+                const bool sn = is_seen(k, v);
+                run += (int64_t)v;
+                *(sn ? dists + at : sink) = k * (int64_t)res;
+                *(sn ? sums + at : sink + 1) = (int64_t)v;
+                *(sn ? cum + at : sink + 2) = run;
+                at += sn ? 1 : 0;
+            }
+        });
         io->nseen = m;
+        double desired = (double)N / (double)noOfBins;  // :476
+        int64_t closed_at = 0, prev_ub = -1, i0 = 0;     // counts up to the last closure; its distance; first open entry
+        int nb = 0;
+        while (i0 < m) {
+            int64_t lo2 = i0, hi2 = m;  // first i >= i0 with (double)(cum[i] - closed_at) >= desired
+            while (lo2 < hi2) {
+                const int64_t mid = (lo2 + hi2) >> 1;
+                if ((double)(cum[mid] - closed_at) >= desired) hi2 = mid; else lo2 = mid + 1;
+            }
+            if (lo2 >= m) break;  // distances after the last closed bin are dropped, as in the reference
+            if (nb >= noOfBins) {
+                fhc::set_error("fhc_host_stage: more than noOfBins=%d bins closed", noOfBins);
+                return FHC_E_RANGE;
+            }
+            io->bin_lb[nb] = nb == 0 ? 0 : prev_ub + 1;  // :518-521
+            io->bin_ub[nb] = dists[lo2];
+            io->bin_sumcc[nb] = cum[lo2] - closed_at;
+            prev_ub = dists[lo2];
+            closed_at = cum[lo2];
+            nb += 1;
+            if (nb < noOfBins) desired = 1.0 * (double)(N - closed_at) / (double)(noOfBins - nb);  // :500-502
+            i0 = lo2 + 1;
+        }
         io->nb = nb;
         io->timings[0] = wall_ms() - t_begin;
     }

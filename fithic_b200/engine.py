@@ -99,13 +99,20 @@ class Biases:
 
 def host_threads():
     """Host threads of this rank for the stages between the kernels: FHC_HOST_THREADS, else the cores this rank can call
-    its own (all of them on one GPU, a share under torchrun), at most 8."""
+    its own, at most 8.  Under torchrun that is its share of the node's cores MINUS ONE: the pool's workers spin while a
+    pass runs, and a node whose cores are all spinning has none left for the other threads of the ranks (measured on a
+    32-core box with 8 GPUs: 8 threads per rank 6.4 ms per pass, 4 threads 2.02 ms, 3 threads 1.97 ms)."""
     env = os.environ.get("FHC_HOST_THREADS")
     if env:
         return max(1, min(64, int(env)))
-    cores = os.cpu_count() or 4
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 4
     local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(8, cores // max(local, 1)))
+    if local > 1:
+        return max(1, min(8, cores // local - 1))
+    return max(1, min(8, cores))
 
 
 class PassResult(dict):
@@ -675,7 +682,7 @@ class Engine:
             dec = self.outlier_bin_decrements(outl, bins["ub"])
             if self.dist is not None:
                 dec = self.dist.allreduce_small(dec)
-        fp = frag_pairs(lib, self.frags, st, bins, dec)
+        fp = frag_pairs(lib, self.frags, st, bins, dec, stream=self._stream())
         x, y = calculate_probabilities(bins, N)
         out.update(dists=dists, sums=sums, bins=bins, x=x, y=y, x_bins=x, y_bins=y, **fp)
         lut = None
@@ -893,9 +900,29 @@ def make_bins(lib, dists, sums, noOfBins, N):
     return dict(n=nb, lb=lb[:nb].copy(), ub=ub[:nb].copy(), sumcc=sc[:nb].copy())
 
 
-def frag_pairs(lib, frags, st, bins, dec=None):
+VARSIZE_GPU_MIN_PAIRS = 200_000_000  # -r 0: more fragment pairs in range than this go to the prefix-sum kernel
+
+
+def varsize_pairs_in_range(mids, off, L, U):
+    """How many fragment pairs (x < y, same chromosome) have L <= mid_y - mid_x <= U (-1: unbounded), by bisection."""
+    total = 0
+    for c in range(len(off) - 1):
+        f = mids[off[c]:off[c + 1]]
+        n = len(f)
+        if n < 2:
+            continue
+        idx = np.arange(n, dtype=np.int64)
+        lo = idx + 1 if L < 0 else np.maximum(np.searchsorted(f, f + L, side="left"), idx + 1)
+        hi = np.full(n, n, dtype=np.int64) if U < 0 else np.searchsorted(f, f + U, side="right")
+        total += int(np.maximum(hi - lo, 0).sum())
+    return total
+
+
+def frag_pairs(lib, frags, st, bins, dec=None, stream=None):
     """generate_FragPairs (fithic/fithic.py:596-689 fixed-size bins, :691-778 restriction fragments).  Mutates `bins`
-    (adds pairs = `[1]`, pairs7 = `[7]`, sumdist = `[3]`; the two pair counts differ only for restriction fragments)."""
+    (adds pairs = `[1]`, pairs7 = `[7]`, sumdist = `[3]`; the two pair counts differ only for restriction fragments).
+    Restriction fragments: the pair-by-pair walk on the host (the reference's bits in `[3]`) up to VARSIZE_GPU_MIN_PAIRS
+    pairs in range, the prefix-sum kernel beyond (FHC_VARSIZE_PAIRS=host|gpu forces one)."""
     order = sorted(range(len(frags.chroms)), key=lambda i: frags.chroms[i])  # sorted chromosome NAMES (:606)
     order = [i for i in order if frags.n_mappable[i] > 0]
     nb = bins["n"]
@@ -910,8 +937,16 @@ def frag_pairs(lib, frags, st, bins, dec=None):
         np.cumsum([len(frags.mids[i]) for i in order], out=off[1:])
         pairs7 = pairs.copy()  # the outlier decrements hit [1] and [7] alike (:544-545)
         totals = np.zeros(5, dtype=np.int64)
-        check(lib.fhc_host_frag_pairs_varsize(dptr(mids), dptr(off), len(order), st.L, st.U, dptr(bins["lb"]), dptr(bins["ub"]),
-                                              nb, dptr(pairs), dptr(pairs7), dptr(sumdist), dptr(totals)))
+        how = os.environ.get("FHC_VARSIZE_PAIRS", "auto")
+        if how == "auto":
+            how = "gpu" if varsize_pairs_in_range(mids, off, st.L, st.U) > VARSIZE_GPU_MIN_PAIRS else "host"
+        lb, ub = np.ascontiguousarray(bins["lb"], dtype=np.int64), np.ascontiguousarray(bins["ub"], dtype=np.int64)
+        if how == "gpu":
+            check(lib.fhc_frag_pairs_varsize(dptr(mids), dptr(off), len(order), st.L, st.U, dptr(lb), dptr(ub), nb, dptr(pairs),
+                                             dptr(pairs7), dptr(sumdist), dptr(totals), stream))
+        else:
+            check(lib.fhc_host_frag_pairs_varsize(dptr(mids), dptr(off), len(order), st.L, st.U, dptr(lb), dptr(ub), nb,
+                                                  dptr(pairs), dptr(pairs7), dptr(sumdist), dptr(totals)))
         bins["pairs"], bins["pairs7"], bins["sumdist"] = pairs[:nb], pairs7[:nb], sumdist[:nb]
         return dict(possibleIntraInRangeCount=int(totals[0]), possibleIntraAllCount=int(totals[1]),
                     possibleInterAllCount=totals[2] / 2, noOfFrags=int(totals[3]), maxPossibleGenomicDist=int(totals[4]))

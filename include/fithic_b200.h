@@ -155,6 +155,19 @@ int fhc_host_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int
                                 const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
                                 int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals);
 
+/* The same on the GPU from prefix sums over the sorted mid points (csrc/fragpairs.cu): O(log n) per (fragment, bin) instead
+ * of one step per pair in range -- what a genome-wide restriction map without -U needs (1e10 pairs on chr1 alone).  Host
+ * arrays in and out like fhc_host_frag_pairs_varsize; copies and kernel run on `stream`, which is synchronised.  `[1]`, `[7]`
+ * and the totals are exact; `[3]` is the correctly rounded exact sum (128-bit integers, one division by 1e6), which differs
+ * from the reference's term-by-term double accumulation by that accumulation's rounding (~1e-13 relative). */
+int fhc_frag_pairs_varsize(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
+                           const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
+                           int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals, void *stream);
+/* the kernel's per-cell code run serially on the host (CPU tests) */
+int fhc_host_frag_pairs_varsize_prefix(const int64_t *mids, const int64_t *chr_off, int32_t nchr, int64_t L, int64_t U,
+                                       const int64_t *bin_lb, const int64_t *bin_ub, int32_t nbins, int64_t *bin_pairs1,
+                                       int64_t *bin_pairs7, double *bin_sumdist, int64_t *totals);
+
 /* ---- the whole host stage between K1 and K3 in one call ----------------------------------------------------------
  * k1buf [host]: fhc_hist_distance's outputs back to back as the engine keeps them, [hist (D) | scalars (FHC_N_SCALARS +
  * n_rank_slots) | present words]; the present words are only read when scalars[FHC_S_NONPOS_LINES] != 0; with

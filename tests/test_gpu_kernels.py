@@ -545,3 +545,54 @@ def test_partition_kernels(lib, n, nparts):
     check(lib.fhc_scatter_f64(dptr(src), dptr(idx), tot, dptr(q), stream()))
     torch.cuda.synchronize()
     assert np.array_equal(q.cpu().numpy()[ih[:tot]], np.arange(tot, dtype=np.float64))
+
+
+@pytest.mark.parametrize("L,U", [(-1, -1), (20000, 5_000_000), (3_000_000, -1)])
+def test_varsize_frag_pairs_kernel(lib, L, U):
+    """fhc_frag_pairs_varsize (csrc/fragpairs.cu, possible pairs of restriction-fragment mode from prefix sums): the kernel
+    equals its own cells run serially on the host bit for bit (integers; `[3]` is one rounding of an exact 128-bit sum), on
+    small inputs also the pair-by-pair walk (`[1]`, `[7]`, totals exact, `[3]` to 1e-12), and on a chromosome set the walk
+    could not finish in a test (up to 1.5e5 fragments per chromosome: 1e10 pairs without -U)."""
+    from tests.test_host import _varsize_case
+    rng = np.random.default_rng(5 + abs(L) + abs(U))
+    for nchr, nmax, nb, walk in ((3, 600, 20, True), (1, 2, 5, True), (5, 4000, 100, True), (3, 150_000, 100, False)):
+        mids, off, lb, ub = _varsize_case(rng, nchr, nmax, nb, U)
+        res = {}
+        names = ["fhc_frag_pairs_varsize", "fhc_host_frag_pairs_varsize_prefix"] + (["fhc_host_frag_pairs_varsize"] if walk else [])
+        for name in names:
+            p1 = np.full(nb, -2, dtype=np.int64)
+            p7 = np.full(nb, -2, dtype=np.int64)
+            sd = np.zeros(nb, dtype=np.float64)
+            tot = np.zeros(5, dtype=np.int64)
+            args = [dptr(mids), dptr(off), nchr, L, U, dptr(lb), dptr(ub), nb, dptr(p1), dptr(p7), dptr(sd), dptr(tot)]
+            if name == "fhc_frag_pairs_varsize":
+                args.append(None)
+            check(getattr(lib, name)(*args))
+            res[name] = (p1, p7, sd, tot)
+        g, h = res["fhc_frag_pairs_varsize"], res["fhc_host_frag_pairs_varsize_prefix"]
+        for a, b in zip(g, h):
+            assert np.array_equal(a, b)
+        if walk:
+            w = res["fhc_host_frag_pairs_varsize"]
+            assert np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) and np.array_equal(g[3], w[3])
+            assert np.allclose(g[2], w[2], rtol=1e-12, atol=0.0)
+
+
+def test_restriction_fragment_pipeline_with_gpu_possible_pairs(lib, monkeypatch):
+    """-r 0 end to end with the possible pairs from the prefix-sum kernel (FHC_VARSIZE_PAIRS=gpu) against the fixture of the
+    unmodified reference: counts exact, p and q inside the 1e-6 of the spec (x moves by ~1e-13 relative, see fragpairs.cu)."""
+    from tests.util import R0_CASES, load_golden, rel_err
+    monkeypatch.setenv("FHC_VARSIZE_PAIRS", "gpu")
+    from fithic_b200.engine import Engine
+    contacts, frags, biases, st, ref, _ = load_golden(R0_CASES[0])
+    eng = Engine(st, frags, biases)
+    eng.upload_contacts(contacts)
+    outl, stats = eng.new_outlier_state()
+    for passNo, r in enumerate(ref, start=1):
+        got = eng.run_pass(passNo, outl, stats)
+        torch.cuda.synchronize()
+        assert got["N"] == r["N"] and got["T"] == r["T"]
+        assert [int(v) for v in got["bins"]["pairs"]] == [b["pairs"] for b in r["bins"]]
+        assert [int(v) for v in got["bins"]["pairs7"]] == [b["pairs7"] for b in r["bins"]]
+        assert np.allclose(got["x"], r["x"], rtol=1e-12, atol=0.0)
+        assert rel_err(got["p"].cpu().numpy(), r["p"]) <= 1e-6 and rel_err(got["q"].cpu().numpy(), r["q"]) <= 1e-6

@@ -12,6 +12,7 @@ import pytest
 from fithic_b200 import _capi, synth
 from fithic_b200 import io as fio
 from fithic_b200.engine import Settings, calculate_probabilities, fit_spline, frag_pairs, make_bins
+from fithic_b200._capi import check, dptr  # noqa: E402
 from oracle import fithic_oracle as O
 from tests.util import GOLDEN_CASES, REAL_CASES, cut_hist_numpy, load_golden
 
@@ -481,6 +482,69 @@ def test_varsize_frag_pairs_bit_exact_against_reference_fixture(lib):
         x, y = calculate_probabilities(bins, r["N"])
         assert sorted(x) == list(r["x"])
         assert [v for _, v in sorted(zip(x, y))] == list(r["y"])
+
+
+def _varsize_case(rng, nchr, nmax, nb, U):
+    mids, off = [], [0]
+    for _ in range(nchr):
+        n = int(rng.integers(0, nmax))
+        f = np.sort(rng.integers(0, 40_000_000, n)).astype(np.int64)
+        mids.append(f)
+        off.append(off[-1] + n)
+    mids = np.ascontiguousarray(np.concatenate(mids) if mids else np.zeros(0, np.int64))
+    off = np.asarray(off, dtype=np.int64)
+    top = U if U >= 0 else 30_000_000
+    ub = np.sort(rng.choice(np.arange(1000, top), nb, replace=False)).astype(np.int64)
+    lb = np.concatenate([[0], ub[:-1] + 1]).astype(np.int64)
+    return mids, off, lb, ub
+
+
+@pytest.mark.parametrize("L,U", [(-1, -1), (20000, 5_000_000), (0, 200_000), (-1, 1_000_000), (3_000_000, -1)])
+def test_varsize_frag_pairs_prefix_sums_against_the_walk(lib, L, U):
+    """csrc/fragpairs.cu (the cells of the -r 0 possible-pair kernel, run serially on the host) against the pair-by-pair
+    walk of fhc_host_frag_pairs_varsize: `[1]`, `[7]` and all totals exact; `[3]` -- the exact sum rounded once instead of
+    a double accumulated pair by pair -- to 1e-12."""
+    rng = np.random.default_rng(abs(L) * 7 + abs(U))
+    for nchr, nmax, nb in ((3, 600, 20), (1, 2, 5), (4, 1500, 60), (2, 900, 1), (1, 1, 3)):
+        mids, off, lb, ub = _varsize_case(rng, nchr, nmax, nb, U)
+        res = {}
+        for name in ("fhc_host_frag_pairs_varsize", "fhc_host_frag_pairs_varsize_prefix"):
+            p1 = np.full(nb, -3, dtype=np.int64)   # (outlier decrements of a later pass ride in)
+            p7 = np.full(nb, -3, dtype=np.int64)
+            sd = np.zeros(nb, dtype=np.float64)
+            tot = np.zeros(5, dtype=np.int64)
+            check(getattr(lib, name)(dptr(mids), dptr(off), nchr, L, U, dptr(lb), dptr(ub), nb, dptr(p1), dptr(p7), dptr(sd),
+                                     dptr(tot)))
+            res[name] = (p1, p7, sd, tot)
+        a, b = res["fhc_host_frag_pairs_varsize"], res["fhc_host_frag_pairs_varsize_prefix"]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+        assert np.allclose(a[2], b[2], rtol=1e-12, atol=0.0)
+        from fithic_b200.engine import varsize_pairs_in_range
+        assert varsize_pairs_in_range(mids, off, L, U) == int(a[3][0])
+
+
+def test_varsize_frag_pairs_prefix_sums_on_the_reference_fixture(lib):
+    """The same on the bundled HindIII fragments with the reference's own bins: `[1]` and `[7]` as the unmodified reference
+    computed them, `[3]` within 1e-12 of its double accumulation."""
+    from tests.util import R0_CASES
+    contacts, frags, biases, st, ref, _ = load_golden(R0_CASES[0])
+    r = ref[0]
+    nb = len(r["bins"])
+    order = sorted(range(len(frags.chroms)), key=lambda i: frags.chroms[i])
+    order = [i for i in order if frags.n_mappable[i] > 0]
+    mids = np.ascontiguousarray(np.concatenate([np.asarray(frags.mids[i], dtype=np.int64) for i in order]))
+    off = np.zeros(len(order) + 1, dtype=np.int64)
+    np.cumsum([len(frags.mids[i]) for i in order], out=off[1:])
+    lb = np.array([b["lb"] for b in r["bins"]], dtype=np.int64)
+    ub = np.array([b["ub"] for b in r["bins"]], dtype=np.int64)
+    p1, p7, sd, tot = np.zeros(nb, np.int64), np.zeros(nb, np.int64), np.zeros(nb), np.zeros(5, np.int64)
+    check(lib.fhc_host_frag_pairs_varsize_prefix(dptr(mids), dptr(off), len(order), st.L, st.U, dptr(lb), dptr(ub), nb,
+                                                 dptr(p1), dptr(p7), dptr(sd), dptr(tot)))
+    assert int(tot[0]) == r["possibleIntraInRangeCount"]
+    assert [int(v) for v in p1] == [b["pairs"] for b in r["bins"]]
+    assert [int(v) for v in p7] == [b["pairs7"] for b in r["bins"]]
+    want = np.array([b["sumdist"] for b in r["bins"]])
+    assert np.allclose(sd, want, rtol=1e-12, atol=0.0), np.max(np.abs(sd - want) / want)
 
 
 def test_refapi_generate_fragpairs_restriction_fragments(lib, tmp_path):

@@ -256,3 +256,48 @@ def test_pool_runs_every_job_exactly_once(lib):
         for jobs in (1, 3, 40):
             ms = lib.fhc_host_pool_selftest(threads, jobs, 5, ctypes.byref(n))
             assert ms >= 0 and 1 <= n.value <= 64  # (the pool is shared: workers started by earlier calls join in)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_host_stage_bins_on_ragged_histograms(lib, threads):
+    """Phase 1 of fhc_host_stage (observed distances compacted in chunks on the pool, bins by bisection on the running sum of
+    the counts) against fhc_host_make_bins' entry-by-entry loop on numpy-compacted input: histograms with long empty
+    stretches, single distances that fill a bin on their own, distances seen only through the bitmap, lengths around the
+    chunk size, and the tail the last closed bin leaves out."""
+    frags = synth.fragments_for(["chrA"], np.array([50_000_000]), 1000)
+    rng = np.random.default_rng(11 + threads)
+    for D in (1, 7, 4095, 4096, 4097, 12289, 30011):
+        for fill in (1.0, 0.3, 0.01):
+            hist = rng.integers(1, 1000, D).astype(np.uint64)
+            hist[rng.random(D) >= fill] = 0
+            if D > 100:
+                hist[rng.integers(0, D, 3)] = 500_000  # more than a bin's share in one distance
+            if hist.sum() == 0:
+                hist[0] = 5
+            nw = (D + 31) // 32
+            bits = (rng.random(D) < 0.05) & (hist == 0)
+            present = np.packbits(bits, bitorder="little")
+            present = np.concatenate([present, np.zeros(4 * nw - len(present), np.uint8)]).view(np.uint32)
+            for use_bitmap in (False, True):
+                scal = np.zeros(_capi.N_SCALARS, dtype=np.uint64)
+                scal[_capi.S_INTRA_INRANGE_SUM] = int(hist.sum())
+                scal[_capi.S_NONPOS_LINES] = 1 if use_bitmap else 0
+                for nbins in (1, 10, 100):
+                    io, keep = _stage_io(lib, hist, scal, present if use_bitmap else None, 1000, nbins, frags, 0, -1, 0, threads)
+                    seen = np.nonzero((hist != 0) | (bits if use_bitmap else False))[0]
+                    dists = (seen * 1000).astype(np.int64)
+                    sums = hist[seen].astype(np.int64)
+                    try:
+                        want = make_bins(lib, dists, sums, nbins, int(hist.sum()))
+                    except _capi.FithicB200Error:
+                        # zero-count distances behind the last count: every one of them would close a bin of its own
+                        # (desired == 0); both refuse to write past noOfBins bins
+                        with pytest.raises(_capi.FithicB200Error, match="more than noOfBins"):
+                            check(lib.fhc_host_stage(ctypes.byref(io), 1))
+                        continue
+                    check(lib.fhc_host_stage(ctypes.byref(io), 1))
+                    v = _views(io, keep, nbins)
+                    assert np.array_equal(v["dists"], dists) and np.array_equal(v["sums"], sums)
+                    assert int(io.nb) == want["n"]
+                    for k in ("lb", "ub", "sumcc"):
+                        assert np.array_equal(v[k], want[k][:want["n"]]), (D, fill, nbins, k)
