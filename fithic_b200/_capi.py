@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libfithic_b200.so")
 
 FHC_OK = 0
 FHC_E_INVALID, FHC_E_CUDA, FHC_E_RANGE, FHC_E_WORKSPACE = -1, -2, -3, -4
-FHC_ABI_VERSION = 8
+FHC_ABI_VERSION = 9
 (S_INTRA_INRANGE_SUM, S_INTRA_ALL_SUM, S_INTER_ALL_SUM, S_INTER_ALL_COUNT, S_MAX_COUNT, S_OFFGRID,
  S_INTRA_INRANGE_LINES, S_INTRA_ALL_LINES, S_NONPOS_LINES) = range(9)
 N_SCALARS = 9
@@ -61,6 +61,7 @@ _SIGNATURES = {
     "fhc_comm_create": (ctypes.c_int, [c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "fhc_comm_connect": (ctypes.c_int, [c_void_p, c_void_p]),
     "fhc_comm_allreduce_u64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "fhc_comm_allreduce_u64_mirror": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_comm_allgather": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fhc_comm_world": (c_int32, [c_void_p]),
     "fhc_comm_rank": (c_int32, [c_void_p]),

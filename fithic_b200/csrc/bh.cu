@@ -1497,9 +1497,20 @@ extern "C" int fhc_bh_dist_cut(fhc_comm *comm, const double *p, int64_t n, doubl
     const int rc = fhc_comm_allreduce_u64(comm, reinterpret_cast<uint64_t *>(summed), kCutBuckets, stream);
     if (rc != FHC_OK) return rc;
     FHC_CUDA(cudaFuncSetAttribute(bh_cut_from_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCutFindSmem));
-    bh_cut_from_sum_kernel<<<1, 1024, kCutFindSmem, st>>>(summed, local, T, p_cut0, info);
+    // pinned host memory is device accessible (unified addressing): the kernel stores its three words there itself and the
+    // device-to-host copy of 64 bytes, a copy-engine launch of its own, is saved.  Anything else gets the copy.
+    bool direct = false;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, info_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer == info_host)
+            direct = true;
+        else
+            cudaGetLastError();
+    }
+    bh_cut_from_sum_kernel<<<1, 1024, kCutFindSmem, st>>>(summed, local, T, p_cut0, direct ? reinterpret_cast<u64 *>(info_host) : info);
     FHC_LAUNCH_CHECK("bh_cut_from_sum_kernel");
-    FHC_CUDA(cudaMemcpyAsync(info_host, info, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (!direct) FHC_CUDA(cudaMemcpyAsync(info_host, info, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     FHC_CUDA(cudaStreamSynchronize(st));
     return FHC_OK;
 }

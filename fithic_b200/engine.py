@@ -31,7 +31,7 @@ class Settings:
     interOnly: bool = False
     allReg: bool = False
     biasLowerBound: float = 0.5
-    biasUpperBound: float = 2.0
+    biasUpperBound: float = 2  # (an int like the reference's default: the log prints it)
     noOfPasses: int = 1
 
     @property
@@ -366,6 +366,12 @@ class Engine:
             if self.st.resolution == 0 and self.st.U >= 0:
                 mx = min(mx, self.st.U)  # on the 1 bp grid only in-range distances need a slot
             self.D = mx // self.grid + 2
+            if self.st.resolution == 0 and self.D > (1 << 27):
+                # the reference keeps its distances in a dict; here every bp of the longest distance is a slot of the
+                # histogram and of the lookup table (8 B each, plus their host copies per pass)
+                import warnings
+                warnings.warn("restriction-fragment mode without -U: the distance axis has %d one-bp slots (%.1f GB per "
+                              "table, moved to the host once per pass); give -U to bound it" % (self.D, self.D * 8 / 1e9))
             if self.dist is not None:
                 self.D = self.dist.max_int(self.D)  # the histogram is all-reduced: every rank needs the same length
         return self.D
@@ -430,10 +436,18 @@ class Engine:
             else:
                 skip_limit = self.n if first_dup == _U64_MAX else first_dup
         hist_d, present_d, scal_d = self.hist_distance(skip, skip_limit)
-        if self.dist is not None:  # exchange 1: [hist | totals | rank slots] summed over the GPUs in one collective
-            self.dist.allreduce_k1(self._ws["k1buf"][:self.D + scal_d.numel()])
         native = (st.resolution > 0 and self.D <= self.NATIVE_STAGE_MAX_SLOTS
                   and os.environ.get("FHC_HOST_STAGE", "native") != "legacy")
+        self._k1_on_host = False
+        if self.dist is not None:  # exchange 1: [hist | totals | rank slots] summed over the GPUs in one collective
+            mirror = None
+            if native:  # ... whose reducing kernel also writes the sums into the host stage's pinned buffer
+                hs = getattr(self, "_stage", None)
+                if hs is None:
+                    hs = self._stage = _HostStage(self)
+                hs.ensure(self.D)
+                mirror = hs.k1.data_ptr()
+            self._k1_on_host = self.dist.allreduce_k1(self._ws["k1buf"][:self.D + scal_d.numel()], host_mirror=mirror)
         tables = self._tables_native if native else self._tables_legacy
         out, lut, lbeta, ev = tables(passNo, outl if passNo > 1 else None, t0)
         N, obsInterAllCount, obsInterAllSum = out["N"], out["observedInterAllCount"], out["observedInterAllSum"]
@@ -547,7 +561,8 @@ class Engine:
         else:
             io.pairs_rank, io.pairs_world, io.shm = 0, 1, None
         nk = D + _capi.N_SCALARS + slots
-        check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
+        if not getattr(self, "_k1_on_host", False):
+            check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
         if hs.event is None:
             ev = ctypes.c_void_p()
             check(lib.fhc_event_create(ctypes.byref(ev)))

@@ -24,6 +24,91 @@ from . import io as fio
 from .engine import Engine, Settings
 
 
+def write_log(logfile, r, st, frags, bias_log, table_path):
+    """${lib}.fithic.log with the reference's sections and wording (re-opened 'w' in every pass like the reference,
+    fithic/fithic.py:444; sections :464-468, :550-552, :563-569, :648-650 / :737-739, :782-791, :844-846, :915-917,
+    :926-928, :1228-1231).  The bias lines (:812-815, :834) sit behind the fragment section in the first pass; a later pass
+    re-opens the log and does not read the biases again, so its log has none -- as in the reference."""
+    res, L, U = st.resolution, st.L, st.U
+    dists = r.get("dists")
+    with open(logfile, "w") as log:
+        log.write("\n\nInteractions file read successfully\n")
+        log.write("------------------------------------------------------------------------------------\n")
+        log.write("Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" % (r["observedIntraInRangeLines"], r["N"]))
+        log.write("Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" % (r["observedIntraAllLines"], r["observedIntraAllSum"]))
+        log.write("Observed, Inter-chr all: pairs= %d\t totalCount= %d\n" % (r["observedInterAllCount"], r["observedInterAllSum"]))
+        if dists is not None and len(dists):
+            log.write("Range of observed genomic distances [%s %s]\n" % (int(dists[0]), int(dists[-1])))
+        else:
+            log.write("Range of observed genomic distances [%s %s]\n" % (float("inf"), 0))
+        log.write("\n")
+        log.write("Making equal occupancy bins\n")
+        log.write("------------------------------------------------------------------------------------\n")
+        log.write("Observed intra-chr read counts in range\t%r\nDesired number of contacts per bin\t%r,\nNumber of bins\t%r\n"
+                  % (r["N"], r["N"] / st.noOfBins, st.noOfBins))
+        log.write("Equal occupancy bins generated\n")
+        log.write("\n")
+        log.write(("Looping through" if res else "Enumerating") + " all possible fragment pairs in-range\n")
+        log.write("------------------------------------------------------------------------------------\n")
+        order = [i for i in sorted(range(len(frags.chroms)), key=lambda i: frags.chroms[i]) if frags.n_mappable[i] > 0]
+        noOfFrags = int(sum(int(frags.n_mappable[i]) for i in order))
+        has_bins = r["bins"]["n"] > 0
+        min_possible = float("inf")
+        for i in order:
+            n = int(frags.n_mappable[i])
+            if res:  # :613-643: npairs = n - k per distance step in range, counted twice when bins exist
+                stop = int(float(frags.max_mid[i]) - res / 2.0 + 1.0)
+                nsteps = (stop + res - 1) // res if stop > 0 else 0
+                k0 = 0 if L <= 0 else (L + res - 1) // res
+                k1 = nsteps - 1 if U < 0 else min(nsteps - 1, U // res)
+                per_chr = 0
+                if k1 >= k0:
+                    cnt = k1 - k0 + 1
+                    per_chr = (n * cnt - (k0 + k1) * cnt // 2) * (2 if has_bins else 1)
+                    min_possible = min(min_possible, k0 * res)
+            else:
+                from .engine import varsize_pairs_in_range
+                f = np.sort(np.asarray(frags.mids[i], dtype=np.int64))
+                per_chr = varsize_pairs_in_range(f, np.array([0, len(f)], dtype=np.int64), L, U)
+                if per_chr:  # the closest pair in range (:713)
+                    idx = np.arange(len(f), dtype=np.int64)
+                    lo = np.maximum(np.searchsorted(f, f + max(L, 0), side="left"), idx + 1)
+                    ok = lo < len(f)
+                    d = f[lo[ok]] - f[ok]
+                    d = d[d <= U] if U >= 0 else d
+                    if len(d):
+                        min_possible = min(min_possible, int(d.min()))
+            log.write("Chromosome %r,\t%d mappable fragments, \t%d possible intra-chr fragment pairs in range,\t%d possible "
+                      "inter-chr fragment pairs\n" % (frags.chroms[i], n, per_chr, (noOfFrags - n) * n))
+        log.write("Number of all fragments= %s\n" % noOfFrags)
+        log.write("Possible, Intra-chr in range: pairs= %s \n" % r["possibleIntraInRangeCount"])
+        log.write("Possible, Intra-chr all: pairs= %s \n" % r["possibleIntraAllCount"])
+        log.write("Possible, Inter-chr all: pairs= %s \n" % r["possibleInterAllCount"])
+        log.write("Desired genomic distance range   [%d %s] \n" % (L if L > 0 else 0, U if U >= 0 else float("inf")))
+        if res:  # :604: the largest maxFrag = max(mid) - res / 2 over the chromosomes
+            max_possible = max([float(frags.max_mid[i]) - res / 2.0 for i in order] or [0])
+        else:
+            max_possible = r.get("maxPossibleGenomicDist", 0)
+        log.write("Range of possible genomic distances  [%s  %d] \n"
+                  % ("%d" % min_possible if min_possible != float("inf") else "inf", max_possible))
+        pia = r["possibleIntraAllCount"]
+        log.write("Baseline intrachromosomal probability is %s \n" % (1.0 / pia if pia > 0 else 0))
+        log.write("Interchromosomal probability is %s \n" % (r["interChrProb"] if r["interChrProb"] else 0))
+        for line in bias_log:
+            log.write(line + "\n")
+        if bias_log:
+            log.write("\n")
+        log.write("\nCalculating probability means and standard deviations of contact counts\n")
+        log.write("------------------------------------------------------------------------------------\n")
+        log.write("Means and error written to %s\n" % table_path)
+        log.write("\n")
+        log.write("\nFitting a univariate spline to the probability means\n")
+        log.write("------------------------------------------------------------------------------------\n")
+        log.write("Spline successfully fit\n")
+        log.write("\n")
+        log.write("\n")
+
+
 def parse_args(args):
     parser = argparse.ArgumentParser(description="Check the help flag")
     parser.add_argument("-i", "--interactions", dest="intersfile", required=True,
@@ -242,22 +327,7 @@ def run(contacts_path, frags_path, outdir, st, libName, bias_path=None, quiet=Fa
         suffix = ".res" + str(st.resolution) if st.resolution else ""  # -r 0 omits the part (:851, :1171)
         tab = os.path.join(outdir, libName + ".fithic_pass" + str(passNo) + suffix + ".txt")
         if rank == 0:
-            # log (re-opened 'w' in every pass like the reference, fithic/fithic.py:444); the reference also lists every
-            # bin and chromosome here, this log keeps the totals
-            with open(logfile, "w") as log:
-                log.write("\n\nInteractions file read successfully\n")
-                log.write("------------------------------------------------------------------------------------\n")
-                log.write("Observed, Intra-chr in range: pairs= %d\t totalCount= %d\n" %
-                          (r["observedIntraInRangeLines"], r["N"]))
-                log.write("Observed, Intra-chr all: pairs= %d\t totalCount= %d\n" %
-                          (r["observedIntraAllLines"], r["observedIntraAllSum"]))
-                log.write("Observed, Inter-chr all: pairs= %d\t totalCount= %d\n" %
-                          (r["observedInterAllCount"], r["observedInterAllSum"]))
-                log.write("\nPossible, Intra-chr in range: pairs= %d\n" % r["possibleIntraInRangeCount"])
-                log.write("Possible, Inter-chr all: pairs= %s\n" % r["possibleInterAllCount"])
-                for line in bias_log:
-                    log.write(line + "\n")
-                log.write("Spline successfully fit\n\n\n")
+            write_log(logfile, r, st, frags, bias_log if passNo == 1 else [], tab)
             # bin table
             say("Writing %s" % tab)
             with open(tab, "w") as out:

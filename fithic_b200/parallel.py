@@ -1,12 +1,12 @@
-"""Multi-GPU execution: one process per GPU, contacts sharded by chromosome, torch.distributed (NCCL over NVLink /
-NVSwitch) for the two exchange steps of a spline pass.
+"""Multi-GPU execution: one process per GPU, contacts sharded by chromosome, torch.distributed (NCCL) as the bootstrap and fall-back, the library's own
+collectives over CUDA IPC peer windows (csrc/comm.cu, NVLink / NVSwitch) for the two exchange steps of a spline pass.
 
   exchange 1  ONE all-reduce (sum) of [distance histogram | observed totals | one slot per rank for the largest count]
               (<= 400 kB, latency bound).  Every rank then runs the identical host binning / spline fit on identical
               inputs, so tables are bit-identical everywhere.
-  exchange 2  global BH: ONE all-gather of every rank's 32768-bucket value histogram; a kernel sums them, finds the cut
-              above which every q is 1.0 and each rank's number of p-values below it, and ONE small read-back tells the
-              host how to go on: nothing below the cut (sparse maps without signal) -> done; few -> all-gather of the
+  exchange 2  global BH: ONE all-reduce of the ranks' 32768-bucket value histograms; a kernel finds the cut above which
+              every q is 1.0 and the number of p-values below it (on all ranks, on this one), and ONE small read-back tells
+              the host how to go on: nothing below the cut (sparse maps without signal) -> done; few -> all-gather of the
               survivors, every rank ranks the small global set itself; many -> the p-values below the cut are
               range-partitioned by value so that rank r ranks one contiguous key range:
               sample keys -> all-gather -> splitters; count per part -> all-gather -> offsets; scatter into send
@@ -246,14 +246,20 @@ class DistCtx:
             self.shm = None
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
-    def allreduce_k1(self, fused):
+    def allreduce_k1(self, fused, host_mirror=None):
         """Sum K1's [hist | totals | rank slots] over the ranks, in place: one collective, no host synchronisation (the
-        largest count travels in the rank slots, see fhc_hist_distance)."""
+        largest count travels in the rank slots, see fhc_hist_distance).  host_mirror: address of pinned host memory that
+        is to receive the summed words as well; returns True when it did (the library's own collective writes it from the
+        reducing kernel), False when the caller still has to copy."""
         n = fused.numel()
         if self.comm is not None and n % 2 == 0 and 8 * n <= self.comm_slot_bytes and fused.dtype == torch.int64:
+            if host_mirror:
+                check(self.ops.lib.fhc_comm_allreduce_u64_mirror(self.comm, dptr(fused), n, host_mirror, self.ops._stream()))
+                return True
             check(self.ops.lib.fhc_comm_allreduce_u64(self.comm, dptr(fused), n, self.ops._stream()))
         else:
             dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
+        return False
 
     def or_present(self, present):
         """OR the 'distance seen with counts <= 0' bitmaps of all ranks, in place.  Only needed when the summed totals

@@ -16,7 +16,7 @@ if [ "$N" = "1" ]; then
   exit 0
 fi
 if [ "$N" = "2" ]; then
-  timeout 1200 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2k_pytest_multi.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2k_pytest_multi.log 2>&1
   echo "pytest rc $?" >> gpurun_out/r2k_pytest_multi.log
   tail -4 gpurun_out/r2k_pytest_multi.log
   timeout 600 $TR --master-port 29531 scripts/multi_gpu_check.py > gpurun_out/r2k_multi_gpu_check_n$N.log 2>&1

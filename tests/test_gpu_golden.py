@@ -1,4 +1,5 @@
 """GPU parity against fixtures captured from the UNMODIFIED reference (tests/golden/, no oracle in the loop)."""
+import os
 import gzip
 
 import numpy as np
@@ -6,7 +7,7 @@ import pytest
 
 from fithic_b200 import synth
 from tests.test_gpu_pipeline import run_engine
-from tests.util import GOLDEN_CASES, R0_CASES, REAL_CASES, compare_pass, load_golden, load_kat
+from tests.util import GOLDEN_CASES, GOLDEN_DIR, R0_CASES, REAL_CASES, compare_pass, load_golden, load_kat
 
 torch = pytest.importorskip("torch")
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("pval_impl")]
@@ -68,6 +69,12 @@ def test_cli_output_file_matches_reference(lib, name, tmp_path):
     assert sig.exists()
     assert (tmp_path / "out" / ("%s.fithic_pass%d.res%d.txt" % (name, npass, st.resolution))).exists()
     assert (tmp_path / "out" / (name + ".fithic.log")).exists()
+    # the log: the reference's own, line for line (tests/golden/make_golden_log.py)
+    with open(tmp_path / "out" / (name + ".fithic.log")) as f:
+        got_log = f.read().replace(str(tmp_path / "out"), "OUT")
+    with open(os.path.join(GOLDEN_DIR, name + ".fithic.log")) as f:
+        want_log = f.read()
+    assert got_log.splitlines() == want_log.splitlines()
     with gzip.open(sig, "rt") as f:
         lines = f.readlines()
     assert len(lines) - 1 == extra["sig_nrows"]
