@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(256) bh_compact_kernel(const double *__restric
                     if (i0 + k < n) q[i0 + k] = qv[k];
             }
         }
+        // nothing of these 2048 values is ranked (most tiles of a sparse map once the cut is tightened): no scan, no atomic
+        if (!__syncthreads_or(mine)) continue;
         int inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -690,11 +692,13 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
             const bool valid = li < tile_n;
             const u32 d = valid ? ((u32)(key[r] >> shift) & 255u) : 256u;
             const u32 m = __match_any_sync(0xffffffffu, d);
+            // the first lane of every group of equal digits advances the warp's own counter and hands the old value to its
+            // group: one shared-memory atomic and one shuffle per round, and no load that waits for the previous round's
+            // store -- the rounds' atomics are in flight together (same-address atomics of one warp keep program order)
+            const int leader = __ffs(m) - 1;
             u32 pre = 0;
-            if (valid) pre = whist[warp][d];
-            __syncwarp();
-            if (valid && lane == (__ffs(m) - 1)) whist[warp][d] = pre + __popc(m);
-            __syncwarp();
+            if (valid && lane == leader) pre = atomicAdd(&whist[warp][d], (u32)__popc(m));
+            pre = __shfl_sync(0xffffffffu, pre, leader);
             rank[r] = (unsigned short)(pre + __popc(m & lt));
         }
         __syncthreads();
