@@ -5,6 +5,9 @@ mkdir -p gpurun_out
 nproc
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 if [ "$N" = "1" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2k_pytest_gpu.log 2>&1
+  echo "pytest rc $?" >> gpurun_out/r2k_pytest_gpu.log
+  tail -4 gpurun_out/r2k_pytest_gpu.log
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
       -k regex:"pval_|hist_distance|bh_|radix_|fill_f64|lbeta_|outlier|digest|gather_ne|mid_range|scatter" -c 400 --csv \
       --log-file gpurun_out/launches_r02_final.csv \
