@@ -10,8 +10,8 @@ for r in rows[hi+1:]:
     v=float(r[iv].replace(',','')); u=r[iu]
     ms = v/1e6 if u in ('ns','nsecond') else (v/1e3 if u in ('us','usecond') else v)
     a=acc.setdefault(name,[0,0.0]); a[0]+=1; a[1]+=ms; tot+=ms; n+=1
-out=[open(src).read().split("==PROF==")[0].strip().splitlines()[0] if False else "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --extras \"\"",
-     "(B200, 300 M contacts in file order, 1 GPU; the first 400 launches of the command: warm-up passes, timed passes and the e2e leg; cold-cache serialised times: compare SHARES)",
+out=['ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pval_|hist_distance|bh_|radix_|fill_f64|lbeta_|outlier|digest|gather_ne|mid_range|scatter" -c 400 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --extras ""',
+     "(B200, 300 M contacts in file order, 1 GPU; every launch of a library kernel in the command: warm-up passes, 2 timed passes, the digest and the e2e leg, whose passes launch K3 slice by slice; cold-cache serialised times: compare SHARES)",
      "launches %d, total %.3f ms" % (n, tot)]
 for k in sorted(acc, key=lambda k:-acc[k][1]):
     out.append("%-40s launches %4d total_ms %9.3f share %5.1f%%" % (k[:40], acc[k][0], acc[k][1], 100*acc[k][1]/tot))
