@@ -721,20 +721,36 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
                 *mine = (cnt << 2) | kStatusPrefix;
             } else {
                 *mine = (cnt << 2) | kStatusAggregate;
-                for (long long t = (long long)tile - 1; t >= 0; --t) {
-                    const volatile u32 *theirs = status + (size_t)t * kRadix + threadIdx.x;
-                    u32 v = *theirs;
-                    int spins = 0;
-                    while ((v & 3u) == 0u) {
-                        if (++spins > kLookbackSpinLimit) {
-                            atomicExch(err, 1u);
-                            v = kStatusPrefix;
-                            break;
+                // The status words of the kLookAhead tiles before the current position are loaded together (their latencies
+                // overlap: the walk is a chain of L2 round trips otherwise, and with ~450 tiles in flight it is ~100 steps
+                // long) and consumed in order up to the first inclusive prefix; what was loaded beyond it is dropped.
+                constexpr int kLookAhead = 8;
+                bool done = false;
+                for (long long t = (long long)tile - 1; t >= 0 && !done; t -= kLookAhead) {
+                    u32 v[kLookAhead];
+#pragma unroll
+                    for (int k = 0; k < kLookAhead; ++k)
+                        v[k] = t - k >= 0 ? (u32)status[(size_t)(t - k) * kRadix + threadIdx.x] : (u32)kStatusPrefix;  // before tile 0: nothing
+#pragma unroll
+                    for (int k = 0; k < kLookAhead; ++k) {
+                        if (done) continue;
+                        u32 x = v[k];
+                        if ((x & 3u) == 0u) {  // not published yet: wait for this one
+                            const volatile u32 *theirs = status + (size_t)(t - k) * kRadix + threadIdx.x;
+                            int spins = 0;
+                            x = *theirs;
+                            while ((x & 3u) == 0u) {
+                                if (++spins > kLookbackSpinLimit) {
+                                    atomicExch(err, 1u);
+                                    x = kStatusPrefix;
+                                    break;
+                                }
+                                x = *theirs;
+                            }
                         }
-                        v = *theirs;
+                        excl += x >> 2;
+                        if ((x & 3u) == kStatusPrefix) done = true;
                     }
-                    excl += v >> 2;
-                    if ((v & 3u) == kStatusPrefix) break;
                 }
                 *mine = ((excl + cnt) << 2) | kStatusPrefix;
             }
