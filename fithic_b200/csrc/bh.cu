@@ -654,15 +654,18 @@ constexpr int kLookbackSpinLimit = 1 << 22;
 // tile and all tiles before it.  Tiles are handed out by an atomic counter, so every tile before a running one has been
 // claimed by a running CTA and publishes its own count without waiting for anybody: the look-back cannot dead-lock.  The
 // spin is bounded all the same (err is raised instead of hanging the GPU).
-__global__ void __launch_bounds__(kSortThreads, 3)
+// kT threads per CTA, kSortTile / kT keys per thread
+template <int kT>
+__global__ void __launch_bounds__(kT, kT == 512 ? 3 : 3)
 radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u64 *__restrict__ keys_out,
                       u32 *__restrict__ vals_out, const u64 *d_n, int shift, const u32 *__restrict__ gbase_pass,
                       volatile u32 *status, u32 *tile_counter, u32 *err) {
     extern __shared__ __align__(16) unsigned char dsmem[];
     u64 *skeys = reinterpret_cast<u64 *>(dsmem);                                  // [kSortTile]
     u32 *svals = reinterpret_cast<u32 *>(skeys + kSortTile);                      // [kSortTile]
-    u32(*whist)[kRadix] = reinterpret_cast<u32(*)[kRadix]>(svals + kSortTile);    // [kSortWarps][kRadix]
-    u32 *tile_off = reinterpret_cast<u32 *>(whist + kSortWarps);                  // [kRadix]
+    u32(*whist)[kRadix] = reinterpret_cast<u32(*)[kRadix]>(svals + kSortTile);    // [kW][kRadix]
+    constexpr int kW = kT / 32, kI = kSortTile / kT;
+    u32 *tile_off = reinterpret_cast<u32 *>(whist + kW);                          // [kRadix]
     u32 *gpos = tile_off + kRadix;                                                // [kRadix]
     u32 *sw = gpos + kRadix;                                                      // [33] + the tile number
     const long long n = (long long)*d_n;
@@ -675,20 +678,20 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
         if (tile >= ntiles) break;
         const long long base = (long long)tile * kSortTile;
         const int tile_n = (int)((n - base) < kSortTile ? (n - base) : kSortTile);
-        for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&whist[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < kW * kRadix; i += kT) (&whist[0][0])[i] = 0;
         __syncthreads();
 
-        u64 key[kSortIPT];
-        unsigned short rank[kSortIPT];
+        u64 key[kI];
+        unsigned short rank[kI];
         const u32 lt = (1u << lane) - 1u;
 #pragma unroll
-        for (int r = 0; r < kSortIPT; ++r) {  // warp `warp` owns [warp*512, warp*512+512) of the tile, 32 at a time
-            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        for (int r = 0; r < kI; ++r) {  // warp `warp` owns 32 * kI consecutive keys of the tile, 32 at a time
+            const int li = warp * (32 * kI) + r * 32 + lane;
             key[r] = li < tile_n ? keys_in[base + li] : ~0ull;
         }
 #pragma unroll
-        for (int r = 0; r < kSortIPT; ++r) {
-            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        for (int r = 0; r < kI; ++r) {
+            const int li = warp * (32 * kI) + r * 32 + lane;
             const bool valid = li < tile_n;
             const u32 d = valid ? ((u32)(key[r] >> shift) & 255u) : 256u;
             const u32 m = __match_any_sync(0xffffffffu, d);
@@ -703,11 +706,12 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
         }
         __syncthreads();
         // per digit (thread = digit): exclusive prefix over warps, tile total
+        const bool digit_thread = kT == kRadix || threadIdx.x < kRadix;
         u32 cnt = 0;
-        {
+        if (digit_thread) {
             const int d = threadIdx.x;
 #pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
+            for (int w = 0; w < kW; ++w) {
                 const u32 c = whist[w][d];
                 whist[w][d] = cnt;
                 cnt += c;
@@ -715,7 +719,7 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
         }
         // publish this tile's count of the digit, then add up the tiles before it
         u32 excl = 0;
-        {
+        if (digit_thread) {
             volatile u32 *mine = status + (size_t)tile * kRadix + threadIdx.x;
             if (tile == 0) {
                 *mine = (cnt << 2) | kStatusPrefix;
@@ -756,13 +760,15 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
             }
         }
         u32 total;
-        const u32 ex = block_exclusive_scan_u32(cnt, sw, total);
-        tile_off[threadIdx.x] = ex;
-        gpos[threadIdx.x] = gbase_pass[threadIdx.x] + excl;
+        const u32 ex = block_exclusive_scan_u32(cnt, sw, total);  // (threads beyond the digits add 0 behind them)
+        if (digit_thread) {
+            tile_off[threadIdx.x] = ex;
+            gpos[threadIdx.x] = gbase_pass[threadIdx.x] + excl;
+        }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kSortIPT; ++r) {
-            const int li = warp * (32 * kSortIPT) + r * 32 + lane;
+        for (int r = 0; r < kI; ++r) {
+            const int li = warp * (32 * kI) + r * 32 + lane;
             if (li < tile_n) {
                 const u32 d = (u32)(key[r] >> shift) & 255u;
                 const u32 pos = tile_off[d] + whist[warp][d] + rank[r];
@@ -772,8 +778,8 @@ radix_onesweep_kernel(const u64 *__restrict__ keys_in, const u32 *__restrict__ v
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kSortIPT; ++r) {
-            const int i = r * kSortThreads + threadIdx.x;
+        for (int r = 0; r < kI; ++r) {
+            const int i = r * kT + threadIdx.x;
             if (i < tile_n) {
                 const u64 k = skeys[i];
                 const u32 d = (u32)(k >> shift) & 255u;
@@ -1030,14 +1036,20 @@ static int sort_pairs_onesweep(u64 *keys_a, u32 *vals_a, u64 *keys_b, u32 *vals_
         FHC_LAUNCH_CHECK("radix_digit_scan_kernel");
     }
     FHC_CUDA(cudaMemsetAsync(os + kOsCounter, 0, (kOsWords - kOsCounter) * sizeof(u32), st));
-    FHC_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDownsweepSmem));
+    // 512 threads x 8 keys (48 warps per SM at 40 registers) measured the same 0.18 ms per pass as 256 x 16, and so did nine
+    // ballots in place of MATCH.ANY: a tile is a chain of exposed latencies (claim, key load, look-back, value load) between
+    // barriers, and three CTAs per SM do not cover them
+    constexpr int kOsThreads = 256;
+    constexpr size_t kOsSmem = kSortTile * (sizeof(unsigned long long) + sizeof(unsigned int)) +
+                               ((kOsThreads / 32) * kRadix + 2 * kRadix + 36) * sizeof(unsigned int);
+    FHC_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<kOsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOsSmem));
     u64 *kin = keys_a, *kout = keys_b;
     u32 *vin = vals_a, *vout = vals_b;
     int in_a = 1;
     for (int pass = 0; pass < 8; ++pass) {
         if (skip != nullptr && skip[pass]) continue;
         FHC_CUDA(cudaMemsetAsync(ws.counts, 0, (size_t)ws.ntiles * kRadix * sizeof(u32), st));
-        radix_onesweep_kernel<<<sort_grid(ws.ntiles, 3), kSortThreads, kDownsweepSmem, st>>>(
+        radix_onesweep_kernel<kOsThreads><<<sort_grid(ws.ntiles, 3), kOsThreads, kOsSmem, st>>>(
             kin, vin, kout, vout, d_n, pass * 8, os + kOsBase + pass * kRadix, ws.counts, os + kOsCounter + pass, os + kOsErr);
         FHC_LAUNCH_CHECK("radix_onesweep_kernel");
         u64 *tk = kin; kin = kout; kout = tk;
