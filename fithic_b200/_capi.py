@@ -61,7 +61,6 @@ _SIGNATURES = {
     "fhc_comm_create": (ctypes.c_int, [c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "fhc_comm_connect": (ctypes.c_int, [c_void_p, c_void_p]),
     "fhc_comm_allreduce_u64": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "fhc_comm_allreduce_u64_mirror": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "fhc_comm_allgather": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fhc_comm_world": (c_int32, [c_void_p]),
     "fhc_comm_rank": (c_int32, [c_void_p]),

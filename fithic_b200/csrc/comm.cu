@@ -88,12 +88,11 @@ __device__ __forceinline__ void comm_wait(unsigned char *win, int world, int par
 }
 
 // reduce: data[i] = sum over ranks of slot r [i]  (uint64, wrap-around), reading the local window around L1; the loads of
-// eight ranks are in flight together.  mirror (nullable): a second copy of the result, e.g. pinned host memory -- the
-// caller's device-to-host copy of a small buffer costs more than these stores.
+// eight ranks are in flight together.  (Also writing the sums into pinned host memory from here, to save the caller's
+// device-to-host copy, was measured at 8 GPUs: the 8-byte stores over PCIe cost the kernel more than the copy engine takes.)
 __global__ void __launch_bounds__(256) comm_sum_u64_kernel(unsigned char *win, int world, long long slot_bytes, int parity,
                                                           unsigned long long epoch, unsigned long long *__restrict__ data,
-                                                          unsigned long long *__restrict__ mirror, long long n,
-                                                          unsigned int *err) {
+                                                          long long n, unsigned int *err) {
     comm_wait(win, world, parity, epoch, err);
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         unsigned long long s = 0;
@@ -108,7 +107,6 @@ __global__ void __launch_bounds__(256) comm_sum_u64_kernel(unsigned char *win, i
             for (int k = 0; k < 8; ++k) s += r0 + k < world ? v[k] : 0ull;
         }
         data[i] = s;
-        if (mirror != nullptr) mirror[i] = s;
     }
 }
 
@@ -205,9 +203,8 @@ static int comm_push(fhc::Comm &c, const void *src, int64_t bytes, cudaStream_t 
     return FHC_OK;
 }
 
-// data[i] (uint64, n of them, n even) <- sum over all ranks, in place; asynchronous on `stream`.  host_mirror (nullable):
-// device-accessible (pinned) host memory that receives the same n words from the reducing kernel.
-static int comm_allreduce(fhc_comm *comm, uint64_t *data, int64_t n, uint64_t *host_mirror, void *stream) {
+// data[i] (uint64, n of them, n even) <- sum over all ranks, in place; asynchronous on `stream`
+extern "C" int fhc_comm_allreduce_u64(fhc_comm *comm, uint64_t *data, int64_t n, void *stream) {
     using namespace fhc;
     FHC_REQUIRE(comm && data && n > 0 && (n & 1) == 0, FHC_E_INVALID, "fhc_comm_allreduce_u64: need an even number of words");
     Comm &c = comm->c;
@@ -219,25 +216,9 @@ static int comm_allreduce(fhc_comm *comm, uint64_t *data, int64_t n, uint64_t *h
     int blocks = (int)((n + 255) / 256);
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     comm_sum_u64_kernel<<<blocks, 256, 0, st>>>(c.window, c.world, c.slot_bytes, parity, c.epoch,
-                                                reinterpret_cast<unsigned long long *>(data),
-                                                reinterpret_cast<unsigned long long *>(host_mirror), n, c.ticket + 1);
+                                                reinterpret_cast<unsigned long long *>(data), n, c.ticket + 1);
     FHC_LAUNCH_CHECK("comm_sum_u64_kernel");
     return FHC_OK;
-}
-
-extern "C" int fhc_comm_allreduce_u64(fhc_comm *comm, uint64_t *data, int64_t n, void *stream) {
-    return comm_allreduce(comm, data, n, nullptr, stream);
-}
-
-extern "C" int fhc_comm_allreduce_u64_mirror(fhc_comm *comm, uint64_t *data, int64_t n, uint64_t *host_mirror, void *stream) {
-    FHC_REQUIRE(host_mirror != nullptr, FHC_E_INVALID, "fhc_comm_allreduce_u64_mirror: null mirror");
-    cudaPointerAttributes attr;
-    const bool ok = cudaPointerGetAttributes(&attr, host_mirror) == cudaSuccess &&
-                    (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged ||
-                     (attr.type == cudaMemoryTypeHost && attr.devicePointer == host_mirror));
-    if (!ok) cudaGetLastError();
-    FHC_REQUIRE(ok, FHC_E_INVALID, "fhc_comm_allreduce_u64_mirror: the mirror must be pinned (device-accessible) memory");
-    return comm_allreduce(comm, data, n, host_mirror, stream);
 }
 
 // dst [world x bytes] <- the payload (bytes, a multiple of 16) of every rank in rank order; asynchronous on `stream`

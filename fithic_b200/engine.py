@@ -111,6 +111,8 @@ def host_threads():
         cores = os.cpu_count() or 4
     local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
     if local > 1:
+        if os.environ.get("FHC_CORES_PINNED") == "1":  # parallel.DistCtx gave this rank its own cores (FHC_PIN_CORES=1)
+            return max(1, min(8, cores - 1))
         return max(1, min(8, cores // local - 1))
     return max(1, min(8, cores))
 
@@ -438,16 +440,8 @@ class Engine:
         hist_d, present_d, scal_d = self.hist_distance(skip, skip_limit)
         native = (st.resolution > 0 and self.D <= self.NATIVE_STAGE_MAX_SLOTS
                   and os.environ.get("FHC_HOST_STAGE", "native") != "legacy")
-        self._k1_on_host = False
         if self.dist is not None:  # exchange 1: [hist | totals | rank slots] summed over the GPUs in one collective
-            mirror = None
-            if native:  # ... whose reducing kernel also writes the sums into the host stage's pinned buffer
-                hs = getattr(self, "_stage", None)
-                if hs is None:
-                    hs = self._stage = _HostStage(self)
-                hs.ensure(self.D)
-                mirror = hs.k1.data_ptr()
-            self._k1_on_host = self.dist.allreduce_k1(self._ws["k1buf"][:self.D + scal_d.numel()], host_mirror=mirror)
+            self.dist.allreduce_k1(self._ws["k1buf"][:self.D + scal_d.numel()])
         tables = self._tables_native if native else self._tables_legacy
         out, lut, lbeta, ev = tables(passNo, outl if passNo > 1 else None, t0)
         N, obsInterAllCount, obsInterAllSum = out["N"], out["observedInterAllCount"], out["observedInterAllSum"]
@@ -561,8 +555,7 @@ class Engine:
         else:
             io.pairs_rank, io.pairs_world, io.shm = 0, 1, None
         nk = D + _capi.N_SCALARS + slots
-        if not getattr(self, "_k1_on_host", False):
-            check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
+        check(lib.fhc_copy_async(hs.k1.data_ptr(), k1buf.data_ptr(), 8 * nk, stream))
         if hs.event is None:
             ev = ctypes.c_void_p()
             check(lib.fhc_event_create(ctypes.byref(ev)))

@@ -197,6 +197,30 @@ class DistCtx:
         env = os.environ.get("FHC_BH_SMALL_SET")  # e.g. 0: always take the range-partitioned route (tests, timing)
         if env is not None:
             self.SMALL_SET = int(env)
+        self.pinned_cores = None
+        if isinstance(self.ops, CudaOps) and os.environ.get("FHC_PIN_CORES", "0") == "1":
+            self._pin_cores()
+
+    def _pin_cores(self):
+        """Give this rank its own slice of the node's cores (FHC_PIN_CORES=1).  The workers of the host stage spin while a
+        pass runs; without a slice of its own a rank can find two of its spinning threads on one core while another core
+        idles, and the ranks wait for the slowest host stage at both exchanges of a pass."""
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        local_rank = int(os.environ.get("LOCAL_RANK", "0") or 0)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            return
+        per = len(cores) // max(local_world, 1)
+        if local_world <= 1 or per < 2:
+            return
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, mine)  # the calling thread; the host pool's workers are created later and inherit it
+            self.pinned_cores = mine
+            os.environ["FHC_CORES_PINNED"] = "1"  # host_threads(): the affinity mask is this rank's own slice now
+        except OSError:
+            pass
 
     def _init_p2p(self, slot_bytes=1 << 20):
         lib = self.ops.lib
@@ -246,20 +270,14 @@ class DistCtx:
             self.shm = None
 
     # ---- exchange 1 -------------------------------------------------------------------------------------------------
-    def allreduce_k1(self, fused, host_mirror=None):
+    def allreduce_k1(self, fused):
         """Sum K1's [hist | totals | rank slots] over the ranks, in place: one collective, no host synchronisation (the
-        largest count travels in the rank slots, see fhc_hist_distance).  host_mirror: address of pinned host memory that
-        is to receive the summed words as well; returns True when it did (the library's own collective writes it from the
-        reducing kernel), False when the caller still has to copy."""
+        largest count travels in the rank slots, see fhc_hist_distance)."""
         n = fused.numel()
         if self.comm is not None and n % 2 == 0 and 8 * n <= self.comm_slot_bytes and fused.dtype == torch.int64:
-            if host_mirror:
-                check(self.ops.lib.fhc_comm_allreduce_u64_mirror(self.comm, dptr(fused), n, host_mirror, self.ops._stream()))
-                return True
             check(self.ops.lib.fhc_comm_allreduce_u64(self.comm, dptr(fused), n, self.ops._stream()))
         else:
             dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=self.group)
-        return False
 
     def or_present(self, present):
         """OR the 'distance seen with counts <= 0' bitmaps of all ranks, in place.  Only needed when the summed totals

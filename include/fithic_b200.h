@@ -99,9 +99,6 @@ int64_t fhc_comm_handle_bytes(void);
 int fhc_comm_create(int32_t rank, int32_t world, int64_t slot_bytes, fhc_comm **comm_out, void *handle_out);
 int fhc_comm_connect(fhc_comm *comm, const void *all_handles);
 int fhc_comm_allreduce_u64(fhc_comm *comm, uint64_t *data, int64_t n, void *stream);
-/* the same, and the n summed words also land in host_mirror [pinned host memory, device accessible]: valid once the stream
- * (or an event recorded behind the call) has been waited for -- saves the device-to-host copy of a small buffer */
-int fhc_comm_allreduce_u64_mirror(fhc_comm *comm, uint64_t *data, int64_t n, uint64_t *host_mirror, void *stream);
 int fhc_comm_allgather(fhc_comm *comm, const void *src, void *dst, int64_t bytes, void *stream);
 int32_t fhc_comm_world(fhc_comm *comm);
 int32_t fhc_comm_rank(fhc_comm *comm);
