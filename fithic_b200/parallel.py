@@ -202,9 +202,9 @@ class DistCtx:
             self._pin_cores()
 
     def _pin_cores(self):
-        """Give this rank its own slice of the node's cores (FHC_PIN_CORES=1).  The workers of the host stage spin while a
-        pass runs; without a slice of its own a rank can find two of its spinning threads on one core while another core
-        idles, and the ranks wait for the slowest host stage at both exchanges of a pass."""
+        """Give this rank its own slice of the node's cores (FHC_PIN_CORES=1; off by default).  Measured at 8 GPUs on a
+        32-core box: the waits for the slowest rank at the two exchanges of a pass go away (0.14 -> 0.04 ms), but every
+        rank's host stage gets slower inside its four cores (fit 0.17 -> 0.24 ms), and the pass takes the same 1.9 ms."""
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
         local_rank = int(os.environ.get("LOCAL_RANK", "0") or 0)
         try:
