@@ -412,6 +412,13 @@ class Engine:
     # and anything larger keep the staged path: evaluation and lookup table on the device)
     NATIVE_STAGE_MAX_SLOTS = 1 << 20
     PREPASS_AUTO_MAX = 120_000_000  # FHC_PREPASS=auto: contacts per GPU up to which the pre-pass hides behind the host stage
+    # ... and what a larger shard gets: the lines that fit into the gap (B200: host stage ~0.55 ms, q fill 5.7 TB/s, pre-pass
+    # 170 M lines per ms); fewer than PREPASS_PARTIAL_MIN lines are not worth K3's second set of launches (measured: 22 M of
+    # 300 M lines on one GPU 9.29 against 9.21 ms per pass; 58 M of 150 M lines on each of two GPUs 4.84 against 5.00 ms)
+    PREPASS_GAP_MS = 0.55
+    PREPASS_FILL_BYTES_PER_MS = 5.7e9
+    PREPASS_LINES_PER_MS = 170e6
+    PREPASS_PARTIAL_MIN = 32_000_000
 
     def run_pass(self, passNo, outl=None, outl_stats=None, after_pvalues=None, pvalue_chunks=1, after_chunk=None):
         """One spline pass.  Returns a dict with host-side tables and device tensors p, q, expcc."""
@@ -765,13 +772,26 @@ class Engine:
                 or self.n == 0:
             return
         # The pre-pass costs more instructions than it takes out of the front kernel (it re-reads the mid points and stores
-        # 12 B per contact): it pays where it hides behind the host stage (about 0.6 ms: shards up to ~100 M contacts, i.e.
-        # every multi-GPU run of a whole genome) and in runs with several spline passes, which reuse it.
+        # 12 B per contact): it pays where it hides behind the host stage (about 0.55 ms, of which the q fill takes its
+        # share) and in runs with several spline passes, which reuse it.  Shards up to ~120 M contacts (every multi-GPU run of
+        # a whole genome) are pre-passed whole; of a larger shard only the first lines are, as many as fit into the gap --
+        # K3 then runs once over those behind the pre-pass and once over the rest without.
+        n_pre = self.n
         if mode == "auto" and self.n > self.PREPASS_AUTO_MAX and self.st.noOfPasses < 2:
-            return
-        code = self._tensor("pre_code", self.n, torch.int32)
-        b12 = self._tensor("pre_b12", self.n, torch.float64)
-        key = (self.contacts[0].data_ptr(), self.n, id(self._bias_dev))
+            gap_ms = self.PREPASS_GAP_MS - self.n * 8 / self.PREPASS_FILL_BYTES_PER_MS
+            n_pre = int(max(gap_ms, 0.0) * self.PREPASS_LINES_PER_MS) // 4096 * 4096
+            if n_pre < self.PREPASS_PARTIAL_MIN:
+                return
+            n_pre = min(n_pre, self.n)
+        forced = os.environ.get("FHC_PREPASS_LINES")  # tests: pre-pass exactly this many lines (rounded down to 4096)
+        if forced:
+            n_pre = min(int(forced) // 4096 * 4096, self.n)
+            if n_pre <= 0:
+                return
+        self._pre_n = n_pre
+        code = self._tensor("pre_code", n_pre, torch.int32)
+        b12 = self._tensor("pre_b12", n_pre, torch.float64)
+        key = (self.contacts[0].data_ptr(), self.n, n_pre, id(self._bias_dev))
         if passNo == 1 or getattr(self, "_pre_key", None) != key:
             st = self.st
             mid1, mid2, cnt, chrs = self.contacts
@@ -782,7 +802,7 @@ class Engine:
                 bias, bmid, boff = self._bias_dev
                 nchr = boff.numel() - 1
             check(self.lib.fhc_pvalues_prepass(st.mode, dptr(mid1), dptr(mid2), None if nruns else dptr(self.chrs_array()),
-                                               dptr(rs), dptr(rv), nruns, self.n, dptr(bias), dptr(bmid), dptr(boff), nchr,
+                                               dptr(rs), dptr(rv), nruns, n_pre, dptr(bias), dptr(bmid), dptr(boff), nchr,
                                                getattr(self, "_bias_sparse", 0), self.grid, st.L, st.U,
                                                float(st.biasLowerBound), float(st.biasUpperBound), 0, dptr(code), dptr(b12),
                                                self._stream()))
@@ -804,8 +824,10 @@ class Engine:
             rs, rv, nruns = None, None, 0
         n = self.n
         pre_code = pre_b12 = None
+        n_pre = 0
         if use_prepass and getattr(self, "_pre_live", False):
-            pre_code, pre_b12 = self._ws["pre_code"][:n], self._ws["pre_b12"][:n]
+            n_pre = min(getattr(self, "_pre_n", n), n)
+            pre_code, pre_b12 = self._ws["pre_code"][:n_pre], self._ws["pre_b12"][:n_pre]
         p = self._tensor("p", n, torch.float64)
         e = self._tensor("expcc", n, torch.float64)
         tab_a = tab_b = None
@@ -823,14 +845,17 @@ class Engine:
             bias, bmid, boff = self._bias_dev
             nchr = boff.numel() - 1
         step = n if nchunks <= 1 else max(((n + nchunks - 1) // nchunks + 4095) // 4096 * 4096, 4096)
-        wsb = int(self.lib.fhc_pvalues_workspace_bytes(min(step, n), max(nta, ntb)))
+        # slices: the caller's chunks, cut once more where the pre-passed lines end (a slice is behind the pre-pass or not)
+        cuts = sorted(set((list(range(0, n, step)) if n > 0 else [0]) + [n] + ([n_pre] if 0 < n_pre < n else [])))
+        if len(cuts) < 2:
+            cuts = [0, n]
+        wsb = int(self.lib.fhc_pvalues_workspace_bytes(max(b - a for a, b in zip(cuts[:-1], cuts[1:])), max(nta, ntb)))
         ws = self._buf("pval_ws", wsb)  # work lists of the contacts that need an iterative evaluation
-        lo = 0
-        while True:
-            hi = min(lo + step, n)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
             whole = lo == 0 and hi == n  # (a slice of a tensor costs microseconds: the usual single launch takes none)
             sl = (lambda t: t) if whole else (lambda t: t[lo:hi])
             o = None if outl is None else sl(outl)
+            pre = pre_code is not None and hi <= n_pre
             check(self.lib.fhc_pvalues(st.mode, dptr(sl(mid1)), dptr(sl(mid2)), dptr(sl(cnt)),
                                        None if chrs is None else dptr(sl(chrs)), dptr(rs), dptr(rv), nruns,
                                        hi - lo, dptr(bias), dptr(bmid), dptr(boff), nchr,
@@ -838,13 +863,10 @@ class Engine:
                                        dptr(lut), self.D if lut is not None else 0, int(N_intra), int(N_inter),
                                        float(interChrProb), float(st.biasLowerBound), float(st.biasUpperBound), dptr(tab_a),
                                        nta, dptr(tab_b), ntb, dptr(o), lo, float(outl_thres), dptr(outl_stats), dptr(sl(p)),
-                                       dptr(sl(e)), None if pre_code is None else dptr(sl(pre_code)),
-                                       None if pre_b12 is None else dptr(sl(pre_b12)), dptr(ws), wsb, self._stream()))
+                                       dptr(sl(e)), dptr(pre_code[lo:hi]) if pre else None,
+                                       dptr(pre_b12[lo:hi]) if pre else None, dptr(ws), wsb, self._stream()))
             if after_chunk is not None:
                 after_chunk(lo, hi, p, e)
-            lo = hi
-            if lo >= n:
-                break
         return p, e
 
     # K4  (myStats.benjamini_hochberg_correction, fithic/myStats.py:24-48)

@@ -158,6 +158,11 @@ def test_prepass_changes_nothing(lib, monkeypatch, mode):
             monkeypatch.setenv("FHC_Q_PREFILL", pre)  # (q = 1.0 written ahead of K4 or by K4 itself)
             monkeypatch.setenv("FHC_CHR_RUNS", runs)
             got[pre, runs] = run_engine(contacts, frags, biases, st)
+    monkeypatch.setenv("FHC_PREPASS", "1")
+    monkeypatch.setenv("FHC_CHR_RUNS", "1")
+    monkeypatch.setenv("FHC_PREPASS_LINES", "102400")  # only the first lines behind the pre-pass: K3 in two parts
+    got["partial", "1"] = run_engine(contacts, frags, biases, st)
+    monkeypatch.delenv("FHC_PREPASS_LINES")
     ref = got["0", "0"]
     for key, res in got.items():
         assert len(res) == len(ref)
