@@ -79,4 +79,10 @@ __device__ __forceinline__ int2 ldg_stream2(const int2 *p) {
     return v;
 }
 
+__device__ __forceinline__ double2 ldg_stream_d2(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 }  // namespace fhc

@@ -34,7 +34,8 @@ struct __align__(16) WorkItem {
 };
 
 struct ListsWs {
-    unsigned long long *ctr;  // [0] continued fractions, [1] tail sums, [2]/[3] the cursors of the iterate kernel
+    unsigned long long *ctr;  // [0] list lengths: continued fractions (low word) | tail sums (high word); [2]/[3] the cursors of
+                              // the iterate kernel
     WorkItem *items;          // capacity n: continued fractions from the front, tail sums from the back
     double2 *pq;              // numerator / denominator of the item at the same position
     double2 *aux_intra, *aux_inter;  // per count: lbeta + log(count), lbeta + log(N - count + 1)
@@ -103,6 +104,24 @@ __device__ __forceinline__ double bias_lookup_rng(const PvalParams &P, const Fro
     return ok ? b : -1.0;
 }
 
+// the lookup for sparse bias tables (restriction fragments: binary search), more than kChrSmem chromosomes or 2^31 slots:
+// out of line, so that its four inlined copies per group do not sit in the middle of the regular grid's instruction stream
+// (the fields it needs go by value: a reference to the kernel's parameter block would force a copy of it onto the stack)
+__device__ __noinline__ double bias_lookup_general_fn(const long long *chr_off, const int *bias_mid, const double *bias,
+                                                      int bias_sparse, int nchr, FastDiv res, unsigned int chr, int mid) {
+    PvalParams Q;
+    Q.chr_off = chr_off;
+    Q.bias_mid = bias_mid;
+    Q.bias = bias;
+    Q.bias_sparse = bias_sparse;
+    Q.nchr = nchr;
+    Q.res = res;
+    return bias_lookup(Q, chr, mid);
+}
+__device__ __forceinline__ double bias_lookup_general(const PvalParams &P, unsigned int chr, int mid) {
+    return bias_lookup_general_fn(P.chr_off, P.bias_mid, P.bias, P.bias_sparse, P.nchr, P.res, chr, mid);
+}
+
 // phase A of a contact: the three gathers (two bias values, the distance table), issued for all four contacts of a group
 // before anything consumes them so that their L2 latencies overlap
 // INTRA: every contact of the tile lies on one chromosome (known from the chromosome runs): `ch` is that chromosome's
@@ -125,8 +144,8 @@ __device__ __forceinline__ void front_gather(const PvalParams &P, const FrontCon
                 b2 = bias_lookup_sel<REGULAR>(P, F, chr_rng, c2, m2);
             }
         } else {
-            b1 = bias_lookup(P, c1, m1);
-            b2 = bias_lookup(P, c2, m2);
+            b1 = bias_lookup_general(P, c1, m1);
+            b2 = bias_lookup_general(P, c2, m2);
         }
     }
     const unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
@@ -165,7 +184,13 @@ __device__ __forceinline__ PvalClass front_score(const PvalParams &P, const Fron
     prior = __dmul_rn(prior0, b12);
     const double dN = intra_path ? F.dN_intra : F.dN_inter;
     const unsigned int N = (unsigned int)(intra_path ? P.N_intra : P.N_inter);  // 0 <= N < 2^31
-    e = (scored && f.b_ok) ? __dmul_rn(dN, prior) : 0.0;
+    // ExpCC = N prior where the line is scored and both biases lie in [tL, tU], else +0.0: as a bit mask (a conditional
+    // on doubles compiles to one pair of selects per term of the condition)
+    // (the empty asm keeps the compiler from folding the mask back into that form)
+    unsigned int eok = (scored && f.b_ok) ? 0xffffffffu : 0u;
+    asm("" : "+r"(eok));
+    const double en = __dmul_rn(dN, prior);
+    e = __hiloint2double(__double2hiint(en) & (int)eok, __double2loint(en) & (int)eok);
     // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
     // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first.  For c >= 1,
     // k = c - 1 is compared as an unsigned 32-bit value (c <= 0, i.e. k < 0, is handled on its own).
@@ -494,8 +519,11 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
         }
         if (tid == 0) {
             const unsigned int nCf = tot & 0xffffu, nTail = tot >> 16;
-            S.base_cf = nCf ? atomicAdd(W.ctr + 0, (unsigned long long)nCf) : 0ull;
-            S.base_tail = nTail ? atomicAdd(W.ctr + 1, (unsigned long long)nTail) : 0ull;
+            // both list lengths advance with one atomic: continued fractions in the low, tail sums in the high word
+            const unsigned long long b =
+                tot ? atomicAdd(W.ctr, (unsigned long long)nCf | ((unsigned long long)nTail << 32)) : 0ull;
+            S.base_cf = b & 0xffffffffull;
+            S.base_tail = b >> 32;
         }
         __syncthreads();
         if (mine) {
@@ -527,6 +555,297 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front_kernel(con
 }
 
 static_assert(sizeof(FrontSmem) <= 48 * 1024, "the front kernel's shared memory must fit the default 48 KB");
+
+// ---- front, second version ----------------------------------------------------------------------------------------------
+// The same arithmetic per contact (front_gather / front_prepare / front_score above), two changes around it, both read off
+// the per-instruction stall samples of the first version (ncu, 300 M contacts: 18 % of all samples sat on the first use of
+// the streamed mid points -- once per group of two contacts, four exposed memory latencies per tile and thread --, 11 % on
+// the two CTA-wide barriers around the list atomics, where 256 threads wait for one thread's round trip to L2):
+//   * the streamed words of the NEXT group (and, at the end of a tile, of the CTA's next tile) are loaded into registers
+//     before the current group is worked on, so their latency hides behind ~500 instructions of arithmetic;
+//   * list positions are handed out per WARP: an inclusive shuffle scan of the lanes' item counts, one 64-bit atomic that
+//     advances both list lengths at once (continued fractions in the low word, tail sums in the high word of ctr[0]), no
+//     shared-memory exchange and no __syncthreads in the tile loop at all.  The parked items (S.x / S.cnt) are read back by
+//     the thread that wrote them.  The order of the items in the lists changes; nothing downstream depends on it (each
+//     item carries its line).
+struct StreamRegs {
+    int2 a, b, c;  // mid1, mid2, count of two contacts (after a pre-pass: count, code, -)
+    double2 d;     // after a pre-pass: the two bias products
+};
+
+template <bool PRE>
+__device__ __forceinline__ void stream_issue(const PvalParams &P, long long pair, StreamRegs &r) {
+    if (PRE) {
+        r.a = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + pair);
+        r.b = ldg_stream2(reinterpret_cast<const int2 *>(P.pre_code) + pair);
+        r.d = ldg_stream_d2(reinterpret_cast<const double2 *>(P.pre_b12) + pair);
+    } else {
+        r.a = ldg_stream2(reinterpret_cast<const int2 *>(P.mid1) + pair);
+        r.b = ldg_stream2(reinterpret_cast<const int2 *>(P.mid2) + pair);
+        r.c = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + pair);
+    }
+}
+
+struct Front2Smem {  // (the run table is read from global memory: a few uniform, cached loads per tile)
+    int2 chr_rng[kChrSmem];
+    double x[kFrontTile];  // parked items: slot li belongs to the thread that handles contact li of the tile
+    int cnt[kFrontTile];
+};
+static_assert(sizeof(Front2Smem) <= 48 * 1024, "the front kernel's shared memory must fit the default 48 KB");
+
+__device__ __noinline__ unsigned int run_lookup2(const long long *run_start, const unsigned int *run_val, int nruns,
+                                                 long long line) {
+    int lo = 0, hi = nruns - 1;  // last run that starts at or before `line`
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(run_start + mid) <= line)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return __ldg(run_val + lo);
+}
+
+// what follows the classification of two contacts: closed form, parking, stores, outlier marks.  Returns their 4 code bits.
+__device__ __forceinline__ unsigned int front2_finish_pair(const PvalParams &P, Front2Smem &S, long long base, int l0, bool full,
+                                                           const int *cc, const PvalClass *cls, const double *prior,
+                                                           const bool *use_inter, double *pv, const double *e,
+                                                           unsigned int &flagged) {
+    unsigned int codes = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int li = l0 + k;
+        if (cls[k] == kClsK0) {
+            pv[k] = bdtrc_k0_fast(use_inter[k] ? P.N_inter : P.N_intra, prior[k]);
+        } else if (cls[k] != kClsDone) {
+            S.x[li] = prior[k];
+            S.cnt[li] = cc[k] | (use_inter[k] ? (int)0x80000000u : 0);
+            pv[k] = 0.0;  // overwritten by pval_finish_kernel
+        }
+        codes |= (unsigned int)cls[k] << (2 * k);
+    }
+    if (full) {
+        __stcs(reinterpret_cast<double2 *>(P.expcc + base + l0), make_double2(e[0], e[1]));
+        *reinterpret_cast<double2 *>(P.p + base + l0) = make_double2(pv[0], pv[1]);  // default caching: see front_tile
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (base + l0 + k < P.n) {
+                P.expcc[base + l0 + k] = e[k];
+                P.p[base + l0 + k] = pv[k];
+            }
+    }
+    if (P.outl != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if ((cls[k] == kClsDone || cls[k] == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
+    }
+    return codes;
+}
+
+// One tile.  `nx` holds the streamed words of this tile's first group when the tile is full (loaded by the previous tile or
+// the prologue) and leaves with those of the first group of the tile at next_base (-1: nothing to load ahead).
+template <bool HAS_BIAS, bool REGULAR, bool INTRA, bool PRE>
+__device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const FrontConst &F, Front2Smem &S, bool rng32,
+                                                    long long base, bool full, bool tile_one_run, unsigned int tile_ch,
+                                                    StreamRegs &nx, long long next_base, unsigned int &flagged) {
+    const int tid = threadIdx.x;
+    int2 rng = make_int2(0, 0);
+    bool chr_ok = false;
+    if (!PRE && INTRA && HAS_BIAS && rng32) {
+        const unsigned int c = tile_ch & 0xffffu;
+        chr_ok = c < (unsigned int)P.nchr;
+        rng = S.chr_rng[chr_ok ? c : 0u];
+    }
+    unsigned int codes = 0;
+    // not unrolled: four copies of the group body are 58 KB of instructions, and without a barrier the warps of an SM
+    // spread over all of it (ncu on the unrolled form: 1.9 warps per issue slot waiting for an instruction fetch)
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+        const int l0 = (h * kFrontThreads + tid) * 2;
+        StreamRegs cur;
+        if (full) {
+            cur = nx;
+            const long long ahead = h < 3 ? base + l0 + 2 * kFrontThreads : next_base + 2 * tid;
+            if (h < 3 || next_base >= 0) stream_issue<PRE>(P, ahead >> 1, nx);
+        }
+        int cc[2];
+        PvalClass cls[2];
+        double prior[2], pv[2], e[2];
+        bool use_inter[2];
+        if (PRE) {
+            unsigned int pc[2];
+            double b12[2];
+            if (full) {
+                cc[0] = cur.a.x; cc[1] = cur.a.y;
+                pc[0] = (unsigned int)cur.b.x; pc[1] = (unsigned int)cur.b.y;
+                b12[0] = cur.d.x; b12[1] = cur.d.y;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const long long i = base + l0 + k;
+                    const bool ok = i < P.n;
+                    cc[k] = ok ? reinterpret_cast<const int *>(P.cnt)[i] : 0;
+                    pc[k] = ok ? P.pre_code[i] : kPreNotScored;
+                    b12[k] = ok ? P.pre_b12[i] : 1.0;
+                }
+            }
+            double gtv[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // the one gather that is left
+                const unsigned int slot = pc[k] & kPreSlotMask;
+                const bool want = pc[k] != kPreNotScored && !(pc[k] & kPreInter) && slot < F.D32 && P.lut != nullptr;
+                const double t = P.lut != nullptr ? __ldg(P.lut + (want ? slot : 0u)) : 0.0;
+                gtv[k] = want ? t : NAN;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                FrontFlags f;
+                f.scored = pc[k] != kPreNotScored;
+                f.intra_path = !(pc[k] & kPreInter);
+                f.b_ok = (pc[k] & kPreBok) != 0;
+                cls[k] = front_score(P, F, f, cc[k], b12[k], gtv[k], pv[k], e[k], prior[k], use_inter[k]);
+            }
+        } else {
+            int m1[2], m2[2];
+            unsigned int ch[2];
+            if (full) {
+                m1[0] = cur.a.x; m1[1] = cur.a.y;
+                m2[0] = cur.b.x; m2[1] = cur.b.y;
+                cc[0] = cur.c.x; cc[1] = cur.c.y;
+                if (!INTRA && P.chrs != nullptr) {
+                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + ((base + l0) >> 1));
+                    ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        ch[k] = (INTRA || tile_one_run) ? tile_ch
+                                                        : run_lookup2(P.run_start, P.run_val, P.nruns, P.line_base + base + l0 + k);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const long long i = base + l0 + k;
+                    const bool ok = i < P.n;
+                    m1[k] = ok ? reinterpret_cast<const int *>(P.mid1)[i] : 0;
+                    m2[k] = ok ? reinterpret_cast<const int *>(P.mid2)[i] : 0;
+                    cc[k] = ok ? reinterpret_cast<const int *>(P.cnt)[i] : 0;
+                    ch[k] = 0x00010000u;  // padding: an inter line
+                    if (ok)
+                        ch[k] = P.chrs != nullptr ? reinterpret_cast<const unsigned int *>(P.chrs)[i]
+                                                  : (tile_one_run ? tile_ch : run_lookup2(P.run_start, P.run_val, P.nruns, P.line_base + i));
+                }
+            }
+            double gb1[2], gb2[2], gtv[2];
+            unsigned int dd[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                front_gather<HAS_BIAS, REGULAR, INTRA>(P, F, S.chr_rng, rng32, rng, chr_ok, m1[k], m2[k], ch[k], gb1[k], gb2[k],
+                                                       gtv[k], dd[k]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool in_file = full || base + l0 + k < P.n;
+                cls[k] = front_prepare<INTRA>(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k], prior[k],
+                                              use_inter[k]);
+            }
+        }
+        codes |= front2_finish_pair(P, S, base, l0, full, cc, cls, prior, use_inter, pv, e, flagged) << (4 * h);
+    }
+    return codes;
+}
+
+// list positions for the items of one warp and their stores (see the note above)
+__device__ __forceinline__ void front2_append(const ListsWs &W, const Front2Smem &S, unsigned int codes, long long base, int tid,
+                                              int lane) {
+    unsigned int mine = 0;  // continued fractions | tail sums << 16 of this thread (<= 8 each)
+#pragma unroll
+    for (int s8 = 0; s8 < 8; ++s8) {
+        const unsigned int c = (codes >> (2 * s8)) & 3u;
+        mine += (c == kClsCf ? 1u : 0u) + (c == kClsTail ? 0x10000u : 0u);
+    }
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const unsigned int tot = __shfl_sync(0xffffffffu, inc, 31);  // <= 256 per half
+    if (tot == 0) return;
+    unsigned long long b = 0;
+    if (lane == 31) b = atomicAdd(W.ctr, (unsigned long long)(tot & 0xffffu) | ((unsigned long long)(tot >> 16) << 32));
+    b = __shfl_sync(0xffffffffu, b, 31);
+    if (mine == 0) return;
+    const unsigned int ex = inc - mine;
+    long long oCf = (long long)(b & 0xffffffffull) + (ex & 0xffffu);
+    long long oTail = W.cap - 1 - ((long long)(b >> 32) + (ex >> 16));
+#pragma unroll
+    for (int s8 = 0; s8 < 8; ++s8) {
+        const unsigned int c = (codes >> (2 * s8)) & 3u;
+        if (c == kClsCf || c == kClsTail) {
+            const int li = ((s8 >> 1) * kFrontThreads + tid) * 2 + (s8 & 1);
+            WorkItem it;
+            it.x = S.x[li];
+            it.idx = (unsigned int)(base + li);
+            it.cnt = S.cnt[li];
+            if (c == kClsCf)
+                W.items[oCf++] = it;
+            else
+                W.items[oTail--] = it;
+        }
+    }
+}
+
+template <bool HAS_BIAS, bool REGULAR, bool PRE, int kMinCtas>
+__global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front2_kernel(const PvalParams P, const FrontConst F, const ListsWs W) {
+    extern __shared__ __align__(16) unsigned char front_smem[];
+    Front2Smem &S = *reinterpret_cast<Front2Smem *>(front_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    bool rng32 = false;
+    if (HAS_BIAS && !PRE) {
+        rng32 = !P.bias_sparse && P.nchr <= kChrSmem && P.chr_off[P.nchr] < 0x7fffffffll;
+        if (rng32)
+            for (int c = tid; c < P.nchr; c += kFrontThreads) S.chr_rng[c] = make_int2((int)P.chr_off[c], (int)P.chr_off[c + 1]);
+    }
+    const bool runs = !PRE && P.chrs == nullptr;
+    __syncthreads();  // the only one: nothing in the tile loop is exchanged between warps
+    const unsigned int ntiles = (unsigned int)((P.n + kFrontTile - 1) / kFrontTile);  // n < 2^32
+    const unsigned int nfull = (unsigned int)(P.n / kFrontTile);                        // tiles [0, nfull) are full
+    unsigned int flagged = 0;
+    int run = 0;  // the tiles of this CTA only move forward, so does its position in the run table
+    StreamRegs nx;
+    nx.a = nx.b = nx.c = make_int2(0, 0);
+    nx.d = make_double2(0.0, 0.0);
+    if (blockIdx.x < nfull) stream_issue<PRE>(P, ((long long)blockIdx.x * kFrontTile + 2 * tid) >> 1, nx);
+
+    for (unsigned int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = (long long)tile * kFrontTile;
+        const bool full = tile < nfull;
+        const unsigned int tnext = tile + gridDim.x;
+        const long long next_base = tnext < nfull ? (long long)tnext * kFrontTile : -1;
+        bool one_run = false;
+        unsigned int tile_ch = 0;
+        if (runs) {
+            const long long g0 = P.line_base + base;
+            long long next_start = __ldg(P.run_start + run + 1);
+            while (next_start <= g0) next_start = __ldg(P.run_start + (++run) + 1);
+            const long long g1 = P.line_base + (full ? base + kFrontTile : P.n);
+            one_run = next_start >= g1;
+            tile_ch = __ldg(P.run_val + run);
+        }
+        unsigned int codes;
+        if (PRE)
+            codes = front2_tile<false, true, false, true>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+        else if (one_run && full && (tile_ch & 0xffffu) == (tile_ch >> 16) && P.mode != FHC_MODE_INTER_ONLY)
+            codes = front2_tile<HAS_BIAS, REGULAR, true, false>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+        else
+            codes = front2_tile<HAS_BIAS, REGULAR, false, false>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+        front2_append(W, S, codes, base, tid, lane);
+    }
+    if (P.outl != nullptr) {
+        const unsigned long long f = warp_sum((unsigned long long)flagged);
+        if (lane == 0 && f) atomicAdd(P.outl_stats, f);
+    }
+}
 
 // ---- pre-pass ---------------------------------------------------------------------------------------------------------
 // Everything of the front kernel that does not depend on the spline table -- the two bias gathers, their product and
@@ -741,7 +1060,7 @@ __global__ void __launch_bounds__(kIterThreads, 4) pval_iterate_kernel(const Pva
     __shared__ Staged stage_all[kIterThreads / 32][kIterChunk];
     const int lane = threadIdx.x & 31;
     Staged *stage = stage_all[threadIdx.x >> 5];
-    const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
+    const unsigned long long nCf = W.ctr[0] & 0xffffffffull, nTail = W.ctr[0] >> 32;
     iterate_list<false>(P, W, nCf, W.ctr + 2, lane, stage);
     iterate_list<true>(P, W, nTail, W.ctr + 3, lane, stage);
 }
@@ -763,7 +1082,7 @@ __global__ void lbeta_aux_kernel(const double *__restrict__ tab, long long ntab,
 // waits on memory, not on arithmetic: two thirds of its stall samples sat on these loads with one item per thread).
 template <int kMinCtas>
 __global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(const PvalParams P, const ListsWs W) {
-    const unsigned long long nCf = W.ctr[0], nTail = W.ctr[1];
+    const unsigned long long nCf = W.ctr[0] & 0xffffffffull, nTail = W.ctr[0] >> 32;
     const unsigned long long total = nCf + nTail;
     const unsigned long long stride = (unsigned long long)gridDim.x * kFinishThreads;
     unsigned int flagged = 0;
@@ -888,34 +1207,34 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     const FrontConst F = make_front_const(P);
     long long tiles = (n + kFrontTile - 1) / kFrontTile;
     long long blocks = tiles;
-    // Default: two contacts per load in 64 registers, 4 CTAs per SM.  FHC_PVAL_FRONT=g4 selects four contacts per load in
-    // 80 registers and 3 CTAs per SM, g4x4 the same squeezed to 64 registers with spills (B200, 300 M contacts in random
-    // order: 4.63 ms against 5.25 ms and 5.40 ms).  Also measured and dropped: the contact arrays of the next tile staged
-    // in shared memory by cp.async with the gathers issued one pair ahead (6.65 ms: the kernel waits on its scattered
-    // gathers -- 21 sectors per warp request, L1TEX at 70 % -- not on the streaming loads, and the extra barriers cost);
-    // an L2 prefetch of the CTA's next tile (file order, where the first use of the streamed data is the largest stall:
-    // 4.02 ms with, 4.04 ms without).
+    // Default: the second version of the front kernel (streamed words loaded one group ahead, list positions per warp,
+    // no barrier in the tile loop).  FHC_PVAL_FRONT=v1 selects the first version (two contacts per load, CTA-wide scan and
+    // two barriers per tile) for comparison.  Measured on the first version and dropped (B200, 300 M contacts in random
+    // order): four contacts per load in 80 registers and 3 CTAs per SM (5.25 ms against 4.63 ms), the same squeezed into
+    // 64 registers with spills (5.40 ms); the contact arrays of the next tile staged in shared memory by cp.async with the
+    // gathers issued one pair ahead (6.65 ms: the extra barriers cost more than the staging saves); an L2 prefetch of the
+    // CTA's next tile (4.02 ms with, 4.04 ms without).
     const char *fv = getenv("FHC_PVAL_FRONT");
-    const int variant = (fv && fv[0] == 'g' && fv[1] == '4') ? (fv[2] == 'x' ? 1 : 0) : 2;
-    const int occ = variant == 0 ? 3 : 4;
-    if (blocks > (long long)kNumSMs * occ) blocks = (long long)kNumSMs * occ;
-#define FHC_FRONT_V(B, R)                                                                                         \
-    do {                                                                                                          \
-        if (variant == 2)                                                                                         \
-            pval_front_kernel<B, R, 4, 2><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
-        else if (variant == 1)                                                                                    \
-            pval_front_kernel<B, R, 4, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
-        else                                                                                                      \
-            pval_front_kernel<B, R, 3, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W); \
+    const bool v1 = fv && fv[0] == 'v' && fv[1] == '1';
+    const bool o5 = fv && fv[0] == 'v' && fv[1] == '2' && fv[2] == 'o' && fv[3] == '5';  // 48 registers, 5 CTAs per SM
+    if (blocks > (long long)kNumSMs * (o5 ? 5 : 4)) blocks = (long long)kNumSMs * (o5 ? 5 : 4);
+#define FHC_FRONT_V(B, R, PRE)                                                                                         \
+    do {                                                                                                               \
+        if (v1)                                                                                                        \
+            pval_front_kernel<B, R, 4, 2, PRE><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W);  \
+        else if (o5)                                                                                                   \
+            pval_front2_kernel<B, R, PRE, 5><<<(unsigned int)blocks, kFrontThreads, sizeof(Front2Smem), st>>>(P, F, W); \
+        else                                                                                                           \
+            pval_front2_kernel<B, R, PRE, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(Front2Smem), st>>>(P, F, W); \
     } while (0)
     if (P.pre_code != nullptr)
-        pval_front_kernel<false, true, 4, 2, true><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W);
+        FHC_FRONT_V(false, true, true);
     else if (!P.bias)
-        FHC_FRONT_V(false, true);
+        FHC_FRONT_V(false, true, false);
     else if (P.bias_mid == nullptr && !P.bias_sparse)
-        FHC_FRONT_V(true, true);
+        FHC_FRONT_V(true, true, false);
     else
-        FHC_FRONT_V(true, false);
+        FHC_FRONT_V(true, false, false);
 #undef FHC_FRONT_V
     FHC_LAUNCH_CHECK("pval_front_kernel");
     // the list lengths are only known on the device: both follow-up kernels are persistent and read them there

@@ -3,6 +3,7 @@ per-kernel device ms for each variant.  One process, one data set.  Usage: pytho
 import os
 import sys
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,14 +17,18 @@ torch.cuda.set_device(0)
 (m1, m2, c, ch), frags, biases, per = synth.make_intra_device(pairs, 5000, 1004, dev, mean_count=3.0, with_bias=True, order=order)
 st = Settings(resolution=5000, noOfBins=100)
 eng = Engine(st, frags, biases, device=dev)
-eng.set_contacts_device(m1, m2, c, ch)
+# chromosome ids as runs, as bench.py and the CLI pass them (K1 and K3 then read no chrs array)
+mine = [k for k in range(len(per)) if per[k] > 0]
+runs = (np.array([k | (k << 16) for k in mine], dtype=np.uint32), np.array([per[k] for k in mine], dtype=np.int64))
+eng.set_contacts_device(m1, m2, c, ch, chr_runs=None if os.environ.get("K3V_CHRS") else runs)
 VARIANTS = [
-    ("lists: g2 front (default)", {}),
-    ("lists: g4 front", {"FHC_PVAL_FRONT": "g4"}),
-    ("tile", {"FHC_PVAL_IMPL": "tile"}),
-    ("lists, rank-bound cut only", {"FHC_BH_TIGHTEN": "0"}),
+    ("lists: front v2 (default)", {}),
+    ("lists: front v2, 5 CTAs/SM", {"FHC_PVAL_FRONT": "v2o5"}),
+    ("lists: front v1", {"FHC_PVAL_FRONT": "v1"}),
 ]
-KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN")
+KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN", "FHC_PREPASS")
+if os.environ.get("K3V_ONLY"):
+    VARIANTS = VARIANTS[:int(os.environ["K3V_ONLY"])]
 print("line order:", order)
 ref = None
 for name, env in VARIANTS:
