@@ -568,6 +568,53 @@ static_assert(sizeof(FrontSmem) <= 48 * 1024, "the front kernel's shared memory 
 //     shared-memory exchange and no __syncthreads in the tile loop at all.  The parked items (S.x / S.cnt) are read back by
 //     the thread that wrote them.  The order of the items in the lists changes; nothing downstream depends on it (each
 //     item carries its line).
+// The gathers of a group in two phases.  Phase 1 turns every contact of the group into where to load from: the slot of
+// each bias value and of the table value, or -- where the first version selects a constant AFTER the load (locus not in the
+// bias table: -1, distance beyond the table: NaN) -- the address of that constant, so the select sits BEFORE the load and
+// nothing has to wait for a gathered value until the arithmetic needs it.  Phase 2 issues all loads of the group back to
+// back (ncu on the form with one select behind each load: a third of the kernel's stall samples sat on those selects, the
+// gathers of the second contact were only issued once the first contact's had come back).
+__device__ const unsigned long long g_front_consts[2] = {0xBFF0000000000000ull, 0x7FF8000000000000ull};  // -1.0, NaN
+
+template <bool REGULAR>
+__device__ __forceinline__ const double *bias_addr_rng(const PvalParams &P, const FrontConst &F, int2 rng, bool chr_ok, int mid,
+                                                       const double *minus_one) {
+    // the checks of bias_lookup_rng in unsigned arithmetic: with mid >= 0 the slot rng.x + mid / res cannot wrap
+    const unsigned int k = fastdiv31((unsigned int)mid, P, F);  // garbage for mid < 0, masked below
+    const unsigned int s = (unsigned int)rng.x + k;
+    bool ok = chr_ok && mid >= 0 && s < (unsigned int)rng.y;
+    if (REGULAR)
+        ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
+    else
+        ok = ok && __ldg(P.bias_mid + (ok ? s : 0u)) == mid;
+    return ok ? P.bias + s : minus_one;
+}
+
+template <bool HAS_BIAS, bool REGULAR, bool INTRA>
+__device__ __forceinline__ void front_addr2(const PvalParams &P, const FrontConst &F, const int2 *chr_rng, bool rng32, int2 rng,
+                                            bool chr_ok, int m1, int m2, unsigned int ch, const double *&a1, const double *&a2,
+                                            const double *&at, unsigned int &d) {
+    const double *cst = reinterpret_cast<const double *>(g_front_consts);
+    const unsigned int c1 = ch & 0xffffu, c2 = ch >> 16;
+    d = m1 > m2 ? (unsigned int)m1 - (unsigned int)m2 : (unsigned int)m2 - (unsigned int)m1;
+    a1 = a2 = cst;
+    if (HAS_BIAS && rng32) {  // uniform
+        int2 r1 = rng, r2 = rng;
+        bool ok1 = chr_ok, ok2 = chr_ok;
+        if (!INTRA) {
+            ok1 = c1 < (unsigned int)P.nchr;
+            ok2 = c2 < (unsigned int)P.nchr;
+            r1 = chr_rng[ok1 ? c1 : 0u];
+            r2 = chr_rng[ok2 ? c2 : 0u];
+        }
+        a1 = bias_addr_rng<REGULAR>(P, F, r1, ok1, m1, cst);
+        a2 = bias_addr_rng<REGULAR>(P, F, r2, ok2, m2, cst);
+    }
+    const unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
+    const bool slot_ok = (INTRA || c1 == c2) && slot < F.D32 && P.lut != nullptr;
+    at = slot_ok ? P.lut + slot : cst + 1;  // NaN beyond the table (or an inter line, which never uses it)
+}
+
 struct StreamRegs {
     int2 a, b, c;  // mid1, mid2, count of two contacts (after a pre-pass: count, code, -)
     double2 d;     // after a pre-pass: the two bias products
@@ -692,11 +739,10 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
             }
             double gtv[2];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // the one gather that is left
+            for (int k = 0; k < 2; ++k) {  // the one gather that is left (NaN where the line uses no table value)
                 const unsigned int slot = pc[k] & kPreSlotMask;
                 const bool want = pc[k] != kPreNotScored && !(pc[k] & kPreInter) && slot < F.D32 && P.lut != nullptr;
-                const double t = P.lut != nullptr ? __ldg(P.lut + (want ? slot : 0u)) : 0.0;
-                gtv[k] = want ? t : NAN;
+                gtv[k] = __ldg(want ? P.lut + slot : reinterpret_cast<const double *>(g_front_consts) + 1);
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -738,10 +784,26 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
             }
             double gb1[2], gb2[2], gtv[2];
             unsigned int dd[2];
+            const double *a1[2], *a2[2], *at[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                front_gather<HAS_BIAS, REGULAR, INTRA>(P, F, S.chr_rng, rng32, rng, chr_ok, m1[k], m2[k], ch[k], gb1[k], gb2[k],
-                                                       gtv[k], dd[k]);
+                front_addr2<HAS_BIAS, REGULAR, INTRA>(P, F, S.chr_rng, rng32, rng, chr_ok, m1[k], m2[k], ch[k], a1[k], a2[k],
+                                                      at[k], dd[k]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                gb1[k] = 1.0;
+                gb2[k] = 1.0;
+                if (HAS_BIAS) {
+                    if (rng32) {  // uniform
+                        gb1[k] = __ldg(a1[k]);
+                        gb2[k] = __ldg(a2[k]);
+                    } else {
+                        gb1[k] = bias_lookup_general(P, ch[k] & 0xffffu, m1[k]);
+                        gb2[k] = bias_lookup_general(P, ch[k] >> 16, m2[k]);
+                    }
+                }
+                gtv[k] = __ldg(at[k]);
+            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const bool in_file = full || base + l0 + k < P.n;

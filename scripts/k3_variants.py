@@ -23,7 +23,6 @@ runs = (np.array([k | (k << 16) for k in mine], dtype=np.uint32), np.array([per[
 eng.set_contacts_device(m1, m2, c, ch, chr_runs=None if os.environ.get("K3V_CHRS") else runs)
 VARIANTS = [
     ("lists: front v2 (default)", {}),
-    ("lists: front v2, 5 CTAs/SM", {"FHC_PVAL_FRONT": "v2o5"}),
     ("lists: front v1", {"FHC_PVAL_FRONT": "v1"}),
 ]
 KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN", "FHC_PREPASS")
