@@ -415,7 +415,7 @@ FHC_HD double expm1_taylor(int i) {
 // its Taylor polynomial (degree 14: 4e-18 relative).  k == 0 returns -P (full relative accuracy for tiny y); otherwise
 // 1 - 2^k (1 + P) in one fused rounding.  The result is 1.0 from y ~ -37.4 on, like 1 - exp(y) in libm arithmetic.
 FHC_HD double one_minus_exp(double y) {
-    y = fmax(y, -100.0);
+    y = y < -100.0 ? -100.0 : y;  // (y is never NaN here: the prior was checked)
     const double t = fma(y, 1.4426950408889634074, 6755399441055744.0);  // 1.5 * 2^52: round to nearest integer
     const int k = dbl_lo(t);
     const double kd = t - 6755399441055744.0;

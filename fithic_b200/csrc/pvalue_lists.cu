@@ -59,7 +59,8 @@ struct FrontConst {
     // n / res for n < 2^31 by one 32-bit multiply-high: m = ceil(2^(31 + l) / res), l = ceil(log2 res), q = hi32(n m) >> (l - 1)
     // (e = m res - 2^(31 + l) < res <= 2^l and n < 2^31 give n e < 2^(31 + l): exact); res == 1 is flagged
     unsigned int div_m, div_sh;
-    unsigned int D32;  // table length clamped to 2^32 - 1
+    unsigned int D32;   // table length clamped to 2^32 - 1; 0 when there is no table (no slot is ever "inside" then)
+    unsigned int half;  // res / 2: where the mid point of a locus of the regular grid sits inside its bin
 };
 
 __device__ __forceinline__ unsigned int fastdiv31(unsigned int n, const PvalParams &P, const FrontConst &F) {
@@ -168,11 +169,28 @@ __device__ __forceinline__ FrontFlags front_flags(const PvalParams &P, const Fro
     const bool inter = INTRA ? false : (ch & 0xffffu) != (ch >> 16);
     FrontFlags f;
     f.intra_path = INTRA ? true : (!inter && P.mode != FHC_MODE_INTER_ONLY);
-    const bool discarded = (b1 < 0.0 || b2 < 0.0) && !inter;                                   // :1057-1063
+    // :1057-1063.  Two compares chained through the predicate (written as b1 < 0 || b2 < 0 the compiler builds
+    // min(b1, b2) with its NaN rules out of nine instructions)
+    unsigned int neg;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, 0d0000000000000000;\n\tsetp.lt.or.f64 p, %2, 0d0000000000000000, p;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(neg)
+        : "d"(b1), "d"(b2));
+    const bool discarded = neg != 0u && !inter;
     const bool in_range = d >= F.Llo && d <= F.Uhi && !F.nothing_in_range;                      // :1065 / :1081-1096
     f.scored = in_file && !discarded && (f.intra_path ? in_range : P.mode != FHC_MODE_INTRA_ONLY);
     f.b_ok = b1 >= P.tL && b1 <= P.tU && b2 >= P.tL && b2 <= P.tU;
     return f;
+}
+
+// value of a scored line that needs neither the closed form nor an iteration (lowest priority first)
+__device__ __noinline__ double front_done_value(int c, unsigned int k, unsigned int N, double prior) {
+    double v = prior >= 1.0 ? 1.0 : 0.0;               // incbet: xx == 1 -> 1, xx == 0 -> 0
+    if (k == N) v = 0.0;                               // bdtrc: k == n
+    if (k > N) v = NAN;                                // bdtrc: n < k
+    if (c <= 0) v = 1.0;                               // bdtrc: k < 0
+    if (!(prior >= 0.0 && prior <= 1.0)) v = NAN;      // NaN or outside [0, 1]
+    return v;
 }
 
 // phase B, second half: prior, ExpCC and the exits of bdtrc / incbet before any real work.  b12 = rn(b1 b2).
@@ -192,25 +210,22 @@ __device__ __forceinline__ PvalClass front_score(const PvalParams &P, const Fron
     const double en = __dmul_rn(dN, prior);
     e = __hiloint2double(__double2hiint(en) & (int)eok, __double2loint(en) & (int)eok);
     // bdtrc(k = c - 1, N, prior) and incbet(c, N - c + 1, prior) up to the first real work (cephes bdtr.h / incbet.h;
-    // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns): lowest priority first.  For c >= 1,
-    // k = c - 1 is compared as an unsigned 32-bit value (c <= 0, i.e. k < 0, is handled on its own).
+    // bdtrc_classify in cephes_dev.cuh is the same ladder with early returns).  k = c - 1 is compared as an unsigned 32-bit
+    // value (c <= 0 wraps to a huge k).  The two classes with real work are decided directly:
+    //   count == 1: the closed form, unless N == 0 (k == N) or the prior is NaN / outside [0, 1]
+    //   count >= 2: an iteration, when k < N and 0 < prior < 1
+    // and everything else that is scored -- rare: counts beyond N, priors of exactly 0 or 1, NaN priors beyond the table --
+    // gets its value from the ladder in front_done_value.
     const unsigned int k = (unsigned int)c - 1u;
-    const bool bad_prior = !(prior >= 0.0 && prior <= 1.0);  // NaN or outside [0, 1]
-    PvalClass cls = kClsDone;
-    double v = 1.0;  // not scored: p = 1
-    if (scored) {
-        v = prior >= 1.0 ? 1.0 : 0.0;  // incbet: xx == 1 -> 1, xx == 0 -> 0 (the values in between are iterated)
-        cls = c == 1 ? kClsK0 : kClsDone;
-        if (k == N) { v = 0.0; cls = kClsDone; }
-        if (k > N) { v = NAN; cls = kClsDone; }
-        if (c <= 0) { v = 1.0; cls = kClsDone; }
-        if (bad_prior) { v = NAN; cls = kClsDone; }
-        if (c >= 2 && k < N && prior > 0.0 && prior < 1.0) {
-            const double dNp1 = intra_path ? F.dNp1_intra : F.dNp1_inter;
-            cls = __dmul_rn(prior, dNp1) > (double)c ? kClsTail : kClsCf;  // x > a / (a + b), a + b = N + 1
-        }
+    const bool k0 = scored & (c == 1) & (N != 0u) & (prior >= 0.0) & (prior <= 1.0);
+    const bool iter = scored & (c >= 2) & (k < N) & (prior > 0.0) & (prior < 1.0);
+    PvalClass cls = k0 ? kClsK0 : kClsDone;
+    if (iter) {
+        const double dNp1 = intra_path ? F.dNp1_intra : F.dNp1_inter;
+        cls = __dmul_rn(prior, dNp1) > (double)c ? kClsTail : kClsCf;  // x > a / (a + b), a + b = N + 1
     }
-    p = v;
+    p = 1.0;  // not scored: p = 1
+    if (scored && !k0 && !iter) p = front_done_value(c, k, N, prior);
     return cls;
 }
 
@@ -582,9 +597,9 @@ __device__ __forceinline__ const double *bias_addr_rng(const PvalParams &P, cons
     // the checks of bias_lookup_rng in unsigned arithmetic: with mid >= 0 the slot rng.x + mid / res cannot wrap
     const unsigned int k = fastdiv31((unsigned int)mid, P, F);  // garbage for mid < 0, masked below
     const unsigned int s = (unsigned int)rng.x + k;
-    bool ok = chr_ok && mid >= 0 && s < (unsigned int)rng.y;
+    bool ok = chr_ok & (mid >= 0) & (s < (unsigned int)rng.y);  // (no short circuits: no branches)
     if (REGULAR)
-        ok = ok && ((unsigned int)mid - k * P.res.d == (P.res.d >> 1));
+        ok = ok & ((unsigned int)mid - k * P.res.d == F.half);
     else
         ok = ok && __ldg(P.bias_mid + (ok ? s : 0u)) == mid;
     return ok ? P.bias + s : minus_one;
@@ -610,8 +625,10 @@ __device__ __forceinline__ void front_addr2(const PvalParams &P, const FrontCons
         a1 = bias_addr_rng<REGULAR>(P, F, r1, ok1, m1, cst);
         a2 = bias_addr_rng<REGULAR>(P, F, r2, ok2, m2, cst);
     }
-    const unsigned int slot = d < 0x80000000u ? fastdiv31(d, P, F) : fastdiv(d, P.res);
-    const bool slot_ok = (INTRA || c1 == c2) && slot < F.D32 && P.lut != nullptr;
+    // the launch code only takes this kernel when the table ends at or below distance 2^31, so a distance of 2^31 or more
+    // (one mid point negative) lies beyond it whatever the quotient is; F.D32 is 0 when there is no table
+    const unsigned int slot = fastdiv31(d, P, F);
+    const bool slot_ok = (INTRA || c1 == c2) & (d < 0x80000000u) & (slot < F.D32);
     at = slot_ok ? P.lut + slot : cst + 1;  // NaN beyond the table (or an inter line, which never uses it)
 }
 
@@ -621,7 +638,7 @@ struct StreamRegs {
 };
 
 template <bool PRE>
-__device__ __forceinline__ void stream_issue(const PvalParams &P, long long pair, StreamRegs &r) {
+__device__ __forceinline__ void stream_issue(const PvalParams &P, unsigned int pair, StreamRegs &r) {  // n < 2^32
     if (PRE) {
         r.a = ldg_stream2(reinterpret_cast<const int2 *>(P.cnt) + pair);
         r.b = ldg_stream2(reinterpret_cast<const int2 *>(P.pre_code) + pair);
@@ -654,10 +671,12 @@ __device__ __noinline__ unsigned int run_lookup2(const long long *run_start, con
 }
 
 // what follows the classification of two contacts: closed form, parking, stores, outlier marks.  Returns their 4 code bits.
-__device__ __forceinline__ unsigned int front2_finish_pair(const PvalParams &P, Front2Smem &S, long long base, int l0, bool full,
+// i0: index of the first of the two contacts in this call's arrays (n < 2^32), l0: its slot in the tile.
+__device__ __forceinline__ unsigned int front2_finish_pair(const PvalParams &P, Front2Smem &S, unsigned int i0, int l0, bool full,
                                                            const int *cc, const PvalClass *cls, const double *prior,
                                                            const bool *use_inter, double *pv, const double *e,
                                                            unsigned int &flagged) {
+    const unsigned int n32 = (unsigned int)P.n;
     unsigned int codes = 0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -672,31 +691,34 @@ __device__ __forceinline__ unsigned int front2_finish_pair(const PvalParams &P, 
         codes |= (unsigned int)cls[k] << (2 * k);
     }
     if (full) {
-        __stcs(reinterpret_cast<double2 *>(P.expcc + base + l0), make_double2(e[0], e[1]));
-        *reinterpret_cast<double2 *>(P.p + base + l0) = make_double2(pv[0], pv[1]);  // default caching: see front_tile
+        __stcs(reinterpret_cast<double2 *>(P.expcc + i0), make_double2(e[0], e[1]));
+        *reinterpret_cast<double2 *>(P.p + i0) = make_double2(pv[0], pv[1]);  // default caching: see front_tile
     } else {
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-            if (base + l0 + k < P.n) {
-                P.expcc[base + l0 + k] = e[k];
-                P.p[base + l0 + k] = pv[k];
+            if (i0 + k < n32) {
+                P.expcc[i0 + k] = e[k];
+                P.p[i0 + k] = pv[k];
             }
     }
     if (P.outl != nullptr) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-            if ((cls[k] == kClsDone || cls[k] == kClsK0) && base + l0 + k < P.n) outlier_mark(P, base + l0 + k, pv[k], flagged);
+            if ((cls[k] == kClsDone || cls[k] == kClsK0) && (full || i0 + k < n32))
+                outlier_mark(P, (long long)(i0 + k), pv[k], flagged);
     }
     return codes;
 }
 
 // One tile.  `nx` holds the streamed words of this tile's first group when the tile is full (loaded by the previous tile or
 // the prologue) and leaves with those of the first group of the tile at next_base (-1: nothing to load ahead).
+// pair0 = (first contact of the tile) / 2 + tid: this thread's pair of group 0; next_pair0: the same of the CTA's next tile.
 template <bool HAS_BIAS, bool REGULAR, bool INTRA, bool PRE>
 __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const FrontConst &F, Front2Smem &S, bool rng32,
-                                                    long long base, bool full, bool tile_one_run, unsigned int tile_ch,
-                                                    StreamRegs &nx, long long next_base, unsigned int &flagged) {
+                                                    unsigned int pair0, bool full, bool tile_one_run, unsigned int tile_ch,
+                                                    StreamRegs &nx, unsigned int next_pair0, unsigned int &flagged) {
     const int tid = threadIdx.x;
+    const unsigned int n32 = (unsigned int)P.n;
     int2 rng = make_int2(0, 0);
     bool chr_ok = false;
     if (!PRE && INTRA && HAS_BIAS && rng32) {
@@ -710,11 +732,11 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
         const int l0 = (h * kFrontThreads + tid) * 2;
+        const unsigned int pr = pair0 + h * kFrontThreads, i0 = 2u * pr;
         StreamRegs cur;
         if (full) {
             cur = nx;
-            const long long ahead = h < 3 ? base + l0 + 2 * kFrontThreads : next_base + 2 * tid;
-            if (h < 3 || next_base >= 0) stream_issue<PRE>(P, ahead >> 1, nx);
+            if (h < 3 || next_pair0 != 0xffffffffu) stream_issue<PRE>(P, h < 3 ? pr + kFrontThreads : next_pair0, nx);
         }
         int cc[2];
         PvalClass cls[2];
@@ -730,8 +752,8 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
             } else {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const long long i = base + l0 + k;
-                    const bool ok = i < P.n;
+                    const unsigned int i = i0 + k;
+                    const bool ok = i < n32;
                     cc[k] = ok ? reinterpret_cast<const int *>(P.cnt)[i] : 0;
                     pc[k] = ok ? P.pre_code[i] : kPreNotScored;
                     b12[k] = ok ? P.pre_b12[i] : 1.0;
@@ -741,7 +763,7 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
 #pragma unroll
             for (int k = 0; k < 2; ++k) {  // the one gather that is left (NaN where the line uses no table value)
                 const unsigned int slot = pc[k] & kPreSlotMask;
-                const bool want = pc[k] != kPreNotScored && !(pc[k] & kPreInter) && slot < F.D32 && P.lut != nullptr;
+                const bool want = (pc[k] != kPreNotScored) & !(pc[k] & kPreInter) & (slot < F.D32);  // D32 = 0: no table
                 gtv[k] = __ldg(want ? P.lut + slot : reinterpret_cast<const double *>(g_front_consts) + 1);
             }
 #pragma unroll
@@ -760,19 +782,19 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
                 m2[0] = cur.b.x; m2[1] = cur.b.y;
                 cc[0] = cur.c.x; cc[1] = cur.c.y;
                 if (!INTRA && P.chrs != nullptr) {
-                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + ((base + l0) >> 1));
+                    const int2 ah = ldg_stream2(reinterpret_cast<const int2 *>(P.chrs) + pr);
                     ch[0] = (unsigned int)ah.x; ch[1] = (unsigned int)ah.y;
                 } else {
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
                         ch[k] = (INTRA || tile_one_run) ? tile_ch
-                                                        : run_lookup2(P.run_start, P.run_val, P.nruns, P.line_base + base + l0 + k);
+                                                        : run_lookup2(P.run_start, P.run_val, P.nruns, P.line_base + (i0 + k));
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const long long i = base + l0 + k;
-                    const bool ok = i < P.n;
+                    const unsigned int i = i0 + k;
+                    const bool ok = i < n32;
                     m1[k] = ok ? reinterpret_cast<const int *>(P.mid1)[i] : 0;
                     m2[k] = ok ? reinterpret_cast<const int *>(P.mid2)[i] : 0;
                     cc[k] = ok ? reinterpret_cast<const int *>(P.cnt)[i] : 0;
@@ -806,19 +828,19 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const bool in_file = full || base + l0 + k < P.n;
+                const bool in_file = full || i0 + k < n32;
                 cls[k] = front_prepare<INTRA>(P, F, dd[k], cc[k], ch[k], in_file, gb1[k], gb2[k], gtv[k], pv[k], e[k], prior[k],
                                               use_inter[k]);
             }
         }
-        codes |= front2_finish_pair(P, S, base, l0, full, cc, cls, prior, use_inter, pv, e, flagged) << (4 * h);
+        codes |= front2_finish_pair(P, S, i0, l0, full, cc, cls, prior, use_inter, pv, e, flagged) << (4 * h);
     }
     return codes;
 }
 
 // list positions for the items of one warp and their stores (see the note above)
-__device__ __forceinline__ void front2_append(const ListsWs &W, const Front2Smem &S, unsigned int codes, long long base, int tid,
-                                              int lane) {
+__device__ __forceinline__ void front2_append(const ListsWs &W, const Front2Smem &S, unsigned int codes, unsigned int base,
+                                              int tid, int lane) {
     unsigned int mine = 0;  // continued fractions | tail sums << 16 of this thread (<= 8 each)
 #pragma unroll
     for (int s8 = 0; s8 < 8; ++s8) {
@@ -847,7 +869,7 @@ __device__ __forceinline__ void front2_append(const ListsWs &W, const Front2Smem
             const int li = ((s8 >> 1) * kFrontThreads + tid) * 2 + (s8 & 1);
             WorkItem it;
             it.x = S.x[li];
-            it.idx = (unsigned int)(base + li);
+            it.idx = base + (unsigned int)li;
             it.cnt = S.cnt[li];
             if (c == kClsCf)
                 W.items[oCf++] = it;
@@ -877,30 +899,33 @@ __global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front2_kernel(co
     StreamRegs nx;
     nx.a = nx.b = nx.c = make_int2(0, 0);
     nx.d = make_double2(0.0, 0.0);
-    if (blockIdx.x < nfull) stream_issue<PRE>(P, ((long long)blockIdx.x * kFrontTile + 2 * tid) >> 1, nx);
+    if (blockIdx.x < nfull) stream_issue<PRE>(P, blockIdx.x * (kFrontTile / 2) + tid, nx);
 
     for (unsigned int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long base = (long long)tile * kFrontTile;
+        const unsigned int base = tile * kFrontTile;  // < 2^32
         const bool full = tile < nfull;
         const unsigned int tnext = tile + gridDim.x;
-        const long long next_base = tnext < nfull ? (long long)tnext * kFrontTile : -1;
+        const unsigned int pair0 = tile * (kFrontTile / 2) + tid;
+        const unsigned int next_pair0 = tnext < nfull ? tnext * (kFrontTile / 2) + tid : 0xffffffffu;
         bool one_run = false;
         unsigned int tile_ch = 0;
         if (runs) {
             const long long g0 = P.line_base + base;
             long long next_start = __ldg(P.run_start + run + 1);
             while (next_start <= g0) next_start = __ldg(P.run_start + (++run) + 1);
-            const long long g1 = P.line_base + (full ? base + kFrontTile : P.n);
+            const long long g1 = P.line_base + (full ? (long long)base + kFrontTile : P.n);
             one_run = next_start >= g1;
             tile_ch = __ldg(P.run_val + run);
         }
         unsigned int codes;
         if (PRE)
-            codes = front2_tile<false, true, false, true>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+            codes = front2_tile<false, true, false, true>(P, F, S, rng32, pair0, full, one_run, tile_ch, nx, next_pair0, flagged);
         else if (one_run && full && (tile_ch & 0xffffu) == (tile_ch >> 16) && P.mode != FHC_MODE_INTER_ONLY)
-            codes = front2_tile<HAS_BIAS, REGULAR, true, false>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+            codes = front2_tile<HAS_BIAS, REGULAR, true, false>(P, F, S, rng32, pair0, full, one_run, tile_ch, nx, next_pair0,
+                                                                flagged);
         else
-            codes = front2_tile<HAS_BIAS, REGULAR, false, false>(P, F, S, rng32, base, full, one_run, tile_ch, nx, next_base, flagged);
+            codes = front2_tile<HAS_BIAS, REGULAR, false, false>(P, F, S, rng32, pair0, full, one_run, tile_ch, nx, next_pair0,
+                                                                 flagged);
         front2_append(W, S, codes, base, tid, lane);
     }
     if (P.outl != nullptr) {
@@ -1203,7 +1228,8 @@ static FrontConst make_front_const(const PvalParams &P) {
     while ((1ull << l) < d) ++l;  // ceil(log2 d)
     F.div_sh = l ? l - 1 : 0;
     F.div_m = d > 1 ? (unsigned int)(((1ull << (31 + l)) + d - 1) / d) : 0u;
-    F.D32 = (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
+    F.D32 = P.lut == nullptr ? 0u : (unsigned int)(P.D > 0xffffffffll ? 0xffffffffll : P.D);
+    F.half = d >> 1;
     return F;
 }
 
@@ -1277,7 +1303,10 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     // gathers issued one pair ahead (6.65 ms: the extra barriers cost more than the staging saves); an L2 prefetch of the
     // CTA's next tile (4.02 ms with, 4.04 ms without).
     const char *fv = getenv("FHC_PVAL_FRONT");
-    const bool v1 = fv && fv[0] == 'v' && fv[1] == '1';
+    // (the second version drops the 64-bit division for distances of 2^31 and more -- one mid point negative --, which is
+    // only right while such a distance lies beyond the table: a table that reaches further goes to the first version)
+    const bool wide_table = (unsigned long long)F.D32 * P.res.d > 0x80000000ull;
+    const bool v1 = (fv && fv[0] == 'v' && fv[1] == '1') || wide_table;
     const bool o5 = fv && fv[0] == 'v' && fv[1] == '2' && fv[2] == 'o' && fv[3] == '5';  // 48 registers, 5 CTAs per SM
     if (blocks > (long long)kNumSMs * (o5 ? 5 : 4)) blocks = (long long)kNumSMs * (o5 ? 5 : 4);
 #define FHC_FRONT_V(B, R, PRE)                                                                                         \
