@@ -728,7 +728,11 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
     }
     unsigned int codes = 0;
     // not unrolled: four copies of the group body are 58 KB of instructions, and without a barrier the warps of an SM
-    // spread over all of it (ncu on the unrolled form: 1.9 warps per issue slot waiting for an instruction fetch)
+    // spread over all of it (ncu on the unrolled form: 1.9 warps per issue slot waiting for an instruction fetch).
+    // Measured and dropped (B200, 300 M contacts, this loop at 2.64 ms): the loop rotated so that the closed forms and
+    // stores of group h - 1 run between the gathers of group h and their first use (2.97 ms: the carried state costs
+    // registers, 24 B spilled, one more trip); 48 registers and 5 CTAs per SM (FHC_PVAL_FRONT=v2o5: 3.5 ms before, 4.2 ms
+    // after the instruction diet -- the spills weigh more the fewer instructions are left).
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
         const int l0 = (h * kFrontThreads + tid) * 2;
@@ -1167,6 +1171,8 @@ __global__ void lbeta_aux_kernel(const double *__restrict__ tab, long long ntab,
 
 // Two items per thread and iteration: their four 16-byte loads are issued before the first logarithm starts (the kernel
 // waits on memory, not on arithmetic: two thirds of its stall samples sat on these loads with one item per thread).
+// Measured and dropped: the four loads of the NEXT iteration issued before the current two items are worked on (1.40 ms
+// against 1.25 ms: 16 more live registers at the 80 the kernel has, 200 B spilled).
 template <int kMinCtas>
 __global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(const PvalParams P, const ListsWs W) {
     const unsigned long long nCf = W.ctr[0] & 0xffffffffull, nTail = W.ctr[0] >> 32;

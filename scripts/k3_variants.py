@@ -25,7 +25,7 @@ VARIANTS = [
     ("lists: front v2 (default)", {}),
     ("lists: front v1", {"FHC_PVAL_FRONT": "v1"}),
 ]
-KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN", "FHC_PREPASS")
+KEYS = ("FHC_PVAL_FRONT", "FHC_PVAL_FINISH_OCC", "FHC_PVAL_IMPL", "FHC_BH_TIGHTEN", "FHC_PREPASS", "FHC_PVAL_FINISH")
 if os.environ.get("K3V_ONLY"):
     VARIANTS = VARIANTS[:int(os.environ["K3V_ONLY"])]
 print("line order:", order)
