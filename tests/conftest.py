@@ -43,9 +43,16 @@ def lib():
     return _capi.load()
 
 
-@pytest.fixture(params=["lists", "tile"])
+@pytest.fixture(params=["lists", "lists-front-v1", "tile"])
 def pval_impl(request, monkeypatch):
-    """K3 has two implementations behind fhc_pvalues (work-list pipeline / tile-phased kernel); the library reads
-    FHC_PVAL_IMPL on every call, so a module that uses this fixture runs each of its tests through both."""
-    monkeypatch.setenv("FHC_PVAL_IMPL", request.param)
-    return request.param
+    """K3 has two implementations behind fhc_pvalues (work-list pipeline / tile-phased kernel), and the work-list
+    pipeline two versions of its front kernel (the first one is what a distance table reaching beyond 2^31 falls back
+    to); the library reads FHC_PVAL_IMPL and FHC_PVAL_FRONT on every call, so a module that uses this fixture runs each
+    of its tests through all three."""
+    impl, _, front = request.param.partition("-front-")
+    monkeypatch.setenv("FHC_PVAL_IMPL", impl)
+    if front:
+        monkeypatch.setenv("FHC_PVAL_FRONT", front)
+    else:
+        monkeypatch.delenv("FHC_PVAL_FRONT", raising=False)
+    return impl

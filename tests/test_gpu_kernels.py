@@ -25,6 +25,127 @@ def stream():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# K3 on inputs no reader would produce: the three implementations must agree on every line
+# ---------------------------------------------------------------------------------------------------------------------
+def _dirty_contacts(rng, n, res, nchr, per_chr_loci):
+    """Contacts as runs of chromosome pairs with everything a front kernel has a branch for: mid points off the grid,
+    negative, beyond the chromosome; chromosome ids beyond the bias table; inter lines; counts of 0, negative, 1 and huge;
+    distances beyond the table."""
+    run_len = rng.integers(1, 6000, size=64)
+    run_len = (run_len * (n / run_len.sum())).astype(np.int64)
+    run_len[-1] += n - run_len.sum()
+    run_len = run_len[run_len > 0]
+    c1 = rng.integers(0, nchr + 2, size=len(run_len))  # nchr, nchr + 1: not in the bias table
+    c2 = np.where(rng.random(len(run_len)) < 0.7, c1, rng.integers(0, nchr + 2, size=len(run_len)))
+    run_val = (c1 | (c2 << 16)).astype(np.uint32)
+    chrs = np.repeat(run_val, run_len)
+    span = per_chr_loci * res
+    mid1 = (rng.integers(0, per_chr_loci, size=n) * res + res // 2).astype(np.int64)
+    mid2 = mid1 + rng.integers(0, 400, size=n) * res
+    dirty = rng.random(n)
+    mid2 = np.where(dirty < 0.03, mid2 + 7, mid2)                      # off the grid
+    mid1 = np.where((dirty > 0.03) & (dirty < 0.05), -mid1 - 1, mid1)  # negative
+    mid2 = np.where((dirty > 0.05) & (dirty < 0.07), mid2 + span, mid2)  # beyond the chromosome's slots
+    mid1 = np.where((dirty > 0.07) & (dirty < 0.08), 2_147_483_000, mid1)  # with a negative partner: distance >= 2^31
+    mid2 = np.where((dirty > 0.07) & (dirty < 0.08), -2500, mid2)
+    cnt = rng.geometric(0.45, size=n).astype(np.int64)
+    cnt = np.where(dirty > 0.98, rng.integers(-3, 1, size=n), cnt)
+    cnt = np.where((dirty > 0.96) & (dirty < 0.98), rng.integers(1000, 200_000, size=n), cnt)
+    swap = rng.random(n) < 0.5
+    m1 = np.where(swap, mid2, mid1)
+    m2 = np.where(swap, mid1, mid2)
+    return m1.astype(np.int32), m2.astype(np.int32), cnt.astype(np.int32), chrs, run_val, run_len
+
+
+@pytest.mark.parametrize("mode,with_bias,regular,LU", [
+    (_capi.MODE_INTRA_ONLY, True, True, (0, -1)),
+    (_capi.MODE_INTRA_ONLY, True, False, (20000, 1_000_000)),
+    (_capi.MODE_INTRA_ONLY, False, True, (0, -1)),
+    (_capi.MODE_ALL, True, True, (0, -1)),
+    (_capi.MODE_INTER_ONLY, True, True, (0, -1)),
+])
+def test_pvalues_on_dirty_lines_all_implementations_agree(lib, monkeypatch, mode, with_bias, regular, LU):
+    """fhc_pvalues through the tile-phased kernel (the most literal restatement of fit_Spline's branch order,
+    pvalue_common.cuh), the first and the second front kernel of the work-list pipeline, with the chromosome ids as an
+    array and as runs, the second one also behind fhc_pvalues_prepass: p and ExpCC agree on every line -- bit for bit between
+    the front kernels (same arithmetic), within 1e-12 and with the same NaN pattern against the tile kernel."""
+    rng = np.random.default_rng(77)
+    n, res, nchr, loci = 200_003, 5000, 5, 3000
+    m1, m2, cnt, chrs, run_val, run_len = _dirty_contacts(rng, n, res, nchr, loci)
+    D = 350  # shorter than the longest distance: lines beyond the table get a NaN prior
+    lut = np.exp(-np.arange(D) / 60.0) * 2e-8
+    lut[0] = 0.0  # a prior of exactly 0
+    lut[1] = 1.0  # ... and of exactly 1 (times a bias of 1: the incbet exits)
+    bias = np.exp(rng.normal(0.0, 0.4, size=nchr * loci))
+    bias[rng.random(len(bias)) < 0.03] = -1.0  # discarded loci
+    bias[rng.random(len(bias)) < 0.01] = 1.0
+    bias[5] = np.nan
+    chr_off = (np.arange(nchr + 1) * loci).astype(np.int64)
+    bias_mid = (np.tile(np.arange(loci), nchr) * res + res // 2).astype(np.int32)
+    bias_mid[::97] += 1  # slots read for another mid point: "missing"
+    N_intra, N_inter = 40_000_000, 7_000_000
+    starts = np.concatenate([[0], np.cumsum(run_len)]).astype(np.int64)
+    d = {k: dev(v) for k, v in dict(m1=m1, m2=m2, cnt=cnt, chrs=chrs.view(np.int32), lut=lut, bias=bias, off=chr_off,
+                                    bmid=bias_mid, rs=starts, rv=run_val.view(np.int32)).items()}
+    ntab = 4096
+    tabs = []
+    for N in (N_intra, N_inter):
+        h = np.empty(ntab)
+        check(lib.fhc_host_lbeta_table(N, dptr(h), ntab, 2))
+        tabs.append(dev(h))
+    wsb = int(lib.fhc_pvalues_workspace_bytes(n, ntab))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    L, U = LU
+    no_lut = mode == _capi.MODE_INTER_ONLY
+
+    def run(impl, front, runs, prepass=False):
+        monkeypatch.setenv("FHC_PVAL_IMPL", impl)
+        if front:
+            monkeypatch.setenv("FHC_PVAL_FRONT", front)
+        else:
+            monkeypatch.delenv("FHC_PVAL_FRONT", raising=False)
+        p = torch.full((n,), -7.0, dtype=torch.float64, device=DEV)
+        e = torch.full((n,), -7.0, dtype=torch.float64, device=DEV)
+        b = dptr(d["bias"]) if with_bias else None
+        bm = dptr(d["bmid"]) if (with_bias and not regular) else None
+        off = dptr(d["off"]) if with_bias else None
+        code = b12 = None
+        if prepass:
+            code = torch.empty(n, dtype=torch.int32, device=DEV)
+            b12 = torch.empty(n, dtype=torch.float64, device=DEV)
+            check(lib.fhc_pvalues_prepass(mode, dptr(d["m1"]), dptr(d["m2"]), None if runs else dptr(d["chrs"]),
+                                          dptr(d["rs"]) if runs else None, dptr(d["rv"]) if runs else None,
+                                          len(run_len) if runs else 0, n, b, bm, off, nchr if with_bias else 0, 0, res, L, U,
+                                          0.5, 2.0, 0, dptr(code), dptr(b12), stream()))
+        check(lib.fhc_pvalues(mode, dptr(d["m1"]), dptr(d["m2"]), dptr(d["cnt"]), None if runs else dptr(d["chrs"]),
+                              dptr(d["rs"]) if runs else None, dptr(d["rv"]) if runs else None, len(run_len) if runs else 0, n,
+                              b, bm, off, nchr if with_bias else 0, 0, res, L, U, None if no_lut else dptr(d["lut"]),
+                              0 if no_lut else D, N_intra, N_inter, 3e-9, 0.5, 2.0, dptr(tabs[0]), ntab, dptr(tabs[1]), ntab,
+                              None, 0, 0.0, None, dptr(p), dptr(e), dptr(code), dptr(b12), dptr(ws), wsb, stream()))
+        torch.cuda.synchronize()
+        return p.cpu().numpy(), e.cpu().numpy()
+
+    p_tile, e_tile = run("tile", None, False)
+    assert not (p_tile == -7.0).any() and not (e_tile == -7.0).any()
+    assert (p_tile == 1.0).any() and ((p_tile > 0) & (p_tile < 1)).any()
+    if mode != _capi.MODE_INTER_ONLY and LU == (0, -1):  # every class of line is present
+        assert np.isnan(p_tile).any() and (p_tile == 0.0).any()
+    ref = None
+    for front in ("v1", "v2"):
+        for runs in (False, True):
+            for prepass in ((False, True) if front == "v2" else (False,)):
+                p, e = run("lists", front, runs, prepass)
+                what = (front, "runs" if runs else "array", "prepass" if prepass else "")
+                assert np.array_equal(np.isnan(p), np.isnan(p_tile)), what
+                ok = ~np.isnan(p)
+                assert np.array_equal(e, e_tile, equal_nan=True), what
+                assert rel_err(p[ok], p_tile[ok]) <= 1e-12, what
+                if ref is None:
+                    ref = p
+                assert np.array_equal(p, ref, equal_nan=True), what
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # K3 arithmetic: scipy.special.bdtrc
 # ---------------------------------------------------------------------------------------------------------------------
 def gpu_bdtrc(lib, km1, N, prior, with_table=True):
