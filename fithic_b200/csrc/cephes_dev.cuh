@@ -372,6 +372,33 @@ FHC_HD double incbet_finish(bool tail, double aa, double bb, double xx, double l
 // State in a CfState: P = pkm1, Q = qkm1 (value = pkm1 / qkm1 as for the fractions), A = pkm2, j = fi, d_j = dprev, cN = z,
 // 1/N = a.
 FHC_HD double tail_cn(double N, double x, double one_minus_x) { return one_minus_x * (1.0 / (x * N)); }
+// Sums of at most kTailInline terms (counts up to kTailInline + 1) stay out of the work queue of the iterate kernel, where
+// handing an item to a lane costs ~100 instructions (and only ~7 of 32 lanes take one per trip) against ~10 per term:
+// pval_finish_kernel runs the same recurrence in place for them.  A warp pays for the longest sum among its lanes -- on the
+// bench input 1.8 terms per item on average, ~10 trips per warp with a limit of 16 -- which is still a seventh of what the
+// queue costs per item.  Measured (B200, 300 M contacts; iterate + finish): everything queued 1.83 + 1.25 ms; limit 4
+// 1.49 + 1.50; limit 16 with the queue's own step function (renormalisation included) 0.81 + 1.96.
+constexpr int kTailInline = 32;
+FHC_HD bool tail_is_short(int count) { return count - 1 <= kTailInline; }
+// tail_fwd_load + tail_fwd_step (below) for such a sum: the same operations on the same operands, without the
+// renormalisation, which cannot trigger here (Q is a product of at most kTailInline factors (N - j + 1) / N with
+// j <= kTailInline < N: never below 33! / 33^32 = 2e-12, far from 2^-100).  Returns P; Q in *q.
+FHC_HD double tail_short_sum(double count, double N, double invN, double cN, double *q) {
+    double A = 1.0, P = 1.0, Q = 1.0;
+    double fi = count - 1.0;
+    double d = (N - fi + 1.0) * invN;
+    bool live = fi > 0.0;
+    while (live) {
+        A *= fi * cN;
+        Q *= d;
+        P = fma(P, d, A);
+        fi -= 1.0;
+        d += invN;
+        live = !(fi <= 0.0 || A < 1e-21 * P);
+    }
+    *q = Q;
+    return P;
+}
 FHC_HD void tail_fwd_load(CfState &s, double count, double N, double invN, double cN) {
     s.a = invN;
     s.z = cN;

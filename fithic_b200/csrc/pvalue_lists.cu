@@ -1065,9 +1065,14 @@ __global__ void __launch_bounds__(256, 4) pval_prepass_kernel(const PvalParams P
 struct __align__(16) Staged {
     double zc;  // continued fraction: z = x or x / (1 - x); tail sum: cN = (1 - x) / (x N)
     int cnt;    // count | inter << 31
-    int use_d;  // continued fraction: cephes incbd instead of incbcf
+    int aux;    // bit 0: continued fraction by cephes incbd instead of incbcf; bits 1...: position of the item in its chunk
 };
 
+// Tail sums of a few terms stay out of the queue (tail_is_short, cephes_dev.cuh): while a chunk is staged -- all lanes
+// busy, ~10 instructions per item -- the items that remain are compacted to the front of the warp's slice.  (ncu before
+// that, bench input with counts around their expectation: 12.4 M trips through the tail loop against 1.6 M through the
+// continued fractions, 7 lanes refilled per trip, almost every item finished after one or two terms -- 80 % of the
+// kernel was spent handing out items.)
 template <bool TAIL>
 __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs &W, unsigned long long total,
                                              unsigned long long *cursor, int lane, Staged *stage) {
@@ -1075,59 +1080,72 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
     CfState st;
     long long pos = -1;
     unsigned long long base = 0;
-    unsigned int lo = 0, hi = 0;  // positions of the chunk not handed out yet: base + [lo, hi)
+    unsigned int lo = 0, hi = 0;  // staged items of the chunk not handed out yet: stage[lo, hi)
     bool drained = false;
+    const unsigned int lt = (1u << lane) - 1u;
     while (true) {
         const unsigned int m = __ballot_sync(0xffffffffu, pos < 0);
         if (m != 0 && !drained) {
-            if (lo >= hi) {
+            while (lo >= hi && !drained) {  // claim chunks until one holds work or the list ends
                 unsigned long long b = 0;
                 if (lane == 0) b = atomicAdd(cursor, (unsigned long long)kIterChunk);
                 b = __shfl_sync(0xffffffffu, b, 0);
                 base = b;
                 lo = 0;
-                hi = b < total ? (unsigned int)(total - b < (unsigned long long)kIterChunk ? total - b : kIterChunk) : 0u;
-                if (hi == 0) {
+                hi = 0;
+                const unsigned int nchunk =
+                    b < total ? (unsigned int)(total - b < (unsigned long long)kIterChunk ? total - b : kIterChunk) : 0u;
+                if (nchunk == 0) {
                     drained = true;
-                } else {
-                    __syncwarp();  // every lane has read what it needed from the previous chunk
+                    break;
+                }
+                __syncwarp();  // every lane has read what it needed from the previous chunk
 #pragma unroll
-                    for (int r = 0; r < kIterChunk / 32; ++r) {
-                        const unsigned int i = r * 32 + lane;
-                        if (i < hi) {
-                            const long long ip = TAIL ? (W.cap - 1 - (long long)(base + i)) : (long long)(base + i);
-                            const WorkItem it = W.items[ip];
+                for (int r = 0; r < kIterChunk / 32; ++r) {
+                    const unsigned int i = r * 32 + lane;
+                    bool keep = false;
+                    Staged sg;
+                    sg.zc = 0.0;
+                    sg.cnt = 0;
+                    sg.aux = 0;
+                    if (i < nchunk) {
+                        const long long ip = TAIL ? (W.cap - 1 - (long long)(base + i)) : (long long)(base + i);
+                        const WorkItem it = W.items[ip];
+                        keep = !TAIL || !tail_is_short(it.cnt & 0x7fffffff);
+                        if (keep) {
                             const bool ui = it.cnt < 0;
                             const double dN = (double)(ui ? P.N_inter : P.N_intra);
-                            Staged sg;
                             sg.cnt = it.cnt;
                             if (TAIL) {
                                 sg.zc = tail_cn(dN, it.x, __dsub_rn(1.0, it.x));
-                                sg.use_d = 0;
+                                sg.aux = (int)(i << 1);
                             } else {
                                 const double aa = (double)(it.cnt & 0x7fffffff);
                                 const bool use_d = cf_uses_d(aa, dN - aa + 1.0, it.x);
                                 sg.zc = cf_z(it.x, use_d);
-                                sg.use_d = use_d ? 1 : 0;
+                                sg.aux = (int)(i << 1) | (use_d ? 1 : 0);
                             }
-                            stage[i] = sg;
                         }
                     }
-                    __syncwarp();
+                    const unsigned int bm = __ballot_sync(0xffffffffu, keep);
+                    if (keep) stage[hi + (unsigned int)__popc(bm & lt)] = sg;
+                    hi += (unsigned int)__popc(bm);
                 }
+                __syncwarp();
             }
             if (pos < 0 && !drained) {
-                const unsigned int k = lo + (unsigned int)__popc(m & ((1u << lane) - 1u));
+                const unsigned int k = lo + (unsigned int)__popc(m & lt);
                 if (k < hi) {
                     const Staged sg = stage[k];
-                    pos = TAIL ? (W.cap - 1 - (long long)(base + k)) : (long long)(base + k);
+                    const unsigned int off = (unsigned int)sg.aux >> 1;
+                    pos = TAIL ? (W.cap - 1 - (long long)(base + off)) : (long long)(base + off);
                     const bool ui = sg.cnt < 0;
                     const double dN = (double)(ui ? P.N_inter : P.N_intra);
                     const double aa = (double)(sg.cnt & 0x7fffffff);
                     if (TAIL)
                         tail_fwd_load(st, aa, dN, ui ? P.invN_inter : P.invN_intra, sg.zc);
                     else
-                        cf_load(st, aa, dN - aa + 1.0, sg.zc, sg.use_d != 0);
+                        cf_load(st, aa, dN - aa + 1.0, sg.zc, (sg.aux & 1) != 0);
                 }
             }
             const unsigned int adv = lo + (unsigned int)__popc(m);
@@ -1208,7 +1226,17 @@ __global__ void __launch_bounds__(kFinishThreads, kMinCtas) pval_finish_kernel(c
                 const double lb = lbeta_cephes(aa, bb);
                 a = make_double2(lb + log(aa), lb + log(bb));
             }
-            const double p = incbet_finish_folded(tail[j], aa, bb, it[j].x, a.x, a.y, pq[j].x / pq[j].y);
+            double w;
+            if (tail[j] && tail_is_short(c)) {  // the few terms of a short tail sum, as pval_iterate_kernel would run them
+                const double dN = (double)N;
+                double q;
+                const double pn = tail_short_sum(aa, dN, ui ? P.invN_inter : P.invN_intra,
+                                                 tail_cn(dN, it[j].x, __dsub_rn(1.0, it[j].x)), &q);
+                w = pn / q;
+            } else {
+                w = pq[j].x / pq[j].y;
+            }
+            const double p = incbet_finish_folded(tail[j], aa, bb, it[j].x, a.x, a.y, w);
             P.p[it[j].idx] = p;
             if (P.outl != nullptr) outlier_mark(P, (long long)it[j].idx, p, flagged);
         }
