@@ -1083,13 +1083,16 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
     unsigned int lo = 0, hi = 0;  // staged items of the chunk not handed out yet: stage[lo, hi)
     bool drained = false;
     const unsigned int lt = (1u << lane) - 1u;
+    // the next chunk is claimed one chunk ahead (the round trip of the atomic hides behind the staging of the current one;
+    // claims beyond the end of the list only move the cursor)
+    unsigned long long claimed = 0;
+    if (lane == 0) claimed = atomicAdd(cursor, (unsigned long long)kIterChunk);
     while (true) {
         const unsigned int m = __ballot_sync(0xffffffffu, pos < 0);
         if (m != 0 && !drained) {
-            while (lo >= hi && !drained) {  // claim chunks until one holds work or the list ends
-                unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(cursor, (unsigned long long)kIterChunk);
-                b = __shfl_sync(0xffffffffu, b, 0);
+            while (lo >= hi && !drained) {  // take chunks until one holds work or the list ends
+                const unsigned long long b = __shfl_sync(0xffffffffu, claimed, 0);
+                if (lane == 0 && b < total) claimed = atomicAdd(cursor, (unsigned long long)kIterChunk);
                 base = b;
                 lo = 0;
                 hi = 0;
@@ -1100,6 +1103,16 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
                     break;
                 }
                 __syncwarp();  // every lane has read what it needed from the previous chunk
+                WorkItem its[kIterChunk / 32];  // all loads of the chunk in flight before the first one is looked at
+#pragma unroll
+                for (int r = 0; r < kIterChunk / 32; ++r) {
+                    const unsigned int i = r * 32 + lane;
+                    const long long ip = TAIL ? (W.cap - 1 - (long long)(base + i)) : (long long)(base + i);
+                    its[r].x = 0.0;
+                    its[r].idx = 0u;
+                    its[r].cnt = 0;
+                    if (i < nchunk) its[r] = W.items[ip];
+                }
 #pragma unroll
                 for (int r = 0; r < kIterChunk / 32; ++r) {
                     const unsigned int i = r * 32 + lane;
@@ -1109,8 +1122,7 @@ __device__ __forceinline__ void iterate_list(const PvalParams &P, const ListsWs 
                     sg.cnt = 0;
                     sg.aux = 0;
                     if (i < nchunk) {
-                        const long long ip = TAIL ? (W.cap - 1 - (long long)(base + i)) : (long long)(base + i);
-                        const WorkItem it = W.items[ip];
+                        const WorkItem it = its[r];
                         keep = !TAIL || !tail_is_short(it.cnt & 0x7fffffff);
                         if (keep) {
                             const bool ui = it.cnt < 0;
