@@ -731,8 +731,8 @@ __device__ __forceinline__ unsigned int front2_tile(const PvalParams &P, const F
     // spread over all of it (ncu on the unrolled form: 1.9 warps per issue slot waiting for an instruction fetch).
     // Measured and dropped (B200, 300 M contacts, this loop at 2.64 ms): the loop rotated so that the closed forms and
     // stores of group h - 1 run between the gathers of group h and their first use (2.97 ms: the carried state costs
-    // registers, 24 B spilled, one more trip); 48 registers and 5 CTAs per SM (FHC_PVAL_FRONT=v2o5: 3.5 ms before, 4.2 ms
-    // after the instruction diet -- the spills weigh more the fewer instructions are left).
+    // registers, 24 B spilled, one more trip); 48 registers and 5 CTAs per SM (3.5 ms before, 4.2 ms
+    // after the instruction diet -- the spills weigh more the fewer instructions are left; the switch is gone).
 #pragma unroll 1
     for (int h = 0; h < 4; ++h) {
         const int l0 = (h * kFrontThreads + tid) * 2;
@@ -883,8 +883,8 @@ __device__ __forceinline__ void front2_append(const ListsWs &W, const Front2Smem
     }
 }
 
-template <bool HAS_BIAS, bool REGULAR, bool PRE, int kMinCtas>
-__global__ void __launch_bounds__(kFrontThreads, kMinCtas) pval_front2_kernel(const PvalParams P, const FrontConst F, const ListsWs W) {
+template <bool HAS_BIAS, bool REGULAR, bool PRE>
+__global__ void __launch_bounds__(kFrontThreads, 4) pval_front2_kernel(const PvalParams P, const FrontConst F, const ListsWs W) {
     extern __shared__ __align__(16) unsigned char front_smem[];
     Front2Smem &S = *reinterpret_cast<Front2Smem *>(front_smem);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -1353,16 +1353,13 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     // only right while such a distance lies beyond the table: a table that reaches further goes to the first version)
     const bool wide_table = (unsigned long long)F.D32 * P.res.d > 0x80000000ull;
     const bool v1 = (fv && fv[0] == 'v' && fv[1] == '1') || wide_table;
-    const bool o5 = fv && fv[0] == 'v' && fv[1] == '2' && fv[2] == 'o' && fv[3] == '5';  // 48 registers, 5 CTAs per SM
-    if (blocks > (long long)kNumSMs * (o5 ? 5 : 4)) blocks = (long long)kNumSMs * (o5 ? 5 : 4);
+    if (blocks > (long long)kNumSMs * 4) blocks = (long long)kNumSMs * 4;
 #define FHC_FRONT_V(B, R, PRE)                                                                                         \
     do {                                                                                                               \
         if (v1)                                                                                                        \
             pval_front_kernel<B, R, 4, 2, PRE><<<(unsigned int)blocks, kFrontThreads, sizeof(FrontSmem), st>>>(P, F, W);  \
-        else if (o5)                                                                                                   \
-            pval_front2_kernel<B, R, PRE, 5><<<(unsigned int)blocks, kFrontThreads, sizeof(Front2Smem), st>>>(P, F, W); \
         else                                                                                                           \
-            pval_front2_kernel<B, R, PRE, 4><<<(unsigned int)blocks, kFrontThreads, sizeof(Front2Smem), st>>>(P, F, W); \
+            pval_front2_kernel<B, R, PRE><<<(unsigned int)blocks, kFrontThreads, sizeof(Front2Smem), st>>>(P, F, W); \
     } while (0)
     if (P.pre_code != nullptr)
         FHC_FRONT_V(false, true, true);
