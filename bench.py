@@ -486,7 +486,8 @@ def main():
     n_items = 0
     ws = eng._ws.get("pval_ws")
     if ws is not None and os.environ.get("FHC_PVAL_IMPL", "lists")[0] != "t":
-        n_items = int(ws[:16].view(torch.int64).sum().item())  # continued fractions + tail sums of the last K3 launch
+        packed = int(ws[:8].view(torch.int64).item())  # list lengths of the last K3 launch in one word (pvalue_lists.cu):
+        n_items = (packed & 0xffffffff) + ((packed >> 32) & 0xffffffff)  # continued fractions (low) + tail sums (high)
     value = cfg["pairs"] * cfg["passes"] / (ms_per_step * 1e-3)
     host_ms = {k: v * 1e3 for k, v in eng.timings.get(cfg["passes"], {}).items()}
 
