@@ -102,6 +102,7 @@ _SIGNATURES = {
     "fhc_host_lbeta": (c_double, [c_double, c_double]),
     "fhc_host_bdtrc_lists": (c_double, [c_int32, c_int64, c_double]),
     "fhc_host_one_minus_exp": (c_double, [c_double]),
+    "fhc_host_tail_sum": (None, [c_int32, c_int64, c_double, c_int32, c_void_p, c_void_p]),
     "fhc_pvalues": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
                                     c_void_p, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64,

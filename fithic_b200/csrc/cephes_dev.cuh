@@ -500,7 +500,11 @@ FHC_HD double bdtrc_lists_scalar(int count, int N, double prior) {
     const bool tail = rn_mul(prior, (double)N + 1.0) > aa;  // front_prepare's division-free form of x > a / (a + b)
     const double lb = lbeta_cephes(aa, bb);
     CfState s;
-    if (tail) {
+    if (tail && tail_is_short(count)) {  // as pval_finish_kernel sums it in place
+        double q;
+        s.pkm1 = tail_short_sum(aa, (double)N, 1.0 / (double)N, tail_cn((double)N, prior, rn_sub(1.0, prior)), &q);
+        s.qkm1 = q;
+    } else if (tail) {
         tail_fwd_load(s, aa, (double)N, 1.0 / (double)N, tail_cn((double)N, prior, rn_sub(1.0, prior)));
         while (!tail_fwd_step(s)) {
         }

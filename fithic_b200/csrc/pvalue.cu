@@ -481,3 +481,19 @@ extern "C" double fhc_host_bdtrc_lists(int32_t count, int64_t N, double prior) {
     return fhc::bdtrc_lists_scalar(count, (int)N, prior);
 }
 extern "C" double fhc_host_one_minus_exp(double y) { return fhc::one_minus_exp(y); }
+// The lower tail sum of the swapped incbet branch for one contact, as numerator and denominator: in_place != 0 as
+// pval_finish_kernel sums the short ones (tail_short_sum), else as the queue of pval_iterate_kernel does (tail_fwd_*).
+extern "C" void fhc_host_tail_sum(int32_t count, int64_t N, double prior, int32_t in_place, double *num, double *den) {
+    const double dN = (double)N;
+    const double cN = fhc::tail_cn(dN, prior, fhc::rn_sub(1.0, prior));
+    if (in_place) {
+        *num = fhc::tail_short_sum((double)count, dN, 1.0 / dN, cN, den);
+        return;
+    }
+    fhc::CfState s;
+    fhc::tail_fwd_load(s, (double)count, dN, 1.0 / dN, cN);
+    while (!fhc::tail_fwd_step(s)) {
+    }
+    *num = s.pkm1;
+    *den = s.qkm1;
+}

@@ -277,6 +277,10 @@ double fhc_host_lbeta(double a, double b);
  * (classification, division-free continued fraction / tail sum, prefactor with folded divisions), and its 1 - exp(y). */
 double fhc_host_bdtrc_lists(int32_t count, int64_t N, double prior);
 double fhc_host_one_minus_exp(double y);
+/* Numerator and denominator of the lower tail sum K3 uses where the count lies below its expectation (cephes incbet's
+ * swapped branch, scipy.special.bdtrc at fithic/fithic.py:1070,:1101): in_place != 0 the form the finish kernel runs for
+ * sums of up to 32 terms, else the form of the iterate kernel's queue.  Both must give the same bits (tests). */
+void fhc_host_tail_sum(int32_t count, int64_t N, double prior, int32_t in_place, double *num, double *den);
 
 /* ---- K3: per-contact p-value ---------------------------------------------------------------------------------
  * Replaces the per-line loop of fit_Spline (fithic/fithic.py:1017-1123) including scipy.special.bdtrc (:1070,:1101).

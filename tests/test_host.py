@@ -350,6 +350,33 @@ def test_one_minus_exp_is_minus_expm1(lib):
     assert lib.fhc_host_one_minus_exp(-0.0) == 0.0 and not np.signbit(lib.fhc_host_one_minus_exp(-0.0))
 
 
+@pytest.mark.parametrize("N", [33, 34, 100, 5000, 4219169, 300_000_000, (1 << 31) - 1])
+def test_short_tail_sums_in_place_equal_the_queue_bit_for_bit(lib, N):
+    """Tail sums of up to 32 terms are summed inside pval_finish_kernel (tail_short_sum) instead of going through the
+    queue of pval_iterate_kernel (tail_fwd_load / tail_fwd_step); the in-place form drops the renormalisation, which
+    cannot trigger for that few factors: numerator and denominator must come out with the same bits, for every count the
+    in-place form takes (2 ... 33) and priors on both sides of the expectation, tiny and close to 1."""
+    import ctypes
+    rng = np.random.default_rng(N % 7919)
+    num = [ctypes.c_double(), ctypes.c_double()]
+    den = [ctypes.c_double(), ctypes.c_double()]
+    checked = 0
+    for c in range(2, 34):
+        if c - 1 >= N:  # the tail class needs count - 1 < N
+            continue
+        lam = np.exp(rng.uniform(np.log(0.01), np.log(100.0), 300))  # expectation relative to the count
+        priors = np.minimum(c * lam / N, 1.0 - 1e-12)
+        priors = np.concatenate([priors, [1e-300, 1e-15, 0.5, 1.0 - 2.0 ** -53]])
+        for x in priors:
+            for k in (0, 1):
+                lib.fhc_host_tail_sum(c, N, float(x), 1 - k, ctypes.byref(num[k]), ctypes.byref(den[k]))
+            a = np.array([num[0].value, den[0].value]).view(np.uint64)
+            b = np.array([num[1].value, den[1].value]).view(np.uint64)
+            assert np.array_equal(a, b), (c, N, x, num[0].value, num[1].value, den[0].value, den[1].value)
+            checked += 1
+    assert checked > 0
+
+
 @pytest.mark.parametrize("N", [100, 171, 5000, 4219169, 300_000_000, 900_000_000, (1 << 31) - 1])
 def test_list_pipeline_arithmetic_matches_oracle(lib, N):
     """fhc_host_bdtrc_lists = the source pval_front / pval_iterate / pval_finish run for one contact (series log1p +
