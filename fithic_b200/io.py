@@ -83,6 +83,23 @@ def read_fragments(path, chroms, mappThres, keep_mids=False):
     return Fragments(list(chroms), n, mx, mids)
 
 
+def _mquantiles(a, prob, alphap=0.4, betap=0.4):
+    """scipy.stats.mstats.mquantiles(a, prob) for a 1-d array without masked entries (what read_biases logs,
+    fithic/fithic.py:812-816), restated so that the command line does not pay for importing scipy.stats (0.5 s): the
+    plotting positions of Hyndman & Fan's family, (1 - g) x[k-1] + g x[k] on the sorted data with
+    aleph = n p + alphap + p (1 - alphap - betap), k = floor(clip(aleph, 1, n - 1)), g = clip(aleph - k, 0, 1)."""
+    x = np.sort(np.asarray(a, dtype=np.float64))
+    n = len(x)
+    p = np.asarray(prob, dtype=np.float64)
+    if n == 1:  # scipy's special case: the value itself, no interpolation arithmetic
+        return np.resize(x, p.shape)
+    m = alphap + p * (1.0 - alphap - betap)
+    aleph = n * p + m
+    k = np.floor(aleph.clip(1, n - 1)).astype(int)
+    gamma = (aleph - k).clip(0, 1)
+    return (1.0 - gamma) * x[(k - 1).tolist()] + gamma * x[k.tolist()]
+
+
 def read_biases(path, chroms, resolution, biasLowerBound, biasUpperBound):
     """bias file: chr mid bias (fithic/fithic.py:798-837).  bias < tL, NaN or > tU -> -1; FIRST occurrence of a
     (chr, mid) wins.  Returns (Biases, log lines); `chroms` is extended in place."""
@@ -100,8 +117,7 @@ def read_biases(path, chroms, resolution, biasLowerBound, biasUpperBound):
     raw = b[b != 1.0]
     log = []
     if len(raw):
-        from scipy.stats.mstats import mquantiles
-        botQ, med, topQ = mquantiles(raw, prob=[0.05, 0.5, 0.95])
+        botQ, med, topQ = _mquantiles(raw, (0.05, 0.5, 0.95))
         log += ["5th quantile of biases: %s" % botQ, "50th quantile of biases: %s" % med,
                 "95th quantile of biases: %s" % topQ]
     bad = (b < biasLowerBound) | np.isnan(b) | (b > biasUpperBound)

@@ -134,6 +134,22 @@ def test_frag_pairs_quirks(lib):
     assert fp["noOfFrags"] == 8 and fp["possibleInterAllCount"] == 15.0
 
 
+def test_bias_quantiles_are_scipys_mquantiles():
+    """read_biases logs the 5th / 50th / 95th quantile of the bias values with scipy.stats.mstats.mquantiles
+    (fithic/fithic.py:812-816); io._mquantiles restates it (the command line then never imports scipy.stats): same bits."""
+    from scipy.stats.mstats import mquantiles
+    from fithic_b200.io import _mquantiles
+    rng = np.random.default_rng(0)
+    for n in [1, 2, 3, 4, 5, 7, 10, 19, 20, 21, 100, 1001, 50_000]:
+        for rep in range(20):
+            a = np.exp(rng.normal(0, 0.5, n))
+            if rep % 3 == 0:
+                a = np.round(a, 1)  # ties
+            want = np.ma.getdata(mquantiles(a, prob=[0.05, 0.5, 0.95])).astype(np.float64)
+            got = np.asarray(_mquantiles(a, (0.05, 0.5, 0.95)), dtype=np.float64)
+            assert [float(v).hex() for v in want] == [float(v).hex() for v in got], (n, rep)
+
+
 def test_io_round_trip_and_bias_semantics(tmp_path):
     contacts, frags, biases, raw = synth.make_intra(5000, 100000, 5, chroms=["chr21", "chr22"], with_bias=True,
                                                     inter_fraction=0.2)
