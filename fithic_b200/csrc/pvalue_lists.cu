@@ -7,13 +7,15 @@
 // drains almost as soon as it starts (13 of 32 lanes active on average in the iteration loop).  Here the work lists live
 // in HBM instead (16 B per item: 8 % of the DRAM bandwidth was in use), which makes them as long as the input:
 //
-//   pval_front_kernel    every contact: classify, bias gather, prior, ExpCC; results known at once and the count == 1
+//   pval_front2_kernel   every contact: classify, bias gather, prior, ExpCC; results known at once and the count == 1
 //                        closed form (65 % of a sparse map) are finished here; contacts that need a continued fraction or
-//                        a tail sum are appended to two lists (one CTA-wide scan + two global atomics per 2048 contacts)
-//   pval_iterate_kernel  persistent warps pull 64-item chunks from a list; a lane whose item has converged stores
-//                        numerator/denominator and takes the next item at once, so warps stay full until the list ends
-//   pval_finish_kernel   one thread per item, uniform: prefactor in log space (2 log + 1 exp, no division besides P/Q),
-//                        p scattered to its line, outlier flag
+//                        a tail sum are appended to two lists (one shuffle scan + one global atomic per warp and 2048
+//                        contacts; pval_front_kernel is the first version: CTA-wide scan between two barriers)
+//   pval_iterate_kernel  persistent warps pull 128-item chunks from a list; a lane whose item has converged stores
+//                        numerator/denominator and takes the next item at once, so warps stay full until the list ends;
+//                        tail sums of up to 32 terms are left to the finish kernel
+//   pval_finish_kernel   one thread per item, uniform: short tail sums in place, prefactor in log space (2 log + 1 exp, no
+//                        division besides P/Q), p scattered to its line, outlier flag
 #define FHC_PROFILE_STREAM st
 #include <stdlib.h>
 
