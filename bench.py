@@ -36,6 +36,7 @@ ALGO_BYTES = {  # kernel: (unit, algorithmic HBM bytes per unit per launch, full
     "hist_distance_kernel": ("pairs", 12, 1),      # 3 x int32 read (the chromosome ids come as runs)
     "pvalues_kernel": ("pairs", 32, 1),            # tile-phased K3: 16 read + p, ExpCC written
     "pval_front_kernel": ("pairs", 28, 1),         # work-list K3, front: 12 read + p, ExpCC written (+ 16 per listed item)
+    "pval_front2_kernel": ("pairs", 28, 1),        # its second version (the default); the first one runs under FHC_PVAL_FRONT=v1
     "pval_iterate_kernel": ("items", 32, 1),       # item read, numerator/denominator written
     "pval_finish_kernel": ("items", 40, 1),        # item + numerator/denominator read, p written
     "bh_cut_hist_kernel": ("pairs", 8, 1),         # p read
@@ -47,7 +48,7 @@ ALGO_BYTES = {  # kernel: (unit, algorithmic HBM bytes per unit per launch, full
     "bh_scatter_kernel": ("sorted", 20, 1),        # (key, index) read, q written
 }
 PASS_BYTES_PER_PAIR = 56  # K1 12 + K3 28 + K4 16 (read p, write q)
-K3_KERNELS = ("pvalues_kernel", "pval_front_kernel", "pval_iterate_kernel", "pval_finish_kernel")
+K3_KERNELS = ("pvalues_kernel", "pval_front_kernel", "pval_front2_kernel", "pval_iterate_kernel", "pval_finish_kernel")
 
 CONFIGS = {
     # BASELINE.json configs[3]: the configuration the metric is quoted on

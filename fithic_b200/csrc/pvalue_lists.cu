@@ -1372,7 +1372,7 @@ int pvalues_lists_launch(const PvalParams &P, void *workspace, size_t workspace_
     else
         FHC_FRONT_V(true, false, false);
 #undef FHC_FRONT_V
-    FHC_LAUNCH_CHECK("pval_front_kernel");
+    FHC_LAUNCH_CHECK(v1 ? "pval_front_kernel" : "pval_front2_kernel");
     // the list lengths are only known on the device: both follow-up kernels are persistent and read them there
     long long iblocks = (n + kIterThreads * 4 - 1) / (kIterThreads * 4);
     if (iblocks > (long long)kNumSMs * 4) iblocks = (long long)kNumSMs * 4;
